@@ -1,0 +1,938 @@
+// capi.cu -- the C ABI (include/dbindex_gpu.h): handle, device memory, build
+// orchestration and query / fetch entry points.  Every device step is one of the
+// hand-written kernels of this directory; there is no CPU fallback.
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "kernels.cuh"
+#include "radix_sort.cuh"
+
+namespace dbi {
+
+std::atomic<uint64_t> g_kernel_launches{0};
+static thread_local char t_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+// Stream-ordered device buffer.  cudaMallocAsync + a never-shrinking pool keeps
+// repeated builds free of cudaMalloc/cudaFree round trips.
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaStream_t s = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  void alloc(size_t b, cudaStream_t st) {
+    release();
+    if (b == 0) b = 16;
+    DBI_CUDA(cudaMallocAsync(&p, b, st));
+    bytes = b;
+    s = st;
+  }
+  void release() {
+    if (p) {
+      cudaFreeAsync(p, s);
+      p = nullptr;
+      bytes = 0;
+    }
+  }
+  void swap(DevBuf& o) {
+    std::swap(p, o.p);
+    std::swap(bytes, o.bytes);
+    std::swap(s, o.s);
+  }
+  ~DevBuf() { release(); }
+  template <typename T>
+  T* as() const { return (T*)p; }
+};
+
+inline uint64_t dbits(double d) {
+  uint64_t u;
+  std::memcpy(&u, &d, 8);
+  return u;
+}
+inline int bit_length(uint64_t v) { return v ? 64 - __builtin_clzll(v) : 0; }
+
+}  // namespace
+}  // namespace dbi
+
+using namespace dbi;
+
+struct dbi_handle {
+  dbi_params p;
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+
+  // host copy of the proteins (ProteinCache)
+  std::vector<uint8_t> h_raw;
+  std::vector<uint64_t> h_off{0};
+
+  // device-resident input
+  DevBuf d_raw, d_off;
+  uint64_t up_res = 0, up_prot = UINT64_MAX;
+
+  // index
+  bool built = false;
+  DevBuf d_tables, d_err;
+  DevBuf d_res, d_pstart;
+  uint32_t res_end = 0;
+  uint64_t n_emitted = 0, n_unique = 0, n_entries = 0;
+  DevBuf u_mass, u_gpos, u_prot, u_len, u_plo, plist;
+  DevBuf e_mass, e_base, e_pat;  // empty when there are no differential mods (entries == unique peptides)
+  // kept raw records (params.keep_emitted)
+  DevBuf k_mass, k_gpos, k_prot, k_len;
+
+  DigestCfg cfg{};
+  dbi_stats st{};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  const double* entry_mass() const { return e_mass.p ? e_mass.as<double>() : u_mass.as<double>(); }
+  const uint32_t* entry_base() const { return e_base.as<uint32_t>(); }
+  const uint32_t* entry_pat() const { return e_pat.as<uint32_t>(); }
+};
+
+namespace {
+
+int fail_cuda(const CudaError& e) {
+  set_error("CUDA error %d (%s) at %s:%d: %s", (int)e.e, cudaGetErrorString(e.e), e.file, e.line, e.what);
+  cudaGetLastError();  // clear the sticky-free error state
+  return e.e == cudaErrorMemoryAllocation ? DBI_ENOMEM : DBI_ECUDA;
+}
+
+#define DBI_API_BEGIN(h)                      \
+  if (!(h)) {                                 \
+    set_error("null handle");                 \
+    return DBI_EINVAL;                        \
+  }                                           \
+  std::lock_guard<std::mutex> _lk((h)->mu);   \
+  try {                                       \
+    DBI_CUDA(cudaSetDevice((h)->device));
+
+#define DBI_API_END                              \
+  }                                              \
+  catch (const CudaError& e) { return fail_cuda(e); } \
+  catch (const std::bad_alloc&) {                \
+    set_error("host allocation failed");         \
+    return DBI_ENOMEM;                           \
+  }
+
+// CUDA-event stage timer (only when params.profile) + launch accounting.
+struct Stage {
+  dbi_handle* h;
+  int id;
+  uint64_t l0;
+  Stage(dbi_handle* h_, int id_) : h(h_), id(id_) {
+    l0 = g_kernel_launches.load();
+    if (h->p.profile) cudaEventRecord(h->ev0, h->stream);
+  }
+  ~Stage() {
+    h->st.stage_launches[id] += (uint32_t)(g_kernel_launches.load() - l0);
+    if (h->p.profile) {
+      cudaEventRecord(h->ev1, h->stream);
+      cudaEventSynchronize(h->ev1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+      h->st.stage_ms[id] += ms;
+    }
+  }
+};
+
+uint32_t read_err(dbi_handle* h) {
+  uint32_t e = 0;
+  DBI_CUDA(cudaMemcpyAsync(&e, h->d_err.p, 4, cudaMemcpyDeviceToHost, h->stream));
+  DBI_CUDA(cudaStreamSynchronize(h->stream));
+  return e;
+}
+
+uint64_t read_u64(dbi_handle* h, const uint64_t* d) {
+  uint64_t v = 0;
+  DBI_CUDA(cudaMemcpyAsync(&v, d, 8, cudaMemcpyDeviceToHost, h->stream));
+  DBI_CUDA(cudaStreamSynchronize(h->stream));
+  return v;
+}
+
+void free_index(dbi_handle* h) {
+  h->built = false;
+  h->d_res.release();
+  h->d_pstart.release();
+  h->u_mass.release(); h->u_gpos.release(); h->u_prot.release(); h->u_len.release();
+  h->u_plo.release(); h->plist.release();
+  h->e_mass.release(); h->e_base.release(); h->e_pat.release();
+  h->k_mass.release(); h->k_gpos.release(); h->k_prot.release(); h->k_len.release();
+  h->n_emitted = h->n_unique = h->n_entries = 0;
+  const uint64_t np = h->st.n_proteins, nr = h->st.n_residues;
+  std::memset(&h->st, 0, sizeof(h->st));
+  h->st.n_proteins = np;
+  h->st.n_residues = nr;
+}
+
+void upload_tables(dbi_handle* h) {
+  DevTables t;
+  std::memset(&t, 0, sizeof(t));
+  const dbi_params& p = h->p;
+  for (int i = 0; i < 256; ++i) {
+    t.mass[i] = p.residue_mass[i];
+    t.flags[i] = (p.is_enzyme[i] ? kFlagEnzyme : 0) | (p.is_nocut[i] ? kFlagNocut : 0);
+  }
+  const bool mods = p.n_mods > 0 && p.max_mods_per_peptide > 0;
+  if (mods)
+    for (int i = 0; i < p.n_mods; ++i) {  // DiffModification.setDiffModMass: last one wins
+      t.diff[p.mods[i].residue] = p.mods[i].delta;
+      t.flags[p.mods[i].residue] |= kFlagDiffMod;
+    }
+  h->d_tables.alloc(sizeof(DevTables), h->stream);
+  DBI_CUDA(cudaMemcpyAsync(h->d_tables.p, &t, sizeof(t), cudaMemcpyHostToDevice, h->stream));
+  DBI_CUDA(cudaStreamSynchronize(h->stream));  // `t` is on this stack frame
+  double init = 0;  // DBIndexer.java:265-271, same order
+  if (p.add_h2o_proton) init += p.h2o_proton;
+  init += p.cterm;
+  init += p.nterm;
+  h->cfg.init_mass = init;
+  h->cfg.min_mass = p.min_mass;
+  h->cfg.max_mass = p.max_mass;
+  h->cfg.max_mc = p.max_missed;
+  h->cfg.semi = p.semi ? 1 : 0;
+  h->cfg.min_len = p.min_len;
+  h->cfg.max_mods = mods ? p.max_mods_per_peptide : 0;
+}
+
+// H2D of the raw residues + offsets (idempotent).
+void ensure_uploaded(dbi_handle* h) {
+  const uint64_t n_res = h->h_raw.size();
+  const uint64_t n_prot = h->h_off.size() - 1;
+  if (h->up_prot == n_prot && h->up_res == n_res) return;
+  h->d_raw.alloc(n_res, h->stream);
+  h->d_off.alloc((n_prot + 1) * 8, h->stream);
+  if (n_res) DBI_CUDA(cudaMemcpyAsync(h->d_raw.p, h->h_raw.data(), n_res, cudaMemcpyHostToDevice, h->stream));
+  DBI_CUDA(cudaMemcpyAsync(h->d_off.p, h->h_off.data(), (n_prot + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+  h->up_prot = n_prot;
+  h->up_res = n_res;
+}
+
+int check_err_bits(uint32_t e) {
+  if (e & kErrZeroResidue) {
+    set_error("residue byte 0 in the protein buffer");
+    return DBI_EINVAL;
+  }
+  if (e & kErrPepTooLong) {
+    set_error("a peptide window exceeds DBI_MAX_PEP_LEN (%d residues)", DBI_MAX_PEP_LEN);
+    return DBI_ERANGE;
+  }
+  if (e & kErrModPos) {
+    set_error("a modifiable residue lies beyond position %d of a peptide", DBI_MAX_MOD_POS);
+    return DBI_ERANGE;
+  }
+  return DBI_OK;
+}
+
+// K1: padded residue buffer + protein starts.
+void pack_residues(dbi_handle* h) {
+  Stage sg(h, DBI_STAGE_PACK);
+  const uint64_t n_res = h->h_raw.size();
+  const uint32_t n_prot = (uint32_t)(h->h_off.size() - 1);
+  const uint64_t res_end = n_res + n_prot + 1;
+  const uint64_t padded = (res_end + 64 + 15) & ~15ull;
+  h->res_end = (uint32_t)res_end;
+  h->d_res.alloc(padded, h->stream);
+  h->d_pstart.alloc(((uint64_t)n_prot + 1) * 4, h->stream);
+  DBI_CUDA(cudaMemsetAsync((uint8_t*)h->d_res.p + res_end, 0, padded - res_end, h->stream));
+  launch_pack(h->d_raw.as<uint8_t>(), h->d_off.as<uint64_t>(), n_prot, n_res, h->d_res.as<uint8_t>(),
+              h->d_pstart.as<uint32_t>(), h->d_err.as<uint32_t>(), h->stream);
+  h->st.algo_bytes[DBI_STAGE_PACK] += 2 * n_res + (uint64_t)n_prot * 12;
+}
+
+// Sort + K8 + K5/K6 on N emitted records already on the device.
+// lo_mass / hi_mass bound every record mass (they fix the radix key width).
+int index_records(dbi_handle* h, DevBuf& r_mass, DevBuf& r_gpos, DevBuf& r_prot, DevBuf& r_len, uint64_t N,
+                  double lo_mass, double hi_mass) {
+  cudaStream_t s = h->stream;
+  h->n_emitted = N;
+  h->st.n_emitted = N;
+  if (N >= (1ull << 32)) {
+    set_error("more than 2^32 emitted records on one GPU (%llu)", (unsigned long long)N);
+    return DBI_ERANGE;
+  }
+  if (N == 0) {
+    h->u_plo.alloc(8, s);
+    DBI_CUDA(cudaMemsetAsync(h->u_plo.p, 0, 8, s));
+    h->built = true;
+    return DBI_OK;
+  }
+  const uint64_t base_bits = dbits(lo_mass);
+  const int nbits = bit_length(dbits(hi_mass) - base_bits);
+  h->st.sort_bits_base = (uint32_t)nbits + 32;
+
+  DevBuf hash, idx[2], hkey[2], mkey[2], tmp, flags, tile_counts, tile_offs;
+  const uint64_t tiles = (N + kScanTile - 1) / kScanTile;
+  hash.alloc(N * 4, s);
+  idx[0].alloc(N * 4, s); idx[1].alloc(N * 4, s);
+  hkey[0].alloc(N * 4, s); hkey[1].alloc(N * 4, s);
+  mkey[0].alloc(N * 8, s); mkey[1].alloc(N * 8, s);
+  tmp.alloc(radix_sort_tmp_bytes(N), s);
+  flags.alloc(N, s);
+  tile_counts.alloc(tiles * 4, s);
+  tile_offs.alloc((tiles + 1) * 8, s);
+
+  int sorted = 0;
+  uint64_t n_unique = 0;
+  for (uint32_t attempt = 0;; ++attempt) {
+    {
+      Stage sg(h, DBI_STAGE_SORT_BASE);
+      const uint32_t seed = 0x9e3779b9u * attempt;
+      launch_hash_records(h->d_res.as<uint8_t>(), r_gpos.as<uint32_t>(), r_len.as<uint16_t>(), N, seed,
+                          hash.as<uint32_t>(), idx[0].as<uint32_t>(), s);
+      DBI_CUDA(cudaMemcpyAsync(hkey[0].p, hash.p, N * 4, cudaMemcpyDeviceToDevice, s));
+      // less significant key first: sequence hash ...
+      uint32_t* hk[2] = {hkey[0].as<uint32_t>(), hkey[1].as<uint32_t>()};
+      uint32_t* ix[2] = {idx[0].as<uint32_t>(), idx[1].as<uint32_t>()};
+      const int r1 = radix_sort_pairs<uint32_t, uint32_t>(hk, ix, N, 0, 32, tmp.p, s, nullptr);
+      // ... then the exact mass bits (stable), so order = (mass, hash, emission ordinal)
+      launch_gather_mass_key(r_mass.as<uint64_t>(), ix[r1], N, base_bits, mkey[0].as<uint64_t>(), s);
+      uint64_t* mk[2] = {mkey[0].as<uint64_t>(), mkey[1].as<uint64_t>()};
+      uint32_t* ix2[2] = {ix[r1], ix[r1 ^ 1]};
+      const int r2 = radix_sort_pairs<uint64_t, uint32_t>(mk, ix2, N, 0, nbits, tmp.p, s, nullptr);
+      sorted = r2;
+      // normalise: sorted keys in mkey[sorted], sorted idx in ix2[sorted]
+      if (ix2[r2] != idx[0].as<uint32_t>()) idx[0].swap(idx[1]);
+      const int passes = 4 + (nbits + 7) / 8;
+      h->st.algo_bytes[DBI_STAGE_SORT_BASE] += N * (20 /*hash: len + 4*/ + 4 + 8 + 8 + 4) + N * 16ull * 4 +
+                                               N * 24ull * (passes - 4) + N * 20;
+    }
+    {
+      Stage sg(h, DBI_STAGE_DEDUP);
+      launch_dedup_flags(h->d_res.as<uint8_t>(), mkey[sorted].as<uint64_t>(), idx[0].as<uint32_t>(),
+                         hash.as<uint32_t>(), r_gpos.as<uint32_t>(), r_len.as<uint16_t>(), N, flags.as<uint8_t>(),
+                         tile_counts.as<uint32_t>(), h->d_err.as<uint32_t>(), s);
+      launch_scan_u32_to_u64(tile_counts.as<uint32_t>(), tiles, tile_offs.as<uint64_t>(), s);
+      n_unique = read_u64(h, tile_offs.as<uint64_t>() + tiles);
+    }
+    const uint32_t e = read_err(h);
+    if (e & kErrHashCollision) {
+      // two different sequences with equal mass bits and equal hash: re-sort with another seed
+      h->st.n_hash_retries++;
+      const uint32_t cleared = e & ~kErrHashCollision;
+      DBI_CUDA(cudaMemcpyAsync(h->d_err.p, &cleared, 4, cudaMemcpyHostToDevice, s));
+      DBI_CUDA(cudaStreamSynchronize(s));
+      if (attempt >= 8) {
+        set_error("sequence-hash collisions persist after %u re-seeds", attempt);
+        return DBI_ERANGE;
+      }
+      continue;
+    }
+    break;
+  }
+  {
+    Stage sg(h, DBI_STAGE_DEDUP);
+    h->n_unique = n_unique;
+    h->st.n_unique = n_unique;
+    h->u_mass.alloc(n_unique * 8, s);
+    h->u_gpos.alloc(n_unique * 4, s);
+    h->u_prot.alloc(n_unique * 4, s);
+    h->u_len.alloc(n_unique * 2, s);
+    h->u_plo.alloc((n_unique + 1) * 8, s);
+    h->plist.alloc(N * 4, s);
+    launch_dedup_emit(mkey[sorted].as<uint64_t>(), idx[0].as<uint32_t>(), flags.as<uint8_t>(),
+                      tile_offs.as<uint64_t>(), r_gpos.as<uint32_t>(), r_prot.as<uint32_t>(), r_len.as<uint16_t>(), N,
+                      base_bits, n_unique, h->u_mass.as<double>(), h->u_gpos.as<uint32_t>(),
+                      h->u_prot.as<uint32_t>(), h->u_len.as<uint16_t>(), h->u_plo.as<uint64_t>(),
+                      h->plist.as<uint32_t>(), s);
+    h->st.algo_bytes[DBI_STAGE_DEDUP] += N * (8 + 4 + 1) + N * (1 + 4 + 4 + 4) + n_unique * (8 + 4 + 4 + 2 + 8 + 10);
+  }
+  // free the sort scratch before the (much larger) variant stage
+  hash.release(); idx[0].release(); idx[1].release(); hkey[0].release(); hkey[1].release();
+  mkey[0].release(); mkey[1].release(); tmp.release(); flags.release(); tile_counts.release(); tile_offs.release();
+
+  if (h->cfg.max_mods == 0) {
+    h->n_entries = n_unique;
+    h->st.n_entries = n_unique;
+    h->built = true;
+    return DBI_OK;
+  }
+
+  // ---- K5/K6: differential-mod variants of the unique peptides ----
+  const uint64_t utiles = (n_unique + kScanTile - 1) / kScanTile;
+  DevBuf counts, ucounts, uoffs;
+  counts.alloc(n_unique * 4, s);
+  ucounts.alloc(utiles * 4, s);
+  uoffs.alloc((utiles + 1) * 8, s);
+  uint64_t V = 0;
+  {
+    Stage sg(h, DBI_STAGE_MOD_COUNT);
+    launch_mod_count(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_mass.as<double>(),
+                     h->u_gpos.as<uint32_t>(), h->u_len.as<uint16_t>(), n_unique, counts.as<uint32_t>(),
+                     ucounts.as<uint32_t>(), h->d_err.as<uint32_t>(), s);
+    launch_scan_u32_to_u64(ucounts.as<uint32_t>(), utiles, uoffs.as<uint64_t>(), s);
+    V = read_u64(h, uoffs.as<uint64_t>() + utiles);
+    h->st.algo_bytes[DBI_STAGE_MOD_COUNT] += n_unique * (8 + 4 + 2 + 4 + 20);
+  }
+  if (int rc = check_err_bits(read_err(h))) return rc;
+  DevBuf vkey[2], vpay[2], vtmp;
+  vkey[0].alloc(V * 8, s); vkey[1].alloc(V * 8, s);
+  vpay[0].alloc(V * 8, s); vpay[1].alloc(V * 8, s);
+  vtmp.alloc(radix_sort_tmp_bytes(V), s);
+  {
+    Stage sg(h, DBI_STAGE_MOD_EMIT);
+    launch_mod_emit(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_mass.as<double>(),
+                    h->u_gpos.as<uint32_t>(), h->u_len.as<uint16_t>(), n_unique, counts.as<uint32_t>(),
+                    uoffs.as<uint64_t>(), base_bits, vkey[0].as<uint64_t>(), vpay[0].as<uint64_t>(), s);
+    h->st.algo_bytes[DBI_STAGE_MOD_EMIT] += n_unique * (8 + 4 + 2 + 4 + 20) + V * 16;
+  }
+  int vs = 0;
+  {
+    Stage sg(h, DBI_STAGE_SORT_VAR);
+    uint64_t* vk[2] = {vkey[0].as<uint64_t>(), vkey[1].as<uint64_t>()};
+    uint64_t* vp[2] = {vpay[0].as<uint64_t>(), vpay[1].as<uint64_t>()};
+    vs = radix_sort_pairs<uint64_t, uint64_t>(vk, vp, V, 0, nbits, vtmp.p, s, nullptr);
+    h->st.sort_bits_var = (uint32_t)nbits;
+    h->st.algo_bytes[DBI_STAGE_SORT_VAR] += V * 8 + V * 32ull * ((nbits + 7) / 8);
+  }
+  {
+    Stage sg(h, DBI_STAGE_GATHER_VAR);
+    h->e_mass.alloc(V * 8, s);
+    h->e_base.alloc(V * 4, s);
+    h->e_pat.alloc(V * 4, s);
+    launch_split_entries(vkey[vs].as<uint64_t>(), vpay[vs].as<uint64_t>(), V, base_bits, h->e_mass.as<double>(),
+                         h->e_base.as<uint32_t>(), h->e_pat.as<uint32_t>(), s);
+    h->st.algo_bytes[DBI_STAGE_GATHER_VAR] += V * 32;
+  }
+  h->n_entries = V;
+  h->st.n_entries = V;
+  h->built = true;
+  return DBI_OK;
+}
+
+void finish_stats(dbi_handle* h) {
+  h->st.device_bytes = h->d_res.bytes + h->d_pstart.bytes + h->u_mass.bytes + h->u_gpos.bytes + h->u_prot.bytes +
+                       h->u_len.bytes + h->u_plo.bytes + h->plist.bytes + h->e_mass.bytes + h->e_base.bytes +
+                       h->e_pat.bytes;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dbi_create(const dbi_params* params, dbi_handle** out) {
+  if (!params || !out) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  *out = nullptr;
+  if (params->abi_version != DBI_ABI_VERSION) {
+    set_error("dbi_params.abi_version %u != %u", params->abi_version, DBI_ABI_VERSION);
+    return DBI_EINVAL;
+  }
+  const dbi_params& p = *params;
+  // Constants.MAX_PRECURSOR_MASS = 8000 (Constants.java:20): masses beyond it have no bucket
+  // in the reference (DBIndexStoreSQLiteMult.java:282-287)
+  if (!(p.min_mass >= 0) || !(p.max_mass >= p.min_mass) || !(p.max_mass <= 8000.0)) {
+    set_error("mass range [%g, %g] must satisfy 0 <= min <= max <= 8000", p.min_mass, p.max_mass);
+    return DBI_EINVAL;
+  }
+  if (p.min_len < 1 || p.max_missed < 0 || p.mass_group_factor < 1 || p.n_mods < 0 || p.n_mods > DBI_MAX_MODS ||
+      p.max_mods_per_peptide < 0 || p.max_mods_per_peptide > DBI_MAX_MODS_PER_PEP) {
+    set_error("parameter out of range (min_len %d, max_missed %d, factor %d, n_mods %d, max_mods_per_peptide %d)",
+              p.min_len, p.max_missed, p.mass_group_factor, p.n_mods, p.max_mods_per_peptide);
+    return DBI_EINVAL;
+  }
+  for (int i = 0; i < 256; ++i)
+    if (!(p.residue_mass[i] >= 0)) {
+      set_error("residue_mass[%d] is negative or NaN", i);
+      return DBI_EINVAL;
+    }
+  dbi_handle* h = nullptr;
+  try {
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev <= 0 || p.device < 0 || p.device >= ndev) {
+      set_error("no usable CUDA device (count %d, requested %d): %s; this library has no CPU fallback", ndev,
+                p.device, cudaGetErrorString(ce));
+      cudaGetLastError();
+      return DBI_ECUDA;
+    }
+    h = new dbi_handle();
+    h->p = p;
+    h->device = p.device;
+    DBI_CUDA(cudaSetDevice(h->device));
+    DBI_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    DBI_CUDA(cudaEventCreate(&h->ev0));
+    DBI_CUDA(cudaEventCreate(&h->ev1));
+    cudaMemPool_t pool;
+    DBI_CUDA(cudaDeviceGetDefaultMemPool(&pool, h->device));
+    uint64_t thr = UINT64_MAX;
+    DBI_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    h->d_err.alloc(4, h->stream);
+    DBI_CUDA(cudaMemsetAsync(h->d_err.p, 0, 4, h->stream));
+    upload_tables(h);
+    *out = h;
+    return DBI_OK;
+  } catch (const CudaError& e) {
+    delete h;
+    return fail_cuda(e);
+  } catch (const std::bad_alloc&) {
+    delete h;
+    set_error("host allocation failed");
+    return DBI_ENOMEM;
+  }
+}
+
+int dbi_set_stream(dbi_handle* h, void* cuda_stream) {
+  DBI_API_BEGIN(h)
+  DBI_CUDA(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_add_proteins(dbi_handle* h, const uint8_t* residues, const uint64_t* offsets, uint32_t n) {
+  DBI_API_BEGIN(h)
+  if (h->built) {
+    set_error("index already built");  // "Already intialized", DBIndexStoreSQLiteMult.java:97-99
+    return DBI_EALREADY;
+  }
+  if (n == 0) return DBI_OK;
+  if (!residues || !offsets) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  for (uint32_t i = 0; i < n; ++i)
+    if (offsets[i + 1] < offsets[i]) {
+      set_error("offsets must be non-decreasing (protein %u)", i);
+      return DBI_EINVAL;
+    }
+  const uint64_t add = offsets[n] - offsets[0];
+  const uint64_t total_res = h->h_raw.size() + add;
+  const uint64_t total_prot = h->h_off.size() - 1 + n;
+  if (total_res + total_prot + 1 + 4096 >= (1ull << 32) || total_prot >= (1ull << 31)) {
+    set_error("more than 2^32 residues on one GPU: shard the FASTA across handles");
+    return DBI_ERANGE;
+  }
+  const uint64_t base = h->h_raw.size();
+  h->h_raw.insert(h->h_raw.end(), residues + offsets[0], residues + offsets[n]);
+  for (uint32_t i = 1; i <= n; ++i) h->h_off.push_back(base + (offsets[i] - offsets[0]));
+  h->st.n_proteins = total_prot;
+  h->st.n_residues = total_res;
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_upload(dbi_handle* h) {
+  DBI_API_BEGIN(h)
+  ensure_uploaded(h);
+  DBI_CUDA(cudaStreamSynchronize(h->stream));
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_reset_index(dbi_handle* h) {
+  DBI_API_BEGIN(h)
+  free_index(h);
+  DBI_CUDA(cudaStreamSynchronize(h->stream));
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_build(dbi_handle* h) {
+  DBI_API_BEGIN(h)
+  if (h->built) {
+    set_error("index already built");
+    return DBI_EALREADY;
+  }
+  cudaStream_t s = h->stream;
+  ensure_uploaded(h);
+  const uint32_t zero = 0;
+  DBI_CUDA(cudaMemcpyAsync(h->d_err.p, &zero, 4, cudaMemcpyHostToDevice, s));
+  pack_residues(h);
+
+  const uint32_t n_prot = (uint32_t)(h->h_off.size() - 1);
+  const uint64_t tiles = ((uint64_t)h->res_end + kDigestTile - 1) / kDigestTile;
+  DevBuf tile_counts, tile_offs;
+  tile_counts.alloc(tiles * 4, s);
+  tile_offs.alloc((tiles + 1) * 8, s);
+  uint64_t N = 0;
+  {
+    Stage sg(h, DBI_STAGE_DIGEST_COUNT);
+    launch_digest_count(h->d_res.as<uint8_t>(), h->res_end, h->d_tables.as<DevTables>(), h->cfg,
+                        tile_counts.as<uint32_t>(), h->d_err.as<uint32_t>(), s);
+    launch_scan_u32_to_u64(tile_counts.as<uint32_t>(), tiles, tile_offs.as<uint64_t>(), s);
+    N = read_u64(h, tile_offs.as<uint64_t>() + tiles);
+    h->st.algo_bytes[DBI_STAGE_DIGEST_COUNT] += h->res_end + tiles * 16;
+  }
+  if (int rc = check_err_bits(read_err(h))) {
+    free_index(h);
+    return rc;
+  }
+  DevBuf r_mass, r_gpos, r_prot, r_len;
+  r_mass.alloc(N * 8, s);
+  r_gpos.alloc(N * 4, s);
+  r_prot.alloc(N * 4, s);
+  r_len.alloc(N * 2, s);
+  {
+    Stage sg(h, DBI_STAGE_DIGEST_EMIT);
+    launch_digest_emit(h->d_res.as<uint8_t>(), h->res_end, h->d_tables.as<DevTables>(), h->cfg,
+                       tile_offs.as<uint64_t>(), h->d_pstart.as<uint32_t>(), n_prot, r_mass.as<uint64_t>(),
+                       r_gpos.as<uint32_t>(), r_prot.as<uint32_t>(), r_len.as<uint16_t>(), h->d_err.as<uint32_t>(), s);
+    h->st.algo_bytes[DBI_STAGE_DIGEST_EMIT] += h->res_end + N * 18;
+  }
+  tile_counts.release();
+  tile_offs.release();
+  int rc = index_records(h, r_mass, r_gpos, r_prot, r_len, N, h->p.min_mass, h->p.max_mass);
+  if (rc == DBI_OK)
+    if (int rc2 = check_err_bits(read_err(h))) rc = rc2;
+  if (rc != DBI_OK) {
+    free_index(h);
+    return rc;
+  }
+  if (h->p.keep_emitted) {
+    h->k_mass.swap(r_mass); h->k_gpos.swap(r_gpos); h->k_prot.swap(r_prot); h->k_len.swap(r_len);
+  }
+  DBI_CUDA(cudaStreamSynchronize(s));
+  finish_stats(h);
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_build_from_records(dbi_handle* h, const double* mass, const uint32_t* prot, const uint32_t* off,
+                           const uint16_t* len, uint64_t n) {
+  DBI_API_BEGIN(h)
+  if (h->built) {
+    set_error("index already built");
+    return DBI_EALREADY;
+  }
+  if (n && (!mass || !prot || !off || !len)) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  cudaStream_t s = h->stream;
+  const uint32_t n_prot = (uint32_t)(h->h_off.size() - 1);
+  double lo = 0, hi = 0;
+  std::vector<uint32_t> gpos(n);
+  for (uint64_t i = 0; i < n; ++i) {
+    if (prot[i] >= n_prot || (uint64_t)off[i] + len[i] > h->h_off[prot[i] + 1] - h->h_off[prot[i]] || !(mass[i] >= 0)) {
+      set_error("record %llu does not lie inside protein %u (or negative mass)", (unsigned long long)i, prot[i]);
+      return DBI_EINVAL;
+    }
+    gpos[i] = (uint32_t)(h->h_off[prot[i]] + prot[i] + 1 + off[i]);
+    lo = i ? std::min(lo, mass[i]) : mass[i];
+    hi = i ? std::max(hi, mass[i]) : mass[i];
+  }
+  ensure_uploaded(h);
+  const uint32_t zero = 0;
+  DBI_CUDA(cudaMemcpyAsync(h->d_err.p, &zero, 4, cudaMemcpyHostToDevice, s));
+  pack_residues(h);
+  DevBuf r_mass, r_gpos, r_prot, r_len;
+  r_mass.alloc(n * 8, s);
+  r_gpos.alloc(n * 4, s);
+  r_prot.alloc(n * 4, s);
+  r_len.alloc(n * 2, s);
+  if (n) {
+    DBI_CUDA(cudaMemcpyAsync(r_mass.p, mass, n * 8, cudaMemcpyHostToDevice, s));
+    DBI_CUDA(cudaMemcpyAsync(r_gpos.p, gpos.data(), n * 4, cudaMemcpyHostToDevice, s));
+    DBI_CUDA(cudaMemcpyAsync(r_prot.p, prot, n * 4, cudaMemcpyHostToDevice, s));
+    DBI_CUDA(cudaMemcpyAsync(r_len.p, len, n * 2, cudaMemcpyHostToDevice, s));
+    DBI_CUDA(cudaStreamSynchronize(s));
+  }
+  // mod variants may move masses outside [lo, hi]: widen by the gate
+  if (h->cfg.max_mods > 0) {
+    lo = std::min(lo, h->p.min_mass);
+    hi = std::max(hi, h->p.max_mass);
+  }
+  int rc = index_records(h, r_mass, r_gpos, r_prot, r_len, n, lo, hi);
+  if (rc == DBI_OK)
+    if (int rc2 = check_err_bits(read_err(h))) rc = rc2;
+  if (rc != DBI_OK) {
+    free_index(h);
+    return rc;
+  }
+  if (h->p.keep_emitted) {
+    h->k_mass.swap(r_mass); h->k_gpos.swap(r_gpos); h->k_prot.swap(r_prot); h->k_len.swap(r_len);
+  }
+  DBI_CUDA(cudaStreamSynchronize(s));
+  finish_stats(h);
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_stats_get(dbi_handle* h, dbi_stats* out) {
+  if (!h || !out) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  std::lock_guard<std::mutex> lk(h->mu);
+  *out = h->st;
+  return DBI_OK;
+}
+
+int dbi_query_device(dbi_handle* h, const double* d_lo, const double* d_hi, uint64_t nq, uint64_t* d_hit_begin,
+                     uint64_t* d_hit_count) {
+  DBI_API_BEGIN(h)
+  if (!h->built) {
+    set_error("Indexer is not initialized");  // DBIndexStoreSQLiteMult.java:316-318
+    return DBI_ENOTINIT;
+  }
+  Stage sg(h, DBI_STAGE_QUERY);
+  launch_query(h->entry_mass(), h->n_entries, d_lo, d_hi, nq, d_hit_begin, d_hit_count, h->stream);
+  h->st.algo_bytes[DBI_STAGE_QUERY] += nq * (32 + 2ull * 32 * (uint64_t)bit_length(h->n_entries));
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_query(dbi_handle* h, const double* lo, const double* hi, uint64_t nq, uint64_t* hit_begin,
+              uint64_t* hit_count) {
+  DBI_API_BEGIN(h)
+  if (!h->built) {
+    set_error("Indexer is not initialized");
+    return DBI_ENOTINIT;
+  }
+  if (nq == 0) return DBI_OK;
+  if (!lo || !hi || !hit_begin || !hit_count) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  cudaStream_t s = h->stream;
+  DevBuf io;  // lo | hi | begin | count
+  io.alloc(nq * 32, s);
+  double* d_lo = io.as<double>();
+  double* d_hi = d_lo + nq;
+  uint64_t* d_b = (uint64_t*)(d_hi + nq);
+  uint64_t* d_c = d_b + nq;
+  DBI_CUDA(cudaMemcpyAsync(d_lo, lo, nq * 8, cudaMemcpyHostToDevice, s));
+  DBI_CUDA(cudaMemcpyAsync(d_hi, hi, nq * 8, cudaMemcpyHostToDevice, s));
+  {
+    Stage sg(h, DBI_STAGE_QUERY);
+    launch_query(h->entry_mass(), h->n_entries, d_lo, d_hi, nq, d_b, d_c, s);
+    h->st.algo_bytes[DBI_STAGE_QUERY] += nq * (32 + 2ull * 32 * (uint64_t)bit_length(h->n_entries));
+  }
+  DBI_CUDA(cudaMemcpyAsync(hit_begin, d_b, nq * 8, cudaMemcpyDeviceToHost, s));
+  DBI_CUDA(cudaMemcpyAsync(hit_count, d_c, nq * 8, cudaMemcpyDeviceToHost, s));
+  DBI_CUDA(cudaStreamSynchronize(s));
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_fetch(dbi_handle* h, uint64_t begin, uint64_t count, double* mass, uint32_t* first_prot,
+              uint32_t* first_off, uint16_t* len, uint32_t* modpat, uint64_t* prot_list_off, uint32_t* prot_ids,
+              uint64_t prot_ids_capacity, uint64_t* n_prot_ids) {
+  DBI_API_BEGIN(h)
+  if (!h->built) {
+    set_error("Indexer is not initialized");
+    return DBI_ENOTINIT;
+  }
+  if (begin > h->n_entries || count > h->n_entries - begin) {
+    set_error("entry range [%llu, +%llu) outside the index (%llu entries)", (unsigned long long)begin,
+              (unsigned long long)count, (unsigned long long)h->n_entries);
+    return DBI_EINVAL;
+  }
+  if (n_prot_ids) *n_prot_ids = 0;
+  if (count == 0) {
+    if (prot_list_off) prot_list_off[0] = 0;
+    return DBI_OK;
+  }
+  cudaStream_t s = h->stream;
+  const uint64_t tiles = (count + kScanTile - 1) / kScanTile;
+  DevBuf sizes, tcnt, toff;
+  sizes.alloc(count * 4, s);
+  tcnt.alloc(tiles * 4, s);
+  toff.alloc((tiles + 1) * 8, s);
+  uint64_t total_ids = 0;
+  {
+    Stage sg(h, DBI_STAGE_FETCH);
+    launch_fetch_sizes(h->entry_base(), h->u_plo.as<uint64_t>(), begin, count, sizes.as<uint32_t>(),
+                       tcnt.as<uint32_t>(), s);
+    launch_scan_u32_to_u64(tcnt.as<uint32_t>(), tiles, toff.as<uint64_t>(), s);
+    total_ids = read_u64(h, toff.as<uint64_t>() + tiles);
+  }
+  if (n_prot_ids) *n_prot_ids = total_ids;
+  const bool want_ids = prot_ids != nullptr;
+  if (want_ids && prot_ids_capacity < total_ids) {
+    set_error("prot_ids capacity %llu < %llu", (unsigned long long)prot_ids_capacity, (unsigned long long)total_ids);
+    return DBI_ERANGE;
+  }
+  DevBuf o_mass, o_prot, o_off, o_len, o_pat, o_lo, o_ids;
+  if (mass) o_mass.alloc(count * 8, s);
+  if (first_prot) o_prot.alloc(count * 4, s);
+  if (first_off) o_off.alloc(count * 4, s);
+  if (len) o_len.alloc(count * 2, s);
+  if (modpat) o_pat.alloc(count * 4, s);
+  if (prot_list_off) o_lo.alloc((count + 1) * 8, s);
+  if (want_ids) o_ids.alloc(total_ids * 4, s);
+  {
+    Stage sg(h, DBI_STAGE_FETCH);
+    launch_fetch_gather(h->entry_mass(), h->entry_base(), h->entry_pat(), h->u_gpos.as<uint32_t>(),
+                        h->u_prot.as<uint32_t>(), h->u_len.as<uint16_t>(), h->u_plo.as<uint64_t>(),
+                        h->plist.as<uint32_t>(), h->d_pstart.as<uint32_t>(), begin, count, sizes.as<uint32_t>(),
+                        toff.as<uint64_t>(), o_mass.as<double>(), o_prot.as<uint32_t>(), o_off.as<uint32_t>(),
+                        o_len.as<uint16_t>(), o_pat.as<uint32_t>(), o_lo.as<uint64_t>(), o_ids.as<uint32_t>(), s);
+    h->st.algo_bytes[DBI_STAGE_FETCH] += count * (20 + 8 + 26) + total_ids * 8;
+  }
+  if (mass) DBI_CUDA(cudaMemcpyAsync(mass, o_mass.p, count * 8, cudaMemcpyDeviceToHost, s));
+  if (first_prot) DBI_CUDA(cudaMemcpyAsync(first_prot, o_prot.p, count * 4, cudaMemcpyDeviceToHost, s));
+  if (first_off) DBI_CUDA(cudaMemcpyAsync(first_off, o_off.p, count * 4, cudaMemcpyDeviceToHost, s));
+  if (len) DBI_CUDA(cudaMemcpyAsync(len, o_len.p, count * 2, cudaMemcpyDeviceToHost, s));
+  if (modpat) DBI_CUDA(cudaMemcpyAsync(modpat, o_pat.p, count * 4, cudaMemcpyDeviceToHost, s));
+  if (prot_list_off) DBI_CUDA(cudaMemcpyAsync(prot_list_off, o_lo.p, (count + 1) * 8, cudaMemcpyDeviceToHost, s));
+  if (want_ids && total_ids) DBI_CUDA(cudaMemcpyAsync(prot_ids, o_ids.p, total_ids * 4, cudaMemcpyDeviceToHost, s));
+  DBI_CUDA(cudaStreamSynchronize(s));
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_get_protein(dbi_handle* h, uint32_t id, const uint8_t** residues, uint64_t* len) {
+  if (!h || !residues || !len) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  std::lock_guard<std::mutex> lk(h->mu);
+  if ((uint64_t)id + 1 >= h->h_off.size()) {
+    set_error("protein id %u out of range", id);
+    return DBI_EINVAL;
+  }
+  *residues = h->h_raw.data() + h->h_off[id];
+  *len = h->h_off[id + 1] - h->h_off[id];
+  return DBI_OK;
+}
+
+int dbi_calculate_mass(dbi_handle* h, const uint8_t* seq, uint64_t len, double* mass) {
+  if (!h || (!seq && len) || !mass) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  const dbi_params& p = h->p;
+  double m = 0;  // util/IndexUtil.java:198-207
+  if (p.add_h2o_proton) m += p.h2o_proton;
+  m += p.cterm;
+  m += p.nterm;
+  for (uint64_t i = 0; i < len; ++i) m += p.residue_mass[seq[i]];
+  *mass = m;
+  return DBI_OK;
+}
+
+int dbi_entry_keys(dbi_handle* h, int32_t* keys, uint64_t capacity, uint64_t* n_keys) {
+  DBI_API_BEGIN(h)
+  if (!h->built) {
+    set_error("Indexer is not initialized");
+    return DBI_ENOTINIT;
+  }
+  if (!n_keys) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  *n_keys = 0;
+  const uint64_t n = h->n_entries;
+  if (n == 0) return DBI_OK;
+  cudaStream_t s = h->stream;
+  const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
+  DevBuf flags, tcnt, toff, out;
+  flags.alloc(n, s);
+  tcnt.alloc(tiles * 4, s);
+  toff.alloc((tiles + 1) * 8, s);
+  Stage sg(h, DBI_STAGE_OTHER);
+  launch_key_flags(h->entry_mass(), n, (double)h->p.mass_group_factor, flags.as<uint8_t>(), tcnt.as<uint32_t>(), s);
+  launch_scan_u32_to_u64(tcnt.as<uint32_t>(), tiles, toff.as<uint64_t>(), s);
+  const uint64_t nk = read_u64(h, toff.as<uint64_t>() + tiles);
+  *n_keys = nk;
+  if (!keys) return DBI_OK;
+  if (capacity < nk) {
+    set_error("keys capacity %llu < %llu", (unsigned long long)capacity, (unsigned long long)nk);
+    return DBI_ERANGE;
+  }
+  out.alloc(nk * 4, s);
+  launch_key_emit(h->entry_mass(), n, (double)h->p.mass_group_factor, flags.as<uint8_t>(), toff.as<uint64_t>(),
+                  out.as<int32_t>(), s);
+  DBI_CUDA(cudaMemcpyAsync(keys, out.p, nk * 4, cudaMemcpyDeviceToHost, s));
+  DBI_CUDA(cudaStreamSynchronize(s));
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_debug_emitted(dbi_handle* h, uint64_t capacity, double* mass, uint32_t* prot, uint32_t* off, uint16_t* len,
+                      uint64_t* n) {
+  DBI_API_BEGIN(h)
+  if (!h->built || !h->p.keep_emitted) {
+    set_error("emitted records were not kept (params.keep_emitted) or the index is not built");
+    return DBI_ENOTINIT;
+  }
+  if (n) *n = h->n_emitted;
+  if (capacity < h->n_emitted) {
+    if (!mass && !prot && !off && !len) return DBI_OK;  // sizing call
+    set_error("capacity %llu < %llu", (unsigned long long)capacity, (unsigned long long)h->n_emitted);
+    return DBI_ERANGE;
+  }
+  const uint64_t N = h->n_emitted;
+  cudaStream_t s = h->stream;
+  std::vector<uint32_t> gpos(N), pr(N);
+  if (N) {
+    DBI_CUDA(cudaMemcpyAsync(gpos.data(), h->k_gpos.p, N * 4, cudaMemcpyDeviceToHost, s));
+    DBI_CUDA(cudaMemcpyAsync(pr.data(), h->k_prot.p, N * 4, cudaMemcpyDeviceToHost, s));
+    if (mass) DBI_CUDA(cudaMemcpyAsync(mass, h->k_mass.p, N * 8, cudaMemcpyDeviceToHost, s));
+    if (len) DBI_CUDA(cudaMemcpyAsync(len, h->k_len.p, N * 2, cudaMemcpyDeviceToHost, s));
+    DBI_CUDA(cudaStreamSynchronize(s));
+  }
+  for (uint64_t i = 0; i < N; ++i) {
+    if (prot) prot[i] = pr[i];
+    if (off) off[i] = gpos[i] - (uint32_t)(h->h_off[pr[i]] + pr[i] + 1);
+  }
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_debug_radix_sort(dbi_handle* h, uint64_t* keys, uint64_t* vals, uint64_t n, int begin_bit, int end_bit) {
+  DBI_API_BEGIN(h)
+  if (n == 0) return DBI_OK;
+  if (!keys || !vals || begin_bit < 0 || end_bit > 64 || end_bit < begin_bit) {
+    set_error("bad argument");
+    return DBI_EINVAL;
+  }
+  cudaStream_t s = h->stream;
+  DevBuf k[2], v[2], tmp;
+  for (int i = 0; i < 2; ++i) {
+    k[i].alloc(n * 8, s);
+    v[i].alloc(n * 8, s);
+  }
+  tmp.alloc(radix_sort_tmp_bytes(n), s);
+  DBI_CUDA(cudaMemcpyAsync(k[0].p, keys, n * 8, cudaMemcpyHostToDevice, s));
+  DBI_CUDA(cudaMemcpyAsync(v[0].p, vals, n * 8, cudaMemcpyHostToDevice, s));
+  uint64_t* kk[2] = {k[0].as<uint64_t>(), k[1].as<uint64_t>()};
+  uint64_t* vv[2] = {v[0].as<uint64_t>(), v[1].as<uint64_t>()};
+  const int r = radix_sort_pairs<uint64_t, uint64_t>(kk, vv, n, begin_bit, end_bit, tmp.p, s, nullptr);
+  DBI_CUDA(cudaMemcpyAsync(keys, kk[r], n * 8, cudaMemcpyDeviceToHost, s));
+  DBI_CUDA(cudaMemcpyAsync(vals, vv[r], n * 8, cudaMemcpyDeviceToHost, s));
+  DBI_CUDA(cudaStreamSynchronize(s));
+  return DBI_OK;
+  DBI_API_END
+}
+
+void dbi_destroy(dbi_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  free_index(h);
+  h->d_raw.release();
+  h->d_off.release();
+  h->d_tables.release();
+  h->d_err.release();
+  cudaStreamSynchronize(h->stream);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+const char* dbi_last_error(void) { return t_err; }
+
+uint64_t dbi_kernel_launches(void) { return g_kernel_launches.load(); }
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+// kernels.cuh -- host-callable launchers of the hand-written sm_100a kernels.
+#pragma once
+#include "common.cuh"
+
+namespace dbi {
+
+// Device-resident lookup tables, one copy per handle (2 KB + 256 B + 2 KB).
+struct DevTables {
+  double mass[256];   // AssignMass.getMass(c), static mods included
+  double diff[256];   // DiffModification.getDiffModMass(c)
+  uint8_t flags[256]; // kFlagEnzyme | kFlagNocut | kFlagDiffMod
+};
+
+// Scalar digestion parameters, passed by value.
+struct DigestCfg {
+  double init_mass;  // ((0 + H2O_PROTON) + cTerm) + nTerm, DBIndexer.java:265-271
+  double min_mass;
+  double max_mass;
+  int32_t max_mc;
+  int32_t semi;
+  int32_t min_len;
+  int32_t max_mods;  // 0 = no differential mods
+};
+
+constexpr int kDigestTile = 2048;   // start positions per CTA
+constexpr int kScanTile = 4096;     // elements per tile of the generic scans
+
+// K1: residues + offsets -> padded buffer res[] (0 separator before, between and
+// after proteins) and pstart[p] = position of protein p's first residue.
+void launch_pack(const uint8_t* d_raw, const uint64_t* d_off, uint32_t n_prot, uint64_t n_res, uint8_t* d_res,
+                 uint32_t* d_pstart, uint32_t* d_err, cudaStream_t s);
+
+// K2: per-tile count of the records cutSeq emits.
+void launch_digest_count(const uint8_t* d_res, uint32_t res_end, const DevTables* d_tb, const DigestCfg& cfg,
+                         uint32_t* d_tile_counts, uint32_t* d_err, cudaStream_t s);
+
+// K3: exclusive scan of u32 tile counts into u64 offsets; offs[n] = total.
+void launch_scan_u32_to_u64(const uint32_t* d_in, uint64_t n, uint64_t* d_offs, cudaStream_t s);
+
+// K4: emit (mass bits, gpos, prot, len) in (protein, start, end) order.
+void launch_digest_emit(const uint8_t* d_res, uint32_t res_end, const DevTables* d_tb, const DigestCfg& cfg,
+                        const uint64_t* d_tile_offs, const uint32_t* d_pstart, uint32_t n_prot, uint64_t* o_mass,
+                        uint32_t* o_gpos, uint32_t* o_prot, uint16_t* o_len, uint32_t* d_err, cudaStream_t s);
+
+// ---- sort helpers / K8 dedup -------------------------------------------------
+// hash[i] = seeded 32-bit hash of the residues of record i; idx[i] = i.
+void launch_hash_records(const uint8_t* d_res, const uint32_t* gpos, const uint16_t* len, uint64_t n, uint32_t seed,
+                         uint32_t* hash, uint32_t* idx, cudaStream_t s);
+// key[i] = mass_bits[idx[i]] - base_bits
+void launch_gather_mass_key(const uint64_t* mass_bits, const uint32_t* idx, uint64_t n, uint64_t base_bits,
+                            uint64_t* key, cudaStream_t s);
+// head flag of every sorted record + per-tile head counts (tile = kScanTile).
+void launch_dedup_flags(const uint8_t* d_res, const uint64_t* skey, const uint32_t* sidx, const uint32_t* hash,
+                        const uint32_t* gpos, const uint16_t* len, uint64_t n, uint8_t* flags,
+                        uint32_t* tile_counts, uint32_t* d_err, cudaStream_t s);
+// unique records + CSR protein lists.
+void launch_dedup_emit(const uint64_t* skey, const uint32_t* sidx, const uint8_t* flags, const uint64_t* tile_offs,
+                       const uint32_t* gpos, const uint32_t* prot, const uint16_t* len, uint64_t n,
+                       uint64_t base_bits, uint64_t n_unique, double* u_mass, uint32_t* u_gpos, uint32_t* u_prot,
+                       uint16_t* u_len, uint64_t* u_plo, uint32_t* plist, cudaStream_t s);
+
+// ---- K5/K6 differential-mod expansion ---------------------------------------
+void launch_mod_count(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const double* u_mass,
+                      const uint32_t* u_gpos, const uint16_t* u_len, uint64_t n_unique, uint32_t* counts,
+                      uint32_t* tile_counts, uint32_t* d_err, cudaStream_t s);
+void launch_mod_emit(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const double* u_mass,
+                     const uint32_t* u_gpos, const uint16_t* u_len, uint64_t n_unique, const uint32_t* counts,
+                     const uint64_t* tile_offs, uint64_t base_bits, uint64_t* v_key, uint64_t* v_payload,
+                     cudaStream_t s);
+// entries from sorted (key, payload): mass = bits(key + base), base id, mod pattern
+void launch_split_entries(const uint64_t* skey, const uint64_t* spayload, uint64_t n, uint64_t base_bits,
+                          double* e_mass, uint32_t* e_base, uint32_t* e_pat, cudaStream_t s);
+
+// ---- K9/K10 query ----------------------------------------------------------------
+void launch_query(const double* e_mass, uint64_t n_entries, const double* lo, const double* hi, uint64_t nq,
+                  uint64_t* hit_begin, uint64_t* hit_count, cudaStream_t s);
+// per-entry protein-list length for entries [begin, begin+count) + per-tile sums.
+// e_base == nullptr means "entry i is unique peptide i" (no differential mods).
+void launch_fetch_sizes(const uint32_t* e_base, const uint64_t* u_plo, uint64_t begin, uint64_t count,
+                        uint32_t* sizes, uint32_t* tile_counts, cudaStream_t s);
+// what parseAddPeptideInfo materialises per hit; any output may be nullptr.
+void launch_fetch_gather(const double* e_mass, const uint32_t* e_base, const uint32_t* e_pat, const uint32_t* u_gpos,
+                         const uint32_t* u_prot, const uint16_t* u_len, const uint64_t* u_plo, const uint32_t* plist,
+                         const uint32_t* pstart, uint64_t begin, uint64_t count, const uint32_t* sizes,
+                         const uint64_t* tile_offs, double* o_mass, uint32_t* o_prot, uint32_t* o_off,
+                         uint16_t* o_len, uint32_t* o_pat, uint64_t* o_list_off, uint32_t* o_ids, cudaStream_t s);
+// distinct (int)(mass*factor) keys: flags + compaction
+void launch_key_flags(const double* e_mass, uint64_t n, double factor, uint8_t* flags, uint32_t* tile_counts,
+                      cudaStream_t s);
+void launch_key_emit(const double* e_mass, uint64_t n, double factor, const uint8_t* flags,
+                     const uint64_t* tile_offs, int32_t* keys, cudaStream_t s);
+
+}  // namespace dbi

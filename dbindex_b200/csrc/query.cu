@@ -1,0 +1,187 @@
+// query.cu -- K9 batched lower/upper bound, K10 hit gather, entry-key listing.
+//
+// Replaces DBIndexStoreSQLiteByteIndexMerge.getSequences (Merge:146-217): the
+// `SELECT ... WHERE precursor_mass_key BETWEEN minKey AND maxKey` plus the exact
+// double filter of parseAddPeptideInfo (Merge:415-419) become one lower_bound and
+// one upper_bound on the totally ordered mass array; both ends inclusive (Q5).
+#include "kernels.cuh"
+
+namespace dbi {
+namespace {
+
+constexpr int Q_THREADS = 256;
+constexpr int Q_IPT = kScanTile / Q_THREADS;
+
+// first index with mass >= v
+__device__ __forceinline__ uint64_t lower_bound_d(const double* __restrict__ a, uint64_t n, double v) {
+  uint64_t lo = 0, len = n;
+  while (len > 0) {
+    const uint64_t half = len >> 1;
+    const double m = __ldg(a + lo + half);
+    if (m < v) { lo += half + 1; len -= half + 1; } else { len = half; }
+  }
+  return lo;
+}
+// first index with mass > v
+__device__ __forceinline__ uint64_t upper_bound_d(const double* __restrict__ a, uint64_t n, double v) {
+  uint64_t lo = 0, len = n;
+  while (len > 0) {
+    const uint64_t half = len >> 1;
+    const double m = __ldg(a + lo + half);
+    if (m <= v) { lo += half + 1; len -= half + 1; } else { len = half; }
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(Q_THREADS)
+    query_kernel(const double* __restrict__ e_mass, uint64_t n, const double* __restrict__ lo,
+                 const double* __restrict__ hi, uint64_t nq, uint64_t* __restrict__ hit_begin,
+                 uint64_t* __restrict__ hit_count) {
+  const uint64_t q = (uint64_t)blockIdx.x * Q_THREADS + threadIdx.x;
+  if (q >= nq) return;
+  const double l = lo[q], h = hi[q];
+  const uint64_t b = lower_bound_d(e_mass, n, l);  // mass < minMass skipped (Merge:419)
+  const uint64_t e = upper_bound_d(e_mass, n, h);  // mass > maxMass stops (Merge:415)
+  hit_begin[q] = b;
+  hit_count[q] = e > b ? e - b : 0;
+}
+
+__global__ void __launch_bounds__(Q_THREADS)
+    fetch_sizes_kernel(const uint32_t* __restrict__ e_base, const uint64_t* __restrict__ u_plo, uint64_t begin,
+                       uint64_t count, uint32_t* __restrict__ sizes, uint32_t* __restrict__ tile_counts) {
+  __shared__ uint32_t scratch[Q_THREADS / 32 + 1];
+  const uint64_t tile_base = (uint64_t)blockIdx.x * kScanTile;
+  uint32_t sum = 0;
+  for (int k = 0; k < Q_IPT; ++k) {
+    const uint64_t i = tile_base + (uint64_t)k * Q_THREADS + threadIdx.x;
+    if (i >= count) break;
+    const uint64_t b = e_base ? (uint64_t)e_base[begin + i] : begin + i;
+    const uint32_t sz = (uint32_t)(u_plo[b + 1] - u_plo[b]);
+    sizes[i] = sz;
+    sum += sz;
+  }
+  uint32_t total;
+  block_exclusive_sum<uint32_t, Q_THREADS>(sum, scratch, &total);
+  if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(Q_THREADS)
+    fetch_gather_kernel(const double* __restrict__ e_mass, const uint32_t* __restrict__ e_base,
+                        const uint32_t* __restrict__ e_pat, const uint32_t* __restrict__ u_gpos,
+                        const uint32_t* __restrict__ u_prot, const uint16_t* __restrict__ u_len,
+                        const uint64_t* __restrict__ u_plo, const uint32_t* __restrict__ plist,
+                        const uint32_t* __restrict__ pstart, uint64_t begin, uint64_t count,
+                        const uint32_t* __restrict__ sizes, const uint64_t* __restrict__ tile_offs,
+                        double* __restrict__ o_mass, uint32_t* __restrict__ o_prot, uint32_t* __restrict__ o_off,
+                        uint16_t* __restrict__ o_len, uint32_t* __restrict__ o_pat, uint64_t* __restrict__ o_list_off,
+                        uint32_t* __restrict__ o_ids) {
+  __shared__ uint32_t scratch[Q_THREADS / 32 + 1];
+  const uint64_t tile_base = (uint64_t)blockIdx.x * kScanTile;
+  const uint64_t ntiles = (count + kScanTile - 1) / kScanTile;
+  uint64_t running = tile_offs[blockIdx.x];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && o_list_off) o_list_off[count] = tile_offs[ntiles];
+  for (int k = 0; k < Q_IPT; ++k) {
+    const uint64_t i = tile_base + (uint64_t)k * Q_THREADS + threadIdx.x;
+    const bool valid = i < count;
+    const uint32_t sz = valid ? sizes[i] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_sum<uint32_t, Q_THREADS>(sz, scratch, &total);
+    if (valid) {
+      const uint64_t e = begin + i;
+      const uint64_t b = e_base ? (uint64_t)e_base[e] : e;
+      const uint32_t pr = u_prot[b];
+      if (o_mass) o_mass[i] = e_mass[e];
+      if (o_prot) o_prot[i] = pr;
+      if (o_off) o_off[i] = u_gpos[b] - pstart[pr];  // sequenceOffset inside the first protein
+      if (o_len) o_len[i] = u_len[b];
+      if (o_pat) o_pat[i] = e_pat ? e_pat[e] : 0u;
+      const uint64_t lo = running + ex;
+      if (o_list_off) o_list_off[i] = lo;
+      if (o_ids) {
+        const uint64_t src = u_plo[b];
+        for (uint32_t j = 0; j < sz; ++j) o_ids[lo + j] = plist[src + j];
+      }
+    }
+    running += total;
+  }
+}
+
+__device__ __forceinline__ int32_t row_key(double m, double factor) { return (int32_t)(m * factor); }
+
+__global__ void __launch_bounds__(Q_THREADS)
+    key_flags_kernel(const double* __restrict__ e_mass, uint64_t n, double factor, uint8_t* __restrict__ flags,
+                     uint32_t* __restrict__ tile_counts) {
+  __shared__ uint32_t scratch[Q_THREADS / 32 + 1];
+  const uint64_t tile_base = (uint64_t)blockIdx.x * kScanTile;
+  uint32_t sum = 0;
+  for (int k = 0; k < Q_IPT; ++k) {
+    const uint64_t i = tile_base + (uint64_t)k * Q_THREADS + threadIdx.x;
+    if (i >= n) break;
+    const uint8_t f = (i == 0) || row_key(e_mass[i], factor) != row_key(e_mass[i - 1], factor);
+    flags[i] = f;
+    sum += f;
+  }
+  uint32_t total;
+  block_exclusive_sum<uint32_t, Q_THREADS>(sum, scratch, &total);
+  if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(Q_THREADS)
+    key_emit_kernel(const double* __restrict__ e_mass, uint64_t n, double factor, const uint8_t* __restrict__ flags,
+                    const uint64_t* __restrict__ tile_offs, int32_t* __restrict__ keys) {
+  __shared__ uint32_t scratch[Q_THREADS / 32 + 1];
+  const uint64_t tile_base = (uint64_t)blockIdx.x * kScanTile;
+  uint64_t running = tile_offs[blockIdx.x];
+  for (int k = 0; k < Q_IPT; ++k) {
+    const uint64_t i = tile_base + (uint64_t)k * Q_THREADS + threadIdx.x;
+    const bool valid = i < n;
+    const uint32_t f = valid ? flags[i] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_sum<uint32_t, Q_THREADS>(f, scratch, &total);
+    if (valid && f) keys[running + ex] = row_key(e_mass[i], factor);
+    running += total;
+  }
+}
+
+}  // namespace
+
+void launch_query(const double* e_mass, uint64_t n_entries, const double* lo, const double* hi, uint64_t nq,
+                  uint64_t* hit_begin, uint64_t* hit_count, cudaStream_t s) {
+  if (nq == 0) return;
+  const unsigned grid = (unsigned)((nq + Q_THREADS - 1) / Q_THREADS);
+  DBI_LAUNCH(query_kernel, grid, Q_THREADS, 0, s, e_mass, n_entries, lo, hi, nq, hit_begin, hit_count);
+}
+
+void launch_fetch_sizes(const uint32_t* e_base, const uint64_t* u_plo, uint64_t begin, uint64_t count,
+                        uint32_t* sizes, uint32_t* tile_counts, cudaStream_t s) {
+  if (count == 0) return;
+  const unsigned tiles = (unsigned)((count + kScanTile - 1) / kScanTile);
+  DBI_LAUNCH(fetch_sizes_kernel, tiles, Q_THREADS, 0, s, e_base, u_plo, begin, count, sizes, tile_counts);
+}
+
+void launch_fetch_gather(const double* e_mass, const uint32_t* e_base, const uint32_t* e_pat, const uint32_t* u_gpos,
+                         const uint32_t* u_prot, const uint16_t* u_len, const uint64_t* u_plo, const uint32_t* plist,
+                         const uint32_t* pstart, uint64_t begin, uint64_t count, const uint32_t* sizes,
+                         const uint64_t* tile_offs, double* o_mass, uint32_t* o_prot, uint32_t* o_off,
+                         uint16_t* o_len, uint32_t* o_pat, uint64_t* o_list_off, uint32_t* o_ids, cudaStream_t s) {
+  if (count == 0) return;
+  const unsigned tiles = (unsigned)((count + kScanTile - 1) / kScanTile);
+  DBI_LAUNCH(fetch_gather_kernel, tiles, Q_THREADS, 0, s, e_mass, e_base, e_pat, u_gpos, u_prot, u_len, u_plo, plist,
+             pstart, begin, count, sizes, tile_offs, o_mass, o_prot, o_off, o_len, o_pat, o_list_off, o_ids);
+}
+
+void launch_key_flags(const double* e_mass, uint64_t n, double factor, uint8_t* flags, uint32_t* tile_counts,
+                      cudaStream_t s) {
+  if (n == 0) return;
+  const unsigned tiles = (unsigned)((n + kScanTile - 1) / kScanTile);
+  DBI_LAUNCH(key_flags_kernel, tiles, Q_THREADS, 0, s, e_mass, n, factor, flags, tile_counts);
+}
+
+void launch_key_emit(const double* e_mass, uint64_t n, double factor, const uint8_t* flags,
+                     const uint64_t* tile_offs, int32_t* keys, cudaStream_t s) {
+  if (n == 0) return;
+  const unsigned tiles = (unsigned)((n + kScanTile - 1) / kScanTile);
+  DBI_LAUNCH(key_emit_kernel, tiles, Q_THREADS, 0, s, e_mass, n, factor, flags, tile_offs, keys);
+}
+
+}  // namespace dbi

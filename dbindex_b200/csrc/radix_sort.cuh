@@ -1,0 +1,18 @@
+// radix_sort.cuh -- host interface of the hand-written onesweep LSD radix sort (K7).
+#pragma once
+#include "common.cuh"
+
+namespace dbi {
+
+// Scratch bytes radix_sort_pairs needs for n pairs.
+size_t radix_sort_tmp_bytes(uint64_t n);
+
+// Stable sort of n (key, value) pairs on key bits [begin_bit, end_bit).
+// keys[0]/vals[0] hold the input; both double buffers are clobbered.  Returns the
+// index (0 or 1) of the buffer pair holding the sorted output.  Instantiated for
+// (u32,u32), (u64,u32) and (u64,u64).
+template <typename K, typename V>
+int radix_sort_pairs(K* keys[2], V* vals[2], uint64_t n, int begin_bit, int end_bit, void* tmp,
+                     cudaStream_t stream, uint32_t* launches);
+
+}  // namespace dbi

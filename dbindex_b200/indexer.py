@@ -1,0 +1,341 @@
+"""Host-side mirror of the reference's indexer / search API over the C ABI.
+
+Same names, argument meaning and error behaviour as the Java classes, so that a
+user of ``DBIndexImpl`` / ``DBIndexer`` finds the calls they know:
+
+* ``DBIndexer``   -- DBIndexer.java (init / run / getSequencesUsing*Tolerance /
+  getSequences(ranges) / getProteins)
+* ``DBIndexImpl`` -- DBIndexImpl.java, the ``DBIndexInterface`` facade
+  (getSequences(mass, tol), getSequences(ranges), getProteins, getIndexedProteinById,
+  getProteinSequenceById)
+
+Only string assembly happens here (peptide substrings, flanking residues); all
+digestion, sorting, merging and searching runs in libdbindex_gpu.so.  The Java shim
+under ``java/`` is the same logic in the reference's own language.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Iterable, List, Optional, Sequence, Set, Tuple
+
+import numpy as np
+
+from .capi import DbiError, DbiParams, GpuIndex
+
+MAX_INDEX_RESIDUE_LEN = 3      # Constants.java:44
+MAX_PRECURSOR_MASS = 8000      # Constants.java:20
+PRECISION = 1e-6               # Constants.java:50
+ONE_MILLION = 1000000.0
+
+
+class DBIndexStoreException(Exception):
+    """edu.scripps.yates.utilities.fasta.dbindex.DBIndexStoreException"""
+
+
+class DBIndexerException(Exception):
+    """DBIndexerException.java:9-18"""
+
+
+@dataclass
+class MassRange:
+    precMass: float
+    tolerance: float
+
+
+@dataclass(frozen=True)
+class IndexedProtein:
+    accession: str
+    id: int
+
+
+@dataclass
+class IndexedSequence:
+    """What parseAddPeptideInfo builds per hit (DBIndexStoreSQLiteByteIndexMerge.java:452-462):
+    IndexedSequence(0, mass, sequence, "", "") + setProteinIds + setResidues.  ``sequenceOffset``
+    and ``modPositions`` are the superset north_star asks for."""
+
+    mass: float
+    sequence: str
+    proteinIds: List[int]
+    resLeft: str = ""
+    resRight: str = ""
+    sequenceOffset: int = -1
+    sequenceLen: int = 0
+    modPositions: Tuple[int, ...] = ()
+    id: int = 0
+
+    def key(self):
+        return (np.float64(self.mass).view(np.uint64).item(), self.sequence, self.modPositions)
+
+
+def get_residues(seq_offset: int, seq_len: int, protein_sequence: str) -> Tuple[str, str]:
+    """Util.getResidues (Util.java:130-162), right flank off-by-one kept."""
+    prot_len = len(protein_sequence)
+    left_i = seq_offset - MAX_INDEX_RESIDUE_LEN if seq_offset >= MAX_INDEX_RESIDUE_LEN else 0
+    left_len = min(MAX_INDEX_RESIDUE_LEN, seq_offset)
+    left = protein_sequence[left_i:left_i + left_len]
+    end = seq_offset + seq_len
+    right_len = min(MAX_INDEX_RESIDUE_LEN, prot_len - end - 1)
+    right = protein_sequence[end:end + right_len] if (end < prot_len and right_len > 0) else ""
+    return left.rjust(MAX_INDEX_RESIDUE_LEN, "-"), right.ljust(MAX_INDEX_RESIDUE_LEN, "-")
+
+
+def tolerance_in_dalton(actual_mass: float, ppm: float) -> float:
+    """IndexUtil.getToleranceInDalton (util/IndexUtil.java:238-240)."""
+    return actual_mass * (1 - 1 / (ppm / ONE_MILLION + 1))
+
+
+def merge_intervals(ranges: Sequence[MassRange]) -> List[Tuple[float, float]]:
+    """Interval.massRangeToInterval (Interval.java:27-38) + MergeIntervals.mergeIntervals
+    (MergeIntervals.java:16-46)."""
+    iv = []
+    for r in ranges:
+        lo = r.precMass - r.tolerance
+        if lo < 0.0:
+            lo = 0.0
+        iv.append((lo, r.precMass + r.tolerance))
+    if len(iv) < 2:
+        return iv
+    iv.sort(key=lambda t: t[0])  # stable, by start
+    out = []
+    start, end = iv[0]
+    for s, e in iv[1:]:
+        if end >= s:
+            end = max(end, e)
+        else:
+            out.append((start, end))
+            start, end = s, e
+    out.append((start, end))
+    return out
+
+
+def read_fasta(path: str) -> Tuple[List[str], List[str]]:
+    """Minimal FASTA reader (the reference uses the external FastaReader)."""
+    deflines, seqs, cur = [], [], []
+    with open(path, "r") as f:
+        for line in f:
+            line = line.rstrip("\r\n")
+            if line.startswith(">"):
+                if deflines:
+                    seqs.append("".join(cur))
+                deflines.append(line[1:])
+                cur = []
+            elif line:
+                cur.append(line.strip().upper())
+    if deflines:
+        seqs.append("".join(cur))
+    return deflines, seqs
+
+
+class DBIndexer:
+    """DBIndexer.java: the indexer / orchestrator, GPU store behind it."""
+
+    def __init__(self, params: DbiParams, index_factor: int = 8):
+        self.sparam = params
+        self.index_factor = index_factor  # dbindex.properties:6; only shapes the ">= MAX_MASS" query rule
+        self.inited = False
+        self.index: Optional[GpuIndex] = None
+        self.deflines: List[str] = []   # ProteinCache.defs
+        self._seq_cache: dict = {}
+
+    # -- lifecycle: init() (DBIndexer.java:412) -> run() (:508) --------------------------
+    def init(self):
+        if self.inited:
+            raise DBIndexerException("Already inited")  # DBIndexer.java:413-415
+        self.index = GpuIndex(self.sparam)
+        self.inited = True
+
+    def _require(self):
+        if not self.inited or self.index is None:
+            raise DBIndexStoreException("Indexer is not initialized")  # DBIndexStoreSQLiteMult.java:153
+
+    def add_proteins(self, deflines: Sequence[str], residues: np.ndarray, offsets: np.ndarray):
+        """protCache.addProtein for a packed batch (DBIndexer.java:605)."""
+        self._require()
+        self.deflines.extend(d.replace("\t", " ") for d in deflines)  # ProteinCache.java:87-89
+        self.index.add_proteins(residues, offsets)
+
+    def run(self, fasta: Optional[str] = None, proteins: Optional[Tuple[Sequence[str], Sequence[str]]] = None):
+        """DBIndexer.run(): stream the FASTA, cut every protein, close the store."""
+        self._require()
+        if fasta is not None:
+            proteins = read_fasta(fasta)
+        if proteins is not None:
+            deflines, seqs = proteins
+            residues = np.frombuffer("".join(seqs).encode("latin-1"), dtype=np.uint8)
+            offsets = np.zeros(len(seqs) + 1, dtype=np.uint64)
+            np.cumsum([len(s) for s in seqs], out=offsets[1:])
+            self.add_proteins(deflines, residues, offsets)
+        try:
+            self.index.build()  # cutSeq per protein + stopAddSeq (DBIndexer.java:616,666)
+        except DbiError as e:
+            raise DBIndexerException(str(e)) from e
+
+    def close(self):
+        if self.index is not None:
+            self.index.close()
+            self.index = None
+        self.inited = False
+
+    # -- helpers ---------------------------------------------------------------------------
+    def getProteinSequence(self, pid: int) -> str:
+        s = self._seq_cache.get(pid)
+        if s is None:
+            s = self.index.get_protein(pid).decode("latin-1")
+            if len(self._seq_cache) < 100000:
+                self._seq_cache[pid] = s
+        return s
+
+    def _out_of_buckets(self, lo: float, hi: float) -> bool:
+        """DBIndexStoreSQLiteMult.getBucketsForMassRange / the 'unsupported precursor mass'
+        early return (Mult:55-56,215-217,333-338): empty answer when a bound reaches MAX_MASS."""
+        bucket_range = MAX_PRECURSOR_MASS // self.index_factor
+        nb = self.index_factor
+        return int(lo) // bucket_range > nb - 1 or int(hi) // bucket_range > nb - 1
+
+    def _materialise(self, begin: np.ndarray, count: np.ndarray) -> List[List[IndexedSequence]]:
+        out = []
+        for b, c in zip(begin.tolist(), count.tolist()):
+            if c == 0:
+                out.append([])
+                continue
+            f = self.index.fetch(b, c)
+            lst = []
+            plo = f["prot_list_off"]
+            for i in range(c):
+                pid = int(f["first_prot"][i])
+                off = int(f["first_off"][i])
+                ln = int(f["len"][i])
+                prot_seq = self.getProteinSequence(pid)
+                pep = prot_seq[off:off + ln]  # ProteinCache.getPeptideSequence (ProteinCache.java:112-127)
+                left, right = get_residues(off, ln, prot_seq)
+                pat = int(f["modpat"][i])
+                pos = tuple(((pat >> (8 * k)) & 0xFF) - 1 for k in range(4) if (pat >> (8 * k)) & 0xFF)
+                ids = f["prot_ids"][int(plo[i]):int(plo[i + 1])].tolist()
+                lst.append(IndexedSequence(float(f["mass"][i]), pep, ids, left, right, off, ln, pos))
+            out.append(lst)
+        return out
+
+    # -- queries --------------------------------------------------------------------------
+    def getSequencesBatch(self, masses: Sequence[float], tolerances: Sequence[float]) -> List[List[IndexedSequence]]:
+        """Many getSequences(precMass, tol) in one device call."""
+        self._require()
+        m = np.asarray(masses, dtype=np.float64)
+        t = np.asarray(tolerances, dtype=np.float64)
+        lo = np.maximum(m - t, 0.0)  # Mult:324-329
+        hi = m + t
+        try:
+            begin, count = self.index.query(lo, hi)
+        except DbiError as e:
+            raise DBIndexStoreException(str(e)) from e
+        for i in range(len(m)):
+            if self._out_of_buckets(lo[i], hi[i]):
+                count[i] = 0
+        return self._materialise(begin, count)
+
+    def getSequencesUsingDaltonTolerance(self, precursorMass: float, massToleranceInDa: float) -> List[IndexedSequence]:
+        """DBIndexer.java:762-772 -> DBIndexStoreSQLiteMult.getSequences (Mult:315-350)."""
+        return self.getSequencesBatch([precursorMass], [massToleranceInDa])[0]
+
+    def getSequencesUsingPPMTolerance(self, precursorMass: float, massToleranceInPPM: float) -> List[IndexedSequence]:
+        """DBIndexer.java:787-844: one Dalton query, then exact-mass probes above the upper
+        bound until one comes back empty."""
+        tol = tolerance_in_dalton(precursorMass, massToleranceInPPM)
+        sequences = self.getSequencesUsingDaltonTolerance(precursorMass, tol)
+        have = {s.key() for s in sequences}
+        upper = precursorMass + tol
+        while True:
+            tol2 = tolerance_in_dalton(upper, massToleranceInPPM)
+            if upper - tol2 < precursorMass:
+                seq2 = self.getSequencesUsingDaltonTolerance(upper, 0.0)
+                if not seq2:
+                    break
+                for s in seq2:
+                    if s.key() not in have:
+                        have.add(s.key())
+                        sequences.append(s)
+            else:
+                break
+            new_upper = upper + PRECISION
+            if new_upper == upper:
+                break
+            upper = new_upper
+        return sequences
+
+    def getSequences(self, ranges: Sequence[MassRange]) -> List[IndexedSequence]:
+        """DBIndexer.java:855-871 -> Mult.getSequences(List<MassRange>) (Mult:353-430)."""
+        self._require()
+        if len(ranges) == 1:
+            return self.getSequencesUsingDaltonTolerance(ranges[0].precMass, ranges[0].tolerance)
+        merged = merge_intervals(ranges)
+        for lo, hi in merged:  # "Cannot query, unsupported precursor mass" -> empty list (Mult:383-387)
+            if self._out_of_buckets(lo, hi):
+                return []
+        if not merged:
+            return []
+        lo = np.array([m[0] for m in merged])
+        hi = np.array([m[1] for m in merged])
+        try:
+            begin, count = self.index.query(lo, hi)
+        except DbiError as e:
+            raise DBIndexStoreException(str(e)) from e
+        out: List[IndexedSequence] = []
+        for lst in self._materialise(begin, count):
+            out.extend(lst)
+        return out
+
+    def getProteins(self, seq) -> Set[IndexedProtein] | List[IndexedProtein]:
+        """getProteins(String) (DBIndexer.java:925-947) / getProteins(IndexedSequence) (:882)."""
+        self._require()
+        if isinstance(seq, IndexedSequence):
+            return [IndexedProtein(self.deflines[i] if i < len(self.deflines) else "", i) for i in seq.proteinIds]
+        mass = self.index.calculate_mass(seq.encode("latin-1"))  # IndexUtil.calculateMass
+        ret: Set[IndexedProtein] = set()
+        for s in self.getSequencesUsingDaltonTolerance(mass, 0.0):
+            if s.sequence == seq and not s.modPositions:
+                ret.update(self.getProteins(s))
+        return ret
+
+    def getNumberSequences(self) -> int:
+        self._require()
+        return int(self.index.stats()["n_entries"])
+
+    def getParentMasses(self) -> List[float]:
+        """DBIndexer.java:984-992: entry keys divided back by massGroupFactor."""
+        self._require()
+        f = float(self.sparam.mass_group_factor)
+        return [k / f for k in self.index.entry_keys().tolist()]
+
+
+class DBIndexImpl:
+    """DBIndexImpl.java: the DBIndexInterface facade a search engine holds."""
+
+    def __init__(self, params: DbiParams, fasta: Optional[str] = None,
+                 proteins: Optional[Tuple[Sequence[str], Sequence[str]]] = None, index_factor: int = 8):
+        self.indexer = DBIndexer(params, index_factor)
+        self.indexer.init()
+        self.indexer.run(fasta=fasta, proteins=proteins)
+        self._proteins_by_seq: dict = {}  # DBIndexImpl.java:33
+
+    def getSequences(self, *args) -> List[IndexedSequence]:
+        """getSequences(double precursorMass, double massTolerance) (DBIndexImpl.java:180) or
+        getSequences(List<MassRange>) (:194)."""
+        if len(args) == 2:
+            return self.indexer.getSequencesUsingDaltonTolerance(float(args[0]), float(args[1]))
+        return self.indexer.getSequences(list(args[0]))
+
+    def getProteins(self, seq):
+        if isinstance(seq, str):  # DBIndexImpl.java:222-237, memoised
+            if seq not in self._proteins_by_seq:
+                self._proteins_by_seq[seq] = self.indexer.getProteins(seq)
+            return self._proteins_by_seq[seq]
+        return self.indexer.getProteins(seq)  # DBIndexImpl.java:208
+
+    def getIndexedProteinById(self, pid: int) -> IndexedProtein:
+        return IndexedProtein(self.indexer.deflines[pid], pid)  # DBIndexImpl.java:501-504
+
+    def getProteinSequenceById(self, pid: int) -> str:
+        return self.indexer.getProteinSequence(pid)  # DBIndexImpl.java:511-513
+
+    def close(self):
+        self.indexer.close()

@@ -1,0 +1,253 @@
+/*
+ * dbindex_gpu.h -- C ABI of the B200-native dbIndex hot path.
+ *
+ * One handle = one peptide index living in the HBM of ONE GPU:
+ *   FASTA residues -> in-silico digestion -> (diff-mod expansion) ->
+ *   mass-sorted, de-duplicated peptide index -> batched precursor-mass
+ *   range lookup.
+ *
+ * Plain C: pointers and sizes only, no C++/torch types.  Bindable from JNI,
+ * Panama FFM, ctypes or cgo.  There is NO CPU fallback behind these entry
+ * points: without a CUDA device every call that needs one returns DBI_ECUDA.
+ *
+ * Each entry point names the reference interface it replaces.  Paths are
+ * relative to src/main/java/edu/scripps/yates/dbindex/ of
+ * proteomicsyates/dbIndex.  See INTEGRATION.md for the Java-side binding.
+ */
+#ifndef DBINDEX_GPU_H
+#define DBINDEX_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBI_ABI_VERSION 1
+
+/* ---- status codes (0 = OK, negative = error) -----------------------------
+ * The shim maps them onto the reference's two exception types:
+ * DBIndexStoreException ("Indexer is not initialized", DBIndexStoreSQLiteMult.java:153,273,316;
+ * "Already intialized", :97-99) and DBIndexerException (DBIndexerException.java:9-18). */
+#define DBI_OK 0
+#define DBI_ENOTINIT (-1) /* query/fetch before dbi_build()            */
+#define DBI_EALREADY (-2) /* add_proteins/build after dbi_build()      */
+#define DBI_EINVAL (-3)   /* bad argument / unsupported parameter      */
+#define DBI_ENOMEM (-4)   /* host or device allocation failed          */
+#define DBI_ECUDA (-5)    /* no device, or a CUDA call failed          */
+#define DBI_ENCCL (-6)    /* reserved for the multi-GPU exchange       */
+#define DBI_ERANGE (-7)   /* a hard limit was exceeded (see below)     */
+
+/* ---- hard limits ---------------------------------------------------------- */
+#define DBI_MAX_MODS 16         /* distinct (residue, delta) entries          */
+#define DBI_MAX_MODS_PER_PEP 4  /* mod pattern = 4 x 8-bit positions          */
+#define DBI_MAX_PEP_LEN 65535   /* len is stored as uint16 (ref: MAX_SEQ_LENGTH 10000, DBIndexer.java:75) */
+#define DBI_MAX_MOD_POS 254     /* modified residue position inside a peptide */
+#define DBI_MIN_PEP_LENGTH 6    /* Constants.java:10                          */
+#define DBI_MASS_GROUP_FACTOR 10000 /* dbindex.properties:20, SearchParamReader.java:705 */
+
+/* One differential (variable) modification: residue -> mass shift.
+ * Mirrors model/ModResidue.java:12-44 and the 256-entry table of
+ * model/DiffModification.java:11-54 (one shift per residue, last one wins). */
+typedef struct dbi_mod {
+  uint8_t residue;
+  uint8_t _pad[7];
+  double delta;
+} dbi_mod;
+
+/* Search parameters that reach the hot path.  POD, passed by
+ * pointer, copied by dbi_create().  Replaces the SearchParams singleton
+ * (SearchParams.java:127-132), DBIndexSearchParamsImpl's 19-arg constructor
+ * (io/DBIndexSearchParamsImpl.java:46-75) and the global AssignMass table
+ * (external utilities jar; call sites DBIndexer.java:268-271,306). */
+typedef struct dbi_params {
+  uint32_t abi_version;   /* must be DBI_ABI_VERSION */
+  int32_t device;         /* CUDA device ordinal */
+
+  /* AssignMass.getMass(char): residue mass table with static mods already
+   * added (AssignMassToStaticParam.java:7-15).  Unknown residues = 0. */
+  double residue_mass[256];
+  double h2o_proton;      /* AssignMass.H2O_PROTON */
+  double nterm;           /* AssignMass.getnTerm() */
+  double cterm;           /* AssignMass.getcTerm() */
+  int32_t add_h2o_proton; /* sparam.isH2OPlusProtonAdded(), DBIndexer.java:268 */
+
+  /* Enzyme (external utilities jar; DBIndexer.java:314-319).  C-terminal cutter. */
+  uint8_t is_enzyme[256]; /* Enzyme.isEnzyme(c)            */
+  uint8_t is_nocut[256];  /* sparam.getEnzymeNocutResidues */
+  int32_t max_missed;     /* sparam.getMaxMissedCleavages(), DBIndexer.java:246,322 */
+  int32_t semi;           /* semi-specific cleavage, Enzyme ctor 3rd arg */
+  int32_t min_len;        /* Constants.MIN_PEP_LENGTH = 6, DBIndexer.java:331 */
+  double min_mass;        /* sparam.getMinPrecursorMass(), DBIndexer.java:331 */
+  double max_mass;        /* sparam.getMaxPrecursorMass(), DBIndexer.java:284,327 */
+  int32_t mass_group_factor; /* key = (int)(mass*factor), DBIndexStoreSQLiteByte.java:187 */
+
+  /* Differential mods (io/SearchParamReader.java:631-667,322). */
+  int32_t n_mods;
+  int32_t max_mods_per_peptide; /* max_num_differential_AA_per_mod */
+  dbi_mod mods[DBI_MAX_MODS];
+
+  /* Test/diagnostic switches (no reference counterpart). */
+  int32_t keep_emitted;   /* keep the raw emitted records for dbi_debug_emitted() */
+  int32_t profile;        /* record a CUDA-event pair around every build stage  */
+  int32_t reserved[6];
+} dbi_params;
+
+/* Counters and per-stage device times (replaces the log4j progress lines,
+ * DBIndexStoreSQLiteMult.java:277-280, and getNumberSequences, DBIndexStore.java). */
+#define DBI_N_STAGES 12
+typedef struct dbi_stats {
+  uint64_t n_proteins;
+  uint64_t n_residues;
+  uint64_t n_emitted;      /* records cutSeq would hand to addSequence           */
+  uint64_t n_unique;       /* distinct (mass, sequence) after the merge           */
+  uint64_t n_entries;      /* searchable entries = unique peptides x mod variants */
+  uint64_t n_hash_retries; /* dedup re-runs caused by a (mass,hash) collision     */
+  uint64_t device_bytes;   /* bytes of HBM held by the finished index             */
+  uint64_t algo_bytes[DBI_N_STAGES]; /* algorithmic bytes moved per stage */
+  float stage_ms[DBI_N_STAGES];      /* device time per stage, only if params.profile */
+  uint32_t stage_launches[DBI_N_STAGES]; /* kernels launched per stage            */
+  uint32_t sort_bits_base;  /* radix key bits sorted for the base records  */
+  uint32_t sort_bits_var;   /* radix key bits sorted for the mod variants  */
+} dbi_stats;
+
+/* stage ids for dbi_stats arrays */
+#define DBI_STAGE_PACK 0
+#define DBI_STAGE_DIGEST_COUNT 1
+#define DBI_STAGE_DIGEST_EMIT 2
+#define DBI_STAGE_SORT_BASE 3
+#define DBI_STAGE_DEDUP 4
+#define DBI_STAGE_MOD_COUNT 5
+#define DBI_STAGE_MOD_EMIT 6
+#define DBI_STAGE_SORT_VAR 7
+#define DBI_STAGE_GATHER_VAR 8
+#define DBI_STAGE_QUERY 9
+#define DBI_STAGE_FETCH 10
+#define DBI_STAGE_OTHER 11
+
+typedef struct dbi_handle dbi_handle;
+
+/* Fill *p with the published defaults: standard monoisotopic (mono != 0) or
+ * average residue masses, H2O+proton added, trypsin (KR), no no-cut residues,
+ * 2 missed cleavages, full specificity, 600..6000 Da, factor 10000, no mods.
+ * This is the written-down contract for the un-vendored AssignMass / Enzyme
+ * (SURVEY.md 8c); a Java host overwrites the tables from the live classes.
+ * Mirrors DBIndexImpl.getDefaultDBIndexParams (DBIndexImpl.java:243-303). */
+void dbi_default_params(dbi_params* p, int mono);
+
+/* AssignMass.addMass(ch, delta) for a static modification; ignored when
+ * delta <= 0 exactly like AssignMassToStaticParam.java:9-10. */
+void dbi_params_add_static_mod(dbi_params* p, uint8_t residue, double delta);
+
+/* Enzyme.addCleavePosition(ch) per character (SearchParams.java:301-307). */
+void dbi_params_set_enzyme(dbi_params* p, const char* residues, const char* nocut);
+
+/* diff_search_options entry: every residue of `residues` gets shift `delta`
+ * (io/SearchParamReader.java:640-660).  Returns DBI_ERANGE past DBI_MAX_MODS. */
+int dbi_params_add_diff_mod(dbi_params* p, const char* residues, double delta);
+
+/* new DBIndexer(params, INDEX) + init()  (DBIndexer.java:167,412). */
+int dbi_create(const dbi_params* params, dbi_handle** out);
+
+/* Use a caller-owned CUDA stream (cudaStream_t cast to void*) for every kernel
+ * and copy of this handle; NULL = the handle's own stream. */
+int dbi_set_stream(dbi_handle* h, void* cuda_stream);
+
+/* The per-protein body of DBIndexer.run() (DBIndexer.java:600-616):
+ * ProteinCache.addProtein (ProteinCache.java:84-95) for n proteins whose
+ * residues are concatenated in `residues`, protein i occupying
+ * [offsets[i], offsets[i+1]).  Host memory, copied.  May be called repeatedly;
+ * ids are assigned in call order (= FASTA order), 0-based like protNum
+ * (DBIndexer.java:70,151,251).  Residue byte 0 is rejected (DBI_EINVAL). */
+int dbi_add_proteins(dbi_handle* h, const uint8_t* residues, const uint64_t* offsets, uint32_t n);
+
+/* Copy the proteins added so far into HBM now (idempotent; dbi_build() does it
+ * implicitly).  Lets a caller separate the host->device copy of the FASTA
+ * residues from the build proper. */
+int dbi_upload(dbi_handle* h);
+
+/* Drop the built index but keep the proteins (host and device copies), so that
+ * dbi_build() can run again: the analogue of deleting the <fasta>_<md5>.idx
+ * directory and re-running DBIndexer.run() (DBIndexer.java:522-531). */
+int dbi_reset_index(dbi_handle* h);
+
+/* cutSeq for every protein + indexStore.stopAddSeq() (DBIndexer.java:616,666;
+ * DBIndexStoreSQLiteByteIndexMerge.java:64-127,620-719): digest, sort by mass,
+ * merge equal peptides, expand differential mods, sort the variants. */
+int dbi_build(dbi_handle* h);
+
+/* getNumberSequences() and friends. */
+int dbi_stats_get(dbi_handle* h, dbi_stats* out);
+
+/* Batched DBIndexStore.getSequences(precMass, tol) (DBIndexStoreSQLiteMult.java:315-350,
+ * DBIndexStoreSQLiteByteIndexMerge.java:146-217).  The caller passes the
+ * inclusive exact-double bounds lo = max(0, m - tol), hi = m + tol
+ * (Mult:324-329); the answer for query i is the contiguous run of index
+ * entries [hit_begin[i], hit_begin[i] + hit_count[i]) with lo <= mass <= hi
+ * (the exact filter of Merge:415-419).  Host pointers. */
+int dbi_query(dbi_handle* h, const double* lo, const double* hi, uint64_t nq, uint64_t* hit_begin,
+              uint64_t* hit_count);
+
+/* Same, with every pointer in DEVICE memory of the handle's GPU (used when the
+ * queries are already resident; also the building block of dbi_query). */
+int dbi_query_device(dbi_handle* h, const double* d_lo, const double* d_hi, uint64_t nq,
+                     uint64_t* d_hit_begin, uint64_t* d_hit_count);
+
+/* Materialise entries [begin, begin+count): what parseAddPeptideInfo builds per
+ * hit (DBIndexStoreSQLiteByteIndexMerge.java:386-481).  Any output pointer may
+ * be NULL.  prot_list_off has count+1 entries (CSR over prot_ids);
+ * *n_prot_ids receives the total id count, so call once with prot_ids == NULL
+ * to size it.  first_prot/first_off/len are the first occurrence's protein,
+ * offset and length (Merge:678-687); modpat holds up to 4 modified residue
+ * positions, byte k = position+1 of the k-th modified residue, 0 = none. */
+int dbi_fetch(dbi_handle* h, uint64_t begin, uint64_t count, double* mass, uint32_t* first_prot,
+              uint32_t* first_off, uint16_t* len, uint32_t* modpat, uint64_t* prot_list_off,
+              uint32_t* prot_ids, uint64_t prot_ids_capacity, uint64_t* n_prot_ids);
+
+/* ProteinCache.getProteinSequence(id) (ProteinCache.java; DBIndexImpl.java:511).
+ * Returns a pointer into the handle's host copy, valid until dbi_destroy. */
+int dbi_get_protein(dbi_handle* h, uint32_t id, const uint8_t** residues, uint64_t* len);
+
+/* IndexUtil.calculateMass(seq) (util/IndexUtil.java:197-208): same summation
+ * order as the digestion, so a zero-tolerance lookup finds the peptide
+ * (DBIndexer.getProteins(String), DBIndexer.java:925-947).  Pure host arithmetic
+ * on the handle's parameter table. */
+int dbi_calculate_mass(dbi_handle* h, const uint8_t* seq, uint64_t len, double* mass);
+
+/* DBIndexStore.getEntryKeys(): distinct (int)(mass*factor) row keys in ascending
+ * order (DBIndexer.java:984-992 divides them back).  Two-call sizing. */
+int dbi_entry_keys(dbi_handle* h, int32_t* keys, uint64_t capacity, uint64_t* n_keys);
+
+/* Test hook: the records cutSeq would pass to addSequence, in call order
+ * (protein, start, end ascending).  Needs params.keep_emitted. */
+int dbi_debug_emitted(dbi_handle* h, uint64_t capacity, double* mass, uint32_t* prot, uint32_t* off,
+                      uint16_t* len, uint64_t* n);
+
+/* Test hook for the store-level known-answer test (the literals of
+ * DBIndexStoreSQLiteMult.main, DBIndexStoreSQLiteMult.java:497-524): index
+ * caller-supplied (mass, prot, off, len) records instead of digesting.
+ * Proteins must have been added so that sequences can be compared. */
+int dbi_build_from_records(dbi_handle* h, const double* mass, const uint32_t* prot,
+                           const uint32_t* off, const uint16_t* len, uint64_t n);
+
+/* Test hook for K7: stable radix sort of n host (key, value) pairs on key bits
+ * [begin_bit, end_bit), in place, on the handle's GPU. */
+int dbi_debug_radix_sort(dbi_handle* h, uint64_t* keys, uint64_t* vals, uint64_t n, int begin_bit, int end_bit);
+
+void dbi_destroy(dbi_handle* h);
+
+/* sizeof(dbi_params) and sizeof(dbi_stats) as compiled: lets a binding check
+ * its struct layout before the first call. */
+void dbi_abi_sizes(uint64_t* sizeof_params, uint64_t* sizeof_stats);
+
+/* Thread-local text of the last error on this thread. */
+const char* dbi_last_error(void);
+
+/* Number of CUDA kernels this library has launched in this process (all
+ * handles); bench.py reports the delta over the timed region as gpu_launches. */
+uint64_t dbi_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBINDEX_GPU_H */

@@ -1,0 +1,158 @@
+"""ctypes binding of oracle/liboracle.so -- TEST INFRASTRUCTURE ONLY.
+
+May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs, never by the product package (dbindex_b200/).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-C", _HERE, "-s"])
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        build()
+    lib = C.CDLL(LIB_PATH)
+    vp, u64p = C.c_void_p, C.POINTER(C.c_uint64)
+    lib.orc_create.restype = vp
+    lib.orc_create.argtypes = [vp]
+    lib.orc_destroy.argtypes = [vp]
+    lib.orc_add_proteins.argtypes = [vp, vp, vp, C.c_uint32]
+    lib.orc_set_threads.argtypes = [C.c_int]
+    lib.orc_max_threads.restype = C.c_int
+    lib.orc_build.argtypes = [vp]
+    lib.orc_build.restype = C.c_int
+    lib.orc_build_from_records.argtypes = [vp, vp, vp, vp, vp, C.c_uint64]
+    lib.orc_build_from_records.restype = C.c_int
+    lib.orc_counts.argtypes = [vp, u64p, u64p, u64p, u64p]
+    lib.orc_emitted.argtypes = [vp, vp, vp, vp, vp]
+    lib.orc_entries.argtypes = [vp, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp, vp, vp]
+    lib.orc_query.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, C.POINTER(C.c_int)]
+    lib.orc_calculate_mass.argtypes = [vp, C.c_char_p, C.c_uint64]
+    lib.orc_calculate_mass.restype = C.c_double
+    lib.orc_tolerance_in_dalton.argtypes = [C.c_double, C.c_double]
+    lib.orc_tolerance_in_dalton.restype = C.c_double
+    lib.orc_merge_intervals.argtypes = [vp, vp, C.c_uint64, vp, vp]
+    lib.orc_merge_intervals.restype = C.c_uint64
+    lib.orc_get_residues.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_char_p, C.c_char_p]
+    _lib = lib
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """CPU restatement of the reference path (see dbindex_oracle.cpp)."""
+
+    def __init__(self, params, threads: int = 1):
+        self.lib = load()
+        self.lib.orc_set_threads(threads)
+        self.threads = threads
+        self._params = params  # keep alive
+        self.h = C.c_void_p(self.lib.orc_create(C.byref(params)))
+
+    def close(self):
+        if self.h:
+            self.lib.orc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_proteins(self, residues, offsets):
+        residues = np.ascontiguousarray(residues, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self.lib.orc_add_proteins(self.h, _p(residues), _p(offsets), len(offsets) - 1)
+
+    def build(self) -> int:
+        self.lib.orc_set_threads(self.threads)
+        return self.lib.orc_build(self.h)
+
+    def build_from_records(self, mass, prot, off, length) -> int:
+        mass = np.ascontiguousarray(mass, np.float64)
+        prot = np.ascontiguousarray(prot, np.uint32)
+        off = np.ascontiguousarray(off, np.uint32)
+        length = np.ascontiguousarray(length, np.uint16)
+        return self.lib.orc_build_from_records(self.h, _p(mass), _p(prot), _p(off), _p(length), len(mass))
+
+    def counts(self):
+        a, b, c, d = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.lib.orc_counts(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        return {"n_emitted": a.value, "n_unique": b.value, "n_entries": c.value, "n_prot_ids": d.value}
+
+    def emitted(self):
+        n = self.counts()["n_emitted"]
+        out = {"mass": np.empty(n, np.float64), "prot": np.empty(n, np.uint32), "off": np.empty(n, np.uint32),
+               "len": np.empty(n, np.uint16)}
+        self.lib.orc_emitted(self.h, _p(out["mass"]), _p(out["prot"]), _p(out["off"]), _p(out["len"]))
+        return out
+
+    def entries(self, begin=0, count=None):
+        c = self.counts()
+        if count is None:
+            count = c["n_entries"] - begin
+        out = {
+            "mass": np.empty(count, np.float64), "first_prot": np.empty(count, np.uint32),
+            "first_off": np.empty(count, np.uint32), "len": np.empty(count, np.uint16),
+            "modpat": np.empty(count, np.uint32), "prot_list_off": np.zeros(count + 1, np.uint64),
+        }
+        # size the id list
+        self.lib.orc_entries(self.h, begin, count, None, None, None, None, None, _p(out["prot_list_off"]), None)
+        ids = np.empty(int(out["prot_list_off"][count]), np.uint32)
+        self.lib.orc_entries(self.h, begin, count, _p(out["mass"]), _p(out["first_prot"]), _p(out["first_off"]),
+                             _p(out["len"]), _p(out["modpat"]), _p(out["prot_list_off"]), _p(ids))
+        out["prot_ids"] = ids
+        return out
+
+    def query(self, lo, hi):
+        lo = np.ascontiguousarray(lo, np.float64)
+        hi = np.ascontiguousarray(hi, np.float64)
+        nq = len(lo)
+        b = np.empty(nq, np.uint64)
+        c = np.empty(nq, np.uint64)
+        contig = C.c_int(1)
+        self.lib.orc_set_threads(self.threads)
+        self.lib.orc_query(self.h, _p(lo), _p(hi), nq, _p(b), _p(c), C.byref(contig))
+        return b, c, bool(contig.value)
+
+    def calculate_mass(self, seq: bytes) -> float:
+        return self.lib.orc_calculate_mass(self.h, seq, len(seq))
+
+
+def tolerance_in_dalton(mass: float, ppm: float) -> float:
+    return load().orc_tolerance_in_dalton(mass, ppm)
+
+
+def merge_intervals(mass, tol):
+    mass = np.ascontiguousarray(mass, np.float64)
+    tol = np.ascontiguousarray(tol, np.float64)
+    lo = np.empty(len(mass), np.float64)
+    hi = np.empty(len(mass), np.float64)
+    n = load().orc_merge_intervals(_p(mass), _p(tol), len(mass), _p(lo), _p(hi))
+    return lo[:n].copy(), hi[:n].copy()
+
+
+def get_residues(prot_seq: bytes, off: int, length: int):
+    l = C.create_string_buffer(3)
+    r = C.create_string_buffer(3)
+    load().orc_get_residues(prot_seq, len(prot_seq), off, length, l, r)
+    return l.raw.decode(), r.raw.decode()

@@ -1,0 +1,321 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs.  Bar: bit-exact (integer/index work and IEEE-double masses alike)."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import dbindex_b200 as dbi
+from dbindex_b200 import synth
+from dbindex_b200.indexer import DBIndexImpl, DBIndexer, MassRange, tolerance_in_dalton
+from oracle.oracle_py import Oracle
+
+from .util import PARAM_SETS, assert_emitted_equal, assert_entries_equal, bits, pack
+
+pytestmark = pytest.mark.gpu
+NCPU = os.cpu_count() or 1
+
+
+def both(params, residues, offsets, keep=True):
+    params = params.copy()
+    params.keep_emitted = 1 if keep else 0
+    g = dbi.GpuIndex(params)
+    g.add_proteins(residues, offsets)
+    g.build()
+    o = Oracle(params, threads=NCPU)
+    o.add_proteins(residues, offsets)
+    assert o.build() == 0
+    return g, o
+
+
+def check_all(g, o, nq=500, seed=1):
+    st, oc = g.stats(), o.counts()
+    assert (st["n_emitted"], st["n_unique"], st["n_entries"]) == (oc["n_emitted"], oc["n_unique"], oc["n_entries"])
+    assert_emitted_equal(g.debug_emitted(), o.emitted())
+    exp = o.entries()
+    got = g.fetch(0, st["n_entries"])
+    assert_entries_equal(got, exp)
+    _, _, lo, hi = synth.synth_queries(exp["mass"], nq, seed, da_fraction=0.3)
+    b, c = g.query(lo, hi)
+    ob, oc_, contig = o.query(lo, hi)
+    assert contig
+    assert np.array_equal(b, ob), "hit_begin differs"
+    assert np.array_equal(c, oc_), "hit_count differs"
+
+
+def test_radix_sort_hook():
+    """K7 alone: stability, tile boundaries, skewed digits."""
+    rng = np.random.default_rng(0)
+    with dbi.GpuIndex(dbi.default_params()) as g:
+        for n in (1, 2, 31, 255, 4095, 4096, 4097, 8192, 100_003, 1_000_000):
+            for kind in ("random", "equal", "few", "sorted", "reverse"):
+                if kind == "random":
+                    keys = rng.integers(0, 1 << 54, size=n, dtype=np.uint64)
+                elif kind == "equal":
+                    keys = np.full(n, 0x2A5A5A5A5A5A5A, dtype=np.uint64)
+                elif kind == "few":
+                    keys = rng.integers(0, 5, size=n, dtype=np.uint64) << np.uint64(20)
+                elif kind == "sorted":
+                    keys = np.arange(n, dtype=np.uint64) * np.uint64(977)
+                else:
+                    keys = (np.arange(n, dtype=np.uint64)[::-1] * np.uint64(977)).copy()
+                vals = np.arange(n, dtype=np.uint64)
+                k2, v2 = keys.copy(), vals.copy()
+                g.debug_radix_sort(k2, v2, 0, 54)
+                order = np.argsort(keys, kind="stable")
+                assert np.array_equal(k2, keys[order]), (n, kind, "keys")
+                assert np.array_equal(v2, vals[order]), (n, kind, "stability / values")
+        # partial bit ranges: only bits [8, 20) take part
+        keys = rng.integers(0, 1 << 30, size=50_000, dtype=np.uint64)
+        vals = np.arange(50_000, dtype=np.uint64)
+        k2, v2 = keys.copy(), vals.copy()
+        g.debug_radix_sort(k2, v2, 8, 20)
+        order = np.argsort((keys >> np.uint64(8)) & np.uint64(0xFFF), kind="stable")
+        assert np.array_equal(k2, keys[order]) and np.array_equal(v2, vals[order])
+
+
+def test_kat_albumin_prefix_gpu():
+    p = dbi.default_params()
+    seq = "MKWVTFISLLLLFSSAYSRGVFRR"
+    p.keep_emitted = 1
+    with dbi.GpuIndex(p) as g:
+        g.add_proteins(*pack([seq]))
+        g.build()
+        e = g.debug_emitted()
+        assert [(int(a), int(b)) for a, b in zip(e["off"], e["len"])] == [(0, 19), (0, 23), (2, 17), (2, 21), (2, 22)]
+        for off, ln, m in zip(e["off"], e["len"], e["mass"]):
+            assert m == g.calculate_mass(seq[off:off + ln].encode())  # zero-tolerance lookups work
+
+
+@pytest.mark.parametrize("name", list(PARAM_SETS))
+def test_parity_param_sets(name):
+    p = dbi.default_params(**PARAM_SETS[name])
+    res, off = synth.synth_proteome(120, 1000 + len(name), median_len=300, min_len=5)
+    seqs = [res[int(off[i]):int(off[i + 1])].tobytes().decode() for i in range(len(off) - 1)]
+    # edge cases the domain has: empty and tiny proteins, poly-K, duplicates (protein lists with
+    # repeats), isomers, mod-rich peptides, a protein without any cleavage site
+    seqs += ["", "K", "A", "KKKKKKKKKKKKKKKK", seqs[0], seqs[0], "AAGGLLKGGAALLKAAGGLLK", "MSTYMSTYMSTYMSTYK",
+             "GGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGG", "", seqs[3][:40], "PKPKPKPRPRPAAAAAAAAK"]
+    g, o = both(p, *pack(seqs))
+    try:
+        check_all(g, o)
+    finally:
+        g.close()
+
+
+def test_empty_and_degenerate_indexes():
+    p = dbi.default_params()
+    for seqs in ([], [""], ["AAA"], ["K" * 5], ["G" * 200]):
+        with dbi.GpuIndex(p) as g:
+            g.add_proteins(*pack(seqs))
+            g.build()
+            st = g.stats()
+            o = Oracle(p); o.add_proteins(*pack(seqs)); o.build()
+            assert st["n_entries"] == o.counts()["n_entries"]
+            b, c = g.query(np.array([0.0, 700.0]), np.array([9000.0, 701.0]))
+            ob, oc_, _ = o.query(np.array([0.0, 700.0]), np.array([9000.0, 701.0]))
+            assert np.array_equal(c, oc_) and np.array_equal(b, ob)
+
+
+def test_long_protein_and_many_small():
+    """A titin-sized protein (work unit is a start residue, not a protein) next to many short ones,
+    added in several dbi_add_proteins calls."""
+    p = dbi.default_params(**PARAM_SETS["cfg2_mods"])
+    p.keep_emitted = 1
+    big, boff = synth.synth_proteome(1, 31, median_len=36000, sigma=0.0, max_len=36000)
+    small, soff = synth.synth_proteome(400, 32, median_len=60, min_len=1)
+    g = dbi.GpuIndex(p)
+    o = Oracle(p, threads=NCPU)
+    for r, f in ((small[:int(soff[200])], soff[:201]), (big, boff), (small[int(soff[200]):], soff[200:] - soff[200])):
+        g.add_proteins(r, f)
+        o.add_proteins(r, f)
+    g.build()
+    assert o.build() == 0
+    try:
+        check_all(g, o)
+    finally:
+        g.close()
+
+
+def test_store_level_kat_mult_main_gpu():
+    """DBIndexStoreSQLiteMult.main literals (DBIndexStoreSQLiteMult.java:497-571) through the GPU store."""
+    p = dbi.default_params(min_mass=0.0, max_mass=8000.0)
+    f32 = lambda x: struct.unpack("f", struct.pack("f", x))[0]
+    seqs = ["ABCDEFGHIJKL", "GHIJKLMNOPR"]
+    mass = [1.0, 2.0, 3.0, 4.0, f32(6000.42323), f32(6999.42323), 3.0, 3.0, 5.0, 3.0, 3.0]
+    prot = [0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1]
+    off = [0, 0, 0, 0, 0, 0, 6, 1, 2, 0, 0]
+    ln = [1, 2, 3, 4, 5, 6, 3, 3, 5, 3, 3]
+    with dbi.GpuIndex(p) as g:
+        g.add_proteins(*pack(seqs))
+        g.build_from_records(mass, prot, off, ln)
+        o = Oracle(p); o.add_proteins(*pack(seqs)); o.build_from_records(mass, prot, off, ln)
+        e = g.fetch(0, g.stats()["n_entries"])
+        assert_entries_equal(e, o.entries())
+        pep = [seqs[a][b:b + c] for a, b, c in zip(e["first_prot"], e["first_off"], e["len"])]
+        i = pep.index("GHI")
+        assert e["prot_ids"][int(e["prot_list_off"][i]):int(e["prot_list_off"][i + 1])].tolist() == [0, 1, 1]
+        tol = f32(8.9)
+        b, c = g.query(np.array([max(0.0, 10 - tol)]), np.array([10 + tol]))
+        assert sorted(pep[int(b[0]):int(b[0] + c[0])]) == sorted(["AB", "ABC", "GHI", "HIJ", "ABCD", "IJKLM"])
+
+
+def test_reference_api_mirror():
+    """The DBIndexImpl / DBIndexer surface (DBIndexImpl.java:180-237,501-513; DBIndexer.java:762-947)."""
+    p = dbi.default_params()
+    res, off = synth.synth_proteome(60, 77)
+    seqs = [res[int(off[i]):int(off[i + 1])].tobytes().decode() for i in range(len(off) - 1)]
+    seqs.append(seqs[5])  # a duplicated protein: every peptide of it maps to two proteins
+    defs = synth.deflines(len(seqs))
+    impl = DBIndexImpl(p, proteins=(defs, seqs))
+    try:
+        o = Oracle(p); o.add_proteins(*pack(seqs)); o.build()
+        exp = o.entries()
+        m = float(exp["mass"][len(exp["mass"]) // 3])
+        tol = tolerance_in_dalton(m, 10.0)
+        hits = impl.getSequences(m, tol)
+        ob, oc, _ = o.query([m - tol], [m + tol])
+        assert len(hits) == int(oc[0]) >= 1
+        for h in hits:
+            assert abs(h.mass - m) <= tol
+            pid = h.proteinIds[0]
+            assert seqs[pid][h.sequenceOffset:h.sequenceOffset + h.sequenceLen] == h.sequence
+            assert impl.indexer.index.calculate_mass(h.sequence.encode()) == h.mass
+            assert len(h.resLeft) == 3 and len(h.resRight) == 3
+        # getProteins(String): zero-tolerance lookup by recomputed mass (bit-exact masses required)
+        target = hits[0]
+        prots = impl.getProteins(target.sequence)
+        assert {q.id for q in prots} == set(target.proteinIds)
+        assert all(q.accession == defs[q.id] for q in prots)
+        assert impl.getProteinSequenceById(3) == seqs[3]
+        assert impl.getIndexedProteinById(3).accession == defs[3]
+        # multi-range: union over merged intervals, no duplicates (MergeIntervals.java:31)
+        rs = [MassRange(m, 0.5), MassRange(m + 0.2, 0.5), MassRange(m, 0.5), MassRange(m + 300, 0.01)]
+        multi = impl.getSequences(rs)
+        keys = [s.key() for s in multi]
+        assert len(keys) == len(set(keys))
+        lo = min(m - 0.5, m - 0.3)
+        n_exp = np.count_nonzero((exp["mass"] >= lo) & (exp["mass"] <= m + 0.7)) + \
+            np.count_nonzero((exp["mass"] >= m + 300 - 0.01) & (exp["mass"] <= m + 300 + 0.01))
+        assert len(multi) == n_exp
+        # queries reaching MAX_MASS return nothing (DBIndexStoreSQLiteMult.java:333-338)
+        assert impl.getSequences(7990.0, 20.0) == []
+        # ppm entry point of DBIndexer
+        ppm_hits = impl.indexer.getSequencesUsingPPMTolerance(m, 10.0)
+        assert {s.key() for s in ppm_hits} >= {s.key() for s in hits}
+        assert impl.indexer.getNumberSequences() == len(exp["mass"])
+        pm = impl.indexer.getParentMasses()
+        assert pm == sorted(set(int(x * 10000) / 10000.0 for x in exp["mass"]))
+    finally:
+        impl.close()
+    d = DBIndexer(p)
+    with pytest.raises(Exception):
+        d.getSequencesUsingDaltonTolerance(1000.0, 1.0)  # "Indexer is not initialized"
+
+
+def test_lifecycle_errors_and_rebuild():
+    p = dbi.default_params()
+    res, off = synth.synth_proteome(50, 9)
+    with dbi.GpuIndex(p) as g:
+        with pytest.raises(dbi.DbiError) as ei:
+            g.query(np.array([1.0]), np.array([2.0]))
+        assert ei.value.code == -1  # DBI_ENOTINIT
+        g.add_proteins(res, off)
+        g.build()
+        n1 = g.stats()["n_entries"]
+        first = g.fetch(0, n1)
+        with pytest.raises(dbi.DbiError) as ei:
+            g.build()
+        assert ei.value.code == -2  # DBI_EALREADY
+        with pytest.raises(dbi.DbiError):
+            g.add_proteins(res, off)
+        g.reset_index()
+        g.build()  # idempotent: the rebuilt index is identical
+        again = g.fetch(0, g.stats()["n_entries"])
+        for k in first:
+            assert np.array_equal(first[k], again[k]), k
+        bad = res.copy(); bad[10] = 0
+    with dbi.GpuIndex(p) as g:
+        g.add_proteins(bad, off)
+        with pytest.raises(dbi.DbiError) as ei:
+            g.build()
+        assert ei.value.code == -3  # residue byte 0 rejected
+
+
+def test_cfg1_full_size_parity():
+    """BASELINE.json configs[0]: ~20k proteins / ~11M residues, trypsin, 2 MC, 600-6000 Da, no mods,
+    index build + 10k queries, complete comparison with the oracle."""
+    p = dbi.default_params()
+    res, off = synth.config_proteome(1)
+    g, o = both(p, res, off)
+    try:
+        check_all(g, o, nq=10_000, seed=20240601)
+        # entry keys = distinct (int)(mass*10000)
+        keys = g.entry_keys()
+        exp_keys = np.unique((o.entries()["mass"] * 10000).astype(np.int32))
+        assert np.array_equal(keys, exp_keys)
+    finally:
+        g.close()
+
+
+def test_cfg2_mods_midsize_and_full_size_properties():
+    """BASELINE.json configs[1] (static C, variable M + STY, <= 3 per peptide): complete comparison
+    on 2000 proteins; at the full 20k proteins size-independent properties plus an order-independent
+    checksum of every entry against the oracle."""
+    p = dbi.default_params(**PARAM_SETS["cfg2_mods"])
+    res, off = synth.config_proteome(2, 2000)
+    g, o = both(p, res, off)
+    try:
+        check_all(g, o, nq=2000)
+    finally:
+        g.close()
+    res, off = synth.config_proteome(2)
+    g, o = both(p, res, off, keep=False)
+    try:
+        st, oc = g.stats(), o.counts()
+        assert (st["n_emitted"], st["n_unique"], st["n_entries"]) == (oc["n_emitted"], oc["n_unique"], oc["n_entries"])
+        n = st["n_entries"]
+        chunk = 8_000_000
+        def checksum(e):
+            h = bits(e["mass"]) * np.uint64(0x9E3779B97F4A7C15)
+            h ^= (e["first_prot"].astype(np.uint64) << np.uint64(32) | e["first_off"].astype(np.uint64)) * np.uint64(0xC2B2AE3D27D4EB4F)
+            h ^= (e["len"].astype(np.uint64) << np.uint64(32) | e["modpat"].astype(np.uint64)) * np.uint64(0x165667B19E3779F9)
+            h *= np.uint64(0xFF51AFD7ED558CCD)
+            return int(np.bitwise_xor.reduce(h)), int(h.sum(dtype=np.uint64))
+        last = 0.0
+        for s in range(0, n, chunk):
+            c = min(chunk, n - s)
+            got = g.fetch(s, c, with_ids=False)
+            exp = o.entries(s, c)
+            assert np.array_equal(bits(got["mass"]), bits(exp["mass"]))   # same masses at the same index
+            assert got["mass"][0] >= last and np.all(np.diff(got["mass"]) >= 0)  # sortedness
+            last = got["mass"][-1]
+        # order-independent checksum over all entries (ties may be ordered differently)
+        gx = gs = ox = os_ = 0
+        for s in range(0, n, chunk):
+            c = min(chunk, n - s)
+            a, b = checksum(g.fetch(s, c, with_ids=False))
+            gx ^= a; gs = (gs + b) % (1 << 64)
+            a, b = checksum(o.entries(s, c))
+            ox ^= a; os_ = (os_ + b) % (1 << 64)
+        assert (gx, gs) == (ox, os_)
+        m_all = o.entries(0, n)["mass"] if n < 100_000_000 else None
+        _, _, lo, hi = synth.synth_queries(m_all, 10_000, 5, da_fraction=0.5)
+        b, c = g.query(lo, hi)
+        ob, oc_, contig = o.query(lo, hi)
+        assert contig and np.array_equal(b, ob) and np.array_equal(c, oc_)
+    finally:
+        g.close()
+
+
+def test_cfg3_semi_sample():
+    """BASELINE.json configs[2] (semi-tryptic window enumeration) on a 4000-protein sample."""
+    p = dbi.default_params(semi=1)
+    res, off = synth.config_proteome(3, 4000)
+    g, o = both(p, res, off)
+    try:
+        check_all(g, o, nq=2000)
+        assert g.stats()["n_emitted"] > 4 * len(res)  # the window explosion is real
+    finally:
+        g.close()
