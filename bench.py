@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of dbIndex on B200: index build + precursor-mass queries.
+
+One step = one pass of the hot path over one batch of synthetic input:
+  dbi_build (pack -> digest -> sort -> merge -> mod expansion -> sort) on the device-resident
+  residues of the workload, followed by one batch of precursor queries.
+Workload at N = 1: BASELINE.json configs[1] -- the synthetic Swiss-Prot-sized FASTA (20 000
+proteins, ~11 M residues, seed 20240602-1), trypsin, 2 missed cleavages, 600-6000 Da, static
+carbamidomethyl-C, variable Met-oxidation + STY-phospho (<= 3 per peptide), 10 000 queries at 10 ppm.
+
+  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+  python bench.py --impl reference ...                    # CPU restatement of the reference (oracle/)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = ("cfg2: synthetic Swiss-Prot-sized FASTA (20000 proteins, ~11M residues), trypsin, 2 missed cleavages, "
+            "600-6000 Da, static C+57.02146, variable M+15.9949 / STY+79.96633, <=3 per peptide, "
+            "index build + 10000 queries @ 10 ppm")
+CFG2 = dict(static_mods={"C": 57.02146}, diff_mods=[("M", 15.9949), ("STY", 79.96633)], max_mods_per_peptide=3)
+METRIC = "peptides_indexed_per_s"
+UNIT = "peptides/s"
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_traffic(kernel: str, units: int):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/traffic.json), scaled per sorted pair; None when no capture is on file."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)[kernel]
+        return float(t["dram_bytes_per_pair"]) * units
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); smax.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def workload_inputs(rank: int, n_proteins: int):
+    from dbindex_b200 import synth
+    if rank == 0:
+        return synth.config_proteome(2, n_proteins)
+    # weak scaling: every further rank digests its own proteome of the same shape
+    return synth.synth_proteome(n_proteins, synth.BASE_SEED + 1 + 1000 * rank)
+
+
+def sample_index_masses(g, n_entries: int, chunks: int = 64, chunk: int = 2048) -> np.ndarray:
+    if n_entries == 0:
+        return np.zeros(0)
+    out = []
+    for i in range(chunks):
+        b = (n_entries - chunk) * i // max(1, chunks - 1) if n_entries > chunk else 0
+        c = min(chunk, n_entries - b)
+        out.append(g.fetch(b, c, with_ids=False)["mass"])
+    return np.concatenate(out)
+
+
+def cpu_baseline(n_proteins: int, nq: int, threads: int):
+    """The oracle (CPU restatement of the reference algorithm) timed on a bounded sample of the same
+    workload: build + query batch on the first `n_proteins` proteins."""
+    import dbindex_b200 as dbi
+    from dbindex_b200 import synth
+    from oracle.oracle_py import Oracle
+    res, off = synth.config_proteome(2, n_proteins)
+    params = dbi.default_params(**CFG2)
+    t0 = time.perf_counter()
+    o = Oracle(params, threads=threads)
+    o.add_proteins(res, off)
+    rc = o.build()
+    t1 = time.perf_counter()
+    assert rc == 0
+    n = o.counts()["n_entries"]
+    m = o.entries(0, min(n, 200_000))["mass"] if n else np.zeros(0)
+    _, _, lo, hi = synth.synth_queries(m, nq, 5)
+    t2 = time.perf_counter()
+    o.query(lo, hi)
+    t3 = time.perf_counter()
+    o.close()
+    return {"entries": n, "build_s": t1 - t0, "query_s": t3 - t2, "nq": nq}
+
+
+def run_reference(args, rank: int, world: int):
+    """--impl reference: the reference's CPU implementation of the path.  The Java reference cannot
+    be built here (no JDK, un-vendored utilities-1.6-SNAPSHOT), so this is the oracle port with every
+    host thread; rank 0 alone runs it."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = args.ref_proteins
+    times, entries, qtimes = [], 0, []
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline(sample, args.queries, threads)
+        if i >= args.warmup:
+            times.append(r["build_s"] + r["query_s"])
+            qtimes.append(r["query_s"])
+        entries = r["entries"]
+    total = sum(times)
+    value = entries * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"first {sample} of the 20000 proteins per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"first {sample} proteins of the workload ({entries} index entries) + "
+                                   f"{args.queries} queries per step; Java reference not buildable here"},
+        "queries": {"value": args.queries * len(qtimes) / max(sum(qtimes), 1e-12), "unit": "queries/s"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank: int, local_rank: int, world: int):
+    import torch
+    import torch.distributed as dist
+    import dbindex_b200 as dbi
+    from dbindex_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = dbi.load_library()
+
+    res, off = workload_inputs(rank, args.proteins)
+    params = dbi.default_params(**CFG2)
+    params.device = local_rank
+    params.profile = 1
+    # a non-default stream: the legacy default stream serialises against every other stream
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    g = dbi.GpuIndex(params)
+    g.set_stream(stream.cuda_stream)
+    g.add_proteins(res, off)
+    g.upload()  # inputs resident in HBM before the timed region
+
+    # query batch: half indexed masses +-5 ppm, half decoys, tol = 10 ppm
+    g.build()
+    n_entries = g.stats()["n_entries"]
+    masses = sample_index_masses(g, n_entries)
+    qmass, qtol, lo, hi = synth.synth_queries(masses, args.queries, 20240602)
+    d_lo = torch.from_numpy(lo).cuda()
+    d_hi = torch.from_numpy(hi).cuda()
+    d_b = torch.empty(args.queries, dtype=torch.int64, device="cuda")
+    d_c = torch.empty(args.queries, dtype=torch.int64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    build_ms, query_ms = [], []
+    dom_ms = dom_launches = 0
+    dom_bytes = 0
+    stage_ms = {}
+    clocks = ClockSampler(local_rank)
+    launches0 = 0
+    for i in range(args.warmup + args.steps):
+        if i == args.warmup:
+            barrier()
+            clocks.start()
+            launches0 = lib.dbi_kernel_launches()
+        g.reset_index()
+        flush.zero_()  # flush L2 between iterations (inputs are 11 MB)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(stream)
+        g.build()
+        e1.record(stream)
+        g.query_device(d_lo.data_ptr(), d_hi.data_ptr(), args.queries, d_b.data_ptr(), d_c.data_ptr())
+        e2.record(stream)
+        torch.cuda.synchronize()
+        if i >= args.warmup:
+            build_ms.append(e0.elapsed_time(e1))
+            query_ms.append(e1.elapsed_time(e2))
+            st = g.stats()
+            dom_ms += st["dom_ms"]; dom_launches += st["dom_launches"]; dom_bytes = st["dom_bytes_per_launch"]
+            for k, v in st["stage_ms"].items():
+                stage_ms[k] = stage_ms.get(k, 0.0) + v
+    barrier()
+    n_launch = lib.dbi_kernel_launches() - launches0
+    clk = clocks.stop()
+    st = g.stats()
+    hits = int(d_c.sum().item())
+
+    # ---- e2e: the user-facing call sequence with HOST buffers, copies inside the timed region ----
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_res, h_off, h_lo, h_hi = pin(res), pin(off.view(np.int64)), pin(lo), pin(hi)
+    h_b = torch.empty(args.queries, dtype=torch.int64).pin_memory()
+    h_c = torch.empty(args.queries, dtype=torch.int64).pin_memory()
+    e2e_ms = []
+    e2e_steps = max(1, min(args.steps, 5))
+    for i in range(1 + e2e_steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        p2 = params.copy()
+        p2.profile = 0
+        g2 = dbi.GpuIndex(p2)
+        g2.set_stream(stream.cuda_stream)
+        g2.add_proteins(h_res.numpy(), h_off.numpy().view(np.uint64))
+        g2.build()
+        g2.query(h_lo.numpy(), h_hi.numpy(), h_b.numpy().view(np.uint64), h_c.numpy().view(np.uint64))
+        b.record(stream)
+        torch.cuda.synchronize()
+        assert g2.stats()["n_entries"] == n_entries and int(h_c.sum()) == hits
+        g2.close()
+        if i >= 1:
+            e2e_ms.append(a.elapsed_time(b))
+    h2d = int(res.nbytes + off.nbytes + lo.nbytes + hi.nbytes + 4352 + 8)
+    d2h = int(2 * 8 * args.queries + 3 * 8 + 4 * 4)
+
+    # ---- reduce over ranks: max time, summed units ----
+    tot_ms = float(sum(build_ms) + sum(query_ms))
+    t = torch.tensor([tot_ms, float(sum(build_ms)), float(sum(query_ms)), float(sum(e2e_ms)) / len(e2e_ms)],
+                     device="cuda", dtype=torch.float64)
+    u = torch.tensor([float(n_entries), float(n_launch)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    tot_ms, b_ms, q_ms, e2e_step_ms = t.tolist()
+    entries_all, launches_all = u.tolist()
+    K = args.steps
+    value = entries_all * K / (tot_ms / 1e3)
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        dom_name = "rs_onesweep_kernel<u64,u64>" if st["dom_kernel"] == 1 else "rs_onesweep_kernel<u64,u32>"
+        achieved = (dom_bytes / 1e9) / ((dom_ms / max(dom_launches, 1)) / 1e3) if dom_launches else None
+        roof = {
+            "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
+            "bytes_per_launch": dom_bytes, "launches": dom_launches, "avg_launch_ms": dom_ms / max(dom_launches, 1),
+            "share_of_build": dom_ms / max(sum(build_ms), 1e-9),
+            "traffic": measured_traffic(dom_name, int(dom_bytes // (32 if st["dom_kernel"] == 1 else 24))),
+        }
+        base = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            r = cpu_baseline(args.ref_proteins, args.queries, threads)
+            base = {"value": r["entries"] / (r["build_s"] + r["query_s"]), "unit": UNIT, "cores": threads, "kind": "port",
+                    "sample": f"first {args.ref_proteins} of the 20000 proteins ({r['entries']} index entries) + "
+                              f"{args.queries} queries, oracle/ (C++ restatement; the Java reference cannot be "
+                              f"built here), build {r['build_s']:.2f} s, queries {r['query_s']:.3f} s",
+                    "queries_per_s": args.queries / max(r["query_s"], 1e-12)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": tot_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "proteins_per_gpu": args.proteins, "residues_per_gpu": int(res.nbytes),
+                       "emitted": st["n_emitted"], "unique": st["n_unique"], "entries_per_gpu": n_entries,
+                       "queries": args.queries, "l2": "flushed between iterations (256 MiB write)",
+                       "parallelism": f"{world} x independent protein shards" if world > 1 else "1 GPU"},
+            "queries": {"value": args.queries * world * K / (q_ms / 1e3), "unit": "queries/s",
+                        "hits_per_batch": hits, "ms_per_batch": q_ms / K},
+            "build_ms": b_ms / K,
+            "stage_ms": {k: v / K for k, v in stage_ms.items() if v > 0},
+            "roofline": roof,
+            "cpu_baseline": base,
+            "e2e": {"value": entries_all / (e2e_step_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_step_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "what": "dbi_create + dbi_add_proteins(host) + dbi_build + dbi_query(host) + dbi_destroy"},
+            "gpu_launches": int(launches_all),
+            "clocks": clk,
+        }
+        print(json.dumps(line), flush=True)
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--proteins", type=int, default=20000, help="proteins per GPU (BASELINE config: 20000)")
+    ap.add_argument("--queries", type=int, default=10000)
+    ap.add_argument("--ref-proteins", type=int, default=2000, help="bounded CPU sample (proteins per step)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -79,6 +79,11 @@ class DbiStats(C.Structure):
         ("stage_launches", C.c_uint32 * DBI_N_STAGES),
         ("sort_bits_base", C.c_uint32),
         ("sort_bits_var", C.c_uint32),
+        ("dom_ms", C.c_float),
+        ("dom_launches", C.c_uint32),
+        ("dom_bytes_per_launch", C.c_uint64),
+        ("dom_kernel", C.c_uint32),
+        ("_pad", C.c_uint32),
     ]
 
 
@@ -132,6 +137,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "dbi_debug_radix_sort": (C.c_int, [vp, vp, vp, C.c_uint64, C.c_int, C.c_int]),
         "dbi_destroy": (None, [vp]),
         "dbi_abi_sizes": (None, [u64p, u64p]),
+        "dbi_release_cached_memory": (C.c_int, [C.c_int]),
         "dbi_last_error": (C.c_char_p, []),
         "dbi_kernel_launches": (C.c_uint64, []),
     }
@@ -156,7 +162,7 @@ ABI_SYMBOLS = [
     "dbi_create", "dbi_set_stream", "dbi_add_proteins", "dbi_upload", "dbi_reset_index", "dbi_build",
     "dbi_stats_get", "dbi_query", "dbi_query_device", "dbi_fetch", "dbi_get_protein", "dbi_calculate_mass",
     "dbi_entry_keys", "dbi_debug_emitted", "dbi_build_from_records", "dbi_debug_radix_sort", "dbi_destroy",
-    "dbi_abi_sizes",
+    "dbi_abi_sizes", "dbi_release_cached_memory",
     "dbi_last_error", "dbi_kernel_launches",
 ]
 
@@ -251,7 +257,8 @@ class GpuIndex:
         st = DbiStats()
         self._check(self.lib.dbi_stats_get(self._h, C.byref(st)))
         d = {k: getattr(st, k) for k in ("n_proteins", "n_residues", "n_emitted", "n_unique", "n_entries",
-                                         "n_hash_retries", "device_bytes", "sort_bits_base", "sort_bits_var")}
+                                         "n_hash_retries", "device_bytes", "sort_bits_base", "sort_bits_var",
+                                         "dom_ms", "dom_launches", "dom_bytes_per_launch", "dom_kernel")}
         d["algo_bytes"] = dict(zip(STAGE_NAMES, list(st.algo_bytes)))
         d["stage_ms"] = dict(zip(STAGE_NAMES, [float(x) for x in st.stage_ms]))
         d["stage_launches"] = dict(zip(STAGE_NAMES, list(st.stage_launches)))

@@ -2,8 +2,11 @@
 // orchestration and query / fetch entry points.  Every device step is one of the
 // hand-written kernels of this directory; there is no CPU fallback.
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -24,25 +27,103 @@ void set_error(const char* fmt, ...) {
 
 namespace {
 
-// Stream-ordered device buffer.  cudaMallocAsync + a never-shrinking pool keeps
-// repeated builds free of cudaMalloc/cudaFree round trips.
+// ---- device memory -----------------------------------------------------------------
+// A process-wide, per-device caching allocator: blocks come from cudaMalloc once and are
+// recycled by size.  Repeated builds (and short-lived handles) then never pay for
+// cudaMalloc / VMM remapping again -- measured: cudaMallocAsync cost 1-6 ms per build in
+// pool re-mapping for the GB-sized variant buffers.  A handle reuses the blocks it freed
+// immediately (same stream, so ordering is implied); they return to the shared cache only
+// after the handle's stream has been synchronised at the end of the API call.
+class DevCache {
+ public:
+  static DevCache& of(int device) {
+    static DevCache caches[64];
+    return caches[device & 63];
+  }
+  void* get(size_t bytes) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      auto it = free_.lower_bound(bytes);
+      if (it != free_.end() && it->first <= bytes + bytes / 4 + 4096) {
+        void* p = it->second;
+        cached_ -= it->first;
+        free_.erase(it);
+        return p;
+      }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation) {  // give the cached blocks back and retry once
+      cudaGetLastError();
+      trim();
+      e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) throw CudaError{e, "cudaMalloc", __FILE__, __LINE__};
+    return p;
+  }
+  void put(void* p, size_t bytes) {
+    std::lock_guard<std::mutex> lk(mu_);
+    free_.emplace(bytes, p);
+    cached_ += bytes;
+  }
+  void trim() {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (auto& kv : free_) cudaFree(kv.second);
+    free_.clear();
+    cached_ = 0;
+  }
+  size_t cached_bytes() {
+    std::lock_guard<std::mutex> lk(mu_);
+    return cached_;
+  }
+
+ private:
+  std::mutex mu_;
+  std::multimap<size_t, void*> free_;
+  size_t cached_ = 0;
+};
+
+// Per-handle front end of the cache.
+struct DevArena {
+  int device = 0;
+  std::multimap<size_t, void*> local;  // freed by this handle, reusable by it right away
+  static size_t round(size_t b) { return b < 512 ? 512 : (b + 511) & ~(size_t)511; }
+  void* get(size_t bytes, size_t* cap) {
+    bytes = round(bytes);
+    auto it = local.lower_bound(bytes);
+    if (it != local.end() && it->first <= bytes + bytes / 4 + 4096) {
+      void* p = it->second;
+      *cap = it->first;
+      local.erase(it);
+      return p;
+    }
+    *cap = bytes;  // blocks handed out by the shared cache may be larger; remember the request
+    return DevCache::of(device).get(bytes);
+  }
+  void put(void* p, size_t cap) { local.emplace(cap, p); }
+  // after the stream is idle: hand everything back to the shared cache
+  void flush() {
+    for (auto& kv : local) DevCache::of(device).put(kv.second, kv.first);
+    local.clear();
+  }
+  ~DevArena() { flush(); }
+};
+
 struct DevBuf {
   void* p = nullptr;
-  size_t bytes = 0;
-  cudaStream_t s = nullptr;
+  size_t bytes = 0;  // capacity handed out
+  DevArena* a = nullptr;
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  void alloc(size_t b, cudaStream_t st) {
+  void alloc(size_t b, DevArena& arena) {
     release();
-    if (b == 0) b = 16;
-    DBI_CUDA(cudaMallocAsync(&p, b, st));
-    bytes = b;
-    s = st;
+    a = &arena;
+    p = arena.get(b, &bytes);
   }
   void release() {
     if (p) {
-      cudaFreeAsync(p, s);
+      a->put(p, bytes);
       p = nullptr;
       bytes = 0;
     }
@@ -50,7 +131,7 @@ struct DevBuf {
   void swap(DevBuf& o) {
     std::swap(p, o.p);
     std::swap(bytes, o.bytes);
-    std::swap(s, o.s);
+    std::swap(a, o.a);
   }
   ~DevBuf() { release(); }
   template <typename T>
@@ -75,6 +156,7 @@ struct dbi_handle {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   std::mutex mu;
+  DevArena arena;  // declared before every DevBuf of the handle: destroyed after them
 
   // host copy of the proteins (ProteinCache)
   std::vector<uint8_t> h_raw;
@@ -97,7 +179,20 @@ struct dbi_handle {
 
   DigestCfg cfg{};
   dbi_stats st{};
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // profiling (params.profile): event pairs recorded on the stream without any extra
+  // synchronisation and resolved after the final sync of the call
+  struct Span { int kind; cudaEvent_t a, b; };
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  std::vector<Span> spans;
+  cudaEvent_t get_event() {
+    if (ev_used == ev_pool.size()) {
+      cudaEvent_t e;
+      DBI_CUDA(cudaEventCreate(&e));
+      ev_pool.push_back(e);
+    }
+    return ev_pool[ev_used++];
+  }
 
   const double* entry_mass() const { return e_mass.p ? e_mass.as<double>() : u_mass.as<double>(); }
   const uint32_t* entry_base() const { return e_base.as<uint32_t>(); }
@@ -106,11 +201,40 @@ struct dbi_handle {
 
 namespace {
 
+// DBI_TRACE=1: host wall-clock marks inside dbi_build, printed to stderr (diagnostic only).
+struct HostTrace {
+  bool on = std::getenv("DBI_TRACE") != nullptr;
+  std::vector<std::pair<const char*, double>> marks;
+  static double now() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  }
+  void mark(const char* what) {
+    if (on) marks.emplace_back(what, now());
+  }
+  void dump() {
+    if (!on || marks.empty()) return;
+    fprintf(stderr, "[dbi trace]");
+    for (size_t i = 1; i < marks.size(); ++i) fprintf(stderr, " %s=%.3f", marks[i].first, marks[i].second - marks[i - 1].second);
+    fprintf(stderr, " total=%.3f ms\n", marks.back().second - marks.front().second);
+    marks.clear();
+  }
+};
+thread_local HostTrace g_trace;
+#define TR(x) g_trace.mark(x)
+
 int fail_cuda(const CudaError& e) {
   set_error("CUDA error %d (%s) at %s:%d: %s", (int)e.e, cudaGetErrorString(e.e), e.file, e.line, e.what);
   cudaGetLastError();  // clear the sticky-free error state
   return e.e == cudaErrorMemoryAllocation ? DBI_ENOMEM : DBI_ECUDA;
 }
+
+// Runs at the end of every API call, after the call's local DevBufs are gone: once the stream
+// is idle the blocks they freed may be shared with other handles.
+struct ArenaFlush {
+  dbi_handle* h;
+  explicit ArenaFlush(dbi_handle* h_) : h(h_) {}
+  ~ArenaFlush();
+};
 
 #define DBI_API_BEGIN(h)                      \
   if (!(h)) {                                 \
@@ -118,6 +242,7 @@ int fail_cuda(const CudaError& e) {
     return DBI_EINVAL;                        \
   }                                           \
   std::lock_guard<std::mutex> _lk((h)->mu);   \
+  ArenaFlush _af(h);                          \
   try {                                       \
     DBI_CUDA(cudaSetDevice((h)->device));
 
@@ -129,26 +254,68 @@ int fail_cuda(const CudaError& e) {
     return DBI_ENOMEM;                           \
   }
 
+constexpr int kSpanDominant = 100;  // span kind of a dominant-kernel launch
+
+ArenaFlush::~ArenaFlush() {
+  if (h->arena.local.empty()) return;
+  cudaStreamSynchronize(h->stream);
+  h->arena.flush();
+}
+
 // CUDA-event stage timer (only when params.profile) + launch accounting.
 struct Stage {
   dbi_handle* h;
   int id;
   uint64_t l0;
+  cudaEvent_t a = nullptr;
   Stage(dbi_handle* h_, int id_) : h(h_), id(id_) {
     l0 = g_kernel_launches.load();
-    if (h->p.profile) cudaEventRecord(h->ev0, h->stream);
+    if (h->p.profile) {
+      a = h->get_event();
+      cudaEventRecord(a, h->stream);
+    }
   }
   ~Stage() {
     h->st.stage_launches[id] += (uint32_t)(g_kernel_launches.load() - l0);
     if (h->p.profile) {
-      cudaEventRecord(h->ev1, h->stream);
-      cudaEventSynchronize(h->ev1);
-      float ms = 0;
-      cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-      h->st.stage_ms[id] += ms;
+      cudaEvent_t b = h->get_event();
+      cudaEventRecord(b, h->stream);
+      h->spans.push_back({id, a, b});
     }
   }
 };
+
+// Brackets every scatter pass of one sort with an event pair.
+struct DomProbe : PassProbe {
+  dbi_handle* h;
+  cudaEvent_t a = nullptr;
+  explicit DomProbe(dbi_handle* h_) : h(h_) {}
+  void before_pass(int) override {
+    a = h->get_event();
+    cudaEventRecord(a, h->stream);
+  }
+  void after_pass(int) override {
+    cudaEvent_t b = h->get_event();
+    cudaEventRecord(b, h->stream);
+    h->spans.push_back({kSpanDominant, a, b});
+  }
+};
+
+// After the stream has been synchronised: turn the recorded spans into stats.
+void resolve_spans(dbi_handle* h) {
+  for (const auto& sp : h->spans) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, sp.a, sp.b) != cudaSuccess) { cudaGetLastError(); continue; }
+    if (sp.kind == kSpanDominant) {
+      h->st.dom_ms += ms;
+      h->st.dom_launches++;
+    } else {
+      h->st.stage_ms[sp.kind] += ms;
+    }
+  }
+  h->spans.clear();
+  h->ev_used = 0;
+}
 
 uint32_t read_err(dbi_handle* h) {
   uint32_t e = 0;
@@ -173,6 +340,8 @@ void free_index(dbi_handle* h) {
   h->e_mass.release(); h->e_base.release(); h->e_pat.release();
   h->k_mass.release(); h->k_gpos.release(); h->k_prot.release(); h->k_len.release();
   h->n_emitted = h->n_unique = h->n_entries = 0;
+  h->spans.clear();
+  h->ev_used = 0;
   const uint64_t np = h->st.n_proteins, nr = h->st.n_residues;
   std::memset(&h->st, 0, sizeof(h->st));
   h->st.n_proteins = np;
@@ -193,9 +362,6 @@ void upload_tables(dbi_handle* h) {
       t.diff[p.mods[i].residue] = p.mods[i].delta;
       t.flags[p.mods[i].residue] |= kFlagDiffMod;
     }
-  h->d_tables.alloc(sizeof(DevTables), h->stream);
-  DBI_CUDA(cudaMemcpyAsync(h->d_tables.p, &t, sizeof(t), cudaMemcpyHostToDevice, h->stream));
-  DBI_CUDA(cudaStreamSynchronize(h->stream));  // `t` is on this stack frame
   double init = 0;  // DBIndexer.java:265-271, same order
   if (p.add_h2o_proton) init += p.h2o_proton;
   init += p.cterm;
@@ -207,6 +373,31 @@ void upload_tables(dbi_handle* h) {
   h->cfg.semi = p.semi ? 1 : 0;
   h->cfg.min_len = p.min_len;
   h->cfg.max_mods = mods ? p.max_mods_per_peptide : 0;
+  h->cfg.mod_hi = 0;
+  h->cfg.mod_lo = 0;
+  h->cfg.n_classes = 0;
+  h->cfg.n_seq = 0;
+  if (mods) {
+    // mod classes = distinct shift values (two residues with the same shift are interchangeable
+    // for the mass); class sequences of length <= K number (C^(K+1)-1)/(C-1)
+    int nc = 0;
+    for (int i = 0; i < 256; ++i)
+      if (t.flags[i] & kFlagDiffMod) {
+        h->cfg.mod_hi = std::max(h->cfg.mod_hi, t.diff[i]);
+        h->cfg.mod_lo = std::min(h->cfg.mod_lo, t.diff[i]);
+        int c = 0;
+        while (c < nc && t.cls_delta[c] != t.diff[i]) ++c;
+        if (c == nc) t.cls_delta[nc++] = t.diff[i];
+        t.cls[i] = (uint8_t)c;
+      }
+    h->cfg.n_classes = nc;
+    uint64_t g = 0, pw = 1;
+    for (int k = 0; k <= p.max_mods_per_peptide; ++k) { g += pw; pw *= (uint64_t)nc; }
+    h->cfg.n_seq = g <= 32 ? (int)g : 0;
+  }
+  h->d_tables.alloc(sizeof(DevTables), h->arena);
+  DBI_CUDA(cudaMemcpyAsync(h->d_tables.p, &t, sizeof(t), cudaMemcpyHostToDevice, h->stream));
+  DBI_CUDA(cudaStreamSynchronize(h->stream));  // `t` is on this stack frame
 }
 
 // H2D of the raw residues + offsets (idempotent).
@@ -214,8 +405,8 @@ void ensure_uploaded(dbi_handle* h) {
   const uint64_t n_res = h->h_raw.size();
   const uint64_t n_prot = h->h_off.size() - 1;
   if (h->up_prot == n_prot && h->up_res == n_res) return;
-  h->d_raw.alloc(n_res, h->stream);
-  h->d_off.alloc((n_prot + 1) * 8, h->stream);
+  h->d_raw.alloc(n_res, h->arena);
+  h->d_off.alloc((n_prot + 1) * 8, h->arena);
   if (n_res) DBI_CUDA(cudaMemcpyAsync(h->d_raw.p, h->h_raw.data(), n_res, cudaMemcpyHostToDevice, h->stream));
   DBI_CUDA(cudaMemcpyAsync(h->d_off.p, h->h_off.data(), (n_prot + 1) * 8, cudaMemcpyHostToDevice, h->stream));
   h->up_prot = n_prot;
@@ -246,8 +437,8 @@ void pack_residues(dbi_handle* h) {
   const uint64_t res_end = n_res + n_prot + 1;
   const uint64_t padded = (res_end + 64 + 15) & ~15ull;
   h->res_end = (uint32_t)res_end;
-  h->d_res.alloc(padded, h->stream);
-  h->d_pstart.alloc(((uint64_t)n_prot + 1) * 4, h->stream);
+  h->d_res.alloc(padded, h->arena);
+  h->d_pstart.alloc(((uint64_t)n_prot + 1) * 4, h->arena);
   DBI_CUDA(cudaMemsetAsync((uint8_t*)h->d_res.p + res_end, 0, padded - res_end, h->stream));
   launch_pack(h->d_raw.as<uint8_t>(), h->d_off.as<uint64_t>(), n_prot, n_res, h->d_res.as<uint8_t>(),
               h->d_pstart.as<uint32_t>(), h->d_err.as<uint32_t>(), h->stream);
@@ -266,7 +457,7 @@ int index_records(dbi_handle* h, DevBuf& r_mass, DevBuf& r_gpos, DevBuf& r_prot,
     return DBI_ERANGE;
   }
   if (N == 0) {
-    h->u_plo.alloc(8, s);
+    h->u_plo.alloc(8, h->arena);
     DBI_CUDA(cudaMemsetAsync(h->u_plo.p, 0, 8, s));
     h->built = true;
     return DBI_OK;
@@ -277,15 +468,17 @@ int index_records(dbi_handle* h, DevBuf& r_mass, DevBuf& r_gpos, DevBuf& r_prot,
 
   DevBuf hash, idx[2], hkey[2], mkey[2], tmp, flags, tile_counts, tile_offs;
   const uint64_t tiles = (N + kScanTile - 1) / kScanTile;
-  hash.alloc(N * 4, s);
-  idx[0].alloc(N * 4, s); idx[1].alloc(N * 4, s);
-  hkey[0].alloc(N * 4, s); hkey[1].alloc(N * 4, s);
-  mkey[0].alloc(N * 8, s); mkey[1].alloc(N * 8, s);
-  tmp.alloc(radix_sort_tmp_bytes(N), s);
-  flags.alloc(N, s);
-  tile_counts.alloc(tiles * 4, s);
-  tile_offs.alloc((tiles + 1) * 8, s);
+  TR("ir_begin");
+  hash.alloc(N * 4, h->arena);
+  idx[0].alloc(N * 4, h->arena); idx[1].alloc(N * 4, h->arena);
+  hkey[0].alloc(N * 4, h->arena); hkey[1].alloc(N * 4, h->arena);
+  mkey[0].alloc(N * 8, h->arena); mkey[1].alloc(N * 8, h->arena);
+  tmp.alloc(radix_sort_tmp_bytes(N), h->arena);
+  flags.alloc(N, h->arena);
+  tile_counts.alloc(tiles * 4, h->arena);
+  tile_offs.alloc((tiles + 1) * 8, h->arena);
 
+  TR("ir_alloc");
   int sorted = 0;
   uint64_t n_unique = 0;
   for (uint32_t attempt = 0;; ++attempt) {
@@ -299,11 +492,21 @@ int index_records(dbi_handle* h, DevBuf& r_mass, DevBuf& r_gpos, DevBuf& r_prot,
       uint32_t* hk[2] = {hkey[0].as<uint32_t>(), hkey[1].as<uint32_t>()};
       uint32_t* ix[2] = {idx[0].as<uint32_t>(), idx[1].as<uint32_t>()};
       const int r1 = radix_sort_pairs<uint32_t, uint32_t>(hk, ix, N, 0, 32, tmp.p, s, nullptr);
+      DomProbe base_probe(h);
+      const bool base_is_dominant = h->p.profile && h->cfg.max_mods == 0;
+      if (base_is_dominant) {  // a retry re-runs the sort: count only the final attempt
+        h->spans.erase(std::remove_if(h->spans.begin(), h->spans.end(),
+                                      [](const dbi_handle::Span& sp) { return sp.kind == kSpanDominant; }),
+                       h->spans.end());
+        h->st.dom_kernel = 0;
+        h->st.dom_bytes_per_launch = N * 24ull;
+      }
       // ... then the exact mass bits (stable), so order = (mass, hash, emission ordinal)
       launch_gather_mass_key(r_mass.as<uint64_t>(), ix[r1], N, base_bits, mkey[0].as<uint64_t>(), s);
       uint64_t* mk[2] = {mkey[0].as<uint64_t>(), mkey[1].as<uint64_t>()};
       uint32_t* ix2[2] = {ix[r1], ix[r1 ^ 1]};
-      const int r2 = radix_sort_pairs<uint64_t, uint32_t>(mk, ix2, N, 0, nbits, tmp.p, s, nullptr);
+      const int r2 = radix_sort_pairs<uint64_t, uint32_t>(mk, ix2, N, 0, nbits, tmp.p, s,
+                                                          base_is_dominant ? &base_probe : nullptr);
       sorted = r2;
       // normalise: sorted keys in mkey[sorted], sorted idx in ix2[sorted]
       if (ix2[r2] != idx[0].as<uint32_t>()) idx[0].swap(idx[1]);
@@ -320,6 +523,7 @@ int index_records(dbi_handle* h, DevBuf& r_mass, DevBuf& r_gpos, DevBuf& r_prot,
       n_unique = read_u64(h, tile_offs.as<uint64_t>() + tiles);
     }
     const uint32_t e = read_err(h);
+    TR("ir_sort+flags+sync");
     if (e & kErrHashCollision) {
       // two different sequences with equal mass bits and equal hash: re-sort with another seed
       h->st.n_hash_retries++;
@@ -338,12 +542,12 @@ int index_records(dbi_handle* h, DevBuf& r_mass, DevBuf& r_gpos, DevBuf& r_prot,
     Stage sg(h, DBI_STAGE_DEDUP);
     h->n_unique = n_unique;
     h->st.n_unique = n_unique;
-    h->u_mass.alloc(n_unique * 8, s);
-    h->u_gpos.alloc(n_unique * 4, s);
-    h->u_prot.alloc(n_unique * 4, s);
-    h->u_len.alloc(n_unique * 2, s);
-    h->u_plo.alloc((n_unique + 1) * 8, s);
-    h->plist.alloc(N * 4, s);
+    h->u_mass.alloc(n_unique * 8, h->arena);
+    h->u_gpos.alloc(n_unique * 4, h->arena);
+    h->u_prot.alloc(n_unique * 4, h->arena);
+    h->u_len.alloc(n_unique * 2, h->arena);
+    h->u_plo.alloc((n_unique + 1) * 8, h->arena);
+    h->plist.alloc(N * 4, h->arena);
     launch_dedup_emit(mkey[sorted].as<uint64_t>(), idx[0].as<uint32_t>(), flags.as<uint8_t>(),
                       tile_offs.as<uint64_t>(), r_gpos.as<uint32_t>(), r_prot.as<uint32_t>(), r_len.as<uint16_t>(), N,
                       base_bits, n_unique, h->u_mass.as<double>(), h->u_gpos.as<uint32_t>(),
@@ -351,6 +555,7 @@ int index_records(dbi_handle* h, DevBuf& r_mass, DevBuf& r_gpos, DevBuf& r_prot,
                       h->plist.as<uint32_t>(), s);
     h->st.algo_bytes[DBI_STAGE_DEDUP] += N * (8 + 4 + 1) + N * (1 + 4 + 4 + 4) + n_unique * (8 + 4 + 4 + 2 + 8 + 10);
   }
+  TR("ir_dedup_emit");
   // free the sort scratch before the (much larger) variant stage
   hash.release(); idx[0].release(); idx[1].release(); hkey[0].release(); hkey[1].release();
   mkey[0].release(); mkey[1].release(); tmp.release(); flags.release(); tile_counts.release(); tile_offs.release();
@@ -363,11 +568,11 @@ int index_records(dbi_handle* h, DevBuf& r_mass, DevBuf& r_gpos, DevBuf& r_prot,
   }
 
   // ---- K5/K6: differential-mod variants of the unique peptides ----
-  const uint64_t utiles = (n_unique + kScanTile - 1) / kScanTile;
+  const uint64_t utiles = (n_unique + kModTile - 1) / kModTile;
   DevBuf counts, ucounts, uoffs;
-  counts.alloc(n_unique * 4, s);
-  ucounts.alloc(utiles * 4, s);
-  uoffs.alloc((utiles + 1) * 8, s);
+  counts.alloc(n_unique * 4, h->arena);
+  ucounts.alloc(utiles * 4, h->arena);
+  uoffs.alloc((utiles + 1) * 8, h->arena);
   uint64_t V = 0;
   {
     Stage sg(h, DBI_STAGE_MOD_COUNT);
@@ -379,10 +584,12 @@ int index_records(dbi_handle* h, DevBuf& r_mass, DevBuf& r_gpos, DevBuf& r_prot,
     h->st.algo_bytes[DBI_STAGE_MOD_COUNT] += n_unique * (8 + 4 + 2 + 4 + 20);
   }
   if (int rc = check_err_bits(read_err(h))) return rc;
+  TR("ir_modcount+sync");
   DevBuf vkey[2], vpay[2], vtmp;
-  vkey[0].alloc(V * 8, s); vkey[1].alloc(V * 8, s);
-  vpay[0].alloc(V * 8, s); vpay[1].alloc(V * 8, s);
-  vtmp.alloc(radix_sort_tmp_bytes(V), s);
+  vkey[0].alloc(V * 8, h->arena); vkey[1].alloc(V * 8, h->arena);
+  vpay[0].alloc(V * 8, h->arena); vpay[1].alloc(V * 8, h->arena);
+  vtmp.alloc(radix_sort_tmp_bytes(V), h->arena);
+  TR("ir_valloc");
   {
     Stage sg(h, DBI_STAGE_MOD_EMIT);
     launch_mod_emit(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_mass.as<double>(),
@@ -390,24 +597,33 @@ int index_records(dbi_handle* h, DevBuf& r_mass, DevBuf& r_gpos, DevBuf& r_prot,
                     uoffs.as<uint64_t>(), base_bits, vkey[0].as<uint64_t>(), vpay[0].as<uint64_t>(), s);
     h->st.algo_bytes[DBI_STAGE_MOD_EMIT] += n_unique * (8 + 4 + 2 + 4 + 20) + V * 16;
   }
-  int vs = 0;
+  TR("ir_modemit");
+  h->e_mass.alloc(V * 8, h->arena);
+  h->e_base.alloc(V * 4, h->arena);
+  h->e_pat.alloc(V * 4, h->arena);
+  TR("ir_ealloc");
   {
+    // the last pass of the sort writes the final entry arrays (mass, base id, mod pattern)
     Stage sg(h, DBI_STAGE_SORT_VAR);
     uint64_t* vk[2] = {vkey[0].as<uint64_t>(), vkey[1].as<uint64_t>()};
     uint64_t* vp[2] = {vpay[0].as<uint64_t>(), vpay[1].as<uint64_t>()};
-    vs = radix_sort_pairs<uint64_t, uint64_t>(vk, vp, V, 0, nbits, vtmp.p, s, nullptr);
+    DomProbe var_probe(h);
+    if (h->p.profile) {
+      h->st.dom_kernel = 1;
+      h->st.dom_bytes_per_launch = V * 32ull;
+    }
+    SplitOut<uint64_t> split{h->e_mass.as<uint64_t>(), base_bits, h->e_base.as<uint32_t>(), h->e_pat.as<uint32_t>()};
+    const int passes = (nbits + 7) / 8;
+    if (V > 1 && passes > 0) {
+      radix_sort_pairs<uint64_t, uint64_t>(vk, vp, V, 0, nbits, vtmp.p, s, h->p.profile ? &var_probe : nullptr, &split);
+    } else {  // nothing to sort: plain split
+      launch_split_entries(vk[0], vp[0], V, base_bits, h->e_mass.as<double>(), h->e_base.as<uint32_t>(),
+                           h->e_pat.as<uint32_t>(), s);
+    }
     h->st.sort_bits_var = (uint32_t)nbits;
-    h->st.algo_bytes[DBI_STAGE_SORT_VAR] += V * 8 + V * 32ull * ((nbits + 7) / 8);
+    h->st.algo_bytes[DBI_STAGE_SORT_VAR] += V * 8 + V * 32ull * passes;
   }
-  {
-    Stage sg(h, DBI_STAGE_GATHER_VAR);
-    h->e_mass.alloc(V * 8, s);
-    h->e_base.alloc(V * 4, s);
-    h->e_pat.alloc(V * 4, s);
-    launch_split_entries(vkey[vs].as<uint64_t>(), vpay[vs].as<uint64_t>(), V, base_bits, h->e_mass.as<double>(),
-                         h->e_base.as<uint32_t>(), h->e_pat.as<uint32_t>(), s);
-    h->st.algo_bytes[DBI_STAGE_GATHER_VAR] += V * 32;
-  }
+  TR("ir_sortvar");
   h->n_entries = V;
   h->st.n_entries = V;
   h->built = true;
@@ -415,6 +631,7 @@ int index_records(dbi_handle* h, DevBuf& r_mass, DevBuf& r_gpos, DevBuf& r_prot,
 }
 
 void finish_stats(dbi_handle* h) {
+  resolve_spans(h);
   h->st.device_bytes = h->d_res.bytes + h->d_pstart.bytes + h->u_mass.bytes + h->u_gpos.bytes + h->u_prot.bytes +
                        h->u_len.bytes + h->u_plo.bytes + h->plist.bytes + h->e_mass.bytes + h->e_base.bytes +
                        h->e_pat.bytes;
@@ -468,13 +685,8 @@ int dbi_create(const dbi_params* params, dbi_handle** out) {
     DBI_CUDA(cudaSetDevice(h->device));
     DBI_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
-    DBI_CUDA(cudaEventCreate(&h->ev0));
-    DBI_CUDA(cudaEventCreate(&h->ev1));
-    cudaMemPool_t pool;
-    DBI_CUDA(cudaDeviceGetDefaultMemPool(&pool, h->device));
-    uint64_t thr = UINT64_MAX;
-    DBI_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-    h->d_err.alloc(4, h->stream);
+    h->arena.device = h->device;
+    h->d_err.alloc(4, h->arena);
     DBI_CUDA(cudaMemsetAsync(h->d_err.p, 0, 4, h->stream));
     upload_tables(h);
     *out = h;
@@ -552,16 +764,18 @@ int dbi_build(dbi_handle* h) {
     return DBI_EALREADY;
   }
   cudaStream_t s = h->stream;
+  TR("begin");
   ensure_uploaded(h);
   const uint32_t zero = 0;
   DBI_CUDA(cudaMemcpyAsync(h->d_err.p, &zero, 4, cudaMemcpyHostToDevice, s));
   pack_residues(h);
+  TR("pack");
 
   const uint32_t n_prot = (uint32_t)(h->h_off.size() - 1);
   const uint64_t tiles = ((uint64_t)h->res_end + kDigestTile - 1) / kDigestTile;
   DevBuf tile_counts, tile_offs;
-  tile_counts.alloc(tiles * 4, s);
-  tile_offs.alloc((tiles + 1) * 8, s);
+  tile_counts.alloc(tiles * 4, h->arena);
+  tile_offs.alloc((tiles + 1) * 8, h->arena);
   uint64_t N = 0;
   {
     Stage sg(h, DBI_STAGE_DIGEST_COUNT);
@@ -575,11 +789,12 @@ int dbi_build(dbi_handle* h) {
     free_index(h);
     return rc;
   }
+  TR("count+sync");
   DevBuf r_mass, r_gpos, r_prot, r_len;
-  r_mass.alloc(N * 8, s);
-  r_gpos.alloc(N * 4, s);
-  r_prot.alloc(N * 4, s);
-  r_len.alloc(N * 2, s);
+  r_mass.alloc(N * 8, h->arena);
+  r_gpos.alloc(N * 4, h->arena);
+  r_prot.alloc(N * 4, h->arena);
+  r_len.alloc(N * 2, h->arena);
   {
     Stage sg(h, DBI_STAGE_DIGEST_EMIT);
     launch_digest_emit(h->d_res.as<uint8_t>(), h->res_end, h->d_tables.as<DevTables>(), h->cfg,
@@ -589,7 +804,9 @@ int dbi_build(dbi_handle* h) {
   }
   tile_counts.release();
   tile_offs.release();
+  TR("emit");
   int rc = index_records(h, r_mass, r_gpos, r_prot, r_len, N, h->p.min_mass, h->p.max_mass);
+  TR("index_records");
   if (rc == DBI_OK)
     if (int rc2 = check_err_bits(read_err(h))) rc = rc2;
   if (rc != DBI_OK) {
@@ -601,6 +818,8 @@ int dbi_build(dbi_handle* h) {
   }
   DBI_CUDA(cudaStreamSynchronize(s));
   finish_stats(h);
+  TR("final_sync");
+  g_trace.dump();
   return DBI_OK;
   DBI_API_END
 }
@@ -634,10 +853,10 @@ int dbi_build_from_records(dbi_handle* h, const double* mass, const uint32_t* pr
   DBI_CUDA(cudaMemcpyAsync(h->d_err.p, &zero, 4, cudaMemcpyHostToDevice, s));
   pack_residues(h);
   DevBuf r_mass, r_gpos, r_prot, r_len;
-  r_mass.alloc(n * 8, s);
-  r_gpos.alloc(n * 4, s);
-  r_prot.alloc(n * 4, s);
-  r_len.alloc(n * 2, s);
+  r_mass.alloc(n * 8, h->arena);
+  r_gpos.alloc(n * 4, h->arena);
+  r_prot.alloc(n * 4, h->arena);
+  r_len.alloc(n * 2, h->arena);
   if (n) {
     DBI_CUDA(cudaMemcpyAsync(r_mass.p, mass, n * 8, cudaMemcpyHostToDevice, s));
     DBI_CUDA(cudaMemcpyAsync(r_gpos.p, gpos.data(), n * 4, cudaMemcpyHostToDevice, s));
@@ -704,7 +923,7 @@ int dbi_query(dbi_handle* h, const double* lo, const double* hi, uint64_t nq, ui
   }
   cudaStream_t s = h->stream;
   DevBuf io;  // lo | hi | begin | count
-  io.alloc(nq * 32, s);
+  io.alloc(nq * 32, h->arena);
   double* d_lo = io.as<double>();
   double* d_hi = d_lo + nq;
   uint64_t* d_b = (uint64_t*)(d_hi + nq);
@@ -719,6 +938,7 @@ int dbi_query(dbi_handle* h, const double* lo, const double* hi, uint64_t nq, ui
   DBI_CUDA(cudaMemcpyAsync(hit_begin, d_b, nq * 8, cudaMemcpyDeviceToHost, s));
   DBI_CUDA(cudaMemcpyAsync(hit_count, d_c, nq * 8, cudaMemcpyDeviceToHost, s));
   DBI_CUDA(cudaStreamSynchronize(s));
+  resolve_spans(h);
   return DBI_OK;
   DBI_API_END
 }
@@ -744,9 +964,9 @@ int dbi_fetch(dbi_handle* h, uint64_t begin, uint64_t count, double* mass, uint3
   cudaStream_t s = h->stream;
   const uint64_t tiles = (count + kScanTile - 1) / kScanTile;
   DevBuf sizes, tcnt, toff;
-  sizes.alloc(count * 4, s);
-  tcnt.alloc(tiles * 4, s);
-  toff.alloc((tiles + 1) * 8, s);
+  sizes.alloc(count * 4, h->arena);
+  tcnt.alloc(tiles * 4, h->arena);
+  toff.alloc((tiles + 1) * 8, h->arena);
   uint64_t total_ids = 0;
   {
     Stage sg(h, DBI_STAGE_FETCH);
@@ -762,13 +982,13 @@ int dbi_fetch(dbi_handle* h, uint64_t begin, uint64_t count, double* mass, uint3
     return DBI_ERANGE;
   }
   DevBuf o_mass, o_prot, o_off, o_len, o_pat, o_lo, o_ids;
-  if (mass) o_mass.alloc(count * 8, s);
-  if (first_prot) o_prot.alloc(count * 4, s);
-  if (first_off) o_off.alloc(count * 4, s);
-  if (len) o_len.alloc(count * 2, s);
-  if (modpat) o_pat.alloc(count * 4, s);
-  if (prot_list_off) o_lo.alloc((count + 1) * 8, s);
-  if (want_ids) o_ids.alloc(total_ids * 4, s);
+  if (mass) o_mass.alloc(count * 8, h->arena);
+  if (first_prot) o_prot.alloc(count * 4, h->arena);
+  if (first_off) o_off.alloc(count * 4, h->arena);
+  if (len) o_len.alloc(count * 2, h->arena);
+  if (modpat) o_pat.alloc(count * 4, h->arena);
+  if (prot_list_off) o_lo.alloc((count + 1) * 8, h->arena);
+  if (want_ids) o_ids.alloc(total_ids * 4, h->arena);
   {
     Stage sg(h, DBI_STAGE_FETCH);
     launch_fetch_gather(h->entry_mass(), h->entry_base(), h->entry_pat(), h->u_gpos.as<uint32_t>(),
@@ -786,6 +1006,7 @@ int dbi_fetch(dbi_handle* h, uint64_t begin, uint64_t count, double* mass, uint3
   if (prot_list_off) DBI_CUDA(cudaMemcpyAsync(prot_list_off, o_lo.p, (count + 1) * 8, cudaMemcpyDeviceToHost, s));
   if (want_ids && total_ids) DBI_CUDA(cudaMemcpyAsync(prot_ids, o_ids.p, total_ids * 4, cudaMemcpyDeviceToHost, s));
   DBI_CUDA(cudaStreamSynchronize(s));
+  resolve_spans(h);
   return DBI_OK;
   DBI_API_END
 }
@@ -836,9 +1057,9 @@ int dbi_entry_keys(dbi_handle* h, int32_t* keys, uint64_t capacity, uint64_t* n_
   cudaStream_t s = h->stream;
   const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
   DevBuf flags, tcnt, toff, out;
-  flags.alloc(n, s);
-  tcnt.alloc(tiles * 4, s);
-  toff.alloc((tiles + 1) * 8, s);
+  flags.alloc(n, h->arena);
+  tcnt.alloc(tiles * 4, h->arena);
+  toff.alloc((tiles + 1) * 8, h->arena);
   Stage sg(h, DBI_STAGE_OTHER);
   launch_key_flags(h->entry_mass(), n, (double)h->p.mass_group_factor, flags.as<uint8_t>(), tcnt.as<uint32_t>(), s);
   launch_scan_u32_to_u64(tcnt.as<uint32_t>(), tiles, toff.as<uint64_t>(), s);
@@ -849,7 +1070,7 @@ int dbi_entry_keys(dbi_handle* h, int32_t* keys, uint64_t capacity, uint64_t* n_
     set_error("keys capacity %llu < %llu", (unsigned long long)capacity, (unsigned long long)nk);
     return DBI_ERANGE;
   }
-  out.alloc(nk * 4, s);
+  out.alloc(nk * 4, h->arena);
   launch_key_emit(h->entry_mass(), n, (double)h->p.mass_group_factor, flags.as<uint8_t>(), toff.as<uint64_t>(),
                   out.as<int32_t>(), s);
   DBI_CUDA(cudaMemcpyAsync(keys, out.p, nk * 4, cudaMemcpyDeviceToHost, s));
@@ -899,10 +1120,10 @@ int dbi_debug_radix_sort(dbi_handle* h, uint64_t* keys, uint64_t* vals, uint64_t
   cudaStream_t s = h->stream;
   DevBuf k[2], v[2], tmp;
   for (int i = 0; i < 2; ++i) {
-    k[i].alloc(n * 8, s);
-    v[i].alloc(n * 8, s);
+    k[i].alloc(n * 8, h->arena);
+    v[i].alloc(n * 8, h->arena);
   }
-  tmp.alloc(radix_sort_tmp_bytes(n), s);
+  tmp.alloc(radix_sort_tmp_bytes(n), h->arena);
   DBI_CUDA(cudaMemcpyAsync(k[0].p, keys, n * 8, cudaMemcpyHostToDevice, s));
   DBI_CUDA(cudaMemcpyAsync(v[0].p, vals, n * 8, cudaMemcpyHostToDevice, s));
   uint64_t* kk[2] = {k[0].as<uint64_t>(), k[1].as<uint64_t>()};
@@ -925,10 +1146,24 @@ void dbi_destroy(dbi_handle* h) {
   h->d_tables.release();
   h->d_err.release();
   cudaStreamSynchronize(h->stream);
-  if (h->ev0) cudaEventDestroy(h->ev0);
-  if (h->ev1) cudaEventDestroy(h->ev1);
+  h->arena.flush();
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
+}
+
+int dbi_release_cached_memory(int device) {
+  if (device < 0 || device >= 64) {
+    set_error("bad device ordinal %d", device);
+    return DBI_EINVAL;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("no such CUDA device %d", device);
+    return DBI_ECUDA;
+  }
+  DevCache::of(device).trim();
+  return DBI_OK;
 }
 
 const char* dbi_last_error(void) { return t_err; }

@@ -9,6 +9,8 @@ struct DevTables {
   double mass[256];   // AssignMass.getMass(c), static mods included
   double diff[256];   // DiffModification.getDiffModMass(c)
   uint8_t flags[256]; // kFlagEnzyme | kFlagNocut | kFlagDiffMod
+  uint8_t cls[256];   // mod class of a residue = index of its shift among the distinct shifts
+  double cls_delta[16]; // shift of each class
 };
 
 // Scalar digestion parameters, passed by value.
@@ -20,10 +22,15 @@ struct DigestCfg {
   int32_t semi;
   int32_t min_len;
   int32_t max_mods;  // 0 = no differential mods
+  double mod_hi;     // max(0, largest shift): upper bound of one mod's mass change
+  double mod_lo;     // min(0, smallest shift)
+  int32_t n_classes; // distinct shift values
+  int32_t n_seq;     // class sequences of length <= max_mods: (C^(K+1)-1)/(C-1); 0 if > 32
 };
 
 constexpr int kDigestTile = 2048;   // start positions per CTA
 constexpr int kScanTile = 4096;     // elements per tile of the generic scans
+constexpr int kModTile = 256;       // base peptides per CTA of the mod kernels (heavy peptides are clustered)
 
 // K1: residues + offsets -> padded buffer res[] (0 separator before, between and
 // after proteins) and pstart[p] = position of protein p's first residue.

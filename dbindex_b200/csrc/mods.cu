@@ -11,73 +11,154 @@
 //     lexicographically by site; k = 0 (unmodified) is always present;
 //   * mass = base mass, then + shift per chosen site left to right (IEEE double);
 //   * the mass gate min <= m <= max is re-applied to every modified variant.
-// Two-pass count / scan / emit like the digestion.
+//
+// Two-pass count / scan / emit.  One WARP per base peptide: the lanes find the
+// sites with a ballot, then each lane takes variant ranks lane, lane+32, ... and
+// un-ranks them (combinatorial number system) so that consecutive lanes write
+// consecutive output slots -- coalesced 8-byte stores, no per-thread serial runs.
+// The count is closed-form (sum of binomials) whenever no variant of the peptide can
+// reach a mass gate, which is the case for all but the heaviest few percent.
 #include "kernels.cuh"
 
 namespace dbi {
 namespace {
 
 constexpr int MD_THREADS = 256;
-constexpr int MD_IPT = kScanTile / MD_THREADS;
+constexpr int MD_WARPS = MD_THREADS / 32;
+constexpr int MD_PER_WARP = kModTile / MD_WARPS;  // bases per warp per tile
 constexpr int MD_MAX_SITES = DBI_MAX_MOD_POS + 1;  // positions 0..254
 
 struct ModTables {
   double diff[256];
   uint8_t flags[256];
+  uint8_t cls[256];
+  double cls_delta[16];
+};
+
+struct WarpSites {
+  uint8_t pos[256];
+  uint8_t res[256];
 };
 
 __device__ __forceinline__ void load_mod_tables(ModTables& mt, const DevTables* __restrict__ tb) {
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     mt.diff[i] = tb->diff[i];
     mt.flags[i] = tb->flags[i];
+    mt.cls[i] = tb->cls[i];
+    if (i < 16) mt.cls_delta[i] = tb->cls_delta[i];
   }
 }
 
-// Collect eligible site positions of the peptide at res[g .. g+len).  Returns the
-// number of sites; *bad is set if a site lies beyond DBI_MAX_MOD_POS.
-__device__ __forceinline__ int collect_sites(const uint8_t* __restrict__ res, uint32_t g, uint32_t len,
-                                             const ModTables& mt, uint8_t* sites, bool* bad) {
+// Heaviest peptides first: the bases are mass-sorted and the variant count grows like the
+// cube of the site count, so the last tiles carry orders of magnitude more work.
+__device__ __forceinline__ uint32_t mod_tile() { return gridDim.x - 1 - blockIdx.x; }
+
+// Gated count of one peptide with one lane per class SEQUENCE (n_seq <= 32).  The variant mass
+// depends only on the sequence of shift classes along the chosen sites, so
+//   #passing = sum over sequences s of [gate(f_s(base))] * #(occurrences of s as a subsequence
+//              of the peptide's site-class string),
+// and the occurrence counts follow from one pass over the sites: a site of class c extends every
+// sequence's parent (heap numbering: children of v are v*C + c + 1).
+__device__ __forceinline__ uint32_t warp_gated_count(uint32_t n, double base_mass, const WarpSites& ws,
+                                                     const ModTables& mt, const DigestCfg& cfg) {
+  const unsigned v = lane_id();
+  const int C = cfg.n_classes;
+  const bool active = (int)v < cfg.n_seq;
+  // this lane's sequence: depth, last class, parent, and the mass it produces
+  int depth = 0;
+  double val = base_mass;
+  {
+    int cl[DBI_MAX_MODS_PER_PEP];
+    uint32_t x = v;
+    while (active && x > 0) { cl[depth++] = (int)((x - 1) % C); x = (x - 1) / C; }
+    for (int i = depth - 1; i >= 0; --i) val = __dadd_rn(val, mt.cls_delta[cl[i]]);  // first chosen site first
+  }
+  const int last = (active && v > 0) ? (int)((v - 1) % C) : -1;
+  const int parent = (active && v > 0) ? (int)((v - 1) / C) : 0;
+  uint32_t cnt = (v == 0) ? 1u : 0u;
+  for (uint32_t j = 0; j < n; ++j) {
+    const int c = mt.cls[ws.res[j]];
+    const uint32_t up = __shfl_sync(0xffffffffu, cnt, parent);  // parent's count BEFORE this site
+    if (last == c) cnt += up;
+  }
+  const bool pass = active && (v == 0 || (val >= cfg.min_mass && val <= cfg.max_mass));
+  uint32_t tot = pass ? cnt : 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  return tot;
+}
+
+// C(m, j) for j <= 4, m <= 255
+__device__ __forceinline__ uint32_t binom(uint32_t m, int j) {
+  switch (j) {
+    case 0: return 1u;
+    case 1: return m;
+    case 2: return m < 2 ? 0u : m * (m - 1) / 2;
+    case 3: return m < 3 ? 0u : m * (m - 1) * (m - 2) / 6;
+    default: return m < 4 ? 0u : (uint32_t)((uint64_t)m * (m - 1) * (m - 2) * (m - 3) / 24);
+  }
+}
+
+// number of subsets of size <= K of n sites
+__device__ __forceinline__ uint32_t total_variants(uint32_t n, int K) {
+  uint32_t t = 0;
+  for (int k = 0; k <= K; ++k) t += binom(n, k);
+  return t;
+}
+
+// Whole warp: eligible sites of the peptide res[g .. g+len) into ws (positions ascending).
+// Returns the number of sites (<= 255); *bad is set if one lies beyond DBI_MAX_MOD_POS.
+__device__ __forceinline__ int warp_collect_sites(const uint8_t* __restrict__ res, uint32_t g, uint32_t len,
+                                                  const ModTables& mt, WarpSites& ws, bool* bad) {
+  const unsigned l = lane_id();
   int n = 0;
-  for (uint32_t i = 0; i < len; ++i) {
-    if (mt.flags[ld_res(res, g + i)] & kFlagDiffMod) {
-      if (i > DBI_MAX_MOD_POS) { *bad = true; break; }
-      sites[n++] = (uint8_t)i;
+  for (uint32_t b = 0; b < len; b += 32) {
+    const uint32_t i = b + l;
+    const uint8_t c = (i < len) ? ld_res(res, g + i) : (uint8_t)0;
+    const bool is = (i < len) && (mt.flags[c] & kFlagDiffMod);
+    const unsigned m = __ballot_sync(0xffffffffu, is);
+    if (is) {
+      if (i > DBI_MAX_MOD_POS) {
+        *bad = true;
+      } else {
+        const int slot = n + __popc(m & lanemask_lt());
+        ws.pos[slot] = (uint8_t)i;
+        ws.res[slot] = c;
+      }
     }
+    n += __popc(m);
   }
-  return n;
+  *bad = __any_sync(0xffffffffu, *bad);  // warp-uniform verdict (also orders the smem writes)
+  return n > MD_MAX_SITES ? MD_MAX_SITES : n;
 }
 
-// Enumerate the modified variants (k >= 1) in SPEC order; F(mass, pattern) per variant
-// that passes the mass gate.  Returns how many passed.
-template <typename F>
-__device__ __forceinline__ uint32_t enumerate_variants(const uint8_t* __restrict__ res, uint32_t g, double base_mass,
-                                                       const uint8_t* sites, int n, const ModTables& mt,
-                                                       const DigestCfg& cfg, F&& f) {
-  uint32_t count = 0;
-  int idx[DBI_MAX_MODS_PER_PEP];
-  const int K = cfg.max_mods;
-  for (int k = 1; k <= K && k <= n; ++k) {
-    for (int i = 0; i < k; ++i) idx[i] = i;
-    while (true) {
-      double m = base_mass;
-      uint32_t pat = 0;
-      for (int i = 0; i < k; ++i) {
-        const uint32_t p = sites[idx[i]];
-        m = __dadd_rn(m, mt.diff[ld_res(res, g + p)]);
-        pat |= (p + 1) << (8 * i);
-      }
-      if (m >= cfg.min_mass && m <= cfg.max_mass) {
-        f(m, pat);
-        ++count;
-      }
-      int i = k - 1;
-      while (i >= 0 && idx[i] == n - k + i) --i;
-      if (i < 0) break;
-      ++idx[i];
-      for (int j = i + 1; j < k; ++j) idx[j] = idx[j - 1] + 1;
-    }
+// Variant of global rank r (0 = unmodified; then k = 1, 2, ... each in lexicographic order):
+// mass and mod pattern.
+__device__ __forceinline__ void decode_variant(uint32_t r, uint32_t n, int K, double base_mass, const WarpSites& ws,
+                                               const ModTables& mt, double* mass, uint32_t* pat) {
+  int k = 0;
+  for (; k <= K; ++k) {
+    const uint32_t c = binom(n, k);
+    if (r < c) break;
+    r -= c;
   }
-  return count;
+  double m = base_mass;
+  uint32_t p = 0;
+  uint32_t x = 0;  // next candidate site ordinal
+  for (int i = 0; i < k; ++i) {
+    // subsets whose i-th element is x: C(n-1-x, k-1-i)
+    while (true) {
+      const uint32_t c = binom(n - 1 - x, k - 1 - i);
+      if (r < c) break;
+      r -= c;
+      ++x;
+    }
+    m = __dadd_rn(m, mt.diff[ws.res[x]]);  // left to right
+    p |= ((uint32_t)ws.pos[x] + 1u) << (8 * i);
+    ++x;
+  }
+  *mass = m;
+  *pat = p;
 }
 
 __global__ void __launch_bounds__(MD_THREADS)
@@ -86,26 +167,56 @@ __global__ void __launch_bounds__(MD_THREADS)
                      const uint16_t* __restrict__ u_len, uint64_t n_unique, uint32_t* __restrict__ counts,
                      uint32_t* __restrict__ tile_counts, uint32_t* err) {
   __shared__ ModTables mt;
-  __shared__ uint32_t scratch[MD_THREADS / 32 + 1];
+  __shared__ WarpSites wsites[MD_WARPS];
+  __shared__ uint32_t wsum[MD_WARPS];
   load_mod_tables(mt, tb);
   __syncthreads();
-  const uint64_t tile_base = (uint64_t)blockIdx.x * kScanTile;
+  const int w = threadIdx.x >> 5;
+  const unsigned l = lane_id();
+  WarpSites& ws = wsites[w];
+  const uint64_t u0 = (uint64_t)mod_tile() * kModTile + (uint64_t)w * MD_PER_WARP;
+  const int K = cfg.max_mods;
   uint32_t sum = 0;
-  uint8_t sites[MD_MAX_SITES];
-  for (int k = 0; k < MD_IPT; ++k) {
-    const uint64_t u = tile_base + (uint64_t)k * MD_THREADS + threadIdx.x;
+  for (int q = 0; q < MD_PER_WARP; ++q) {
+    const uint64_t u = u0 + q;
     if (u >= n_unique) break;
+    const double bm = u_mass[u];
     bool bad = false;
-    const uint32_t g = u_gpos[u];
-    const int n = collect_sites(res, g, u_len[u], mt, sites, &bad);
-    if (bad) atomicOr(err, kErrModPos);
-    const uint32_t c = 1u + enumerate_variants(res, g, u_mass[u], sites, n, mt, cfg, [](double, uint32_t) {});
-    counts[u] = c;
+    const uint32_t n = (uint32_t)warp_collect_sites(res, u_gpos[u], u_len[u], mt, ws, &bad);
+    if (bad && l == 0) atomicOr(err, kErrModPos);
+    const int kk = K < (int)n ? K : (int)n;
+    const uint32_t total = total_variants(n, kk);
+    uint32_t c;
+    // no variant can reach a gate: every subset counts
+    if (bm + kk * cfg.mod_hi <= cfg.max_mass - 1e-6 && bm + kk * cfg.mod_lo >= cfg.min_mass + 1e-6) {
+      c = total;
+    } else if (cfg.n_seq > 0) {
+      c = warp_gated_count(n, bm, ws, mt, cfg);
+    } else {
+      c = 0;
+      for (uint32_t r0 = 0; r0 < total; r0 += 32) {
+        const uint32_t r = r0 + l;
+        bool pass = false;
+        if (r < total) {
+          double m;
+          uint32_t pat;
+          decode_variant(r, n, kk, bm, ws, mt, &m, &pat);
+          pass = (r == 0) || (m >= cfg.min_mass && m <= cfg.max_mass);
+        }
+        c += __popc(__ballot_sync(0xffffffffu, pass));
+      }
+    }
+    if (l == 0) counts[u] = c;
     sum += c;
+    __syncwarp();
   }
-  uint32_t total;
-  block_exclusive_sum<uint32_t, MD_THREADS>(sum, scratch, &total);
-  if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+  if (l == 0) wsum[w] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int i = 0; i < MD_WARPS; ++i) t += wsum[i];
+    tile_counts[mod_tile()] = t;
+  }
 }
 
 __global__ void __launch_bounds__(MD_THREADS)
@@ -115,37 +226,65 @@ __global__ void __launch_bounds__(MD_THREADS)
                     const uint64_t* __restrict__ tile_offs, uint64_t base_bits, uint64_t* __restrict__ v_key,
                     uint64_t* __restrict__ v_payload) {
   __shared__ ModTables mt;
-  __shared__ uint32_t scratch[MD_THREADS / 32 + 1];
+  __shared__ WarpSites wsites[MD_WARPS];
+  __shared__ uint32_t wsum[MD_WARPS];
   load_mod_tables(mt, tb);
+  const int w = threadIdx.x >> 5;
+  const unsigned l = lane_id();
+  WarpSites& ws = wsites[w];
+  const uint64_t u0 = (uint64_t)mod_tile() * kModTile + (uint64_t)w * MD_PER_WARP;
+  // output offset of this warp's first base: tile offset + counts of the earlier warps' bases
+  uint32_t part = 0;
+  for (int q = l; q < MD_PER_WARP; q += 32) {
+    const uint64_t u = u0 + q;
+    if (u < n_unique) part += counts[u];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (l == 0) wsum[w] = part;
   __syncthreads();
-  const uint64_t tile_base = (uint64_t)blockIdx.x * kScanTile;
-  uint64_t running = tile_offs[blockIdx.x];
-  uint8_t sites[MD_MAX_SITES];
-  for (int k = 0; k < MD_IPT; ++k) {
-    const uint64_t u = tile_base + (uint64_t)k * MD_THREADS + threadIdx.x;
-    const bool valid = u < n_unique;
-    const uint32_t c = valid ? counts[u] : 0u;
-    uint32_t total;
-    const uint32_t ex = block_exclusive_sum<uint32_t, MD_THREADS>(c, scratch, &total);
-    if (valid) {
-      uint64_t o = running + ex;
-      const double bm = u_mass[u];
-      const uint32_t g = u_gpos[u];
-      // k = 0: the unmodified peptide
-      v_key[o] = (uint64_t)__double_as_longlong(bm) - base_bits;
-      v_payload[o] = u << 32;
-      ++o;
-      if (c > 1) {
-        bool bad = false;
-        const int n = collect_sites(res, g, u_len[u], mt, sites, &bad);
-        enumerate_variants(res, g, bm, sites, n, mt, cfg, [&](double m, uint32_t pat) {
-          v_key[o] = (uint64_t)__double_as_longlong(m) - base_bits;
-          v_payload[o] = (u << 32) | pat;
-          ++o;
-        });
+  uint64_t out = tile_offs[mod_tile()];
+  for (int i = 0; i < w; ++i) out += wsum[i];
+
+  const int K = cfg.max_mods;
+  for (int q = 0; q < MD_PER_WARP; ++q) {
+    const uint64_t u = u0 + q;
+    if (u >= n_unique) break;
+    const uint32_t cnt = counts[u];
+    const double bm = u_mass[u];
+    if (cnt == 1) {  // only the unmodified peptide
+      if (l == 0) {
+        v_key[out] = (uint64_t)__double_as_longlong(bm) - base_bits;
+        v_payload[out] = u << 32;
       }
+      out += 1;
+      continue;
     }
-    running += total;
+    bool bad = false;
+    const uint32_t n = (uint32_t)warp_collect_sites(res, u_gpos[u], u_len[u], mt, ws, &bad);
+    const int kk = K < (int)n ? K : (int)n;
+    const uint32_t total = total_variants(n, kk);
+    const bool gated = cnt != total;
+    uint64_t o = out;
+    for (uint32_t r0 = 0; r0 < total; r0 += 32) {
+      const uint32_t r = r0 + l;
+      bool pass = false;
+      double m = bm;
+      uint32_t pat = 0;
+      if (r < total) {
+        decode_variant(r, n, kk, bm, ws, mt, &m, &pat);
+        pass = !gated || r == 0 || (m >= cfg.min_mass && m <= cfg.max_mass);
+      }
+      const unsigned pm = __ballot_sync(0xffffffffu, pass);
+      if (pass) {
+        const uint64_t slot = o + __popc(pm & lanemask_lt());
+        v_key[slot] = (uint64_t)__double_as_longlong(m) - base_bits;
+        v_payload[slot] = (u << 32) | pat;
+      }
+      o += __popc(pm);
+    }
+    out += cnt;
+    __syncwarp();
   }
 }
 
@@ -167,7 +306,7 @@ void launch_mod_count(const uint8_t* d_res, const DevTables* d_tb, const DigestC
                       const uint32_t* u_gpos, const uint16_t* u_len, uint64_t n_unique, uint32_t* counts,
                       uint32_t* tile_counts, uint32_t* d_err, cudaStream_t s) {
   if (n_unique == 0) return;
-  const unsigned tiles = (unsigned)((n_unique + kScanTile - 1) / kScanTile);
+  const unsigned tiles = (unsigned)((n_unique + kModTile - 1) / kModTile);
   DBI_LAUNCH(mod_count_kernel, tiles, MD_THREADS, 0, s, d_res, d_tb, cfg, u_mass, u_gpos, u_len, n_unique, counts,
              tile_counts, d_err);
 }
@@ -177,7 +316,7 @@ void launch_mod_emit(const uint8_t* d_res, const DevTables* d_tb, const DigestCf
                      const uint64_t* tile_offs, uint64_t base_bits, uint64_t* v_key, uint64_t* v_payload,
                      cudaStream_t s) {
   if (n_unique == 0) return;
-  const unsigned tiles = (unsigned)((n_unique + kScanTile - 1) / kScanTile);
+  const unsigned tiles = (unsigned)((n_unique + kModTile - 1) / kModTile);
   DBI_LAUNCH(mod_emit_kernel, tiles, MD_THREADS, 0, s, d_res, d_tb, cfg, u_mass, u_gpos, u_len, n_unique, counts,
              tile_offs, base_bits, v_key, v_payload);
 }
@@ -186,7 +325,8 @@ void launch_split_entries(const uint64_t* skey, const uint64_t* spayload, uint64
                           double* e_mass, uint32_t* e_base, uint32_t* e_pat, cudaStream_t s) {
   if (n == 0) return;
   const unsigned grid = (unsigned)((n + MD_THREADS - 1) / MD_THREADS);
-  DBI_LAUNCH(split_entries_kernel, grid, MD_THREADS, 0, s, skey, spayload, n, base_bits, e_mass, e_base, e_pat);
+  DBI_LAUNCH(split_entries_kernel, grid, MD_THREADS, 0, s, skey, spayload, n, base_bits, e_mass,
+             e_base, e_pat);
 }
 
 }  // namespace dbi

@@ -37,20 +37,31 @@ __global__ void __launch_bounds__(RS_THREADS) rs_histogram_kernel(const K* __res
   __shared__ uint32_t sh[RS_MAX_PASSES * RS_RADIX];
   for (int i = threadIdx.x; i < num_passes * RS_RADIX; i += RS_THREADS) sh[i] = 0;
   __syncthreads();
-  const uint64_t stride = (uint64_t)gridDim.x * RS_THREADS;
+  constexpr int HU = 4;  // independent key loads in flight per thread
+  const uint64_t stride = (uint64_t)gridDim.x * RS_THREADS * HU;
   // whole warps iterate together so that match_any sees a full mask
   const uint64_t n_round = (n + 31) & ~31ull;
-  for (uint64_t i = (uint64_t)blockIdx.x * RS_THREADS + threadIdx.x; i < n_round; i += stride) {
-    const bool valid = i < n;
-    const K key = valid ? keys[i] : K(0);
-    for (int p = 0; p < num_passes; ++p) {
-      const int shift = begin_bit + p * RS_BITS;
-      const int bits = min(RS_BITS, end_bit - shift);
-      uint32_t d = (uint32_t)(key >> shift) & ((1u << bits) - 1);
-      if (!valid) d = 0xffffffffu;
-      // aggregate equal digits inside the warp: one shared atomic per distinct digit
-      const unsigned m = __match_any_sync(0xffffffffu, d);
-      if (valid && (int)lane_id() == __ffs(m) - 1) atomicAdd(&sh[p * RS_RADIX + d], (uint32_t)__popc(m));
+  // i0 - lane and n_round are multiples of 32, so the loop condition is warp-uniform
+  for (uint64_t i0 = (uint64_t)blockIdx.x * RS_THREADS * HU + threadIdx.x; i0 < n_round; i0 += stride) {
+    K key[HU];
+    bool valid[HU];
+#pragma unroll
+    for (int u = 0; u < HU; ++u) {
+      const uint64_t i = i0 + (uint64_t)u * RS_THREADS;
+      valid[u] = i < n;
+      key[u] = valid[u] ? keys[i] : K(0);
+    }
+#pragma unroll
+    for (int u = 0; u < HU; ++u) {
+      for (int p = 0; p < num_passes; ++p) {
+        const int shift = begin_bit + p * RS_BITS;
+        const int bits = min(RS_BITS, end_bit - shift);
+        uint32_t d = (uint32_t)(key[u] >> shift) & ((1u << bits) - 1);
+        if (!valid[u]) d = 0xffffffffu;
+        // aggregate equal digits inside the warp: one shared atomic per distinct digit
+        const unsigned m = __match_any_sync(0xffffffffu, d);
+        if (valid[u] && (int)lane_id() == __ffs(m) - 1) atomicAdd(&sh[p * RS_RADIX + d], (uint32_t)__popc(m));
+      }
     }
   }
   __syncthreads();
@@ -71,8 +82,11 @@ __global__ void __launch_bounds__(RS_RADIX) rs_scan_hist_kernel(unsigned long lo
 // ---- one scatter pass ------------------------------------------------------
 template <typename K, typename V>
 struct RsSmem {
-  K keys[RS_TILE];
-  V vals[RS_TILE];
+  union {  // keys are staged and written out first, then the values reuse the space
+    K keys[RS_TILE];
+    V vals[RS_TILE];
+  } st;
+  uint8_t sdig[RS_TILE];                // digit of the key in each local slot
   uint32_t whist[RS_WARPS * RS_RADIX];  // per-warp digit counters, then exclusive warp prefixes
   uint64_t outbase[RS_RADIX];           // global position of local slot 0 of each digit run (mod 2^64)
   uint32_t dstart[RS_RADIX];            // first local slot of each digit
@@ -80,12 +94,15 @@ struct RsSmem {
   uint32_t tile;
 };
 
-template <typename K, typename V>
-__global__ void __launch_bounds__(RS_THREADS)
+// SPLIT (last pass of the variant sort): keys leave as key + key_add (the mass bits), the
+// 64-bit values as two u32 arrays (vout_hi = base peptide, vout_lo = mod pattern).
+template <typename K, typename V, bool SPLIT>
+__global__ void __launch_bounds__(RS_THREADS, sizeof(K) == 8 ? 3 : 4)
     rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const V* __restrict__ vin,
                        V* __restrict__ vout, uint64_t n, int shift, uint32_t mask,
                        const unsigned long long* __restrict__ digit_off, unsigned long long* lookback,
-                       uint32_t* tile_counter, uint32_t pass_id) {
+                       uint32_t* tile_counter, uint32_t pass_id, K key_add, uint32_t* __restrict__ vout_hi,
+                       uint32_t* __restrict__ vout_lo) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   RsSmem<K, V>& s = *reinterpret_cast<RsSmem<K, V>*>(smem_raw);
   const int t = threadIdx.x;
@@ -170,27 +187,35 @@ __global__ void __launch_bounds__(RS_THREADS)
   for (int i = 0; i < RS_IPT; ++i) {
     const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
     rank[i] += s.dstart[d] + wh[d];
-    s.keys[rank[i]] = key[i];
+    s.st.keys[rank[i]] = key[i];
   }
   __syncthreads();
   // coalesced write-out: consecutive local slots of one digit are consecutive in HBM
 #pragma unroll 4
   for (uint32_t j = t; j < tile_n; j += RS_THREADS) {
-    const K k = s.keys[j];
+    const K k = s.st.keys[j];
     const uint32_t d = (uint32_t)(k >> shift) & mask;
-    kout[s.outbase[d] + j] = k;
+    s.sdig[j] = (uint8_t)d;
+    kout[s.outbase[d] + j] = SPLIT ? (K)(k + key_add) : k;
   }
-  // values take the same route
+  __syncthreads();  // every key has left the staging buffer
+  // values take the same route through the same buffer
 #pragma unroll
   for (int i = 0; i < RS_IPT; ++i) {
     const uint32_t e = (uint32_t)w * 32 * RS_IPT + i * 32 + l;
-    if (e < tile_n) s.vals[rank[i]] = vin[base + e];
+    if (e < tile_n) s.st.vals[rank[i]] = vin[base + e];
   }
   __syncthreads();
 #pragma unroll 4
   for (uint32_t j = t; j < tile_n; j += RS_THREADS) {
-    const uint32_t d = (uint32_t)(s.keys[j] >> shift) & mask;
-    vout[s.outbase[d] + j] = s.vals[j];
+    const uint64_t o = s.outbase[s.sdig[j]] + j;
+    const V v = s.st.vals[j];
+    if (SPLIT) {
+      vout_hi[o] = (uint32_t)((uint64_t)v >> 32);
+      vout_lo[o] = (uint32_t)v;
+    } else {
+      vout[o] = v;
+    }
   }
 }
 
@@ -204,7 +229,7 @@ size_t radix_sort_tmp_bytes(uint64_t n) {
 
 template <typename K, typename V>
 int radix_sort_pairs(K* keys[2], V* vals[2], uint64_t n, int begin_bit, int end_bit, void* tmp,
-                     cudaStream_t stream, uint32_t* launches) {
+                     cudaStream_t stream, PassProbe* probe, const SplitOut<K>* split) {
   if (n <= 1 || end_bit <= begin_bit) return 0;
   const int num_passes = (end_bit - begin_bit + RS_BITS - 1) / RS_BITS;
   if (num_passes > RS_MAX_PASSES) throw CudaError{cudaErrorInvalidValue, "radix_sort_pairs: too many passes", __FILE__, __LINE__};
@@ -218,31 +243,39 @@ int radix_sort_pairs(K* keys[2], V* vals[2], uint64_t n, int begin_bit, int end_
 
   DBI_CUDA(cudaMemsetAsync(tp, 0, RS_MAX_PASSES * RS_RADIX * 8 + 256 + (size_t)tiles * RS_RADIX * 8, stream));
 
-  uint64_t hg = (n + RS_THREADS * 8 - 1) / (RS_THREADS * 8);
+  uint64_t hg = (n + RS_THREADS * 4 - 1) / (RS_THREADS * 4);
   if (hg > (uint64_t)kNumSMsB200 * 8) hg = (uint64_t)kNumSMsB200 * 8;
   const int hgrid = (int)hg;
   DBI_LAUNCH((rs_histogram_kernel<K>), hgrid, RS_THREADS, 0, stream, keys[0], n, begin_bit, end_bit, num_passes, hist);
   DBI_LAUNCH(rs_scan_hist_kernel, num_passes, RS_RADIX, 0, stream, hist);
-  if (launches) *launches += 2;
 
   const size_t smem = sizeof(RsSmem<K, V>);
-  DBI_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<K, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DBI_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<K, V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DBI_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel<K, V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int cur = 0;
   for (int p = 0; p < num_passes; ++p) {
     const int shift = begin_bit + p * RS_BITS;
     const int bits = (end_bit - shift) < RS_BITS ? (end_bit - shift) : RS_BITS;
     const uint32_t mask = (1u << bits) - 1;
-    DBI_LAUNCH((rs_onesweep_kernel<K, V>), (unsigned)tiles, RS_THREADS, smem, stream, keys[cur], keys[cur ^ 1],
-               vals[cur], vals[cur ^ 1], n, shift, mask, hist + (size_t)p * RS_RADIX, lookback, counters + p,
-               (uint32_t)(p + 1));
-    if (launches) *launches += 1;
+    if (probe) probe->before_pass(p);
+    if (split && p == num_passes - 1) {
+      // last pass writes the final arrays directly: key + key_add -> split->keys, value halves
+      DBI_LAUNCH((rs_onesweep_kernel<K, V, true>), (unsigned)tiles, RS_THREADS, smem, stream, keys[cur], split->keys,
+                 vals[cur], vals[cur ^ 1], n, shift, mask, hist + (size_t)p * RS_RADIX, lookback, counters + p,
+                 (uint32_t)(p + 1), split->key_add, split->vals_hi, split->vals_lo);
+    } else {
+      DBI_LAUNCH((rs_onesweep_kernel<K, V, false>), (unsigned)tiles, RS_THREADS, smem, stream, keys[cur],
+                 keys[cur ^ 1], vals[cur], vals[cur ^ 1], n, shift, mask, hist + (size_t)p * RS_RADIX, lookback,
+                 counters + p, (uint32_t)(p + 1), (K)0, (uint32_t*)nullptr, (uint32_t*)nullptr);
+    }
+    if (probe) probe->after_pass(p);
     cur ^= 1;
   }
   return cur;
 }
 
-template int radix_sort_pairs<uint32_t, uint32_t>(uint32_t* [2], uint32_t* [2], uint64_t, int, int, void*, cudaStream_t, uint32_t*);
-template int radix_sort_pairs<uint64_t, uint32_t>(uint64_t* [2], uint32_t* [2], uint64_t, int, int, void*, cudaStream_t, uint32_t*);
-template int radix_sort_pairs<uint64_t, uint64_t>(uint64_t* [2], uint64_t* [2], uint64_t, int, int, void*, cudaStream_t, uint32_t*);
+template int radix_sort_pairs<uint32_t, uint32_t>(uint32_t* [2], uint32_t* [2], uint64_t, int, int, void*, cudaStream_t, PassProbe*, const SplitOut<uint32_t>*);
+template int radix_sort_pairs<uint64_t, uint32_t>(uint64_t* [2], uint32_t* [2], uint64_t, int, int, void*, cudaStream_t, PassProbe*, const SplitOut<uint64_t>*);
+template int radix_sort_pairs<uint64_t, uint64_t>(uint64_t* [2], uint64_t* [2], uint64_t, int, int, void*, cudaStream_t, PassProbe*, const SplitOut<uint64_t>*);
 
 }  // namespace dbi

@@ -109,6 +109,13 @@ typedef struct dbi_stats {
   uint32_t stage_launches[DBI_N_STAGES]; /* kernels launched per stage            */
   uint32_t sort_bits_base;  /* radix key bits sorted for the base records  */
   uint32_t sort_bits_var;   /* radix key bits sorted for the mod variants  */
+  /* The dominant kernel of a build = the onesweep scatter passes of its largest
+   * sort (mod variants if any, else the base records); only if params.profile. */
+  float dom_ms;                  /* summed device time of those launches      */
+  uint32_t dom_launches;         /* how many                                  */
+  uint64_t dom_bytes_per_launch; /* algorithmic bytes one launch moves        */
+  uint32_t dom_kernel;           /* 0 = <u64 key,u32 val> base, 1 = <u64,u64> variants */
+  uint32_t _pad;
 } dbi_stats;
 
 /* stage ids for dbi_stats arrays */
@@ -239,6 +246,12 @@ void dbi_destroy(dbi_handle* h);
 /* sizeof(dbi_params) and sizeof(dbi_stats) as compiled: lets a binding check
  * its struct layout before the first call. */
 void dbi_abi_sizes(uint64_t* sizeof_params, uint64_t* sizeof_stats);
+
+/* Device buffers are recycled through a process-wide per-device cache (blocks come
+ * from cudaMalloc once and are reused by size, like a long-lived SQLite page cache,
+ * DBIndexStoreSQLiteAbstract.java:114-121).  This returns the cached, currently
+ * unused blocks of `device` to the driver. */
+int dbi_release_cached_memory(int device);
 
 /* Thread-local text of the last error on this thread. */
 const char* dbi_last_error(void);
