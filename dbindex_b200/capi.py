@@ -164,6 +164,10 @@ ABI_SYMBOLS = [
     "dbi_entry_keys", "dbi_debug_emitted", "dbi_build_from_records", "dbi_debug_radix_sort", "dbi_destroy",
     "dbi_abi_sizes", "dbi_release_cached_memory",
     "dbi_last_error", "dbi_kernel_launches",
+    # multi-GPU staged build, bound in dbindex_b200/multigpu.py
+    "dbi_mg_begin", "dbi_mg_digest", "dbi_mg_histogram", "dbi_mg_partition", "dbi_mg_pack_send",
+    "dbi_mg_index_base", "dbi_mg_unique_counts", "dbi_mg_export_unique", "dbi_mg_import_unique", "dbi_mg_finish",
+    "dbi_mg_mod_tile_counts", "dbi_mg_expand", "dbi_mg_index_variants",
 ]
 
 

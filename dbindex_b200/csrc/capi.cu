@@ -177,6 +177,16 @@ struct dbi_handle {
   // kept raw records (params.keep_emitted)
   DevBuf k_mass, k_gpos, k_prot, k_len;
 
+  // multi-GPU staged build (dbi_mg_*): this rank, and the slice of the replicated unique tables
+  // it owns; without mods the entries of a rank are that slice (entry i = unique ent_base_off + i)
+  int mg_rank = 0, mg_world = 1;
+  uint64_t ent_base_off = 0;
+  DevBuf mg_mass, mg_gpos, mg_prot, mg_len;  // local records between digest and exchange
+  uint64_t mg_n = 0;
+  DevBuf mg_vkey, mg_vpay;                   // local variants between expansion and exchange
+  uint64_t mg_v = 0;
+  DevBuf mg_dest, mg_idx[2], mg_counts, mg_thr;
+
   DigestCfg cfg{};
   dbi_stats st{};
   // profiling (params.profile): event pairs recorded on the stream without any extra
@@ -194,7 +204,7 @@ struct dbi_handle {
     return ev_pool[ev_used++];
   }
 
-  const double* entry_mass() const { return e_mass.p ? e_mass.as<double>() : u_mass.as<double>(); }
+  const double* entry_mass() const { return e_mass.p ? e_mass.as<double>() : u_mass.as<double>() + ent_base_off; }
   const uint32_t* entry_base() const { return e_base.as<uint32_t>(); }
   const uint32_t* entry_pat() const { return e_pat.as<uint32_t>(); }
 };
@@ -339,6 +349,11 @@ void free_index(dbi_handle* h) {
   h->u_plo.release(); h->plist.release();
   h->e_mass.release(); h->e_base.release(); h->e_pat.release();
   h->k_mass.release(); h->k_gpos.release(); h->k_prot.release(); h->k_len.release();
+  h->mg_mass.release(); h->mg_gpos.release(); h->mg_prot.release(); h->mg_len.release();
+  h->mg_vkey.release(); h->mg_vpay.release(); h->mg_dest.release(); h->mg_idx[0].release(); h->mg_idx[1].release();
+  h->mg_counts.release(); h->mg_thr.release();
+  h->mg_n = h->mg_v = 0;
+  h->ent_base_off = 0;
   h->n_emitted = h->n_unique = h->n_entries = 0;
   h->spans.clear();
   h->ev_used = 0;
@@ -445,25 +460,38 @@ void pack_residues(dbi_handle* h) {
   h->st.algo_bytes[DBI_STAGE_PACK] += 2 * n_res + (uint64_t)n_prot * 12;
 }
 
-// Sort + K8 + K5/K6 on N emitted records already on the device.
-// lo_mass / hi_mass bound every record mass (they fix the radix key width).
-int index_records(dbi_handle* h, DevBuf& r_mass, DevBuf& r_gpos, DevBuf& r_prot, DevBuf& r_len, uint64_t N,
-                  double lo_mass, double hi_mass) {
+// Emitted records as they leave K4 (or arrive from the other GPUs).
+struct RecView {
+  const uint64_t* mass;  // IEEE bits
+  const uint32_t* gpos;
+  const uint32_t* prot;
+  const uint16_t* len;
+};
+
+// Radix key of a mass: bits(mass) - bits(lo); every mass of a build lies in [lo, hi].
+struct KeySpace {
+  uint64_t base_bits;
+  int nbits;
+  KeySpace(double lo, double hi) : base_bits(dbits(lo)), nbits(bit_length(dbits(hi) - dbits(lo))) {}
+};
+
+// K7 + K8: sort N records by (mass, sequence hash, arrival order), merge equal peptides into
+// the handle's unique tables (u_*, plist).
+int sort_dedup(dbi_handle* h, const RecView& r, uint64_t N, const KeySpace& ks) {
   cudaStream_t s = h->stream;
-  h->n_emitted = N;
-  h->st.n_emitted = N;
   if (N >= (1ull << 32)) {
     set_error("more than 2^32 emitted records on one GPU (%llu)", (unsigned long long)N);
     return DBI_ERANGE;
   }
+  h->n_unique = 0;
+  h->st.n_unique = 0;
   if (N == 0) {
     h->u_plo.alloc(8, h->arena);
     DBI_CUDA(cudaMemsetAsync(h->u_plo.p, 0, 8, s));
-    h->built = true;
     return DBI_OK;
   }
-  const uint64_t base_bits = dbits(lo_mass);
-  const int nbits = bit_length(dbits(hi_mass) - base_bits);
+  const uint64_t base_bits = ks.base_bits;
+  const int nbits = ks.nbits;
   h->st.sort_bits_base = (uint32_t)nbits + 32;
 
   DevBuf hash, idx[2], hkey[2], mkey[2], tmp, flags, tile_counts, tile_offs;
@@ -485,8 +513,7 @@ int index_records(dbi_handle* h, DevBuf& r_mass, DevBuf& r_gpos, DevBuf& r_prot,
     {
       Stage sg(h, DBI_STAGE_SORT_BASE);
       const uint32_t seed = 0x9e3779b9u * attempt;
-      launch_hash_records(h->d_res.as<uint8_t>(), r_gpos.as<uint32_t>(), r_len.as<uint16_t>(), N, seed,
-                          hash.as<uint32_t>(), idx[0].as<uint32_t>(), s);
+      launch_hash_records(h->d_res.as<uint8_t>(), r.gpos, r.len, N, seed, hash.as<uint32_t>(), idx[0].as<uint32_t>(), s);
       DBI_CUDA(cudaMemcpyAsync(hkey[0].p, hash.p, N * 4, cudaMemcpyDeviceToDevice, s));
       // less significant key first: sequence hash ...
       uint32_t* hk[2] = {hkey[0].as<uint32_t>(), hkey[1].as<uint32_t>()};
@@ -501,14 +528,14 @@ int index_records(dbi_handle* h, DevBuf& r_mass, DevBuf& r_gpos, DevBuf& r_prot,
         h->st.dom_kernel = 0;
         h->st.dom_bytes_per_launch = N * 24ull;
       }
-      // ... then the exact mass bits (stable), so order = (mass, hash, emission ordinal)
-      launch_gather_mass_key(r_mass.as<uint64_t>(), ix[r1], N, base_bits, mkey[0].as<uint64_t>(), s);
+      // ... then the exact mass bits (stable), so order = (mass, hash, arrival order)
+      launch_gather_mass_key(r.mass, ix[r1], N, base_bits, mkey[0].as<uint64_t>(), s);
       uint64_t* mk[2] = {mkey[0].as<uint64_t>(), mkey[1].as<uint64_t>()};
       uint32_t* ix2[2] = {ix[r1], ix[r1 ^ 1]};
       const int r2 = radix_sort_pairs<uint64_t, uint32_t>(mk, ix2, N, 0, nbits, tmp.p, s,
                                                           base_is_dominant ? &base_probe : nullptr);
       sorted = r2;
-      // normalise: sorted keys in mkey[sorted], sorted idx in ix2[sorted]
+      // normalise: sorted keys in mkey[sorted], sorted idx in idx[0]
       if (ix2[r2] != idx[0].as<uint32_t>()) idx[0].swap(idx[1]);
       const int passes = 4 + (nbits + 7) / 8;
       h->st.algo_bytes[DBI_STAGE_SORT_BASE] += N * (20 /*hash: len + 4*/ + 4 + 8 + 8 + 4) + N * 16ull * 4 +
@@ -517,8 +544,8 @@ int index_records(dbi_handle* h, DevBuf& r_mass, DevBuf& r_gpos, DevBuf& r_prot,
     {
       Stage sg(h, DBI_STAGE_DEDUP);
       launch_dedup_flags(h->d_res.as<uint8_t>(), mkey[sorted].as<uint64_t>(), idx[0].as<uint32_t>(),
-                         hash.as<uint32_t>(), r_gpos.as<uint32_t>(), r_len.as<uint16_t>(), N, flags.as<uint8_t>(),
-                         tile_counts.as<uint32_t>(), h->d_err.as<uint32_t>(), s);
+                         hash.as<uint32_t>(), r.gpos, r.len, N, flags.as<uint8_t>(), tile_counts.as<uint32_t>(),
+                         h->d_err.as<uint32_t>(), s);
       launch_scan_u32_to_u64(tile_counts.as<uint32_t>(), tiles, tile_offs.as<uint64_t>(), s);
       n_unique = read_u64(h, tile_offs.as<uint64_t>() + tiles);
     }
@@ -549,55 +576,71 @@ int index_records(dbi_handle* h, DevBuf& r_mass, DevBuf& r_gpos, DevBuf& r_prot,
     h->u_plo.alloc((n_unique + 1) * 8, h->arena);
     h->plist.alloc(N * 4, h->arena);
     launch_dedup_emit(mkey[sorted].as<uint64_t>(), idx[0].as<uint32_t>(), flags.as<uint8_t>(),
-                      tile_offs.as<uint64_t>(), r_gpos.as<uint32_t>(), r_prot.as<uint32_t>(), r_len.as<uint16_t>(), N,
-                      base_bits, n_unique, h->u_mass.as<double>(), h->u_gpos.as<uint32_t>(),
-                      h->u_prot.as<uint32_t>(), h->u_len.as<uint16_t>(), h->u_plo.as<uint64_t>(),
-                      h->plist.as<uint32_t>(), s);
+                      tile_offs.as<uint64_t>(), r.gpos, r.prot, r.len, N, base_bits, n_unique, h->u_mass.as<double>(),
+                      h->u_gpos.as<uint32_t>(), h->u_prot.as<uint32_t>(), h->u_len.as<uint16_t>(),
+                      h->u_plo.as<uint64_t>(), h->plist.as<uint32_t>(), s);
     h->st.algo_bytes[DBI_STAGE_DEDUP] += N * (8 + 4 + 1) + N * (1 + 4 + 4 + 4) + n_unique * (8 + 4 + 4 + 2 + 8 + 10);
   }
   TR("ir_dedup_emit");
-  // free the sort scratch before the (much larger) variant stage
-  hash.release(); idx[0].release(); idx[1].release(); hkey[0].release(); hkey[1].release();
-  mkey[0].release(); mkey[1].release(); tmp.release(); flags.release(); tile_counts.release(); tile_offs.release();
+  return DBI_OK;
+}
 
-  if (h->cfg.max_mods == 0) {
-    h->n_entries = n_unique;
-    h->st.n_entries = n_unique;
-    h->built = true;
+// K5 + K6 over base tiles [tile0, tile0 + ntiles) of the unique tables: (key, payload) pairs of
+// every variant into freshly allocated vkey / vpay; *V = how many.
+int emit_variants(dbi_handle* h, uint32_t tile0, uint32_t ntiles, const KeySpace& ks, DevBuf& vkey, DevBuf& vpay,
+                  uint64_t* V_out) {
+  cudaStream_t s = h->stream;
+  const uint64_t n_unique = h->n_unique;
+  *V_out = 0;
+  if (ntiles == 0 || n_unique == 0) {
+    vkey.alloc(8, h->arena);
+    vpay.alloc(8, h->arena);
     return DBI_OK;
   }
-
-  // ---- K5/K6: differential-mod variants of the unique peptides ----
-  const uint64_t utiles = (n_unique + kModTile - 1) / kModTile;
   DevBuf counts, ucounts, uoffs;
-  counts.alloc(n_unique * 4, h->arena);
-  ucounts.alloc(utiles * 4, h->arena);
-  uoffs.alloc((utiles + 1) * 8, h->arena);
+  counts.alloc(n_unique * 4, h->arena);  // indexed by global base id
+  ucounts.alloc((uint64_t)ntiles * 4, h->arena);
+  uoffs.alloc(((uint64_t)ntiles + 1) * 8, h->arena);
+  const uint64_t n_in_tiles = std::min<uint64_t>((uint64_t)ntiles * kModTile, n_unique - (uint64_t)tile0 * kModTile);
   uint64_t V = 0;
   {
     Stage sg(h, DBI_STAGE_MOD_COUNT);
     launch_mod_count(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_mass.as<double>(),
-                     h->u_gpos.as<uint32_t>(), h->u_len.as<uint16_t>(), n_unique, counts.as<uint32_t>(),
-                     ucounts.as<uint32_t>(), h->d_err.as<uint32_t>(), s);
-    launch_scan_u32_to_u64(ucounts.as<uint32_t>(), utiles, uoffs.as<uint64_t>(), s);
-    V = read_u64(h, uoffs.as<uint64_t>() + utiles);
-    h->st.algo_bytes[DBI_STAGE_MOD_COUNT] += n_unique * (8 + 4 + 2 + 4 + 20);
+                     h->u_gpos.as<uint32_t>(), h->u_len.as<uint16_t>(), n_unique, tile0, ntiles,
+                     counts.as<uint32_t>(), ucounts.as<uint32_t>(), h->d_err.as<uint32_t>(), s);
+    launch_scan_u32_to_u64(ucounts.as<uint32_t>(), ntiles, uoffs.as<uint64_t>(), s);
+    V = read_u64(h, uoffs.as<uint64_t>() + ntiles);
+    h->st.algo_bytes[DBI_STAGE_MOD_COUNT] += n_in_tiles * (8 + 4 + 2 + 4 + 20);
   }
   if (int rc = check_err_bits(read_err(h))) return rc;
   TR("ir_modcount+sync");
-  DevBuf vkey[2], vpay[2], vtmp;
-  vkey[0].alloc(V * 8, h->arena); vkey[1].alloc(V * 8, h->arena);
-  vpay[0].alloc(V * 8, h->arena); vpay[1].alloc(V * 8, h->arena);
-  vtmp.alloc(radix_sort_tmp_bytes(V), h->arena);
+  vkey.alloc(V * 8, h->arena);
+  vpay.alloc(V * 8, h->arena);
   TR("ir_valloc");
   {
     Stage sg(h, DBI_STAGE_MOD_EMIT);
     launch_mod_emit(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_mass.as<double>(),
-                    h->u_gpos.as<uint32_t>(), h->u_len.as<uint16_t>(), n_unique, counts.as<uint32_t>(),
-                    uoffs.as<uint64_t>(), base_bits, vkey[0].as<uint64_t>(), vpay[0].as<uint64_t>(), s);
-    h->st.algo_bytes[DBI_STAGE_MOD_EMIT] += n_unique * (8 + 4 + 2 + 4 + 20) + V * 16;
+                    h->u_gpos.as<uint32_t>(), h->u_len.as<uint16_t>(), n_unique, tile0, ntiles,
+                    counts.as<uint32_t>(), uoffs.as<uint64_t>(), ks.base_bits, vkey.as<uint64_t>(),
+                    vpay.as<uint64_t>(), s);
+    h->st.algo_bytes[DBI_STAGE_MOD_EMIT] += n_in_tiles * (8 + 4 + 2 + 4 + 20) + V * 16;
   }
   TR("ir_modemit");
+  *V_out = V;
+  return DBI_OK;
+}
+
+// K7 on V (key, payload) variant pairs (clobbered) -> the handle's entry arrays.
+int sort_variants(dbi_handle* h, uint64_t* key_in, uint64_t* pay_in, uint64_t V, const KeySpace& ks) {
+  cudaStream_t s = h->stream;
+  if (V >= (1ull << 32)) {
+    set_error("more than 2^32 index entries on one GPU (%llu)", (unsigned long long)V);
+    return DBI_ERANGE;
+  }
+  DevBuf key2, pay2, vtmp;
+  key2.alloc(V * 8, h->arena);
+  pay2.alloc(V * 8, h->arena);
+  vtmp.alloc(radix_sort_tmp_bytes(V), h->arena);
   h->e_mass.alloc(V * 8, h->arena);
   h->e_base.alloc(V * 4, h->arena);
   h->e_pat.alloc(V * 4, h->arena);
@@ -605,27 +648,49 @@ int index_records(dbi_handle* h, DevBuf& r_mass, DevBuf& r_gpos, DevBuf& r_prot,
   {
     // the last pass of the sort writes the final entry arrays (mass, base id, mod pattern)
     Stage sg(h, DBI_STAGE_SORT_VAR);
-    uint64_t* vk[2] = {vkey[0].as<uint64_t>(), vkey[1].as<uint64_t>()};
-    uint64_t* vp[2] = {vpay[0].as<uint64_t>(), vpay[1].as<uint64_t>()};
+    uint64_t* vk[2] = {key_in, key2.as<uint64_t>()};
+    uint64_t* vp[2] = {pay_in, pay2.as<uint64_t>()};
     DomProbe var_probe(h);
     if (h->p.profile) {
       h->st.dom_kernel = 1;
       h->st.dom_bytes_per_launch = V * 32ull;
     }
-    SplitOut<uint64_t> split{h->e_mass.as<uint64_t>(), base_bits, h->e_base.as<uint32_t>(), h->e_pat.as<uint32_t>()};
-    const int passes = (nbits + 7) / 8;
+    SplitOut<uint64_t> split{h->e_mass.as<uint64_t>(), ks.base_bits, h->e_base.as<uint32_t>(), h->e_pat.as<uint32_t>()};
+    const int passes = (ks.nbits + 7) / 8;
     if (V > 1 && passes > 0) {
-      radix_sort_pairs<uint64_t, uint64_t>(vk, vp, V, 0, nbits, vtmp.p, s, h->p.profile ? &var_probe : nullptr, &split);
+      radix_sort_pairs<uint64_t, uint64_t>(vk, vp, V, 0, ks.nbits, vtmp.p, s, h->p.profile ? &var_probe : nullptr, &split);
     } else {  // nothing to sort: plain split
-      launch_split_entries(vk[0], vp[0], V, base_bits, h->e_mass.as<double>(), h->e_base.as<uint32_t>(),
+      launch_split_entries(vk[0], vp[0], V, ks.base_bits, h->e_mass.as<double>(), h->e_base.as<uint32_t>(),
                            h->e_pat.as<uint32_t>(), s);
     }
-    h->st.sort_bits_var = (uint32_t)nbits;
+    h->st.sort_bits_var = (uint32_t)ks.nbits;
     h->st.algo_bytes[DBI_STAGE_SORT_VAR] += V * 8 + V * 32ull * passes;
   }
   TR("ir_sortvar");
   h->n_entries = V;
   h->st.n_entries = V;
+  return DBI_OK;
+}
+
+// Single-GPU: sort + merge + (mods) expand + sort on N emitted records already on the device.
+// lo_mass / hi_mass bound every record mass (they fix the radix key width).
+int index_records(dbi_handle* h, const RecView& r, uint64_t N, double lo_mass, double hi_mass) {
+  h->n_emitted = N;
+  h->st.n_emitted = N;
+  const KeySpace ks(lo_mass, hi_mass);
+  if (int rc = sort_dedup(h, r, N, ks)) return rc;
+  h->ent_base_off = 0;
+  if (h->cfg.max_mods == 0 || h->n_unique == 0) {
+    h->n_entries = h->n_unique;
+    h->st.n_entries = h->n_unique;
+    h->built = true;
+    return DBI_OK;
+  }
+  const uint32_t utiles = (uint32_t)((h->n_unique + kModTile - 1) / kModTile);
+  DevBuf vkey, vpay;
+  uint64_t V = 0;
+  if (int rc = emit_variants(h, 0, utiles, ks, vkey, vpay, &V)) return rc;
+  if (int rc = sort_variants(h, vkey.as<uint64_t>(), vpay.as<uint64_t>(), V, ks)) return rc;
   h->built = true;
   return DBI_OK;
 }
@@ -779,7 +844,7 @@ int dbi_build(dbi_handle* h) {
   uint64_t N = 0;
   {
     Stage sg(h, DBI_STAGE_DIGEST_COUNT);
-    launch_digest_count(h->d_res.as<uint8_t>(), h->res_end, h->d_tables.as<DevTables>(), h->cfg,
+    launch_digest_count(h->d_res.as<uint8_t>(), h->res_end, h->d_tables.as<DevTables>(), h->cfg, 0, (uint32_t)tiles,
                         tile_counts.as<uint32_t>(), h->d_err.as<uint32_t>(), s);
     launch_scan_u32_to_u64(tile_counts.as<uint32_t>(), tiles, tile_offs.as<uint64_t>(), s);
     N = read_u64(h, tile_offs.as<uint64_t>() + tiles);
@@ -797,7 +862,7 @@ int dbi_build(dbi_handle* h) {
   r_len.alloc(N * 2, h->arena);
   {
     Stage sg(h, DBI_STAGE_DIGEST_EMIT);
-    launch_digest_emit(h->d_res.as<uint8_t>(), h->res_end, h->d_tables.as<DevTables>(), h->cfg,
+    launch_digest_emit(h->d_res.as<uint8_t>(), h->res_end, h->d_tables.as<DevTables>(), h->cfg, 0, (uint32_t)tiles,
                        tile_offs.as<uint64_t>(), h->d_pstart.as<uint32_t>(), n_prot, r_mass.as<uint64_t>(),
                        r_gpos.as<uint32_t>(), r_prot.as<uint32_t>(), r_len.as<uint16_t>(), h->d_err.as<uint32_t>(), s);
     h->st.algo_bytes[DBI_STAGE_DIGEST_EMIT] += h->res_end + N * 18;
@@ -805,7 +870,8 @@ int dbi_build(dbi_handle* h) {
   tile_counts.release();
   tile_offs.release();
   TR("emit");
-  int rc = index_records(h, r_mass, r_gpos, r_prot, r_len, N, h->p.min_mass, h->p.max_mass);
+  const RecView rv{r_mass.as<uint64_t>(), r_gpos.as<uint32_t>(), r_prot.as<uint32_t>(), r_len.as<uint16_t>()};
+  int rc = index_records(h, rv, N, h->p.min_mass, h->p.max_mass);
   TR("index_records");
   if (rc == DBI_OK)
     if (int rc2 = check_err_bits(read_err(h))) rc = rc2;
@@ -869,7 +935,8 @@ int dbi_build_from_records(dbi_handle* h, const double* mass, const uint32_t* pr
     lo = std::min(lo, h->p.min_mass);
     hi = std::max(hi, h->p.max_mass);
   }
-  int rc = index_records(h, r_mass, r_gpos, r_prot, r_len, n, lo, hi);
+  const RecView rv{r_mass.as<uint64_t>(), r_gpos.as<uint32_t>(), r_prot.as<uint32_t>(), r_len.as<uint16_t>()};
+  int rc = index_records(h, rv, n, lo, hi);
   if (rc == DBI_OK)
     if (int rc2 = check_err_bits(read_err(h))) rc = rc2;
   if (rc != DBI_OK) {
@@ -970,7 +1037,7 @@ int dbi_fetch(dbi_handle* h, uint64_t begin, uint64_t count, double* mass, uint3
   uint64_t total_ids = 0;
   {
     Stage sg(h, DBI_STAGE_FETCH);
-    launch_fetch_sizes(h->entry_base(), h->u_plo.as<uint64_t>(), begin, count, sizes.as<uint32_t>(),
+    launch_fetch_sizes(h->entry_base(), h->ent_base_off, h->u_plo.as<uint64_t>(), begin, count, sizes.as<uint32_t>(),
                        tcnt.as<uint32_t>(), s);
     launch_scan_u32_to_u64(tcnt.as<uint32_t>(), tiles, toff.as<uint64_t>(), s);
     total_ids = read_u64(h, toff.as<uint64_t>() + tiles);
@@ -991,7 +1058,7 @@ int dbi_fetch(dbi_handle* h, uint64_t begin, uint64_t count, double* mass, uint3
   if (want_ids) o_ids.alloc(total_ids * 4, h->arena);
   {
     Stage sg(h, DBI_STAGE_FETCH);
-    launch_fetch_gather(h->entry_mass(), h->entry_base(), h->entry_pat(), h->u_gpos.as<uint32_t>(),
+    launch_fetch_gather(h->entry_mass(), h->entry_base(), h->ent_base_off, h->entry_pat(), h->u_gpos.as<uint32_t>(),
                         h->u_prot.as<uint32_t>(), h->u_len.as<uint16_t>(), h->u_plo.as<uint64_t>(),
                         h->plist.as<uint32_t>(), h->d_pstart.as<uint32_t>(), begin, count, sizes.as<uint32_t>(),
                         toff.as<uint64_t>(), o_mass.as<double>(), o_prot.as<uint32_t>(), o_off.as<uint32_t>(),
@@ -1106,6 +1173,359 @@ int dbi_debug_emitted(dbi_handle* h, uint64_t capacity, double* mass, uint32_t* 
     if (prot) prot[i] = pr[i];
     if (off) off[i] = gpos[i] - (uint32_t)(h->h_off[pr[i]] + pr[i] + 1);
   }
+  return DBI_OK;
+  DBI_API_END
+}
+
+// ---- multi-GPU staged build ------------------------------------------------------------------
+
+int dbi_mg_begin(dbi_handle* h, int rank, int world) {
+  DBI_API_BEGIN(h)
+  if (h->built) {
+    set_error("index already built");
+    return DBI_EALREADY;
+  }
+  if (world < 1 || world > 64 || rank < 0 || rank >= world) {
+    set_error("bad rank %d / world %d (1..64)", rank, world);
+    return DBI_EINVAL;
+  }
+  h->mg_rank = rank;
+  h->mg_world = world;
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_mg_digest(dbi_handle* h, uint64_t* n_records) {
+  DBI_API_BEGIN(h)
+  if (h->built) {
+    set_error("index already built");
+    return DBI_EALREADY;
+  }
+  cudaStream_t s = h->stream;
+  ensure_uploaded(h);
+  const uint32_t zero = 0;
+  DBI_CUDA(cudaMemcpyAsync(h->d_err.p, &zero, 4, cudaMemcpyHostToDevice, s));
+  pack_residues(h);
+  const uint32_t n_prot = (uint32_t)(h->h_off.size() - 1);
+  const uint64_t tiles_all = ((uint64_t)h->res_end + kDigestTile - 1) / kDigestTile;
+  // contiguous, ascending tile ranges: rank order == global emission order
+  const uint32_t t0 = (uint32_t)(tiles_all * h->mg_rank / h->mg_world);
+  const uint32_t t1 = (uint32_t)(tiles_all * (h->mg_rank + 1) / h->mg_world);
+  const uint32_t nt = t1 - t0;
+  DevBuf tile_counts, tile_offs;
+  tile_counts.alloc((uint64_t)nt * 4, h->arena);
+  tile_offs.alloc(((uint64_t)nt + 1) * 8, h->arena);
+  uint64_t N = 0;
+  {
+    Stage sg(h, DBI_STAGE_DIGEST_COUNT);
+    launch_digest_count(h->d_res.as<uint8_t>(), h->res_end, h->d_tables.as<DevTables>(), h->cfg, t0, nt,
+                        tile_counts.as<uint32_t>(), h->d_err.as<uint32_t>(), s);
+    launch_scan_u32_to_u64(tile_counts.as<uint32_t>(), nt, tile_offs.as<uint64_t>(), s);
+    N = read_u64(h, tile_offs.as<uint64_t>() + nt);
+    h->st.algo_bytes[DBI_STAGE_DIGEST_COUNT] += (uint64_t)nt * kDigestTile + (uint64_t)nt * 16;
+  }
+  if (int rc = check_err_bits(read_err(h))) {
+    free_index(h);
+    return rc;
+  }
+  if (N >= (1ull << 32)) {
+    set_error("more than 2^32 emitted records on one GPU");
+    return DBI_ERANGE;
+  }
+  h->mg_mass.alloc(N * 8, h->arena);
+  h->mg_gpos.alloc(N * 4, h->arena);
+  h->mg_prot.alloc(N * 4, h->arena);
+  h->mg_len.alloc(N * 2, h->arena);
+  {
+    Stage sg(h, DBI_STAGE_DIGEST_EMIT);
+    launch_digest_emit(h->d_res.as<uint8_t>(), h->res_end, h->d_tables.as<DevTables>(), h->cfg, t0, nt,
+                       tile_offs.as<uint64_t>(), h->d_pstart.as<uint32_t>(), n_prot, h->mg_mass.as<uint64_t>(),
+                       h->mg_gpos.as<uint32_t>(), h->mg_prot.as<uint32_t>(), h->mg_len.as<uint16_t>(),
+                       h->d_err.as<uint32_t>(), s);
+    h->st.algo_bytes[DBI_STAGE_DIGEST_EMIT] += (uint64_t)nt * kDigestTile + N * 18;
+  }
+  DBI_CUDA(cudaStreamSynchronize(s));
+  h->mg_n = N;
+  h->n_emitted = N;
+  h->st.n_emitted = N;
+  if (n_records) *n_records = N;
+  return DBI_OK;
+  DBI_API_END
+}
+
+namespace {
+// key array, count and key offset of an exchange stage
+struct MgStage {
+  const uint64_t* key;
+  uint64_t n;
+  uint64_t sub;
+};
+MgStage mg_stage(dbi_handle* h, int stage, const KeySpace& ks) {
+  if (stage == 0) return {h->mg_mass.as<uint64_t>(), h->mg_n, ks.base_bits};  // raw mass bits
+  return {h->mg_vkey.as<uint64_t>(), h->mg_v, 0};                              // already key - base
+}
+}  // namespace
+
+int dbi_mg_histogram(dbi_handle* h, int stage, uint64_t* d_hist, int* shift) {
+  DBI_API_BEGIN(h)
+  if (!d_hist || (stage != 0 && stage != 1)) {
+    set_error("bad argument");
+    return DBI_EINVAL;
+  }
+  const KeySpace ks(h->p.min_mass, h->p.max_mass);
+  const MgStage st = mg_stage(h, stage, ks);
+  const int sh = ks.nbits > 12 ? ks.nbits - 12 : 0;
+  launch_mg_hist(st.key, st.n, st.sub, sh, (unsigned long long*)d_hist, h->stream);
+  DBI_CUDA(cudaStreamSynchronize(h->stream));
+  if (shift) *shift = sh;
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_mg_partition(dbi_handle* h, int stage, const uint32_t* bin_splitters, uint64_t* send_counts) {
+  DBI_API_BEGIN(h)
+  if ((h->mg_world > 1 && !bin_splitters) || !send_counts || (stage != 0 && stage != 1)) {
+    set_error("bad argument");
+    return DBI_EINVAL;
+  }
+  cudaStream_t s = h->stream;
+  const KeySpace ks(h->p.min_mass, h->p.max_mass);
+  const MgStage st = mg_stage(h, stage, ks);
+  const int sh = ks.nbits > 12 ? ks.nbits - 12 : 0;
+  const int n_thr = h->mg_world - 1;
+  uint64_t thr[64];
+  for (int d = 0; d < n_thr; ++d) {
+    if (d > 0 && bin_splitters[d] < bin_splitters[d - 1]) {
+      set_error("bin_splitters must be ascending");
+      return DBI_EINVAL;
+    }
+    thr[d] = (uint64_t)bin_splitters[d] << sh;
+  }
+  const uint64_t n = st.n;
+  h->mg_dest.alloc(n * 4, h->arena);
+  h->mg_idx[0].alloc(n * 4, h->arena);
+  h->mg_idx[1].alloc(n * 4, h->arena);
+  h->mg_counts.alloc(64 * 8, h->arena);
+  h->mg_thr.alloc(64 * 8, h->arena);
+  DBI_CUDA(cudaMemsetAsync(h->mg_counts.p, 0, 64 * 8, s));
+  if (n_thr) DBI_CUDA(cudaMemcpyAsync(h->mg_thr.p, thr, n_thr * 8, cudaMemcpyHostToDevice, s));
+  {
+    Stage sg(h, DBI_STAGE_OTHER);
+    launch_mg_dest(st.key, n, st.sub, h->mg_thr.as<uint64_t>(), n_thr, h->mg_dest.as<uint32_t>(),
+                   h->mg_idx[0].as<uint32_t>(), (unsigned long long*)h->mg_counts.p, s);
+    // stable counting sort by destination = one radix pass over the rank id
+    DevBuf dest2, tmp;
+    dest2.alloc(n * 4, h->arena);
+    tmp.alloc(radix_sort_tmp_bytes(n), h->arena);
+    uint32_t* dk[2] = {h->mg_dest.as<uint32_t>(), dest2.as<uint32_t>()};
+    uint32_t* ix[2] = {h->mg_idx[0].as<uint32_t>(), h->mg_idx[1].as<uint32_t>()};
+    const int r = radix_sort_pairs<uint32_t, uint32_t>(dk, ix, n, 0, 6, tmp.p, s, nullptr);
+    if (r == 1) h->mg_idx[0].swap(h->mg_idx[1]);  // sorted permutation in mg_idx[0]
+  }
+  uint64_t counts[64];
+  DBI_CUDA(cudaMemcpyAsync(counts, h->mg_counts.p, 64 * 8, cudaMemcpyDeviceToHost, s));
+  DBI_CUDA(cudaStreamSynchronize(s));
+  for (int d = 0; d < h->mg_world; ++d) send_counts[d] = counts[d];
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_mg_pack_send(dbi_handle* h, int stage, void* d0, void* d1, void* d2, void* d3) {
+  DBI_API_BEGIN(h)
+  cudaStream_t s = h->stream;
+  const uint32_t* idx = h->mg_idx[0].as<uint32_t>();
+  Stage sg(h, DBI_STAGE_OTHER);
+  if (stage == 0) {
+    const uint64_t n = h->mg_n;
+    if (n && (!d0 || !d1 || !d2 || !d3)) {
+      set_error("null send buffer");
+      return DBI_EINVAL;
+    }
+    launch_gather_u64(h->mg_mass.as<uint64_t>(), idx, n, (uint64_t*)d0, s);
+    launch_gather_u32(h->mg_gpos.as<uint32_t>(), idx, n, (uint32_t*)d1, s);
+    launch_gather_u32(h->mg_prot.as<uint32_t>(), idx, n, (uint32_t*)d2, s);
+    launch_gather_u16(h->mg_len.as<uint16_t>(), idx, n, (uint16_t*)d3, s);
+    DBI_CUDA(cudaStreamSynchronize(s));
+    h->mg_mass.release(); h->mg_gpos.release(); h->mg_prot.release(); h->mg_len.release();
+  } else if (stage == 1) {
+    const uint64_t n = h->mg_v;
+    if (n && (!d0 || !d1)) {
+      set_error("null send buffer");
+      return DBI_EINVAL;
+    }
+    launch_gather_u64(h->mg_vkey.as<uint64_t>(), idx, n, (uint64_t*)d0, s);
+    launch_gather_u64(h->mg_vpay.as<uint64_t>(), idx, n, (uint64_t*)d1, s);
+    DBI_CUDA(cudaStreamSynchronize(s));
+    h->mg_vkey.release(); h->mg_vpay.release();
+  } else {
+    set_error("bad stage");
+    return DBI_EINVAL;
+  }
+  h->mg_dest.release(); h->mg_idx[0].release(); h->mg_idx[1].release();
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_mg_index_base(dbi_handle* h, const void* d_mass, const void* d_gpos, const void* d_prot, const void* d_len,
+                      uint64_t n) {
+  DBI_API_BEGIN(h)
+  if (n && (!d_mass || !d_gpos || !d_prot || !d_len)) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  const KeySpace ks(h->p.min_mass, h->p.max_mass);
+  const RecView rv{(const uint64_t*)d_mass, (const uint32_t*)d_gpos, (const uint32_t*)d_prot, (const uint16_t*)d_len};
+  int rc = sort_dedup(h, rv, n, ks);
+  if (rc == DBI_OK) rc = check_err_bits(read_err(h));
+  if (rc == DBI_OK && n == 0) {  // empty slice: still needs (empty) tables
+    h->u_mass.alloc(8, h->arena); h->u_gpos.alloc(8, h->arena); h->u_prot.alloc(8, h->arena);
+    h->u_len.alloc(8, h->arena); h->plist.alloc(8, h->arena);
+  }
+  DBI_CUDA(cudaStreamSynchronize(h->stream));
+  return rc;
+  DBI_API_END
+}
+
+int dbi_mg_unique_counts(dbi_handle* h, uint64_t* n_unique, uint64_t* n_plist) {
+  DBI_API_BEGIN(h)
+  if (n_unique) *n_unique = h->n_unique;
+  if (n_plist) *n_plist = h->n_unique ? read_u64(h, h->u_plo.as<uint64_t>() + h->n_unique) : 0;
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_mg_export_unique(dbi_handle* h, void* d_mass, void* d_gpos, void* d_prot, void* d_len, void* d_pcnt,
+                         void* d_plist) {
+  DBI_API_BEGIN(h)
+  cudaStream_t s = h->stream;
+  const uint64_t u = h->n_unique;
+  if (u) {
+    const uint64_t np = read_u64(h, h->u_plo.as<uint64_t>() + u);
+    DBI_CUDA(cudaMemcpyAsync(d_mass, h->u_mass.p, u * 8, cudaMemcpyDeviceToDevice, s));
+    DBI_CUDA(cudaMemcpyAsync(d_gpos, h->u_gpos.p, u * 4, cudaMemcpyDeviceToDevice, s));
+    DBI_CUDA(cudaMemcpyAsync(d_prot, h->u_prot.p, u * 4, cudaMemcpyDeviceToDevice, s));
+    DBI_CUDA(cudaMemcpyAsync(d_len, h->u_len.p, u * 2, cudaMemcpyDeviceToDevice, s));
+    launch_plo_to_counts(h->u_plo.as<uint64_t>(), u, (uint32_t*)d_pcnt, s);
+    DBI_CUDA(cudaMemcpyAsync(d_plist, h->plist.p, np * 4, cudaMemcpyDeviceToDevice, s));
+    DBI_CUDA(cudaStreamSynchronize(s));
+  }
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_mg_import_unique(dbi_handle* h, const uint64_t* rank_unique, const uint64_t* rank_plist, const void* d_mass,
+                         const void* d_gpos, const void* d_prot, const void* d_len, const void* d_pcnt,
+                         const void* d_plist) {
+  DBI_API_BEGIN(h)
+  if (!rank_unique || !rank_plist) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  cudaStream_t s = h->stream;
+  uint64_t U = 0, P = 0, off = 0;
+  for (int r = 0; r < h->mg_world; ++r) {
+    if (r == h->mg_rank) off = U;
+    U += rank_unique[r];
+    P += rank_plist[r];
+  }
+  if (U >= (1ull << 32)) {
+    set_error("more than 2^32 unique peptides in total");
+    return DBI_ERANGE;
+  }
+  const uint64_t own = rank_unique[h->mg_rank];
+  h->u_mass.alloc(U * 8, h->arena);
+  h->u_gpos.alloc(U * 4, h->arena);
+  h->u_prot.alloc(U * 4, h->arena);
+  h->u_len.alloc(U * 2, h->arena);
+  h->u_plo.alloc((U + 1) * 8, h->arena);
+  h->plist.alloc(P * 4, h->arena);
+  if (U) {
+    DBI_CUDA(cudaMemcpyAsync(h->u_mass.p, d_mass, U * 8, cudaMemcpyDeviceToDevice, s));
+    DBI_CUDA(cudaMemcpyAsync(h->u_gpos.p, d_gpos, U * 4, cudaMemcpyDeviceToDevice, s));
+    DBI_CUDA(cudaMemcpyAsync(h->u_prot.p, d_prot, U * 4, cudaMemcpyDeviceToDevice, s));
+    DBI_CUDA(cudaMemcpyAsync(h->u_len.p, d_len, U * 2, cudaMemcpyDeviceToDevice, s));
+    DBI_CUDA(cudaMemcpyAsync(h->plist.p, d_plist, P * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  DevBuf tmp;
+  tmp.alloc(full_scan_tmp_bytes(U), h->arena);
+  launch_full_scan_u32_to_u64((const uint32_t*)d_pcnt, U, h->u_plo.as<uint64_t>(), tmp.p, s);
+  DBI_CUDA(cudaStreamSynchronize(s));
+  h->n_unique = U;
+  h->st.n_unique = U;
+  h->ent_base_off = off;
+  h->n_entries = own;  // until variants are indexed
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_mg_finish(dbi_handle* h) {
+  DBI_API_BEGIN(h)
+  if (h->cfg.max_mods != 0) {
+    set_error("dbi_mg_finish is for builds without differential mods; use dbi_mg_index_variants");
+    return DBI_EINVAL;
+  }
+  h->e_mass.release(); h->e_base.release(); h->e_pat.release();
+  h->st.n_entries = h->n_entries;
+  h->built = true;
+  finish_stats(h);
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_mg_mod_tile_counts(dbi_handle* h, uint32_t* tile_begin, uint32_t* n_tiles, void* d_tile_counts) {
+  DBI_API_BEGIN(h)
+  if (!tile_begin || !n_tiles || !d_tile_counts) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  cudaStream_t s = h->stream;
+  const uint64_t a = h->ent_base_off, b = h->ent_base_off + h->n_entries;  // own slice of the unique tables
+  const uint32_t t0 = (uint32_t)((a + kModTile - 1) / kModTile);            // tiles that START in the slice
+  const uint32_t t1 = (uint32_t)((b + kModTile - 1) / kModTile);
+  *tile_begin = t0;
+  *n_tiles = t1 - t0;
+  if (t1 > t0) {
+    DevBuf counts;
+    counts.alloc(h->n_unique * 4, h->arena);
+    Stage sg(h, DBI_STAGE_MOD_COUNT);
+    launch_mod_count(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_mass.as<double>(),
+                     h->u_gpos.as<uint32_t>(), h->u_len.as<uint16_t>(), h->n_unique, t0, t1 - t0,
+                     counts.as<uint32_t>(), (uint32_t*)d_tile_counts, h->d_err.as<uint32_t>(), s);
+    DBI_CUDA(cudaStreamSynchronize(s));
+  }
+  return check_err_bits(read_err(h));
+  DBI_API_END
+}
+
+int dbi_mg_expand(dbi_handle* h, uint32_t tile_begin, uint32_t n_tiles, uint64_t* n_variants) {
+  DBI_API_BEGIN(h)
+  const KeySpace ks(h->p.min_mass, h->p.max_mass);
+  const uint64_t all_tiles = (h->n_unique + kModTile - 1) / kModTile;
+  if ((uint64_t)tile_begin + n_tiles > all_tiles) {
+    set_error("tile range [%u, +%u) beyond %llu tiles", tile_begin, n_tiles, (unsigned long long)all_tiles);
+    return DBI_EINVAL;
+  }
+  uint64_t V = 0;
+  int rc = emit_variants(h, tile_begin, n_tiles, ks, h->mg_vkey, h->mg_vpay, &V);
+  DBI_CUDA(cudaStreamSynchronize(h->stream));
+  h->mg_v = V;
+  if (n_variants) *n_variants = V;
+  return rc;
+  DBI_API_END
+}
+
+int dbi_mg_index_variants(dbi_handle* h, void* d_key, void* d_payload, uint64_t n) {
+  DBI_API_BEGIN(h)
+  if (n && (!d_key || !d_payload)) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  const KeySpace ks(h->p.min_mass, h->p.max_mass);
+  int rc = sort_variants(h, (uint64_t*)d_key, (uint64_t*)d_payload, n, ks);
+  DBI_CUDA(cudaStreamSynchronize(h->stream));
+  if (rc != DBI_OK) return rc;
+  h->built = true;
+  finish_stats(h);
   return DBI_OK;
   DBI_API_END
 }

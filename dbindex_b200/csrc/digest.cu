@@ -80,12 +80,12 @@ __device__ __forceinline__ uint32_t walk_start(const uint8_t* __restrict__ res, 
 // ---- K2 -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(DG_THREADS)
     digest_count_kernel(const uint8_t* __restrict__ res, uint32_t res_end, const DevTables* __restrict__ tb,
-                        DigestCfg cfg, uint32_t* __restrict__ tile_counts, uint32_t* err) {
+                        DigestCfg cfg, uint32_t tile0, uint32_t* __restrict__ tile_counts, uint32_t* err) {
   __shared__ TileTables tt;
   __shared__ uint32_t scratch[DG_THREADS / 32 + 1];
   load_tables(tt, tb);
   __syncthreads();
-  const uint32_t tile_base = 1u + blockIdx.x * (uint32_t)kDigestTile;
+  const uint32_t tile_base = 1u + (tile0 + blockIdx.x) * (uint32_t)kDigestTile;
   uint32_t cnt = 0;
 #pragma unroll 1
   for (int k = 0; k < DG_SPT; ++k) {
@@ -100,15 +100,15 @@ __global__ void __launch_bounds__(DG_THREADS)
 // ---- K4 -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(DG_THREADS)
     digest_emit_kernel(const uint8_t* __restrict__ res, uint32_t res_end, const DevTables* __restrict__ tb,
-                       DigestCfg cfg, const uint64_t* __restrict__ tile_offs, const uint32_t* __restrict__ pstart,
-                       uint32_t n_prot, uint64_t* __restrict__ o_mass, uint32_t* __restrict__ o_gpos,
+                       DigestCfg cfg, uint32_t tile0, const uint64_t* __restrict__ tile_offs,
+                       const uint32_t* __restrict__ pstart, uint32_t n_prot, uint64_t* __restrict__ o_mass, uint32_t* __restrict__ o_gpos,
                        uint32_t* __restrict__ o_prot, uint16_t* __restrict__ o_len, uint32_t* err) {
   __shared__ TileTables tt;
   __shared__ uint32_t s_cnt[kDigestTile];
   __shared__ uint32_t scratch[DG_THREADS / 32 + 1];
   load_tables(tt, tb);
   __syncthreads();
-  const uint32_t tile_base = 1u + blockIdx.x * (uint32_t)kDigestTile;
+  const uint32_t tile_base = 1u + (tile0 + blockIdx.x) * (uint32_t)kDigestTile;
   // pass A: records per start, start i of the tile handled by thread i % DG_THREADS
 #pragma unroll 1
   for (int k = 0; k < DG_SPT; ++k) {
@@ -220,9 +220,9 @@ void launch_pack(const uint8_t* d_raw, const uint64_t* d_off, uint32_t n_prot, u
 }
 
 void launch_digest_count(const uint8_t* d_res, uint32_t res_end, const DevTables* d_tb, const DigestCfg& cfg,
-                         uint32_t* d_tile_counts, uint32_t* d_err, cudaStream_t s) {
-  const unsigned tiles = (res_end + kDigestTile - 1) / kDigestTile;
-  DBI_LAUNCH(digest_count_kernel, tiles, DG_THREADS, 0, s, d_res, res_end, d_tb, cfg, d_tile_counts, d_err);
+                         uint32_t tile0, uint32_t ntiles, uint32_t* d_tile_counts, uint32_t* d_err, cudaStream_t s) {
+  if (ntiles == 0) return;
+  DBI_LAUNCH(digest_count_kernel, ntiles, DG_THREADS, 0, s, d_res, res_end, d_tb, cfg, tile0, d_tile_counts, d_err);
 }
 
 void launch_scan_u32_to_u64(const uint32_t* d_in, uint64_t n, uint64_t* d_offs, cudaStream_t s) {
@@ -230,11 +230,12 @@ void launch_scan_u32_to_u64(const uint32_t* d_in, uint64_t n, uint64_t* d_offs, 
 }
 
 void launch_digest_emit(const uint8_t* d_res, uint32_t res_end, const DevTables* d_tb, const DigestCfg& cfg,
-                        const uint64_t* d_tile_offs, const uint32_t* d_pstart, uint32_t n_prot, uint64_t* o_mass,
-                        uint32_t* o_gpos, uint32_t* o_prot, uint16_t* o_len, uint32_t* d_err, cudaStream_t s) {
-  const unsigned tiles = (res_end + kDigestTile - 1) / kDigestTile;
-  DBI_LAUNCH(digest_emit_kernel, tiles, DG_THREADS, 0, s, d_res, res_end, d_tb, cfg, d_tile_offs, d_pstart, n_prot,
-             o_mass, o_gpos, o_prot, o_len, d_err);
+                        uint32_t tile0, uint32_t ntiles, const uint64_t* d_tile_offs, const uint32_t* d_pstart,
+                        uint32_t n_prot, uint64_t* o_mass, uint32_t* o_gpos, uint32_t* o_prot, uint16_t* o_len,
+                        uint32_t* d_err, cudaStream_t s) {
+  if (ntiles == 0) return;
+  DBI_LAUNCH(digest_emit_kernel, ntiles, DG_THREADS, 0, s, d_res, res_end, d_tb, cfg, tile0, d_tile_offs, d_pstart,
+             n_prot, o_mass, o_gpos, o_prot, o_len, d_err);
 }
 
 }  // namespace dbi

@@ -38,16 +38,19 @@ void launch_pack(const uint8_t* d_raw, const uint64_t* d_off, uint32_t n_prot, u
                  uint32_t* d_pstart, uint32_t* d_err, cudaStream_t s);
 
 // K2: per-tile count of the records cutSeq emits.
+// Tiles [tile0, tile0 + ntiles) of kDigestTile start positions each (a multi-GPU rank digests
+// only its own tile range of the replicated buffer).
 void launch_digest_count(const uint8_t* d_res, uint32_t res_end, const DevTables* d_tb, const DigestCfg& cfg,
-                         uint32_t* d_tile_counts, uint32_t* d_err, cudaStream_t s);
+                         uint32_t tile0, uint32_t ntiles, uint32_t* d_tile_counts, uint32_t* d_err, cudaStream_t s);
 
 // K3: exclusive scan of u32 tile counts into u64 offsets; offs[n] = total.
 void launch_scan_u32_to_u64(const uint32_t* d_in, uint64_t n, uint64_t* d_offs, cudaStream_t s);
 
 // K4: emit (mass bits, gpos, prot, len) in (protein, start, end) order.
 void launch_digest_emit(const uint8_t* d_res, uint32_t res_end, const DevTables* d_tb, const DigestCfg& cfg,
-                        const uint64_t* d_tile_offs, const uint32_t* d_pstart, uint32_t n_prot, uint64_t* o_mass,
-                        uint32_t* o_gpos, uint32_t* o_prot, uint16_t* o_len, uint32_t* d_err, cudaStream_t s);
+                        uint32_t tile0, uint32_t ntiles, const uint64_t* d_tile_offs, const uint32_t* d_pstart,
+                        uint32_t n_prot, uint64_t* o_mass, uint32_t* o_gpos, uint32_t* o_prot, uint16_t* o_len,
+                        uint32_t* d_err, cudaStream_t s);
 
 // ---- sort helpers / K8 dedup -------------------------------------------------
 // hash[i] = seeded 32-bit hash of the residues of record i; idx[i] = i.
@@ -67,13 +70,15 @@ void launch_dedup_emit(const uint64_t* skey, const uint32_t* sidx, const uint8_t
                        uint16_t* u_len, uint64_t* u_plo, uint32_t* plist, cudaStream_t s);
 
 // ---- K5/K6 differential-mod expansion ---------------------------------------
+// Tiles [tile0, tile0 + ntiles) of kModTile base peptides; counts[] is indexed by the global
+// base id, tile_counts[] / tile_offs[] by (tile - tile0).
 void launch_mod_count(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const double* u_mass,
-                      const uint32_t* u_gpos, const uint16_t* u_len, uint64_t n_unique, uint32_t* counts,
-                      uint32_t* tile_counts, uint32_t* d_err, cudaStream_t s);
+                      const uint32_t* u_gpos, const uint16_t* u_len, uint64_t n_unique, uint32_t tile0,
+                      uint32_t ntiles, uint32_t* counts, uint32_t* tile_counts, uint32_t* d_err, cudaStream_t s);
 void launch_mod_emit(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const double* u_mass,
-                     const uint32_t* u_gpos, const uint16_t* u_len, uint64_t n_unique, const uint32_t* counts,
-                     const uint64_t* tile_offs, uint64_t base_bits, uint64_t* v_key, uint64_t* v_payload,
-                     cudaStream_t s);
+                     const uint32_t* u_gpos, const uint16_t* u_len, uint64_t n_unique, uint32_t tile0,
+                     uint32_t ntiles, const uint32_t* counts, const uint64_t* tile_offs, uint64_t base_bits,
+                     uint64_t* v_key, uint64_t* v_payload, cudaStream_t s);
 // entries from sorted (key, payload): mass = bits(key + base), base id, mod pattern
 void launch_split_entries(const uint64_t* skey, const uint64_t* spayload, uint64_t n, uint64_t base_bits,
                           double* e_mass, uint32_t* e_base, uint32_t* e_pat, cudaStream_t s);
@@ -83,11 +88,11 @@ void launch_query(const double* e_mass, uint64_t n_entries, const double* lo, co
                   uint64_t* hit_begin, uint64_t* hit_count, cudaStream_t s);
 // per-entry protein-list length for entries [begin, begin+count) + per-tile sums.
 // e_base == nullptr means "entry i is unique peptide i" (no differential mods).
-void launch_fetch_sizes(const uint32_t* e_base, const uint64_t* u_plo, uint64_t begin, uint64_t count,
-                        uint32_t* sizes, uint32_t* tile_counts, cudaStream_t s);
+void launch_fetch_sizes(const uint32_t* e_base, uint64_t base_off, const uint64_t* u_plo, uint64_t begin,
+                        uint64_t count, uint32_t* sizes, uint32_t* tile_counts, cudaStream_t s);
 // what parseAddPeptideInfo materialises per hit; any output may be nullptr.
-void launch_fetch_gather(const double* e_mass, const uint32_t* e_base, const uint32_t* e_pat, const uint32_t* u_gpos,
-                         const uint32_t* u_prot, const uint16_t* u_len, const uint64_t* u_plo, const uint32_t* plist,
+void launch_fetch_gather(const double* e_mass, const uint32_t* e_base, uint64_t base_off, const uint32_t* e_pat,
+                         const uint32_t* u_gpos, const uint32_t* u_prot, const uint16_t* u_len, const uint64_t* u_plo, const uint32_t* plist,
                          const uint32_t* pstart, uint64_t begin, uint64_t count, const uint32_t* sizes,
                          const uint64_t* tile_offs, double* o_mass, uint32_t* o_prot, uint32_t* o_off,
                          uint16_t* o_len, uint32_t* o_pat, uint64_t* o_list_off, uint32_t* o_ids, cudaStream_t s);
@@ -96,5 +101,22 @@ void launch_key_flags(const double* e_mass, uint64_t n, double factor, uint8_t* 
                       cudaStream_t s);
 void launch_key_emit(const double* e_mass, uint64_t n, double factor, const uint8_t* flags,
                      const uint64_t* tile_offs, int32_t* keys, cudaStream_t s);
+
+// ---- multi-GPU exchange helpers (mg.cu) -----------------------------------------------------
+constexpr int kMgBins = 4096;  // histogram bins over the top bits of the radix key
+// hist[min(kMgBins-1, (key[i] - sub) >> shift)] += 1   (hist is zeroed by the caller)
+void launch_mg_hist(const uint64_t* key, uint64_t n, uint64_t sub, int shift, unsigned long long* hist,
+                    cudaStream_t s);
+// dest[i] = number of thresholds <= (key[i] - sub); idx[i] = i; counts[dest] += 1
+void launch_mg_dest(const uint64_t* key, uint64_t n, uint64_t sub, const uint64_t* thresholds, int n_thr,
+                    uint32_t* dest, uint32_t* idx, unsigned long long* counts, cudaStream_t s);
+void launch_gather_u64(const uint64_t* src, const uint32_t* idx, uint64_t n, uint64_t* dst, cudaStream_t s);
+void launch_gather_u32(const uint32_t* src, const uint32_t* idx, uint64_t n, uint32_t* dst, cudaStream_t s);
+void launch_gather_u16(const uint16_t* src, const uint32_t* idx, uint64_t n, uint16_t* dst, cudaStream_t s);
+// list length of every unique peptide: cnt[u] = plo[u+1] - plo[u]
+void launch_plo_to_counts(const uint64_t* plo, uint64_t n, uint32_t* cnt, cudaStream_t s);
+// full exclusive scan: offs[i] = sum(in[0..i)), offs[n] = total; tmp = (ntiles + 1) u64 + ntiles u32
+void launch_full_scan_u32_to_u64(const uint32_t* in, uint64_t n, uint64_t* offs, void* tmp, cudaStream_t s);
+size_t full_scan_tmp_bytes(uint64_t n);
 
 }  // namespace dbi

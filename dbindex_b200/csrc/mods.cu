@@ -51,7 +51,7 @@ __device__ __forceinline__ void load_mod_tables(ModTables& mt, const DevTables* 
 
 // Heaviest peptides first: the bases are mass-sorted and the variant count grows like the
 // cube of the site count, so the last tiles carry orders of magnitude more work.
-__device__ __forceinline__ uint32_t mod_tile() { return gridDim.x - 1 - blockIdx.x; }
+__device__ __forceinline__ uint32_t mod_tile_local() { return gridDim.x - 1 - blockIdx.x; }
 
 // Gated count of one peptide with one lane per class SEQUENCE (n_seq <= 32).  The variant mass
 // depends only on the sequence of shift classes along the chosen sites, so
@@ -164,8 +164,8 @@ __device__ __forceinline__ void decode_variant(uint32_t r, uint32_t n, int K, do
 __global__ void __launch_bounds__(MD_THREADS)
     mod_count_kernel(const uint8_t* __restrict__ res, const DevTables* __restrict__ tb, DigestCfg cfg,
                      const double* __restrict__ u_mass, const uint32_t* __restrict__ u_gpos,
-                     const uint16_t* __restrict__ u_len, uint64_t n_unique, uint32_t* __restrict__ counts,
-                     uint32_t* __restrict__ tile_counts, uint32_t* err) {
+                     const uint16_t* __restrict__ u_len, uint64_t n_unique, uint32_t tile0,
+                     uint32_t* __restrict__ counts, uint32_t* __restrict__ tile_counts, uint32_t* err) {
   __shared__ ModTables mt;
   __shared__ WarpSites wsites[MD_WARPS];
   __shared__ uint32_t wsum[MD_WARPS];
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(MD_THREADS)
   const int w = threadIdx.x >> 5;
   const unsigned l = lane_id();
   WarpSites& ws = wsites[w];
-  const uint64_t u0 = (uint64_t)mod_tile() * kModTile + (uint64_t)w * MD_PER_WARP;
+  const uint64_t u0 = (uint64_t)(tile0 + mod_tile_local()) * kModTile + (uint64_t)w * MD_PER_WARP;
   const int K = cfg.max_mods;
   uint32_t sum = 0;
   for (int q = 0; q < MD_PER_WARP; ++q) {
@@ -215,16 +215,16 @@ __global__ void __launch_bounds__(MD_THREADS)
   if (threadIdx.x == 0) {
     uint32_t t = 0;
     for (int i = 0; i < MD_WARPS; ++i) t += wsum[i];
-    tile_counts[mod_tile()] = t;
+    tile_counts[mod_tile_local()] = t;
   }
 }
 
 __global__ void __launch_bounds__(MD_THREADS)
     mod_emit_kernel(const uint8_t* __restrict__ res, const DevTables* __restrict__ tb, DigestCfg cfg,
                     const double* __restrict__ u_mass, const uint32_t* __restrict__ u_gpos,
-                    const uint16_t* __restrict__ u_len, uint64_t n_unique, const uint32_t* __restrict__ counts,
-                    const uint64_t* __restrict__ tile_offs, uint64_t base_bits, uint64_t* __restrict__ v_key,
-                    uint64_t* __restrict__ v_payload) {
+                    const uint16_t* __restrict__ u_len, uint64_t n_unique, uint32_t tile0,
+                    const uint32_t* __restrict__ counts, const uint64_t* __restrict__ tile_offs, uint64_t base_bits,
+                    uint64_t* __restrict__ v_key, uint64_t* __restrict__ v_payload) {
   __shared__ ModTables mt;
   __shared__ WarpSites wsites[MD_WARPS];
   __shared__ uint32_t wsum[MD_WARPS];
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(MD_THREADS)
   const int w = threadIdx.x >> 5;
   const unsigned l = lane_id();
   WarpSites& ws = wsites[w];
-  const uint64_t u0 = (uint64_t)mod_tile() * kModTile + (uint64_t)w * MD_PER_WARP;
+  const uint64_t u0 = (uint64_t)(tile0 + mod_tile_local()) * kModTile + (uint64_t)w * MD_PER_WARP;
   // output offset of this warp's first base: tile offset + counts of the earlier warps' bases
   uint32_t part = 0;
   for (int q = l; q < MD_PER_WARP; q += 32) {
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(MD_THREADS)
   for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
   if (l == 0) wsum[w] = part;
   __syncthreads();
-  uint64_t out = tile_offs[mod_tile()];
+  uint64_t out = tile_offs[mod_tile_local()];
   for (int i = 0; i < w; ++i) out += wsum[i];
 
   const int K = cfg.max_mods;
@@ -303,22 +303,20 @@ __global__ void __launch_bounds__(MD_THREADS)
 }  // namespace
 
 void launch_mod_count(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const double* u_mass,
-                      const uint32_t* u_gpos, const uint16_t* u_len, uint64_t n_unique, uint32_t* counts,
-                      uint32_t* tile_counts, uint32_t* d_err, cudaStream_t s) {
-  if (n_unique == 0) return;
-  const unsigned tiles = (unsigned)((n_unique + kModTile - 1) / kModTile);
-  DBI_LAUNCH(mod_count_kernel, tiles, MD_THREADS, 0, s, d_res, d_tb, cfg, u_mass, u_gpos, u_len, n_unique, counts,
-             tile_counts, d_err);
+                      const uint32_t* u_gpos, const uint16_t* u_len, uint64_t n_unique, uint32_t tile0,
+                      uint32_t ntiles, uint32_t* counts, uint32_t* tile_counts, uint32_t* d_err, cudaStream_t s) {
+  if (n_unique == 0 || ntiles == 0) return;
+  DBI_LAUNCH(mod_count_kernel, ntiles, MD_THREADS, 0, s, d_res, d_tb, cfg, u_mass, u_gpos, u_len, n_unique, tile0,
+             counts, tile_counts, d_err);
 }
 
 void launch_mod_emit(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const double* u_mass,
-                     const uint32_t* u_gpos, const uint16_t* u_len, uint64_t n_unique, const uint32_t* counts,
-                     const uint64_t* tile_offs, uint64_t base_bits, uint64_t* v_key, uint64_t* v_payload,
-                     cudaStream_t s) {
-  if (n_unique == 0) return;
-  const unsigned tiles = (unsigned)((n_unique + kModTile - 1) / kModTile);
-  DBI_LAUNCH(mod_emit_kernel, tiles, MD_THREADS, 0, s, d_res, d_tb, cfg, u_mass, u_gpos, u_len, n_unique, counts,
-             tile_offs, base_bits, v_key, v_payload);
+                     const uint32_t* u_gpos, const uint16_t* u_len, uint64_t n_unique, uint32_t tile0,
+                     uint32_t ntiles, const uint32_t* counts, const uint64_t* tile_offs, uint64_t base_bits,
+                     uint64_t* v_key, uint64_t* v_payload, cudaStream_t s) {
+  if (n_unique == 0 || ntiles == 0) return;
+  DBI_LAUNCH(mod_emit_kernel, ntiles, MD_THREADS, 0, s, d_res, d_tb, cfg, u_mass, u_gpos, u_len, n_unique, tile0,
+             counts, tile_offs, base_bits, v_key, v_payload);
 }
 
 void launch_split_entries(const uint64_t* skey, const uint64_t* spayload, uint64_t n, uint64_t base_bits,

@@ -47,15 +47,16 @@ __global__ void __launch_bounds__(Q_THREADS)
 }
 
 __global__ void __launch_bounds__(Q_THREADS)
-    fetch_sizes_kernel(const uint32_t* __restrict__ e_base, const uint64_t* __restrict__ u_plo, uint64_t begin,
-                       uint64_t count, uint32_t* __restrict__ sizes, uint32_t* __restrict__ tile_counts) {
+    fetch_sizes_kernel(const uint32_t* __restrict__ e_base, uint64_t base_off, const uint64_t* __restrict__ u_plo,
+                       uint64_t begin, uint64_t count, uint32_t* __restrict__ sizes,
+                       uint32_t* __restrict__ tile_counts) {
   __shared__ uint32_t scratch[Q_THREADS / 32 + 1];
   const uint64_t tile_base = (uint64_t)blockIdx.x * kScanTile;
   uint32_t sum = 0;
   for (int k = 0; k < Q_IPT; ++k) {
     const uint64_t i = tile_base + (uint64_t)k * Q_THREADS + threadIdx.x;
     if (i >= count) break;
-    const uint64_t b = e_base ? (uint64_t)e_base[begin + i] : begin + i;
+    const uint64_t b = e_base ? (uint64_t)e_base[begin + i] : base_off + begin + i;
     const uint32_t sz = (uint32_t)(u_plo[b + 1] - u_plo[b]);
     sizes[i] = sz;
     sum += sz;
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(Q_THREADS)
 }
 
 __global__ void __launch_bounds__(Q_THREADS)
-    fetch_gather_kernel(const double* __restrict__ e_mass, const uint32_t* __restrict__ e_base,
+    fetch_gather_kernel(const double* __restrict__ e_mass, const uint32_t* __restrict__ e_base, uint64_t base_off,
                         const uint32_t* __restrict__ e_pat, const uint32_t* __restrict__ u_gpos,
                         const uint32_t* __restrict__ u_prot, const uint16_t* __restrict__ u_len,
                         const uint64_t* __restrict__ u_plo, const uint32_t* __restrict__ plist,
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(Q_THREADS)
     const uint32_t ex = block_exclusive_sum<uint32_t, Q_THREADS>(sz, scratch, &total);
     if (valid) {
       const uint64_t e = begin + i;
-      const uint64_t b = e_base ? (uint64_t)e_base[e] : e;
+      const uint64_t b = e_base ? (uint64_t)e_base[e] : base_off + e;
       const uint32_t pr = u_prot[b];
       if (o_mass) o_mass[i] = e_mass[e];
       if (o_prot) o_prot[i] = pr;
@@ -152,21 +153,21 @@ void launch_query(const double* e_mass, uint64_t n_entries, const double* lo, co
   DBI_LAUNCH(query_kernel, grid, Q_THREADS, 0, s, e_mass, n_entries, lo, hi, nq, hit_begin, hit_count);
 }
 
-void launch_fetch_sizes(const uint32_t* e_base, const uint64_t* u_plo, uint64_t begin, uint64_t count,
-                        uint32_t* sizes, uint32_t* tile_counts, cudaStream_t s) {
+void launch_fetch_sizes(const uint32_t* e_base, uint64_t base_off, const uint64_t* u_plo, uint64_t begin,
+                        uint64_t count, uint32_t* sizes, uint32_t* tile_counts, cudaStream_t s) {
   if (count == 0) return;
   const unsigned tiles = (unsigned)((count + kScanTile - 1) / kScanTile);
-  DBI_LAUNCH(fetch_sizes_kernel, tiles, Q_THREADS, 0, s, e_base, u_plo, begin, count, sizes, tile_counts);
+  DBI_LAUNCH(fetch_sizes_kernel, tiles, Q_THREADS, 0, s, e_base, base_off, u_plo, begin, count, sizes, tile_counts);
 }
 
-void launch_fetch_gather(const double* e_mass, const uint32_t* e_base, const uint32_t* e_pat, const uint32_t* u_gpos,
-                         const uint32_t* u_prot, const uint16_t* u_len, const uint64_t* u_plo, const uint32_t* plist,
+void launch_fetch_gather(const double* e_mass, const uint32_t* e_base, uint64_t base_off, const uint32_t* e_pat,
+                         const uint32_t* u_gpos, const uint32_t* u_prot, const uint16_t* u_len, const uint64_t* u_plo, const uint32_t* plist,
                          const uint32_t* pstart, uint64_t begin, uint64_t count, const uint32_t* sizes,
                          const uint64_t* tile_offs, double* o_mass, uint32_t* o_prot, uint32_t* o_off,
                          uint16_t* o_len, uint32_t* o_pat, uint64_t* o_list_off, uint32_t* o_ids, cudaStream_t s) {
   if (count == 0) return;
   const unsigned tiles = (unsigned)((count + kScanTile - 1) / kScanTile);
-  DBI_LAUNCH(fetch_gather_kernel, tiles, Q_THREADS, 0, s, e_mass, e_base, e_pat, u_gpos, u_prot, u_len, u_plo, plist,
+  DBI_LAUNCH(fetch_gather_kernel, tiles, Q_THREADS, 0, s, e_mass, e_base, base_off, e_pat, u_gpos, u_prot, u_len, u_plo, plist,
              pstart, begin, count, sizes, tile_offs, o_mass, o_prot, o_off, o_len, o_pat, o_list_off, o_ids);
 }
 

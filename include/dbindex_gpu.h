@@ -237,6 +237,65 @@ int dbi_debug_emitted(dbi_handle* h, uint64_t capacity, double* mass, uint32_t* 
 int dbi_build_from_records(dbi_handle* h, const double* mass, const uint32_t* prot,
                            const uint32_t* off, const uint16_t* len, uint64_t n);
 
+/* ---- multi-GPU staged build -----------------------------------------
+ * One process and one handle per GPU.  Every rank adds the SAME proteins (the residue
+ * buffer is replicated, 3 GB even at TrEMBL scale), digests only its own range of start
+ * positions, and the ranks exchange records so that rank d ends up with one contiguous
+ * mass slice -- the GPU analogue of DBIndexStoreSQLiteMult's per-bucket SQLite files
+ * (DBIndexStoreSQLiteMult.java:55-56,215-217).  The collectives themselves (all-reduce of
+ * the histograms, all-to-all of the records, broadcast of the unique tables) are issued by
+ * the host over NCCL on caller-owned device buffers; these entry points are the device work
+ * between them.  dbindex_b200/multigpu.py is the reference orchestration.  All `d_` pointers
+ * are device memory of the handle's GPU.
+ *
+ *   dbi_mg_begin -> dbi_mg_digest
+ *   -> dbi_mg_histogram(0) .. all-reduce .. dbi_mg_partition(0) -> dbi_mg_pack_send(0) .. all-to-all ..
+ *   -> dbi_mg_index_base -> dbi_mg_export_unique .. broadcast from every rank .. dbi_mg_import_unique
+ *   no mods:  -> dbi_mg_finish
+ *   mods:     -> dbi_mg_mod_tile_counts .. all-gather .. dbi_mg_expand
+ *             -> dbi_mg_histogram(1) .. dbi_mg_partition(1) -> dbi_mg_pack_send(1) .. all-to-all ..
+ *             -> dbi_mg_index_variants
+ */
+#define DBI_MG_BINS 4096
+int dbi_mg_begin(dbi_handle* h, int rank, int world);
+/* pack the replicated proteome, digest this rank's share of the start positions */
+int dbi_mg_digest(dbi_handle* h, uint64_t* n_records);
+/* stage 0 = digested records, 1 = mod variants: d_hist[DBI_MG_BINS] (u64) += histogram of
+ * (radix key >> *shift) */
+int dbi_mg_histogram(dbi_handle* h, int stage, uint64_t* d_hist, int* shift);
+/* bin_splitters[world-1] (host, ascending bin indices): items whose bin >= bin_splitters[d-1]
+ * go to rank >= d.  send_counts[world] (host) receives how many items go to each rank. */
+int dbi_mg_partition(dbi_handle* h, int stage, const uint32_t* bin_splitters, uint64_t* send_counts);
+/* items grouped by destination rank (stable) into caller buffers.  stage 0: d0 = mass bits
+ * u64[n], d1 = gpos u32[n], d2 = prot u32[n], d3 = len u16[n]; stage 1: d0 = key u64[n],
+ * d1 = payload u64[n]. */
+int dbi_mg_pack_send(dbi_handle* h, int stage, void* d0, void* d1, void* d2, void* d3);
+/* sort + merge the n records received for this rank's mass slice (rank-ordered receive
+ * buffers keep the global emission order, so "first occurrence" stays global) */
+int dbi_mg_index_base(dbi_handle* h, const void* d_mass, const void* d_gpos, const void* d_prot,
+                      const void* d_len, uint64_t n);
+int dbi_mg_unique_counts(dbi_handle* h, uint64_t* n_unique, uint64_t* n_plist);
+/* copy the local unique tables out: mass f64[u], gpos u32[u], prot u32[u], len u16[u],
+ * protein-list length u32[u], protein ids u32[n_plist] */
+int dbi_mg_export_unique(dbi_handle* h, void* d_mass, void* d_gpos, void* d_prot, void* d_len, void* d_pcnt,
+                         void* d_plist);
+/* adopt the rank-order concatenation of every rank's tables as the (replicated) global
+ * unique tables; this rank's slice is [sum(rank_unique[0..rank)), +rank_unique[rank]) */
+int dbi_mg_import_unique(dbi_handle* h, const uint64_t* rank_unique, const uint64_t* rank_plist,
+                         const void* d_mass, const void* d_gpos, const void* d_prot, const void* d_len,
+                         const void* d_pcnt, const void* d_plist);
+/* no differential mods: the entries of this rank are its slice of the unique tables */
+int dbi_mg_finish(dbi_handle* h);
+/* variant counts of the mod tiles (256 unique peptides each) that START in this rank's
+ * slice: *tile_begin, *n_tiles, and d_tile_counts[0..*n_tiles) (u32, capacity >= slice/256 + 2) */
+int dbi_mg_mod_tile_counts(dbi_handle* h, uint32_t* tile_begin, uint32_t* n_tiles, void* d_tile_counts);
+/* expand the variants of tiles [tile_begin, tile_begin + n_tiles) of the global tables (any
+ * range: the tables are replicated, so the host can balance by variant count) */
+int dbi_mg_expand(dbi_handle* h, uint32_t tile_begin, uint32_t n_tiles, uint64_t* n_variants);
+/* sort the n variants received for this rank's variant-mass slice into its entry arrays;
+ * d_key / d_payload are clobbered */
+int dbi_mg_index_variants(dbi_handle* h, void* d_key, void* d_payload, uint64_t n);
+
 /* Test hook for K7: stable radix sort of n host (key, value) pairs on key bits
  * [begin_bit, end_bit), in place, on the handle's GPU. */
 int dbi_debug_radix_sort(dbi_handle* h, uint64_t* keys, uint64_t* vals, uint64_t n, int begin_bit, int end_bit);
