@@ -56,53 +56,66 @@ def measured_traffic(kernel: str, units: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML every 5 ms from a thread, started at the
+    first warm-up step (same load as the timed steps) and stopped right after the timed region."""
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = False
+        self._thr = None
 
     def start(self):
+        import threading
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "200", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except (ValueError, IndexError):
+                    idx = self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.p = None
+            return
+        names = {
+            getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+
+        def loop():
+            while not self._stop:
+                try:
+                    self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    try:
+                        r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                time.sleep(0.005)
+
+        self._thr = threading.Thread(target=loop, daemon=True)
+        self._thr.start()
 
     def stop(self) -> dict:
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, smax, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1])); smax.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        try:
-            os.unlink(self.f.name)
-        except OSError:
-            pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+        self._stop = True
+        if self._thr is not None:
+            self._thr.join(timeout=2)
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
+               "how": "NVML, 5 ms period, warm-up + timed steps"}
+        if self.samples:
+            out["sm_mhz"] = float(np.median(self.samples))
         return out
 
 
@@ -181,6 +194,150 @@ def run_reference(args, rank: int, world: int):
     print(json.dumps(line), flush=True)
 
 
+def run_sharded(args, rank: int, local_rank: int, world: int):
+    """N > 1: ONE index over world x 20000 proteins (weak scaling), built with the real exchange:
+    replicated residues, range-sharded digestion, NCCL all-to-all of the peptide records by mass
+    slice, replicated unique tables, variant all-to-all by variant mass, routed queries."""
+    import torch
+    import torch.distributed as dist
+    import dbindex_b200 as dbi
+    from dbindex_b200 import synth
+    from dbindex_b200.multigpu import GpuShardEngine, build_sharded, route_queries
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    lib = dbi.load_library()
+    res, off = synth.config_proteome(2, args.proteins * world)  # same on every rank
+    params = dbi.default_params(**CFG2)
+    params.device = local_rank
+    params.profile = 1
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    g = dbi.GpuIndex(params)
+    g.set_stream(stream.cuda_stream)
+    g.add_proteins(res, off)
+    g.upload()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    nq = args.queries * world
+    info = build_sharded(GpuShardEngine(g, dev))  # also warms NCCL up
+    masses = sample_index_masses(g, g.stats()["n_entries"])
+    # every rank contributes samples of its own slice so that the queries cover the whole range
+    gathered = [None] * world
+    dist.all_gather_object(gathered, masses[:: max(1, len(masses) // 4096)].tolist())
+    allm = np.sort(np.concatenate([np.asarray(x) for x in gathered]))
+    _, _, lo, hi = synth.synth_queries(allm, nq, 20240602)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    step_ms, query_ms, a2a_ms, a2a_bytes = [], [], 0.0, 0
+    dom_ms = dom_launches = 0
+    dom_bytes = 0
+    clocks = ClockSampler(local_rank)
+    launches0 = 0
+    hits = 0
+    clocks.start()
+    for i in range(args.warmup + args.steps):
+        if i == args.warmup:
+            barrier()
+            launches0 = lib.dbi_kernel_launches()
+        g.reset_index()
+        flush.zero_()
+        dist.barrier()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(stream)
+        info = build_sharded(GpuShardEngine(g, dev))
+        e1.record(stream)
+        sel = route_queries(lo, hi, info["split_mass"], rank)
+        d_lo = torch.from_numpy(lo[sel]).cuda()
+        d_hi = torch.from_numpy(hi[sel]).cuda()
+        d_b = torch.empty(len(sel), dtype=torch.int64, device="cuda")
+        d_c = torch.empty(len(sel), dtype=torch.int64, device="cuda")
+        stream.synchronize()
+        g.query_device(d_lo.data_ptr(), d_hi.data_ptr(), len(sel), d_b.data_ptr(), d_c.data_ptr())
+        e2.record(stream)
+        torch.cuda.synchronize()
+        if i >= args.warmup:
+            step_ms.append(e0.elapsed_time(e2))
+            query_ms.append(e1.elapsed_time(e2))
+            a2a_ms += info["a2a_ms"]
+            a2a_bytes += info["a2a_bytes"]
+            st = g.stats()
+            dom_ms += st["dom_ms"]; dom_launches += st["dom_launches"]; dom_bytes = st["dom_bytes_per_launch"]
+            hits = int(d_c.sum().item())
+    barrier()
+    n_launch = lib.dbi_kernel_launches() - launches0
+    clk = clocks.stop()
+    st = g.stats()
+    n_entries = st["n_entries"]
+
+    # ---- e2e: fresh handle, host buffers, copies and routing inside the timed region ----
+    e2e_ms = []
+    for i in range(1 + max(1, min(args.steps, 3))):
+        flush.zero_()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        p2 = params.copy(); p2.profile = 0
+        g2 = dbi.GpuIndex(p2)
+        g2.set_stream(stream.cuda_stream)
+        g2.add_proteins(res, off)
+        inf2 = build_sharded(GpuShardEngine(g2, dev))
+        sel = route_queries(lo, hi, inf2["split_mass"], rank)
+        hb, hc = g2.query(lo[sel], hi[sel])
+        b.record(stream)
+        torch.cuda.synchronize()
+        g2.close()
+        if i >= 1:
+            e2e_ms.append(a.elapsed_time(b))
+
+    t = torch.tensor([float(sum(step_ms)), float(sum(query_ms)), float(sum(e2e_ms)) / len(e2e_ms), a2a_ms],
+                     device="cuda", dtype=torch.float64)
+    u = torch.tensor([float(n_entries), float(n_launch), float(hits), float(a2a_bytes)], device="cuda",
+                     dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    tot_ms, q_ms, e2e_step_ms, a2a_max_ms = t.tolist()
+    entries_all, launches_all, hits_all, a2a_all = u.tolist()
+    K = args.steps
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        achieved = (dom_bytes / 1e9) / ((dom_ms / max(dom_launches, 1)) / 1e3) if dom_launches else None
+        line = {
+            "metric": METRIC, "value": entries_all * K / (tot_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": args.warmup, "ms_per_step": tot_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD.replace("20000 proteins", f"{args.proteins} proteins per GPU"),
+                       "proteins_total": args.proteins * world, "residues_total": int(res.nbytes),
+                       "entries_total": int(entries_all), "unique_total": info["n_unique"],
+                       "queries": nq, "l2": "flushed between iterations (256 MiB write)",
+                       "parallelism": f"{world} GPUs: replicated residues, range-sharded digest, NCCL all-to-all by "
+                                      "mass slice (records, then mod variants), routed queries"},
+            "queries": {"value": nq * K / (q_ms / 1e3), "unit": "queries/s", "hits_per_batch": int(hits_all),
+                        "ms_per_batch": q_ms / K, "includes": "host routing + H2D of the routed queries"},
+            "all_to_all": {"bytes_per_step_all_ranks": a2a_all / K, "ms_per_step_max_rank": a2a_max_ms / K,
+                           "bus_gbs_per_gpu": (a2a_all / K / world / 1e9) / max(a2a_max_ms / K / 1e3, 1e-12),
+                           "nvlink_ref_gbs": 770.0},
+            "roofline": {"bound": "hbm", "kernel": "rs_onesweep_kernel<u64,u64>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
+                         "bytes_per_launch": dom_bytes, "launches": dom_launches,
+                         "avg_launch_ms": dom_ms / max(dom_launches, 1), "traffic": None, "rank": 0},
+            "cpu_baseline": None,
+            "e2e": {"value": entries_all / (e2e_step_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_step_ms,
+                    "h2d_bytes_per_step": int((res.nbytes + off.nbytes + 4360) * world + 16 * nq),
+                    "d2h_bytes_per_step": int(16 * nq + 4096 * 8 * 2 * world),
+                    "what": "per rank: dbi_create + dbi_add_proteins(host) + staged sharded build + routed dbi_query(host)"},
+            "gpu_launches": int(launches_all),
+            "clocks": clk,
+            "host_stage_ms_rank0_last_step": {k: round(v, 3) for k, v in info["t"].items()},
+        }
+        print(json.dumps(line), flush=True)
+    g.close()
+    dist.destroy_process_group()
+
+
 def run_ours(args, rank: int, local_rank: int, world: int):
     import torch
     import torch.distributed as dist
@@ -190,6 +347,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
                          "(use --impl reference for the CPU baseline)")
+    if world > 1:
+        return run_sharded(args, rank, local_rank, world)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -229,10 +388,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     stage_ms = {}
     clocks = ClockSampler(local_rank)
     launches0 = 0
+    clocks.start()
     for i in range(args.warmup + args.steps):
         if i == args.warmup:
             barrier()
-            clocks.start()
             launches0 = lib.dbi_kernel_launches()
         g.reset_index()
         flush.zero_()  # flush L2 between iterations (inputs are 11 MB)

@@ -156,28 +156,52 @@ class ShardEngine:
 def build_sharded(engine: ShardEngine) -> dict:
     """Run the staged multi-rank build on this rank.  Returns routing info:
     {"split_mass": masses at which the entry slices are cut, "bytes_sent": ..., ...}."""
+    import time
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
     dev = engine.device
-    info = {"rank": rank, "world": world, "a2a_bytes": 0}
+    info = {"rank": rank, "world": world, "a2a_bytes": 0, "t": {}}
+    t_last = [time.perf_counter()]
+
+    def lap(name):  # host wall-clock per stage (every engine call ends synchronised)
+        now = time.perf_counter()
+        info["t"][name] = info["t"].get(name, 0.0) + 1e3 * (now - t_last[0])
+        t_last[0] = now
+
     engine.begin(rank, world)
     engine.digest()
+    lap("digest")
+
+    info["a2a_ms"] = 0.0
+    cuda = dev.type == "cuda"
 
     def exchange(stage: int, widths: Sequence[int]):
         hist, shift = engine.histogram(stage)
         if world > 1:
             dist.all_reduce(hist)
         splitters = pick_splitters(hist.cpu().numpy(), world)
+        lap(f"hist{stage}")
         send_counts = engine.partition(stage, splitters)
+        lap(f"partition{stage}")
         recv_counts = _exchange_counts(send_counts, dev)
         bufs = engine.pack_send(stage)
+        lap(f"pack{stage}")
+        if cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         recv = [_all_to_all_rows(b, send_counts, recv_counts) for b in bufs]
+        if cuda:
+            e1.record()
+            e1.synchronize()
+            info["a2a_ms"] += e0.elapsed_time(e1)
         sent_off_rank = int(send_counts.sum() - send_counts[rank])
         info["a2a_bytes"] += sent_off_rank * int(sum(widths))
+        lap(f"a2a{stage}")
         return recv, splitters, shift
 
     recv, base_split, shift = exchange(0, (8, 4, 4, 2))
     engine.index_base(*recv)
     del recv
+    lap("index_base")
     tables = engine.export_unique()
     n_u, n_p = int(tables[0].numel()), int(tables[5].numel())
     cnt = _all_gather_ints([n_u, n_p], dev)
@@ -185,8 +209,10 @@ def build_sharded(engine: ShardEngine) -> dict:
     gathered = []
     for i, t in enumerate(tables):
         gathered.append(_gather_concat(t, rank_plist if i == 5 else rank_unique))
+    lap("replicate_tables")
     engine.import_unique(rank_unique, rank_plist, gathered)
     del tables, gathered
+    lap("import_unique")
     info["n_unique"] = int(rank_unique.sum())
     if not engine.has_mods:
         engine.finish()
@@ -199,11 +225,16 @@ def build_sharded(engine: ShardEngine) -> dict:
     all_counts = _gather_concat(tc, meta[:, 1]).cpu().numpy()
     # ranks own ascending slices, so the concatenation is in tile order starting at tile meta[0, 0]
     first_tile = int(meta[0, 0]) if len(all_counts) else 0
-    ranges = balance_tiles(all_counts, world)
+    # cost model of the expansion: one warp round per 32 variants plus a fixed per-peptide part
+    # (site scan, table loads) worth ~64 variants -- light slices hold many cheap peptides
+    ranges = balance_tiles(all_counts.astype(np.int64) + 64 * 256, world)
     tb, tn = ranges[rank]
+    lap("tile_counts")
     engine.expand(first_tile + tb, tn)
+    lap("expand")
     recv, var_split, shift = exchange(1, (8, 8))
     engine.index_variants(*recv)
+    lap("index_variants")
     info["split_mass"] = splitter_masses(var_split, shift, engine.min_mass)
     return info
 

@@ -1,0 +1,96 @@
+package edu.scripps.yates.dbindex.gpu;
+
+import java.lang.foreign.Arena;
+import java.lang.foreign.FunctionDescriptor;
+import java.lang.foreign.Linker;
+import java.lang.foreign.MemoryLayout;
+import java.lang.foreign.MemorySegment;
+import java.lang.foreign.StructLayout;
+import java.lang.foreign.SymbolLookup;
+import java.lang.invoke.MethodHandle;
+
+import static java.lang.foreign.ValueLayout.ADDRESS;
+import static java.lang.foreign.ValueLayout.JAVA_BYTE;
+import static java.lang.foreign.ValueLayout.JAVA_DOUBLE;
+import static java.lang.foreign.ValueLayout.JAVA_INT;
+import static java.lang.foreign.ValueLayout.JAVA_LONG;
+
+/**
+ * Panama FFM (java.lang.foreign, JDK 22+) binding of include/dbindex_gpu.h. No jni.h and no generated
+ * glue: every entry point is a downcall handle on the C ABI of libdbindex_gpu.so.
+ *
+ * NOT COMPILED IN THIS REPOSITORY: the build image has no JDK and the reference's core dependency
+ * (edu.scripps.yates:utilities:1.6-SNAPSHOT) is not vendored. The same calls are exercised from Python
+ * (dbindex_b200/capi.py); this file is what a dbIndex maintainer drops next to DBIndexStoreSQLiteMult.
+ */
+public final class DbiNative {
+	public static final int DBI_OK = 0, DBI_ENOTINIT = -1, DBI_EALREADY = -2, DBI_EINVAL = -3, DBI_ENOMEM = -4,
+			DBI_ECUDA = -5, DBI_ENCCL = -6, DBI_ERANGE = -7;
+	public static final int DBI_ABI_VERSION = 1, DBI_MAX_MODS = 16;
+
+	/** struct dbi_mod { uint8_t residue; uint8_t _pad[7]; double delta; } */
+	static final StructLayout MOD = MemoryLayout.structLayout(JAVA_BYTE.withName("residue"),
+			MemoryLayout.paddingLayout(7), JAVA_DOUBLE.withName("delta"));
+
+	/** struct dbi_params, field for field (natural alignment, see dbi_abi_sizes). */
+	static final StructLayout PARAMS = MemoryLayout.structLayout(JAVA_INT.withName("abi_version"),
+			JAVA_INT.withName("device"), MemoryLayout.sequenceLayout(256, JAVA_DOUBLE).withName("residue_mass"),
+			JAVA_DOUBLE.withName("h2o_proton"), JAVA_DOUBLE.withName("nterm"), JAVA_DOUBLE.withName("cterm"),
+			JAVA_INT.withName("add_h2o_proton"), MemoryLayout.sequenceLayout(256, JAVA_BYTE).withName("is_enzyme"),
+			MemoryLayout.sequenceLayout(256, JAVA_BYTE).withName("is_nocut"), JAVA_INT.withName("max_missed"),
+			JAVA_INT.withName("semi"), JAVA_INT.withName("min_len"), MemoryLayout.paddingLayout(4),
+			JAVA_DOUBLE.withName("min_mass"), JAVA_DOUBLE.withName("max_mass"), JAVA_INT.withName("mass_group_factor"),
+			JAVA_INT.withName("n_mods"), JAVA_INT.withName("max_mods_per_peptide"), MemoryLayout.paddingLayout(4),
+			MemoryLayout.sequenceLayout(DBI_MAX_MODS, MOD).withName("mods"), JAVA_INT.withName("keep_emitted"),
+			JAVA_INT.withName("profile"), MemoryLayout.sequenceLayout(6, JAVA_INT).withName("reserved"));
+
+	private static final Linker LINKER = Linker.nativeLinker();
+	private static final SymbolLookup LIB = SymbolLookup
+			.libraryLookup(System.getProperty("dbindex.gpu.lib", "libdbindex_gpu.so"), Arena.global());
+
+	private static MethodHandle h(String name, FunctionDescriptor fd) {
+		return LINKER.downcallHandle(LIB.find(name).orElseThrow(() -> new UnsatisfiedLinkError(name)), fd);
+	}
+
+	static final MethodHandle dbi_default_params = h("dbi_default_params", FunctionDescriptor.ofVoid(ADDRESS, JAVA_INT));
+	static final MethodHandle dbi_abi_sizes = h("dbi_abi_sizes", FunctionDescriptor.ofVoid(ADDRESS, ADDRESS));
+	static final MethodHandle dbi_create = h("dbi_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+	static final MethodHandle dbi_add_proteins = h("dbi_add_proteins",
+			FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_INT));
+	static final MethodHandle dbi_build = h("dbi_build", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+	static final MethodHandle dbi_query = h("dbi_query",
+			FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS));
+	static final MethodHandle dbi_fetch = h("dbi_fetch", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, JAVA_LONG,
+			ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
+	static final MethodHandle dbi_entry_keys = h("dbi_entry_keys",
+			FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
+	static final MethodHandle dbi_stats_get = h("dbi_stats_get", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+	static final MethodHandle dbi_calculate_mass = h("dbi_calculate_mass",
+			FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
+	static final MethodHandle dbi_destroy = h("dbi_destroy", FunctionDescriptor.ofVoid(ADDRESS));
+	static final MethodHandle dbi_last_error = h("dbi_last_error", FunctionDescriptor.of(ADDRESS));
+
+	static {
+		try (Arena a = Arena.ofConfined()) {
+			MemorySegment sp = a.allocate(JAVA_LONG), ss = a.allocate(JAVA_LONG);
+			dbi_abi_sizes.invoke(sp, ss);
+			if (sp.get(JAVA_LONG, 0) != PARAMS.byteSize())
+				throw new IllegalStateException("dbi_params layout mismatch: native " + sp.get(JAVA_LONG, 0)
+						+ " vs " + PARAMS.byteSize());
+		} catch (Throwable t) {
+			throw new ExceptionInInitializerError(t);
+		}
+	}
+
+	static String lastError() {
+		try {
+			MemorySegment p = (MemorySegment) dbi_last_error.invoke();
+			return p.reinterpret(512).getString(0);
+		} catch (Throwable t) {
+			return t.toString();
+		}
+	}
+
+	private DbiNative() {
+	}
+}

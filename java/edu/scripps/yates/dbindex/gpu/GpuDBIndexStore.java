@@ -1,0 +1,323 @@
+package edu.scripps.yates.dbindex.gpu;
+
+import java.lang.foreign.Arena;
+import java.lang.foreign.MemorySegment;
+import java.util.ArrayList;
+import java.util.Iterator;
+import java.util.List;
+
+import edu.scripps.yates.dbindex.DBIndexStore;
+import edu.scripps.yates.dbindex.Interval;
+import edu.scripps.yates.dbindex.MergeIntervals;
+import edu.scripps.yates.dbindex.ProteinCache;
+import edu.scripps.yates.dbindex.Util;
+import edu.scripps.yates.utilities.fasta.dbindex.DBIndexSearchParams;
+import edu.scripps.yates.utilities.fasta.dbindex.DBIndexStoreException;
+import edu.scripps.yates.utilities.fasta.dbindex.IndexedProtein;
+import edu.scripps.yates.utilities.fasta.dbindex.IndexedSequence;
+import edu.scripps.yates.utilities.fasta.dbindex.MassRange;
+import edu.scripps.yates.utilities.fasta.dbindex.ResidueInfo;
+import edu.scripps.yates.utilities.masses.AssignMass;
+
+import static java.lang.foreign.ValueLayout.ADDRESS;
+import static java.lang.foreign.ValueLayout.JAVA_BYTE;
+import static java.lang.foreign.ValueLayout.JAVA_DOUBLE;
+import static java.lang.foreign.ValueLayout.JAVA_INT;
+import static java.lang.foreign.ValueLayout.JAVA_LONG;
+import static java.lang.foreign.ValueLayout.JAVA_SHORT;
+
+/**
+ * The GPU store behind the reference's own plugin seam: DBIndexStore (DBIndexStore.java:19-194), handed
+ * to the indexer through its 3-argument constructor (DBIndexer.java:143). Digestion, mass-ordering,
+ * merging and range search run in libdbindex_gpu.so; this class only marshals and rebuilds the
+ * IndexedSequence objects exactly as DBIndexStoreSQLiteByteIndexMerge.parseAddPeptideInfo does
+ * (DBIndexStoreSQLiteByteIndexMerge.java:452-462). NOT COMPILED HERE (no JDK, see DbiNative).
+ */
+public class GpuDBIndexStore implements DBIndexStore {
+	private static final int MAX_MASS = 8000; // Constants.MAX_PRECURSOR_MASS, DBIndexStoreSQLiteMult buckets
+	private final DBIndexSearchParams sparam;
+	private final Arena arena = Arena.ofShared();
+	private MemorySegment handle = MemorySegment.NULL;
+	private boolean inited = false, built = false;
+	private ProteinCache proteinCache;
+	// proteins gathered by addProteinDef until stopAddSeq() (subsystem 1: packed residue buffer)
+	private final java.io.ByteArrayOutputStream residues = new java.io.ByteArrayOutputStream();
+	private final List<Long> offsets = new ArrayList<>(List.of(0L));
+
+	public GpuDBIndexStore(DBIndexSearchParams sparam) {
+		this.sparam = sparam;
+	}
+
+	private static void check(int rc) throws DBIndexStoreException {
+		if (rc != DbiNative.DBI_OK)
+			throw new DBIndexStoreException(DbiNative.lastError());
+	}
+
+	/** dbi_params from the live AssignMass / Enzyme / search parameters (SURVEY.md 5.1). */
+	private MemorySegment params() throws Throwable {
+		final MemorySegment p = arena.allocate(DbiNative.PARAMS);
+		DbiNative.dbi_default_params.invoke(p, sparam.isUseMonoParent() ? 1 : 0);
+		final long massOff = DbiNative.PARAMS.byteOffset(java.lang.foreign.MemoryLayout.PathElement.groupElement("residue_mass"));
+		for (int c = 0; c < 256; ++c) // the real table, static mods already applied by SearchParamReader
+			p.set(JAVA_DOUBLE, massOff + 8L * c, AssignMass.getMass((char) c));
+		set(p, "h2o_proton", AssignMass.H2O_PROTON);
+		set(p, "nterm", AssignMass.getnTerm());
+		set(p, "cterm", AssignMass.getcTerm());
+		setInt(p, "add_h2o_proton", sparam.isH2OPlusProtonAdded() ? 1 : 0);
+		final long enzOff = DbiNative.PARAMS.byteOffset(java.lang.foreign.MemoryLayout.PathElement.groupElement("is_enzyme"));
+		final long nocOff = DbiNative.PARAMS.byteOffset(java.lang.foreign.MemoryLayout.PathElement.groupElement("is_nocut"));
+		for (int c = 0; c < 256; ++c) {
+			p.set(JAVA_BYTE, enzOff + c, (byte) (sparam.getEnzyme().isEnzyme((char) c) ? 1 : 0));
+			p.set(JAVA_BYTE, nocOff + c, (byte) 0);
+		}
+		final String nocut = sparam.getEnzymeNocutResidues();
+		if (nocut != null)
+			for (final char c : nocut.toCharArray())
+				p.set(JAVA_BYTE, nocOff + c, (byte) 1);
+		setInt(p, "max_missed", sparam.getMaxMissedCleavages());
+		setInt(p, "semi", sparam.isSemiCleavage() ? 1 : 0);
+		set(p, "min_mass", sparam.getMinPrecursorMass());
+		set(p, "max_mass", sparam.getMaxPrecursorMass());
+		setInt(p, "mass_group_factor", sparam.getMassGroupFactor());
+		// differential mods: DiffModification table + max_num_differential_AA_per_mod when the host has them
+		return p;
+	}
+
+	private static void set(MemorySegment p, String f, double v) {
+		p.set(JAVA_DOUBLE, DbiNative.PARAMS.byteOffset(java.lang.foreign.MemoryLayout.PathElement.groupElement(f)), v);
+	}
+
+	private static void setInt(MemorySegment p, String f, int v) {
+		p.set(JAVA_INT, DbiNative.PARAMS.byteOffset(java.lang.foreign.MemoryLayout.PathElement.groupElement(f)), v);
+	}
+
+	@Override
+	public void init(String databaseID) throws DBIndexStoreException {
+		if (inited)
+			throw new DBIndexStoreException("Already intialized"); // DBIndexStoreSQLiteMult.java:97-99
+		try {
+			final MemorySegment out = arena.allocate(ADDRESS);
+			check((int) DbiNative.dbi_create.invoke(params(), out));
+			handle = out.get(ADDRESS, 0);
+		} catch (final DBIndexStoreException e) {
+			throw e;
+		} catch (final Throwable t) {
+			throw new DBIndexStoreException("dbi_create failed", t);
+		}
+		inited = true;
+	}
+
+	private void requireInit() throws DBIndexStoreException {
+		if (!inited)
+			throw new DBIndexStoreException("Indexer is not initialized"); // Mult:153,273,316
+	}
+
+	@Override
+	public boolean indexExists() {
+		return built; // the index lives in HBM: it exists once stopAddSeq() has run
+	}
+
+	@Override
+	public void startAddSeq() throws DBIndexStoreException {
+		requireInit();
+	}
+
+	/** cutSeq is replaced by the digestion kernels: the indexer hands whole proteins over here. */
+	@Override
+	public long addProteinDef(long num, String accession, String protSequence) throws DBIndexStoreException {
+		requireInit();
+		final byte[] b = protSequence.getBytes(java.nio.charset.StandardCharsets.ISO_8859_1);
+		residues.write(b, 0, b.length);
+		offsets.add(offsets.get(offsets.size() - 1) + b.length);
+		return num; // Mult:446-450
+	}
+
+	@Override
+	public FilterResult filterSequence(double precMass, String sequence) {
+		return FilterResult.INCLUDE; // gates are applied on the device (DBIndexer.java:327-331)
+	}
+
+	@Override
+	public void addSequence(double precMass, int sequenceOffset, int sequenceLen, String sequence, String resLeft,
+			String resRight, long proteinId) {
+		// no-op: GpuDBIndexer never calls it, peptides are emitted by digest_emit_kernel
+	}
+
+	/** stopAddSeq = commit + mergePeptides + createIndex of the SQLite stack -> dbi_build. */
+	@Override
+	public void stopAddSeq() throws DBIndexStoreException {
+		requireInit();
+		try (Arena a = Arena.ofConfined()) {
+			final byte[] res = residues.toByteArray();
+			final MemorySegment r = a.allocate(Math.max(1, res.length));
+			MemorySegment.copy(res, 0, r, JAVA_BYTE, 0, res.length);
+			final MemorySegment o = a.allocate(JAVA_LONG, offsets.size());
+			for (int i = 0; i < offsets.size(); ++i)
+				o.setAtIndex(JAVA_LONG, i, offsets.get(i));
+			check((int) DbiNative.dbi_add_proteins.invoke(handle, r, o, offsets.size() - 1));
+			check((int) DbiNative.dbi_build.invoke(handle));
+			built = true;
+		} catch (final DBIndexStoreException e) {
+			throw e;
+		} catch (final Throwable t) {
+			throw new DBIndexStoreException("dbi_build failed", t);
+		}
+	}
+
+	@Override
+	public List<IndexedSequence> getSequences(double precMass, double tolerance) throws DBIndexStoreException {
+		requireInit();
+		double lo = precMass - tolerance; // Mult:324-329
+		if (lo < 0)
+			lo = 0;
+		final double hi = precMass + tolerance;
+		return query(new double[] { lo }, new double[] { hi });
+	}
+
+	@Override
+	public List<IndexedSequence> getSequences(List<MassRange> ranges) throws DBIndexStoreException {
+		if (ranges.size() == 1) // Mult:354-358
+			return getSequences(ranges.get(0).getPrecMass(), ranges.get(0).getTolerance());
+		requireInit();
+		final ArrayList<Interval> intervals = new ArrayList<>();
+		for (final MassRange r : ranges)
+			intervals.add(Interval.massRangeToInterval(r)); // Interval.java:27-38
+		final List<Interval> merged = MergeIntervals.mergeIntervals(intervals); // MergeIntervals.java:16-46
+		final double[] lo = new double[merged.size()], hi = new double[merged.size()];
+		for (int i = 0; i < merged.size(); ++i) {
+			lo[i] = merged.get(i).getStart();
+			hi[i] = merged.get(i).getEnd();
+		}
+		return query(lo, hi);
+	}
+
+	/** dbi_query + dbi_fetch, then the object assembly of parseAddPeptideInfo (Merge:452-477). */
+	private List<IndexedSequence> query(double[] lo, double[] hi) throws DBIndexStoreException {
+		final List<IndexedSequence> ret = new ArrayList<>();
+		final int bucketRange = MAX_MASS / sparam.getIndexFactor();
+		for (int i = 0; i < lo.length; ++i) // "Cannot query, unsupported precursor mass" -> empty (Mult:333-338)
+			if ((int) lo[i] / bucketRange > sparam.getIndexFactor() - 1 || (int) hi[i] / bucketRange > sparam.getIndexFactor() - 1)
+				return ret;
+		try (Arena a = Arena.ofConfined()) {
+			final int nq = lo.length;
+			final MemorySegment dlo = a.allocate(JAVA_DOUBLE, nq), dhi = a.allocate(JAVA_DOUBLE, nq);
+			final MemorySegment beg = a.allocate(JAVA_LONG, nq), cnt = a.allocate(JAVA_LONG, nq);
+			MemorySegment.copy(lo, 0, dlo, JAVA_DOUBLE, 0, nq);
+			MemorySegment.copy(hi, 0, dhi, JAVA_DOUBLE, 0, nq);
+			check((int) DbiNative.dbi_query.invoke(handle, dlo, dhi, (long) nq, beg, cnt));
+			for (int q = 0; q < nq; ++q) {
+				final long b = beg.getAtIndex(JAVA_LONG, q), c = cnt.getAtIndex(JAVA_LONG, q);
+				if (c == 0)
+					continue;
+				final MemorySegment mass = a.allocate(JAVA_DOUBLE, c), prot = a.allocate(JAVA_INT, c);
+				final MemorySegment off = a.allocate(JAVA_INT, c), len = a.allocate(JAVA_SHORT, c);
+				final MemorySegment plo = a.allocate(JAVA_LONG, c + 1), nIds = a.allocate(JAVA_LONG);
+				check((int) DbiNative.dbi_fetch.invoke(handle, b, c, MemorySegment.NULL, MemorySegment.NULL,
+						MemorySegment.NULL, MemorySegment.NULL, MemorySegment.NULL, MemorySegment.NULL,
+						MemorySegment.NULL, 0L, nIds)); // sizing call
+				final long n = nIds.get(JAVA_LONG, 0);
+				final MemorySegment ids = a.allocate(JAVA_INT, Math.max(1, n));
+				check((int) DbiNative.dbi_fetch.invoke(handle, b, c, mass, prot, off, len, MemorySegment.NULL, plo, ids,
+						n, nIds));
+				for (long i = 0; i < c; ++i) {
+					final int pid = prot.getAtIndex(JAVA_INT, i), o = off.getAtIndex(JAVA_INT, i);
+					final int l = len.getAtIndex(JAVA_SHORT, i) & 0xffff;
+					final String pep = proteinCache.getPeptideSequence(pid, o, l); // ProteinCache.java:112-127
+					final IndexedSequence s = new IndexedSequence(0, mass.getAtIndex(JAVA_DOUBLE, i), pep, "", "");
+					final List<Integer> pids = new ArrayList<>();
+					for (long k = plo.getAtIndex(JAVA_LONG, i); k < plo.getAtIndex(JAVA_LONG, i + 1); ++k)
+						pids.add(ids.getAtIndex(JAVA_INT, k));
+					s.setProteinIds(pids);
+					s.setResidues(Util.getResidues(null, o, l, proteinCache.getProteinSequence(pid))); // keeps Q8
+					ret.add(s);
+				}
+			}
+		} catch (final DBIndexStoreException e) {
+			throw e;
+		} catch (final Throwable t) {
+			throw new DBIndexStoreException("Error getting peptides ", t);
+		}
+		return ret;
+	}
+
+	@Override
+	public Iterator<IndexedSequence> getSequencesIterator(List<MassRange> ranges) throws DBIndexStoreException {
+		return getSequences(ranges).iterator(); // Mult:634-636
+	}
+
+	@Override
+	public void setProteinCache(ProteinCache proteinCache) {
+		this.proteinCache = proteinCache;
+	}
+
+	@Override
+	public boolean supportsProteinCache() {
+		return true; // Mult:433-436
+	}
+
+	@Override
+	public List<IndexedProtein> getProteins(IndexedSequence sequence) {
+		final List<IndexedProtein> ret = new ArrayList<>(); // Mult:453-463
+		for (final int id : sequence.getProteinIds())
+			ret.add(new IndexedProtein(proteinCache.getProteinDef(id), id));
+		return ret;
+	}
+
+	@Override
+	public long getNumberSequences() throws DBIndexStoreException {
+		requireInit();
+		try (Arena a = Arena.ofConfined()) {
+			final MemorySegment st = a.allocate(512);
+			check((int) DbiNative.dbi_stats_get.invoke(handle, st));
+			return st.get(JAVA_LONG, 32); // dbi_stats.n_entries
+		} catch (final DBIndexStoreException e) {
+			throw e;
+		} catch (final Throwable t) {
+			throw new DBIndexStoreException("dbi_stats_get failed", t);
+		}
+	}
+
+	@Override
+	public ResidueInfo getResidues(IndexedSequence peptideSequence, IndexedProtein protein) {
+		final String protSeq = proteinCache.getProteinSequence((int) protein.getId());
+		int off = peptideSequence.getSequenceOffset();
+		if (off == IndexedSequence.OFFSET_UNKNOWN)
+			off = protSeq.indexOf(peptideSequence.getSequence()); // Mult:303-312
+		return Util.getResidues(peptideSequence, off, peptideSequence.getSequenceLen(), protSeq);
+	}
+
+	@Override
+	public List<Integer> getEntryKeys() throws DBIndexStoreException {
+		requireInit();
+		try (Arena a = Arena.ofConfined()) {
+			final MemorySegment n = a.allocate(JAVA_LONG);
+			check((int) DbiNative.dbi_entry_keys.invoke(handle, MemorySegment.NULL, 0L, n));
+			final long k = n.get(JAVA_LONG, 0);
+			final MemorySegment keys = a.allocate(JAVA_INT, Math.max(1, k));
+			check((int) DbiNative.dbi_entry_keys.invoke(handle, keys, k, n));
+			final List<Integer> ret = new ArrayList<>((int) k);
+			for (long i = 0; i < k; ++i)
+				ret.add(keys.getAtIndex(JAVA_INT, i));
+			return ret;
+		} catch (final DBIndexStoreException e) {
+			throw e;
+		} catch (final Throwable t) {
+			throw new DBIndexStoreException("dbi_entry_keys failed", t);
+		}
+	}
+
+	@Override
+	public void lastBuffertoDatabase() {
+		throw new UnsupportedOperationException("Not supported yet."); // Mult:620-622
+	}
+
+	public void close() {
+		try {
+			if (!handle.equals(MemorySegment.NULL))
+				DbiNative.dbi_destroy.invoke(handle);
+		} catch (final Throwable ignored) {
+		}
+		handle = MemorySegment.NULL;
+		arena.close();
+	}
+}
