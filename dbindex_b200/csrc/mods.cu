@@ -133,29 +133,48 @@ __device__ __forceinline__ int warp_collect_sites(const uint8_t* __restrict__ re
 }
 
 // Variant of global rank r (0 = unmodified; then k = 1, 2, ... each in lexicographic order):
-// mass and mod pattern.
-__device__ __forceinline__ void decode_variant(uint32_t r, uint32_t n, int K, double base_mass, const WarpSites& ws,
-                                               const ModTables& mt, double* mass, uint32_t* pat) {
+// mass and mod pattern.  cn[k] = C(n, k) is warp-uniform (computed once per peptide).  The
+// combinatorial-number-system walk keeps its binomials incrementally
+// (C(m-1, j) = C(m, j) - C(m-1, j-1)), so a step of the search is 3-5 integer instructions.
+__device__ __forceinline__ void decode_variant(uint32_t r, uint32_t n, int K, const uint32_t* cn, double base_mass,
+                                               const WarpSites& ws, const ModTables& mt, double* mass,
+                                               uint32_t* pat) {
   int k = 0;
-  for (; k <= K; ++k) {
-    const uint32_t c = binom(n, k);
-    if (r < c) break;
-    r -= c;
+#pragma unroll
+  for (int q = 0; q <= DBI_MAX_MODS_PER_PEP; ++q) {
+    if (q <= K && k == q && r >= cn[q]) {
+      r -= cn[q];
+      k = q + 1;
+    }
   }
   double m = base_mass;
   uint32_t p = 0;
   uint32_t x = 0;  // next candidate site ordinal
-  for (int i = 0; i < k; ++i) {
-    // subsets whose i-th element is x: C(n-1-x, k-1-i)
-    while (true) {
-      const uint32_t c = binom(n - 1 - x, k - 1 - i);
-      if (r < c) break;
-      r -= c;
+#pragma unroll
+  for (int i = 0; i < DBI_MAX_MODS_PER_PEP; ++i) {
+    if (i < k) {
+      const int j = k - 1 - i;       // elements still to choose after this one
+      const uint32_t rest = n - x;   // candidates x .. n-1
+      if (j == 0) {
+        x += r;
+        r = 0;
+      } else if (j == 1) {
+        uint32_t w = rest - 1;       // C(rest-1, 1): subsets whose next element is x
+        while (r >= w) { r -= w; --w; ++x; }
+      } else if (j == 2) {
+        uint32_t d = rest - 2;
+        uint32_t w = (rest - 1) * d / 2;  // C(rest-1, 2)
+        while (r >= w) { r -= w; w -= d; --d; ++x; }
+      } else {
+        uint32_t d = rest - 3;
+        uint32_t w2 = (rest - 2) * d / 2;                 // C(rest-2, 2)
+        uint32_t w = (uint32_t)((uint64_t)(rest - 1) * (rest - 2) * d / 6);  // C(rest-1, 3)
+        while (r >= w) { r -= w; w -= w2; w2 -= d; --d; ++x; }
+      }
+      m = __dadd_rn(m, mt.diff[ws.res[x]]);  // left to right
+      p |= ((uint32_t)ws.pos[x] + 1u) << (8 * i);
       ++x;
     }
-    m = __dadd_rn(m, mt.diff[ws.res[x]]);  // left to right
-    p |= ((uint32_t)ws.pos[x] + 1u) << (8 * i);
-    ++x;
   }
   *mass = m;
   *pat = p;
@@ -185,6 +204,9 @@ __global__ void __launch_bounds__(MD_THREADS)
     const uint32_t n = (uint32_t)warp_collect_sites(res, u_gpos[u], u_len[u], mt, ws, &bad);
     if (bad && l == 0) atomicOr(err, kErrModPos);
     const int kk = K < (int)n ? K : (int)n;
+    uint32_t cn[DBI_MAX_MODS_PER_PEP + 1];
+#pragma unroll
+    for (int q = 0; q <= DBI_MAX_MODS_PER_PEP; ++q) cn[q] = binom(n, q);
     const uint32_t total = total_variants(n, kk);
     uint32_t c;
     // no variant can reach a gate: every subset counts
@@ -200,7 +222,7 @@ __global__ void __launch_bounds__(MD_THREADS)
         if (r < total) {
           double m;
           uint32_t pat;
-          decode_variant(r, n, kk, bm, ws, mt, &m, &pat);
+          decode_variant(r, n, kk, cn, bm, ws, mt, &m, &pat);
           pass = (r == 0) || (m >= cfg.min_mass && m <= cfg.max_mass);
         }
         c += __popc(__ballot_sync(0xffffffffu, pass));
@@ -263,6 +285,9 @@ __global__ void __launch_bounds__(MD_THREADS)
     bool bad = false;
     const uint32_t n = (uint32_t)warp_collect_sites(res, u_gpos[u], u_len[u], mt, ws, &bad);
     const int kk = K < (int)n ? K : (int)n;
+    uint32_t cn[DBI_MAX_MODS_PER_PEP + 1];
+#pragma unroll
+    for (int q = 0; q <= DBI_MAX_MODS_PER_PEP; ++q) cn[q] = binom(n, q);
     const uint32_t total = total_variants(n, kk);
     const bool gated = cnt != total;
     uint64_t o = out;
@@ -272,7 +297,7 @@ __global__ void __launch_bounds__(MD_THREADS)
       double m = bm;
       uint32_t pat = 0;
       if (r < total) {
-        decode_variant(r, n, kk, bm, ws, mt, &m, &pat);
+        decode_variant(r, n, kk, cn, bm, ws, mt, &m, &pat);
         pass = !gated || r == 0 || (m >= cfg.min_mass && m <= cfg.max_mass);
       }
       const unsigned pm = __ballot_sync(0xffffffffu, pass);
