@@ -20,7 +20,7 @@ DBI_MAX_MODS = 16
 DBI_N_STAGES = 12
 STAGE_NAMES = [
     "pack", "digest_count", "digest_emit", "sort_base", "dedup", "mod_count",
-    "mod_emit", "sort_var", "gather_var", "query", "fetch", "other",
+    "mod_emit", "sort_var", "expand_var", "query", "fetch", "other",
 ]
 ERR_NAMES = {
     0: "DBI_OK", -1: "DBI_ENOTINIT", -2: "DBI_EALREADY", -3: "DBI_EINVAL", -4: "DBI_ENOMEM",

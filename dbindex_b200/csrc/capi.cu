@@ -409,6 +409,7 @@ void upload_tables(dbi_handle* h) {
     uint64_t g = 0, pw = 1;
     for (int k = 0; k <= p.max_mods_per_peptide; ++k) { g += pw; pw *= (uint64_t)nc; }
     h->cfg.n_seq = g <= 32 ? (int)g : 0;
+    if (std::getenv("DBI_NO_GROUPS")) h->cfg.n_seq = 0;  // diagnostic: force the per-variant path
   }
   h->d_tables.alloc(sizeof(DevTables), h->arena);
   DBI_CUDA(cudaMemcpyAsync(h->d_tables.p, &t, sizeof(t), cudaMemcpyHostToDevice, h->stream));
@@ -672,6 +673,113 @@ int sort_variants(dbi_handle* h, uint64_t* key_in, uint64_t* pay_in, uint64_t V,
   return DBI_OK;
 }
 
+// Group path (class sequences <= 32): K5g + K6g over base tiles [tile0, tile0 + ntiles): one
+// {key, payload} record per (peptide, class sequence) group.  *NG = groups, *V = variants.
+constexpr uint64_t kGrpCntMask = (1ull << 27) - 1;
+
+int emit_groups(dbi_handle* h, uint32_t tile0, uint32_t ntiles, const KeySpace& ks, DevBuf& gkey, DevBuf& gpay,
+                uint64_t* NG_out, uint64_t* V_out) {
+  cudaStream_t s = h->stream;
+  const uint64_t n_unique = h->n_unique;
+  *NG_out = 0;
+  *V_out = 0;
+  if (ntiles == 0 || n_unique == 0) {
+    gkey.alloc(8, h->arena);
+    gpay.alloc(8, h->arena);
+    return DBI_OK;
+  }
+  DevBuf ng, tg, tv, goffs, voffs;
+  ng.alloc(n_unique, h->arena);  // indexed by global peptide id
+  tg.alloc((uint64_t)ntiles * 4, h->arena);
+  tv.alloc((uint64_t)ntiles * 4, h->arena);
+  goffs.alloc(((uint64_t)ntiles + 1) * 8, h->arena);
+  voffs.alloc(((uint64_t)ntiles + 1) * 8, h->arena);
+  const uint64_t n_in_tiles = std::min<uint64_t>((uint64_t)ntiles * kModTile, n_unique - (uint64_t)tile0 * kModTile);
+  uint64_t NG = 0, V = 0;
+  {
+    Stage sg(h, DBI_STAGE_MOD_COUNT);
+    launch_grp_count(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_mass.as<double>(),
+                     h->u_gpos.as<uint32_t>(), h->u_len.as<uint16_t>(), n_unique, tile0, ntiles, ng.as<uint8_t>(),
+                     tg.as<uint32_t>(), tv.as<uint32_t>(), h->d_err.as<uint32_t>(), s);
+    launch_scan_u32_to_u64(tg.as<uint32_t>(), ntiles, goffs.as<uint64_t>(), s);
+    launch_scan_u32_to_u64(tv.as<uint32_t>(), ntiles, voffs.as<uint64_t>(), s);
+    NG = read_u64(h, goffs.as<uint64_t>() + ntiles);
+    V = read_u64(h, voffs.as<uint64_t>() + ntiles);
+    h->st.algo_bytes[DBI_STAGE_MOD_COUNT] += n_in_tiles * (8 + 4 + 2 + 1 + 20);
+  }
+  if (int rc = check_err_bits(read_err(h))) return rc;
+  TR("ir_modcount+sync");
+  gkey.alloc(NG * 8, h->arena);
+  gpay.alloc(NG * 8, h->arena);
+  TR("ir_valloc");
+  {
+    Stage sg(h, DBI_STAGE_MOD_EMIT);
+    launch_grp_emit(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_mass.as<double>(),
+                    h->u_gpos.as<uint32_t>(), h->u_len.as<uint16_t>(), n_unique, tile0, ntiles, ng.as<uint8_t>(),
+                    goffs.as<uint64_t>(), ks.base_bits, gkey.as<uint64_t>(), gpay.as<uint64_t>(), s);
+    h->st.algo_bytes[DBI_STAGE_MOD_EMIT] += n_in_tiles * (8 + 4 + 2 + 1 + 20) + NG * 16;
+  }
+  TR("ir_modemit");
+  *NG_out = NG;
+  *V_out = V;
+  return DBI_OK;
+}
+
+// K7 on NG group records (clobbered), then K6x: expand the sorted groups into the entry arrays.
+int sort_expand_groups(dbi_handle* h, uint64_t* key_in, uint64_t* pay_in, uint64_t NG, const KeySpace& ks) {
+  cudaStream_t s = h->stream;
+  if (NG >= (1ull << 32)) {
+    set_error("more than 2^32 variant groups on one GPU (%llu)", (unsigned long long)NG);
+    return DBI_ERANGE;
+  }
+  DevBuf key2, pay2, vtmp;
+  key2.alloc(NG * 8, h->arena);
+  pay2.alloc(NG * 8, h->arena);
+  vtmp.alloc(radix_sort_tmp_bytes(NG), h->arena);
+  uint64_t* vk[2] = {key_in, key2.as<uint64_t>()};
+  uint64_t* vp[2] = {pay_in, pay2.as<uint64_t>()};
+  int r = 0;
+  {
+    Stage sg(h, DBI_STAGE_SORT_VAR);
+    DomProbe var_probe(h);
+    if (h->p.profile) {
+      h->st.dom_kernel = 1;
+      h->st.dom_bytes_per_launch = NG * 32ull;
+    }
+    r = radix_sort_pairs<uint64_t, uint64_t>(vk, vp, NG, 0, ks.nbits, vtmp.p, s, h->p.profile ? &var_probe : nullptr);
+    h->st.sort_bits_var = (uint32_t)ks.nbits;
+    h->st.algo_bytes[DBI_STAGE_SORT_VAR] += NG * 8 + NG * 32ull * ((ks.nbits + 7) / 8);
+  }
+  TR("ir_sortvar");
+  DevBuf cnt, eoff, stmp;
+  cnt.alloc(NG * 4, h->arena);
+  eoff.alloc((NG + 1) * 8, h->arena);
+  stmp.alloc(full_scan_tmp_bytes(NG), h->arena);
+  uint64_t V = 0;
+  {
+    Stage sg(h, DBI_STAGE_GATHER_VAR);
+    launch_grp_extract_cnt(vp[r], NG, cnt.as<uint32_t>(), s);
+    launch_full_scan_u32_to_u64(cnt.as<uint32_t>(), NG, eoff.as<uint64_t>(), stmp.p, s);
+    V = read_u64(h, eoff.as<uint64_t>() + NG);
+    if (V >= (1ull << 32)) {
+      set_error("more than 2^32 index entries on one GPU (%llu)", (unsigned long long)V);
+      return DBI_ERANGE;
+    }
+    h->e_mass.alloc(V * 8, h->arena);
+    h->e_base.alloc(V * 4, h->arena);
+    h->e_pat.alloc(V * 4, h->arena);
+    TR("ir_ealloc");
+    launch_grp_expand(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_gpos.as<uint32_t>(),
+                      h->u_len.as<uint16_t>(), vk[r], vp[r], eoff.as<uint64_t>(), NG, ks.base_bits,
+                      h->e_mass.as<double>(), h->e_base.as<uint32_t>(), h->e_pat.as<uint32_t>(), s);
+    h->st.algo_bytes[DBI_STAGE_GATHER_VAR] += NG * (16 + 4 + 4 + 8 + 8 + 6 + 12) + V * 16;
+  }
+  TR("ir_expand");
+  h->n_entries = V;
+  h->st.n_entries = V;
+  return DBI_OK;
+}
+
 // Single-GPU: sort + merge + (mods) expand + sort on N emitted records already on the device.
 // lo_mass / hi_mass bound every record mass (they fix the radix key width).
 int index_records(dbi_handle* h, const RecView& r, uint64_t N, double lo_mass, double hi_mass) {
@@ -688,9 +796,14 @@ int index_records(dbi_handle* h, const RecView& r, uint64_t N, double lo_mass, d
   }
   const uint32_t utiles = (uint32_t)((h->n_unique + kModTile - 1) / kModTile);
   DevBuf vkey, vpay;
-  uint64_t V = 0;
-  if (int rc = emit_variants(h, 0, utiles, ks, vkey, vpay, &V)) return rc;
-  if (int rc = sort_variants(h, vkey.as<uint64_t>(), vpay.as<uint64_t>(), V, ks)) return rc;
+  uint64_t V = 0, NG = 0;
+  if (h->cfg.n_seq > 0) {  // group path: sort one record per (peptide, class sequence)
+    if (int rc = emit_groups(h, 0, utiles, ks, vkey, vpay, &NG, &V)) return rc;
+    if (int rc = sort_expand_groups(h, vkey.as<uint64_t>(), vpay.as<uint64_t>(), NG, ks)) return rc;
+  } else {  // many shift classes: one record per variant
+    if (int rc = emit_variants(h, 0, utiles, ks, vkey, vpay, &V)) return rc;
+    if (int rc = sort_variants(h, vkey.as<uint64_t>(), vpay.as<uint64_t>(), V, ks)) return rc;
+  }
   h->built = true;
   return DBI_OK;
 }
@@ -1275,7 +1388,9 @@ int dbi_mg_histogram(dbi_handle* h, int stage, uint64_t* d_hist, int* shift) {
   const KeySpace ks(h->p.min_mass, h->p.max_mass);
   const MgStage st = mg_stage(h, stage, ks);
   const int sh = ks.nbits > 12 ? ks.nbits - 12 : 0;
-  launch_mg_hist(st.key, st.n, st.sub, sh, (unsigned long long*)d_hist, h->stream);
+  const bool weighted = stage == 1 && h->cfg.n_seq > 0;  // group records: weigh by their variant count
+  launch_mg_hist(st.key, st.n, st.sub, sh, weighted ? h->mg_vpay.as<uint64_t>() : nullptr, kGrpCntMask,
+                 (unsigned long long*)d_hist, h->stream);
   DBI_CUDA(cudaStreamSynchronize(h->stream));
   if (shift) *shift = sh;
   return DBI_OK;
@@ -1505,10 +1620,16 @@ int dbi_mg_expand(dbi_handle* h, uint32_t tile_begin, uint32_t n_tiles, uint64_t
     set_error("tile range [%u, +%u) beyond %llu tiles", tile_begin, n_tiles, (unsigned long long)all_tiles);
     return DBI_EINVAL;
   }
-  uint64_t V = 0;
-  int rc = emit_variants(h, tile_begin, n_tiles, ks, h->mg_vkey, h->mg_vpay, &V);
+  uint64_t V = 0, NG = 0;
+  int rc;
+  if (h->cfg.n_seq > 0) {
+    rc = emit_groups(h, tile_begin, n_tiles, ks, h->mg_vkey, h->mg_vpay, &NG, &V);
+  } else {
+    rc = emit_variants(h, tile_begin, n_tiles, ks, h->mg_vkey, h->mg_vpay, &V);
+    NG = V;
+  }
   DBI_CUDA(cudaStreamSynchronize(h->stream));
-  h->mg_v = V;
+  h->mg_v = NG;  // items that travel: group records, or variants on the per-variant path
   if (n_variants) *n_variants = V;
   return rc;
   DBI_API_END
@@ -1521,7 +1642,8 @@ int dbi_mg_index_variants(dbi_handle* h, void* d_key, void* d_payload, uint64_t 
     return DBI_EINVAL;
   }
   const KeySpace ks(h->p.min_mass, h->p.max_mass);
-  int rc = sort_variants(h, (uint64_t*)d_key, (uint64_t*)d_payload, n, ks);
+  int rc = h->cfg.n_seq > 0 ? sort_expand_groups(h, (uint64_t*)d_key, (uint64_t*)d_payload, n, ks)
+                            : sort_variants(h, (uint64_t*)d_key, (uint64_t*)d_payload, n, ks);
   DBI_CUDA(cudaStreamSynchronize(h->stream));
   if (rc != DBI_OK) return rc;
   h->built = true;

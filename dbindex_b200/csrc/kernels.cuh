@@ -83,6 +83,22 @@ void launch_mod_emit(const uint8_t* d_res, const DevTables* d_tb, const DigestCf
 void launch_split_entries(const uint64_t* skey, const uint64_t* spayload, uint64_t n, uint64_t base_bits,
                           double* e_mass, uint32_t* e_base, uint32_t* e_pat, cudaStream_t s);
 
+// Group path (class sequences <= 32): one sort record per (peptide, class sequence) group.
+// payload = peptide << 32 | sequence << 27 | variant count.
+void launch_grp_count(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const double* u_mass,
+                      const uint32_t* u_gpos, const uint16_t* u_len, uint64_t n_unique, uint32_t tile0,
+                      uint32_t ntiles, uint8_t* ng, uint32_t* tile_groups, uint32_t* tile_vars, uint32_t* d_err,
+                      cudaStream_t s);
+void launch_grp_emit(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const double* u_mass,
+                     const uint32_t* u_gpos, const uint16_t* u_len, uint64_t n_unique, uint32_t tile0,
+                     uint32_t ntiles, const uint8_t* ng, const uint64_t* tile_goffs, uint64_t base_bits,
+                     uint64_t* g_key, uint64_t* g_pay, cudaStream_t s);
+void launch_grp_extract_cnt(const uint64_t* pay, uint64_t n, uint32_t* cnt, cudaStream_t s);
+void launch_grp_expand(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const uint32_t* u_gpos,
+                       const uint16_t* u_len, const uint64_t* skey, const uint64_t* spay, const uint64_t* eoff,
+                       uint64_t n_groups, uint64_t base_bits, double* e_mass, uint32_t* e_base, uint32_t* e_pat,
+                       cudaStream_t s);
+
 // ---- K9/K10 query ----------------------------------------------------------------
 void launch_query(const double* e_mass, uint64_t n_entries, const double* lo, const double* hi, uint64_t nq,
                   uint64_t* hit_begin, uint64_t* hit_count, cudaStream_t s);
@@ -105,8 +121,9 @@ void launch_key_emit(const double* e_mass, uint64_t n, double factor, const uint
 // ---- multi-GPU exchange helpers (mg.cu) -----------------------------------------------------
 constexpr int kMgBins = 4096;  // histogram bins over the top bits of the radix key
 // hist[min(kMgBins-1, (key[i] - sub) >> shift)] += 1   (hist is zeroed by the caller)
-void launch_mg_hist(const uint64_t* key, uint64_t n, uint64_t sub, int shift, unsigned long long* hist,
-                    cudaStream_t s);
+// weight of item i = wpay ? (wpay[i] & wmask) : 1   (group records carry their variant count)
+void launch_mg_hist(const uint64_t* key, uint64_t n, uint64_t sub, int shift, const uint64_t* wpay, uint64_t wmask,
+                    unsigned long long* hist, cudaStream_t s);
 // dest[i] = number of thresholds <= (key[i] - sub); idx[i] = i; counts[dest] += 1
 void launch_mg_dest(const uint64_t* key, uint64_t n, uint64_t sub, const uint64_t* thresholds, int n_thr,
                     uint32_t* dest, uint32_t* idx, unsigned long long* counts, cudaStream_t s);

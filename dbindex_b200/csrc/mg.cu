@@ -14,7 +14,7 @@ constexpr int MG_THREADS = 256;
 
 __global__ void __launch_bounds__(MG_THREADS)
     mg_hist_kernel(const uint64_t* __restrict__ key, uint64_t n, uint64_t sub, int shift,
-                   unsigned long long* __restrict__ hist) {
+                   const uint64_t* __restrict__ wpay, uint64_t wmask, unsigned long long* __restrict__ hist) {
   __shared__ uint32_t sh[kMgBins];
   for (int i = threadIdx.x; i < kMgBins; i += MG_THREADS) sh[i] = 0;
   __syncthreads();
@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(MG_THREADS)
   for (uint64_t i = (uint64_t)blockIdx.x * MG_THREADS + threadIdx.x; i < n; i += stride) {
     uint64_t b = (key[i] - sub) >> shift;
     if (b >= kMgBins) b = kMgBins - 1;
-    atomicAdd(&sh[b], 1u);
+    atomicAdd(&sh[b], wpay ? (uint32_t)(wpay[i] & wmask) : 1u);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < kMgBins; i += MG_THREADS)
@@ -101,12 +101,12 @@ __global__ void __launch_bounds__(MG_THREADS)
 
 }  // namespace
 
-void launch_mg_hist(const uint64_t* key, uint64_t n, uint64_t sub, int shift, unsigned long long* hist,
-                    cudaStream_t s) {
+void launch_mg_hist(const uint64_t* key, uint64_t n, uint64_t sub, int shift, const uint64_t* wpay, uint64_t wmask,
+                    unsigned long long* hist, cudaStream_t s) {
   if (n == 0) return;
   uint64_t g = (n + MG_THREADS * 8 - 1) / (MG_THREADS * 8);
   if (g > (uint64_t)kNumSMsB200 * 8) g = (uint64_t)kNumSMsB200 * 8;
-  DBI_LAUNCH(mg_hist_kernel, (unsigned)g, MG_THREADS, 0, s, key, n, sub, shift, hist);
+  DBI_LAUNCH(mg_hist_kernel, (unsigned)g, MG_THREADS, 0, s, key, n, sub, shift, wpay, wmask, hist);
 }
 
 void launch_mg_dest(const uint64_t* key, uint64_t n, uint64_t sub, const uint64_t* thresholds, int n_thr,

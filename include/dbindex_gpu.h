@@ -290,7 +290,10 @@ int dbi_mg_finish(dbi_handle* h);
  * slice: *tile_begin, *n_tiles, and d_tile_counts[0..*n_tiles) (u32, capacity >= slice/256 + 2) */
 int dbi_mg_mod_tile_counts(dbi_handle* h, uint32_t* tile_begin, uint32_t* n_tiles, void* d_tile_counts);
 /* expand the variants of tiles [tile_begin, tile_begin + n_tiles) of the global tables (any
- * range: the tables are replicated, so the host can balance by variant count) */
+ * range: the tables are replicated, so the host can balance by variant count).  What travels
+ * in stage 1 is one {key, payload} record per (peptide, class sequence) group -- all its
+ * variants share one mass -- or one per variant when there are more than 32 class sequences;
+ * the stage-1 histogram weighs a group by its variant count. */
 int dbi_mg_expand(dbi_handle* h, uint32_t tile_begin, uint32_t n_tiles, uint64_t* n_variants);
 /* sort the n variants received for this rank's variant-mass slice into its entry arrays;
  * d_key / d_payload are clobbered */

@@ -96,7 +96,9 @@ def test_parity_param_sets(name):
     # edge cases the domain has: empty and tiny proteins, poly-K, duplicates (protein lists with
     # repeats), isomers, mod-rich peptides, a protein without any cleavage site
     seqs += ["", "K", "A", "KKKKKKKKKKKKKKKK", seqs[0], seqs[0], "AAGGLLKGGAALLKAAGGLLK", "MSTYMSTYMSTYMSTYK",
-             "GGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGG", "", seqs[3][:40], "PKPKPKPRPRPAAAAAAAAK"]
+             "GGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGG", "", seqs[3][:40], "PKPKPKPRPRPAAAAAAAAK",
+             # modifiable sites beyond residue 64 of a peptide: the long-peptide expansion path
+             "G" * 70 + "MSTYMWSTK" + "G" * 12 + "MR", "A" * 66 + "SSTTYYMMWK"]
     g, o = both(p, *pack(seqs))
     try:
         check_all(g, o)

@@ -14,6 +14,9 @@ PARAM_SETS = {
     "semi_nocut_mods": dict(semi=1, nocut="P", max_missed=1, diff_mods=[("M", 15.9949)], max_mods_per_peptide=2),
     "avg_no_h2o": dict(add_h2o_proton=0, min_mass=500.0, max_mass=4000.0),
     "lysc_neg_mod": dict(enzyme="K", diff_mods=[("ST", -18.010565), ("K", 42.010565)], max_mods_per_peptide=2),
+    # 4 distinct shifts, K = 3 -> 85 class sequences > 32: the per-variant (non-group) path
+    "many_classes": dict(diff_mods=[("M", 15.9949), ("ST", 79.96633), ("K", 42.010565), ("N", 0.984016)],
+                         max_mods_per_peptide=3, max_missed=1),
     "wide_mass_mod4": dict(min_mass=0.0, max_mass=8000.0, max_missed=1, diff_mods=[("W", 15.9949)],
                            max_mods_per_peptide=4),
 }
