@@ -174,6 +174,10 @@ struct dbi_handle {
   uint64_t n_emitted = 0, n_unique = 0, n_entries = 0;
   DevBuf u_mass, u_gpos, u_prot, u_len, u_plo, plist;
   DevBuf e_mass, e_base, e_pat;  // empty when there are no differential mods (entries == unique peptides)
+  // group path: site masks of the unique peptides (u_cmask[u * C + c]), valid for cmask_n peptides;
+  // d_nlong = how many peptides are longer than 64 residues (they have no masks)
+  DevBuf u_cmask, d_nlong;
+  uint64_t cmask_n = UINT64_MAX;
   // kept raw records (params.keep_emitted)
   DevBuf k_mass, k_gpos, k_prot, k_len;
 
@@ -348,6 +352,8 @@ void free_index(dbi_handle* h) {
   h->u_mass.release(); h->u_gpos.release(); h->u_prot.release(); h->u_len.release();
   h->u_plo.release(); h->plist.release();
   h->e_mass.release(); h->e_base.release(); h->e_pat.release();
+  h->u_cmask.release(); h->d_nlong.release();
+  h->cmask_n = UINT64_MAX;
   h->k_mass.release(); h->k_gpos.release(); h->k_prot.release(); h->k_len.release();
   h->mg_mass.release(); h->mg_gpos.release(); h->mg_prot.release(); h->mg_len.release();
   h->mg_vkey.release(); h->mg_vpay.release(); h->mg_dest.release(); h->mg_idx[0].release(); h->mg_idx[1].release();
@@ -673,9 +679,23 @@ int sort_variants(dbi_handle* h, uint64_t* key_in, uint64_t* pay_in, uint64_t V,
   return DBI_OK;
 }
 
-// Group path (class sequences <= 32): K5g + K6g over base tiles [tile0, tile0 + ntiles): one
+// Group path (class sequences <= 32): K5m + K5g + K6g over base tiles [tile0, tile0 + ntiles): one
 // {key, payload} record per (peptide, class sequence) group.  *NG = groups, *V = variants.
 constexpr uint64_t kGrpCntMask = (1ull << 27) - 1;
+
+// K5m over the whole unique table (once per table: the multi-GPU build replaces the table).
+void ensure_site_masks(dbi_handle* h) {
+  if (h->cmask_n == h->n_unique && h->u_cmask.p) return;
+  Stage sg(h, DBI_STAGE_MOD_COUNT);
+  h->u_cmask.alloc(std::max<uint64_t>(1, h->n_unique) * (uint64_t)h->cfg.n_classes * 8, h->arena);
+  h->d_nlong.alloc(16, h->arena);
+  DBI_CUDA(cudaMemsetAsync(h->d_nlong.p, 0, 16, h->stream));
+  launch_site_masks(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_gpos.as<uint32_t>(),
+                    h->u_len.as<uint16_t>(), h->n_unique, h->u_cmask.as<uint64_t>(),
+                    (unsigned long long*)h->d_nlong.p, h->stream);
+  h->cmask_n = h->n_unique;
+  h->st.algo_bytes[DBI_STAGE_MOD_COUNT] += h->n_unique * (4 + 2 + 12 + 8ull * h->cfg.n_classes);
+}
 
 int emit_groups(dbi_handle* h, uint32_t tile0, uint32_t ntiles, const KeySpace& ks, DevBuf& gkey, DevBuf& gpay,
                 uint64_t* NG_out, uint64_t* V_out) {
@@ -688,6 +708,7 @@ int emit_groups(dbi_handle* h, uint32_t tile0, uint32_t ntiles, const KeySpace& 
     gpay.alloc(8, h->arena);
     return DBI_OK;
   }
+  ensure_site_masks(h);
   DevBuf ng, tg, tv, goffs, voffs;
   ng.alloc(n_unique, h->arena);  // indexed by global peptide id
   tg.alloc((uint64_t)ntiles * 4, h->arena);
@@ -695,19 +716,23 @@ int emit_groups(dbi_handle* h, uint32_t tile0, uint32_t ntiles, const KeySpace& 
   goffs.alloc(((uint64_t)ntiles + 1) * 8, h->arena);
   voffs.alloc(((uint64_t)ntiles + 1) * 8, h->arena);
   const uint64_t n_in_tiles = std::min<uint64_t>((uint64_t)ntiles * kModTile, n_unique - (uint64_t)tile0 * kModTile);
+  const uint64_t per_pep = 8 + 4 + 2 + 1 + 8ull * h->cfg.n_classes;
   uint64_t NG = 0, V = 0;
   {
     Stage sg(h, DBI_STAGE_MOD_COUNT);
     launch_grp_count(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_mass.as<double>(),
-                     h->u_gpos.as<uint32_t>(), h->u_len.as<uint16_t>(), n_unique, tile0, ntiles, ng.as<uint8_t>(),
-                     tg.as<uint32_t>(), tv.as<uint32_t>(), h->d_err.as<uint32_t>(), s);
+                     h->u_gpos.as<uint32_t>(), h->u_len.as<uint16_t>(), h->u_cmask.as<uint64_t>(), n_unique, tile0,
+                     ntiles, ng.as<uint8_t>(), tg.as<uint32_t>(), tv.as<uint32_t>(), h->d_err.as<uint32_t>(), s);
     launch_scan_u32_to_u64(tg.as<uint32_t>(), ntiles, goffs.as<uint64_t>(), s);
     launch_scan_u32_to_u64(tv.as<uint32_t>(), ntiles, voffs.as<uint64_t>(), s);
-    NG = read_u64(h, goffs.as<uint64_t>() + ntiles);
-    V = read_u64(h, voffs.as<uint64_t>() + ntiles);
-    h->st.algo_bytes[DBI_STAGE_MOD_COUNT] += n_in_tiles * (8 + 4 + 2 + 1 + 20);
+    uint32_t e = 0;
+    DBI_CUDA(cudaMemcpyAsync(&NG, goffs.as<uint64_t>() + ntiles, 8, cudaMemcpyDeviceToHost, s));
+    DBI_CUDA(cudaMemcpyAsync(&V, voffs.as<uint64_t>() + ntiles, 8, cudaMemcpyDeviceToHost, s));
+    DBI_CUDA(cudaMemcpyAsync(&e, h->d_err.p, 4, cudaMemcpyDeviceToHost, s));
+    DBI_CUDA(cudaStreamSynchronize(s));
+    h->st.algo_bytes[DBI_STAGE_MOD_COUNT] += n_in_tiles * per_pep;
+    if (int rc = check_err_bits(e)) return rc;
   }
-  if (int rc = check_err_bits(read_err(h))) return rc;
   TR("ir_modcount+sync");
   gkey.alloc(NG * 8, h->arena);
   gpay.alloc(NG * 8, h->arena);
@@ -715,9 +740,10 @@ int emit_groups(dbi_handle* h, uint32_t tile0, uint32_t ntiles, const KeySpace& 
   {
     Stage sg(h, DBI_STAGE_MOD_EMIT);
     launch_grp_emit(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_mass.as<double>(),
-                    h->u_gpos.as<uint32_t>(), h->u_len.as<uint16_t>(), n_unique, tile0, ntiles, ng.as<uint8_t>(),
-                    goffs.as<uint64_t>(), ks.base_bits, gkey.as<uint64_t>(), gpay.as<uint64_t>(), s);
-    h->st.algo_bytes[DBI_STAGE_MOD_EMIT] += n_in_tiles * (8 + 4 + 2 + 1 + 20) + NG * 16;
+                    h->u_gpos.as<uint32_t>(), h->u_len.as<uint16_t>(), h->u_cmask.as<uint64_t>(), n_unique, tile0,
+                    ntiles, ng.as<uint8_t>(), goffs.as<uint64_t>(), ks.base_bits, gkey.as<uint64_t>(),
+                    gpay.as<uint64_t>(), h->d_err.as<uint32_t>(), s);
+    h->st.algo_bytes[DBI_STAGE_MOD_EMIT] += n_in_tiles * per_pep + NG * 16;
   }
   TR("ir_modemit");
   *NG_out = NG;
@@ -732,6 +758,13 @@ int sort_expand_groups(dbi_handle* h, uint64_t* key_in, uint64_t* pay_in, uint64
     set_error("more than 2^32 variant groups on one GPU (%llu)", (unsigned long long)NG);
     return DBI_ERANGE;
   }
+  if (NG == 0) {
+    h->e_mass.alloc(8, h->arena); h->e_base.alloc(8, h->arena); h->e_pat.alloc(8, h->arena);
+    h->n_entries = 0;
+    h->st.n_entries = 0;
+    return DBI_OK;
+  }
+  ensure_site_masks(h);
   DevBuf key2, pay2, vtmp;
   key2.alloc(NG * 8, h->arena);
   pay2.alloc(NG * 8, h->arena);
@@ -751,28 +784,40 @@ int sort_expand_groups(dbi_handle* h, uint64_t* key_in, uint64_t* pay_in, uint64
     h->st.algo_bytes[DBI_STAGE_SORT_VAR] += NG * 8 + NG * 32ull * ((ks.nbits + 7) / 8);
   }
   TR("ir_sortvar");
-  DevBuf cnt, eoff, stmp;
+  DevBuf cnt, eoff, stmp, tfirst, llist, lcount;
   cnt.alloc(NG * 4, h->arena);
   eoff.alloc((NG + 1) * 8, h->arena);
   stmp.alloc(full_scan_tmp_bytes(NG), h->arena);
-  uint64_t V = 0;
+  lcount.alloc(16, h->arena);
+  uint64_t V = 0, n_long = 0;
   {
     Stage sg(h, DBI_STAGE_GATHER_VAR);
     launch_grp_extract_cnt(vp[r], NG, cnt.as<uint32_t>(), s);
     launch_full_scan_u32_to_u64(cnt.as<uint32_t>(), NG, eoff.as<uint64_t>(), stmp.p, s);
-    V = read_u64(h, eoff.as<uint64_t>() + NG);
+    DBI_CUDA(cudaMemsetAsync(lcount.p, 0, 16, s));
+    DBI_CUDA(cudaMemcpyAsync(&V, eoff.as<uint64_t>() + NG, 8, cudaMemcpyDeviceToHost, s));
+    DBI_CUDA(cudaMemcpyAsync(&n_long, h->d_nlong.p, 8, cudaMemcpyDeviceToHost, s));
+    DBI_CUDA(cudaStreamSynchronize(s));
     if (V >= (1ull << 32)) {
       set_error("more than 2^32 index entries on one GPU (%llu)", (unsigned long long)V);
       return DBI_ERANGE;
     }
+    // groups of long peptides that can land here: at most every modified class sequence of each
+    const uint64_t long_cap = std::min<uint64_t>(NG, n_long * (uint64_t)(h->cfg.n_seq - 1));
+    const uint64_t tiles = (V + kExpTile - 1) / kExpTile;
     h->e_mass.alloc(V * 8, h->arena);
     h->e_base.alloc(V * 4, h->arena);
     h->e_pat.alloc(V * 4, h->arena);
+    tfirst.alloc((tiles + 1) * 4, h->arena);
+    llist.alloc(std::max<uint64_t>(1, long_cap) * 4, h->arena);
     TR("ir_ealloc");
+    launch_grp_tile_first(eoff.as<uint64_t>(), NG, V, tfirst.as<uint32_t>(), s);
     launch_grp_expand(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_gpos.as<uint32_t>(),
-                      h->u_len.as<uint16_t>(), vk[r], vp[r], eoff.as<uint64_t>(), NG, ks.base_bits,
-                      h->e_mass.as<double>(), h->e_base.as<uint32_t>(), h->e_pat.as<uint32_t>(), s);
-    h->st.algo_bytes[DBI_STAGE_GATHER_VAR] += NG * (16 + 4 + 4 + 8 + 8 + 6 + 12) + V * 16;
+                      h->u_len.as<uint16_t>(), h->u_cmask.as<uint64_t>(), vk[r], vp[r], eoff.as<uint64_t>(),
+                      tfirst.as<uint32_t>(), NG, V, ks.base_bits, h->e_mass.as<double>(), h->e_base.as<uint32_t>(),
+                      h->e_pat.as<uint32_t>(), llist.as<uint32_t>(), lcount.as<uint32_t>(), (uint32_t)long_cap,
+                      h->d_err.as<uint32_t>(), s);
+    h->st.algo_bytes[DBI_STAGE_GATHER_VAR] += NG * (8 + 4 + 8 + 8 + 8 + 8ull * h->cfg.max_mods) + V * 16;
   }
   TR("ir_expand");
   h->n_entries = V;
@@ -1567,6 +1612,7 @@ int dbi_mg_import_unique(dbi_handle* h, const uint64_t* rank_unique, const uint6
   DBI_CUDA(cudaStreamSynchronize(s));
   h->n_unique = U;
   h->st.n_unique = U;
+  h->cmask_n = UINT64_MAX;  // the site masks belong to the table that was just replaced
   h->ent_base_off = off;
   h->n_entries = own;  // until variants are indexed
   return DBI_OK;
@@ -1600,13 +1646,25 @@ int dbi_mg_mod_tile_counts(dbi_handle* h, uint32_t* tile_begin, uint32_t* n_tile
   *tile_begin = t0;
   *n_tiles = t1 - t0;
   if (t1 > t0) {
-    DevBuf counts;
-    counts.alloc(h->n_unique * 4, h->arena);
     Stage sg(h, DBI_STAGE_MOD_COUNT);
-    launch_mod_count(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_mass.as<double>(),
-                     h->u_gpos.as<uint32_t>(), h->u_len.as<uint16_t>(), h->n_unique, t0, t1 - t0,
-                     counts.as<uint32_t>(), (uint32_t*)d_tile_counts, h->d_err.as<uint32_t>(), s);
-    DBI_CUDA(cudaStreamSynchronize(s));
+    if (h->cfg.n_seq > 0) {
+      ensure_site_masks(h);
+      DevBuf ng, tg;
+      ng.alloc(h->n_unique, h->arena);
+      tg.alloc((uint64_t)(t1 - t0) * 4, h->arena);
+      launch_grp_count(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_mass.as<double>(),
+                       h->u_gpos.as<uint32_t>(), h->u_len.as<uint16_t>(), h->u_cmask.as<uint64_t>(), h->n_unique, t0,
+                       t1 - t0, ng.as<uint8_t>(), tg.as<uint32_t>(), (uint32_t*)d_tile_counts,
+                       h->d_err.as<uint32_t>(), s);
+      DBI_CUDA(cudaStreamSynchronize(s));
+    } else {
+      DevBuf counts;
+      counts.alloc(h->n_unique * 4, h->arena);
+      launch_mod_count(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_mass.as<double>(),
+                       h->u_gpos.as<uint32_t>(), h->u_len.as<uint16_t>(), h->n_unique, t0, t1 - t0,
+                       counts.as<uint32_t>(), (uint32_t*)d_tile_counts, h->d_err.as<uint32_t>(), s);
+      DBI_CUDA(cudaStreamSynchronize(s));
+    }
   }
   return check_err_bits(read_err(h));
   DBI_API_END

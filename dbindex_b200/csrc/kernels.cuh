@@ -83,21 +83,33 @@ void launch_mod_emit(const uint8_t* d_res, const DevTables* d_tb, const DigestCf
 void launch_split_entries(const uint64_t* skey, const uint64_t* spayload, uint64_t n, uint64_t base_bits,
                           double* e_mass, uint32_t* e_base, uint32_t* e_pat, cudaStream_t s);
 
-// Group path (class sequences <= 32): one sort record per (peptide, class sequence) group.
-// payload = peptide << 32 | sequence << 27 | variant count.
-void launch_grp_count(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const double* u_mass,
-                      const uint32_t* u_gpos, const uint16_t* u_len, uint64_t n_unique, uint32_t tile0,
-                      uint32_t ntiles, uint8_t* ng, uint32_t* tile_groups, uint32_t* tile_vars, uint32_t* d_err,
-                      cudaStream_t s);
-void launch_grp_emit(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const double* u_mass,
-                     const uint32_t* u_gpos, const uint16_t* u_len, uint64_t n_unique, uint32_t tile0,
-                     uint32_t ntiles, const uint8_t* ng, const uint64_t* tile_goffs, uint64_t base_bits,
-                     uint64_t* g_key, uint64_t* g_pay, cudaStream_t s);
-void launch_grp_extract_cnt(const uint64_t* pay, uint64_t n, uint32_t* cnt, cudaStream_t s);
-void launch_grp_expand(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const uint32_t* u_gpos,
-                       const uint16_t* u_len, const uint64_t* skey, const uint64_t* spay, const uint64_t* eoff,
-                       uint64_t n_groups, uint64_t base_bits, double* e_mass, uint32_t* e_base, uint32_t* e_pat,
+// Group path (class sequences <= 32, mods_grp.cu): one sort record per (peptide, class sequence)
+// group; payload = peptide << 32 | sequence << 27 | variant count.
+constexpr int kExpTile = 1024;  // entries per CTA of the expansion
+// cmask[u * C + c] = 64-bit mask of the sites of shift class c in peptide u (all zero for peptides
+// longer than 64 residues, which are counted into *n_long).
+void launch_site_masks(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const uint32_t* u_gpos,
+                       const uint16_t* u_len, uint64_t n_unique, uint64_t* cmask, unsigned long long* n_long,
                        cudaStream_t s);
+void launch_grp_count(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const double* u_mass,
+                      const uint32_t* u_gpos, const uint16_t* u_len, const uint64_t* cmask, uint64_t n_unique,
+                      uint32_t tile0, uint32_t ntiles, uint8_t* ng, uint32_t* tile_groups, uint32_t* tile_vars,
+                      uint32_t* d_err, cudaStream_t s);
+void launch_grp_emit(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const double* u_mass,
+                     const uint32_t* u_gpos, const uint16_t* u_len, const uint64_t* cmask, uint64_t n_unique,
+                     uint32_t tile0, uint32_t ntiles, const uint8_t* ng, const uint64_t* tile_goffs,
+                     uint64_t base_bits, uint64_t* g_key, uint64_t* g_pay, uint32_t* d_err, cudaStream_t s);
+void launch_grp_extract_cnt(const uint64_t* pay, uint64_t n, uint32_t* cnt, cudaStream_t s);
+// first[t] = group holding entry t * kExpTile, t in [0, tiles]; first[tiles] = n_groups - 1
+void launch_grp_tile_first(const uint64_t* eoff, uint64_t n_groups, uint64_t n_entries, uint32_t* first,
+                           cudaStream_t s);
+// entries of the sorted groups; groups of long peptides are listed in long_list and written by a
+// second kernel (launched when long_cap > 0)
+void launch_grp_expand(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const uint32_t* u_gpos,
+                       const uint16_t* u_len, const uint64_t* cmask, const uint64_t* skey, const uint64_t* spay,
+                       const uint64_t* eoff, const uint32_t* tile_first, uint64_t n_groups, uint64_t n_entries,
+                       uint64_t base_bits, double* e_mass, uint32_t* e_base, uint32_t* e_pat, uint32_t* long_list,
+                       uint32_t* long_count, uint32_t long_cap, uint32_t* d_err, cudaStream_t s);
 
 // ---- K9/K10 query ----------------------------------------------------------------
 void launch_query(const double* e_mass, uint64_t n_entries, const double* lo, const double* hi, uint64_t nq,

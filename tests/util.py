@@ -17,6 +17,10 @@ PARAM_SETS = {
     # 4 distinct shifts, K = 3 -> 85 class sequences > 32: the per-variant (non-group) path
     "many_classes": dict(diff_mods=[("M", 15.9949), ("ST", 79.96633), ("K", 42.010565), ("N", 0.984016)],
                          max_mods_per_peptide=3, max_missed=1),
+    # 3 and 5 distinct shifts with K = 2: 13 and 31 class sequences (group path, generic class loops)
+    "three_classes_k2": dict(diff_mods=[("M", 15.9949), ("ST", 79.96633), ("K", 42.010565)], max_mods_per_peptide=2),
+    "five_classes_k2": dict(diff_mods=[("M", 15.9949), ("ST", 79.96633), ("K", 42.010565), ("N", 0.984016),
+                                       ("Q", 0.98)], max_mods_per_peptide=2, max_missed=1),
     "wide_mass_mod4": dict(min_mass=0.0, max_mass=8000.0, max_missed=1, diff_mods=[("W", 15.9949)],
                            max_mods_per_peptide=4),
 }
