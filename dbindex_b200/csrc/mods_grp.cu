@@ -258,23 +258,16 @@ __global__ void __launch_bounds__(MD_THREADS)
 }
 
 // ---- K6x ------------------------------------------------------------------------------
-// number of ways to pick `nrem` further sites above position i, from the masks ma, mb, mc in order
-__device__ __forceinline__ uint32_t count_tail(int nrem, int i, uint64_t ma, uint64_t mb, uint64_t mc) {
-  if (nrem == 0) return 1u;
-  uint64_t a = ma & above(i);
-  if (nrem == 1) return (uint32_t)__popcll(a);
-  uint32_t c = 0;
-  for (; a; a &= a - 1) {
-    const int ia = __ffsll((long long)a) - 1;
-    uint64_t b = mb & above(ia);
-    if (nrem == 2) {
-      c += (uint32_t)__popcll(b);
-    } else {
-      for (; b; b &= b - 1) c += (uint32_t)__popcll(mc & above(__ffsll((long long)b) - 1));
-    }
-  }
-  return c;
+// An occurrence of a class sequence of length k is the tuple of its site positions, kept as the
+// bytes of one register: byte j = position of the j-th chosen site.  Pattern = positions + 1.
+__device__ __forceinline__ uint64_t mask_at(int l, uint64_t c0, uint64_t c1, uint64_t c2, uint64_t c3) {
+  return l == 0 ? c0 : (l == 1 ? c1 : (l == 2 ? c2 : c3));
 }
+__device__ __forceinline__ int pos_at(uint32_t P, int l) { return (int)((P >> (8 * l)) & 0xffu); }
+__device__ __forceinline__ uint32_t pos_set(uint32_t P, int l, int v) {
+  return (P & ~(0xffu << (8 * l))) | ((uint32_t)v << (8 * l));
+}
+__device__ __forceinline__ uint32_t occ_pattern(uint32_t P, int k) { return (P + 0x01010101u) & low_bytes_mask(k); }
 
 // position of the (r+1)-th set bit of m (r < popc(m)): binary search on popcounts, constant cost
 __device__ __forceinline__ int select_bit(uint64_t m, uint32_t r) {
@@ -294,65 +287,163 @@ __device__ __forceinline__ int select_bit(uint64_t m, uint32_t r) {
   return pos;
 }
 
-// The r-th occurrence (lexicographic by sites) of a class sequence of length k whose j-th class
-// has the site mask cm_j: pattern byte j = position + 1 of the j-th chosen site.
-__device__ __forceinline__ uint32_t unrank_occurrence(uint32_t r, int k, uint64_t cm0, uint64_t cm1, uint64_t cm2,
-                                                      uint64_t cm3) {
-  uint32_t pat = 0;
+// Walker over the occurrences of one class sequence in lexicographic site order.  The levels are
+// aligned to the END: D is the last chosen site, C the one before, ... (unused leading levels stay
+// zero).  Each register holds the remaining candidates of its level with the CURRENT site as its
+// lowest set bit, so the common step (next candidate of the last level) is two instructions.
+// cA..cD are the site masks of the classes in the same alignment.
+__device__ __forceinline__ uint64_t above_low(uint64_t x) { return x ? above(__ffsll((long long)x) - 1) : ~0ull; }
+
+struct OccWalker {
+  uint64_t cA, cB, cC, cD;
+  uint64_t A, B, C, D;
+  int shift;  // 8 * (4 - k)
+  // masks of the sequence's classes in site order c0..c3 (k of them)
+  __device__ __forceinline__ void load(int k, uint64_t c0, uint64_t c1, uint64_t c2, uint64_t c3) {
+    shift = 8 * (4 - k);
+    cD = k == 1 ? c0 : (k == 2 ? c1 : (k == 3 ? c2 : c3));
+    cC = k == 2 ? c0 : (k == 3 ? c1 : (k == 4 ? c2 : 0ull));
+    cB = k == 3 ? c0 : (k == 4 ? c1 : 0ull);
+    cA = k == 4 ? c0 : 0ull;
+  }
+  // leftmost embedding = first occurrence
+  __device__ __forceinline__ void first() {
+    A = cA;
+    B = cB & above_low(A);
+    C = cC & above_low(B);
+    D = cD & above_low(C);
+  }
+  // occurrence with site positions P (byte j = position of the j-th site, sequence order)
+  __device__ __forceinline__ void seek(uint32_t P, int k) {
+    const uint32_t Q = P << shift;  // byte 3 = last site
+    A = k > 3 ? (cA & (~0ull << (Q & 0xffu))) : 0ull;
+    B = k > 2 ? (cB & (~0ull << ((Q >> 8) & 0xffu))) : 0ull;
+    C = k > 1 ? (cC & (~0ull << ((Q >> 16) & 0xffu))) : 0ull;
+    D = cD & (~0ull << ((Q >> 24) & 0xffu));
+  }
+  __device__ __forceinline__ uint32_t pattern() const {
+    const uint32_t full = (uint32_t)__ffsll((long long)A) | ((uint32_t)__ffsll((long long)B) << 8) |
+                          ((uint32_t)__ffsll((long long)C) << 16) | ((uint32_t)__ffsll((long long)D) << 24);
+    return full >> shift;
+  }
+  // next occurrence; a site without completion ends its level (no later site of the level has one)
+  __device__ __forceinline__ void next() {
+    D &= D - 1;
+    if (D) return;
+    C &= C - 1;
+    if (C) {
+      D = cD & above_low(C);
+      if (D) return;
+    }
+    B &= B - 1;
+    if (B) {
+      C = cC & above_low(B);
+      if (C) {
+        D = cD & above_low(C);
+        if (D) return;
+      }
+    }
+    A &= A - 1;
+    if (A) {
+      B = cB & above_low(A);
+      C = B ? (cC & above_low(B)) : 0ull;
+      D = C ? (cD & above_low(C)) : 0ull;
+    }
+  }
+};
+
+// number of ways to pick `nrem` further sites above position i, from the masks ma, mb, mc in order
+__device__ __forceinline__ uint32_t count_tail(int nrem, int i, uint64_t ma, uint64_t mb, uint64_t mc) {
+  if (nrem == 0) return 1u;
+  uint64_t a = ma & above(i);
+  if (nrem == 1) return (uint32_t)__popcll(a);
+  uint32_t c = 0;
+  for (; a; a &= a - 1) {
+    const int ia = __ffsll((long long)a) - 1;
+    uint64_t b = mb & above(ia);
+    if (nrem == 2) {
+      c += (uint32_t)__popcll(b);
+    } else {
+      for (; b; b &= b - 1) c += (uint32_t)__popcll(mc & above(__ffsll((long long)b) - 1));
+    }
+  }
+  return c;
+}
+
+// The r-th occurrence (0-based, lexicographic by sites) of a class sequence of length k whose j-th
+// class has the site mask c_j.  Linear in the number of sites for k <= 3.
+__device__ __forceinline__ uint32_t unrank_occurrence(uint32_t r, int k, uint64_t c0, uint64_t c1, uint64_t c2,
+                                                      uint64_t c3) {
+  uint32_t P = 0;
   int prev = -1;
-  // levels 0 .. k-2: walk the candidates of the level until the remaining rank falls inside one
-  if (k > 1) {
-    uint64_t m = cm0;
+  int l = 0;
+  if (k == 4) {  // first site of four: plain nested counting (K = 4 is rare)
+    uint64_t m = c0;
     int i = 0;
     for (; m; m &= m - 1) {
       i = __ffsll((long long)m) - 1;
-      const uint32_t w = count_tail(k - 1, i, cm1, cm2, cm3);
+      const uint32_t w = count_tail(3, i, c1, c2, c3);
       if (r < w) break;
       r -= w;
     }
-    pat = (uint32_t)(i + 1);
+    P = (uint32_t)i;
     prev = i;
-    if (k > 2) {
-      m = cm1 & above(prev);
-      for (; m; m &= m - 1) {
-        i = __ffsll((long long)m) - 1;
-        const uint32_t w = count_tail(k - 2, i, cm2, cm3, 0);
-        if (r < w) break;
-        r -= w;
-      }
-      pat |= (uint32_t)(i + 1) << 8;
-      prev = i;
-      if (k > 3) {
-        m = cm2 & above(prev);
-        for (; m; m &= m - 1) {
-          i = __ffsll((long long)m) - 1;
-          const uint32_t w = count_tail(1, i, cm3, 0, 0);
-          if (r < w) break;
-          r -= w;
-        }
-        pat |= (uint32_t)(i + 1) << 16;
-        prev = i;
-      }
-    }
+    l = 1;
   }
-  // last level: plain select
-  const uint64_t last = k == 1 ? cm0 : (k == 2 ? cm1 : (k == 3 ? cm2 : cm3));
-  const uint64_t cand = prev < 0 ? last : (last & above(prev));
-  const int il = select_bit(cand, r);
-  return pat | ((uint32_t)(il + 1) << (8 * (k - 1)));
+  if (k - l == 3) {
+    // first site of three: W = occurrences whose first site is the current candidate; walking the
+    // candidates upward only ever removes second sites from below, so W is kept incrementally
+    const uint64_t a0 = mask_at(l, c0, c1, c2, c3) & (prev < 0 ? ~0ull : above(prev));
+    const uint64_t a1 = mask_at(l + 1, c0, c1, c2, c3);
+    const uint64_t a2 = mask_at(l + 2, c0, c1, c2, c3);
+    uint64_t rem1 = prev < 0 ? a1 : (a1 & above(prev));
+    uint32_t W = 0;
+    for (uint64_t q = rem1; q; q &= q - 1) W += (uint32_t)__popcll(a2 & above(__ffsll((long long)q) - 1));
+    int i = 0;
+    for (uint64_t m = a0; m; m &= m - 1) {
+      i = __ffsll((long long)m) - 1;
+      for (uint64_t drop = rem1 & ~above(i); drop; drop &= drop - 1)
+        W -= (uint32_t)__popcll(a2 & above(__ffsll((long long)drop) - 1));
+      rem1 &= above(i);
+      if (r < W) break;
+      r -= W;
+    }
+    P |= (uint32_t)i << (8 * l);
+    prev = i;
+    ++l;
+  }
+  if (k - l == 2) {
+    const uint64_t a1 = mask_at(l + 1, c0, c1, c2, c3);
+    int i = 0;
+    for (uint64_t m = mask_at(l, c0, c1, c2, c3) & (prev < 0 ? ~0ull : above(prev)); m; m &= m - 1) {
+      i = __ffsll((long long)m) - 1;
+      const uint32_t w = (uint32_t)__popcll(a1 & above(i));
+      if (r < w) break;
+      r -= w;
+    }
+    P |= (uint32_t)i << (8 * l);
+    prev = i;
+    ++l;
+  }
+  // last site: plain select
+  const uint64_t cand = mask_at(l, c0, c1, c2, c3) & (prev < 0 ? ~0ull : above(prev));
+  return P | ((uint32_t)select_bit(cand, r) << (8 * l));
 }
 
-constexpr int EX_THREADS = 256;
-constexpr int EX_GMAX = kExpTile + 1;  // groups that can overlap one tile (every group has >= 1 entry)
+constexpr int EX_THREADS = 128;
+constexpr int EX_PER = kExpTile / EX_THREADS;  // consecutive entries per thread
+constexpr int EX_GMAX = kExpTile + 1;          // groups that can overlap one tile (every group has >= 1 entry)
 constexpr uint8_t kLongGroup = 0xff;
+static_assert(EX_PER == 8, "the pattern staging is skewed for a stride of 8 words");
 
+// the site masks cm[n_masks][EX_GMAX] (n_masks = max mods per peptide) follow this struct
 struct ExpSmem {
-  uint64_t cm[4][EX_GMAX];
   double mass[EX_GMAX];
-  int32_t off[EX_GMAX];  // first entry of the group relative to the tile start (negative: began earlier)
+  int32_t off[EX_GMAX + 1];  // first entry of the group relative to the tile start (negative: began earlier)
   uint32_t base[EX_GMAX];
+  uint32_t pat[kExpTile + kExpTile / 32];
+  uint16_t head[kExpTile];   // local group of every entry (after the max-scan)
   uint8_t k[EX_GMAX];
-  uint16_t head[kExpTile];  // local group of every entry (after the max-scan)
   uint32_t scratch[EX_THREADS / 32 + 1];
 };
 
@@ -365,6 +456,9 @@ __global__ void __launch_bounds__(EX_THREADS)
                       uint32_t* err) {
   extern __shared__ __align__(16) uint8_t ex_raw[];
   ExpSmem& s = *reinterpret_cast<ExpSmem*>(ex_raw);
+  uint64_t* const s_cm = reinterpret_cast<uint64_t*>(ex_raw + sizeof(ExpSmem));  // [max_mods][EX_GMAX]
+  const int K = cfg.max_mods;
+  auto cm_of = [&](int l, uint32_t j) -> uint64_t { return l < K ? s_cm[l * EX_GMAX + j] : 0ull; };
   const int C = cfg.n_classes;
   const int t = threadIdx.x;
   const uint64_t tile = blockIdx.x;
@@ -376,24 +470,23 @@ __global__ void __launch_bounds__(EX_THREADS)
   for (int i = t; i < kExpTile; i += EX_THREADS) s.head[i] = 0;
   __syncthreads();
   // stage the groups of this tile: offsets, masses, peptides, the site masks of their classes
-  for (uint32_t j = t; j < ngrp; j += EX_THREADS) {
+  for (uint32_t j = t; j <= ngrp; j += EX_THREADS) {
     const uint64_t g = (uint64_t)g0 + j;
-    const int64_t rel = (int64_t)eoff[g] - (int64_t)e0;
+    const int64_t rel = (int64_t)eoff[g] - (int64_t)e0;  // eoff has n_groups + 1 elements
+    s.off[j] = (int32_t)rel;  // |rel| < 2^27 + kExpTile: a group holds at most 2^27 entries
+    if (j == ngrp) break;
     const uint64_t pay = spay[g];
     const uint32_t b = (uint32_t)(pay >> 32);
     const uint32_t seq = ((uint32_t)pay >> kGrpCntBits) & 31u;
     uint32_t pk;
     int k = pack_seq(seq, C, &pk);
-    s.off[j] = (int32_t)rel;
     s.mass[j] = __longlong_as_double((long long)(skey[g] + base_bits));
     s.base[j] = b;
     if (k > 0) {
       const uint64_t* cm = cmask + (uint64_t)b * (uint64_t)C;
       const uint64_t c0 = cm[seq_class_at(pk, 0)];
-      s.cm[0][j] = c0;
-      s.cm[1][j] = k > 1 ? cm[seq_class_at(pk, 1)] : 0ull;
-      s.cm[2][j] = k > 2 ? cm[seq_class_at(pk, 2)] : 0ull;
-      s.cm[3][j] = k > 3 ? cm[seq_class_at(pk, 3)] : 0ull;
+      s_cm[j] = c0;
+      for (int l = 1; l < K; ++l) s_cm[l * EX_GMAX + j] = l < k ? cm[seq_class_at(pk, l)] : 0ull;
       if (c0 == 0) {  // a peptide longer than 64 residues: K6l writes this group
         k = kLongGroup;
         if (rel >= 0 && rel < (int64_t)kExpTile) {  // the tile where the group starts reports it
@@ -408,15 +501,13 @@ __global__ void __launch_bounds__(EX_THREADS)
   __syncthreads();
   // inclusive max-scan of the heads: entry -> local group
   {
-    constexpr int PER = kExpTile / EX_THREADS;
-    uint32_t loc[PER];
+    uint32_t loc[EX_PER];
     uint32_t run = 0;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      run = max(run, (uint32_t)s.head[t * PER + i]);
+    for (int i = 0; i < EX_PER; ++i) {
+      run = max(run, (uint32_t)s.head[t * EX_PER + i]);
       loc[i] = run;
     }
-    // warp inclusive max, then across warps
     uint32_t inc = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -430,20 +521,54 @@ __global__ void __launch_bounds__(EX_THREADS)
     const uint32_t prev = __shfl_up_sync(0xffffffffu, inc, 1);
     if (lane_id() > 0) carry = max(carry, prev);
 #pragma unroll
-    for (int i = 0; i < PER; ++i) s.head[t * PER + i] = (uint16_t)max(loc[i], carry);
+    for (int i = 0; i < EX_PER; ++i) s.head[t * EX_PER + i] = (uint16_t)max(loc[i], carry);
   }
   __syncthreads();
-  // one thread per entry, consecutive threads = consecutive entries
+  // every thread walks EX_PER consecutive entries: un-rank the first one inside its group, then
+  // step from occurrence to occurrence (and from group to group)
+  {
+    const uint32_t i0 = (uint32_t)t * EX_PER;
+    if (i0 < tile_n) {
+      uint32_t j = s.head[i0];
+      uint32_t r = (uint32_t)((int32_t)i0 - s.off[j]);
+      int k = s.k[j];
+      uint32_t cnt = (uint32_t)(s.off[j + 1] - s.off[j]);
+      OccWalker wk;
+      bool sites = k > 0 && k != kLongGroup;
+      if (sites) {
+        const uint64_t c0 = cm_of(0, j), c1 = cm_of(1, j), c2 = cm_of(2, j), c3 = cm_of(3, j);
+        wk.load(k, c0, c1, c2, c3);
+        if (r == 0) wk.first(); else wk.seek(unrank_occurrence(r, k, c0, c1, c2, c3), k);
+      }
+      const uint32_t i1 = min(i0 + EX_PER, tile_n);
+      for (uint32_t i = i0; i < i1; ++i) {
+        s.pat[i + (i >> 5)] = sites ? wk.pattern() : 0u;
+        if (i + 1 == i1) break;
+        if (++r == cnt) {
+          ++j;  // j < ngrp: entries remain
+          r = 0;
+          k = s.k[j];
+          cnt = (uint32_t)(s.off[j + 1] - s.off[j]);
+          sites = k > 0 && k != kLongGroup;
+          if (sites) {
+            wk.load(k, cm_of(0, j), cm_of(1, j), cm_of(2, j), cm_of(3, j));
+            wk.first();
+          }
+        } else if (sites) {
+          wk.next();
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // coalesced write-out: consecutive threads = consecutive entries
   for (uint32_t i = t; i < tile_n; i += EX_THREADS) {
     const uint32_t j = s.head[i];
-    const int k = s.k[j];
-    if (k == kLongGroup) continue;
-    uint32_t pat = 0;
-    if (k > 0) pat = unrank_occurrence((uint32_t)((int32_t)i - s.off[j]), k, s.cm[0][j], s.cm[1][j], s.cm[2][j], s.cm[3][j]);
+    if (s.k[j] == kLongGroup) continue;
     const uint64_t e = e0 + i;
     e_mass[e] = s.mass[j];
     e_base[e] = s.base[j];
-    e_pat[e] = pat;
+    e_pat[e] = s.pat[i + (i >> 5)];
   }
 }
 
@@ -573,11 +698,13 @@ void launch_grp_expand(const uint8_t* d_res, const DevTables* d_tb, const Digest
   if (n_groups == 0 || n_entries == 0) return;
   const uint64_t n_tiles = (n_entries + kExpTile - 1) / kExpTile;
   static const bool attr_set = [] {
-    cudaFuncSetAttribute(grp_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ExpSmem));
+    cudaFuncSetAttribute(grp_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(sizeof(ExpSmem) + (size_t)DBI_MAX_MODS_PER_PEP * EX_GMAX * 8));
     return true;
   }();
   (void)attr_set;
-  DBI_LAUNCH(grp_expand_kernel, (unsigned)n_tiles, EX_THREADS, sizeof(ExpSmem), s, cfg, cmask, skey, spay, eoff,
+  const size_t smem = sizeof(ExpSmem) + (size_t)cfg.max_mods * EX_GMAX * 8;
+  DBI_LAUNCH(grp_expand_kernel, (unsigned)n_tiles, EX_THREADS, smem, s, cfg, cmask, skey, spay, eoff,
              tile_first, n_entries, base_bits, e_mass, e_base, e_pat, long_list, long_count, long_cap, d_err);
   if (long_cap > 0) {
     unsigned grid = (long_cap + MD_WARPS - 1) / MD_WARPS;
