@@ -44,15 +44,43 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def measured_traffic(kernel: str, units: int):
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture
-    (profiles/traffic.json), scaled per sorted pair; None when no capture is on file."""
+def measured_traffic(kernel: str, algo_bytes: float):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a kernel from the
+    committed ncu --set full capture (profiles/traffic.json: bytes measured on this workload next
+    to the algorithmic bytes of that launch), scaled to this run's launch; None without a capture."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)[kernel]
-        return float(t["dram_bytes_per_pair"]) * units
+        return float(t["dram_bytes_per_launch"]) * algo_bytes / float(t["algo_bytes_per_launch"])
     except Exception:
         return None
+
+
+def roofline_of(st_sum: dict, launches_per_build: dict, build_ms_total: float):
+    """The dominant kernel of the build = the one with the largest summed device time among the
+    kernels bracketed by CUDA events inside the library (dbi_stats): the onesweep scatter passes of
+    the largest radix sort, and the mod-expansion kernel."""
+    peak, peak_src = measured_peak_gbs()
+    cands = []
+    if st_sum["dom_launches"]:
+        name = "rs_onesweep_kernel<u64,u64>" if st_sum["dom_kernel"] == 1 else "rs_onesweep_kernel<u64,u32>"
+        cands.append((name, st_sum["dom_ms"], st_sum["dom_launches"], st_sum["dom_bytes_per_launch"]))
+    if st_sum["exp_launches"]:
+        cands.append(("grp_expand_kernel", st_sum["exp_ms"], st_sum["exp_launches"], st_sum["exp_bytes_per_launch"]))
+    if not cands:
+        return None
+    out = []
+    for name, ms, n, bytes_per in cands:
+        avg_ms = ms / n
+        achieved = (bytes_per / 1e9) / (avg_ms / 1e3)
+        out.append({"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "peak_source": peak_src, "bytes_per_launch": int(bytes_per),
+                    "launches": int(n), "avg_launch_ms": avg_ms, "share_of_build": ms / max(build_ms_total, 1e-9),
+                    "traffic": measured_traffic(name, bytes_per)})
+    out.sort(key=lambda r: -r["share_of_build"])
+    roof = out[0]
+    roof["other_kernels"] = out[1:]
+    return roof
 
 
 class ClockSampler:
@@ -233,8 +261,8 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
         torch.cuda.synchronize()
 
     step_ms, query_ms, a2a_ms, a2a_bytes = [], [], 0.0, 0
-    dom_ms = dom_launches = 0
-    dom_bytes = 0
+    probes = {"dom_ms": 0.0, "dom_launches": 0, "dom_bytes_per_launch": 0, "dom_kernel": 0, "exp_ms": 0.0,
+              "exp_launches": 0, "exp_bytes_per_launch": 0}
     clocks = ClockSampler(local_rank)
     launches0 = 0
     hits = 0
@@ -265,7 +293,10 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
             a2a_ms += info["a2a_ms"]
             a2a_bytes += info["a2a_bytes"]
             st = g.stats()
-            dom_ms += st["dom_ms"]; dom_launches += st["dom_launches"]; dom_bytes = st["dom_bytes_per_launch"]
+            for k in ("dom_ms", "dom_launches", "exp_ms", "exp_launches"):
+                probes[k] += st[k]
+            for k in ("dom_bytes_per_launch", "dom_kernel", "exp_bytes_per_launch"):
+                probes[k] = st[k]
             hits = int(d_c.sum().item())
     barrier()
     n_launch = lib.dbi_kernel_launches() - launches0
@@ -303,8 +334,9 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
     entries_all, launches_all, hits_all, a2a_all = u.tolist()
     K = args.steps
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        achieved = (dom_bytes / 1e9) / ((dom_ms / max(dom_launches, 1)) / 1e3) if dom_launches else None
+        roof = roofline_of(probes, {}, sum(step_ms))
+        if roof:
+            roof["rank"] = 0
         line = {
             "metric": METRIC, "value": entries_all * K / (tot_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": args.warmup, "ms_per_step": tot_ms / K, "higher_is_better": True, "scaling": "weak",
@@ -320,10 +352,7 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
             "all_to_all": {"bytes_per_step_all_ranks": a2a_all / K, "ms_per_step_max_rank": a2a_max_ms / K,
                            "bus_gbs_per_gpu": (a2a_all / K / world / 1e9) / max(a2a_max_ms / K / 1e3, 1e-12),
                            "nvlink_ref_gbs": 770.0},
-            "roofline": {"bound": "hbm", "kernel": "rs_onesweep_kernel<u64,u64>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
-                         "bytes_per_launch": dom_bytes, "launches": dom_launches,
-                         "avg_launch_ms": dom_ms / max(dom_launches, 1), "traffic": None, "rank": 0},
+            "roofline": roof,
             "cpu_baseline": None,
             "e2e": {"value": entries_all / (e2e_step_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_step_ms,
                     "h2d_bytes_per_step": int((res.nbytes + off.nbytes + 4360) * world + 16 * nq),
@@ -383,8 +412,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         torch.cuda.synchronize()
 
     build_ms, query_ms = [], []
-    dom_ms = dom_launches = 0
-    dom_bytes = 0
+    probes = {"dom_ms": 0.0, "dom_launches": 0, "dom_bytes_per_launch": 0, "dom_kernel": 0, "exp_ms": 0.0,
+              "exp_launches": 0, "exp_bytes_per_launch": 0}
     stage_ms = {}
     clocks = ClockSampler(local_rank)
     launches0 = 0
@@ -406,7 +435,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             build_ms.append(e0.elapsed_time(e1))
             query_ms.append(e1.elapsed_time(e2))
             st = g.stats()
-            dom_ms += st["dom_ms"]; dom_launches += st["dom_launches"]; dom_bytes = st["dom_bytes_per_launch"]
+            for k in ("dom_ms", "dom_launches", "exp_ms", "exp_launches"):
+                probes[k] += st[k]
+            for k in ("dom_bytes_per_launch", "dom_kernel", "exp_bytes_per_launch"):
+                probes[k] = st[k]
             for k, v in st["stage_ms"].items():
                 stage_ms[k] = stage_ms.get(k, 0.0) + v
     barrier()
@@ -457,16 +489,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     value = entries_all * K / (tot_ms / 1e3)
 
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        dom_name = "rs_onesweep_kernel<u64,u64>" if st["dom_kernel"] == 1 else "rs_onesweep_kernel<u64,u32>"
-        achieved = (dom_bytes / 1e9) / ((dom_ms / max(dom_launches, 1)) / 1e3) if dom_launches else None
-        roof = {
-            "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
-            "bytes_per_launch": dom_bytes, "launches": dom_launches, "avg_launch_ms": dom_ms / max(dom_launches, 1),
-            "share_of_build": dom_ms / max(sum(build_ms), 1e-9),
-            "traffic": measured_traffic(dom_name, int(dom_bytes // (32 if st["dom_kernel"] == 1 else 24))),
-        }
+        roof = roofline_of(probes, {}, sum(build_ms))
         base = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

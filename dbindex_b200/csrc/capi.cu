@@ -269,6 +269,7 @@ struct ArenaFlush {
   }
 
 constexpr int kSpanDominant = 100;  // span kind of a dominant-kernel launch
+constexpr int kSpanExpand = 101;    // span kind of the expansion kernel
 
 ArenaFlush::~ArenaFlush() {
   if (h->arena.local.empty()) return;
@@ -323,6 +324,9 @@ void resolve_spans(dbi_handle* h) {
     if (sp.kind == kSpanDominant) {
       h->st.dom_ms += ms;
       h->st.dom_launches++;
+    } else if (sp.kind == kSpanExpand) {
+      h->st.exp_ms += ms;
+      h->st.exp_launches++;
     } else {
       h->st.stage_ms[sp.kind] += ms;
     }
@@ -812,11 +816,24 @@ int sort_expand_groups(dbi_handle* h, uint64_t* key_in, uint64_t* pay_in, uint64
     llist.alloc(std::max<uint64_t>(1, long_cap) * 4, h->arena);
     TR("ir_ealloc");
     launch_grp_tile_first(eoff.as<uint64_t>(), NG, V, tfirst.as<uint32_t>(), s);
+    cudaEvent_t xa = nullptr;
+    if (h->p.profile) {
+      xa = h->get_event();
+      cudaEventRecord(xa, s);
+    }
     launch_grp_expand(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_gpos.as<uint32_t>(),
                       h->u_len.as<uint16_t>(), h->u_cmask.as<uint64_t>(), vk[r], vp[r], eoff.as<uint64_t>(),
                       tfirst.as<uint32_t>(), NG, V, ks.base_bits, h->e_mass.as<double>(), h->e_base.as<uint32_t>(),
                       h->e_pat.as<uint32_t>(), llist.as<uint32_t>(), lcount.as<uint32_t>(), (uint32_t)long_cap,
                       h->d_err.as<uint32_t>(), s);
+    if (h->p.profile) {
+      cudaEvent_t xb = h->get_event();
+      cudaEventRecord(xb, s);
+      h->spans.push_back({kSpanExpand, xa, xb});
+      // per group: offset + key + payload + tile bookkeeping read, <= max_mods site masks gathered;
+      // per entry: mass + peptide + pattern written
+      h->st.exp_bytes_per_launch = NG * (8 + 8 + 8 + 8ull * h->cfg.max_mods) + V * 16;
+    }
     h->st.algo_bytes[DBI_STAGE_GATHER_VAR] += NG * (8 + 4 + 8 + 8 + 8 + 8ull * h->cfg.max_mods) + V * 16;
   }
   TR("ir_expand");

@@ -115,7 +115,12 @@ typedef struct dbi_stats {
   uint32_t dom_launches;         /* how many                                  */
   uint64_t dom_bytes_per_launch; /* algorithmic bytes one launch moves        */
   uint32_t dom_kernel;           /* 0 = <u64 key,u32 val> base, 1 = <u64,u64> variants */
+  /* The mod-expansion kernel (grp_expand_kernel: sorted groups -> entries), bracketed the
+   * same way; bench.py reports whichever of the two takes more of the build. */
+  uint32_t exp_launches;
+  float exp_ms;
   uint32_t _pad;
+  uint64_t exp_bytes_per_launch;
 } dbi_stats;
 
 /* stage ids for dbi_stats arrays */
