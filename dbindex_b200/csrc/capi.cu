@@ -1650,6 +1650,21 @@ int dbi_mg_finish(dbi_handle* h) {
   DBI_API_END
 }
 
+int dbi_mg_own_tiles(dbi_handle* h, uint32_t* tile_begin, uint32_t* n_tiles) {
+  DBI_API_BEGIN(h)
+  if (!tile_begin || !n_tiles) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  const uint64_t a = h->ent_base_off, b = h->ent_base_off + h->n_entries;  // own slice of the unique tables
+  const uint32_t t0 = (uint32_t)((a + kModTile - 1) / kModTile);            // tiles that START in the slice
+  const uint32_t t1 = (uint32_t)((b + kModTile - 1) / kModTile);
+  *tile_begin = t0;
+  *n_tiles = t1 - t0;
+  return DBI_OK;
+  DBI_API_END
+}
+
 int dbi_mg_mod_tile_counts(dbi_handle* h, uint32_t* tile_begin, uint32_t* n_tiles, void* d_tile_counts) {
   DBI_API_BEGIN(h)
   if (!tile_begin || !n_tiles || !d_tile_counts) {

@@ -95,18 +95,43 @@ def _all_to_all_rows(send: torch.Tensor, send_counts: Sequence[int], recv_counts
 
 def _gather_concat(local: torch.Tensor, counts: Sequence[int]) -> torch.Tensor:
     """Rank-order concatenation of every rank's 1-D tensor on every rank (variable sizes)."""
+    return _gather_tables([local], [counts])[0]
+
+
+def _gather_tables(tables: Sequence[torch.Tensor], counts: Sequence[Sequence[int]]) -> List[torch.Tensor]:
+    """Rank-order concatenation of several 1-D tensors at once: every rank packs its tables into one
+    byte buffer (padded to the largest rank), ONE all-gather moves them, and each table is cut out
+    of the gathered rows.  counts[i][r] = elements of table i on rank r."""
     if _world() == 1:
-        return local
-    world, rank = dist.get_world_size(), dist.get_rank()
-    out = torch.empty(int(sum(counts)), dtype=local.dtype, device=local.device)
-    off = 0
+        return list(tables)
+    world = dist.get_world_size()
+    dev = tables[0].device
+    widths = [t.element_size() for t in tables]
+    # byte offset of table i inside rank r's row (16-byte aligned so that typed views stay aligned)
+    offs = []
+    row_bytes = 0
     for r in range(world):
-        part = out[off:off + int(counts[r])]
-        if r == rank:
-            part.copy_(local)
-        if counts[r]:
-            dist.broadcast(part.view(torch.uint8), src=r)
-        off += int(counts[r])
+        o, cur = [], 0
+        for i, w in enumerate(widths):
+            o.append(cur)
+            cur += (int(counts[i][r]) * w + 15) & ~15
+        offs.append(o)
+        row_bytes = max(row_bytes, cur)
+    row_bytes = max(row_bytes, 16)
+    rank = dist.get_rank()
+    row = torch.empty(row_bytes, dtype=torch.uint8, device=dev)
+    for i, t in enumerate(tables):
+        n = t.numel() * widths[i]
+        if n:
+            row[offs[rank][i]:offs[rank][i] + n].copy_(t.contiguous().view(torch.uint8))
+    rows = torch.empty(world * row_bytes, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(rows, row)
+    rows = rows.view(world, row_bytes)
+    out = []
+    for i, t in enumerate(tables):
+        parts = [rows[r, offs[r][i]:offs[r][i] + int(counts[i][r]) * widths[i]] for r in range(world) if counts[i][r]]
+        cat = torch.cat(parts) if parts else torch.empty(0, dtype=torch.uint8, device=dev)
+        out.append(cat.view(t.dtype))
     return out
 
 
@@ -148,12 +173,13 @@ class ShardEngine:
     def export_unique(self) -> List[torch.Tensor]: ...   # mass, gpos, prot, len, pcnt, plist
     def import_unique(self, rank_unique, rank_plist, tables: List[torch.Tensor]): ...
     def finish(self): ...
+    def own_tiles(self) -> Tuple[int, int]: ...                                # (tile_begin, n_tiles) of the own slice
     def mod_tile_counts(self) -> Tuple[int, torch.Tensor]: ...                # (tile_begin, int32 counts)
     def expand(self, tile_begin: int, n_tiles: int) -> int: ...
     def index_variants(self, key, payload): ...
 
 
-def build_sharded(engine: ShardEngine) -> dict:
+def build_sharded(engine: ShardEngine, rebalance: bool = False) -> dict:
     """Run the staged multi-rank build on this rank.  Returns routing info:
     {"split_mass": masses at which the entry slices are cut, "bytes_sent": ..., ...}."""
     import time
@@ -206,9 +232,7 @@ def build_sharded(engine: ShardEngine) -> dict:
     n_u, n_p = int(tables[0].numel()), int(tables[5].numel())
     cnt = _all_gather_ints([n_u, n_p], dev)
     rank_unique, rank_plist = cnt[:, 0], cnt[:, 1]
-    gathered = []
-    for i, t in enumerate(tables):
-        gathered.append(_gather_concat(t, rank_plist if i == 5 else rank_unique))
+    gathered = _gather_tables(tables, [rank_plist if i == 5 else rank_unique for i in range(len(tables))])
     lap("replicate_tables")
     engine.import_unique(rank_unique, rank_plist, gathered)
     del tables, gathered
@@ -219,17 +243,23 @@ def build_sharded(engine: ShardEngine) -> dict:
         info["split_mass"] = splitter_masses(base_split, shift, engine.min_mass)
         return info
 
-    # re-deal the base tiles by variant count
-    t0, tc = engine.mod_tile_counts()
-    meta = _all_gather_ints([t0, int(tc.numel())], dev)
-    all_counts = _gather_concat(tc, meta[:, 1]).cpu().numpy()
-    # ranks own ascending slices, so the concatenation is in tile order starting at tile meta[0, 0]
-    first_tile = int(meta[0, 0]) if len(all_counts) else 0
-    # cost model of the expansion: one warp round per 32 variants plus a fixed per-peptide part
-    # (site scan, table loads) worth ~64 variants -- light slices hold many cheap peptides
-    ranges = balance_tiles(all_counts.astype(np.int64) + 64 * 256, world)
-    tb, tn = ranges[rank]
-    lap("tile_counts")
+    if rebalance:
+        # re-deal the base tiles by variant count (the heavy slices hold more variants per peptide)
+        t0, tc = engine.mod_tile_counts()
+        meta = _all_gather_ints([t0, int(tc.numel())], dev)
+        all_counts = _gather_concat(tc, meta[:, 1]).cpu().numpy()
+        # ranks own ascending slices, so the concatenation is in tile order starting at tile meta[0, 0]
+        first_tile = int(meta[0, 0]) if len(all_counts) else 0
+        # cost model of the expansion: one unit per variant plus a fixed per-peptide part (site scan,
+        # table loads) worth ~64 variants -- light slices hold many cheap peptides
+        ranges = balance_tiles(all_counts.astype(np.int64) + 64 * 256, world)
+        tb, tn = ranges[rank]
+        lap("tile_counts")
+    else:
+        # every rank lists the groups of its own slice: that work is small and nearly even; the
+        # expensive part (sort + expansion) is balanced by the variant-weighted splitters below
+        first_tile = 0
+        tb, tn = engine.own_tiles()
     engine.expand(first_tile + tb, tn)
     lap("expand")
     recv, var_split, shift = exchange(1, (8, 8))
@@ -266,6 +296,7 @@ class GpuShardEngine(ShardEngine):
             "dbi_mg_import_unique": [vp, vp, vp, vp, vp, vp, vp, vp, vp],
             "dbi_mg_finish": [vp],
             "dbi_mg_mod_tile_counts": [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), vp],
+            "dbi_mg_own_tiles": [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
             "dbi_mg_expand": [vp, C.c_uint32, C.c_uint32, u64p],
             "dbi_mg_index_variants": [vp, vp, vp, C.c_uint64],
         }
@@ -341,6 +372,11 @@ class GpuShardEngine(ShardEngine):
 
     def finish(self):
         self._ck(self.lib.dbi_mg_finish(self.g._h))
+
+    def own_tiles(self):
+        t0, nt = self.C.c_uint32(), self.C.c_uint32()
+        self._ck(self.lib.dbi_mg_own_tiles(self.g._h, self.C.byref(t0), self.C.byref(nt)))
+        return t0.value, nt.value
 
     def mod_tile_counts(self):
         st = self.g.stats()

@@ -257,7 +257,7 @@ int dbi_build_from_records(dbi_handle* h, const double* mass, const uint32_t* pr
  *   -> dbi_mg_histogram(0) .. all-reduce .. dbi_mg_partition(0) -> dbi_mg_pack_send(0) .. all-to-all ..
  *   -> dbi_mg_index_base -> dbi_mg_export_unique .. broadcast from every rank .. dbi_mg_import_unique
  *   no mods:  -> dbi_mg_finish
- *   mods:     -> dbi_mg_mod_tile_counts .. all-gather .. dbi_mg_expand
+ *   mods:     -> dbi_mg_own_tiles (or dbi_mg_mod_tile_counts .. all-gather, to re-deal by cost) -> dbi_mg_expand
  *             -> dbi_mg_histogram(1) .. dbi_mg_partition(1) -> dbi_mg_pack_send(1) .. all-to-all ..
  *             -> dbi_mg_index_variants
  */
@@ -291,6 +291,8 @@ int dbi_mg_import_unique(dbi_handle* h, const uint64_t* rank_unique, const uint6
                          const void* d_pcnt, const void* d_plist);
 /* no differential mods: the entries of this rank are its slice of the unique tables */
 int dbi_mg_finish(dbi_handle* h);
+/* the mod tiles (256 unique peptides each) that START in this rank's slice of the tables */
+int dbi_mg_own_tiles(dbi_handle* h, uint32_t* tile_begin, uint32_t* n_tiles);
 /* variant counts of the mod tiles (256 unique peptides each) that START in this rank's
  * slice: *tile_begin, *n_tiles, and d_tile_counts[0..*n_tiles) (u32, capacity >= slice/256 + 2) */
 int dbi_mg_mod_tile_counts(dbi_handle* h, uint32_t* tile_begin, uint32_t* n_tiles, void* d_tile_counts);

@@ -113,6 +113,11 @@ class OracleShardEngine(ShardEngine):
         off = int(self.u_gpos[u]) - int(self.pstart[pr])
         return pyref.expand_set(self.params, self._seq(pr, off, self.u_len[u]), float(self.u_mass[u]))
 
+    def own_tiles(self):
+        a, b = self.slice
+        t0, t1 = (a + 255) // 256, (b + 255) // 256
+        return t0, t1 - t0
+
     def mod_tile_counts(self):
         a, b = self.slice
         t0, t1 = (a + 255) // 256, (b + 255) // 256
