@@ -508,9 +508,16 @@ int sort_dedup(dbi_handle* h, const RecView& r, uint64_t N, const KeySpace& ks) 
   DevBuf hash, idx[2], hkey[2], mkey[2], tmp, flags, tile_counts, tile_offs;
   const uint64_t tiles = (N + kScanTile - 1) / kScanTile;
   TR("ir_begin");
-  hash.alloc(N * 4, h->arena);
+  // Width of the sequence hash: the number of distinct-string pairs with bit-equal mass grows with
+  // N^2, so two more bits per doubling of N beyond 4 M records; a detected collision adds 8.
+  int hash_bits = 32;
+  for (uint64_t m = N >> 22; m > 1; m >>= 1) hash_bits += 2;
+  hash_bits = std::min(hash_bits, 64);
+  if (const char* e = std::getenv("DBI_HASH_BITS")) {  // test hook: force the wide-hash path on small inputs
+    const int v = std::atoi(e);
+    if (v >= 32 && v <= 64) hash_bits = v;
+  }
   idx[0].alloc(N * 4, h->arena); idx[1].alloc(N * 4, h->arena);
-  hkey[0].alloc(N * 4, h->arena); hkey[1].alloc(N * 4, h->arena);
   mkey[0].alloc(N * 8, h->arena); mkey[1].alloc(N * 8, h->arena);
   tmp.alloc(radix_sort_tmp_bytes(N), h->arena);
   flags.alloc(N, h->arena);
@@ -521,15 +528,26 @@ int sort_dedup(dbi_handle* h, const RecView& r, uint64_t N, const KeySpace& ks) 
   int sorted = 0;
   uint64_t n_unique = 0;
   for (uint32_t attempt = 0;; ++attempt) {
+    const bool wide = hash_bits > 32;
+    h->st.sort_bits_base = (uint32_t)(nbits + hash_bits);
     {
       Stage sg(h, DBI_STAGE_SORT_BASE);
       const uint32_t seed = 0x9e3779b9u * attempt;
-      launch_hash_records(h->d_res.as<uint8_t>(), r.gpos, r.len, N, seed, hash.as<uint32_t>(), idx[0].as<uint32_t>(), s);
-      DBI_CUDA(cudaMemcpyAsync(hkey[0].p, hash.p, N * 4, cudaMemcpyDeviceToDevice, s));
+      hash.alloc(N * (wide ? 8 : 4), h->arena);
+      hkey[0].alloc(N * (wide ? 8 : 4), h->arena);
+      hkey[1].alloc(N * (wide ? 8 : 4), h->arena);
+      launch_hash_records(h->d_res.as<uint8_t>(), r.gpos, r.len, N, seed, wide, hash.p, idx[0].as<uint32_t>(), s);
+      DBI_CUDA(cudaMemcpyAsync(hkey[0].p, hash.p, N * (wide ? 8 : 4), cudaMemcpyDeviceToDevice, s));
       // less significant key first: sequence hash ...
-      uint32_t* hk[2] = {hkey[0].as<uint32_t>(), hkey[1].as<uint32_t>()};
       uint32_t* ix[2] = {idx[0].as<uint32_t>(), idx[1].as<uint32_t>()};
-      const int r1 = radix_sort_pairs<uint32_t, uint32_t>(hk, ix, N, 0, 32, tmp.p, s, nullptr);
+      int r1;
+      if (wide) {
+        uint64_t* hk[2] = {hkey[0].as<uint64_t>(), hkey[1].as<uint64_t>()};
+        r1 = radix_sort_pairs<uint64_t, uint32_t>(hk, ix, N, 0, hash_bits, tmp.p, s, nullptr);
+      } else {
+        uint32_t* hk[2] = {hkey[0].as<uint32_t>(), hkey[1].as<uint32_t>()};
+        r1 = radix_sort_pairs<uint32_t, uint32_t>(hk, ix, N, 0, 32, tmp.p, s, nullptr);
+      }
       DomProbe base_probe(h);
       const bool base_is_dominant = h->p.profile && h->cfg.max_mods == 0;
       if (base_is_dominant) {  // a retry re-runs the sort: count only the final attempt
@@ -548,14 +566,15 @@ int sort_dedup(dbi_handle* h, const RecView& r, uint64_t N, const KeySpace& ks) 
       sorted = r2;
       // normalise: sorted keys in mkey[sorted], sorted idx in idx[0]
       if (ix2[r2] != idx[0].as<uint32_t>()) idx[0].swap(idx[1]);
-      const int passes = 4 + (nbits + 7) / 8;
-      h->st.algo_bytes[DBI_STAGE_SORT_BASE] += N * (20 /*hash: len + 4*/ + 4 + 8 + 8 + 4) + N * 16ull * 4 +
-                                               N * 24ull * (passes - 4) + N * 20;
+      const int hpasses = (hash_bits + 7) / 8, mpasses = (nbits + 7) / 8;
+      const uint64_t hw = wide ? 8 : 4;
+      h->st.algo_bytes[DBI_STAGE_SORT_BASE] += N * (16 /*hash: len + gpos*/ + 3 * hw + 4 + 8 + 8 + 4) +
+                                               N * 2 * (hw + 4) * hpasses + N * 24ull * mpasses + N * 20;
     }
     {
       Stage sg(h, DBI_STAGE_DEDUP);
-      launch_dedup_flags(h->d_res.as<uint8_t>(), mkey[sorted].as<uint64_t>(), idx[0].as<uint32_t>(),
-                         hash.as<uint32_t>(), r.gpos, r.len, N, flags.as<uint8_t>(), tile_counts.as<uint32_t>(),
+      launch_dedup_flags(h->d_res.as<uint8_t>(), mkey[sorted].as<uint64_t>(), idx[0].as<uint32_t>(), hash.p,
+                         hash_bits, r.gpos, r.len, N, flags.as<uint8_t>(), tile_counts.as<uint32_t>(),
                          h->d_err.as<uint32_t>(), s);
       launch_scan_u32_to_u64(tile_counts.as<uint32_t>(), tiles, tile_offs.as<uint64_t>(), s);
       n_unique = read_u64(h, tile_offs.as<uint64_t>() + tiles);
@@ -569,9 +588,10 @@ int sort_dedup(dbi_handle* h, const RecView& r, uint64_t N, const KeySpace& ks) 
       DBI_CUDA(cudaMemcpyAsync(h->d_err.p, &cleared, 4, cudaMemcpyHostToDevice, s));
       DBI_CUDA(cudaStreamSynchronize(s));
       if (attempt >= 8) {
-        set_error("sequence-hash collisions persist after %u re-seeds", attempt);
+        set_error("sequence-hash collisions persist after %u re-seeds (%d hash bits)", attempt, hash_bits);
         return DBI_ERANGE;
       }
+      hash_bits = std::min(64, std::max(hash_bits + 8, 40));
       continue;
     }
     break;

@@ -8,8 +8,10 @@
 // The records arrive sorted by (mass bits, sequence hash, emission ordinal), so the
 // occurrences of one string are adjacent and in insertion order; equal mass does
 // NOT imply equal string (permutation isomers), hence the residue comparison.
-// Two different strings with equal mass bits AND equal 32-bit hash would interleave;
-// that case is detected here and the caller re-sorts with another hash seed.
+// Two different strings with equal mass bits AND equal hash would interleave; that case is
+// detected here and the caller re-sorts with another seed and a wider hash.  The number of
+// distinct-string pairs with equal mass grows with the square of the record count, so the hash
+// is 32 bits for small builds and up to 64 bits (two independent 32-bit halves) for large ones.
 #include "kernels.cuh"
 
 namespace dbi {
@@ -27,17 +29,26 @@ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
   return h;
 }
 
+// WIDE: hash is uint64_t[n] (low half = the 32-bit hash, high half = a second, independent one)
+template <bool WIDE>
 __global__ void __launch_bounds__(DD_THREADS)
     hash_records_kernel(const uint8_t* __restrict__ res, const uint32_t* __restrict__ gpos,
-                        const uint16_t* __restrict__ len, uint64_t n, uint32_t seed, uint32_t* __restrict__ hash,
+                        const uint16_t* __restrict__ len, uint64_t n, uint32_t seed, void* __restrict__ hash,
                         uint32_t* __restrict__ idx) {
   const uint64_t i = (uint64_t)blockIdx.x * DD_THREADS + threadIdx.x;
   if (i >= n) return;
   const uint32_t g = gpos[i];
   const uint32_t l = len[i];
   uint32_t h = 0x811c9dc5u ^ seed;
-  for (uint32_t k = 0; k < l; ++k) h = (h ^ ld_res(res, g + k)) * 16777619u;
-  hash[i] = fmix32(h ^ (l * 0x9e3779b1u));
+  uint32_t h2 = 0x9747b28cu + seed;
+  for (uint32_t k = 0; k < l; ++k) {
+    const uint32_t c = ld_res(res, g + k);
+    h = (h ^ c) * 16777619u;
+    if (WIDE) h2 = (h2 + c + 1u) * 0x9e3779b1u ^ (h2 >> 15);
+  }
+  const uint32_t lo = fmix32(h ^ (l * 0x9e3779b1u));
+  if (WIDE) ((uint64_t*)hash)[i] = ((uint64_t)fmix32(h2 ^ l) << 32) | lo;
+  else ((uint32_t*)hash)[i] = lo;
   idx[i] = (uint32_t)i;
 }
 
@@ -48,9 +59,10 @@ __global__ void __launch_bounds__(DD_THREADS)
   if (i < n) key[i] = mass_bits[idx[i]] - base_bits;
 }
 
+template <typename H>
 __global__ void __launch_bounds__(DD_THREADS)
     dedup_flags_kernel(const uint8_t* __restrict__ res, const uint64_t* __restrict__ skey,
-                       const uint32_t* __restrict__ sidx, const uint32_t* __restrict__ hash,
+                       const uint32_t* __restrict__ sidx, const H* __restrict__ hash, H hash_mask,
                        const uint32_t* __restrict__ gpos, const uint16_t* __restrict__ len, uint64_t n,
                        uint8_t* __restrict__ flags, uint32_t* __restrict__ tile_counts, uint32_t* err) {
   __shared__ uint32_t scratch[DD_THREADS / 32 + 1];
@@ -63,7 +75,7 @@ __global__ void __launch_bounds__(DD_THREADS)
     uint8_t head = 1;
     if (i > 0 && skey[i] == skey[i - 1]) {
       const uint32_t a = sidx[i], b = sidx[i - 1];
-      if (hash[a] == hash[b]) {
+      if (((hash[a] ^ hash[b]) & hash_mask) == 0) {  // only the sorted bits of the hash group the run
         const uint32_t la = len[a], lb = len[b];
         bool same = la == lb;
         if (same) {
@@ -121,10 +133,11 @@ __global__ void __launch_bounds__(DD_THREADS)
 }  // namespace
 
 void launch_hash_records(const uint8_t* d_res, const uint32_t* gpos, const uint16_t* len, uint64_t n, uint32_t seed,
-                         uint32_t* hash, uint32_t* idx, cudaStream_t s) {
+                         bool wide, void* hash, uint32_t* idx, cudaStream_t s) {
   if (n == 0) return;
   const unsigned grid = (unsigned)((n + DD_THREADS - 1) / DD_THREADS);
-  DBI_LAUNCH(hash_records_kernel, grid, DD_THREADS, 0, s, d_res, gpos, len, n, seed, hash, idx);
+  if (wide) DBI_LAUNCH(hash_records_kernel<true>, grid, DD_THREADS, 0, s, d_res, gpos, len, n, seed, hash, idx);
+  else DBI_LAUNCH(hash_records_kernel<false>, grid, DD_THREADS, 0, s, d_res, gpos, len, n, seed, hash, idx);
 }
 
 void launch_gather_mass_key(const uint64_t* mass_bits, const uint32_t* idx, uint64_t n, uint64_t base_bits,
@@ -134,13 +147,19 @@ void launch_gather_mass_key(const uint64_t* mass_bits, const uint32_t* idx, uint
   DBI_LAUNCH(gather_mass_key_kernel, grid, DD_THREADS, 0, s, mass_bits, idx, n, base_bits, key);
 }
 
-void launch_dedup_flags(const uint8_t* d_res, const uint64_t* skey, const uint32_t* sidx, const uint32_t* hash,
-                        const uint32_t* gpos, const uint16_t* len, uint64_t n, uint8_t* flags,
+void launch_dedup_flags(const uint8_t* d_res, const uint64_t* skey, const uint32_t* sidx, const void* hash,
+                        int hash_bits, const uint32_t* gpos, const uint16_t* len, uint64_t n, uint8_t* flags,
                         uint32_t* tile_counts, uint32_t* d_err, cudaStream_t s) {
   if (n == 0) return;
   const unsigned tiles = (unsigned)((n + kScanTile - 1) / kScanTile);
-  DBI_LAUNCH(dedup_flags_kernel, tiles, DD_THREADS, 0, s, d_res, skey, sidx, hash, gpos, len, n, flags, tile_counts,
-             d_err);
+  if (hash_bits > 32) {
+    const uint64_t mask = hash_bits >= 64 ? ~0ull : ((1ull << hash_bits) - 1);
+    DBI_LAUNCH(dedup_flags_kernel<uint64_t>, tiles, DD_THREADS, 0, s, d_res, skey, sidx, (const uint64_t*)hash, mask,
+               gpos, len, n, flags, tile_counts, d_err);
+  } else {
+    DBI_LAUNCH(dedup_flags_kernel<uint32_t>, tiles, DD_THREADS, 0, s, d_res, skey, sidx, (const uint32_t*)hash,
+               0xffffffffu, gpos, len, n, flags, tile_counts, d_err);
+  }
 }
 
 void launch_dedup_emit(const uint64_t* skey, const uint32_t* sidx, const uint8_t* flags, const uint64_t* tile_offs,

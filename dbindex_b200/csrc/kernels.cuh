@@ -53,15 +53,16 @@ void launch_digest_emit(const uint8_t* d_res, uint32_t res_end, const DevTables*
                         uint32_t* d_err, cudaStream_t s);
 
 // ---- sort helpers / K8 dedup -------------------------------------------------
-// hash[i] = seeded 32-bit hash of the residues of record i; idx[i] = i.
+// hash[i] = seeded hash of the residues of record i (u32, or u64 when wide); idx[i] = i.
 void launch_hash_records(const uint8_t* d_res, const uint32_t* gpos, const uint16_t* len, uint64_t n, uint32_t seed,
-                         uint32_t* hash, uint32_t* idx, cudaStream_t s);
+                         bool wide, void* hash, uint32_t* idx, cudaStream_t s);
 // key[i] = mass_bits[idx[i]] - base_bits
 void launch_gather_mass_key(const uint64_t* mass_bits, const uint32_t* idx, uint64_t n, uint64_t base_bits,
                             uint64_t* key, cudaStream_t s);
 // head flag of every sorted record + per-tile head counts (tile = kScanTile).
-void launch_dedup_flags(const uint8_t* d_res, const uint64_t* skey, const uint32_t* sidx, const uint32_t* hash,
-                        const uint32_t* gpos, const uint16_t* len, uint64_t n, uint8_t* flags,
+// (hash: u32[n] when hash_bits <= 32, else u64[n] of which the low hash_bits were sorted)
+void launch_dedup_flags(const uint8_t* d_res, const uint64_t* skey, const uint32_t* sidx, const void* hash,
+                        int hash_bits, const uint32_t* gpos, const uint16_t* len, uint64_t n, uint8_t* flags,
                         uint32_t* tile_counts, uint32_t* d_err, cudaStream_t s);
 // unique records + CSR protein lists.
 void launch_dedup_emit(const uint64_t* skey, const uint32_t* sidx, const uint8_t* flags, const uint64_t* tile_offs,

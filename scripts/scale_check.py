@@ -110,18 +110,20 @@ def main():
             i = sel[k]
             assert c0 >= 1, f"oracle entry of protein {pid} not found (mass {lo[k]!r})"
             want = seq[int(e["first_off"][i]):int(e["first_off"][i]) + int(e["len"][i])].tobytes()
-            hit = g.fetch(int(b0), int(min(c0, 4096)))
             ok = False
-            plo = hit["prot_list_off"].astype(np.int64)
-            for h in range(len(hit["mass"])):
-                if int(hit["len"][h]) != len(want) or int(hit["modpat"][h]) != int(e["modpat"][i]):
-                    continue
-                fp, fo = int(hit["first_prot"][h]), int(hit["first_off"][h])
-                got = res[int(off[fp]) + fo:int(off[fp]) + fo + len(want)].tobytes()
-                if got == want and pid in hit["prot_ids"][plo[h]:plo[h + 1]]:
-                    ok = True
+            for h0 in range(int(b0), int(b0 + c0), 1 << 18):  # isomers share the mass bit for bit: runs can be long
+                hit = g.fetch(h0, int(min(b0 + c0 - h0, 1 << 18)))
+                plo = hit["prot_list_off"].astype(np.int64)
+                cand = np.nonzero((hit["len"] == len(want)) & (hit["modpat"] == e["modpat"][i]))[0]
+                for h in cand:
+                    fp, fo = int(hit["first_prot"][h]), int(hit["first_off"][h])
+                    got = res[int(off[fp]) + fo:int(off[fp]) + fo + len(want)].tobytes()
+                    if got == want and pid in hit["prot_ids"][plo[h]:plo[h + 1]]:
+                        ok = True
+                        break
+                if ok:
                     break
-            assert ok, f"entry ({want!r}, pat {int(e['modpat'][i]):#x}) of protein {pid} missing from the index"
+            assert ok, f"entry ({want!r}, pat {int(e['modpat'][i]):#x}) of protein {pid} missing from the index ({int(c0)} entries at that mass)"
             checked += 1
     out["oracle_entries_found"] = checked
     out["oracle_proteins_sampled"] = int(len(pick))

@@ -106,6 +106,22 @@ def test_parity_param_sets(name):
         g.close()
 
 
+def test_wide_sequence_hash_path(monkeypatch):
+    """Large builds sort a sequence hash of more than 32 bits (the number of equal-mass string pairs
+    grows with N^2); force that path on a small input with duplicates and isomers."""
+    monkeypatch.setenv("DBI_HASH_BITS", "44")
+    p = dbi.default_params(**PARAM_SETS["cfg2_mods"])
+    res, off = synth.synth_proteome(150, 77, median_len=250, min_len=5)
+    seqs = [res[int(off[i]):int(off[i + 1])].tobytes().decode() for i in range(len(off) - 1)]
+    seqs += [seqs[0], seqs[5], "AAGGLLKGGAALLKAAGGLLK", "GALKAGLKLAGKGLAK", seqs[0]]
+    g, o = both(p, *pack(seqs))
+    try:
+        check_all(g, o)
+        assert g.stats()["sort_bits_base"] >= 44
+    finally:
+        g.close()
+
+
 def test_empty_and_degenerate_indexes():
     p = dbi.default_params()
     for seqs in ([], [""], ["AAA"], ["K" * 5], ["G" * 200]):
