@@ -430,11 +430,11 @@ __device__ __forceinline__ uint32_t unrank_occurrence(uint32_t r, int k, uint64_
   return P | ((uint32_t)select_bit(cand, r) << (8 * l));
 }
 
-constexpr int EX_THREADS = 128;
+constexpr int EX_THREADS = 256;
 constexpr int EX_PER = kExpTile / EX_THREADS;  // consecutive entries per thread
 constexpr int EX_GMAX = kExpTile + 1;          // groups that can overlap one tile (every group has >= 1 entry)
 constexpr uint8_t kLongGroup = 0xff;
-static_assert(EX_PER == 8, "the pattern staging is skewed for a stride of 8 words");
+static_assert(EX_PER == 4 || EX_PER == 8, "the pattern staging is skewed for a stride of 4 or 8 words");
 
 // the site masks cm[n_masks][EX_GMAX] (n_masks = max mods per peptide) follow this struct
 struct ExpSmem {
