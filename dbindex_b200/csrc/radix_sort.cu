@@ -56,11 +56,17 @@ __global__ void __launch_bounds__(RS_THREADS) rs_histogram_kernel(const K* __res
       for (int p = 0; p < num_passes; ++p) {
         const int shift = begin_bit + p * RS_BITS;
         const int bits = min(RS_BITS, end_bit - shift);
-        uint32_t d = (uint32_t)(key[u] >> shift) & ((1u << bits) - 1);
-        if (!valid[u]) d = 0xffffffffu;
-        // aggregate equal digits inside the warp: one shared atomic per distinct digit
-        const unsigned m = __match_any_sync(0xffffffffu, d);
-        if (valid[u] && (int)lane_id() == __ffs(m) - 1) atomicAdd(&sh[p * RS_RADIX + d], (uint32_t)__popc(m));
+        const uint32_t d = (uint32_t)(key[u] >> shift) & ((1u << bits) - 1);
+        // high digits of neighbouring keys are mostly equal (the input is emitted in near mass
+        // order): one atomic for the whole warp then; otherwise plain shared atomics, which
+        // rarely conflict on the well-mixed low digits
+        const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
+        const unsigned vm = __ballot_sync(0xffffffffu, valid[u]);
+        if (vm == 0xffffffffu && __all_sync(0xffffffffu, d == d0)) {
+          if (lane_id() == 0) atomicAdd(&sh[p * RS_RADIX + d], 32u);
+        } else if (valid[u]) {
+          atomicAdd(&sh[p * RS_RADIX + d], 1u);
+        }
       }
     }
   }
