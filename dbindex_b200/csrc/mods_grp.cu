@@ -20,6 +20,8 @@
 // HBM-bound byte/integer work; no tensor cores.  Algorithmic bytes: K5m 14 + len per peptide read,
 // 8 C written; K5g/K6g 22 + 8 C per peptide, 16 per group written; K6x 24 per group + 8 C per
 // group (random 32-B sectors) read, 16 per entry written.
+#include <cstdlib>
+
 #include "mods_common.cuh"
 
 namespace dbi {
@@ -572,6 +574,235 @@ __global__ void __launch_bounds__(EX_THREADS)
   }
 }
 
+// ---- K6x, table variant ------------------------------------------------------------------
+// One thread per ENTRY with constant-time un-ranking.  The entries of a group are ordered by
+// BLOCKS that are product sets, so that a rank splits by one division:
+//   k = 1: the sites of the class, ascending;
+//   k = 2: block = first site i0;   entries = sites of the second class above i0;
+//   k = 3: block = MIDDLE site i1;  entries = (sites of the first class below i1) x (sites of the
+//          third class above i1), the third site running fastest;
+//   k = 4: block = second site i1;  entries = (first-class sites below i1) x (pairs i2 < i3 above i1).
+// (The order of the entries INSIDE a group is free: they all have the same mass and peptide.)
+// Phase 1 stages the groups of the tile and, per group, the exclusive prefix sums of its block sizes
+// and the block sites in a shared pool; phase 3 finds the block by binary search, then selects bits.
+constexpr int ET_THREADS = 256;
+constexpr int ET_PER = kExpTile / ET_THREADS;
+constexpr int ET_POOL = 3072;          // block-table slots shared by the groups of a tile
+constexpr uint16_t kNoTable = 0xffff;  // pool exhausted or group too large for 16-bit sums: scan on the fly
+
+struct ExpTabSmem {
+  double mass[EX_GMAX];
+  int32_t off[EX_GMAX + 1];
+  uint32_t base[EX_GMAX];
+  uint16_t head[kExpTile];
+  uint16_t tab[EX_GMAX];       // first pool slot of the group's block table
+  uint16_t cum[ET_POOL];       // exclusive prefix sums of the block sizes
+  uint8_t pos[ET_POOL];        // site of the block
+  uint8_t k[EX_GMAX];
+  uint32_t pool_used;
+  uint32_t scratch[ET_THREADS / 32 + 1];
+};
+
+__device__ __forceinline__ uint64_t below(int i) { return ~(~0ull << i); }  // bits strictly below position i
+
+// pairs i2 < i3 above position i (third and fourth class)
+__device__ __forceinline__ uint32_t pairs_above(int i, uint64_t c2, uint64_t c3) {
+  uint32_t w = 0;
+  for (uint64_t m = c2 & above(i); m; m &= m - 1) w += (uint32_t)__popcll(c3 & above(__ffsll((long long)m) - 1));
+  return w;
+}
+
+// mask of the block sites of a group and the size of the block at site p
+__device__ __forceinline__ uint64_t block_sites(int k, uint64_t c0, uint64_t c1) { return k == 2 ? c0 : c1; }
+__device__ __forceinline__ uint32_t block_size(int k, int p, uint64_t c0, uint64_t c1, uint64_t c2, uint64_t c3) {
+  if (k == 2) return (uint32_t)__popcll(c1 & above(p));
+  const uint32_t nl = (uint32_t)__popcll(c0 & below(p));
+  if (k == 3) return nl * (uint32_t)__popcll(c2 & above(p));
+  return nl ? nl * pairs_above(p, c2, c3) : 0u;
+}
+
+// pattern of entry q of the block at site p
+__device__ __forceinline__ uint32_t block_entry(int k, int p, uint32_t q, uint64_t c0, uint64_t c1, uint64_t c2,
+                                                uint64_t c3) {
+  if (k == 2) return (uint32_t)(p + 1) | ((uint32_t)(select_bit(c1 & above(p), q) + 1) << 8);
+  const uint64_t L = c0 & below(p);
+  if (k == 3) {
+    const uint64_t R = c2 & above(p);
+    const uint32_t nr = (uint32_t)__popcll(R);
+    const uint32_t a = q / nr, b = q - a * nr;
+    return (uint32_t)(select_bit(L, a) + 1) | ((uint32_t)(p + 1) << 8) | ((uint32_t)(select_bit(R, b) + 1) << 16);
+  }
+  const uint32_t w2 = pairs_above(p, c2, c3);
+  const uint32_t a = q / w2;
+  uint32_t b = q - a * w2;
+  int i2 = 0;
+  uint64_t r3 = 0;
+  for (uint64_t m = c2 & above(p); m; m &= m - 1) {
+    i2 = __ffsll((long long)m) - 1;
+    r3 = c3 & above(i2);
+    const uint32_t w = (uint32_t)__popcll(r3);
+    if (b < w) break;
+    b -= w;
+  }
+  return (uint32_t)(select_bit(L, a) + 1) | ((uint32_t)(p + 1) << 8) | ((uint32_t)(i2 + 1) << 16) |
+         ((uint32_t)(select_bit(r3, b) + 1) << 24);
+}
+
+__global__ void __launch_bounds__(ET_THREADS)
+    grp_expand_tab_kernel(DigestCfg cfg, const uint64_t* __restrict__ cmask, const uint64_t* __restrict__ skey,
+                          const uint64_t* __restrict__ spay, const uint64_t* __restrict__ eoff,
+                          const uint32_t* __restrict__ tile_first, uint64_t n_entries, uint64_t base_bits,
+                          double* __restrict__ e_mass, uint32_t* __restrict__ e_base, uint32_t* __restrict__ e_pat,
+                          uint32_t* __restrict__ long_list, uint32_t* __restrict__ long_count, uint32_t long_cap,
+                          uint32_t* err) {
+  extern __shared__ __align__(16) uint8_t ex_raw[];
+  ExpTabSmem& s = *reinterpret_cast<ExpTabSmem*>(ex_raw);
+  uint64_t* const s_cm = reinterpret_cast<uint64_t*>(ex_raw + sizeof(ExpTabSmem));  // [max_mods][EX_GMAX]
+  const int K = cfg.max_mods;
+  auto cm_of = [&](int l, uint32_t j) -> uint64_t { return l < K ? s_cm[l * EX_GMAX + j] : 0ull; };
+  const int C = cfg.n_classes;
+  const int t = threadIdx.x;
+  const uint64_t tile = blockIdx.x;
+  const uint64_t e0 = tile * (uint64_t)kExpTile;
+  const uint32_t tile_n = (uint32_t)min((uint64_t)kExpTile, n_entries - e0);
+  const uint32_t g0 = tile_first[tile];
+  const uint32_t ngrp = tile_first[tile + 1] - g0 + 1;
+
+  for (int i = t; i < kExpTile; i += ET_THREADS) s.head[i] = 0;
+  if (t == 0) s.pool_used = 0;
+  __syncthreads();
+  // (1) stage the groups and their block tables
+  for (uint32_t j = t; j <= ngrp; j += ET_THREADS) {
+    const uint64_t g = (uint64_t)g0 + j;
+    const int64_t rel = (int64_t)eoff[g] - (int64_t)e0;
+    s.off[j] = (int32_t)rel;
+    if (j == ngrp) break;
+    const uint64_t pay = spay[g];
+    const uint32_t b = (uint32_t)(pay >> 32);
+    const uint32_t seq = ((uint32_t)pay >> kGrpCntBits) & 31u;
+    const uint32_t cnt = (uint32_t)pay & kGrpCntMask;
+    uint32_t pk;
+    int k = pack_seq(seq, C, &pk);
+    s.mass[j] = __longlong_as_double((long long)(skey[g] + base_bits));
+    s.base[j] = b;
+    uint16_t tab = kNoTable;
+    if (k > 0) {
+      const uint64_t* cm = cmask + (uint64_t)b * (uint64_t)C;
+      const uint64_t c0 = cm[seq_class_at(pk, 0)];
+      const uint64_t c1 = k > 1 ? cm[seq_class_at(pk, 1)] : 0ull;
+      const uint64_t c2 = k > 2 ? cm[seq_class_at(pk, 2)] : 0ull;
+      const uint64_t c3 = k > 3 ? cm[seq_class_at(pk, 3)] : 0ull;
+      s_cm[j] = c0;
+      if (K > 1) s_cm[EX_GMAX + j] = c1;
+      if (K > 2) s_cm[2 * EX_GMAX + j] = c2;
+      if (K > 3) s_cm[3 * EX_GMAX + j] = c3;
+      if (c0 == 0) {  // a peptide longer than 64 residues: K6l writes this group
+        k = kLongGroup;
+        if (rel >= 0 && rel < (int64_t)kExpTile) {
+          const uint32_t slot = atomicAdd(long_count, 1u);
+          if (slot < long_cap) long_list[slot] = (uint32_t)g; else atomicOr(err, kErrModPos);
+        }
+      } else if (k > 1 && cnt <= 0xffffu) {
+        const uint64_t sites = block_sites(k, c0, c1);
+        const uint32_t nb = (uint32_t)__popcll(sites);
+        const uint32_t at = atomicAdd(&s.pool_used, nb);
+        if (at + nb <= (uint32_t)ET_POOL) {
+          tab = (uint16_t)at;
+          uint32_t acc = 0, x = at;
+          for (uint64_t m = sites; m; m &= m - 1, ++x) {
+            const int p = __ffsll((long long)m) - 1;
+            s.cum[x] = (uint16_t)acc;
+            s.pos[x] = (uint8_t)p;
+            acc += block_size(k, p, c0, c1, c2, c3);
+          }
+        }
+      }
+    }
+    s.k[j] = (uint8_t)k;
+    s.tab[j] = tab;
+    if (rel > 0 && rel < (int64_t)kExpTile) s.head[rel] = (uint16_t)j;
+  }
+  __syncthreads();
+  // (2) inclusive max-scan of the heads: entry -> local group
+  {
+    uint32_t loc[ET_PER];
+    uint32_t run = 0;
+#pragma unroll
+    for (int i = 0; i < ET_PER; ++i) {
+      run = max(run, (uint32_t)s.head[t * ET_PER + i]);
+      loc[i] = run;
+    }
+    uint32_t inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((int)lane_id() >= o) inc = max(inc, n);
+    }
+    if (lane_id() == 31) s.scratch[t >> 5] = inc;
+    __syncthreads();
+    uint32_t carry = 0;
+    for (int w = 0; w < (t >> 5); ++w) carry = max(carry, s.scratch[w]);
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane_id() > 0) carry = max(carry, prev);
+#pragma unroll
+    for (int i = 0; i < ET_PER; ++i) s.head[t * ET_PER + i] = (uint16_t)max(loc[i], carry);
+  }
+  __syncthreads();
+  // (3) one thread per entry, consecutive threads = consecutive entries.  The lanes of a warp sit
+  // in different groups with different k, so the work is phrased uniformly: find the block (site p,
+  // rank q inside it), then pattern = select(A, q / |B|), p, select(B, q % |B|) with the masks A / B
+  // empty where a level does not exist -- one code path for k = 1, 2, 3.
+  for (uint32_t i = t; i < tile_n; i += ET_THREADS) {
+    const uint32_t j = s.head[i];
+    const int k = s.k[j];
+    if (k == kLongGroup) continue;
+    uint32_t q = (uint32_t)((int32_t)i - s.off[j]);
+    const uint64_t c0 = k > 0 ? s_cm[j] : 1ull;
+    const uint64_t c1 = cm_of(1, j), c2 = cm_of(2, j), c3 = cm_of(3, j);
+    int p = 0;
+    if (k > 1) {
+      const uint32_t tab = s.tab[j];
+      if (tab != kNoTable) {
+        // last block whose first entry is <= q
+        uint32_t lo = 0, hi = (uint32_t)__popcll(block_sites(k, c0, c1));
+        while (hi - lo > 1) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (s.cum[tab + mid] <= q) lo = mid; else hi = mid;
+        }
+        p = s.pos[tab + lo];
+        q -= s.cum[tab + lo];
+      } else {
+        for (uint64_t m = block_sites(k, c0, c1); m; m &= m - 1) {
+          p = __ffsll((long long)m) - 1;
+          const uint32_t w = block_size(k, p, c0, c1, c2, c3);
+          if (q < w) break;
+          q -= w;
+        }
+      }
+    }
+    uint32_t pat;
+    if (k == 4) {
+      pat = block_entry(4, p, q, c0, c1, c2, c3);
+    } else {
+      // k = 3: A = first-class sites below p, B = third-class sites above p;  k = 2: B = second-class
+      // sites above p;  k = 1 (and 0): B = the sites of the class (one dummy site for k = 0)
+      const uint64_t A = k == 3 ? (c0 & below(p)) : 0ull;
+      const uint64_t B = k == 3 ? (c2 & above(p)) : (k == 2 ? (c1 & above(p)) : c0);
+      const uint32_t nb = (uint32_t)__popcll(B);
+      const uint32_t a = k == 3 ? q / nb : 0u;
+      const uint32_t b = q - a * nb;
+      const uint32_t sb = (uint32_t)select_bit(B, b) + 1u;
+      const uint32_t sa = (uint32_t)select_bit(A | (1ull << 63), a) + 1u;  // the guard bit keeps k < 3 in range
+      pat = k == 3 ? (sa | ((uint32_t)(p + 1) << 8) | (sb << 16))
+                   : (k == 2 ? ((uint32_t)(p + 1) | (sb << 8)) : (k == 1 ? sb : 0u));
+    }
+    const uint64_t e = e0 + i;
+    e_mass[e] = s.mass[j];
+    e_base[e] = s.base[j];
+    e_pat[e] = pat;
+  }
+}
+
 // ---- K6l ------------------------------------------------------------------------------
 // Groups of peptides longer than 64 residues (rare): one warp per listed group enumerates the
 // occurrences from the site list in shared memory; the last matched site is searched by all lanes
@@ -700,12 +931,21 @@ void launch_grp_expand(const uint8_t* d_res, const DevTables* d_tb, const Digest
   static const bool attr_set = [] {
     cudaFuncSetAttribute(grp_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(sizeof(ExpSmem) + (size_t)DBI_MAX_MODS_PER_PEP * EX_GMAX * 8));
+    cudaFuncSetAttribute(grp_expand_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(sizeof(ExpTabSmem) + (size_t)DBI_MAX_MODS_PER_PEP * EX_GMAX * 8));
     return true;
   }();
   (void)attr_set;
-  const size_t smem = sizeof(ExpSmem) + (size_t)cfg.max_mods * EX_GMAX * 8;
-  DBI_LAUNCH(grp_expand_kernel, (unsigned)n_tiles, EX_THREADS, smem, s, cfg, cmask, skey, spay, eoff,
-             tile_first, n_entries, base_bits, e_mass, e_base, e_pat, long_list, long_count, long_cap, d_err);
+  static const bool use_walker = std::getenv("DBI_EXPAND_WALKER") != nullptr;  // diagnostic: the walker variant
+  if (use_walker) {
+    const size_t smem = sizeof(ExpSmem) + (size_t)cfg.max_mods * EX_GMAX * 8;
+    DBI_LAUNCH(grp_expand_kernel, (unsigned)n_tiles, EX_THREADS, smem, s, cfg, cmask, skey, spay, eoff, tile_first,
+               n_entries, base_bits, e_mass, e_base, e_pat, long_list, long_count, long_cap, d_err);
+  } else {
+    const size_t smem = sizeof(ExpTabSmem) + (size_t)cfg.max_mods * EX_GMAX * 8;
+    DBI_LAUNCH(grp_expand_tab_kernel, (unsigned)n_tiles, ET_THREADS, smem, s, cfg, cmask, skey, spay, eoff,
+               tile_first, n_entries, base_bits, e_mass, e_base, e_pat, long_list, long_count, long_cap, d_err);
+  }
   if (long_cap > 0) {
     unsigned grid = (long_cap + MD_WARPS - 1) / MD_WARPS;
     if (grid > (unsigned)kNumSMsB200 * 4) grid = (unsigned)kNumSMsB200 * 4;
