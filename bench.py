@@ -66,7 +66,7 @@ def roofline_of(st_sum: dict, launches_per_build: dict, build_ms_total: float):
         name = "rs_onesweep_kernel<u64,u64>" if st_sum["dom_kernel"] == 1 else "rs_onesweep_kernel<u64,u32>"
         cands.append((name, st_sum["dom_ms"], st_sum["dom_launches"], st_sum["dom_bytes_per_launch"]))
     if st_sum["exp_launches"]:
-        cands.append(("grp_expand_kernel", st_sum["exp_ms"], st_sum["exp_launches"], st_sum["exp_bytes_per_launch"]))
+        cands.append(("grp_expand_tab_kernel", st_sum["exp_ms"], st_sum["exp_launches"], st_sum["exp_bytes_per_launch"]))
     if not cands:
         return None
     out = []
