@@ -170,7 +170,7 @@ ABI_SYMBOLS = [
     # multi-GPU staged build, bound in dbindex_b200/multigpu.py
     "dbi_mg_begin", "dbi_mg_digest", "dbi_mg_histogram", "dbi_mg_partition", "dbi_mg_pack_send",
     "dbi_mg_index_base", "dbi_mg_unique_counts", "dbi_mg_export_unique", "dbi_mg_import_unique", "dbi_mg_finish",
-    "dbi_mg_own_tiles", "dbi_mg_mod_tile_counts", "dbi_mg_expand", "dbi_mg_index_variants",
+    "dbi_mg_own_tiles", "dbi_mg_lookup_unique", "dbi_mg_expand", "dbi_mg_index_variants",
 ]
 
 

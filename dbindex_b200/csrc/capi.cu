@@ -184,7 +184,11 @@ struct dbi_handle {
   // multi-GPU staged build (dbi_mg_*): this rank, and the slice of the replicated unique tables
   // it owns; without mods the entries of a rank are that slice (entry i = unique ent_base_off + i)
   int mg_rank = 0, mg_world = 1;
-  uint64_t ent_base_off = 0;
+  uint64_t ent_base_off = 0;  // global id of this rank's first unique peptide (0 on a single GPU)
+  // sharded build with mods: (gpos, len) of EVERY rank's unique peptides, by global id -- all a
+  // rank needs to expand the groups it receives; the other unique tables stay with their owner
+  DevBuf ug_gpos, ug_len, ug_nlong;
+  uint64_t n_unique_global = 0;
   DevBuf mg_mass, mg_gpos, mg_prot, mg_len;  // local records between digest and exchange
   uint64_t mg_n = 0;
   DevBuf mg_vkey, mg_vpay;                   // local variants between expansion and exchange
@@ -208,7 +212,7 @@ struct dbi_handle {
     return ev_pool[ev_used++];
   }
 
-  const double* entry_mass() const { return e_mass.p ? e_mass.as<double>() : u_mass.as<double>() + ent_base_off; }
+  const double* entry_mass() const { return e_mass.p ? e_mass.as<double>() : u_mass.as<double>(); }
   const uint32_t* entry_base() const { return e_base.as<uint32_t>(); }
   const uint32_t* entry_pat() const { return e_pat.as<uint32_t>(); }
 };
@@ -364,6 +368,8 @@ void free_index(dbi_handle* h) {
   h->mg_counts.release(); h->mg_thr.release();
   h->mg_n = h->mg_v = 0;
   h->ent_base_off = 0;
+  h->ug_gpos.release(); h->ug_len.release(); h->ug_nlong.release();
+  h->n_unique_global = 0;
   h->n_emitted = h->n_unique = h->n_entries = 0;
   h->spans.clear();
   h->ev_used = 0;
@@ -652,7 +658,7 @@ int emit_variants(dbi_handle* h, uint32_t tile0, uint32_t ntiles, const KeySpace
     Stage sg(h, DBI_STAGE_MOD_EMIT);
     launch_mod_emit(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_mass.as<double>(),
                     h->u_gpos.as<uint32_t>(), h->u_len.as<uint16_t>(), n_unique, tile0, ntiles,
-                    counts.as<uint32_t>(), uoffs.as<uint64_t>(), ks.base_bits, vkey.as<uint64_t>(),
+                    counts.as<uint32_t>(), uoffs.as<uint64_t>(), ks.base_bits, h->ent_base_off, vkey.as<uint64_t>(),
                     vpay.as<uint64_t>(), s);
     h->st.algo_bytes[DBI_STAGE_MOD_EMIT] += n_in_tiles * (8 + 4 + 2 + 4 + 20) + V * 16;
   }
@@ -765,8 +771,8 @@ int emit_groups(dbi_handle* h, uint32_t tile0, uint32_t ntiles, const KeySpace& 
     Stage sg(h, DBI_STAGE_MOD_EMIT);
     launch_grp_emit(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_mass.as<double>(),
                     h->u_gpos.as<uint32_t>(), h->u_len.as<uint16_t>(), h->u_cmask.as<uint64_t>(), n_unique, tile0,
-                    ntiles, ng.as<uint8_t>(), goffs.as<uint64_t>(), ks.base_bits, gkey.as<uint64_t>(),
-                    gpay.as<uint64_t>(), h->d_err.as<uint32_t>(), s);
+                    ntiles, ng.as<uint8_t>(), goffs.as<uint64_t>(), ks.base_bits, h->ent_base_off,
+                    gkey.as<uint64_t>(), gpay.as<uint64_t>(), h->d_err.as<uint32_t>(), s);
     h->st.algo_bytes[DBI_STAGE_MOD_EMIT] += n_in_tiles * per_pep + NG * 16;
   }
   TR("ir_modemit");
@@ -788,7 +794,26 @@ int sort_expand_groups(dbi_handle* h, uint64_t* key_in, uint64_t* pay_in, uint64
     h->st.n_entries = 0;
     return DBI_OK;
   }
-  ensure_site_masks(h);
+  // sharded build: the groups received here belong to any rank's peptides.  Their site masks come
+  // from a table over ALL unique peptides when that is affordable (8 C bytes each, computed locally
+  // from the replicated residues: cheaper than re-deriving the masks per group up to ~8 ranks),
+  // otherwise the expansion kernel rebuilds them per group from (gpos, len).
+  const bool sharded = h->ug_gpos.p != nullptr;
+  const uint64_t mask_bytes = h->n_unique_global * (uint64_t)h->cfg.n_classes * 8;
+  static const bool no_table = std::getenv("DBI_MG_NO_MASK_TABLE") != nullptr;  // test hook
+  const bool global_masks = sharded && !no_table && mask_bytes <= (6ull << 30);
+  DevBuf ug_cmask, scratch_nlong;
+  if (!sharded) {
+    ensure_site_masks(h);
+  } else if (global_masks) {
+    Stage sg(h, DBI_STAGE_MOD_COUNT);
+    ug_cmask.alloc(std::max<uint64_t>(mask_bytes, 8), h->arena);
+    scratch_nlong.alloc(16, h->arena);
+    DBI_CUDA(cudaMemsetAsync(scratch_nlong.p, 0, 16, s));
+    launch_site_masks(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->ug_gpos.as<uint32_t>(),
+                      h->ug_len.as<uint16_t>(), h->n_unique_global, ug_cmask.as<uint64_t>(),
+                      (unsigned long long*)scratch_nlong.p, s);
+  }
   DevBuf key2, pay2, vtmp;
   key2.alloc(NG * 8, h->arena);
   pay2.alloc(NG * 8, h->arena);
@@ -820,7 +845,7 @@ int sort_expand_groups(dbi_handle* h, uint64_t* key_in, uint64_t* pay_in, uint64
     launch_full_scan_u32_to_u64(cnt.as<uint32_t>(), NG, eoff.as<uint64_t>(), stmp.p, s);
     DBI_CUDA(cudaMemsetAsync(lcount.p, 0, 16, s));
     DBI_CUDA(cudaMemcpyAsync(&V, eoff.as<uint64_t>() + NG, 8, cudaMemcpyDeviceToHost, s));
-    DBI_CUDA(cudaMemcpyAsync(&n_long, h->d_nlong.p, 8, cudaMemcpyDeviceToHost, s));
+    DBI_CUDA(cudaMemcpyAsync(&n_long, sharded ? h->ug_nlong.p : h->d_nlong.p, 8, cudaMemcpyDeviceToHost, s));
     DBI_CUDA(cudaStreamSynchronize(s));
     if (V >= (1ull << 32)) {
       set_error("more than 2^32 index entries on one GPU (%llu)", (unsigned long long)V);
@@ -841,8 +866,11 @@ int sort_expand_groups(dbi_handle* h, uint64_t* key_in, uint64_t* pay_in, uint64
       xa = h->get_event();
       cudaEventRecord(xa, s);
     }
-    launch_grp_expand(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_gpos.as<uint32_t>(),
-                      h->u_len.as<uint16_t>(), h->u_cmask.as<uint64_t>(), vk[r], vp[r], eoff.as<uint64_t>(),
+    launch_grp_expand(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg,
+                      sharded ? h->ug_gpos.as<uint32_t>() : h->u_gpos.as<uint32_t>(),
+                      sharded ? h->ug_len.as<uint16_t>() : h->u_len.as<uint16_t>(),
+                      sharded ? (global_masks ? ug_cmask.as<uint64_t>() : nullptr) : h->u_cmask.as<uint64_t>(), vk[r],
+                      vp[r], eoff.as<uint64_t>(),
                       tfirst.as<uint32_t>(), NG, V, ks.base_bits, h->e_mass.as<double>(), h->e_base.as<uint32_t>(),
                       h->e_pat.as<uint32_t>(), llist.as<uint32_t>(), lcount.as<uint32_t>(), (uint32_t)long_cap,
                       h->d_err.as<uint32_t>(), s);
@@ -894,7 +922,7 @@ void finish_stats(dbi_handle* h) {
   resolve_spans(h);
   h->st.device_bytes = h->d_res.bytes + h->d_pstart.bytes + h->u_mass.bytes + h->u_gpos.bytes + h->u_prot.bytes +
                        h->u_len.bytes + h->u_plo.bytes + h->plist.bytes + h->e_mass.bytes + h->e_base.bytes +
-                       h->e_pat.bytes;
+                       h->e_pat.bytes + h->ug_gpos.bytes + h->ug_len.bytes;
 }
 
 }  // namespace
@@ -1232,8 +1260,8 @@ int dbi_fetch(dbi_handle* h, uint64_t begin, uint64_t count, double* mass, uint3
   uint64_t total_ids = 0;
   {
     Stage sg(h, DBI_STAGE_FETCH);
-    launch_fetch_sizes(h->entry_base(), h->ent_base_off, h->u_plo.as<uint64_t>(), begin, count, sizes.as<uint32_t>(),
-                       tcnt.as<uint32_t>(), s);
+    launch_fetch_sizes(h->entry_base(), h->ent_base_off, h->ent_base_off, h->n_unique, h->u_plo.as<uint64_t>(), begin,
+                       count, sizes.as<uint32_t>(), tcnt.as<uint32_t>(), s);
     launch_scan_u32_to_u64(tcnt.as<uint32_t>(), tiles, toff.as<uint64_t>(), s);
     total_ids = read_u64(h, toff.as<uint64_t>() + tiles);
   }
@@ -1253,7 +1281,8 @@ int dbi_fetch(dbi_handle* h, uint64_t begin, uint64_t count, double* mass, uint3
   if (want_ids) o_ids.alloc(total_ids * 4, h->arena);
   {
     Stage sg(h, DBI_STAGE_FETCH);
-    launch_fetch_gather(h->entry_mass(), h->entry_base(), h->ent_base_off, h->entry_pat(), h->u_gpos.as<uint32_t>(),
+    launch_fetch_gather(h->entry_mass(), h->entry_base(), h->ent_base_off, h->ent_base_off, h->n_unique,
+                        h->ug_len.as<uint16_t>(), h->entry_pat(), h->u_gpos.as<uint32_t>(),
                         h->u_prot.as<uint32_t>(), h->u_len.as<uint16_t>(), h->u_plo.as<uint64_t>(),
                         h->plist.as<uint32_t>(), h->d_pstart.as<uint32_t>(), begin, count, sizes.as<uint32_t>(),
                         toff.as<uint64_t>(), o_mass.as<double>(), o_prot.as<uint32_t>(), o_off.as<uint32_t>(),
@@ -1591,67 +1620,61 @@ int dbi_mg_unique_counts(dbi_handle* h, uint64_t* n_unique, uint64_t* n_plist) {
   DBI_API_END
 }
 
-int dbi_mg_export_unique(dbi_handle* h, void* d_mass, void* d_gpos, void* d_prot, void* d_len, void* d_pcnt,
-                         void* d_plist) {
+int dbi_mg_export_unique(dbi_handle* h, void* d_gpos, void* d_len) {
   DBI_API_BEGIN(h)
   cudaStream_t s = h->stream;
   const uint64_t u = h->n_unique;
   if (u) {
-    const uint64_t np = read_u64(h, h->u_plo.as<uint64_t>() + u);
-    DBI_CUDA(cudaMemcpyAsync(d_mass, h->u_mass.p, u * 8, cudaMemcpyDeviceToDevice, s));
+    if (!d_gpos || !d_len) {
+      set_error("null argument");
+      return DBI_EINVAL;
+    }
     DBI_CUDA(cudaMemcpyAsync(d_gpos, h->u_gpos.p, u * 4, cudaMemcpyDeviceToDevice, s));
-    DBI_CUDA(cudaMemcpyAsync(d_prot, h->u_prot.p, u * 4, cudaMemcpyDeviceToDevice, s));
     DBI_CUDA(cudaMemcpyAsync(d_len, h->u_len.p, u * 2, cudaMemcpyDeviceToDevice, s));
-    launch_plo_to_counts(h->u_plo.as<uint64_t>(), u, (uint32_t*)d_pcnt, s);
-    DBI_CUDA(cudaMemcpyAsync(d_plist, h->plist.p, np * 4, cudaMemcpyDeviceToDevice, s));
     DBI_CUDA(cudaStreamSynchronize(s));
   }
   return DBI_OK;
   DBI_API_END
 }
 
-int dbi_mg_import_unique(dbi_handle* h, const uint64_t* rank_unique, const uint64_t* rank_plist, const void* d_mass,
-                         const void* d_gpos, const void* d_prot, const void* d_len, const void* d_pcnt,
-                         const void* d_plist) {
+int dbi_mg_import_unique(dbi_handle* h, const uint64_t* rank_unique, const void* d_gpos, const void* d_len) {
   DBI_API_BEGIN(h)
-  if (!rank_unique || !rank_plist) {
+  if (!rank_unique) {
     set_error("null argument");
     return DBI_EINVAL;
   }
   cudaStream_t s = h->stream;
-  uint64_t U = 0, P = 0, off = 0;
+  uint64_t U = 0, off = 0;
   for (int r = 0; r < h->mg_world; ++r) {
     if (r == h->mg_rank) off = U;
     U += rank_unique[r];
-    P += rank_plist[r];
   }
   if (U >= (1ull << 32)) {
     set_error("more than 2^32 unique peptides in total");
     return DBI_ERANGE;
   }
-  const uint64_t own = rank_unique[h->mg_rank];
-  h->u_mass.alloc(U * 8, h->arena);
-  h->u_gpos.alloc(U * 4, h->arena);
-  h->u_prot.alloc(U * 4, h->arena);
-  h->u_len.alloc(U * 2, h->arena);
-  h->u_plo.alloc((U + 1) * 8, h->arena);
-  h->plist.alloc(P * 4, h->arena);
-  if (U) {
-    DBI_CUDA(cudaMemcpyAsync(h->u_mass.p, d_mass, U * 8, cudaMemcpyDeviceToDevice, s));
-    DBI_CUDA(cudaMemcpyAsync(h->u_gpos.p, d_gpos, U * 4, cudaMemcpyDeviceToDevice, s));
-    DBI_CUDA(cudaMemcpyAsync(h->u_prot.p, d_prot, U * 4, cudaMemcpyDeviceToDevice, s));
-    DBI_CUDA(cudaMemcpyAsync(h->u_len.p, d_len, U * 2, cudaMemcpyDeviceToDevice, s));
-    DBI_CUDA(cudaMemcpyAsync(h->plist.p, d_plist, P * 4, cudaMemcpyDeviceToDevice, s));
+  if (rank_unique[h->mg_rank] != h->n_unique) {
+    set_error("rank_unique[%d] = %llu but this rank holds %llu unique peptides", h->mg_rank,
+              (unsigned long long)rank_unique[h->mg_rank], (unsigned long long)h->n_unique);
+    return DBI_EINVAL;
   }
-  DevBuf tmp;
-  tmp.alloc(full_scan_tmp_bytes(U), h->arena);
-  launch_full_scan_u32_to_u64((const uint32_t*)d_pcnt, U, h->u_plo.as<uint64_t>(), tmp.p, s);
+  if (U && (!d_gpos || !d_len)) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  h->ug_gpos.alloc(std::max<uint64_t>(U, 1) * 4, h->arena);
+  h->ug_len.alloc(std::max<uint64_t>(U, 1) * 2, h->arena);
+  h->ug_nlong.alloc(16, h->arena);
+  DBI_CUDA(cudaMemsetAsync(h->ug_nlong.p, 0, 16, s));
+  if (U) {
+    DBI_CUDA(cudaMemcpyAsync(h->ug_gpos.p, d_gpos, U * 4, cudaMemcpyDeviceToDevice, s));
+    DBI_CUDA(cudaMemcpyAsync(h->ug_len.p, d_len, U * 2, cudaMemcpyDeviceToDevice, s));
+    launch_count_long(h->ug_len.as<uint16_t>(), U, (unsigned long long*)h->ug_nlong.p, s);
+  }
   DBI_CUDA(cudaStreamSynchronize(s));
-  h->n_unique = U;
-  h->st.n_unique = U;
-  h->cmask_n = UINT64_MAX;  // the site masks belong to the table that was just replaced
+  h->n_unique_global = U;
   h->ent_base_off = off;
-  h->n_entries = own;  // until variants are indexed
+  h->n_entries = h->n_unique;  // until the groups are indexed
   return DBI_OK;
   DBI_API_END
 }
@@ -1663,6 +1686,7 @@ int dbi_mg_finish(dbi_handle* h) {
     return DBI_EINVAL;
   }
   h->e_mass.release(); h->e_base.release(); h->e_pat.release();
+  h->n_entries = h->n_unique;  // the entries of this rank are its own unique peptides
   h->st.n_entries = h->n_entries;
   h->built = true;
   finish_stats(h);
@@ -1676,49 +1700,69 @@ int dbi_mg_own_tiles(dbi_handle* h, uint32_t* tile_begin, uint32_t* n_tiles) {
     set_error("null argument");
     return DBI_EINVAL;
   }
-  const uint64_t a = h->ent_base_off, b = h->ent_base_off + h->n_entries;  // own slice of the unique tables
-  const uint32_t t0 = (uint32_t)((a + kModTile - 1) / kModTile);            // tiles that START in the slice
-  const uint32_t t1 = (uint32_t)((b + kModTile - 1) / kModTile);
-  *tile_begin = t0;
-  *n_tiles = t1 - t0;
+  *tile_begin = 0;
+  *n_tiles = (uint32_t)((h->n_unique + kModTile - 1) / kModTile);
   return DBI_OK;
   DBI_API_END
 }
 
-int dbi_mg_mod_tile_counts(dbi_handle* h, uint32_t* tile_begin, uint32_t* n_tiles, void* d_tile_counts) {
+int dbi_mg_lookup_unique(dbi_handle* h, const uint32_t* gids, uint64_t n, uint32_t* first_prot, uint32_t* first_off,
+                         uint16_t* len, uint64_t* prot_list_off, uint32_t* prot_ids, uint64_t prot_ids_capacity,
+                         uint64_t* n_prot_ids) {
   DBI_API_BEGIN(h)
-  if (!tile_begin || !n_tiles || !d_tile_counts) {
+  if (!h->built) {
+    set_error("Indexer is not initialized");
+    return DBI_ENOTINIT;
+  }
+  if (n_prot_ids) *n_prot_ids = 0;
+  if (n == 0) {
+    if (prot_list_off) prot_list_off[0] = 0;
+    return DBI_OK;
+  }
+  if (!gids) {
     set_error("null argument");
     return DBI_EINVAL;
   }
-  cudaStream_t s = h->stream;
-  const uint64_t a = h->ent_base_off, b = h->ent_base_off + h->n_entries;  // own slice of the unique tables
-  const uint32_t t0 = (uint32_t)((a + kModTile - 1) / kModTile);            // tiles that START in the slice
-  const uint32_t t1 = (uint32_t)((b + kModTile - 1) / kModTile);
-  *tile_begin = t0;
-  *n_tiles = t1 - t0;
-  if (t1 > t0) {
-    Stage sg(h, DBI_STAGE_MOD_COUNT);
-    if (h->cfg.n_seq > 0) {
-      ensure_site_masks(h);
-      DevBuf ng, tg;
-      ng.alloc(h->n_unique, h->arena);
-      tg.alloc((uint64_t)(t1 - t0) * 4, h->arena);
-      launch_grp_count(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_mass.as<double>(),
-                       h->u_gpos.as<uint32_t>(), h->u_len.as<uint16_t>(), h->u_cmask.as<uint64_t>(), h->n_unique, t0,
-                       t1 - t0, ng.as<uint8_t>(), tg.as<uint32_t>(), (uint32_t*)d_tile_counts,
-                       h->d_err.as<uint32_t>(), s);
-      DBI_CUDA(cudaStreamSynchronize(s));
-    } else {
-      DevBuf counts;
-      counts.alloc(h->n_unique * 4, h->arena);
-      launch_mod_count(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_mass.as<double>(),
-                       h->u_gpos.as<uint32_t>(), h->u_len.as<uint16_t>(), h->n_unique, t0, t1 - t0,
-                       counts.as<uint32_t>(), (uint32_t*)d_tile_counts, h->d_err.as<uint32_t>(), s);
-      DBI_CUDA(cudaStreamSynchronize(s));
+  for (uint64_t i = 0; i < n; ++i)
+    if ((uint64_t)gids[i] - h->ent_base_off >= h->n_unique) {
+      set_error("unique peptide %u is not held by this rank ([%llu, +%llu))", gids[i],
+                (unsigned long long)h->ent_base_off, (unsigned long long)h->n_unique);
+      return DBI_EINVAL;
     }
+  cudaStream_t s = h->stream;
+  const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
+  DevBuf d_g, sizes, tcnt, toff, o_prot, o_off, o_len, o_lo, o_ids;
+  d_g.alloc(n * 4, h->arena);
+  sizes.alloc(n * 4, h->arena);
+  tcnt.alloc(tiles * 4, h->arena);
+  toff.alloc((tiles + 1) * 8, h->arena);
+  DBI_CUDA(cudaMemcpyAsync(d_g.p, gids, n * 4, cudaMemcpyHostToDevice, s));
+  launch_fetch_sizes(d_g.as<uint32_t>(), 0, h->ent_base_off, h->n_unique, h->u_plo.as<uint64_t>(), 0, n,
+                     sizes.as<uint32_t>(), tcnt.as<uint32_t>(), s);
+  launch_scan_u32_to_u64(tcnt.as<uint32_t>(), tiles, toff.as<uint64_t>(), s);
+  const uint64_t total_ids = read_u64(h, toff.as<uint64_t>() + tiles);
+  if (n_prot_ids) *n_prot_ids = total_ids;
+  if (prot_ids && prot_ids_capacity < total_ids) {
+    set_error("prot_ids capacity %llu < %llu", (unsigned long long)prot_ids_capacity, (unsigned long long)total_ids);
+    return DBI_ERANGE;
   }
-  return check_err_bits(read_err(h));
+  if (first_prot) o_prot.alloc(n * 4, h->arena);
+  if (first_off) o_off.alloc(n * 4, h->arena);
+  if (len) o_len.alloc(n * 2, h->arena);
+  if (prot_list_off) o_lo.alloc((n + 1) * 8, h->arena);
+  if (prot_ids) o_ids.alloc(std::max<uint64_t>(total_ids, 1) * 4, h->arena);
+  launch_fetch_gather(nullptr, d_g.as<uint32_t>(), 0, h->ent_base_off, h->n_unique, h->ug_len.as<uint16_t>(), nullptr,
+                      h->u_gpos.as<uint32_t>(), h->u_prot.as<uint32_t>(), h->u_len.as<uint16_t>(),
+                      h->u_plo.as<uint64_t>(), h->plist.as<uint32_t>(), h->d_pstart.as<uint32_t>(), 0, n,
+                      sizes.as<uint32_t>(), toff.as<uint64_t>(), nullptr, o_prot.as<uint32_t>(), o_off.as<uint32_t>(),
+                      o_len.as<uint16_t>(), nullptr, o_lo.as<uint64_t>(), o_ids.as<uint32_t>(), s);
+  if (first_prot) DBI_CUDA(cudaMemcpyAsync(first_prot, o_prot.p, n * 4, cudaMemcpyDeviceToHost, s));
+  if (first_off) DBI_CUDA(cudaMemcpyAsync(first_off, o_off.p, n * 4, cudaMemcpyDeviceToHost, s));
+  if (len) DBI_CUDA(cudaMemcpyAsync(len, o_len.p, n * 2, cudaMemcpyDeviceToHost, s));
+  if (prot_list_off) DBI_CUDA(cudaMemcpyAsync(prot_list_off, o_lo.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+  if (prot_ids && total_ids) DBI_CUDA(cudaMemcpyAsync(prot_ids, o_ids.p, total_ids * 4, cudaMemcpyDeviceToHost, s));
+  DBI_CUDA(cudaStreamSynchronize(s));
+  return DBI_OK;
   DBI_API_END
 }
 

@@ -79,7 +79,7 @@ void launch_mod_count(const uint8_t* d_res, const DevTables* d_tb, const DigestC
 void launch_mod_emit(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const double* u_mass,
                      const uint32_t* u_gpos, const uint16_t* u_len, uint64_t n_unique, uint32_t tile0,
                      uint32_t ntiles, const uint32_t* counts, const uint64_t* tile_offs, uint64_t base_bits,
-                     uint64_t* v_key, uint64_t* v_payload, cudaStream_t s);
+                     uint64_t id_off, uint64_t* v_key, uint64_t* v_payload, cudaStream_t s);
 // entries from sorted (key, payload): mass = bits(key + base), base id, mod pattern
 void launch_split_entries(const uint64_t* skey, const uint64_t* spayload, uint64_t n, uint64_t base_bits,
                           double* e_mass, uint32_t* e_base, uint32_t* e_pat, cudaStream_t s);
@@ -92,6 +92,8 @@ constexpr int kExpTile = 1024;  // entries per CTA of the expansion
 void launch_site_masks(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const uint32_t* u_gpos,
                        const uint16_t* u_len, uint64_t n_unique, uint64_t* cmask, unsigned long long* n_long,
                        cudaStream_t s);
+// *n_long += peptides longer than 64 residues in a length table
+void launch_count_long(const uint16_t* len, uint64_t n, unsigned long long* n_long, cudaStream_t s);
 void launch_grp_count(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const double* u_mass,
                       const uint32_t* u_gpos, const uint16_t* u_len, const uint64_t* cmask, uint64_t n_unique,
                       uint32_t tile0, uint32_t ntiles, uint8_t* ng, uint32_t* tile_groups, uint32_t* tile_vars,
@@ -99,13 +101,16 @@ void launch_grp_count(const uint8_t* d_res, const DevTables* d_tb, const DigestC
 void launch_grp_emit(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const double* u_mass,
                      const uint32_t* u_gpos, const uint16_t* u_len, const uint64_t* cmask, uint64_t n_unique,
                      uint32_t tile0, uint32_t ntiles, const uint8_t* ng, const uint64_t* tile_goffs,
-                     uint64_t base_bits, uint64_t* g_key, uint64_t* g_pay, uint32_t* d_err, cudaStream_t s);
+                     uint64_t base_bits, uint64_t id_off, uint64_t* g_key, uint64_t* g_pay, uint32_t* d_err,
+                     cudaStream_t s);
 void launch_grp_extract_cnt(const uint64_t* pay, uint64_t n, uint32_t* cnt, cudaStream_t s);
 // first[t] = group holding entry t * kExpTile, t in [0, tiles]; first[tiles] = n_groups - 1
 void launch_grp_tile_first(const uint64_t* eoff, uint64_t n_groups, uint64_t n_entries, uint32_t* first,
                            cudaStream_t s);
 // entries of the sorted groups; groups of long peptides are listed in long_list and written by a
-// second kernel (launched when long_cap > 0)
+// second kernel (launched when long_cap > 0).  Payloads name peptides by global id.  cmask ==
+// nullptr (sharded build): u_gpos / u_len are the replicated global tables and the site masks
+// are rebuilt from the residues.
 void launch_grp_expand(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const uint32_t* u_gpos,
                        const uint16_t* u_len, const uint64_t* cmask, const uint64_t* skey, const uint64_t* spay,
                        const uint64_t* eoff, const uint32_t* tile_first, uint64_t n_groups, uint64_t n_entries,
@@ -117,10 +122,15 @@ void launch_query(const double* e_mass, uint64_t n_entries, const double* lo, co
                   uint64_t* hit_begin, uint64_t* hit_count, cudaStream_t s);
 // per-entry protein-list length for entries [begin, begin+count) + per-tile sums.
 // e_base == nullptr means "entry i is unique peptide i" (no differential mods).
-void launch_fetch_sizes(const uint32_t* e_base, uint64_t base_off, const uint64_t* u_plo, uint64_t begin,
-                        uint64_t count, uint32_t* sizes, uint32_t* tile_counts, cudaStream_t s);
+// Base peptides are named by global ids; the handle holds [own_lo, own_lo + own_n) of them (all of
+// them on a single GPU).  A base outside that range (sharded build) has list size 0 and comes back
+// as first_prot = DBI_REMOTE_BASE, first_off = global id, len = g_len[global id].
+void launch_fetch_sizes(const uint32_t* e_base, uint64_t base_off, uint64_t own_lo, uint64_t own_n,
+                        const uint64_t* u_plo, uint64_t begin, uint64_t count, uint32_t* sizes, uint32_t* tile_counts,
+                        cudaStream_t s);
 // what parseAddPeptideInfo materialises per hit; any output may be nullptr.
-void launch_fetch_gather(const double* e_mass, const uint32_t* e_base, uint64_t base_off, const uint32_t* e_pat,
+void launch_fetch_gather(const double* e_mass, const uint32_t* e_base, uint64_t base_off, uint64_t own_lo,
+                         uint64_t own_n, const uint16_t* g_len, const uint32_t* e_pat,
                          const uint32_t* u_gpos, const uint32_t* u_prot, const uint16_t* u_len, const uint64_t* u_plo, const uint32_t* plist,
                          const uint32_t* pstart, uint64_t begin, uint64_t count, const uint32_t* sizes,
                          const uint64_t* tile_offs, double* o_mass, uint32_t* o_prot, uint32_t* o_off,

@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(MD_THREADS)
                     const double* __restrict__ u_mass, const uint32_t* __restrict__ u_gpos,
                     const uint16_t* __restrict__ u_len, uint64_t n_unique, uint32_t tile0,
                     const uint32_t* __restrict__ counts, const uint64_t* __restrict__ tile_offs, uint64_t base_bits,
-                    uint64_t* __restrict__ v_key, uint64_t* __restrict__ v_payload) {
+                    uint64_t id_off, uint64_t* __restrict__ v_key, uint64_t* __restrict__ v_payload) {
   __shared__ ModTables mt;
   __shared__ WarpSites wsites[MD_WARPS];
   __shared__ uint32_t wsum[MD_WARPS];
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(MD_THREADS)
     if (cnt == 1) {  // only the unmodified peptide
       if (l == 0) {
         v_key[out] = (uint64_t)__double_as_longlong(bm) - base_bits;
-        v_payload[out] = u << 32;
+        v_payload[out] = (id_off + u) << 32;  // peptides are named by global id (id_off = 0 on a single GPU)
       }
       out += 1;
       continue;
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(MD_THREADS)
       if (pass) {
         const uint64_t slot = o + __popc(pm & lanemask_lt());
         v_key[slot] = (uint64_t)__double_as_longlong(m) - base_bits;
-        v_payload[slot] = (u << 32) | pat;
+        v_payload[slot] = ((id_off + u) << 32) | pat;
       }
       o += __popc(pm);
     }
@@ -272,10 +272,10 @@ void launch_mod_count(const uint8_t* d_res, const DevTables* d_tb, const DigestC
 void launch_mod_emit(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const double* u_mass,
                      const uint32_t* u_gpos, const uint16_t* u_len, uint64_t n_unique, uint32_t tile0,
                      uint32_t ntiles, const uint32_t* counts, const uint64_t* tile_offs, uint64_t base_bits,
-                     uint64_t* v_key, uint64_t* v_payload, cudaStream_t s) {
+                     uint64_t id_off, uint64_t* v_key, uint64_t* v_payload, cudaStream_t s) {
   if (n_unique == 0 || ntiles == 0) return;
   DBI_LAUNCH(mod_emit_kernel, ntiles, MD_THREADS, 0, s, d_res, d_tb, cfg, u_mass, u_gpos, u_len, n_unique, tile0,
-             counts, tile_offs, base_bits, v_key, v_payload);
+             counts, tile_offs, base_bits, id_off, v_key, v_payload);
 }
 
 void launch_split_entries(const uint64_t* skey, const uint64_t* spayload, uint64_t n, uint64_t base_bits,

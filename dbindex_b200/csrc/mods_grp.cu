@@ -148,6 +148,15 @@ __global__ void __launch_bounds__(MD_THREADS)
   }
 }
 
+// peptides longer than kMaskLen in a (global) length table
+__global__ void __launch_bounds__(MD_THREADS)
+    count_long_kernel(const uint16_t* __restrict__ len, uint64_t n, unsigned long long* __restrict__ n_long) {
+  const uint64_t i = (uint64_t)blockIdx.x * MD_THREADS + threadIdx.x;
+  const bool is = i < n && len[i] > kMaskLen;
+  const unsigned m = __ballot_sync(0xffffffffu, is);
+  if (m && lane_id() == 0) atomicAdd(n_long, (unsigned long long)__popc(m));
+}
+
 // ---- K5g ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MD_THREADS)
     grp_count_kernel(const uint8_t* __restrict__ res, const DevTables* __restrict__ tb, DigestCfg cfg,
@@ -199,7 +208,8 @@ __global__ void __launch_bounds__(MD_THREADS)
                     const double* __restrict__ u_mass, const uint32_t* __restrict__ u_gpos,
                     const uint16_t* __restrict__ u_len, const uint64_t* __restrict__ cmask, uint64_t n_unique,
                     uint32_t tile0, const uint8_t* __restrict__ ng_in, const uint64_t* __restrict__ tile_goffs,
-                    uint64_t base_bits, uint64_t* __restrict__ g_key, uint64_t* __restrict__ g_pay, uint32_t* err) {
+                    uint64_t base_bits, uint64_t id_off, uint64_t* __restrict__ g_key, uint64_t* __restrict__ g_pay,
+                    uint32_t* err) {
   extern __shared__ uint32_t s_cnt[];  // [n_seq][MD_THREADS]
   __shared__ ModTables mt;
   __shared__ uint32_t scratch[MD_WARPS + 1];
@@ -216,7 +226,8 @@ __global__ void __launch_bounds__(MD_THREADS)
   uint64_t o = tile_goffs[blockIdx.x] + ex;
   const double bm = u_mass[u];
   g_key[o] = (uint64_t)__double_as_longlong(bm) - base_bits;
-  g_pay[o] = (u << 32) | 1u;
+  const uint64_t gid = (id_off + u) << 32;  // global id of the peptide (id_off = 0 on a single GPU)
+  g_pay[o] = gid | 1u;
   ++o;
   if (ng == 1) return;  // no sites, or every modified mass is gated out
   SeqCounts sc{s_cnt + threadIdx.x};
@@ -228,7 +239,7 @@ __global__ void __launch_bounds__(MD_THREADS)
     const double m = seq_mass((uint32_t)v, C, bm, mt.cls_delta);
     if (gated && !(m >= cfg.min_mass && m <= cfg.max_mass)) continue;
     g_key[o] = (uint64_t)__double_as_longlong(m) - base_bits;
-    g_pay[o] = (u << 32) | ((uint64_t)v << kGrpCntBits) | (uint64_t)(c & kGrpCntMask);
+    g_pay[o] = gid | ((uint64_t)v << kGrpCntBits) | (uint64_t)(c & kGrpCntMask);
     ++o;
   }
 }
@@ -649,7 +660,9 @@ __device__ __forceinline__ uint32_t block_entry(int k, int p, uint32_t q, uint64
 }
 
 __global__ void __launch_bounds__(ET_THREADS)
-    grp_expand_tab_kernel(DigestCfg cfg, const uint64_t* __restrict__ cmask, const uint64_t* __restrict__ skey,
+    grp_expand_tab_kernel(DigestCfg cfg, const uint64_t* __restrict__ cmask, const uint8_t* __restrict__ res,
+                          const DevTables* __restrict__ tb, const uint32_t* __restrict__ g_gpos,
+                          const uint16_t* __restrict__ g_len, const uint64_t* __restrict__ skey,
                           const uint64_t* __restrict__ spay, const uint64_t* __restrict__ eoff,
                           const uint32_t* __restrict__ tile_first, uint64_t n_entries, uint64_t base_bits,
                           double* __restrict__ e_mass, uint32_t* __restrict__ e_base, uint32_t* __restrict__ e_pat,
@@ -670,6 +683,12 @@ __global__ void __launch_bounds__(ET_THREADS)
 
   for (int i = t; i < kExpTile; i += ET_THREADS) s.head[i] = 0;
   if (t == 0) s.pool_used = 0;
+  // sharded build: the peptides of the groups live on other GPUs and have no mask table here; their
+  // masks are rebuilt from the (replicated) residues through the global (gpos, len) tables
+  __shared__ uint8_t s_cls[256];  // class + 1 of a modifiable residue, 0 otherwise
+  if (!cmask)
+    for (int i = t; i < 256; i += ET_THREADS)
+      s_cls[i] = (tb->flags[i] & kFlagDiffMod) ? (uint8_t)(tb->cls[i] + 1) : (uint8_t)0;
   __syncthreads();
   // (1) stage the groups and their block tables
   for (uint32_t j = t; j <= ngrp; j += ET_THREADS) {
@@ -687,11 +706,27 @@ __global__ void __launch_bounds__(ET_THREADS)
     s.base[j] = b;
     uint16_t tab = kNoTable;
     if (k > 0) {
-      const uint64_t* cm = cmask + (uint64_t)b * (uint64_t)C;
-      const uint64_t c0 = cm[seq_class_at(pk, 0)];
-      const uint64_t c1 = k > 1 ? cm[seq_class_at(pk, 1)] : 0ull;
-      const uint64_t c2 = k > 2 ? cm[seq_class_at(pk, 2)] : 0ull;
-      const uint64_t c3 = k > 3 ? cm[seq_class_at(pk, 3)] : 0ull;
+      uint64_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+      if (cmask) {
+        const uint64_t* cm = cmask + (uint64_t)b * (uint64_t)C;
+        c0 = cm[seq_class_at(pk, 0)];
+        c1 = k > 1 ? cm[seq_class_at(pk, 1)] : 0ull;
+        c2 = k > 2 ? cm[seq_class_at(pk, 2)] : 0ull;
+        c3 = k > 3 ? cm[seq_class_at(pk, 3)] : 0ull;
+      } else if (g_len[b] <= kMaskLen) {
+        const uint32_t gp = g_gpos[b], len = g_len[b];
+        const uint32_t q0 = (uint32_t)seq_class_at(pk, 0) + 1u, q1 = k > 1 ? (uint32_t)seq_class_at(pk, 1) + 1u : 0xffu;
+        const uint32_t q2 = k > 2 ? (uint32_t)seq_class_at(pk, 2) + 1u : 0xffu;
+        const uint32_t q3 = k > 3 ? (uint32_t)seq_class_at(pk, 3) + 1u : 0xffu;
+        for (uint32_t i = 0; i < len; ++i) {
+          const uint32_t x = s_cls[ld_res(res, gp + i)];
+          const uint64_t bit = 1ull << i;
+          if (x == q0) c0 |= bit;
+          if (x == q1) c1 |= bit;
+          if (x == q2) c2 |= bit;
+          if (x == q3) c3 |= bit;
+        }
+      }
       s_cm[j] = c0;
       if (K > 1) s_cm[EX_GMAX + j] = c1;
       if (K > 2) s_cm[2 * EX_GMAX + j] = c2;
@@ -888,6 +923,11 @@ void launch_site_masks(const uint8_t* d_res, const DevTables* d_tb, const Digest
              cfg.n_classes, u_gpos, u_len, n_unique, cmask, n_long);
 }
 
+void launch_count_long(const uint16_t* len, uint64_t n, unsigned long long* n_long, cudaStream_t s) {
+  if (n == 0) return;
+  DBI_LAUNCH(count_long_kernel, (unsigned)((n + MD_THREADS - 1) / MD_THREADS), MD_THREADS, 0, s, len, n, n_long);
+}
+
 void launch_grp_count(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const double* u_mass,
                       const uint32_t* u_gpos, const uint16_t* u_len, const uint64_t* cmask, uint64_t n_unique,
                       uint32_t tile0, uint32_t ntiles, uint8_t* ng, uint32_t* tile_groups, uint32_t* tile_vars,
@@ -901,11 +941,12 @@ void launch_grp_count(const uint8_t* d_res, const DevTables* d_tb, const DigestC
 void launch_grp_emit(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const double* u_mass,
                      const uint32_t* u_gpos, const uint16_t* u_len, const uint64_t* cmask, uint64_t n_unique,
                      uint32_t tile0, uint32_t ntiles, const uint8_t* ng, const uint64_t* tile_goffs,
-                     uint64_t base_bits, uint64_t* g_key, uint64_t* g_pay, uint32_t* d_err, cudaStream_t s) {
+                     uint64_t base_bits, uint64_t id_off, uint64_t* g_key, uint64_t* g_pay, uint32_t* d_err,
+                     cudaStream_t s) {
   if (n_unique == 0 || ntiles == 0) return;
   const size_t smem = (size_t)cfg.n_seq * MD_THREADS * 4;
   DBI_LAUNCH(grp_emit_kernel, ntiles, MD_THREADS, smem, s, d_res, d_tb, cfg, u_mass, u_gpos, u_len, cmask, n_unique,
-             tile0, ng, tile_goffs, base_bits, g_key, g_pay, d_err);
+             tile0, ng, tile_goffs, base_bits, id_off, g_key, g_pay, d_err);
 }
 
 void launch_grp_extract_cnt(const uint64_t* pay, uint64_t n, uint32_t* cnt, cudaStream_t s) {
@@ -921,6 +962,7 @@ void launch_grp_tile_first(const uint64_t* eoff, uint64_t n_groups, uint64_t n_e
              n_groups, n_tiles, first);
 }
 
+// cmask == nullptr (sharded build): u_gpos / u_len are the GLOBAL tables and the masks are rebuilt from them
 void launch_grp_expand(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const uint32_t* u_gpos,
                        const uint16_t* u_len, const uint64_t* cmask, const uint64_t* skey, const uint64_t* spay,
                        const uint64_t* eoff, const uint32_t* tile_first, uint64_t n_groups, uint64_t n_entries,
@@ -937,13 +979,14 @@ void launch_grp_expand(const uint8_t* d_res, const DevTables* d_tb, const Digest
   }();
   (void)attr_set;
   static const bool use_walker = std::getenv("DBI_EXPAND_WALKER") != nullptr;  // diagnostic: the walker variant
-  if (use_walker) {
+  if (use_walker && cmask) {
     const size_t smem = sizeof(ExpSmem) + (size_t)cfg.max_mods * EX_GMAX * 8;
     DBI_LAUNCH(grp_expand_kernel, (unsigned)n_tiles, EX_THREADS, smem, s, cfg, cmask, skey, spay, eoff, tile_first,
                n_entries, base_bits, e_mass, e_base, e_pat, long_list, long_count, long_cap, d_err);
   } else {
     const size_t smem = sizeof(ExpTabSmem) + (size_t)cfg.max_mods * EX_GMAX * 8;
-    DBI_LAUNCH(grp_expand_tab_kernel, (unsigned)n_tiles, ET_THREADS, smem, s, cfg, cmask, skey, spay, eoff,
+    DBI_LAUNCH(grp_expand_tab_kernel, (unsigned)n_tiles, ET_THREADS, smem, s, cfg, cmask, d_res, d_tb, u_gpos, u_len,
+               skey, spay, eoff,
                tile_first, n_entries, base_bits, e_mass, e_base, e_pat, long_list, long_count, long_cap, d_err);
   }
   if (long_cap > 0) {

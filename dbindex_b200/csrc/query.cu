@@ -47,17 +47,18 @@ __global__ void __launch_bounds__(Q_THREADS)
 }
 
 __global__ void __launch_bounds__(Q_THREADS)
-    fetch_sizes_kernel(const uint32_t* __restrict__ e_base, uint64_t base_off, const uint64_t* __restrict__ u_plo,
-                       uint64_t begin, uint64_t count, uint32_t* __restrict__ sizes,
-                       uint32_t* __restrict__ tile_counts) {
+    fetch_sizes_kernel(const uint32_t* __restrict__ e_base, uint64_t base_off, uint64_t own_lo, uint64_t own_n,
+                       const uint64_t* __restrict__ u_plo, uint64_t begin, uint64_t count,
+                       uint32_t* __restrict__ sizes, uint32_t* __restrict__ tile_counts) {
   __shared__ uint32_t scratch[Q_THREADS / 32 + 1];
   const uint64_t tile_base = (uint64_t)blockIdx.x * kScanTile;
   uint32_t sum = 0;
   for (int k = 0; k < Q_IPT; ++k) {
     const uint64_t i = tile_base + (uint64_t)k * Q_THREADS + threadIdx.x;
     if (i >= count) break;
-    const uint64_t b = e_base ? (uint64_t)e_base[begin + i] : base_off + begin + i;
-    const uint32_t sz = (uint32_t)(u_plo[b + 1] - u_plo[b]);
+    // base peptides are named by GLOBAL ids; this handle holds [own_lo, own_lo + own_n) of them
+    const uint64_t b = (e_base ? (uint64_t)e_base[begin + i] : base_off + begin + i) - own_lo;
+    const uint32_t sz = b < own_n ? (uint32_t)(u_plo[b + 1] - u_plo[b]) : 0u;
     sizes[i] = sz;
     sum += sz;
   }
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(Q_THREADS)
 
 __global__ void __launch_bounds__(Q_THREADS)
     fetch_gather_kernel(const double* __restrict__ e_mass, const uint32_t* __restrict__ e_base, uint64_t base_off,
+                        uint64_t own_lo, uint64_t own_n, const uint16_t* __restrict__ g_len,
                         const uint32_t* __restrict__ e_pat, const uint32_t* __restrict__ u_gpos,
                         const uint32_t* __restrict__ u_prot, const uint16_t* __restrict__ u_len,
                         const uint64_t* __restrict__ u_plo, const uint32_t* __restrict__ plist,
@@ -89,16 +91,18 @@ __global__ void __launch_bounds__(Q_THREADS)
     const uint32_t ex = block_exclusive_sum<uint32_t, Q_THREADS>(sz, scratch, &total);
     if (valid) {
       const uint64_t e = begin + i;
-      const uint64_t b = e_base ? (uint64_t)e_base[e] : base_off + e;
-      const uint32_t pr = u_prot[b];
+      const uint64_t gid = e_base ? (uint64_t)e_base[e] : base_off + e;
+      const uint64_t b = gid - own_lo;
+      const bool own = b < own_n;  // else the base peptide lives on another GPU of a sharded build
+      const uint32_t pr = own ? u_prot[b] : 0xffffffffu;
       if (o_mass) o_mass[i] = e_mass[e];
-      if (o_prot) o_prot[i] = pr;
-      if (o_off) o_off[i] = u_gpos[b] - pstart[pr];  // sequenceOffset inside the first protein
-      if (o_len) o_len[i] = u_len[b];
+      if (o_prot) o_prot[i] = pr;  // DBI_REMOTE_BASE
+      if (o_off) o_off[i] = own ? u_gpos[b] - pstart[pr] : (uint32_t)gid;  // sequenceOffset inside the first protein
+      if (o_len) o_len[i] = own ? u_len[b] : g_len[gid];
       if (o_pat) o_pat[i] = e_pat ? e_pat[e] : 0u;
       const uint64_t lo = running + ex;
       if (o_list_off) o_list_off[i] = lo;
-      if (o_ids) {
+      if (o_ids && own) {
         const uint64_t src = u_plo[b];
         for (uint32_t j = 0; j < sz; ++j) o_ids[lo + j] = plist[src + j];
       }
@@ -153,21 +157,24 @@ void launch_query(const double* e_mass, uint64_t n_entries, const double* lo, co
   DBI_LAUNCH(query_kernel, grid, Q_THREADS, 0, s, e_mass, n_entries, lo, hi, nq, hit_begin, hit_count);
 }
 
-void launch_fetch_sizes(const uint32_t* e_base, uint64_t base_off, const uint64_t* u_plo, uint64_t begin,
-                        uint64_t count, uint32_t* sizes, uint32_t* tile_counts, cudaStream_t s) {
+void launch_fetch_sizes(const uint32_t* e_base, uint64_t base_off, uint64_t own_lo, uint64_t own_n,
+                        const uint64_t* u_plo, uint64_t begin, uint64_t count, uint32_t* sizes, uint32_t* tile_counts,
+                        cudaStream_t s) {
   if (count == 0) return;
   const unsigned tiles = (unsigned)((count + kScanTile - 1) / kScanTile);
-  DBI_LAUNCH(fetch_sizes_kernel, tiles, Q_THREADS, 0, s, e_base, base_off, u_plo, begin, count, sizes, tile_counts);
+  DBI_LAUNCH(fetch_sizes_kernel, tiles, Q_THREADS, 0, s, e_base, base_off, own_lo, own_n, u_plo, begin, count, sizes,
+             tile_counts);
 }
 
-void launch_fetch_gather(const double* e_mass, const uint32_t* e_base, uint64_t base_off, const uint32_t* e_pat,
+void launch_fetch_gather(const double* e_mass, const uint32_t* e_base, uint64_t base_off, uint64_t own_lo,
+                         uint64_t own_n, const uint16_t* g_len, const uint32_t* e_pat,
                          const uint32_t* u_gpos, const uint32_t* u_prot, const uint16_t* u_len, const uint64_t* u_plo, const uint32_t* plist,
                          const uint32_t* pstart, uint64_t begin, uint64_t count, const uint32_t* sizes,
                          const uint64_t* tile_offs, double* o_mass, uint32_t* o_prot, uint32_t* o_off,
                          uint16_t* o_len, uint32_t* o_pat, uint64_t* o_list_off, uint32_t* o_ids, cudaStream_t s) {
   if (count == 0) return;
   const unsigned tiles = (unsigned)((count + kScanTile - 1) / kScanTile);
-  DBI_LAUNCH(fetch_gather_kernel, tiles, Q_THREADS, 0, s, e_mass, e_base, base_off, e_pat, u_gpos, u_prot, u_len, u_plo, plist,
+  DBI_LAUNCH(fetch_gather_kernel, tiles, Q_THREADS, 0, s, e_mass, e_base, base_off, own_lo, own_n, g_len, e_pat, u_gpos, u_prot, u_len, u_plo, plist,
              pstart, begin, count, sizes, tile_offs, o_mass, o_prot, o_off, o_len, o_pat, o_list_off, o_ids);
 }
 

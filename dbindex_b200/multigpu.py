@@ -10,11 +10,15 @@ touches (:333-343).  Here a bucket is a GPU:
   2. global key histogram (all-reduce) -> equal-count splitters -> all-to-all of the records, so
      rank d receives one contiguous mass slice, rank-ordered = global emission order, which keeps
      "first occurrence" (SURVEY.md Q6) global;
-  3. local sort + merge; the unique tables are then replicated to every rank (they are ~20 B per
-     unique peptide), so any rank can materialise any hit locally;
-  4. differential mods: base tiles are re-dealt by VARIANT count (the heavy slice has orders of
-     magnitude more variants per peptide), expanded, and the variants go through a second
-     histogram -> splitters -> all-to-all by variant mass, then a local sort;
+  3. local sort + merge: every rank owns the unique peptides (first occurrence, protein lists) of
+     its base-mass slice; a peptide is named by its global id = rank offset + local row;
+  4. differential mods: every rank lists the variant GROUPS of its own peptides (one record per
+     peptide and sequence of shift classes -- they share one mass); the groups go through a second
+     histogram -> splitters (weighted by variant count) -> all-to-all by VARIANT mass, and the
+     receiver sorts and expands them.  To expand a foreign peptide's group a rank only needs where
+     its residues are, so (gpos, len) of all unique peptides -- 6 bytes each -- are all-gathered;
+     nothing else is replicated.  A hit whose base peptide lives elsewhere is resolved by its owner
+     (`fetch_resolved`), the way a query is answered by the rank that owns its mass;
   5. queries are routed on the host with the same splitters; a range that straddles a splitter is
      answered by both neighbours, exactly like Mult.getSequences walking two buckets.
 
@@ -170,16 +174,15 @@ class ShardEngine:
     def partition(self, stage: int, splitters: np.ndarray) -> np.ndarray: ...  # send counts [world]
     def pack_send(self, stage: int) -> List[torch.Tensor]: ...
     def index_base(self, mass, gpos, prot, length): ...
-    def export_unique(self) -> List[torch.Tensor]: ...   # mass, gpos, prot, len, pcnt, plist
-    def import_unique(self, rank_unique, rank_plist, tables: List[torch.Tensor]): ...
+    def export_unique(self) -> List[torch.Tensor]: ...   # gpos (int32), len (int16) of the own unique peptides
+    def import_unique(self, rank_unique, tables: List[torch.Tensor]): ...   # their rank-order concatenation
     def finish(self): ...
-    def own_tiles(self) -> Tuple[int, int]: ...                                # (tile_begin, n_tiles) of the own slice
-    def mod_tile_counts(self) -> Tuple[int, torch.Tensor]: ...                # (tile_begin, int32 counts)
+    def own_tiles(self) -> Tuple[int, int]: ...                                # (tile_begin, n_tiles) of the own peptides
     def expand(self, tile_begin: int, n_tiles: int) -> int: ...
     def index_variants(self, key, payload): ...
 
 
-def build_sharded(engine: ShardEngine, rebalance: bool = False) -> dict:
+def build_sharded(engine: ShardEngine) -> dict:
     """Run the staged multi-rank build on this rank.  Returns routing info:
     {"split_mass": masses at which the entry slices are cut, "bytes_sent": ..., ...}."""
     import time
@@ -228,38 +231,27 @@ def build_sharded(engine: ShardEngine, rebalance: bool = False) -> dict:
     engine.index_base(*recv)
     del recv
     lap("index_base")
-    tables = engine.export_unique()
-    n_u, n_p = int(tables[0].numel()), int(tables[5].numel())
-    cnt = _all_gather_ints([n_u, n_p], dev)
-    rank_unique, rank_plist = cnt[:, 0], cnt[:, 1]
-    gathered = _gather_tables(tables, [rank_plist if i == 5 else rank_unique for i in range(len(tables))])
-    lap("replicate_tables")
-    engine.import_unique(rank_unique, rank_plist, gathered)
-    del tables, gathered
-    lap("import_unique")
-    info["n_unique"] = int(rank_unique.sum())
     if not engine.has_mods:
+        n_u = engine.n_unique()
+        info["unique_off"] = np.concatenate(([0], np.cumsum(_all_gather_ints([n_u], dev)[:, 0])))
+        info["n_unique"] = int(info["unique_off"][-1])
         engine.finish()
         info["split_mass"] = splitter_masses(base_split, shift, engine.min_mass)
         return info
 
-    if rebalance:
-        # re-deal the base tiles by variant count (the heavy slices hold more variants per peptide)
-        t0, tc = engine.mod_tile_counts()
-        meta = _all_gather_ints([t0, int(tc.numel())], dev)
-        all_counts = _gather_concat(tc, meta[:, 1]).cpu().numpy()
-        # ranks own ascending slices, so the concatenation is in tile order starting at tile meta[0, 0]
-        first_tile = int(meta[0, 0]) if len(all_counts) else 0
-        # cost model of the expansion: one unit per variant plus a fixed per-peptide part (site scan,
-        # table loads) worth ~64 variants -- light slices hold many cheap peptides
-        ranges = balance_tiles(all_counts.astype(np.int64) + 64 * 256, world)
-        tb, tn = ranges[rank]
-        lap("tile_counts")
-    else:
-        # every rank lists the groups of its own slice: that work is small and nearly even; the
-        # expensive part (sort + expansion) is balanced by the variant-weighted splitters below
-        first_tile = 0
-        tb, tn = engine.own_tiles()
+    tables = engine.export_unique()
+    rank_unique = _all_gather_ints([int(tables[0].numel())], dev)[:, 0]
+    gathered = _gather_tables(tables, [rank_unique] * len(tables))
+    lap("gather_gpos_len")
+    engine.import_unique(rank_unique, gathered)
+    del tables, gathered
+    lap("import_unique")
+    info["unique_off"] = np.concatenate(([0], np.cumsum(rank_unique)))
+    info["n_unique"] = int(rank_unique.sum())
+    # every rank lists the groups of its own peptides: that work is small and nearly even; the
+    # expensive part (sort + expansion) is balanced by the variant-weighted splitters below
+    first_tile = 0
+    tb, tn = engine.own_tiles()
     engine.expand(first_tile + tb, tn)
     lap("expand")
     recv, var_split, shift = exchange(1, (8, 8))
@@ -292,10 +284,9 @@ class GpuShardEngine(ShardEngine):
             "dbi_mg_pack_send": [vp, C.c_int, vp, vp, vp, vp],
             "dbi_mg_index_base": [vp, vp, vp, vp, vp, C.c_uint64],
             "dbi_mg_unique_counts": [vp, u64p, u64p],
-            "dbi_mg_export_unique": [vp, vp, vp, vp, vp, vp, vp],
-            "dbi_mg_import_unique": [vp, vp, vp, vp, vp, vp, vp, vp, vp],
+            "dbi_mg_export_unique": [vp, vp, vp],
+            "dbi_mg_import_unique": [vp, vp, vp, vp],
             "dbi_mg_finish": [vp],
-            "dbi_mg_mod_tile_counts": [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), vp],
             "dbi_mg_own_tiles": [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
             "dbi_mg_expand": [vp, C.c_uint32, C.c_uint32, u64p],
             "dbi_mg_index_variants": [vp, vp, vp, C.c_uint64],
@@ -355,20 +346,22 @@ class GpuShardEngine(ShardEngine):
         self._ck(self.lib.dbi_mg_index_base(self.g._h, self._p(mass), self._p(gpos), self._p(prot), self._p(length),
                                             int(mass.numel())))
 
-    def export_unique(self):
+    def n_unique(self):
         u, p = self.C.c_uint64(), self.C.c_uint64()
         self._ck(self.lib.dbi_mg_unique_counts(self.g._h, self.C.byref(u), self.C.byref(p)))
-        t = [self._empty(u.value, torch.int64), self._empty(u.value, torch.int32), self._empty(u.value, torch.int32),
-             self._empty(u.value, torch.int16), self._empty(u.value, torch.int32), self._empty(p.value, torch.int32)]
+        return u.value
+
+    def export_unique(self):
+        u = self.n_unique()
+        t = [self._empty(u, torch.int32), self._empty(u, torch.int16)]
         torch.cuda.current_stream().synchronize()
         self._ck(self.lib.dbi_mg_export_unique(self.g._h, *[self._p(x) for x in t]))
         return t
 
-    def import_unique(self, rank_unique, rank_plist, tables):
+    def import_unique(self, rank_unique, tables):
         ru = np.ascontiguousarray(rank_unique, dtype=np.uint64)
-        rp = np.ascontiguousarray(rank_plist, dtype=np.uint64)
         torch.cuda.current_stream().synchronize()
-        self._ck(self.lib.dbi_mg_import_unique(self.g._h, ru.ctypes.data, rp.ctypes.data, *[self._p(x) for x in tables]))
+        self._ck(self.lib.dbi_mg_import_unique(self.g._h, ru.ctypes.data, *[self._p(x) for x in tables]))
 
     def finish(self):
         self._ck(self.lib.dbi_mg_finish(self.g._h))
@@ -378,15 +371,6 @@ class GpuShardEngine(ShardEngine):
         self._ck(self.lib.dbi_mg_own_tiles(self.g._h, self.C.byref(t0), self.C.byref(nt)))
         return t0.value, nt.value
 
-    def mod_tile_counts(self):
-        st = self.g.stats()
-        cap = int(st["n_unique"]) // 256 + 4
-        buf = torch.zeros(cap, dtype=torch.int32, device=self.device)
-        t0, nt = self.C.c_uint32(), self.C.c_uint32()
-        torch.cuda.current_stream().synchronize()
-        self._ck(self.lib.dbi_mg_mod_tile_counts(self.g._h, self.C.byref(t0), self.C.byref(nt), buf.data_ptr()))
-        return t0.value, buf[:nt.value].clone()
-
     def expand(self, tile_begin, n_tiles):
         v = self.C.c_uint64()
         self._ck(self.lib.dbi_mg_expand(self.g._h, tile_begin, n_tiles, self.C.byref(v)))
@@ -395,3 +379,63 @@ class GpuShardEngine(ShardEngine):
     def index_variants(self, key, payload):
         torch.cuda.current_stream().synchronize()
         self._ck(self.lib.dbi_mg_index_variants(self.g._h, self._p(key), self._p(payload), int(key.numel())))
+
+
+# ---- hits whose base peptide lives on another rank ---------------------------------------------
+REMOTE_BASE = 0xFFFFFFFF
+
+
+def lookup_unique(g, gids: np.ndarray) -> dict:
+    """dbi_mg_lookup_unique on the rank that owns `gids`: first occurrence and protein list of each."""
+    import ctypes as C
+    lib = g.lib
+    lib.dbi_mg_lookup_unique.restype = C.c_int
+    lib.dbi_mg_lookup_unique.argtypes = [C.c_void_p] * 2 + [C.c_uint64] + [C.c_void_p] * 5 + [C.c_uint64, C.c_void_p]
+    gids = np.ascontiguousarray(gids, dtype=np.uint32)
+    n = len(gids)
+    prot, off = np.empty(n, np.uint32), np.empty(n, np.uint32)
+    ln, plo = np.empty(n, np.uint16), np.empty(n + 1, np.uint64)
+    n_ids = C.c_uint64()
+    p = lambda a: a.ctypes.data if a.size else None  # noqa: E731
+    g._check(lib.dbi_mg_lookup_unique(g._h, p(gids), n, None, None, None, None, None, 0, C.byref(n_ids)))
+    ids = np.empty(n_ids.value, np.uint32)
+    g._check(lib.dbi_mg_lookup_unique(g._h, p(gids), n, p(prot), p(off), p(ln), plo.ctypes.data, p(ids), len(ids),
+                                      C.byref(n_ids)))
+    return {"first_prot": prot, "first_off": off, "len": ln, "prot_list_off": plo, "prot_ids": ids}
+
+
+def fetch_resolved(g, info: dict, begin: int, count: int) -> dict:
+    """COLLECTIVE dbi_fetch of entries [begin, begin + count) of this rank's slice with every base
+    peptide resolved: hits whose base lives on another rank (first_prot == DBI_REMOTE_BASE, first_off
+    = global id) are answered by their owners.  A process that holds all the handles (the Java host)
+    calls the owner's handle directly instead of this exchange."""
+    f = g.fetch(begin, count)
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return f
+    world, rank = dist.get_world_size(), dist.get_rank()
+    uoff = np.asarray(info["unique_off"], dtype=np.int64)
+    remote = np.nonzero(f["first_prot"] == REMOTE_BASE)[0]
+    gids = f["first_off"][remote].astype(np.int64)
+    owner = np.searchsorted(uoff, gids, side="right") - 1
+    ask = [np.unique(gids[owner == r]).astype(np.uint32) for r in range(world)]
+    asked = [None] * world
+    dist.all_gather_object(asked, ask)           # asked[src][dst] = ids src wants from dst
+    answers = [lookup_unique(g, asked[src][rank]) if len(asked[src][rank]) else None for src in range(world)]
+    got = [None] * world
+    dist.all_gather_object(got, answers)         # got[dst][src] = dst's answer to src
+    plo = f["prot_list_off"].astype(np.int64)
+    lists = [f["prot_ids"][plo[i]:plo[i + 1]] for i in range(len(plo) - 1)]
+    for r in range(world):
+        ans = got[r][rank]
+        if ans is None:
+            continue
+        pos = {int(gid): k for k, gid in enumerate(ask[r])}
+        alo = ans["prot_list_off"].astype(np.int64)
+        for i in remote[owner == r]:
+            k = pos[int(f["first_off"][i])]
+            f["first_prot"][i], f["first_off"][i] = ans["first_prot"][k], ans["first_off"][k]
+            lists[i] = ans["prot_ids"][alo[k]:alo[k + 1]]
+    sizes = np.array([len(x) for x in lists], dtype=np.int64)
+    f["prot_list_off"] = np.concatenate(([0], np.cumsum(sizes))).astype(np.uint64)
+    f["prot_ids"] = np.concatenate(lists).astype(np.uint32) if len(lists) and sizes.sum() else np.zeros(0, np.uint32)
+    return f

@@ -255,9 +255,10 @@ int dbi_build_from_records(dbi_handle* h, const double* mass, const uint32_t* pr
  *
  *   dbi_mg_begin -> dbi_mg_digest
  *   -> dbi_mg_histogram(0) .. all-reduce .. dbi_mg_partition(0) -> dbi_mg_pack_send(0) .. all-to-all ..
- *   -> dbi_mg_index_base -> dbi_mg_export_unique .. broadcast from every rank .. dbi_mg_import_unique
+ *   -> dbi_mg_index_base
  *   no mods:  -> dbi_mg_finish
- *   mods:     -> dbi_mg_own_tiles (or dbi_mg_mod_tile_counts .. all-gather, to re-deal by cost) -> dbi_mg_expand
+ *   mods:     -> dbi_mg_export_unique .. all-gather of (gpos, len) .. dbi_mg_import_unique
+ *             -> dbi_mg_own_tiles -> dbi_mg_expand
  *             -> dbi_mg_histogram(1) .. dbi_mg_partition(1) -> dbi_mg_pack_send(1) .. all-to-all ..
  *             -> dbi_mg_index_variants
  */
@@ -280,24 +281,28 @@ int dbi_mg_pack_send(dbi_handle* h, int stage, void* d0, void* d1, void* d2, voi
 int dbi_mg_index_base(dbi_handle* h, const void* d_mass, const void* d_gpos, const void* d_prot,
                       const void* d_len, uint64_t n);
 int dbi_mg_unique_counts(dbi_handle* h, uint64_t* n_unique, uint64_t* n_plist);
-/* copy the local unique tables out: mass f64[u], gpos u32[u], prot u32[u], len u16[u],
- * protein-list length u32[u], protein ids u32[n_plist] */
-int dbi_mg_export_unique(dbi_handle* h, void* d_mass, void* d_gpos, void* d_prot, void* d_len, void* d_pcnt,
-                         void* d_plist);
-/* adopt the rank-order concatenation of every rank's tables as the (replicated) global
- * unique tables; this rank's slice is [sum(rank_unique[0..rank)), +rank_unique[rank]) */
-int dbi_mg_import_unique(dbi_handle* h, const uint64_t* rank_unique, const uint64_t* rank_plist,
-                         const void* d_mass, const void* d_gpos, const void* d_prot, const void* d_len,
-                         const void* d_pcnt, const void* d_plist);
-/* no differential mods: the entries of this rank are its slice of the unique tables */
+/* Differential mods only.  A rank expands the groups whose MASS falls into its slice, and their
+ * peptides belong to any rank; all it needs of a foreign peptide is where its residues are.  So
+ * every rank publishes (gpos u32[u], len u16[u]) of its unique peptides ... */
+int dbi_mg_export_unique(dbi_handle* h, void* d_gpos, void* d_len);
+/* ... and adopts the rank-order concatenation of them (device buffers, all-gathered by the host).
+ * From here on a unique peptide is named by its GLOBAL id = sum(rank_unique[0..owner)) + local row;
+ * masses, first occurrences and protein lists stay with the owner (dbi_mg_lookup_unique). */
+int dbi_mg_import_unique(dbi_handle* h, const uint64_t* rank_unique, const void* d_gpos, const void* d_len);
+/* no differential mods: the entries of this rank are its own unique peptides (no table exchange) */
 int dbi_mg_finish(dbi_handle* h);
-/* the mod tiles (256 unique peptides each) that START in this rank's slice of the tables */
+/* the mod tiles (256 unique peptides each) of this rank's own unique peptides */
 int dbi_mg_own_tiles(dbi_handle* h, uint32_t* tile_begin, uint32_t* n_tiles);
-/* variant counts of the mod tiles (256 unique peptides each) that START in this rank's
- * slice: *tile_begin, *n_tiles, and d_tile_counts[0..*n_tiles) (u32, capacity >= slice/256 + 2) */
-int dbi_mg_mod_tile_counts(dbi_handle* h, uint32_t* tile_begin, uint32_t* n_tiles, void* d_tile_counts);
-/* expand the variants of tiles [tile_begin, tile_begin + n_tiles) of the global tables (any
- * range: the tables are replicated, so the host can balance by variant count).  What travels
+/* dbi_fetch on a sharded index with mods returns first_prot = DBI_REMOTE_BASE and first_off =
+ * global id for entries whose base peptide is held by another rank; that rank resolves them here:
+ * first occurrence (protein, offset), length and the protein list of each listed global id
+ * (same two-call sizing of prot_ids as dbi_fetch). */
+#define DBI_REMOTE_BASE 0xffffffffu
+int dbi_mg_lookup_unique(dbi_handle* h, const uint32_t* gids, uint64_t n, uint32_t* first_prot, uint32_t* first_off,
+                         uint16_t* len, uint64_t* prot_list_off, uint32_t* prot_ids, uint64_t prot_ids_capacity,
+                         uint64_t* n_prot_ids);
+/* list the variant groups of tiles [tile_begin, tile_begin + n_tiles) of this rank's unique
+ * peptides.  What travels
  * in stage 1 is one {key, payload} record per (peptide, class sequence) group -- all its
  * variants share one mass -- or one per variant when there are more than 32 class sequences;
  * the stage-1 histogram weighs a group by its variant count. */

@@ -22,7 +22,7 @@ import torch.distributed as dist  # noqa: E402
 import dbindex_b200 as dbi  # noqa: E402
 from bench import CFG2  # noqa: E402
 from dbindex_b200 import synth  # noqa: E402
-from dbindex_b200.multigpu import GpuShardEngine, build_sharded, route_queries  # noqa: E402
+from dbindex_b200.multigpu import GpuShardEngine, build_sharded, fetch_resolved, route_queries  # noqa: E402
 from oracle.oracle_py import Oracle  # noqa: E402  (checker only)
 
 
@@ -106,16 +106,15 @@ def main():
         for k2, (b0, c0) in enumerate(zip(bq, cq)):
             i2 = sel[k2]
             want = res[r0 + int(e["first_off"][i2]):r0 + int(e["first_off"][i2]) + int(e["len"][i2])].tobytes()
-            for h0 in range(int(b0), int(b0 + c0), 1 << 18):
-                hit = g.fetch(h0, int(min(b0 + c0 - h0, 1 << 18)))
-                plo = hit["prot_list_off"].astype(np.int64)
-                for h in np.nonzero((hit["len"] == len(want)) & (hit["modpat"] == e["modpat"][i2]))[0]:
-                    fp, fo = int(hit["first_prot"][h]), int(hit["first_off"][h])
-                    if res[int(off[fp]) + fo:int(off[fp]) + fo + len(want)].tobytes() == want and \
-                            pid in hit["prot_ids"][plo[h]:plo[h + 1]]:
-                        ok[k2] = 1
-                        break
-                if ok[k2]:
+            # COLLECTIVE: every rank fetches its (possibly empty) hit range; base peptides held by other
+            # ranks are resolved by their owners
+            hit = fetch_resolved(g, info, int(b0), int(min(c0, 1 << 16)))
+            plo = hit["prot_list_off"].astype(np.int64)
+            for h in np.nonzero((hit["len"] == len(want)) & (hit["modpat"] == e["modpat"][i2]))[0]:
+                fp, fo = int(hit["first_prot"][h]), int(hit["first_off"][h])
+                if res[int(off[fp]) + fo:int(off[fp]) + fo + len(want)].tobytes() == want and \
+                        pid in hit["prot_ids"][plo[h]:plo[h + 1]]:
+                    ok[k2] = 1
                     break
         found = np.concatenate([found, ok])
         checked += len(sel)

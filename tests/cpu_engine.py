@@ -91,48 +91,40 @@ class OracleShardEngine(ShardEngine):
                       e["first_prot"].view(np.int32), e["len"].view(np.int16),
                       np.diff(e["prot_list_off"].astype(np.int64)).astype(np.int32), e["prot_ids"].view(np.int32)]
 
-    def export_unique(self):
-        return [torch.from_numpy(np.ascontiguousarray(a)) for a in self.local]
+    def n_unique(self):
+        return len(self.local[0])
 
-    def import_unique(self, rank_unique, rank_plist, tables):
-        t = [x.numpy() for x in tables]
-        self.u_mass = t[0].view(np.float64)
-        self.u_gpos, self.u_prot, self.u_len = t[1].view(np.uint32), t[2].view(np.uint32), t[3].view(np.uint16)
-        self.u_plo = np.concatenate(([0], np.cumsum(t[4].astype(np.int64))))
-        self.plist = t[5].view(np.uint32)
-        self.slice = (int(sum(rank_unique[:self.rank])), int(sum(rank_unique[:self.rank + 1])))
+    def export_unique(self):
+        return [torch.from_numpy(np.ascontiguousarray(self.local[1])), torch.from_numpy(np.ascontiguousarray(self.local[3]))]
+
+    def import_unique(self, rank_unique, tables):
+        # all a rank learns about foreign peptides: where their residues are
+        self.g_gpos, self.g_len = tables[0].numpy().view(np.uint32), tables[1].numpy().view(np.uint16)
+        self.uoff = int(sum(rank_unique[:self.rank]))
+        assert int(rank_unique[self.rank]) == self.n_unique()
 
     def finish(self):
-        a, b = self.slice
-        self.e_mass = self.u_mass[a:b]
-        self.e_base = np.arange(a, b, dtype=np.uint32)
-        self.e_pat = np.zeros(b - a, np.uint32)
+        self.e_mass = self.local[0].view(np.float64)
+        self.e_base = None  # entry i = own unique peptide i
+        self.e_pat = np.zeros(self.n_unique(), np.uint32)
 
     def _variants(self, u):
-        pr = int(self.u_prot[u])
-        off = int(self.u_gpos[u]) - int(self.pstart[pr])
-        return pyref.expand_set(self.params, self._seq(pr, off, self.u_len[u]), float(self.u_mass[u]))
+        pr = int(self.local[2].view(np.uint32)[u])
+        off = int(self.local[1].view(np.uint32)[u]) - int(self.pstart[pr])
+        return pyref.expand_set(self.params, self._seq(pr, off, self.local[3].view(np.uint16)[u]),
+                                float(self.local[0].view(np.float64)[u]))
 
     def own_tiles(self):
-        a, b = self.slice
-        t0, t1 = (a + 255) // 256, (b + 255) // 256
-        return t0, t1 - t0
-
-    def mod_tile_counts(self):
-        a, b = self.slice
-        t0, t1 = (a + 255) // 256, (b + 255) // 256
-        U = len(self.u_mass)
-        counts = [sum(len(self._variants(u)) for u in range(t * 256, min(U, t * 256 + 256))) for t in range(t0, t1)]
-        return t0, torch.tensor(counts, dtype=torch.int32)
+        return 0, (self.n_unique() + 255) // 256
 
     def expand(self, tile_begin, n_tiles):
-        U = len(self.u_mass)
+        U = self.n_unique()
         keys, pay = [], []
         for u in range(tile_begin * 256, min(U, (tile_begin + n_tiles) * 256)):
             for m, pos in self._variants(u):
                 pat = sum((q + 1) << (8 * k) for k, q in enumerate(pos))
                 keys.append(int(np.float64(m).view(np.uint64)) - self.base_bits)
-                pay.append((u << 32) | pat)
+                pay.append(((self.uoff + u) << 32) | pat)  # peptides travel under their global id
         self.var = [np.array(keys, dtype=np.uint64), np.array(pay, dtype=np.uint64)]
         return len(keys)
 
@@ -143,12 +135,21 @@ class OracleShardEngine(ShardEngine):
         self.e_base = (payload[order] >> np.uint64(32)).astype(np.uint32)
         self.e_pat = (payload[order] & np.uint64(0xFFFFFFFF)).astype(np.uint32)
 
-    # ---- what a query sees
+    # ---- what a query sees (COLLECTIVE: base peptides of other ranks are looked up in their tables)
     def entries(self):
-        b = self.e_base.astype(np.int64)
-        return {"mass": self.e_mass, "first_prot": self.u_prot[b], "len": self.u_len[b], "modpat": self.e_pat,
-                "first_off": self._prot_off(self.u_gpos[b], self.u_prot[b]),
-                "plist": [tuple(self.plist[self.u_plo[x]:self.u_plo[x + 1]].tolist()) for x in b]}
+        import torch.distributed as dist
+        tabs = [None] * self.world
+        dist.all_gather_object(tabs, [np.asarray(a) for a in self.local])
+        u_gpos = np.concatenate([t[1].view(np.uint32) for t in tabs])
+        u_prot = np.concatenate([t[2].view(np.uint32) for t in tabs])
+        u_len = np.concatenate([t[3].view(np.uint16) for t in tabs])
+        u_plo = np.concatenate(([0], np.cumsum(np.concatenate([t[4].astype(np.int64) for t in tabs]))))
+        plist = np.concatenate([t[5].view(np.uint32) for t in tabs])
+        my_off = sum(len(t[0]) for t in tabs[:self.rank])
+        b = (np.arange(len(self.e_mass)) + my_off) if self.e_base is None else self.e_base.astype(np.int64)
+        return {"mass": self.e_mass, "first_prot": u_prot[b], "len": u_len[b], "modpat": self.e_pat,
+                "first_off": self._prot_off(u_gpos[b], u_prot[b]),
+                "plist": [tuple(plist[u_plo[x]:u_plo[x + 1]].tolist()) for x in b]}
 
     def query(self, lo, hi):
         b = np.searchsorted(self.e_mass, lo, side="left")

@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 
 import dbindex_b200 as dbi  # noqa: E402
 from dbindex_b200 import synth  # noqa: E402
-from dbindex_b200.multigpu import build_sharded, route_queries  # noqa: E402
+from dbindex_b200.multigpu import build_sharded, fetch_resolved, route_queries  # noqa: E402
 from oracle.oracle_py import Oracle  # noqa: E402
 from tests.cpu_engine import OracleShardEngine  # noqa: E402
 from tests.util import PARAM_SETS, bits  # noqa: E402
@@ -21,12 +21,13 @@ from tests.util import PARAM_SETS, bits  # noqa: E402
 class GpuEntries:
     """Adapter giving the GPU handle the two calls the checks below use."""
 
-    def __init__(self, g, deflines=None):
+    def __init__(self, g, info):
         self.g = g
+        self.info = info
 
     def entries(self):
         n = self.g.stats()["n_entries"]
-        f = self.g.fetch(0, n)
+        f = fetch_resolved(self.g, self.info, 0, n)  # collective: remote base peptides are resolved by their owners
         plo = f["prot_list_off"].astype(np.int64)
         f["plist"] = [tuple(f["prot_ids"][plo[i]:plo[i + 1]].tolist()) for i in range(n)]
         return f
@@ -63,7 +64,7 @@ def main():
         g = dbi.GpuIndex(params)
         g.add_proteins(res, off)
         info = build_sharded(GpuShardEngine(g, torch.device("cuda", local)))
-        eng = GpuEntries(g)
+        eng = GpuEntries(g, info)
     else:
         eng = OracleShardEngine(params, res, off)
         info = build_sharded(eng)

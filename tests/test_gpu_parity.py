@@ -344,11 +344,14 @@ def _visible_gpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("name", ["cfg1_tryptic", "cfg2_mods", "cfg3_semi"])
+@pytest.mark.parametrize("name", ["cfg1_tryptic", "cfg2_mods", "cfg3_semi", "cfg2_mods:no_mask_table",
+                                  "many_classes"])
 def test_multi_gpu_sharded_build_matches_oracle(name, tmp_path):
     """SURVEY.md 8e / invariant 11: the N-GPU index (range-sharded digest, NCCL all-to-all by mass
-    slice, replicated unique tables, variant re-exchange) equals the oracle's, slice by slice, and
-    routed queries sum to the global answer.  Runs with every visible GPU (needs >= 2)."""
+    slice, group exchange by variant mass, base peptides resolved by their owners) equals the
+    oracle's, slice by slice, and routed queries sum to the global answer.  Runs with every visible
+    GPU (needs >= 2).  ":no_mask_table" forces the expansion to rebuild site masks per group (the
+    path taken when a mask table over all unique peptides would not fit)."""
     import subprocess
     import sys
     n = _visible_gpus()
@@ -357,8 +360,12 @@ def test_multi_gpu_sharded_build_matches_oracle(name, tmp_path):
     n = 2 if n < 4 else (4 if n < 8 else 8)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = tmp_path / "r.json"
+    env = dict(os.environ)
+    name, _, variant = name.partition(":")
+    if variant == "no_mask_table":
+        env["DBI_MG_NO_MASK_TABLE"] = "1"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
-           "127.0.0.1", "--master-port", str(29800 + len(name)), os.path.join(root, "tests", "dist_worker.py"), name,
-           str(out), "gpu", "1500"]
-    p = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=900)
+           "127.0.0.1", "--master-port", str(29800 + len(name) + len(variant)), os.path.join(root, "tests", "dist_worker.py"),
+           name, str(out), "gpu", "1500"]
+    p = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=900, env=env)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
