@@ -158,13 +158,16 @@ struct dbi_handle {
   std::mutex mu;
   DevArena arena;  // declared before every DevBuf of the handle: destroyed after them
 
-  // host copy of the proteins (ProteinCache)
+  // The residues go straight from the caller's buffer to the device (dbi_add_proteins); the host
+  // keeps the offsets, and a copy of the residues (ProteinCache) only once dbi_get_protein asks.
   std::vector<uint8_t> h_raw;
+  bool h_raw_valid = false;
   std::vector<uint64_t> h_off{0};
+  uint64_t n_res = 0;  // residues added so far = bytes valid in d_raw
 
   // device-resident input
   DevBuf d_raw, d_off;
-  uint64_t up_res = 0, up_prot = UINT64_MAX;
+  uint64_t up_prot = UINT64_MAX;
 
   // index
   bool built = false;
@@ -432,17 +435,14 @@ void upload_tables(dbi_handle* h) {
   DBI_CUDA(cudaStreamSynchronize(h->stream));  // `t` is on this stack frame
 }
 
-// H2D of the raw residues + offsets (idempotent).
+// H2D of the protein offsets (idempotent); the residues are already on the device.
 void ensure_uploaded(dbi_handle* h) {
-  const uint64_t n_res = h->h_raw.size();
   const uint64_t n_prot = h->h_off.size() - 1;
-  if (h->up_prot == n_prot && h->up_res == n_res) return;
-  h->d_raw.alloc(n_res, h->arena);
+  if (h->up_prot == n_prot) return;
+  if (!h->d_raw.p) h->d_raw.alloc(16, h->arena);
   h->d_off.alloc((n_prot + 1) * 8, h->arena);
-  if (n_res) DBI_CUDA(cudaMemcpyAsync(h->d_raw.p, h->h_raw.data(), n_res, cudaMemcpyHostToDevice, h->stream));
   DBI_CUDA(cudaMemcpyAsync(h->d_off.p, h->h_off.data(), (n_prot + 1) * 8, cudaMemcpyHostToDevice, h->stream));
   h->up_prot = n_prot;
-  h->up_res = n_res;
 }
 
 int check_err_bits(uint32_t e) {
@@ -464,7 +464,7 @@ int check_err_bits(uint32_t e) {
 // K1: padded residue buffer + protein starts.
 void pack_residues(dbi_handle* h) {
   Stage sg(h, DBI_STAGE_PACK);
-  const uint64_t n_res = h->h_raw.size();
+  const uint64_t n_res = h->n_res;
   const uint32_t n_prot = (uint32_t)(h->h_off.size() - 1);
   const uint64_t res_end = n_res + n_prot + 1;
   const uint64_t padded = (res_end + 64 + 15) & ~15ull;
@@ -1014,15 +1014,29 @@ int dbi_add_proteins(dbi_handle* h, const uint8_t* residues, const uint64_t* off
       return DBI_EINVAL;
     }
   const uint64_t add = offsets[n] - offsets[0];
-  const uint64_t total_res = h->h_raw.size() + add;
+  const uint64_t total_res = h->n_res + add;
   const uint64_t total_prot = h->h_off.size() - 1 + n;
   if (total_res + total_prot + 1 + 4096 >= (1ull << 32) || total_prot >= (1ull << 31)) {
     set_error("more than 2^32 residues on one GPU: shard the FASTA across handles");
     return DBI_ERANGE;
   }
-  const uint64_t base = h->h_raw.size();
-  h->h_raw.insert(h->h_raw.end(), residues + offsets[0], residues + offsets[n]);
+  const uint64_t base = h->n_res;
+  cudaStream_t s = h->stream;
+  if (total_res > h->d_raw.bytes) {  // grow geometrically; the residues added so far move over
+    DevBuf bigger;
+    bigger.alloc(std::max<uint64_t>(total_res, h->d_raw.bytes + h->d_raw.bytes / 2), h->arena);
+    if (base) DBI_CUDA(cudaMemcpyAsync(bigger.p, h->d_raw.p, base, cudaMemcpyDeviceToDevice, s));
+    h->d_raw.swap(bigger);
+  }
+  // DMA straight from the caller's buffer (pinned memory makes it asynchronous) while the host
+  // appends the offsets; the buffer is the caller's again when this call returns
+  if (add)
+    DBI_CUDA(cudaMemcpyAsync((uint8_t*)h->d_raw.p + base, residues + offsets[0], add, cudaMemcpyHostToDevice, s));
+  h->h_off.reserve(h->h_off.size() + n);
   for (uint32_t i = 1; i <= n; ++i) h->h_off.push_back(base + (offsets[i] - offsets[0]));
+  if (h->h_raw_valid) h->h_raw.insert(h->h_raw.end(), residues + offsets[0], residues + offsets[n]);
+  h->n_res = total_res;
+  DBI_CUDA(cudaStreamSynchronize(s));
   h->st.n_proteins = total_prot;
   h->st.n_residues = total_res;
   return DBI_OK;
@@ -1311,6 +1325,17 @@ int dbi_get_protein(dbi_handle* h, uint32_t id, const uint8_t** residues, uint64
   if ((uint64_t)id + 1 >= h->h_off.size()) {
     set_error("protein id %u out of range", id);
     return DBI_EINVAL;
+  }
+  if (!h->h_raw_valid) {  // first use: bring the residues back once (ProteinCache on demand)
+    try {
+      DBI_CUDA(cudaSetDevice(h->device));
+      h->h_raw.resize(h->n_res);
+      if (h->n_res) DBI_CUDA(cudaMemcpyAsync(h->h_raw.data(), h->d_raw.p, h->n_res, cudaMemcpyDeviceToHost, h->stream));
+      DBI_CUDA(cudaStreamSynchronize(h->stream));
+      h->h_raw_valid = true;
+    } catch (const CudaError& e) {
+      return fail_cuda(e);
+    }
   }
   *residues = h->h_raw.data() + h->h_off[id];
   *len = h->h_off[id + 1] - h->h_off[id];
