@@ -103,7 +103,7 @@ struct RsSmem {
 // SPLIT (last pass of the variant sort): keys leave as key + key_add (the mass bits), the
 // 64-bit values as two u32 arrays (vout_hi = base peptide, vout_lo = mod pattern).
 template <typename K, typename V, bool SPLIT>
-__global__ void __launch_bounds__(RS_THREADS, sizeof(K) == 8 ? 3 : 4)
+__global__ void __launch_bounds__(RS_THREADS, 4)
     rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const V* __restrict__ vin,
                        V* __restrict__ vout, uint64_t n, int shift, uint32_t mask,
                        const unsigned long long* __restrict__ digit_off, unsigned long long* lookback,
