@@ -12,16 +12,14 @@
 //   K6g grp_emit   : {key = mass bits - base, payload = peptide << 32 | sequence << 27 | count}
 //   (K7 sorts the records, K3 scans the counts into entry offsets)
 //   K6t grp_tile_first : first group of every tile of kExpTile consecutive ENTRIES
-//   K6x grp_expand : one thread per ENTRY: un-rank the entry inside its group with the site
-//                    masks and write (mass, peptide, pattern) -- coalesced stores, no divergent
-//                    per-group enumeration
+//   K6x grp_expand_tab : one thread per ENTRY: un-rank the entry inside its group in constant
+//                    time (product-set blocks, per-group block tables in shared memory) and write
+//                    (mass, peptide, pattern) -- coalesced stores, no divergent per-group enumeration
 //   K6l grp_expand_long : groups of peptides longer than 64 residues (no masks): one warp each
 //
 // HBM-bound byte/integer work; no tensor cores.  Algorithmic bytes: K5m 14 + len per peptide read,
 // 8 C written; K5g/K6g 22 + 8 C per peptide, 16 per group written; K6x 24 per group + 8 C per
 // group (random 32-B sectors) read, 16 per entry written.
-#include <cstdlib>
-
 #include "mods_common.cuh"
 
 namespace dbi {
@@ -271,17 +269,6 @@ __global__ void __launch_bounds__(MD_THREADS)
 }
 
 // ---- K6x ------------------------------------------------------------------------------
-// An occurrence of a class sequence of length k is the tuple of its site positions, kept as the
-// bytes of one register: byte j = position of the j-th chosen site.  Pattern = positions + 1.
-__device__ __forceinline__ uint64_t mask_at(int l, uint64_t c0, uint64_t c1, uint64_t c2, uint64_t c3) {
-  return l == 0 ? c0 : (l == 1 ? c1 : (l == 2 ? c2 : c3));
-}
-__device__ __forceinline__ int pos_at(uint32_t P, int l) { return (int)((P >> (8 * l)) & 0xffu); }
-__device__ __forceinline__ uint32_t pos_set(uint32_t P, int l, int v) {
-  return (P & ~(0xffu << (8 * l))) | ((uint32_t)v << (8 * l));
-}
-__device__ __forceinline__ uint32_t occ_pattern(uint32_t P, int k) { return (P + 0x01010101u) & low_bytes_mask(k); }
-
 // position of the (r+1)-th set bit of m (r < popc(m)): binary search on popcounts, constant cost
 __device__ __forceinline__ int select_bit(uint64_t m, uint32_t r) {
   int pos = 0;
@@ -300,292 +287,9 @@ __device__ __forceinline__ int select_bit(uint64_t m, uint32_t r) {
   return pos;
 }
 
-// Walker over the occurrences of one class sequence in lexicographic site order.  The levels are
-// aligned to the END: D is the last chosen site, C the one before, ... (unused leading levels stay
-// zero).  Each register holds the remaining candidates of its level with the CURRENT site as its
-// lowest set bit, so the common step (next candidate of the last level) is two instructions.
-// cA..cD are the site masks of the classes in the same alignment.
-__device__ __forceinline__ uint64_t above_low(uint64_t x) { return x ? above(__ffsll((long long)x) - 1) : ~0ull; }
-
-struct OccWalker {
-  uint64_t cA, cB, cC, cD;
-  uint64_t A, B, C, D;
-  int shift;  // 8 * (4 - k)
-  // masks of the sequence's classes in site order c0..c3 (k of them)
-  __device__ __forceinline__ void load(int k, uint64_t c0, uint64_t c1, uint64_t c2, uint64_t c3) {
-    shift = 8 * (4 - k);
-    cD = k == 1 ? c0 : (k == 2 ? c1 : (k == 3 ? c2 : c3));
-    cC = k == 2 ? c0 : (k == 3 ? c1 : (k == 4 ? c2 : 0ull));
-    cB = k == 3 ? c0 : (k == 4 ? c1 : 0ull);
-    cA = k == 4 ? c0 : 0ull;
-  }
-  // leftmost embedding = first occurrence
-  __device__ __forceinline__ void first() {
-    A = cA;
-    B = cB & above_low(A);
-    C = cC & above_low(B);
-    D = cD & above_low(C);
-  }
-  // occurrence with site positions P (byte j = position of the j-th site, sequence order)
-  __device__ __forceinline__ void seek(uint32_t P, int k) {
-    const uint32_t Q = P << shift;  // byte 3 = last site
-    A = k > 3 ? (cA & (~0ull << (Q & 0xffu))) : 0ull;
-    B = k > 2 ? (cB & (~0ull << ((Q >> 8) & 0xffu))) : 0ull;
-    C = k > 1 ? (cC & (~0ull << ((Q >> 16) & 0xffu))) : 0ull;
-    D = cD & (~0ull << ((Q >> 24) & 0xffu));
-  }
-  __device__ __forceinline__ uint32_t pattern() const {
-    const uint32_t full = (uint32_t)__ffsll((long long)A) | ((uint32_t)__ffsll((long long)B) << 8) |
-                          ((uint32_t)__ffsll((long long)C) << 16) | ((uint32_t)__ffsll((long long)D) << 24);
-    return full >> shift;
-  }
-  // next occurrence; a site without completion ends its level (no later site of the level has one)
-  __device__ __forceinline__ void next() {
-    D &= D - 1;
-    if (D) return;
-    C &= C - 1;
-    if (C) {
-      D = cD & above_low(C);
-      if (D) return;
-    }
-    B &= B - 1;
-    if (B) {
-      C = cC & above_low(B);
-      if (C) {
-        D = cD & above_low(C);
-        if (D) return;
-      }
-    }
-    A &= A - 1;
-    if (A) {
-      B = cB & above_low(A);
-      C = B ? (cC & above_low(B)) : 0ull;
-      D = C ? (cD & above_low(C)) : 0ull;
-    }
-  }
-};
-
-// number of ways to pick `nrem` further sites above position i, from the masks ma, mb, mc in order
-__device__ __forceinline__ uint32_t count_tail(int nrem, int i, uint64_t ma, uint64_t mb, uint64_t mc) {
-  if (nrem == 0) return 1u;
-  uint64_t a = ma & above(i);
-  if (nrem == 1) return (uint32_t)__popcll(a);
-  uint32_t c = 0;
-  for (; a; a &= a - 1) {
-    const int ia = __ffsll((long long)a) - 1;
-    uint64_t b = mb & above(ia);
-    if (nrem == 2) {
-      c += (uint32_t)__popcll(b);
-    } else {
-      for (; b; b &= b - 1) c += (uint32_t)__popcll(mc & above(__ffsll((long long)b) - 1));
-    }
-  }
-  return c;
-}
-
-// The r-th occurrence (0-based, lexicographic by sites) of a class sequence of length k whose j-th
-// class has the site mask c_j.  Linear in the number of sites for k <= 3.
-__device__ __forceinline__ uint32_t unrank_occurrence(uint32_t r, int k, uint64_t c0, uint64_t c1, uint64_t c2,
-                                                      uint64_t c3) {
-  uint32_t P = 0;
-  int prev = -1;
-  int l = 0;
-  if (k == 4) {  // first site of four: plain nested counting (K = 4 is rare)
-    uint64_t m = c0;
-    int i = 0;
-    for (; m; m &= m - 1) {
-      i = __ffsll((long long)m) - 1;
-      const uint32_t w = count_tail(3, i, c1, c2, c3);
-      if (r < w) break;
-      r -= w;
-    }
-    P = (uint32_t)i;
-    prev = i;
-    l = 1;
-  }
-  if (k - l == 3) {
-    // first site of three: W = occurrences whose first site is the current candidate; walking the
-    // candidates upward only ever removes second sites from below, so W is kept incrementally
-    const uint64_t a0 = mask_at(l, c0, c1, c2, c3) & (prev < 0 ? ~0ull : above(prev));
-    const uint64_t a1 = mask_at(l + 1, c0, c1, c2, c3);
-    const uint64_t a2 = mask_at(l + 2, c0, c1, c2, c3);
-    uint64_t rem1 = prev < 0 ? a1 : (a1 & above(prev));
-    uint32_t W = 0;
-    for (uint64_t q = rem1; q; q &= q - 1) W += (uint32_t)__popcll(a2 & above(__ffsll((long long)q) - 1));
-    int i = 0;
-    for (uint64_t m = a0; m; m &= m - 1) {
-      i = __ffsll((long long)m) - 1;
-      for (uint64_t drop = rem1 & ~above(i); drop; drop &= drop - 1)
-        W -= (uint32_t)__popcll(a2 & above(__ffsll((long long)drop) - 1));
-      rem1 &= above(i);
-      if (r < W) break;
-      r -= W;
-    }
-    P |= (uint32_t)i << (8 * l);
-    prev = i;
-    ++l;
-  }
-  if (k - l == 2) {
-    const uint64_t a1 = mask_at(l + 1, c0, c1, c2, c3);
-    int i = 0;
-    for (uint64_t m = mask_at(l, c0, c1, c2, c3) & (prev < 0 ? ~0ull : above(prev)); m; m &= m - 1) {
-      i = __ffsll((long long)m) - 1;
-      const uint32_t w = (uint32_t)__popcll(a1 & above(i));
-      if (r < w) break;
-      r -= w;
-    }
-    P |= (uint32_t)i << (8 * l);
-    prev = i;
-    ++l;
-  }
-  // last site: plain select
-  const uint64_t cand = mask_at(l, c0, c1, c2, c3) & (prev < 0 ? ~0ull : above(prev));
-  return P | ((uint32_t)select_bit(cand, r) << (8 * l));
-}
-
-constexpr int EX_THREADS = 256;
-constexpr int EX_PER = kExpTile / EX_THREADS;  // consecutive entries per thread
-constexpr int EX_GMAX = kExpTile + 1;          // groups that can overlap one tile (every group has >= 1 entry)
+constexpr int EX_GMAX = kExpTile + 1;  // groups that can overlap one tile (every group has >= 1 entry)
 constexpr uint8_t kLongGroup = 0xff;
-static_assert(EX_PER == 4 || EX_PER == 8, "the pattern staging is skewed for a stride of 4 or 8 words");
 
-// the site masks cm[n_masks][EX_GMAX] (n_masks = max mods per peptide) follow this struct
-struct ExpSmem {
-  double mass[EX_GMAX];
-  int32_t off[EX_GMAX + 1];  // first entry of the group relative to the tile start (negative: began earlier)
-  uint32_t base[EX_GMAX];
-  uint32_t pat[kExpTile + kExpTile / 32];
-  uint16_t head[kExpTile];   // local group of every entry (after the max-scan)
-  uint8_t k[EX_GMAX];
-  uint32_t scratch[EX_THREADS / 32 + 1];
-};
-
-__global__ void __launch_bounds__(EX_THREADS)
-    grp_expand_kernel(DigestCfg cfg, const uint64_t* __restrict__ cmask, const uint64_t* __restrict__ skey,
-                      const uint64_t* __restrict__ spay, const uint64_t* __restrict__ eoff,
-                      const uint32_t* __restrict__ tile_first, uint64_t n_entries, uint64_t base_bits,
-                      double* __restrict__ e_mass, uint32_t* __restrict__ e_base, uint32_t* __restrict__ e_pat,
-                      uint32_t* __restrict__ long_list, uint32_t* __restrict__ long_count, uint32_t long_cap,
-                      uint32_t* err) {
-  extern __shared__ __align__(16) uint8_t ex_raw[];
-  ExpSmem& s = *reinterpret_cast<ExpSmem*>(ex_raw);
-  uint64_t* const s_cm = reinterpret_cast<uint64_t*>(ex_raw + sizeof(ExpSmem));  // [max_mods][EX_GMAX]
-  const int K = cfg.max_mods;
-  auto cm_of = [&](int l, uint32_t j) -> uint64_t { return l < K ? s_cm[l * EX_GMAX + j] : 0ull; };
-  const int C = cfg.n_classes;
-  const int t = threadIdx.x;
-  const uint64_t tile = blockIdx.x;
-  const uint64_t e0 = tile * (uint64_t)kExpTile;
-  const uint32_t tile_n = (uint32_t)min((uint64_t)kExpTile, n_entries - e0);
-  const uint32_t g0 = tile_first[tile];
-  const uint32_t ngrp = tile_first[tile + 1] - g0 + 1;  // <= kExpTile + 1; the last one may start past the tile
-
-  for (int i = t; i < kExpTile; i += EX_THREADS) s.head[i] = 0;
-  __syncthreads();
-  // stage the groups of this tile: offsets, masses, peptides, the site masks of their classes
-  for (uint32_t j = t; j <= ngrp; j += EX_THREADS) {
-    const uint64_t g = (uint64_t)g0 + j;
-    const int64_t rel = (int64_t)eoff[g] - (int64_t)e0;  // eoff has n_groups + 1 elements
-    s.off[j] = (int32_t)rel;  // |rel| < 2^27 + kExpTile: a group holds at most 2^27 entries
-    if (j == ngrp) break;
-    const uint64_t pay = spay[g];
-    const uint32_t b = (uint32_t)(pay >> 32);
-    const uint32_t seq = ((uint32_t)pay >> kGrpCntBits) & 31u;
-    uint32_t pk;
-    int k = pack_seq(seq, C, &pk);
-    s.mass[j] = __longlong_as_double((long long)(skey[g] + base_bits));
-    s.base[j] = b;
-    if (k > 0) {
-      const uint64_t* cm = cmask + (uint64_t)b * (uint64_t)C;
-      const uint64_t c0 = cm[seq_class_at(pk, 0)];
-      s_cm[j] = c0;
-      for (int l = 1; l < K; ++l) s_cm[l * EX_GMAX + j] = l < k ? cm[seq_class_at(pk, l)] : 0ull;
-      if (c0 == 0) {  // a peptide longer than 64 residues: K6l writes this group
-        k = kLongGroup;
-        if (rel >= 0 && rel < (int64_t)kExpTile) {  // the tile where the group starts reports it
-          const uint32_t slot = atomicAdd(long_count, 1u);
-          if (slot < long_cap) long_list[slot] = (uint32_t)g; else atomicOr(err, kErrModPos);
-        }
-      }
-    }
-    s.k[j] = (uint8_t)k;
-    if (rel > 0 && rel < (int64_t)kExpTile) s.head[rel] = (uint16_t)j;
-  }
-  __syncthreads();
-  // inclusive max-scan of the heads: entry -> local group
-  {
-    uint32_t loc[EX_PER];
-    uint32_t run = 0;
-#pragma unroll
-    for (int i = 0; i < EX_PER; ++i) {
-      run = max(run, (uint32_t)s.head[t * EX_PER + i]);
-      loc[i] = run;
-    }
-    uint32_t inc = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
-      if ((int)lane_id() >= o) inc = max(inc, n);
-    }
-    if (lane_id() == 31) s.scratch[t >> 5] = inc;
-    __syncthreads();
-    uint32_t carry = 0;
-    for (int w = 0; w < (t >> 5); ++w) carry = max(carry, s.scratch[w]);
-    const uint32_t prev = __shfl_up_sync(0xffffffffu, inc, 1);
-    if (lane_id() > 0) carry = max(carry, prev);
-#pragma unroll
-    for (int i = 0; i < EX_PER; ++i) s.head[t * EX_PER + i] = (uint16_t)max(loc[i], carry);
-  }
-  __syncthreads();
-  // every thread walks EX_PER consecutive entries: un-rank the first one inside its group, then
-  // step from occurrence to occurrence (and from group to group)
-  {
-    const uint32_t i0 = (uint32_t)t * EX_PER;
-    if (i0 < tile_n) {
-      uint32_t j = s.head[i0];
-      uint32_t r = (uint32_t)((int32_t)i0 - s.off[j]);
-      int k = s.k[j];
-      uint32_t cnt = (uint32_t)(s.off[j + 1] - s.off[j]);
-      OccWalker wk;
-      bool sites = k > 0 && k != kLongGroup;
-      if (sites) {
-        const uint64_t c0 = cm_of(0, j), c1 = cm_of(1, j), c2 = cm_of(2, j), c3 = cm_of(3, j);
-        wk.load(k, c0, c1, c2, c3);
-        if (r == 0) wk.first(); else wk.seek(unrank_occurrence(r, k, c0, c1, c2, c3), k);
-      }
-      const uint32_t i1 = min(i0 + EX_PER, tile_n);
-      for (uint32_t i = i0; i < i1; ++i) {
-        s.pat[i + (i >> 5)] = sites ? wk.pattern() : 0u;
-        if (i + 1 == i1) break;
-        if (++r == cnt) {
-          ++j;  // j < ngrp: entries remain
-          r = 0;
-          k = s.k[j];
-          cnt = (uint32_t)(s.off[j + 1] - s.off[j]);
-          sites = k > 0 && k != kLongGroup;
-          if (sites) {
-            wk.load(k, cm_of(0, j), cm_of(1, j), cm_of(2, j), cm_of(3, j));
-            wk.first();
-          }
-        } else if (sites) {
-          wk.next();
-        }
-      }
-    }
-  }
-  __syncthreads();
-  // coalesced write-out: consecutive threads = consecutive entries
-  for (uint32_t i = t; i < tile_n; i += EX_THREADS) {
-    const uint32_t j = s.head[i];
-    if (s.k[j] == kLongGroup) continue;
-    const uint64_t e = e0 + i;
-    e_mass[e] = s.mass[j];
-    e_base[e] = s.base[j];
-    e_pat[e] = s.pat[i + (i >> 5)];
-  }
-}
-
-// ---- K6x, table variant ------------------------------------------------------------------
 // One thread per ENTRY with constant-time un-ranking.  The entries of a group are ordered by
 // BLOCKS that are product sets, so that a rank splits by one division:
 //   k = 1: the sites of the class, ascending;
@@ -971,24 +675,14 @@ void launch_grp_expand(const uint8_t* d_res, const DevTables* d_tb, const Digest
   if (n_groups == 0 || n_entries == 0) return;
   const uint64_t n_tiles = (n_entries + kExpTile - 1) / kExpTile;
   static const bool attr_set = [] {
-    cudaFuncSetAttribute(grp_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(sizeof(ExpSmem) + (size_t)DBI_MAX_MODS_PER_PEP * EX_GMAX * 8));
     cudaFuncSetAttribute(grp_expand_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(sizeof(ExpTabSmem) + (size_t)DBI_MAX_MODS_PER_PEP * EX_GMAX * 8));
     return true;
   }();
   (void)attr_set;
-  static const bool use_walker = std::getenv("DBI_EXPAND_WALKER") != nullptr;  // diagnostic: the walker variant
-  if (use_walker && cmask) {
-    const size_t smem = sizeof(ExpSmem) + (size_t)cfg.max_mods * EX_GMAX * 8;
-    DBI_LAUNCH(grp_expand_kernel, (unsigned)n_tiles, EX_THREADS, smem, s, cfg, cmask, skey, spay, eoff, tile_first,
-               n_entries, base_bits, e_mass, e_base, e_pat, long_list, long_count, long_cap, d_err);
-  } else {
-    const size_t smem = sizeof(ExpTabSmem) + (size_t)cfg.max_mods * EX_GMAX * 8;
-    DBI_LAUNCH(grp_expand_tab_kernel, (unsigned)n_tiles, ET_THREADS, smem, s, cfg, cmask, d_res, d_tb, u_gpos, u_len,
-               skey, spay, eoff,
-               tile_first, n_entries, base_bits, e_mass, e_base, e_pat, long_list, long_count, long_cap, d_err);
-  }
+  const size_t smem = sizeof(ExpTabSmem) + (size_t)cfg.max_mods * EX_GMAX * 8;
+  DBI_LAUNCH(grp_expand_tab_kernel, (unsigned)n_tiles, ET_THREADS, smem, s, cfg, cmask, d_res, d_tb, u_gpos, u_len, skey,
+             spay, eoff, tile_first, n_entries, base_bits, e_mass, e_base, e_pat, long_list, long_count, long_cap, d_err);
   if (long_cap > 0) {
     unsigned grid = (long_cap + MD_WARPS - 1) / MD_WARPS;
     if (grid > (unsigned)kNumSMsB200 * 4) grid = (unsigned)kNumSMsB200 * 4;
