@@ -133,6 +133,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "dbi_query_device": (C.c_int, [vp, vp, vp, C.c_uint64, vp, vp]),
         "dbi_fetch": (C.c_int, [vp, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp, vp, vp, C.c_uint64, u64p]),
         "dbi_get_protein": (C.c_int, [vp, C.c_uint32, C.POINTER(vp), u64p]),
+        "dbi_fasta_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(vp)]),
+        "dbi_fasta_counts": (C.c_int, [vp, u32p, u64p, u64p]),
+        "dbi_fasta_read": (C.c_int, [vp, vp, vp, vp, vp]),
+        "dbi_fasta_close": (None, [vp]),
         "dbi_calculate_mass": (C.c_int, [vp, C.c_char_p, C.c_uint64, dp]),
         "dbi_entry_keys": (C.c_int, [vp, vp, C.c_uint64, u64p]),
         "dbi_debug_emitted": (C.c_int, [vp, C.c_uint64, vp, vp, vp, vp, u64p]),
@@ -167,6 +171,7 @@ ABI_SYMBOLS = [
     "dbi_entry_keys", "dbi_debug_emitted", "dbi_build_from_records", "dbi_debug_radix_sort", "dbi_destroy",
     "dbi_abi_sizes", "dbi_release_cached_memory",
     "dbi_last_error", "dbi_kernel_launches",
+    "dbi_fasta_open", "dbi_fasta_counts", "dbi_fasta_read", "dbi_fasta_close",
     # multi-GPU staged build, bound in dbindex_b200/multigpu.py
     "dbi_mg_begin", "dbi_mg_digest", "dbi_mg_histogram", "dbi_mg_partition", "dbi_mg_pack_send",
     "dbi_mg_index_base", "dbi_mg_unique_counts", "dbi_mg_export_unique", "dbi_mg_import_unique", "dbi_mg_finish",
@@ -201,6 +206,32 @@ def default_params(mono: bool = True, **overrides) -> DbiParams:
 
 def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def parse_fasta(path: str, threads: int = 0):
+    """FASTA file -> (deflines list[str], residues uint8[R], offsets uint64[n + 1]) through the native
+    multi-threaded parser (dbi_fasta_*, csrc/fasta.cpp): the packed layout `add_proteins` takes."""
+    lib = load_library()
+    f = C.c_void_p()
+    rc = lib.dbi_fasta_open(os.fsencode(path), int(threads), C.byref(f))
+    if rc != 0:
+        raise DbiError(rc, (lib.dbi_last_error() or b"").decode(errors="replace"))
+    try:
+        n, r, d = C.c_uint32(), C.c_uint64(), C.c_uint64()
+        lib.dbi_fasta_counts(f, C.byref(n), C.byref(r), C.byref(d))
+        residues = np.empty(r.value, dtype=np.uint8)
+        offsets = np.empty(n.value + 1, dtype=np.uint64)
+        dbuf = np.empty(d.value, dtype=np.uint8)
+        doff = np.empty(n.value + 1, dtype=np.uint64)
+        rc = lib.dbi_fasta_read(f, residues.ctypes.data if r.value else None, offsets.ctypes.data,
+                                dbuf.ctypes.data if d.value else None, doff.ctypes.data)
+        if rc != 0:
+            raise DbiError(rc, (lib.dbi_last_error() or b"").decode(errors="replace"))
+    finally:
+        lib.dbi_fasta_close(f)
+    raw = dbuf.tobytes()
+    deflines = [raw[int(doff[i]):int(doff[i + 1])].decode("latin-1") for i in range(n.value)]
+    return deflines, residues, offsets
 
 
 class GpuIndex:

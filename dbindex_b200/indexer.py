@@ -20,7 +20,7 @@ from typing import Iterable, List, Optional, Sequence, Set, Tuple
 
 import numpy as np
 
-from .capi import DbiError, DbiParams, GpuIndex
+from .capi import DbiError, DbiParams, GpuIndex, parse_fasta
 
 MAX_INDEX_RESIDUE_LEN = 3      # Constants.java:44
 MAX_PRECURSOR_MASS = 8000      # Constants.java:20
@@ -109,22 +109,10 @@ def merge_intervals(ranges: Sequence[MassRange]) -> List[Tuple[float, float]]:
     return out
 
 
-def read_fasta(path: str) -> Tuple[List[str], List[str]]:
-    """Minimal FASTA reader (the reference uses the external FastaReader)."""
-    deflines, seqs, cur = [], [], []
-    with open(path, "r") as f:
-        for line in f:
-            line = line.rstrip("\r\n")
-            if line.startswith(">"):
-                if deflines:
-                    seqs.append("".join(cur))
-                deflines.append(line[1:])
-                cur = []
-            elif line:
-                cur.append(line.strip().upper())
-    if deflines:
-        seqs.append("".join(cur))
-    return deflines, seqs
+def read_fasta(path: str) -> Tuple[List[str], np.ndarray, np.ndarray]:
+    """FASTA -> (deflines, residues, offsets) through the native multi-threaded parser
+    (capi.parse_fasta; the reference uses the external FastaReader, DBIndexer.java:560-571)."""
+    return parse_fasta(path)
 
 
 class DBIndexer:
@@ -159,8 +147,9 @@ class DBIndexer:
         """DBIndexer.run(): stream the FASTA, cut every protein, close the store."""
         self._require()
         if fasta is not None:
-            proteins = read_fasta(fasta)
-        if proteins is not None:
+            deflines, residues, offsets = read_fasta(fasta)
+            self.add_proteins(deflines, residues, offsets)
+        elif proteins is not None:
             deflines, seqs = proteins
             residues = np.frombuffer("".join(seqs).encode("latin-1"), dtype=np.uint8)
             offsets = np.zeros(len(seqs) + 1, dtype=np.uint64)

@@ -242,6 +242,21 @@ int dbi_debug_emitted(dbi_handle* h, uint64_t capacity, double* mass, uint32_t* 
 int dbi_build_from_records(dbi_handle* h, const double* mass, const uint32_t* prot,
                            const uint32_t* off, const uint16_t* len, uint64_t n);
 
+/* ---- FASTA ingest (host only): the step before the path ------------------------------------
+ * Replaces the external FastaReader passes of DBIndexer.run (DBIndexer.java:560-571,600-605): the
+ * file is mapped and parsed by n_threads host threads (<= 0: all) into the packed layout
+ * dbi_add_proteins takes.  A line starting with '>' opens a record (defline = rest of the line);
+ * the sequence is the following non-empty lines, stripped of white space at both ends,
+ * concatenated and upper-cased; anything before the first '>' is ignored.
+ *   dbi_fasta_open -> dbi_fasta_counts -> (caller allocates) -> dbi_fasta_read -> dbi_fasta_close
+ * residues[n_residues], offsets[n_proteins + 1]; deflines[defline_bytes] (not NUL-terminated) and
+ * defline_off[n_proteins + 1] may be NULL. */
+typedef struct dbi_fasta dbi_fasta;
+int dbi_fasta_open(const char* path, int n_threads, dbi_fasta** out);
+int dbi_fasta_counts(const dbi_fasta* f, uint32_t* n_proteins, uint64_t* n_residues, uint64_t* defline_bytes);
+int dbi_fasta_read(const dbi_fasta* f, uint8_t* residues, uint64_t* offsets, char* deflines, uint64_t* defline_off);
+void dbi_fasta_close(dbi_fasta* f);
+
 /* ---- multi-GPU staged build -----------------------------------------
  * One process and one handle per GPU.  Every rank adds the SAME proteins (the residue
  * buffer is replicated, 3 GB even at TrEMBL scale), digests only its own range of start

@@ -62,3 +62,26 @@ def expand_set(p, pep: str, base_mass: float):
             if p.min_mass <= m <= p.max_mass:
                 out.append((m, combo))
     return out
+
+
+def read_fasta_py(path: str):
+    """Pure-Python restatement of the FASTA record grammar (what csrc/fasta.cpp must reproduce):
+    '>' at the start of a line opens a record, the defline is the rest of that line; the sequence is
+    the following non-empty lines, stripped at both ends, concatenated, upper-cased; anything before
+    the first '>' is ignored.  Lines end with '\\n' (an optional '\\r' before it is dropped)."""
+    deflines, seqs, cur = [], [], []
+    with open(path, "rb") as f:
+        data = f.read().decode("latin-1")
+    for line in data.split("\n"):
+        if line.startswith(">"):
+            if deflines:
+                seqs.append("".join(cur))
+            deflines.append(line[1:].rstrip("\r\n"))
+            cur = []
+        else:
+            t = line.strip(" \t\r\n\v\f")
+            if t:
+                cur.append("".join(chr(ord(c) - 32) if "a" <= c <= "z" else c for c in t))
+    if deflines:
+        seqs.append("".join(cur))
+    return deflines, seqs
