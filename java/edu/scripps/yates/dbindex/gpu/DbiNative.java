@@ -67,6 +67,18 @@ public final class DbiNative {
 	static final MethodHandle dbi_stats_get = h("dbi_stats_get", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
 	static final MethodHandle dbi_calculate_mass = h("dbi_calculate_mass",
 			FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
+	// host-side FASTA ingest (csrc/fasta.cpp): packed residues + offsets + deflines for dbi_add_proteins
+	static final MethodHandle dbi_fasta_open = h("dbi_fasta_open", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
+	static final MethodHandle dbi_fasta_counts = h("dbi_fasta_counts",
+			FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+	static final MethodHandle dbi_fasta_read = h("dbi_fasta_read",
+			FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+	static final MethodHandle dbi_fasta_close = h("dbi_fasta_close", FunctionDescriptor.ofVoid(ADDRESS));
+	// sharded build (one handle per GPU): a hit whose base peptide lives on another GPU comes back from
+	// dbi_fetch as first_prot == DBI_REMOTE_BASE, first_off == global id; its owner resolves it here
+	static final int DBI_REMOTE_BASE = 0xffffffff;
+	static final MethodHandle dbi_mg_lookup_unique = h("dbi_mg_lookup_unique", FunctionDescriptor.of(JAVA_INT, ADDRESS,
+			ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
 	static final MethodHandle dbi_destroy = h("dbi_destroy", FunctionDescriptor.ofVoid(ADDRESS));
 	static final MethodHandle dbi_last_error = h("dbi_last_error", FunctionDescriptor.of(ADDRESS));
 
