@@ -208,9 +208,10 @@ def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def parse_fasta(path: str, threads: int = 0):
+def parse_fasta(path: str, threads: int = 0, raw_deflines: bool = False):
     """FASTA file -> (deflines list[str], residues uint8[R], offsets uint64[n + 1]) through the native
-    multi-threaded parser (dbi_fasta_*, csrc/fasta.cpp): the packed layout `add_proteins` takes."""
+    multi-threaded parser (dbi_fasta_*, csrc/fasta.cpp): the packed layout `add_proteins` takes.
+    raw_deflines: return the deflines as (bytes buffer uint8[], offsets uint64[n + 1]) instead of strings."""
     lib = load_library()
     f = C.c_void_p()
     rc = lib.dbi_fasta_open(os.fsencode(path), int(threads), C.byref(f))
@@ -229,6 +230,8 @@ def parse_fasta(path: str, threads: int = 0):
             raise DbiError(rc, (lib.dbi_last_error() or b"").decode(errors="replace"))
     finally:
         lib.dbi_fasta_close(f)
+    if raw_deflines:
+        return (dbuf, doff), residues, offsets
     raw = dbuf.tobytes()
     deflines = [raw[int(doff[i]):int(doff[i + 1])].decode("latin-1") for i in range(n.value)]
     return deflines, residues, offsets
