@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cerrno>
 #include <cstring>
+#include <exception>
 #include <thread>
 #include <vector>
 
@@ -105,7 +106,9 @@ int dbi_fasta_open(const char* path, int n_threads, dbi_fasta** out) {
     close(fd);
     return DBI_EINVAL;
   }
-  dbi_fasta* f = new dbi_fasta();
+  dbi_fasta* f = nullptr;
+  try {
+  f = new dbi_fasta();
   f->fd = fd;
   f->size = (size_t)st.st_size;
   f->n_threads = n_threads > 0 ? n_threads : (int)std::max(1u, std::thread::hardware_concurrency());
@@ -164,6 +167,11 @@ int dbi_fasta_open(const char* path, int n_threads, dbi_fasta** out) {
   }
   *out = f;
   return DBI_OK;
+  } catch (const std::exception& e) {  // bad_alloc, or a thread that could not be started
+    dbi::set_error("FASTA ingest failed: %s", e.what());
+    if (f) dbi_fasta_close(f); else close(fd);
+    return DBI_ENOMEM;
+  }
 }
 
 int dbi_fasta_counts(const dbi_fasta* f, uint32_t* n_proteins, uint64_t* n_residues, uint64_t* defline_bytes) {
@@ -191,6 +199,7 @@ int dbi_fasta_read(const dbi_fasta* f, uint8_t* residues, uint64_t* offsets, cha
   if (defline_off) std::memcpy(defline_off, f->def_off.data(), (R + 1) * sizeof(uint64_t));
   const char* d = f->data;
   const size_t n = f->size;
+  try {
   parallel_for(f->n_threads, R, [&](size_t lo, size_t hi, int) {
     for (size_t r = lo; r < hi; ++r) {
       const char* p = d + f->rec_begin[r];
@@ -207,6 +216,10 @@ int dbi_fasta_read(const dbi_fasta* f, uint8_t* residues, uint64_t* offsets, cha
       });
     }
   });
+  } catch (const std::exception& e) {
+    dbi::set_error("FASTA ingest failed: %s", e.what());
+    return DBI_ENOMEM;
+  }
   return DBI_OK;
 }
 

@@ -404,7 +404,7 @@ def lookup_unique(g, gids: np.ndarray) -> dict:
     return {"first_prot": prot, "first_off": off, "len": ln, "prot_list_off": plo, "prot_ids": ids}
 
 
-def fetch_resolved(g, info: dict, begin: int, count: int) -> dict:
+def fetch_resolved(g, info: dict, begin: int, count: int, lookup=None) -> dict:
     """COLLECTIVE dbi_fetch of entries [begin, begin + count) of this rank's slice with every base
     peptide resolved: hits whose base lives on another rank (first_prot == DBI_REMOTE_BASE, first_off
     = global id) are answered by their owners.  A process that holds all the handles (the Java host)
@@ -412,6 +412,7 @@ def fetch_resolved(g, info: dict, begin: int, count: int) -> dict:
     f = g.fetch(begin, count)
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return f
+    lookup = lookup or lookup_unique
     world, rank = dist.get_world_size(), dist.get_rank()
     uoff = np.asarray(info["unique_off"], dtype=np.int64)
     remote = np.nonzero(f["first_prot"] == REMOTE_BASE)[0]
@@ -420,7 +421,7 @@ def fetch_resolved(g, info: dict, begin: int, count: int) -> dict:
     ask = [np.unique(gids[owner == r]).astype(np.uint32) for r in range(world)]
     asked = [None] * world
     dist.all_gather_object(asked, ask)           # asked[src][dst] = ids src wants from dst
-    answers = [lookup_unique(g, asked[src][rank]) if len(asked[src][rank]) else None for src in range(world)]
+    answers = [lookup(g, asked[src][rank]) if len(asked[src][rank]) else None for src in range(world)]
     got = [None] * world
     dist.all_gather_object(got, answers)         # got[dst][src] = dst's answer to src
     plo = f["prot_list_off"].astype(np.int64)

@@ -1,6 +1,7 @@
 """world_size-2 gloo tests of the N>1 path on CPU: the orchestration of dbindex_b200/multigpu.py
-(splitters, all-to-all-v, replicated unique tables, tile re-dealing, query routing) with a CPU
-engine, against the single-process oracle."""
+(splitters, all-to-all-v, the fused all-gather of (gpos, len), group exchange by variant mass,
+query routing, resolution of hits whose base peptide lives on another rank) with a CPU engine,
+against the single-process oracle."""
 import json
 import os
 import subprocess
@@ -62,3 +63,15 @@ def test_two_rank_gloo_build_matches_oracle(name, tmp_path):
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     r = json.loads(out.read_text())
     assert r["ok"] and all(c > 0 for c in r["counts"]) and r["a2a_bytes"] > 0
+
+
+def test_fetch_resolved_two_ranks(tmp_path):
+    """Hits whose base peptide is held by the other rank come back as DBI_REMOTE_BASE + global id and
+    are completed by their owner (multigpu.fetch_resolved), lists and first occurrences intact."""
+    out = tmp_path / "ok.txt"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29871", os.path.join(ROOT, "tests", "resolve_worker.py"), str(out)]
+    p = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, OMP_NUM_THREADS="1"), capture_output=True, text=True,
+                       timeout=300)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert out.read_text() == "ok"
