@@ -247,3 +247,43 @@ def test_property_digest(seqs, mc, semi, nocut):
     e = o.emitted()
     assert [(int(a), int(b), int(c)) for a, b, c in zip(e["prot"], e["off"], e["len"])] == [(a, b, c) for a, b, c, _ in exp]
     assert np.array_equal(bits(e["mass"]), bits([m for *_, m in exp]))
+
+
+def test_oracle_matches_a_sqlite_restatement_of_the_reference_store():
+    """The oracle's rows / merge / query against tests/sqlite_ref.py: the reference's table, records
+    and SQL on a real SQLite B-tree, fed with the same addSequence calls."""
+    import struct
+
+    from .sqlite_ref import SqliteStore
+    p = dbi.default_params()
+    res, off = synth.synth_proteome(60, 4242, median_len=220, min_len=5)
+    seqs = [res[int(off[i]):int(off[i + 1])].tobytes().decode() for i in range(len(off) - 1)]
+    seqs += [seqs[0], seqs[7], "AAGGLLKGGAALLKAAGGLLK", "GALKAGLKLAGKGLAK", seqs[0]]  # duplicates and isomers
+    o = Oracle(p)
+    o.add_proteins(*pack(seqs))
+    assert o.build() == 0
+    em = o.emitted()
+    store = SqliteStore(seqs, p.mass_group_factor)
+    for m, pr, of, ln in zip(em["mass"], em["prot"], em["off"], em["len"]):
+        store.add_sequence(float(m), int(of), int(ln), int(pr))
+    store.stop_add_seq()
+
+    def canon(entries):
+        return sorted((struct.pack("<d", m), s, ids) for m, s, ids in entries)
+
+    e = o.entries()
+    plo = e["prot_list_off"].astype(np.int64)
+    mine = [(float(e["mass"][i]), seqs[int(e["first_prot"][i])][int(e["first_off"][i]):int(e["first_off"][i]) + int(e["len"][i])],
+             tuple(int(x) for x in e["prot_ids"][plo[i]:plo[i + 1]])) for i in range(len(e["mass"]))]
+    assert canon(store.all_entries()) == canon(mine)
+    # queries: 10 ppm windows around indexed masses, wide windows, decoys, zero tolerance
+    rng = np.random.default_rng(3)
+    qm = np.concatenate([e["mass"][rng.integers(0, len(e["mass"]), 40)], rng.uniform(600, 6000, 20)])
+    tol = np.concatenate([qm[:20] * 1e-5, np.zeros(20), np.full(10, 3.0), np.full(10, 0.02)])
+    lo, hi = np.maximum(qm - tol, 0.0), qm + tol
+    b, c, contig = o.query(lo, hi)
+    assert contig
+    for k in range(len(qm)):
+        got = canon(store.get_sequences(float(qm[k]), float(tol[k])))
+        exp = canon(mine[int(b[k]):int(b[k] + c[k])])
+        assert got == exp, (k, qm[k], tol[k], len(got), len(exp))
