@@ -248,7 +248,7 @@ def run_reference(args, rank: int, world: int):
 def run_sharded(args, rank: int, local_rank: int, world: int):
     """N > 1: ONE index over world x 20000 proteins (weak scaling), built with the real exchange:
     replicated residues, range-sharded digestion, NCCL all-to-all of the peptide records by mass
-    slice, replicated unique tables, variant all-to-all by variant mass, routed queries."""
+    slice, (gpos, len) all-gather, group all-to-all by variant mass, routed queries."""
     import torch
     import torch.distributed as dist
     import dbindex_b200 as dbi

@@ -51,19 +51,6 @@ def pick_splitters(hist: np.ndarray, world: int) -> np.ndarray:
     return np.maximum.accumulate(out) if len(out) else out
 
 
-def balance_tiles(tile_counts: np.ndarray, world: int) -> List[Tuple[int, int]]:
-    """Contiguous tile ranges with near-equal total count: [(begin, n_tiles)] per rank."""
-    n = len(tile_counts)
-    cum = np.concatenate(([0], np.cumsum(tile_counts.astype(np.int64))))
-    total = int(cum[-1])
-    cuts = [0]
-    for d in range(1, world):
-        cuts.append(int(np.searchsorted(cum, total * d // world, side="left")))
-    cuts.append(n)
-    cuts = np.maximum.accumulate(np.minimum(cuts, n))
-    return [(int(cuts[d]), int(cuts[d + 1] - cuts[d])) for d in range(world)]
-
-
 def splitter_masses(bin_splitters: np.ndarray, shift: int, min_mass: float) -> np.ndarray:
     """The mass at which each splitter sits: radix key = bits(mass) - bits(min_mass)."""
     base = np.float64(min_mass).view(np.uint64)

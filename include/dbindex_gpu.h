@@ -259,11 +259,12 @@ void dbi_fasta_close(dbi_fasta* f);
 
 /* ---- multi-GPU staged build -----------------------------------------
  * One process and one handle per GPU.  Every rank adds the SAME proteins (the residue
- * buffer is replicated, 3 GB even at TrEMBL scale), digests only its own range of start
+ * buffer is replicated, 4 GB even at TrEMBL scale), digests only its own range of start
  * positions, and the ranks exchange records so that rank d ends up with one contiguous
  * mass slice -- the GPU analogue of DBIndexStoreSQLiteMult's per-bucket SQLite files
  * (DBIndexStoreSQLiteMult.java:55-56,215-217).  The collectives themselves (all-reduce of
- * the histograms, all-to-all of the records, broadcast of the unique tables) are issued by
+ * the histograms, all-to-all of the records and of the variant groups, all-gather of the
+ * (gpos, len) of the unique peptides) are issued by
  * the host over NCCL on caller-owned device buffers; these entry points are the device work
  * between them.  dbindex_b200/multigpu.py is the reference orchestration.  All `d_` pointers
  * are device memory of the handle's GPU.

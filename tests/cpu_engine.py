@@ -1,6 +1,6 @@
 """A CPU ShardEngine backed by the oracle and numpy -- TEST INFRASTRUCTURE.  Lets the multi-rank
-orchestration of dbindex_b200/multigpu.py (splitters, all-to-all, table replication, tile
-re-dealing, query routing) run under gloo without a GPU.  It shards by PROTEIN ranges (the GPU
+orchestration of dbindex_b200/multigpu.py (splitters, all-to-all, the (gpos, len) all-gather, group
+exchange under global peptide ids, query routing) run under gloo without a GPU.  It shards by PROTEIN ranges (the GPU
 engine shards by start-position tiles; both concatenate to the global emission order)."""
 from __future__ import annotations
 

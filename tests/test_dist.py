@@ -10,7 +10,7 @@ import sys
 import numpy as np
 import pytest
 
-from dbindex_b200.multigpu import balance_tiles, pick_splitters, route_queries, splitter_masses
+from dbindex_b200.multigpu import pick_splitters, route_queries, splitter_masses
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -27,19 +27,6 @@ def test_pick_splitters_equal_count_and_monotone():
         assert sum(loads) == hist.sum()
         assert max(loads) - min(loads) <= 2 * hist.max()  # bins are never split
     assert pick_splitters(np.zeros(4096, np.int64), 4).tolist() == [0, 0, 0]
-
-
-def test_balance_tiles_covers_everything():
-    rng = np.random.default_rng(1)
-    counts = (rng.integers(1, 50, size=1000) ** 3) % 100000  # heavy tail like the variant counts
-    for world in (1, 2, 3, 8):
-        r = balance_tiles(counts, world)
-        assert r[0][0] == 0 and sum(n for _, n in r) == 1000
-        for (b0, n0), (b1, _) in zip(r, r[1:]):
-            assert b0 + n0 == b1
-        loads = [counts[b:b + n].sum() for b, n in r]
-        assert max(loads) <= counts.sum() / world + counts.max()
-    assert balance_tiles(np.zeros(0, np.int64), 2) == [(0, 0), (0, 0)]
 
 
 def test_route_queries_straddling():
