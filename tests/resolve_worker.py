@@ -10,7 +10,9 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from dbindex_b200.multigpu import REMOTE_BASE, fetch_resolved  # noqa: E402
+import torch  # noqa: E402
+
+from dbindex_b200.multigpu import REMOTE_BASE, _gather_tables, fetch_resolved  # noqa: E402
 
 
 def truth(gid):  # what the owner knows about unique peptide gid
@@ -59,6 +61,17 @@ def main():
             assert int(f["len"][i]) == t["len"]
             assert f["prot_ids"][plo[i]:plo[i + 1]].tolist() == t["ids"], (rank, i, gid)
         assert len(plo) == count + 1
+    # the fused all-gather of several tables with different widths and uneven (also empty) sizes
+    for sizes in ([5, 3], [0, 4], [7, 0], [0, 0]):
+        n = sizes[rank]
+        a = torch.arange(n, dtype=torch.int32) + 1000 * rank
+        b = (torch.arange(n, dtype=torch.int16) * 3 + rank).to(torch.int16)
+        c = torch.arange(2 * n, dtype=torch.int64) - 7 * rank           # a table with its own counts
+        ga, gb, gc = _gather_tables([a, b, c], [sizes, sizes, [2 * x for x in sizes]])
+        ea = torch.cat([torch.arange(sizes[r], dtype=torch.int32) + 1000 * r for r in range(2)])
+        eb = torch.cat([(torch.arange(sizes[r], dtype=torch.int16) * 3 + r).to(torch.int16) for r in range(2)])
+        ec = torch.cat([torch.arange(2 * sizes[r], dtype=torch.int64) - 7 * r for r in range(2)])
+        assert torch.equal(ga, ea) and torch.equal(gb, eb) and torch.equal(gc, ec), (rank, sizes)
     dist.barrier()
     if rank == 0:
         open(sys.argv[1], "w").write("ok")
