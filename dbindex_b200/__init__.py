@@ -15,4 +15,12 @@ from .capi import (  # noqa: F401
     load_library,
     STAGE_NAMES,
 )
-from .indexer import DBIndexer, DBIndexImpl, IndexedSequence, IndexedProtein, MassRange  # noqa: F401
+from .indexer import (  # noqa: F401
+    DBIndexer,
+    DBIndexImpl,
+    DBIndexSearchParams,
+    IndexedSequence,
+    IndexedProtein,
+    MassRange,
+    getDefaultDBIndexParams,
+)

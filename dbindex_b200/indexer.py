@@ -15,6 +15,7 @@ under ``java/`` is the same logic in the reference's own language (INTEGRATION.m
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Set, Tuple
 
@@ -113,6 +114,81 @@ def read_fasta(path: str) -> Tuple[List[str], np.ndarray, np.ndarray]:
     """FASTA -> (deflines, residues, offsets) through the native multi-threaded parser
     (capi.parse_fasta; the reference uses the external FastaReader, DBIndexer.java:560-571)."""
     return parse_fasta(path)
+
+
+# resources/dbindex.properties:3-26, restated (the file itself is configuration of the reference)
+DBINDEX_PROPERTIES = {
+    "default_index_type": "INDEX_NORMAL", "default_in_memory_index": True, "default_index_factor": 8,
+    "default_max_internal_cleavages": 6, "default_max_precursor_mass": 6000.0, "default_min_precursor_mass": 500.0,
+    "default_use_index": True, "default_enzyme_nocut_residues": "", "default_enzyme_residues": "KR",
+    "default_enzyme_offset": 0, "default_mass_type_parent": "1", "mass_group_factor": 10000,
+    "add_h2o_plus_proton": True, "mandatory_internal_AAs": "K", "default_semicleavage": False,
+}
+
+
+@dataclass
+class DBIndexSearchParams:
+    """io/DBIndexSearchParamsImpl.java:46-75 -- the programmatic parameter object: the kernel-facing
+    part is `params` (dbi_params), the rest is what the facade needs."""
+    params: DbiParams
+    dataBaseName: str
+    indexFactor: int = 8
+    inMemoryIndex: bool = True
+    useIndex: bool = True
+    indexType: str = "INDEX_NORMAL"
+    enzymeOffset: int = 0          # never reaches the Enzyme (SearchParams.java:303); only named the index file
+    useMonoParent: bool = False
+    mandatoryInternalAAs: Optional[str] = None
+    discardDecoyRegexp: Optional[str] = None
+
+    def key(self) -> str:
+        """What getByParam keys its registry on (DBIndexImpl.java:44-49: the full index file name, i.e.
+        the database plus every parameter that shapes the index, IndexUtil.java:276-323)."""
+        p = self.params
+        enz = "".join(chr(i) for i in range(256) if p.is_enzyme[i])
+        nocut = "".join(chr(i) for i in range(256) if p.is_nocut[i])
+        mods = ",".join(f"{chr(p.mods[i].residue)}{p.mods[i].delta!r}" for i in range(p.n_mods))
+        statics = ",".join(f"{i}:{p.residue_mass[i]!r}" for i in range(256) if p.residue_mass[i])
+        return "|".join(str(x) for x in (
+            self.dataBaseName, self.indexFactor, p.max_missed, p.min_mass, p.max_mass, enz, nocut, self.enzymeOffset,
+            self.useMonoParent, p.add_h2o_proton, p.mass_group_factor, p.semi, p.min_len, self.mandatoryInternalAAs,
+            self.discardDecoyRegexp, p.max_mods_per_peptide, mods, statics))
+
+
+def getDefaultDBIndexParams(fastaFilePath, inMemoryIndex: Optional[bool] = None, use_mono: Optional[bool] = None,
+                            **overrides) -> DBIndexSearchParams:
+    """DBIndexImpl.getDefaultDBIndexParams(File | String [, boolean inMemoryIndex]) (DBIndexImpl.java:243-332):
+    the defaults of dbindex.properties -- KR, no no-cut residues, 6 missed cleavages, 500-6000 Da, full
+    specificity, H2O + proton added, factor 10000, index factor 8.
+
+    Mass type: the reference reads `default_mass_type_parent=1` with `Boolean.valueOf("1")`, which is
+    false, so this factory builds an AVERAGE-mass index (DBIndexImpl.java:281-282; only the proteoform
+    factory compares with "1", :407-409).  use_mono=None reproduces that; pass True for monoisotopic."""
+    from .capi import default_params
+    pr = DBINDEX_PROPERTIES
+    mono = bool(use_mono) if use_mono is not None else False
+    kw = dict(enzyme=pr["default_enzyme_residues"], nocut=pr["default_enzyme_nocut_residues"],
+              max_missed=pr["default_max_internal_cleavages"], min_mass=pr["default_min_precursor_mass"],
+              max_mass=pr["default_max_precursor_mass"], mass_group_factor=pr["mass_group_factor"],
+              add_h2o_proton=1 if pr["add_h2o_plus_proton"] else 0, semi=1 if pr["default_semicleavage"] else 0)
+    kw.update(overrides)
+    return DBIndexSearchParams(
+        params=default_params(mono=mono, **kw), dataBaseName=os.fspath(fastaFilePath),
+        indexFactor=pr["default_index_factor"],
+        inMemoryIndex=pr["default_in_memory_index"] if inMemoryIndex is None else bool(inMemoryIndex),
+        useIndex=pr["default_use_index"], indexType=pr["default_index_type"],
+        enzymeOffset=pr["default_enzyme_offset"], useMonoParent=mono)
+
+
+def getDefaultDBIndexParamsForCrosslinkerAnalysis(fastaFilePath, inMemoryIndex: Optional[bool] = None):
+    """DBIndexImpl.java:342-372,443-491: no H2O + proton and mandatory internal K.  The mandatory
+    internal residues (DBIndexer.java:334-344) are a "next" row of the scope table: not built yet."""
+    raise DBIndexerException("mandatoryInternalAAs (cross-linker parameter set) is not supported by the GPU index yet")
+
+
+def getDefaultDBIndexParamsForProteoformAnalysis(*args, **kwargs):
+    """DBIndexImpl.java:392-432: needs UniProt annotations and proteoform FASTA expansion -- out of scope."""
+    raise DBIndexerException("proteoform analysis needs the UniProt annotation service; out of scope of the GPU index")
 
 
 class DBIndexer:
@@ -299,12 +375,30 @@ class DBIndexer:
 class DBIndexImpl:
     """DBIndexImpl.java: the DBIndexInterface facade a search engine holds."""
 
-    def __init__(self, params: DbiParams, fasta: Optional[str] = None,
+    _by_param_key: dict = {}  # DBIndexImpl.java:35 dbIndexByParamKey
+
+    def __init__(self, params, fasta: Optional[str] = None,
                  proteins: Optional[Tuple[Sequence[str], Sequence[str]]] = None, index_factor: int = 8):
+        """params: dbi_params, or a DBIndexSearchParams (then the FASTA is its dataBaseName, as in
+        DBIndexImpl(DBIndexSearchParams), DBIndexImpl.java:117-145)."""
+        self.sparam = params if isinstance(params, DBIndexSearchParams) else None
+        if self.sparam is not None:
+            if fasta is None and proteins is None:
+                fasta = self.sparam.dataBaseName
+            index_factor = self.sparam.indexFactor
+            params = self.sparam.params
         self.indexer = DBIndexer(params, index_factor)
         self.indexer.init()
         self.indexer.run(fasta=fasta, proteins=proteins)
         self._proteins_by_seq: dict = {}  # DBIndexImpl.java:33
+        if self.sparam is not None:
+            DBIndexImpl._by_param_key[self.sparam.key()] = self  # DBIndexImpl.java:137-139
+
+    @staticmethod
+    def getByParam(sParam: "DBIndexSearchParams") -> "DBIndexImpl":
+        """DBIndexImpl.getByParam (DBIndexImpl.java:44-49): one index per parameter key."""
+        hit = DBIndexImpl._by_param_key.get(sParam.key())
+        return hit if hit is not None else DBIndexImpl(sParam)
 
     def getSequences(self, *args) -> List[IndexedSequence]:
         """getSequences(double precursorMass, double massTolerance) (DBIndexImpl.java:180) or
@@ -327,4 +421,6 @@ class DBIndexImpl:
         return self.indexer.getProteinSequence(pid)  # DBIndexImpl.java:511-513
 
     def close(self):
+        if self.sparam is not None:
+            DBIndexImpl._by_param_key.pop(self.sparam.key(), None)
         self.indexer.close()

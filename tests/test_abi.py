@@ -89,3 +89,27 @@ def test_product_never_imports_the_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", "Makefile")):
                     txt = open(os.path.join(root, f), errors="replace").read()
                     assert "liboracle" not in txt and "oracle_py" not in txt and "orc_" not in txt, os.path.join(root, f)
+
+
+def test_default_dbindex_params_factory_mirrors_the_reference():
+    """DBIndexImpl.getDefaultDBIndexParams (DBIndexImpl.java:243-332) with the values of
+    resources/dbindex.properties, including the reference's mass-type quirk (Boolean.valueOf("1"))."""
+    from dbindex_b200.indexer import (DBIndexerException, getDefaultDBIndexParams,
+                                      getDefaultDBIndexParamsForCrosslinkerAnalysis)
+    sp = getDefaultDBIndexParams("/data/uniprot.fasta")
+    p = sp.params
+    assert (sp.dataBaseName, sp.indexFactor, sp.inMemoryIndex, sp.useIndex, sp.enzymeOffset) == \
+        ("/data/uniprot.fasta", 8, True, True, 0)
+    assert (p.max_missed, p.min_mass, p.max_mass, p.semi, p.min_len, p.mass_group_factor, p.add_h2o_proton) == \
+        (6, 500.0, 6000.0, 0, 6, 10000, 1)
+    assert [chr(i) for i in range(256) if p.is_enzyme[i]] == ["K", "R"] and not any(p.is_nocut)
+    # average masses by default, as the reference computes it; monoisotopic on request
+    assert not sp.useMonoParent and abs(p.residue_mass[ord("G")] - 57.0513) < 1e-9
+    mono = getDefaultDBIndexParams("/data/uniprot.fasta", use_mono=True)
+    assert mono.useMonoParent and abs(mono.params.residue_mass[ord("G")] - 57.02146372) < 1e-9
+    assert getDefaultDBIndexParams("x.fasta", inMemoryIndex=False).inMemoryIndex is False
+    # the registry key separates everything that shapes the index
+    assert sp.key() != mono.key() and sp.key() == getDefaultDBIndexParams("/data/uniprot.fasta").key()
+    assert sp.key() != getDefaultDBIndexParams("/data/uniprot.fasta", max_missed=2).key()
+    with pytest.raises(DBIndexerException):
+        getDefaultDBIndexParamsForCrosslinkerAnalysis("x.fasta")
