@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdbindex_gpu.so")
 
-DBI_ABI_VERSION = 1
+DBI_ABI_VERSION = 2
 DBI_MAX_MODS = 16
 DBI_N_STAGES = 12
 STAGE_NAMES = [
@@ -54,6 +54,11 @@ class DbiParams(C.Structure):
         ("n_mods", C.c_int32),
         ("max_mods_per_peptide", C.c_int32),
         ("mods", DbiMod * DBI_MAX_MODS),
+        ("is_mandatory", C.c_uint8 * 256),
+        ("has_mandatory", C.c_int32),
+        ("filter_aa", C.c_int32),
+        ("filter_max", C.c_int32),
+        ("_pad_filters", C.c_int32),
         ("keep_emitted", C.c_int32),
         ("profile", C.c_int32),
         ("reserved", C.c_int32 * 6),
@@ -183,7 +188,7 @@ def default_params(mono: bool = True, **overrides) -> DbiParams:
     """dbi_default_params + keyword overrides.
 
     Extra keywords: enzyme="KR", nocut="", static_mods={"C": 57.02146},
-    diff_mods=[("M", 15.9949), ("STY", 79.96633)]."""
+    diff_mods=[("M", 15.9949), ("STY", 79.96633)], mandatory_internal="K", peptide_filter=("K", 2)."""
     lib = load_library()
     p = DbiParams()
     lib.dbi_default_params(C.byref(p), 1 if mono else 0)
@@ -197,6 +202,14 @@ def default_params(mono: bool = True, **overrides) -> DbiParams:
         rc = lib.dbi_params_add_diff_mod(C.byref(p), residues.encode(), float(delta))
         if rc != 0:
             raise DbiError(rc, "too many differential mods")
+    mandatory = overrides.pop("mandatory_internal", None)  # sparam.getMandatoryInternalAAs()
+    if mandatory is not None:
+        p.has_mandatory = 1
+        for ch in mandatory:
+            p.is_mandatory[ord(ch)] = 1
+    pep_filter = overrides.pop("peptide_filter", None)      # PeptideFilterByMaxOccurrencies("K", 2) -> ("K", 2)
+    if pep_filter is not None:
+        p.filter_aa, p.filter_max = ord(pep_filter[0]), int(pep_filter[1])
     for k, v in overrides.items():
         if not hasattr(p, k):
             raise TypeError(f"unknown dbi_params field {k!r}")

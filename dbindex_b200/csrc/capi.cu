@@ -174,6 +174,7 @@ struct dbi_handle {
   DevBuf d_tables, d_err;
   DevBuf d_res, d_pstart;
   uint32_t res_end = 0;
+  uint64_t res_alloc = 0;  // bytes readable at d_res (multiple of 16: tiles are staged with bulk copies)
   uint64_t n_emitted = 0, n_unique = 0, n_entries = 0;
   DevBuf u_mass, u_gpos, u_prot, u_len, u_plo, plist;
   DevBuf e_mass, e_base, e_pat;  // empty when there are no differential mods (entries == unique peptides)
@@ -388,7 +389,9 @@ void upload_tables(dbi_handle* h) {
   const dbi_params& p = h->p;
   for (int i = 0; i < 256; ++i) {
     t.mass[i] = p.residue_mass[i];
-    t.flags[i] = (p.is_enzyme[i] ? kFlagEnzyme : 0) | (p.is_nocut[i] ? kFlagNocut : 0);
+    t.flags[i] = (p.is_enzyme[i] ? kFlagEnzyme : 0) | (p.is_nocut[i] ? kFlagNocut : 0) |
+                 ((p.has_mandatory && p.is_mandatory[i]) ? kFlagMandatory : 0) |
+                 ((p.filter_aa > 0 && p.filter_aa == i) ? kFlagFilterAA : 0);
   }
   const bool mods = p.n_mods > 0 && p.max_mods_per_peptide > 0;
   if (mods)
@@ -411,6 +414,8 @@ void upload_tables(dbi_handle* h) {
   h->cfg.mod_lo = 0;
   h->cfg.n_classes = 0;
   h->cfg.n_seq = 0;
+  h->cfg.mand_on = p.has_mandatory ? 1 : 0;
+  h->cfg.filt_max = p.filter_aa > 0 ? std::max(p.filter_max, 0) : -1;
   if (mods) {
     // mod classes = distinct shift values (two residues with the same shift are interchangeable
     // for the mass); class sequences of length <= K number (C^(K+1)-1)/(C-1)
@@ -469,6 +474,7 @@ void pack_residues(dbi_handle* h) {
   const uint64_t res_end = n_res + n_prot + 1;
   const uint64_t padded = (res_end + 64 + 15) & ~15ull;
   h->res_end = (uint32_t)res_end;
+  h->res_alloc = padded;
   h->d_res.alloc(padded, h->arena);
   h->d_pstart.alloc(((uint64_t)n_prot + 1) * 4, h->arena);
   DBI_CUDA(cudaMemsetAsync((uint8_t*)h->d_res.p + res_end, 0, padded - res_end, h->stream));
@@ -1075,17 +1081,18 @@ int dbi_build(dbi_handle* h) {
 
   const uint32_t n_prot = (uint32_t)(h->h_off.size() - 1);
   const uint64_t tiles = ((uint64_t)h->res_end + kDigestTile - 1) / kDigestTile;
-  DevBuf tile_counts, tile_offs;
+  DevBuf tile_counts, tile_offs, start_cnt;
   tile_counts.alloc(tiles * 4, h->arena);
   tile_offs.alloc((tiles + 1) * 8, h->arena);
+  start_cnt.alloc(tiles * kDigestTile, h->arena);
   uint64_t N = 0;
   {
     Stage sg(h, DBI_STAGE_DIGEST_COUNT);
-    launch_digest_count(h->d_res.as<uint8_t>(), h->res_end, h->d_tables.as<DevTables>(), h->cfg, 0, (uint32_t)tiles,
-                        tile_counts.as<uint32_t>(), h->d_err.as<uint32_t>(), s);
+    launch_digest_count(h->d_res.as<uint8_t>(), h->res_end, h->res_alloc, h->d_tables.as<DevTables>(), h->cfg, 0,
+                        (uint32_t)tiles, start_cnt.as<uint8_t>(), tile_counts.as<uint32_t>(), h->d_err.as<uint32_t>(), s);
     launch_scan_u32_to_u64(tile_counts.as<uint32_t>(), tiles, tile_offs.as<uint64_t>(), s);
     N = read_u64(h, tile_offs.as<uint64_t>() + tiles);
-    h->st.algo_bytes[DBI_STAGE_DIGEST_COUNT] += h->res_end + tiles * 16;
+    h->st.algo_bytes[DBI_STAGE_DIGEST_COUNT] += 2ull * h->res_end + tiles * 16;
   }
   if (int rc = check_err_bits(read_err(h))) {
     free_index(h);
@@ -1099,13 +1106,15 @@ int dbi_build(dbi_handle* h) {
   r_len.alloc(N * 2, h->arena);
   {
     Stage sg(h, DBI_STAGE_DIGEST_EMIT);
-    launch_digest_emit(h->d_res.as<uint8_t>(), h->res_end, h->d_tables.as<DevTables>(), h->cfg, 0, (uint32_t)tiles,
-                       tile_offs.as<uint64_t>(), h->d_pstart.as<uint32_t>(), n_prot, r_mass.as<uint64_t>(),
-                       r_gpos.as<uint32_t>(), r_prot.as<uint32_t>(), r_len.as<uint16_t>(), h->d_err.as<uint32_t>(), s);
-    h->st.algo_bytes[DBI_STAGE_DIGEST_EMIT] += h->res_end + N * 18;
+    launch_digest_emit(h->d_res.as<uint8_t>(), h->res_end, h->res_alloc, h->d_tables.as<DevTables>(), h->cfg, 0,
+                       (uint32_t)tiles, start_cnt.as<uint8_t>(), tile_offs.as<uint64_t>(), h->d_pstart.as<uint32_t>(),
+                       n_prot, r_mass.as<uint64_t>(), r_gpos.as<uint32_t>(), r_prot.as<uint32_t>(),
+                       r_len.as<uint16_t>(), h->d_err.as<uint32_t>(), s);
+    h->st.algo_bytes[DBI_STAGE_DIGEST_EMIT] += 2ull * h->res_end + N * 18;
   }
   tile_counts.release();
   tile_offs.release();
+  start_cnt.release();
   TR("emit");
   const RecView rv{r_mass.as<uint64_t>(), r_gpos.as<uint32_t>(), r_prot.as<uint32_t>(), r_len.as<uint16_t>()};
   int rc = index_records(h, rv, N, h->p.min_mass, h->p.max_mass);
@@ -1461,14 +1470,15 @@ int dbi_mg_digest(dbi_handle* h, uint64_t* n_records) {
   const uint32_t t0 = (uint32_t)(tiles_all * h->mg_rank / h->mg_world);
   const uint32_t t1 = (uint32_t)(tiles_all * (h->mg_rank + 1) / h->mg_world);
   const uint32_t nt = t1 - t0;
-  DevBuf tile_counts, tile_offs;
+  DevBuf tile_counts, tile_offs, start_cnt;
   tile_counts.alloc((uint64_t)nt * 4, h->arena);
   tile_offs.alloc(((uint64_t)nt + 1) * 8, h->arena);
+  start_cnt.alloc(std::max<uint64_t>(1, nt) * kDigestTile, h->arena);
   uint64_t N = 0;
   {
     Stage sg(h, DBI_STAGE_DIGEST_COUNT);
-    launch_digest_count(h->d_res.as<uint8_t>(), h->res_end, h->d_tables.as<DevTables>(), h->cfg, t0, nt,
-                        tile_counts.as<uint32_t>(), h->d_err.as<uint32_t>(), s);
+    launch_digest_count(h->d_res.as<uint8_t>(), h->res_end, h->res_alloc, h->d_tables.as<DevTables>(), h->cfg, t0, nt,
+                        start_cnt.as<uint8_t>(), tile_counts.as<uint32_t>(), h->d_err.as<uint32_t>(), s);
     launch_scan_u32_to_u64(tile_counts.as<uint32_t>(), nt, tile_offs.as<uint64_t>(), s);
     N = read_u64(h, tile_offs.as<uint64_t>() + nt);
     h->st.algo_bytes[DBI_STAGE_DIGEST_COUNT] += (uint64_t)nt * kDigestTile + (uint64_t)nt * 16;
@@ -1487,8 +1497,9 @@ int dbi_mg_digest(dbi_handle* h, uint64_t* n_records) {
   h->mg_len.alloc(N * 2, h->arena);
   {
     Stage sg(h, DBI_STAGE_DIGEST_EMIT);
-    launch_digest_emit(h->d_res.as<uint8_t>(), h->res_end, h->d_tables.as<DevTables>(), h->cfg, t0, nt,
-                       tile_offs.as<uint64_t>(), h->d_pstart.as<uint32_t>(), n_prot, h->mg_mass.as<uint64_t>(),
+    launch_digest_emit(h->d_res.as<uint8_t>(), h->res_end, h->res_alloc, h->d_tables.as<DevTables>(), h->cfg, t0, nt,
+                       start_cnt.as<uint8_t>(), tile_offs.as<uint64_t>(), h->d_pstart.as<uint32_t>(), n_prot,
+                       h->mg_mass.as<uint64_t>(),
                        h->mg_gpos.as<uint32_t>(), h->mg_prot.as<uint32_t>(), h->mg_len.as<uint16_t>(),
                        h->d_err.as<uint32_t>(), s);
     h->st.algo_bytes[DBI_STAGE_DIGEST_EMIT] += (uint64_t)nt * kDigestTile + N * 18;

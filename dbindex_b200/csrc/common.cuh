@@ -45,6 +45,8 @@ constexpr int kNumSMsB200 = 148;
 constexpr uint8_t kFlagEnzyme = 1;
 constexpr uint8_t kFlagNocut = 2;
 constexpr uint8_t kFlagDiffMod = 4;
+constexpr uint8_t kFlagMandatory = 8;  // sparam.getMandatoryInternalAAs()
+constexpr uint8_t kFlagFilterAA = 16;  // PeptideFilterByMaxOccurrencies.aa
 
 // error bits raised by kernels (OR-ed into a device word)
 constexpr uint32_t kErrZeroResidue = 1;   // residue byte 0 in the input

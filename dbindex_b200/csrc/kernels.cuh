@@ -26,6 +26,8 @@ struct DigestCfg {
   double mod_lo;     // min(0, smallest shift)
   int32_t n_classes; // distinct shift values
   int32_t n_seq;     // class sequences of length <= max_mods: (C^(K+1)-1)/(C-1); 0 if > 32
+  int32_t mand_on;   // mandatoryInternalAAs != null (DBIndexer.java:334-344)
+  int32_t filt_max;  // PeptideFilterByMaxOccurrencies: break once kFlagFilterAA residues exceed this; < 0 = off
 };
 
 constexpr int kDigestTile = 2048;   // start positions per CTA
@@ -37,20 +39,23 @@ constexpr int kModTile = 256;       // base peptides per CTA of the mod kernels 
 void launch_pack(const uint8_t* d_raw, const uint64_t* d_off, uint32_t n_prot, uint64_t n_res, uint8_t* d_res,
                  uint32_t* d_pstart, uint32_t* d_err, cudaStream_t s);
 
-// K2: per-tile count of the records cutSeq emits.
-// Tiles [tile0, tile0 + ntiles) of kDigestTile start positions each (a multi-GPU rank digests
-// only its own tile range of the replicated buffer).
-void launch_digest_count(const uint8_t* d_res, uint32_t res_end, const DevTables* d_tb, const DigestCfg& cfg,
-                         uint32_t tile0, uint32_t ntiles, uint32_t* d_tile_counts, uint32_t* d_err, cudaStream_t s);
+// K2: records cutSeq emits per START position (start_cnt[g - first position of tile0], saturating
+// at 255) and per tile.  Tiles [tile0, tile0 + ntiles) of kDigestTile start positions each (a
+// multi-GPU rank digests only its own tile range of the replicated buffer).  res_alloc = bytes
+// readable at d_res (a multiple of 16: the tiles are staged with 16-byte bulk copies).
+void launch_digest_count(const uint8_t* d_res, uint32_t res_end, uint64_t res_alloc, const DevTables* d_tb,
+                         const DigestCfg& cfg, uint32_t tile0, uint32_t ntiles, uint8_t* d_start_cnt,
+                         uint32_t* d_tile_counts, uint32_t* d_err, cudaStream_t s);
 
 // K3: exclusive scan of u32 tile counts into u64 offsets; offs[n] = total.
 void launch_scan_u32_to_u64(const uint32_t* d_in, uint64_t n, uint64_t* d_offs, cudaStream_t s);
 
 // K4: emit (mass bits, gpos, prot, len) in (protein, start, end) order.
-void launch_digest_emit(const uint8_t* d_res, uint32_t res_end, const DevTables* d_tb, const DigestCfg& cfg,
-                        uint32_t tile0, uint32_t ntiles, const uint64_t* d_tile_offs, const uint32_t* d_pstart,
-                        uint32_t n_prot, uint64_t* o_mass, uint32_t* o_gpos, uint32_t* o_prot, uint16_t* o_len,
-                        uint32_t* d_err, cudaStream_t s);
+// (one walk per emitting start: the per-start counts of K2 replace the counting walk)
+void launch_digest_emit(const uint8_t* d_res, uint32_t res_end, uint64_t res_alloc, const DevTables* d_tb,
+                        const DigestCfg& cfg, uint32_t tile0, uint32_t ntiles, const uint8_t* d_start_cnt,
+                        const uint64_t* d_tile_offs, const uint32_t* d_pstart, uint32_t n_prot, uint64_t* o_mass,
+                        uint32_t* o_gpos, uint32_t* o_prot, uint16_t* o_len, uint32_t* d_err, cudaStream_t s);
 
 // ---- sort helpers / K8 dedup -------------------------------------------------
 // hash[i] = seeded hash of the residues of record i (u32, or u64 when wide); idx[i] = i.

@@ -363,7 +363,7 @@ __device__ __forceinline__ uint32_t block_entry(int k, int p, uint32_t q, uint64
          ((uint32_t)(select_bit(r3, b) + 1) << 24);
 }
 
-__global__ void __launch_bounds__(ET_THREADS)
+__global__ void __launch_bounds__(ET_THREADS, 4)
     grp_expand_tab_kernel(DigestCfg cfg, const uint64_t* __restrict__ cmask, const uint8_t* __restrict__ res,
                           const DevTables* __restrict__ tb, const uint32_t* __restrict__ g_gpos,
                           const uint16_t* __restrict__ g_len, const uint64_t* __restrict__ skey,
@@ -377,6 +377,18 @@ __global__ void __launch_bounds__(ET_THREADS)
   uint64_t* const s_cm = reinterpret_cast<uint64_t*>(ex_raw + sizeof(ExpTabSmem));  // [max_mods][EX_GMAX]
   const int K = cfg.max_mods;
   auto cm_of = [&](int l, uint32_t j) -> uint64_t { return l < K ? s_cm[l * EX_GMAX + j] : 0ull; };
+  // k = 4 (rare): every entry is un-ranked on its own
+  auto block_entry_k4 = [&](uint32_t j, uint32_t q) -> uint32_t {
+    const uint64_t c0 = s_cm[j], c1 = cm_of(1, j), c2 = cm_of(2, j), c3 = cm_of(3, j);
+    int p = 0;
+    for (uint64_t m = c1; m; m &= m - 1) {
+      p = __ffsll((long long)m) - 1;
+      const uint32_t w = block_size(4, p, c0, c1, c2, c3);
+      if (q < w) break;
+      q -= w;
+    }
+    return block_entry(4, p, q, c0, c1, c2, c3);
+  };
   const int C = cfg.n_classes;
   const int t = threadIdx.x;
   const uint64_t tile = blockIdx.x;
@@ -462,15 +474,13 @@ __global__ void __launch_bounds__(ET_THREADS)
     if (rel > 0 && rel < (int64_t)kExpTile) s.head[rel] = (uint16_t)j;
   }
   __syncthreads();
-  // (2) inclusive max-scan of the heads: entry -> local group
+  // (2) group of every thread's FIRST entry: max-scan of the heads (kept in registers)
+  const uint32_t i0 = (uint32_t)t * ET_PER;
+  uint32_t j;
   {
-    uint32_t loc[ET_PER];
     uint32_t run = 0;
 #pragma unroll
-    for (int i = 0; i < ET_PER; ++i) {
-      run = max(run, (uint32_t)s.head[t * ET_PER + i]);
-      loc[i] = run;
-    }
+    for (int i = 0; i < ET_PER; ++i) run = max(run, (uint32_t)s.head[i0 + i]);
     uint32_t inc = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -483,62 +493,136 @@ __global__ void __launch_bounds__(ET_THREADS)
     for (int w = 0; w < (t >> 5); ++w) carry = max(carry, s.scratch[w]);
     const uint32_t prev = __shfl_up_sync(0xffffffffu, inc, 1);
     if (lane_id() > 0) carry = max(carry, prev);
-#pragma unroll
-    for (int i = 0; i < ET_PER; ++i) s.head[t * ET_PER + i] = (uint16_t)max(loc[i], carry);
+    j = max(carry, (uint32_t)s.head[i0]);
   }
-  __syncthreads();
-  // (3) one thread per entry, consecutive threads = consecutive entries.  The lanes of a warp sit
-  // in different groups with different k, so the work is phrased uniformly: find the block (site p,
-  // rank q inside it), then pattern = select(A, q / |B|), p, select(B, q % |B|) with the masks A / B
-  // empty where a level does not exist -- one code path for k = 1, 2, 3.
-  for (uint32_t i = t; i < tile_n; i += ET_THREADS) {
-    const uint32_t j = s.head[i];
-    const int k = s.k[j];
-    if (k == kLongGroup) continue;
-    uint32_t q = (uint32_t)((int32_t)i - s.off[j]);
-    const uint64_t c0 = k > 0 ? s_cm[j] : 1ull;
-    const uint64_t c1 = cm_of(1, j), c2 = cm_of(2, j), c3 = cm_of(3, j);
-    int p = 0;
-    if (k > 1) {
-      const uint32_t tab = s.tab[j];
-      if (tab != kNoTable) {
-        // last block whose first entry is <= q
-        uint32_t lo = 0, hi = (uint32_t)__popcll(block_sites(k, c0, c1));
-        while (hi - lo > 1) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (s.cum[tab + mid] <= q) lo = mid; else hi = mid;
-        }
-        p = s.pos[tab + lo];
-        q -= s.cum[tab + lo];
-      } else {
-        for (uint64_t m = block_sites(k, c0, c1); m; m &= m - 1) {
-          p = __ffsll((long long)m) - 1;
-          const uint32_t w = block_size(k, p, c0, c1, c2, c3);
-          if (q < w) break;
-          q -= w;
-        }
+  if (i0 >= tile_n) return;
+  // (3) every thread WALKS its ET_PER consecutive entries: the first one is un-ranked (block table
+  // + two bit-selects), the following ones cost a few mask operations each -- the iterator state
+  // (remaining block sites S, remaining first-level sites A, remaining last-level sites B) lives in
+  // registers.  Entries leave as 16-byte vector stores.
+  //   k = 1: B runs over the sites of the class;  k = 2: block = first site p, B = second-class sites
+  //   above p;  k = 3: block = MIDDLE site p, A = first-class sites below p, B = third-class sites above.
+  uint64_t S = 0, A = 1, B = 1, Bf = 1;
+  uint32_t pat_ap = 0, sb = 0, bmask = 0;
+  int k = 0, p = 0;
+  uint32_t q = 0;      // rank of the current entry inside its group (only k = 4 needs it per entry)
+  auto next_block = [&]() -> bool {  // advance to the next non-empty block of group j
+    while (S) {
+      p = __ffsll((long long)S) - 1;
+      S &= S - 1;
+      const uint64_t Af = k == 3 ? (s_cm[j] & below(p)) : 1ull;
+      Bf = (k == 3 ? cm_of(2, j) : cm_of(1, j)) & above(p);
+      if (Af && Bf) {
+        A = Af;
+        B = Bf;
+        pat_ap = k == 3 ? ((uint32_t)__ffsll((long long)A) | ((uint32_t)(p + 1) << 8)) : (uint32_t)(p + 1);
+        return true;
       }
     }
-    uint32_t pat;
-    if (k == 4) {
-      pat = block_entry(4, p, q, c0, c1, c2, c3);
-    } else {
-      // k = 3: A = first-class sites below p, B = third-class sites above p;  k = 2: B = second-class
-      // sites above p;  k = 1 (and 0): B = the sites of the class (one dummy site for k = 0)
-      const uint64_t A = k == 3 ? (c0 & below(p)) : 0ull;
-      const uint64_t B = k == 3 ? (c2 & above(p)) : (k == 2 ? (c1 & above(p)) : c0);
-      const uint32_t nb = (uint32_t)__popcll(B);
-      const uint32_t a = k == 3 ? q / nb : 0u;
-      const uint32_t b = q - a * nb;
-      const uint32_t sb = (uint32_t)select_bit(B, b) + 1u;
-      const uint32_t sa = (uint32_t)select_bit(A | (1ull << 63), a) + 1u;  // the guard bit keeps k < 3 in range
-      pat = k == 3 ? (sa | ((uint32_t)(p + 1) << 8) | (sb << 16))
-                   : (k == 2 ? ((uint32_t)(p + 1) | (sb << 8)) : (k == 1 ? sb : 0u));
+    return false;
+  };
+  auto init_group = [&]() {  // iterator at entry 0 of group j
+    k = s.k[j];
+    q = 0;
+    S = 0; A = 1; B = Bf = 1; pat_ap = 0; sb = 0; bmask = 0;
+    if (k == 1) {
+      B = Bf = s_cm[j];
+      bmask = 0xffu;
+    } else if (k == 2 || k == 3) {
+      sb = 8u * (uint32_t)(k - 1);
+      bmask = 0xffu;
+      S = k == 2 ? s_cm[j] : cm_of(1, j);
+      if (!next_block()) { A = 1; B = Bf = 1; }
+    }  // k = 0, k = 4 (un-ranked per entry) and long groups (written by K6l): dummy iterator
+  };
+  auto step = [&]() {
+    B &= B - 1;
+    if (!B) {
+      A &= A - 1;
+      if (A) {
+        B = Bf;
+        if (k == 3) pat_ap = (uint32_t)__ffsll((long long)A) | ((uint32_t)(p + 1) << 8);
+      } else if (!next_block()) {
+        A = 1; B = Bf = 1;
+      }
     }
-    const uint64_t e = e0 + i;
-    e_mass[e] = s.mass[j];
-    e_base[e] = s.base[j];
-    e_pat[e] = pat;
+  };
+  uint32_t rem;  // entries of group j from the current one on
+  {
+    const int32_t qs = (int32_t)i0 - s.off[j];
+    rem = (uint32_t)(s.off[j + 1] - (int32_t)i0);
+    init_group();
+    q = (uint32_t)qs;
+    if (qs > 0 && k >= 1 && k <= 3) {
+      if (k == 1) {
+        B = Bf & ~below(select_bit(Bf, q));
+      } else {
+        const uint64_t c0 = s_cm[j], c1 = cm_of(1, j), c2 = cm_of(2, j);
+        const uint64_t sites = block_sites(k, c0, c1);
+        uint32_t qq = q;
+        const uint32_t tab = s.tab[j];
+        if (tab != kNoTable) {  // last block whose first entry is <= q
+          uint32_t lo = 0, hi = (uint32_t)__popcll(sites);
+          while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s.cum[tab + mid] <= qq) lo = mid; else hi = mid;
+          }
+          p = s.pos[tab + lo];
+          qq -= s.cum[tab + lo];
+        } else {
+          for (uint64_t m = sites; m; m &= m - 1) {
+            p = __ffsll((long long)m) - 1;
+            const uint32_t w = block_size(k, p, c0, c1, c2, 0ull);
+            if (qq < w) break;
+            qq -= w;
+          }
+        }
+        S = sites & above(p);
+        const uint64_t Af = k == 3 ? (c0 & below(p)) : 1ull;
+        Bf = (k == 3 ? c2 : c1) & above(p);
+        const uint32_t nb = (uint32_t)__popcll(Bf);
+        const uint32_t ai = k == 3 ? qq / nb : 0u;
+        const uint32_t bi = qq - ai * nb;
+        A = k == 3 ? (Af & ~below(select_bit(Af, ai))) : 1ull;
+        B = Bf & ~below(select_bit(Bf, bi));
+        pat_ap = k == 3 ? ((uint32_t)__ffsll((long long)A) | ((uint32_t)(p + 1) << 8)) : (uint32_t)(p + 1);
+      }
+    }
+  }
+  double om[ET_PER];
+  uint32_t ob[ET_PER], op[ET_PER];
+  const uint32_t n_mine = min((uint32_t)ET_PER, tile_n - i0);
+#pragma unroll
+  for (int e = 0; e < ET_PER; ++e) {
+    if ((uint32_t)e < n_mine) {
+      om[e] = s.mass[j];
+      ob[e] = s.base[j];
+      op[e] = k == 4 ? block_entry_k4(j, q) : (pat_ap | (((uint32_t)__ffsll((long long)B) & bmask) << sb));
+      if (--rem == 0) {
+        ++j;  // the next group starts at the next entry (j <= ngrp: off[ngrp] is staged)
+        if ((uint32_t)e + 1 < n_mine) {
+          rem = (uint32_t)(s.off[j + 1] - s.off[j]);
+          init_group();
+        }
+      } else {
+        ++q;
+        step();
+      }
+    }
+  }
+  const uint64_t e = e0 + i0;
+  if (n_mine == (uint32_t)ET_PER) {
+    static_assert(ET_PER == 4, "vector stores below are written for 4 entries per thread");
+    reinterpret_cast<double2*>(e_mass + e)[0] = make_double2(om[0], om[1]);
+    reinterpret_cast<double2*>(e_mass + e)[1] = make_double2(om[2], om[3]);
+    *reinterpret_cast<uint4*>(e_base + e) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+    *reinterpret_cast<uint4*>(e_pat + e) = make_uint4(op[0], op[1], op[2], op[3]);
+  } else {
+    for (uint32_t x = 0; x < n_mine; ++x) {
+      e_mass[e + x] = om[x];
+      e_base[e + x] = ob[x];
+      e_pat[e + x] = op[x];
+    }
   }
 }
 
@@ -674,13 +758,9 @@ void launch_grp_expand(const uint8_t* d_res, const DevTables* d_tb, const Digest
                        uint32_t* long_count, uint32_t long_cap, uint32_t* d_err, cudaStream_t s) {
   if (n_groups == 0 || n_entries == 0) return;
   const uint64_t n_tiles = (n_entries + kExpTile - 1) / kExpTile;
-  static const bool attr_set = [] {
-    cudaFuncSetAttribute(grp_expand_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(sizeof(ExpTabSmem) + (size_t)DBI_MAX_MODS_PER_PEP * EX_GMAX * 8));
-    return true;
-  }();
-  (void)attr_set;
   const size_t smem = sizeof(ExpTabSmem) + (size_t)cfg.max_mods * EX_GMAX * 8;
+  // function attributes are per device: set before every launch (a process may hold handles on several GPUs)
+  DBI_CUDA(cudaFuncSetAttribute(grp_expand_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   DBI_LAUNCH(grp_expand_tab_kernel, (unsigned)n_tiles, ET_THREADS, smem, s, cfg, cmask, d_res, d_tb, u_gpos, u_len, skey,
              spay, eoff, tile_first, n_entries, base_bits, e_mass, e_base, e_pat, long_list, long_count, long_cap, d_err);
   if (long_cap > 0) {

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DBI_ABI_VERSION 1
+#define DBI_ABI_VERSION 2
 
 /* ---- status codes (0 = OK, negative = error) -----------------------------
  * The shim maps them onto the reference's two exception types:
@@ -86,6 +86,19 @@ typedef struct dbi_params {
   int32_t n_mods;
   int32_t max_mods_per_peptide; /* max_num_differential_AA_per_mod */
   dbi_mod mods[DBI_MAX_MODS];
+
+  /* Peptide filters applied while a start position is walked.
+   * mandatoryInternalAAs (DBIndexer.java:248,334-344 + DBIndexStoreSQLiteMult.java:245-263): a
+   * qualifying window with none of these residues ENDS the start; one that has them only as its
+   * last residue is skipped.  has_mandatory = "the array is not null" (an empty array is legal in
+   * the reference and then nothing qualifies).
+   * PeptideFilterByMaxOccurrencies (util/PeptideFilterByMaxOccurrencies.java:22-34, break at
+   * DBIndexer.java:310-313): the start ends once residue filter_aa occurs more than filter_max times. */
+  uint8_t is_mandatory[256];
+  int32_t has_mandatory;
+  int32_t filter_aa;      /* residue code, 0 = no filter */
+  int32_t filter_max;
+  int32_t _pad_filters;
 
   /* Test/diagnostic switches (no reference counterpart). */
   int32_t keep_emitted;   /* keep the raw emitted records for dbi_debug_emitted() */

@@ -87,8 +87,32 @@ inline bool check_cleavage(const dbi_params& p, const std::string& s, int start,
   return p.semi ? (n_ok || c_ok) : (n_ok && c_ok);
 }
 
-// DBIndexer.cutSeq (DBIndexer.java:237-405), bracketed-formula PTMs (:288-303),
-// peptideFilter (:310-313) and mandatoryInternalAAs (:334-344) excluded.
+// PeptideFilterByMaxOccurrencies.isValid (util/PeptideFilterByMaxOccurrencies.java:22-34).
+inline bool filter_is_valid(const dbi_params& p, const char* pep, int n) {
+  if (p.filter_aa <= 0) return true;  // peptideFilter == null
+  int matches = 0;
+  for (int i = 0; i < n; ++i)
+    if ((uint8_t)pep[i] == (uint8_t)p.filter_aa) {
+      ++matches;
+      if (matches > p.filter_max) return false;
+    }
+  return true;
+}
+
+// DBIndexStoreSQLiteMult.filterSequence (DBIndexStoreSQLiteMult.java:245-268): true = INCLUDE.
+inline bool store_filter_include(const dbi_params& p, double mass, const char* pep, int n) {
+  bool any_mandatory = false;
+  for (int c = 0; c < 256; ++c) any_mandatory |= p.is_mandatory[c] != 0;
+  if (p.has_mandatory && any_mandatory) {  // "!= null && length > 0"
+    for (int i = 0; i + 1 < n; ++i)        // the last AA, the cleavage site, is excluded (:255-256)
+      if (p.is_mandatory[(uint8_t)pep[i]]) return true;
+    return false;  // SKIP
+  }
+  return !(p.max_mass < mass || p.min_mass > mass);
+}
+
+// DBIndexer.cutSeq (DBIndexer.java:237-405); bracketed-formula PTMs (:288-303) excluded (they need
+// the un-vendored FormulaCalculator and rewrite the protein string).
 void cut_seq(const dbi_params& p, const std::string& seq, int32_t prot_id, std::vector<Rec>& out) {
   const int length = (int)seq.size();
   const int max_mc = p.max_missed;
@@ -104,14 +128,21 @@ void cut_seq(const dbi_params& p, const std::string& seq, int32_t prot_id, std::
       pep_size++;
       const uint8_t c = (uint8_t)seq[end];
       prec = prec + p.residue_mass[c];           // :306-308
+      if (!filter_is_valid(p, seq.data() + start, pep_size)) break;  // :310-313
       if (p.is_enzyme[c]) mc++;                  // :314-316
       if (check_cleavage(p, seq, start, end)) {  // :318-320
         if (mc > max_mc) break;                  // :322-324
         if (prec > p.max_mass) break;            // :327-329
         if (pep_size >= p.min_len && prec >= p.min_mass) {  // :331
-          // indexStore.filterSequence (DBIndexStoreSQLiteMult.java:245-268) repeats the
-          // mass gate; always INCLUDE here.  addSequence(mass, start, curSeqI, ...) :388
-          out.push_back(Rec{prec, start, pep_size, prot_id});
+          if (p.has_mandatory) {  // mandatoryInternalAAs != null, :334-344
+            bool found = false;
+            for (int i = 0; i < pep_size; ++i)
+              if (p.is_mandatory[(uint8_t)seq[start + i]]) found = true;
+            if (!found) break;
+          }
+          // indexStore.filterSequence (:347); SKIP_PROTEIN_START is never returned by this store
+          if (store_filter_include(p, prec, seq.data() + start, pep_size))
+            out.push_back(Rec{prec, start, pep_size, prot_id});  // addSequence(mass, start, curSeqI, ...) :388
         }
       }
       ++end;  // :394
@@ -425,6 +456,48 @@ double orc_calculate_mass(void* h, const uint8_t* seq, uint64_t len) {
 // IndexUtil.getToleranceInDalton (util/IndexUtil.java:238-240), Constants.ONE_MILLION
 double orc_tolerance_in_dalton(double actual_mass, double ppm) {
   return actual_mass * (1 - 1 / (ppm / 1000000.0 + 1));
+}
+
+// DBIndexer.getSequencesUsingPPMTolerance (DBIndexer.java:787-844) for one precursor mass: the
+// Dalton query, then exact-mass probes at upperBound, upperBound + PRECISION, ... while the PPM
+// window of the probe still reaches down to the precursor mass and the probe finds something.
+// Writes the entry indices of the result in list order (first query, then new ones per probe;
+// `sequences.contains` is identity of the index entry here); returns how many (<= cap kept).
+uint64_t orc_query_ppm(void* h, double precursor_mass, double ppm, uint64_t* out_idx, uint64_t cap,
+                       uint64_t* n_probes) {
+  std::vector<uint64_t> seqs;
+  auto get = [&](double m, double tol, std::vector<uint64_t>& dst) {  // indexStore.getSequences(m, tol)
+    double lo = m - tol, hi = m + tol;
+    if (lo < 0.0) lo = 0.0;  // Mult:324-329
+    uint64_t b = 0, c = 0;
+    int contig = 1;
+    orc_query(h, &lo, &hi, 1, &b, &c, &contig);
+    for (uint64_t i = 0; i < c; ++i) dst.push_back(b + i);
+  };
+  const double tol = orc_tolerance_in_dalton(precursor_mass, ppm);  // :790
+  get(precursor_mass, tol, seqs);                                    // :799
+  double upper = precursor_mass + tol;                               // :808
+  uint64_t probes = 0;
+  while (true) {
+    const double tol2 = orc_tolerance_in_dalton(upper, ppm);  // :812
+    const double lower_of_upper = upper - tol2;               // :813
+    if (lower_of_upper < precursor_mass) {                    // :814
+      std::vector<uint64_t> s2;
+      get(upper, 0.0, s2);                                    // :815
+      ++probes;
+      if (s2.empty()) break;                                  // :816-817
+      for (uint64_t e : s2)
+        if (std::find(seqs.begin(), seqs.end(), e) == seqs.end()) seqs.push_back(e);  // :821-826
+    } else {
+      break;
+    }
+    const double next = upper + 1e-6;  // Constants.PRECISION, :833
+    if (next == upper) break;
+    upper = next;
+  }
+  for (uint64_t i = 0; i < seqs.size() && i < cap; ++i) out_idx[i] = seqs[i];
+  if (n_probes) *n_probes = probes;
+  return seqs.size();
 }
 
 // Interval.massRangeToInterval (Interval.java:27-38) + MergeIntervals.mergeIntervals

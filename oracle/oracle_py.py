@@ -42,6 +42,8 @@ def load():
     lib.orc_emitted.argtypes = [vp, vp, vp, vp, vp]
     lib.orc_entries.argtypes = [vp, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp, vp, vp]
     lib.orc_query.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, C.POINTER(C.c_int)]
+    lib.orc_query_ppm.argtypes = [vp, C.c_double, C.c_double, vp, C.c_uint64, u64p]
+    lib.orc_query_ppm.restype = C.c_uint64
     lib.orc_calculate_mass.argtypes = [vp, C.c_char_p, C.c_uint64]
     lib.orc_calculate_mass.restype = C.c_double
     lib.orc_tolerance_in_dalton.argtypes = [C.c_double, C.c_double]
@@ -133,6 +135,14 @@ class Oracle:
         self.lib.orc_set_threads(self.threads)
         self.lib.orc_query(self.h, _p(lo), _p(hi), nq, _p(b), _p(c), C.byref(contig))
         return b, c, bool(contig.value)
+
+    def query_ppm(self, precursor_mass: float, ppm: float):
+        """getSequencesUsingPPMTolerance restated: entry indices in result-list order, number of probes."""
+        probes = C.c_uint64()
+        n = self.lib.orc_query_ppm(self.h, precursor_mass, ppm, None, 0, C.byref(probes))
+        idx = np.empty(n, np.uint64)
+        self.lib.orc_query_ppm(self.h, precursor_mass, ppm, _p(idx), n, C.byref(probes))
+        return idx, probes.value
 
     def calculate_mass(self, seq: bytes) -> float:
         return self.lib.orc_calculate_mass(self.h, seq, len(seq))

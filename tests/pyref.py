@@ -23,13 +23,20 @@ def digest_set(p, seqs):
     residue masses are >= 0 both the mass and the missed-cleavage count are monotone in `end`, so
     the reference's break conditions are equivalent to plain per-window predicates."""
     out = []
+    filt = chr(p.filter_aa) if p.filter_aa > 0 else None
     for pid, s in enumerate(seqs):
         L = len(s)
         enz = [bool(p.is_enzyme[ord(c)]) for c in s]
         nocut = [bool(p.is_nocut[ord(c)]) for c in s]
+        mand = [bool(p.has_mandatory and p.is_mandatory[ord(c)]) for c in s]
         for start in range(L):
             n_ok = start == 0 or (enz[start - 1] and not nocut[start])
+            dead = False  # a qualifying window without any mandatory residue ended this start (DBIndexer.java:334-344)
             for end in range(start, L):
+                # PeptideFilterByMaxOccurrencies: the occurrence count is monotone in `end`, so the
+                # reference's break is a per-window predicate
+                if filt is not None and s[start:end + 1].count(filt) > p.filter_max:
+                    continue
                 c_ok = end == L - 1 or (enz[end] and not nocut[end + 1])
                 if not ((n_ok or c_ok) if p.semi else (n_ok and c_ok)):
                     continue
@@ -41,6 +48,14 @@ def digest_set(p, seqs):
                 m = seq_mass(p, s[start:end + 1])
                 if m < p.min_mass or m > p.max_mass:
                     continue
+                if p.has_mandatory:
+                    if dead:
+                        continue
+                    if not any(mand[start:end + 1]):
+                        dead = True
+                        continue
+                    if not any(mand[start:end]):  # only as the last residue: SKIP (DBIndexStoreSQLiteMult.java:245-263)
+                        continue
                 out.append((pid, start, ln, m))
     return out
 

@@ -249,6 +249,63 @@ def test_property_digest(seqs, mc, semi, nocut):
     assert np.array_equal(bits(e["mass"]), bits([m for *_, m in exp]))
 
 
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.text(aa, min_size=0, max_size=60), min_size=1, max_size=4), st.integers(0, 4), st.booleans(),
+       st.sampled_from([None, "", "K", "KR", "C"]), st.sampled_from([None, ("K", 0), ("K", 1), ("L", 2)]))
+def test_property_digest_filters(seqs, mc, semi, mandatory, pep_filter):
+    """mandatoryInternalAAs (break / skip semantics) and PeptideFilterByMaxOccurrencies; an
+    empty (non-null) mandatory array emits nothing, like the reference."""
+    kw = dict(max_missed=mc, semi=int(semi), min_mass=400.0, max_mass=3000.0)
+    if mandatory is not None:
+        kw["mandatory_internal"] = mandatory
+    if pep_filter is not None:
+        kw["peptide_filter"] = pep_filter
+    p = dbi.default_params(**kw)
+    o = run_oracle(p, seqs)
+    exp = pyref.digest_set(p, seqs)
+    e = o.emitted()
+    assert [(int(a), int(b), int(c)) for a, b, c in zip(e["prot"], e["off"], e["len"])] == [(a, b, c) for a, b, c, _ in exp]
+    assert np.array_equal(bits(e["mass"]), bits([m for *_, m in exp]))
+    if mandatory == "":
+        assert len(exp) == 0
+
+
+def test_kat_mandatory_internal_and_filter():
+    """Hand-derived from DBIndexer.java:310-313,334-344 and DBIndexStoreSQLiteMult.java:245-263.
+    Protein AAAAAAKAAAAAAR, trypsin, 2 missed cleavages, min mass 300: windows from start 0 are
+    AAAAAAK (K only as the LAST residue: found, but the store SKIPs it) and AAAAAAKAAAAAAR (K internal:
+    kept); start 7 gives AAAAAAR -- no K at all, so the start ends there."""
+    p = dbi.default_params(mandatory_internal="K", min_mass=300.0)
+    o = run_oracle(p, ["AAAAAAKAAAAAAR"])
+    e = o.emitted()
+    assert [(int(a), int(b)) for a, b in zip(e["off"], e["len"])] == [(0, 14)]
+    # without the mandatory set: all three windows
+    o2 = run_oracle(dbi.default_params(min_mass=300.0), ["AAAAAAKAAAAAAR"])
+    e2 = o2.emitted()
+    assert [(int(a), int(b)) for a, b in zip(e2["off"], e2["len"])] == [(0, 7), (0, 14), (7, 7)]
+    # occurrence filter A <= 6: the 14-residue window holds 12 A, the walk from start 0 ends at the 7th A
+    o3 = run_oracle(dbi.default_params(peptide_filter=("A", 6), min_mass=300.0), ["AAAAAAKAAAAAAR"])
+    e3 = o3.emitted()
+    assert [(int(a), int(b)) for a, b in zip(e3["off"], e3["len"])] == [(0, 7), (7, 7)]
+
+
+def test_ppm_probe_loop_restatement():
+    """DBIndexer.getSequencesUsingPPMTolerance (DBIndexer.java:787-844) restated in the oracle: the result
+    starts with the Dalton answer and only ever grows by entries at the probed exact masses."""
+    p = dbi.default_params(min_mass=400.0, max_mass=3000.0)
+    res, off = synth.synth_proteome(30, 4242, median_len=150, min_len=20)
+    seqs = [res[int(off[i]):int(off[i + 1])].tobytes().decode() for i in range(len(off) - 1)]
+    o = run_oracle(p, seqs)
+    ent = o.entries()
+    for m in ent["mass"][:: max(1, len(ent["mass"]) // 25)]:
+        for ppm in (5.0, 50.0):
+            idx, probes = o.query_ppm(float(m) * (1 - 2e-6), ppm)
+            tol = tolerance_in_dalton(float(m) * (1 - 2e-6), ppm)
+            b, c, _ = o.query(np.array([max(0.0, float(m) * (1 - 2e-6) - tol)]), np.array([float(m) * (1 - 2e-6) + tol]))
+            assert idx[:int(c[0])].tolist() == list(range(int(b[0]), int(b[0] + c[0])))
+            assert len(set(idx.tolist())) == len(idx) and probes >= 1
+
+
 def test_oracle_matches_a_sqlite_restatement_of_the_reference_store():
     """The oracle's rows / merge / query against tests/sqlite_ref.py: the reference's table, records
     and SQL on a real SQLite B-tree, fed with the same addSequence calls."""

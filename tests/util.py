@@ -21,6 +21,11 @@ PARAM_SETS = {
     "three_classes_k2": dict(diff_mods=[("M", 15.9949), ("ST", 79.96633), ("K", 42.010565)], max_mods_per_peptide=2),
     "five_classes_k2": dict(diff_mods=[("M", 15.9949), ("ST", 79.96633), ("K", 42.010565), ("N", 0.984016),
                                        ("Q", 0.98)], max_mods_per_peptide=2, max_missed=1),
+    # the cross-linker parameter set (DBIndexImpl.java:443-491) and the occurrence filter
+    "mandatory_K_no_h2o": dict(add_h2o_proton=0, mandatory_internal="K", max_missed=3, min_mass=500.0),
+    "mandatory_KC_semi": dict(semi=1, mandatory_internal="KC", max_missed=1),
+    "filter_K2_mods": dict(peptide_filter=("K", 2), max_missed=3, diff_mods=[("M", 15.9949)], max_mods_per_peptide=2),
+    "mandatory_filter": dict(mandatory_internal="K", peptide_filter=("L", 3), max_missed=4),
     "wide_mass_mod4": dict(min_mass=0.0, max_mass=8000.0, max_missed=1, diff_mods=[("W", 15.9949)],
                            max_mods_per_peptide=4),
 }
