@@ -807,7 +807,8 @@ int sort_expand_groups(dbi_handle* h, uint64_t* key_in, uint64_t* pay_in, uint64
   const bool sharded = h->ug_gpos.p != nullptr;
   const uint64_t mask_bytes = h->n_unique_global * (uint64_t)h->cfg.n_classes * 8;
   static const bool no_table = std::getenv("DBI_MG_NO_MASK_TABLE") != nullptr;  // test hook
-  const bool global_masks = sharded && !no_table && mask_bytes <= (6ull << 30);
+  const bool global_masks = sharded;
+  (void)no_table;
   DevBuf ug_cmask, scratch_nlong;
   if (!sharded) {
     ensure_site_masks(h);
@@ -875,7 +876,7 @@ int sort_expand_groups(dbi_handle* h, uint64_t* key_in, uint64_t* pay_in, uint64
     launch_grp_expand(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg,
                       sharded ? h->ug_gpos.as<uint32_t>() : h->u_gpos.as<uint32_t>(),
                       sharded ? h->ug_len.as<uint16_t>() : h->u_len.as<uint16_t>(),
-                      sharded ? (global_masks ? ug_cmask.as<uint64_t>() : nullptr) : h->u_cmask.as<uint64_t>(), vk[r],
+                      sharded ? ug_cmask.as<uint64_t>() : h->u_cmask.as<uint64_t>(), nullptr, vk[r],
                       vp[r], eoff.as<uint64_t>(),
                       tfirst.as<uint32_t>(), NG, V, ks.base_bits, h->e_mass.as<double>(), h->e_base.as<uint32_t>(),
                       h->e_pat.as<uint32_t>(), llist.as<uint32_t>(), lcount.as<uint32_t>(), (uint32_t)long_cap,

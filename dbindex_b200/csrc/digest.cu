@@ -127,7 +127,8 @@ __device__ __forceinline__ void at_pos(const TileCtx& cx, uint32_t pos, uint8_t*
 
 // The body of the reference's `for start` iteration (DBIndexer.java:256-395) for the
 // start at buffer position g.  F is called as emit(mass, len) for every record.
-template <typename F>
+// FILTERS = false compiles the two peptide filters out of the loop.
+template <bool FILTERS, typename F>
 __device__ __forceinline__ uint32_t walk_start(const TileCtx& cx, uint32_t g, const DigestCfg& cfg, uint32_t* err,
                                                F&& emit) {
   uint8_t inf;
@@ -149,14 +150,14 @@ __device__ __forceinline__ uint32_t walk_start(const TileCtx& cx, uint32_t g, co
   while (mass <= cfg.max_mass && !(inf & I_SEP)) {  // :284  (end < length  <=>  not a separator)
     ++len;                                          // pepSize++, :285
     mass = __dadd_rn(mass, m);                      // precMass = precMass + aaMass, :308
-    if ((inf & I_FILT) && ++n_filt > cfg.filt_max && cfg.filt_max >= 0) break;  // peptideFilter.isValid, :310-313
-    if (inf & I_ENZ) ++mc;                          // :314-316
+    if (FILTERS && (inf & I_FILT) && ++n_filt > cfg.filt_max && cfg.filt_max >= 0) break;  // peptideFilter.isValid, :310-313
+    mc += (inf >> 1) & 1;                           // isEnzyme(cur) -> intMisCleavageCount++, :314-316 (I_ENZ = 2)
     if (cok_any || (inf & I_COK)) {                 // cleavageStatus, :318-320
       if (mc > cfg.max_mc) break;                   // :322-324
       if (mass > cfg.max_mass) break;               // :327-329
       if ((int)len >= cfg.min_len && mass >= cfg.min_mass) {  // :331
         bool include = true;
-        if (cfg.mand_on) {
+        if (FILTERS && cfg.mand_on) {
           if (n_mand == 0 && !(inf & I_MAND)) break;  // none in the whole window: :334-344
           include = n_mand > 0;                       // only as the last residue: SKIP (Mult:245-263)
         }
@@ -170,7 +171,7 @@ __device__ __forceinline__ uint32_t walk_start(const TileCtx& cx, uint32_t g, co
         }
       }
     }
-    if (inf & I_MAND) ++n_mand;
+    if (FILTERS && (inf & I_MAND)) ++n_mand;
     ++pos;  // ++end, :394
     at_pos(cx, pos, &inf, &m);
   }
@@ -209,6 +210,7 @@ __device__ __forceinline__ void stage_tile(TileSmem& s, const uint8_t* __restric
 // Warp-cooperative cleavage-site scan: the CTA compacts the live starts of its tile (for trypsin
 // ~11 % of the residues can start a peptide), one lane walks each, and the per-start counts go
 // back to HBM for K4.
+template <bool FILTERS>
 __global__ void __launch_bounds__(DG_THREADS)
     digest_count_kernel(const uint8_t* __restrict__ res, uint32_t res_end, uint64_t res_alloc,
                         const DevTables* __restrict__ tb, DigestCfg cfg, uint32_t tile0,
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(DG_THREADS)
   uint32_t cnt = 0;
   for (uint32_t i = t; i < total; i += DG_THREADS) {
     const uint32_t l = s.list[i];
-    const uint32_t c = walk_start(cx, w0 + 1 + l, cfg, err, [](double, uint32_t) {});
+    const uint32_t c = walk_start<FILTERS>(cx, w0 + 1 + l, cfg, err, [](double, uint32_t) {});
     s.cnt8[l] = (uint8_t)(c < 255u ? c : 255u);
     cnt += c;
   }
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(DG_THREADS)
 }
 
 // ---- K4 -----------------------------------------------------------------------------
+template <bool FILTERS>
 __global__ void __launch_bounds__(DG_THREADS)
     digest_emit_kernel(const uint8_t* __restrict__ res, uint32_t res_end, uint64_t res_alloc,
                        const DevTables* __restrict__ tb, DigestCfg cfg, uint32_t tile0,
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(DG_THREADS)
 #pragma unroll
     for (int k = 0; k < DG_SPT; ++k) {
       c[k] = ((k < 4 ? packed.x : packed.y) >> (8 * (k & 3))) & 0xffu;
-      if (c[k] == 255u) c[k] = walk_start(cx, w0 + 1 + t * DG_SPT + k, cfg, err, [](double, uint32_t) {});
+      if (c[k] == 255u) c[k] = walk_start<FILTERS>(cx, w0 + 1 + t * DG_SPT + k, cfg, err, [](double, uint32_t) {});
       n_emit += c[k] ? 1u : 0u;
       sum += c[k];
       if (s.info[1 + t * DG_SPT + k] & I_SEP) {
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(DG_THREADS)
     // protein of this start = separators at positions <= g, minus one
     const uint32_t prot = zbase + s_zero[i] - 1u;
     uint64_t o = tile_off + s_off[i];
-    walk_start(cx, g, cfg, err, [&](double m, uint32_t len) {
+    walk_start<FILTERS>(cx, g, cfg, err, [&](double m, uint32_t len) {
       o_mass[o] = (uint64_t)__double_as_longlong(m);
       o_gpos[o] = g;
       o_prot[o] = prot;
@@ -390,8 +393,12 @@ void launch_digest_count(const uint8_t* d_res, uint32_t res_end, uint64_t res_al
                          const DigestCfg& cfg, uint32_t tile0, uint32_t ntiles, uint8_t* d_start_cnt,
                          uint32_t* d_tile_counts, uint32_t* d_err, cudaStream_t s) {
   if (ntiles == 0) return;
-  DBI_LAUNCH(digest_count_kernel, ntiles, DG_THREADS, 0, s, d_res, res_end, res_alloc, d_tb, cfg, tile0, d_start_cnt,
-             d_tile_counts, d_err);
+  if (cfg.mand_on || cfg.filt_max >= 0)
+    DBI_LAUNCH(digest_count_kernel<true>, ntiles, DG_THREADS, 0, s, d_res, res_end, res_alloc, d_tb, cfg, tile0,
+               d_start_cnt, d_tile_counts, d_err);
+  else
+    DBI_LAUNCH(digest_count_kernel<false>, ntiles, DG_THREADS, 0, s, d_res, res_end, res_alloc, d_tb, cfg, tile0,
+               d_start_cnt, d_tile_counts, d_err);
 }
 
 void launch_scan_u32_to_u64(const uint32_t* d_in, uint64_t n, uint64_t* d_offs, cudaStream_t s) {
@@ -403,8 +410,12 @@ void launch_digest_emit(const uint8_t* d_res, uint32_t res_end, uint64_t res_all
                         const uint64_t* d_tile_offs, const uint32_t* d_pstart, uint32_t n_prot, uint64_t* o_mass,
                         uint32_t* o_gpos, uint32_t* o_prot, uint16_t* o_len, uint32_t* d_err, cudaStream_t s) {
   if (ntiles == 0) return;
-  DBI_LAUNCH(digest_emit_kernel, ntiles, DG_THREADS, 0, s, d_res, res_end, res_alloc, d_tb, cfg, tile0, d_start_cnt,
-             d_tile_offs, d_pstart, n_prot, o_mass, o_gpos, o_prot, o_len, d_err);
+  if (cfg.mand_on || cfg.filt_max >= 0)
+    DBI_LAUNCH(digest_emit_kernel<true>, ntiles, DG_THREADS, 0, s, d_res, res_end, res_alloc, d_tb, cfg, tile0,
+               d_start_cnt, d_tile_offs, d_pstart, n_prot, o_mass, o_gpos, o_prot, o_len, d_err);
+  else
+    DBI_LAUNCH(digest_emit_kernel<false>, ntiles, DG_THREADS, 0, s, d_res, res_end, res_alloc, d_tb, cfg, tile0,
+               d_start_cnt, d_tile_offs, d_pstart, n_prot, o_mass, o_gpos, o_prot, o_len, d_err);
 }
 
 }  // namespace dbi

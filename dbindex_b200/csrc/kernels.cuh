@@ -113,14 +113,14 @@ void launch_grp_extract_cnt(const uint64_t* pay, uint64_t n, uint32_t* cnt, cuda
 void launch_grp_tile_first(const uint64_t* eoff, uint64_t n_groups, uint64_t n_entries, uint32_t* first,
                            cudaStream_t s);
 // entries of the sorted groups; groups of long peptides are listed in long_list and written by a
-// second kernel (launched when long_cap > 0).  Payloads name peptides by global id.  cmask ==
-// nullptr (sharded build): u_gpos / u_len are the replicated global tables and the site masks
-// are rebuilt from the residues.
+// second kernel (launched when long_cap > 0).  The payload's peptide field is a ROW of cmask /
+// u_gpos / u_len; gid_tab (sharded build: rows are arrival slots of the group exchange) maps a row
+// to the peptide's global id, nullptr = the row is the id.
 void launch_grp_expand(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const uint32_t* u_gpos,
-                       const uint16_t* u_len, const uint64_t* cmask, const uint64_t* skey, const uint64_t* spay,
-                       const uint64_t* eoff, const uint32_t* tile_first, uint64_t n_groups, uint64_t n_entries,
-                       uint64_t base_bits, double* e_mass, uint32_t* e_base, uint32_t* e_pat, uint32_t* long_list,
-                       uint32_t* long_count, uint32_t long_cap, uint32_t* d_err, cudaStream_t s);
+                       const uint16_t* u_len, const uint64_t* cmask, const uint32_t* gid_tab, const uint64_t* skey,
+                       const uint64_t* spay, const uint64_t* eoff, const uint32_t* tile_first, uint64_t n_groups,
+                       uint64_t n_entries, uint64_t base_bits, double* e_mass, uint32_t* e_base, uint32_t* e_pat,
+                       uint32_t* long_list, uint32_t* long_count, uint32_t long_cap, uint32_t* d_err, cudaStream_t s);
 
 // ---- K9/K10 query ----------------------------------------------------------------
 void launch_query(const double* e_mass, uint64_t n_entries, const double* lo, const double* hi, uint64_t nq,

@@ -288,33 +288,45 @@ __device__ __forceinline__ int select_bit(uint64_t m, uint32_t r) {
 }
 
 constexpr int EX_GMAX = kExpTile + 1;  // groups that can overlap one tile (every group has >= 1 entry)
-constexpr uint8_t kLongGroup = 0xff;
+constexpr uint8_t kLongGroup = 0xff;   // peptide longer than 64 residues: K6l writes the group
+constexpr uint8_t kSlowGroup = 0xfe;   // k = 4, or the tile's list pool is full: every entry un-ranks from the masks
 
-// One thread per ENTRY with constant-time un-ranking.  The entries of a group are ordered by
-// BLOCKS that are product sets, so that a rank splits by one division:
-//   k = 1: the sites of the class, ascending;
-//   k = 2: block = first site i0;   entries = sites of the second class above i0;
-//   k = 3: block = MIDDLE site i1;  entries = (sites of the first class below i1) x (sites of the
-//          third class above i1), the third site running fastest;
-//   k = 4: block = second site i1;  entries = (first-class sites below i1) x (pairs i2 < i3 above i1).
+// One thread per ENTRY with constant, convergent work.  The entries of a group are ordered by BLOCKS
+// that are product sets:
+//   k = 1: one block, the sites of the class, ascending;
+//   k = 2: block = first site p;   entries = sites of the second class above p;
+//   k = 3: block = MIDDLE site p;  entries = (sites of the first class below p) x (sites of the
+//          third class above p), the third site running fastest;
+//   k = 4: block = second site p;  entries = (first-class sites below p) x (pairs i2 < i3 above p).
 // (The order of the entries INSIDE a group is free: they all have the same mass and peptide.)
-// Phase 1 stages the groups of the tile and, per group, the exclusive prefix sums of its block sizes
-// and the block sites in a shared pool; phase 3 finds the block by binary search, then selects bits.
+// Phase 1 (thread per group) turns the site masks of a group into byte LISTS of site positions in a
+// shared pool and appends one record per block that overlaps the tile; phase 2 max-scans the block
+// heads so that every entry knows its block; phase 3 (thread per entry) is then
+//   rank in block -> (a, b) by one multiplication -> two byte loads -> pattern -> three coalesced stores.
 constexpr int ET_THREADS = 256;
 constexpr int ET_PER = kExpTile / ET_THREADS;
-constexpr int ET_POOL = 3072;          // block-table slots shared by the groups of a tile
-constexpr uint16_t kNoTable = 0xffff;  // pool exhausted or group too large for 16-bit sums: scan on the fly
+constexpr int EP_POOL = 6144;  // bytes of site lists shared by the groups of a tile; pool[0] = 0 = "no site"
 
-struct ExpTabSmem {
+struct ExpBlk {    // 16 bytes, read with one LDS.128
+  int32_t start;   // tile-local entry of the block's first entry (may be negative)
+  uint16_t grp;    // tile-local group
+  uint16_t a0;     // pool index of the first-level list (0 = none)
+  uint16_t b0;     // pool index of the first last-level site of this block
+  uint8_t nb;      // last-level sites of this block
+  uint8_t p;       // block site
+  uint32_t k;      // class-sequence length, or kLongGroup / kSlowGroup
+};
+
+struct ExpSmem {
   double mass[EX_GMAX];
-  int32_t off[EX_GMAX + 1];
   uint32_t base[EX_GMAX];
-  uint16_t head[kExpTile];
-  uint16_t tab[EX_GMAX];       // first pool slot of the group's block table
-  uint16_t cum[ET_POOL];       // exclusive prefix sums of the block sizes
-  uint8_t pos[ET_POOL];        // site of the block
-  uint8_t k[EX_GMAX];
-  uint32_t pool_used;
+  uint32_t idx[EX_GMAX];      // row of the group's peptide in the mask table
+  uint32_t head[kExpTile];    // (entry << 16 | block slot) at block starts, max-scanned
+  ExpBlk blk[kExpTile];       // every listed block owns >= 1 entry of the tile
+  uint8_t pool[EP_POOL];
+  uint8_t seq[EX_GMAX];
+  uint32_t recip[65];         // ceil(2^20 / n): exact quotient for ranks < 4096
+  uint32_t nblk, pool_used;
   uint32_t scratch[ET_THREADS / 32 + 1];
 };
 
@@ -336,7 +348,7 @@ __device__ __forceinline__ uint32_t block_size(int k, int p, uint64_t c0, uint64
   return nl ? nl * pairs_above(p, c2, c3) : 0u;
 }
 
-// pattern of entry q of the block at site p
+// pattern of entry q of the block at site p, from the masks (slow path)
 __device__ __forceinline__ uint32_t block_entry(int k, int p, uint32_t q, uint64_t c0, uint64_t c1, uint64_t c2,
                                                 uint64_t c3) {
   if (k == 2) return (uint32_t)(p + 1) | ((uint32_t)(select_bit(c1 & above(p), q) + 1) << 8);
@@ -363,32 +375,31 @@ __device__ __forceinline__ uint32_t block_entry(int k, int p, uint32_t q, uint64
          ((uint32_t)(select_bit(r3, b) + 1) << 24);
 }
 
+// entry q of a whole group, from the masks (slow path: k = 4, or no room for the lists)
+__device__ __forceinline__ uint32_t group_entry_slow(int k, uint32_t q, uint64_t c0, uint64_t c1, uint64_t c2,
+                                                     uint64_t c3) {
+  if (k == 1) return (uint32_t)select_bit(c0, q) + 1u;
+  int p = 0;
+  for (uint64_t m = block_sites(k, c0, c1); m; m &= m - 1) {
+    p = __ffsll((long long)m) - 1;
+    const uint32_t w = block_size(k, p, c0, c1, c2, c3);
+    if (q < w) break;
+    q -= w;
+  }
+  return block_entry(k, p, q, c0, c1, c2, c3);
+}
+
+// cmask[row * C + c]: the site masks; row = the payload's peptide field.  gid_tab (sharded build: the
+// rows are arrival slots of the group exchange) maps a row to the peptide's global id, else row = id.
 __global__ void __launch_bounds__(ET_THREADS, 4)
-    grp_expand_tab_kernel(DigestCfg cfg, const uint64_t* __restrict__ cmask, const uint8_t* __restrict__ res,
-                          const DevTables* __restrict__ tb, const uint32_t* __restrict__ g_gpos,
-                          const uint16_t* __restrict__ g_len, const uint64_t* __restrict__ skey,
-                          const uint64_t* __restrict__ spay, const uint64_t* __restrict__ eoff,
-                          const uint32_t* __restrict__ tile_first, uint64_t n_entries, uint64_t base_bits,
-                          double* __restrict__ e_mass, uint32_t* __restrict__ e_base, uint32_t* __restrict__ e_pat,
+    grp_expand_tab_kernel(DigestCfg cfg, const uint64_t* __restrict__ cmask, const uint32_t* __restrict__ gid_tab,
+                          const uint64_t* __restrict__ skey, const uint64_t* __restrict__ spay,
+                          const uint64_t* __restrict__ eoff, const uint32_t* __restrict__ tile_first,
+                          uint64_t n_entries, uint64_t base_bits, double* __restrict__ e_mass,
+                          uint32_t* __restrict__ e_base, uint32_t* __restrict__ e_pat,
                           uint32_t* __restrict__ long_list, uint32_t* __restrict__ long_count, uint32_t long_cap,
                           uint32_t* err) {
-  extern __shared__ __align__(16) uint8_t ex_raw[];
-  ExpTabSmem& s = *reinterpret_cast<ExpTabSmem*>(ex_raw);
-  uint64_t* const s_cm = reinterpret_cast<uint64_t*>(ex_raw + sizeof(ExpTabSmem));  // [max_mods][EX_GMAX]
-  const int K = cfg.max_mods;
-  auto cm_of = [&](int l, uint32_t j) -> uint64_t { return l < K ? s_cm[l * EX_GMAX + j] : 0ull; };
-  // k = 4 (rare): every entry is un-ranked on its own
-  auto block_entry_k4 = [&](uint32_t j, uint32_t q) -> uint32_t {
-    const uint64_t c0 = s_cm[j], c1 = cm_of(1, j), c2 = cm_of(2, j), c3 = cm_of(3, j);
-    int p = 0;
-    for (uint64_t m = c1; m; m &= m - 1) {
-      p = __ffsll((long long)m) - 1;
-      const uint32_t w = block_size(4, p, c0, c1, c2, c3);
-      if (q < w) break;
-      q -= w;
-    }
-    return block_entry(4, p, q, c0, c1, c2, c3);
-  };
+  __shared__ __align__(16) ExpSmem s;
   const int C = cfg.n_classes;
   const int t = threadIdx.x;
   const uint64_t tile = blockIdx.x;
@@ -398,89 +409,115 @@ __global__ void __launch_bounds__(ET_THREADS, 4)
   const uint32_t ngrp = tile_first[tile + 1] - g0 + 1;
 
   for (int i = t; i < kExpTile; i += ET_THREADS) s.head[i] = 0;
-  if (t == 0) s.pool_used = 0;
-  // sharded build: the peptides of the groups live on other GPUs and have no mask table here; their
-  // masks are rebuilt from the (replicated) residues through the global (gpos, len) tables
-  __shared__ uint8_t s_cls[256];  // class + 1 of a modifiable residue, 0 otherwise
-  if (!cmask)
-    for (int i = t; i < 256; i += ET_THREADS)
-      s_cls[i] = (tb->flags[i] & kFlagDiffMod) ? (uint8_t)(tb->cls[i] + 1) : (uint8_t)0;
+  if (t <= 64) s.recip[t] = t ? ((1u << 20) + (uint32_t)t - 1u) / (uint32_t)t : 0u;
+  if (t == 0) {
+    s.nblk = 0;
+    s.pool_used = 1;
+    s.pool[0] = 0;
+  }
   __syncthreads();
-  // (1) stage the groups and their block tables
-  for (uint32_t j = t; j <= ngrp; j += ET_THREADS) {
+  // (1) one thread per group: site lists + block records
+  for (uint32_t j = t; j < ngrp; j += ET_THREADS) {
     const uint64_t g = (uint64_t)g0 + j;
-    const int64_t rel = (int64_t)eoff[g] - (int64_t)e0;
-    s.off[j] = (int32_t)rel;
-    if (j == ngrp) break;
+    const int64_t rel64 = (int64_t)eoff[g] - (int64_t)e0;
+    const int32_t rel = (int32_t)max(rel64, (int64_t)INT32_MIN / 2);
     const uint64_t pay = spay[g];
-    const uint32_t b = (uint32_t)(pay >> 32);
+    const uint32_t row = (uint32_t)(pay >> 32);
     const uint32_t seq = ((uint32_t)pay >> kGrpCntBits) & 31u;
-    const uint32_t cnt = (uint32_t)pay & kGrpCntMask;
     uint32_t pk;
     int k = pack_seq(seq, C, &pk);
     s.mass[j] = __longlong_as_double((long long)(skey[g] + base_bits));
-    s.base[j] = b;
-    uint16_t tab = kNoTable;
-    if (k > 0) {
-      uint64_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-      if (cmask) {
-        const uint64_t* cm = cmask + (uint64_t)b * (uint64_t)C;
-        c0 = cm[seq_class_at(pk, 0)];
-        c1 = k > 1 ? cm[seq_class_at(pk, 1)] : 0ull;
-        c2 = k > 2 ? cm[seq_class_at(pk, 2)] : 0ull;
-        c3 = k > 3 ? cm[seq_class_at(pk, 3)] : 0ull;
-      } else if (g_len[b] <= kMaskLen) {
-        const uint32_t gp = g_gpos[b], len = g_len[b];
-        const uint32_t q0 = (uint32_t)seq_class_at(pk, 0) + 1u, q1 = k > 1 ? (uint32_t)seq_class_at(pk, 1) + 1u : 0xffu;
-        const uint32_t q2 = k > 2 ? (uint32_t)seq_class_at(pk, 2) + 1u : 0xffu;
-        const uint32_t q3 = k > 3 ? (uint32_t)seq_class_at(pk, 3) + 1u : 0xffu;
-        for (uint32_t i = 0; i < len; ++i) {
-          const uint32_t x = s_cls[ld_res(res, gp + i)];
-          const uint64_t bit = 1ull << i;
-          if (x == q0) c0 |= bit;
-          if (x == q1) c1 |= bit;
-          if (x == q2) c2 |= bit;
-          if (x == q3) c3 |= bit;
-        }
-      }
-      s_cm[j] = c0;
-      if (K > 1) s_cm[EX_GMAX + j] = c1;
-      if (K > 2) s_cm[2 * EX_GMAX + j] = c2;
-      if (K > 3) s_cm[3 * EX_GMAX + j] = c3;
-      if (c0 == 0) {  // a peptide longer than 64 residues: K6l writes this group
-        k = kLongGroup;
-        if (rel >= 0 && rel < (int64_t)kExpTile) {
-          const uint32_t slot = atomicAdd(long_count, 1u);
-          if (slot < long_cap) long_list[slot] = (uint32_t)g; else atomicOr(err, kErrModPos);
-        }
-      } else if (k > 1 && cnt <= 0xffffu) {
-        const uint64_t sites = block_sites(k, c0, c1);
-        const uint32_t nb = (uint32_t)__popcll(sites);
-        const uint32_t at = atomicAdd(&s.pool_used, nb);
-        if (at + nb <= (uint32_t)ET_POOL) {
-          tab = (uint16_t)at;
-          uint32_t acc = 0, x = at;
-          for (uint64_t m = sites; m; m &= m - 1, ++x) {
-            const int p = __ffsll((long long)m) - 1;
-            s.cum[x] = (uint16_t)acc;
-            s.pos[x] = (uint8_t)p;
-            acc += block_size(k, p, c0, c1, c2, c3);
-          }
-        }
-      }
+    s.base[j] = gid_tab ? gid_tab[row] : row;
+    s.idx[j] = row;
+    s.seq[j] = (uint8_t)seq;
+    ExpBlk b;
+    b.start = rel; b.grp = (uint16_t)j; b.a0 = 0; b.b0 = 0; b.nb = 1; b.p = 0; b.k = (uint32_t)k;
+    auto append = [&](const ExpBlk& x) {
+      const uint32_t slot = atomicAdd(&s.nblk, 1u);  // < kExpTile: every listed block owns an entry of the tile
+      s.blk[slot] = x;
+      s.head[x.start > 0 ? x.start : 0] = ((uint32_t)(x.start > 0 ? x.start : 0) << 16) | slot;
+    };
+    if (k == 0) {
+      append(b);
+      continue;
     }
-    s.k[j] = (uint8_t)k;
-    s.tab[j] = tab;
-    if (rel > 0 && rel < (int64_t)kExpTile) s.head[rel] = (uint16_t)j;
+    const uint64_t* cm = cmask + (uint64_t)row * (uint64_t)C;
+    const int q0 = seq_class_at(pk, 0), q1 = k > 1 ? seq_class_at(pk, 1) : q0, q2 = k > 2 ? seq_class_at(pk, 2) : q0;
+    const uint64_t c0 = cm[q0];
+    const uint64_t c1 = k > 1 ? cm[q1] : 0ull;
+    const uint64_t c2 = k > 2 ? cm[q2] : 0ull;
+    if (c0 == 0) {  // a peptide longer than 64 residues: K6l writes this group
+      b.k = kLongGroup;
+      append(b);
+      if (rel >= 0 && rel < (int32_t)kExpTile) {
+        const uint32_t slot = atomicAdd(long_count, 1u);
+        if (slot < long_cap) long_list[slot] = (uint32_t)g; else atomicOr(err, kErrModPos);
+      }
+      continue;
+    }
+    // lists of the distinct classes of the sequence (a class used at two levels shares its list)
+    const uint32_t n0 = (uint32_t)__popcll(c0);
+    const uint32_t n1 = (k > 1 && q1 != q0) ? (uint32_t)__popcll(c1) : 0u;
+    const uint32_t n2 = (k > 2 && q2 != q0 && q2 != q1) ? (uint32_t)__popcll(c2) : 0u;
+    const uint32_t need = n0 + n1 + n2;
+    const uint32_t at = k == 4 ? (uint32_t)EP_POOL : atomicAdd(&s.pool_used, need);
+    if (at + need > (uint32_t)EP_POOL) {
+      b.k = kSlowGroup;
+      append(b);
+      continue;
+    }
+    uint32_t x = at;
+    for (uint64_t m = c0; m; m &= m - 1) s.pool[x++] = (uint8_t)__ffsll((long long)m);  // position + 1
+    const uint32_t l0 = at;
+    uint32_t l1 = l0, l2 = l0;
+    if (n1) {
+      l1 = x;
+      for (uint64_t m = c1; m; m &= m - 1) s.pool[x++] = (uint8_t)__ffsll((long long)m);
+    }
+    if (k > 2) {
+      l2 = q2 == q0 ? l0 : (q2 == q1 ? l1 : x);
+      if (n2)
+        for (uint64_t m = c2; m; m &= m - 1) s.pool[x++] = (uint8_t)__ffsll((long long)m);
+    }
+    if (k == 1) {
+      b.b0 = (uint16_t)l0;
+      b.nb = (uint8_t)n0;
+      append(b);
+      continue;
+    }
+    // k = 2: blocks over the first site;  k = 3: blocks over the middle site
+    const uint64_t sites = k == 2 ? c0 : c1;
+    const uint64_t cb = k == 2 ? c1 : c2;  // last-level class
+    const uint32_t lb = k == 2 ? l1 : l2;
+    const uint32_t nb_all = (uint32_t)__popcll(cb);
+    int32_t run = rel;
+    for (uint64_t m = sites; m && run < (int32_t)tile_n; m &= m - 1) {
+      const int p = __ffsll((long long)m) - 1;
+      const uint32_t nB = (uint32_t)__popcll(cb & above(p));
+      const uint32_t nA = k == 3 ? (uint32_t)__popcll(c0 & below(p)) : 1u;
+      const uint32_t sz = nA * nB;
+      if (sz == 0) continue;
+      if (run + (int32_t)sz > 0) {
+        b.start = run;
+        b.a0 = k == 3 ? (uint16_t)l0 : (uint16_t)0;
+        b.b0 = (uint16_t)(lb + nb_all - nB);  // the last nB sites of the list lie above p
+        b.nb = (uint8_t)nB;
+        b.p = (uint8_t)p;
+        append(b);
+      }
+      run += (int32_t)sz;
+    }
   }
   __syncthreads();
-  // (2) group of every thread's FIRST entry: max-scan of the heads (kept in registers)
-  const uint32_t i0 = (uint32_t)t * ET_PER;
-  uint32_t j;
+  // (2) inclusive max-scan of the heads: entry -> block slot
   {
+    uint32_t loc[ET_PER];
     uint32_t run = 0;
 #pragma unroll
-    for (int i = 0; i < ET_PER; ++i) run = max(run, (uint32_t)s.head[i0 + i]);
+    for (int i = 0; i < ET_PER; ++i) {
+      run = max(run, s.head[t * ET_PER + i]);
+      loc[i] = run;
+    }
     uint32_t inc = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -493,136 +530,36 @@ __global__ void __launch_bounds__(ET_THREADS, 4)
     for (int w = 0; w < (t >> 5); ++w) carry = max(carry, s.scratch[w]);
     const uint32_t prev = __shfl_up_sync(0xffffffffu, inc, 1);
     if (lane_id() > 0) carry = max(carry, prev);
-    j = max(carry, (uint32_t)s.head[i0]);
-  }
-  if (i0 >= tile_n) return;
-  // (3) every thread WALKS its ET_PER consecutive entries: the first one is un-ranked (block table
-  // + two bit-selects), the following ones cost a few mask operations each -- the iterator state
-  // (remaining block sites S, remaining first-level sites A, remaining last-level sites B) lives in
-  // registers.  Entries leave as 16-byte vector stores.
-  //   k = 1: B runs over the sites of the class;  k = 2: block = first site p, B = second-class sites
-  //   above p;  k = 3: block = MIDDLE site p, A = first-class sites below p, B = third-class sites above.
-  uint64_t S = 0, A = 1, B = 1, Bf = 1;
-  uint32_t pat_ap = 0, sb = 0, bmask = 0;
-  int k = 0, p = 0;
-  uint32_t q = 0;      // rank of the current entry inside its group (only k = 4 needs it per entry)
-  auto next_block = [&]() -> bool {  // advance to the next non-empty block of group j
-    while (S) {
-      p = __ffsll((long long)S) - 1;
-      S &= S - 1;
-      const uint64_t Af = k == 3 ? (s_cm[j] & below(p)) : 1ull;
-      Bf = (k == 3 ? cm_of(2, j) : cm_of(1, j)) & above(p);
-      if (Af && Bf) {
-        A = Af;
-        B = Bf;
-        pat_ap = k == 3 ? ((uint32_t)__ffsll((long long)A) | ((uint32_t)(p + 1) << 8)) : (uint32_t)(p + 1);
-        return true;
-      }
-    }
-    return false;
-  };
-  auto init_group = [&]() {  // iterator at entry 0 of group j
-    k = s.k[j];
-    q = 0;
-    S = 0; A = 1; B = Bf = 1; pat_ap = 0; sb = 0; bmask = 0;
-    if (k == 1) {
-      B = Bf = s_cm[j];
-      bmask = 0xffu;
-    } else if (k == 2 || k == 3) {
-      sb = 8u * (uint32_t)(k - 1);
-      bmask = 0xffu;
-      S = k == 2 ? s_cm[j] : cm_of(1, j);
-      if (!next_block()) { A = 1; B = Bf = 1; }
-    }  // k = 0, k = 4 (un-ranked per entry) and long groups (written by K6l): dummy iterator
-  };
-  auto step = [&]() {
-    B &= B - 1;
-    if (!B) {
-      A &= A - 1;
-      if (A) {
-        B = Bf;
-        if (k == 3) pat_ap = (uint32_t)__ffsll((long long)A) | ((uint32_t)(p + 1) << 8);
-      } else if (!next_block()) {
-        A = 1; B = Bf = 1;
-      }
-    }
-  };
-  uint32_t rem;  // entries of group j from the current one on
-  {
-    const int32_t qs = (int32_t)i0 - s.off[j];
-    rem = (uint32_t)(s.off[j + 1] - (int32_t)i0);
-    init_group();
-    q = (uint32_t)qs;
-    if (qs > 0 && k >= 1 && k <= 3) {
-      if (k == 1) {
-        B = Bf & ~below(select_bit(Bf, q));
-      } else {
-        const uint64_t c0 = s_cm[j], c1 = cm_of(1, j), c2 = cm_of(2, j);
-        const uint64_t sites = block_sites(k, c0, c1);
-        uint32_t qq = q;
-        const uint32_t tab = s.tab[j];
-        if (tab != kNoTable) {  // last block whose first entry is <= q
-          uint32_t lo = 0, hi = (uint32_t)__popcll(sites);
-          while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (s.cum[tab + mid] <= qq) lo = mid; else hi = mid;
-          }
-          p = s.pos[tab + lo];
-          qq -= s.cum[tab + lo];
-        } else {
-          for (uint64_t m = sites; m; m &= m - 1) {
-            p = __ffsll((long long)m) - 1;
-            const uint32_t w = block_size(k, p, c0, c1, c2, 0ull);
-            if (qq < w) break;
-            qq -= w;
-          }
-        }
-        S = sites & above(p);
-        const uint64_t Af = k == 3 ? (c0 & below(p)) : 1ull;
-        Bf = (k == 3 ? c2 : c1) & above(p);
-        const uint32_t nb = (uint32_t)__popcll(Bf);
-        const uint32_t ai = k == 3 ? qq / nb : 0u;
-        const uint32_t bi = qq - ai * nb;
-        A = k == 3 ? (Af & ~below(select_bit(Af, ai))) : 1ull;
-        B = Bf & ~below(select_bit(Bf, bi));
-        pat_ap = k == 3 ? ((uint32_t)__ffsll((long long)A) | ((uint32_t)(p + 1) << 8)) : (uint32_t)(p + 1);
-      }
-    }
-  }
-  double om[ET_PER];
-  uint32_t ob[ET_PER], op[ET_PER];
-  const uint32_t n_mine = min((uint32_t)ET_PER, tile_n - i0);
 #pragma unroll
-  for (int e = 0; e < ET_PER; ++e) {
-    if ((uint32_t)e < n_mine) {
-      om[e] = s.mass[j];
-      ob[e] = s.base[j];
-      op[e] = k == 4 ? block_entry_k4(j, q) : (pat_ap | (((uint32_t)__ffsll((long long)B) & bmask) << sb));
-      if (--rem == 0) {
-        ++j;  // the next group starts at the next entry (j <= ngrp: off[ngrp] is staged)
-        if ((uint32_t)e + 1 < n_mine) {
-          rem = (uint32_t)(s.off[j + 1] - s.off[j]);
-          init_group();
-        }
-      } else {
-        ++q;
-        step();
-      }
-    }
+    for (int i = 0; i < ET_PER; ++i) s.head[t * ET_PER + i] = max(loc[i], carry);
   }
-  const uint64_t e = e0 + i0;
-  if (n_mine == (uint32_t)ET_PER) {
-    static_assert(ET_PER == 4, "vector stores below are written for 4 entries per thread");
-    reinterpret_cast<double2*>(e_mass + e)[0] = make_double2(om[0], om[1]);
-    reinterpret_cast<double2*>(e_mass + e)[1] = make_double2(om[2], om[3]);
-    *reinterpret_cast<uint4*>(e_base + e) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
-    *reinterpret_cast<uint4*>(e_pat + e) = make_uint4(op[0], op[1], op[2], op[3]);
-  } else {
-    for (uint32_t x = 0; x < n_mine; ++x) {
-      e_mass[e + x] = om[x];
-      e_base[e + x] = ob[x];
-      e_pat[e + x] = op[x];
+  __syncthreads();
+  // (3) one thread per entry, consecutive threads = consecutive entries
+  for (uint32_t i = t; i < tile_n; i += ET_THREADS) {
+    const uint4 br = reinterpret_cast<const uint4*>(s.blk)[s.head[i] & 0xffffu];
+    const uint32_t j = br.y & 0xffffu;
+    const uint32_t k = br.w;
+    const uint32_t q = (uint32_t)((int32_t)i - (int32_t)br.x);
+    uint32_t pat;
+    if (k <= 3u) {
+      const uint32_t nb = (br.z >> 16) & 0xffu, p1 = (br.z >> 24) + 1u;
+      const uint32_t a = (q * s.recip[nb]) >> 20;  // q / nb (q < 4096)
+      const uint32_t pa = s.pool[(br.y >> 16) + a];
+      const uint32_t pb = s.pool[(br.z & 0xffffu) + (q - a * nb)];
+      pat = k == 3u ? (pa | (p1 << 8) | (pb << 16)) : (k == 2u ? (p1 | (pb << 8)) : pb);
+    } else if (k == kSlowGroup) {
+      uint32_t pk;
+      const int kk = pack_seq(s.seq[j], C, &pk);
+      const uint64_t* cm = cmask + (uint64_t)s.idx[j] * (uint64_t)C;
+      pat = group_entry_slow(kk, q, cm[seq_class_at(pk, 0)], kk > 1 ? cm[seq_class_at(pk, 1)] : 0ull,
+                             kk > 2 ? cm[seq_class_at(pk, 2)] : 0ull, kk > 3 ? cm[seq_class_at(pk, 3)] : 0ull);
+    } else {
+      continue;  // long group: K6l
     }
+    const uint64_t e = e0 + i;
+    e_mass[e] = s.mass[j];
+    e_base[e] = s.base[j];
+    e_pat[e] = pat;
   }
 }
 
@@ -633,8 +570,9 @@ __global__ void __launch_bounds__(ET_THREADS, 4)
 __global__ void __launch_bounds__(MD_THREADS)
     grp_expand_long_kernel(const uint8_t* __restrict__ res, const DevTables* __restrict__ tb, DigestCfg cfg,
                            const uint32_t* __restrict__ u_gpos, const uint16_t* __restrict__ u_len,
-                           const uint64_t* __restrict__ skey, const uint64_t* __restrict__ spay,
-                           const uint64_t* __restrict__ eoff, const uint32_t* __restrict__ long_list,
+                           const uint32_t* __restrict__ gid_tab, const uint64_t* __restrict__ skey,
+                           const uint64_t* __restrict__ spay, const uint64_t* __restrict__ eoff,
+                           const uint32_t* __restrict__ long_list,
                            const uint32_t* __restrict__ long_count, uint64_t base_bits, double* __restrict__ e_mass,
                            uint32_t* __restrict__ e_base, uint32_t* __restrict__ e_pat) {
   __shared__ ModTables mt;
@@ -675,7 +613,7 @@ __global__ void __launch_bounds__(MD_THREADS)
           if (ok) {
             const uint64_t slot = bo + __popc(om & lanemask_lt());
             e_mass[slot] = bmass;
-            e_base[slot] = bb;
+            e_base[slot] = gid_tab ? gid_tab[bb] : bb;
             e_pat[slot] = prefix | (((uint32_t)ws.pos[j] + 1u) << (8 * level));
           }
           bo += __popc(om);
@@ -750,23 +688,20 @@ void launch_grp_tile_first(const uint64_t* eoff, uint64_t n_groups, uint64_t n_e
              n_groups, n_tiles, first);
 }
 
-// cmask == nullptr (sharded build): u_gpos / u_len are the GLOBAL tables and the masks are rebuilt from them
+// payload rows index cmask (and gid_tab, when the rows are arrival slots of a sharded build)
 void launch_grp_expand(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const uint32_t* u_gpos,
-                       const uint16_t* u_len, const uint64_t* cmask, const uint64_t* skey, const uint64_t* spay,
-                       const uint64_t* eoff, const uint32_t* tile_first, uint64_t n_groups, uint64_t n_entries,
-                       uint64_t base_bits, double* e_mass, uint32_t* e_base, uint32_t* e_pat, uint32_t* long_list,
-                       uint32_t* long_count, uint32_t long_cap, uint32_t* d_err, cudaStream_t s) {
+                       const uint16_t* u_len, const uint64_t* cmask, const uint32_t* gid_tab, const uint64_t* skey,
+                       const uint64_t* spay, const uint64_t* eoff, const uint32_t* tile_first, uint64_t n_groups,
+                       uint64_t n_entries, uint64_t base_bits, double* e_mass, uint32_t* e_base, uint32_t* e_pat,
+                       uint32_t* long_list, uint32_t* long_count, uint32_t long_cap, uint32_t* d_err, cudaStream_t s) {
   if (n_groups == 0 || n_entries == 0) return;
   const uint64_t n_tiles = (n_entries + kExpTile - 1) / kExpTile;
-  const size_t smem = sizeof(ExpTabSmem) + (size_t)cfg.max_mods * EX_GMAX * 8;
-  // function attributes are per device: set before every launch (a process may hold handles on several GPUs)
-  DBI_CUDA(cudaFuncSetAttribute(grp_expand_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  DBI_LAUNCH(grp_expand_tab_kernel, (unsigned)n_tiles, ET_THREADS, smem, s, cfg, cmask, d_res, d_tb, u_gpos, u_len, skey,
-             spay, eoff, tile_first, n_entries, base_bits, e_mass, e_base, e_pat, long_list, long_count, long_cap, d_err);
+  DBI_LAUNCH(grp_expand_tab_kernel, (unsigned)n_tiles, ET_THREADS, 0, s, cfg, cmask, gid_tab, skey, spay, eoff,
+             tile_first, n_entries, base_bits, e_mass, e_base, e_pat, long_list, long_count, long_cap, d_err);
   if (long_cap > 0) {
     unsigned grid = (long_cap + MD_WARPS - 1) / MD_WARPS;
     if (grid > (unsigned)kNumSMsB200 * 4) grid = (unsigned)kNumSMsB200 * 4;
-    DBI_LAUNCH(grp_expand_long_kernel, grid, MD_THREADS, 0, s, d_res, d_tb, cfg, u_gpos, u_len, skey, spay, eoff,
+    DBI_LAUNCH(grp_expand_long_kernel, grid, MD_THREADS, 0, s, d_res, d_tb, cfg, u_gpos, u_len, gid_tab, skey, spay, eoff,
                long_list, long_count, base_bits, e_mass, e_base, e_pat);
   }
 }

@@ -442,6 +442,75 @@ int orc_query(void* h, const double* lo, const double* hi, uint64_t nq, uint64_t
   return 0;
 }
 
+// What getSequences hands back for a batch of ranges: parseAddPeptideInfo (Merge:386-481) for every
+// hit of every query -- exact mass, the first occurrence (protein, offset, length), the peptide
+// string cut from the protein (ProteinCache.getPeptideSequence, ProteinCache.java:112-127), the
+// flanking residues (Util.getResidues, Merge:456-458) and the protein-id list.  Two-pass: call with
+// mass == NULL for the sizes.  hit_off[nq + 1], seq_off / prot_list_off [n_hits + 1].
+void orc_get_residues(const uint8_t* prot_seq, uint64_t prot_len, uint32_t seq_off, uint32_t seq_len, char* left3,
+                      char* right3);
+int orc_query_hits(void* h, const double* lo, const double* hi, uint64_t nq, uint64_t* hit_off, double* mass,
+                   uint32_t* first_prot, uint32_t* first_off, uint16_t* len, uint32_t* modpat, uint64_t* seq_off,
+                   uint8_t* seq, char* flanks /* 6 per hit */, uint64_t* prot_list_off, uint32_t* prot_ids,
+                   uint64_t* n_hits, uint64_t* n_seq_bytes, uint64_t* n_prot_ids) {
+  Oracle* o = (Oracle*)h;
+  std::vector<uint64_t> b(nq), c(nq);
+  int contig = 1;
+  orc_query(h, lo, hi, nq, b.data(), c.data(), &contig);
+  if (!contig) return -1;
+  // sizes per query, then their prefix sums (the fill below runs on every host thread)
+  std::vector<uint64_t> qs(nq + 1, 0), qp(nq + 1, 0);
+#pragma omp parallel for schedule(static)
+  for (int64_t q = 0; q < (int64_t)nq; ++q) {
+    uint64_t sb = 0, pi = 0;
+    for (uint64_t i = 0; i < c[q]; ++i) {
+      const Merged& u = o->uniq[o->entries[b[q] + i].base];
+      sb += (uint64_t)u.len;
+      pi += u.prots.size();
+    }
+    qs[q + 1] = sb;
+    qp[q + 1] = pi;
+  }
+  hit_off[0] = 0;
+  for (uint64_t q = 0; q < nq; ++q) {
+    hit_off[q + 1] = hit_off[q] + c[q];
+    qs[q + 1] += qs[q];
+    qp[q + 1] += qp[q];
+  }
+  const uint64_t H = hit_off[nq], SB = qs[nq], PI = qp[nq];
+  if (mass) {
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t q = 0; q < (int64_t)nq; ++q) {
+      uint64_t hh = hit_off[q], sb = qs[q], pi = qp[q];
+      for (uint64_t i = 0; i < c[q]; ++i, ++hh) {
+        const Entry& e = o->entries[b[q] + i];
+        const Merged& u = o->uniq[e.base];
+        mass[hh] = e.mass;
+        first_prot[hh] = (uint32_t)u.prots[0];
+        first_off[hh] = (uint32_t)u.off;
+        len[hh] = (uint16_t)u.len;
+        modpat[hh] = e.modpat;
+        seq_off[hh] = sb;
+        prot_list_off[hh] = pi;
+        const std::string& ps = o->prot[u.prots[0]];
+        std::memcpy(seq + sb, ps.data() + u.off, (size_t)u.len);  // protSeq.substring(off, off + len)
+        if (flanks)
+          orc_get_residues((const uint8_t*)ps.data(), ps.size(), (uint32_t)u.off, (uint32_t)u.len, flanks + 6 * hh,
+                           flanks + 6 * hh + 3);
+        for (size_t k = 0; k < u.prots.size(); ++k) prot_ids[pi + k] = (uint32_t)u.prots[k];
+        sb += (uint64_t)u.len;
+        pi += u.prots.size();
+      }
+    }
+    seq_off[H] = SB;
+    prot_list_off[H] = PI;
+  }
+  *n_hits = H;
+  *n_seq_bytes = SB;
+  *n_prot_ids = PI;
+  return 0;
+}
+
 // IndexUtil.calculateMass(sequence, isH2OPlusProtonAdded) (util/IndexUtil.java:197-208)
 double orc_calculate_mass(void* h, const uint8_t* seq, uint64_t len) {
   Oracle* o = (Oracle*)h;

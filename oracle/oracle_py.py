@@ -44,6 +44,8 @@ def load():
     lib.orc_query.argtypes = [vp, vp, vp, C.c_uint64, vp, vp, C.POINTER(C.c_int)]
     lib.orc_query_ppm.argtypes = [vp, C.c_double, C.c_double, vp, C.c_uint64, u64p]
     lib.orc_query_ppm.restype = C.c_uint64
+    lib.orc_query_hits.argtypes = [vp, vp, vp, C.c_uint64] + [vp] * 11 + [u64p, u64p, u64p]
+    lib.orc_query_hits.restype = C.c_int
     lib.orc_calculate_mass.argtypes = [vp, C.c_char_p, C.c_uint64]
     lib.orc_calculate_mass.restype = C.c_double
     lib.orc_tolerance_in_dalton.argtypes = [C.c_double, C.c_double]
@@ -135,6 +137,30 @@ class Oracle:
         self.lib.orc_set_threads(self.threads)
         self.lib.orc_query(self.h, _p(lo), _p(hi), nq, _p(b), _p(c), C.byref(contig))
         return b, c, bool(contig.value)
+
+    def query_hits(self, lo, hi, flanks: bool = True) -> dict:
+        """Every hit of every [lo, hi] materialised like parseAddPeptideInfo (same shape as dbi_query_hits)."""
+        lo = np.ascontiguousarray(lo, np.float64)
+        hi = np.ascontiguousarray(hi, np.float64)
+        nq = len(lo)
+        hit_off = np.zeros(nq + 1, np.uint64)
+        nh, ns, ni = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.lib.orc_set_threads(self.threads)
+        rc = self.lib.orc_query_hits(self.h, _p(lo), _p(hi), nq, _p(hit_off), *([None] * 10), C.byref(nh), C.byref(ns),
+                                     C.byref(ni))
+        assert rc == 0
+        H = nh.value
+        out = {"hit_off": hit_off, "mass": np.empty(H, np.float64), "first_prot": np.empty(H, np.uint32),
+               "first_off": np.empty(H, np.uint32), "len": np.empty(H, np.uint16), "modpat": np.empty(H, np.uint32),
+               "seq_off": np.zeros(H + 1, np.uint64), "seq": np.empty(ns.value, np.uint8),
+               "flanks": np.empty(6 * H, np.uint8) if flanks else None,
+               "prot_list_off": np.zeros(H + 1, np.uint64), "prot_ids": np.empty(ni.value, np.uint32)}
+        rc = self.lib.orc_query_hits(self.h, _p(lo), _p(hi), nq, _p(hit_off), _p(out["mass"]), _p(out["first_prot"]),
+                                     _p(out["first_off"]), _p(out["len"]), _p(out["modpat"]), _p(out["seq_off"]),
+                                     _p(out["seq"]), _p(out["flanks"]), _p(out["prot_list_off"]), _p(out["prot_ids"]),
+                                     C.byref(nh), C.byref(ns), C.byref(ni))
+        assert rc == 0
+        return out
 
     def query_ppm(self, precursor_mass: float, ppm: float):
         """getSequencesUsingPPMTolerance restated: entry indices in result-list order, number of probes."""
