@@ -95,6 +95,25 @@ class DbiStats(C.Structure):
     ]
 
 
+class DbiHitCounts(C.Structure):
+    _fields_ = [("nq", C.c_uint64), ("n_hits", C.c_uint64), ("n_seq_bytes", C.c_uint64), ("n_prot_ids", C.c_uint64)]
+
+
+class DbiHitBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("hit_off", "mass", "first_prot", "first_off", "len", "modpat", "flanks",
+                                          "seq_off", "seq", "prot_list_off", "prot_ids")]
+
+
+HIT_FIELDS = {  # name -> (dtype, size as a function of the counts)
+    "hit_off": (np.uint64, lambda c: c.nq + 1), "mass": (np.float64, lambda c: c.n_hits),
+    "first_prot": (np.uint32, lambda c: c.n_hits), "first_off": (np.uint32, lambda c: c.n_hits),
+    "len": (np.uint16, lambda c: c.n_hits), "modpat": (np.uint32, lambda c: c.n_hits),
+    "flanks": (np.uint8, lambda c: 6 * c.n_hits), "seq_off": (np.uint64, lambda c: c.n_hits + 1),
+    "seq": (np.uint8, lambda c: c.n_seq_bytes), "prot_list_off": (np.uint64, lambda c: c.n_hits + 1),
+    "prot_ids": (np.uint32, lambda c: c.n_prot_ids),
+}
+
+
 class DbiError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
@@ -137,6 +156,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "dbi_query": (C.c_int, [vp, vp, vp, C.c_uint64, vp, vp]),
         "dbi_query_device": (C.c_int, [vp, vp, vp, C.c_uint64, vp, vp]),
         "dbi_fetch": (C.c_int, [vp, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp, vp, vp, C.c_uint64, u64p]),
+        "dbi_query_hits": (C.c_int, [vp, vp, vp, C.c_uint64, C.POINTER(DbiHitCounts)]),
+        "dbi_query_hits_read": (C.c_int, [vp, C.POINTER(DbiHitBuffers)]),
+        "dbi_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(vp)]),
+        "dbi_host_free": (C.c_int, [vp]),
         "dbi_get_protein": (C.c_int, [vp, C.c_uint32, C.POINTER(vp), u64p]),
         "dbi_fasta_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(vp)]),
         "dbi_fasta_counts": (C.c_int, [vp, u32p, u64p, u64p]),
@@ -172,7 +195,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
 ABI_SYMBOLS = [
     "dbi_default_params", "dbi_params_add_static_mod", "dbi_params_set_enzyme", "dbi_params_add_diff_mod",
     "dbi_create", "dbi_set_stream", "dbi_add_proteins", "dbi_upload", "dbi_reset_index", "dbi_build",
-    "dbi_stats_get", "dbi_query", "dbi_query_device", "dbi_fetch", "dbi_get_protein", "dbi_calculate_mass",
+    "dbi_stats_get", "dbi_query", "dbi_query_device", "dbi_fetch", "dbi_query_hits", "dbi_query_hits_read",
+    "dbi_host_alloc", "dbi_host_free", "dbi_get_protein", "dbi_calculate_mass",
     "dbi_entry_keys", "dbi_debug_emitted", "dbi_build_from_records", "dbi_debug_radix_sort", "dbi_destroy",
     "dbi_abi_sizes", "dbi_release_cached_memory",
     "dbi_last_error", "dbi_kernel_launches",
@@ -352,6 +376,24 @@ class GpuIndex:
                                        _ptr(out["first_off"]), _ptr(out["len"]), _ptr(out["modpat"]),
                                        _ptr(out["prot_list_off"]), _ptr(ids), n_ids.value, C.byref(n_ids)))
         out["prot_ids"] = ids
+        return out
+
+    def query_hits(self, lo: np.ndarray, hi: np.ndarray, fields=None, alloc=None) -> dict:
+        """dbi_query_hits + dbi_query_hits_read: every hit of every [lo[i], hi[i]] materialised (mass, first
+        occurrence, peptide residues, flanks, mod pattern, protein ids).  `fields`: subset of HIT_FIELDS to
+        read back (default all); `alloc(name, dtype, n)`: buffer factory (e.g. pinned memory), default numpy."""
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        cnt = DbiHitCounts()
+        self._check(self.lib.dbi_query_hits(self._h, _ptr(lo), _ptr(hi), len(lo), C.byref(cnt)))
+        out, bufs = {"counts": cnt}, DbiHitBuffers()
+        for name, (dt, size) in HIT_FIELDS.items():
+            if fields is not None and name not in fields:
+                continue
+            a = alloc(name, dt, int(size(cnt))) if alloc else np.empty(int(size(cnt)), dtype=dt)
+            out[name] = a
+            setattr(bufs, name, a.ctypes.data)
+        self._check(self.lib.dbi_query_hits_read(self._h, C.byref(bufs)))
         return out
 
     def entry_keys(self) -> np.ndarray:

@@ -199,6 +199,18 @@ struct dbi_handle {
   uint64_t mg_v = 0;
   DevBuf mg_dest, mg_idx[2], mg_counts, mg_thr;
 
+  // pending result of dbi_query_hits (device side), read by dbi_query_hits_read
+  struct HitResult {
+    bool valid = false;
+    dbi_hit_counts n{};
+    DevBuf hit_off, mass, prot, off, len, pat, flanks, seq_off, seq, plo, ids;
+    void drop() {
+      valid = false;
+      hit_off.release(); mass.release(); prot.release(); off.release(); len.release(); pat.release();
+      flanks.release(); seq_off.release(); seq.release(); plo.release(); ids.release();
+    }
+  } hits;
+
   DigestCfg cfg{};
   dbi_stats st{};
   // profiling (params.profile): event pairs recorded on the stream without any extra
@@ -359,6 +371,7 @@ uint64_t read_u64(dbi_handle* h, const uint64_t* d) {
 
 void free_index(dbi_handle* h) {
   h->built = false;
+  h->hits.drop();
   h->d_res.release();
   h->d_pstart.release();
   h->u_mass.release(); h->u_gpos.release(); h->u_prot.release(); h->u_len.release();
@@ -1217,7 +1230,7 @@ int dbi_query_device(dbi_handle* h, const double* d_lo, const double* d_hi, uint
     return DBI_ENOTINIT;
   }
   Stage sg(h, DBI_STAGE_QUERY);
-  launch_query(h->entry_mass(), h->n_entries, d_lo, d_hi, nq, d_hit_begin, d_hit_count, h->stream);
+  launch_query(h->entry_mass(), h->n_entries, d_lo, d_hi, nq, d_hit_begin, d_hit_count, nullptr, h->stream);
   h->st.algo_bytes[DBI_STAGE_QUERY] += nq * (32 + 2ull * 32 * (uint64_t)bit_length(h->n_entries));
   return DBI_OK;
   DBI_API_END
@@ -1246,7 +1259,7 @@ int dbi_query(dbi_handle* h, const double* lo, const double* hi, uint64_t nq, ui
   DBI_CUDA(cudaMemcpyAsync(d_hi, hi, nq * 8, cudaMemcpyHostToDevice, s));
   {
     Stage sg(h, DBI_STAGE_QUERY);
-    launch_query(h->entry_mass(), h->n_entries, d_lo, d_hi, nq, d_b, d_c, s);
+    launch_query(h->entry_mass(), h->n_entries, d_lo, d_hi, nq, d_b, d_c, nullptr, s);
     h->st.algo_bytes[DBI_STAGE_QUERY] += nq * (32 + 2ull * 32 * (uint64_t)bit_length(h->n_entries));
   }
   DBI_CUDA(cudaMemcpyAsync(hit_begin, d_b, nq * 8, cudaMemcpyDeviceToHost, s));
@@ -1324,6 +1337,173 @@ int dbi_fetch(dbi_handle* h, uint64_t begin, uint64_t count, double* mass, uint3
   resolve_spans(h);
   return DBI_OK;
   DBI_API_END
+}
+
+namespace {
+// the unique-peptide tables a fetch resolves base peptides through: this GPU's own
+UniqView uniq_view(dbi_handle* h) {
+  UniqView uv;
+  std::memset(&uv, 0, sizeof(uv));
+  uv.world = 1;
+  uv.gpos[0] = h->u_gpos.as<uint32_t>();
+  uv.prot[0] = h->u_prot.as<uint32_t>();
+  uv.len[0] = h->u_len.as<uint16_t>();
+  uv.plo[0] = h->u_plo.as<uint64_t>();
+  uv.plist[0] = h->plist.as<uint32_t>();
+  uv.uoff[0] = h->ent_base_off;
+  uv.uoff[1] = h->ent_base_off + h->n_unique;
+  return uv;
+}
+}  // namespace
+
+int dbi_query_hits(dbi_handle* h, const double* lo, const double* hi, uint64_t nq, dbi_hit_counts* counts) {
+  DBI_API_BEGIN(h)
+  if (!h->built) {
+    set_error("Indexer is not initialized");
+    return DBI_ENOTINIT;
+  }
+  if (!counts || (nq && (!lo || !hi))) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  cudaStream_t s = h->stream;
+  dbi_handle::HitResult& r = h->hits;
+  r.drop();
+  std::memset(counts, 0, sizeof(*counts));
+  counts->nq = nq;
+  r.n = *counts;
+  r.hit_off.alloc((nq + 1) * 8, h->arena);
+  if (nq == 0) {
+    DBI_CUDA(cudaMemsetAsync(r.hit_off.p, 0, 8, s));
+    DBI_CUDA(cudaStreamSynchronize(s));
+    r.valid = true;
+    return DBI_OK;
+  }
+  DevBuf io, cnt32, stmp, hit_entry, len32, np32, stmp2;
+  io.alloc(nq * 32, h->arena);  // lo | hi | begin | count
+  double* d_lo = io.as<double>();
+  double* d_hi = d_lo + nq;
+  uint64_t* d_b = (uint64_t*)(d_hi + nq);
+  uint64_t* d_c = d_b + nq;
+  cnt32.alloc(nq * 4, h->arena);
+  stmp.alloc(full_scan_tmp_bytes(nq), h->arena);
+  DBI_CUDA(cudaMemcpyAsync(d_lo, lo, nq * 8, cudaMemcpyHostToDevice, s));
+  DBI_CUDA(cudaMemcpyAsync(d_hi, hi, nq * 8, cudaMemcpyHostToDevice, s));
+  uint64_t H = 0;
+  {
+    Stage sg(h, DBI_STAGE_QUERY);
+    launch_query(h->entry_mass(), h->n_entries, d_lo, d_hi, nq, d_b, d_c, cnt32.as<uint32_t>(), s);
+    launch_full_scan_u32_to_u64(cnt32.as<uint32_t>(), nq, r.hit_off.as<uint64_t>(), stmp.p, s);
+    h->st.algo_bytes[DBI_STAGE_QUERY] += nq * (32 + 2ull * 32 * (uint64_t)bit_length(h->n_entries));
+    H = read_u64(h, r.hit_off.as<uint64_t>() + nq);
+  }
+  if (H >= (1ull << 32)) {
+    set_error("%llu hits in one batch: split the batch (< 2^32 hits per call)", (unsigned long long)H);
+    r.drop();
+    return DBI_ERANGE;
+  }
+  const UniqView uv = uniq_view(h);
+  r.seq_off.alloc((H + 1) * 8, h->arena);
+  r.plo.alloc((H + 1) * 8, h->arena);
+  uint64_t SB = 0, PI = 0;
+  if (H) {
+    Stage sg(h, DBI_STAGE_FETCH);
+    hit_entry.alloc(H * 4, h->arena);
+    len32.alloc(H * 4, h->arena);
+    np32.alloc(H * 4, h->arena);
+    stmp2.alloc(full_scan_tmp_bytes(H), h->arena);
+    launch_hits_expand(h->entry_base(), h->ent_base_off, uv, d_b, r.hit_off.as<uint64_t>(), nq, hit_entry.as<uint32_t>(),
+                       len32.as<uint32_t>(), np32.as<uint32_t>(), s);
+    launch_full_scan_u32_to_u64(len32.as<uint32_t>(), H, r.seq_off.as<uint64_t>(), stmp2.p, s);
+    launch_full_scan_u32_to_u64(np32.as<uint32_t>(), H, r.plo.as<uint64_t>(), stmp2.p, s);
+    DBI_CUDA(cudaMemcpyAsync(&SB, r.seq_off.as<uint64_t>() + H, 8, cudaMemcpyDeviceToHost, s));
+    DBI_CUDA(cudaMemcpyAsync(&PI, r.plo.as<uint64_t>() + H, 8, cudaMemcpyDeviceToHost, s));
+    DBI_CUDA(cudaStreamSynchronize(s));
+    r.mass.alloc(H * 8, h->arena);
+    r.prot.alloc(H * 4, h->arena);
+    r.off.alloc(H * 4, h->arena);
+    r.len.alloc(H * 2, h->arena);
+    r.pat.alloc(H * 4, h->arena);
+    r.flanks.alloc(H * 6, h->arena);
+    r.seq.alloc(std::max<uint64_t>(SB, 1), h->arena);
+    r.ids.alloc(std::max<uint64_t>(PI, 1) * 4, h->arena);
+    launch_hits_gather(h->d_res.as<uint8_t>(), h->d_pstart.as<uint32_t>(), h->entry_mass(), h->entry_base(),
+                       h->ent_base_off, h->entry_pat(), uv, hit_entry.as<uint32_t>(), r.seq_off.as<uint64_t>(),
+                       r.plo.as<uint64_t>(), H, r.mass.as<double>(), r.prot.as<uint32_t>(), r.off.as<uint32_t>(),
+                       r.len.as<uint16_t>(), r.pat.as<uint32_t>(), r.flanks.as<uint8_t>(), r.seq.as<uint8_t>(),
+                       r.ids.as<uint32_t>(), s);
+    // per hit: entry (8 + 4 + 4) + peptide tables (4 + 4 + 2 + 16) read, 44 written; residues and ids copied
+    h->st.algo_bytes[DBI_STAGE_FETCH] += H * (16 + 26 + 44 + 12) + 2 * SB + 8 * PI;
+  } else {
+    DBI_CUDA(cudaMemsetAsync(r.seq_off.p, 0, 8, s));
+    DBI_CUDA(cudaMemsetAsync(r.plo.p, 0, 8, s));
+  }
+  DBI_CUDA(cudaStreamSynchronize(s));
+  resolve_spans(h);
+  counts->n_hits = H;
+  counts->n_seq_bytes = SB;
+  counts->n_prot_ids = PI;
+  r.n = *counts;
+  r.valid = true;
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_query_hits_read(dbi_handle* h, const dbi_hit_buffers* out) {
+  DBI_API_BEGIN(h)
+  dbi_handle::HitResult& r = h->hits;
+  if (!r.valid) {
+    set_error("no pending dbi_query_hits result on this handle");
+    return DBI_ENOTINIT;
+  }
+  if (!out) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  cudaStream_t s = h->stream;
+  const uint64_t H = r.n.n_hits;
+  auto d2h = [&](void* dst, const DevBuf& src, uint64_t bytes) {
+    if (dst && bytes) DBI_CUDA(cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, s));
+  };
+  d2h(out->hit_off, r.hit_off, (r.n.nq + 1) * 8);
+  d2h(out->seq_off, r.seq_off, (H + 1) * 8);
+  d2h(out->prot_list_off, r.plo, (H + 1) * 8);
+  d2h(out->mass, r.mass, H * 8);
+  d2h(out->first_prot, r.prot, H * 4);
+  d2h(out->first_off, r.off, H * 4);
+  d2h(out->len, r.len, H * 2);
+  d2h(out->modpat, r.pat, H * 4);
+  d2h(out->flanks, r.flanks, H * 6);
+  d2h(out->seq, r.seq, r.n.n_seq_bytes);
+  d2h(out->prot_ids, r.ids, r.n.n_prot_ids * 4);
+  DBI_CUDA(cudaStreamSynchronize(s));
+  r.drop();
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_host_alloc(uint64_t bytes, void** out) {
+  if (!out) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  *out = nullptr;
+  const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    set_error("cudaHostAlloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? DBI_ENOMEM : DBI_ECUDA;
+  }
+  return DBI_OK;
+}
+
+int dbi_host_free(void* p) {
+  if (p && cudaFreeHost(p) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaFreeHost failed");
+    return DBI_ECUDA;
+  }
+  return DBI_OK;
 }
 
 int dbi_get_protein(dbi_handle* h, uint32_t id, const uint8_t** residues, uint64_t* len) {

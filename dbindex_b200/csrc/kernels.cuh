@@ -123,8 +123,34 @@ void launch_grp_expand(const uint8_t* d_res, const DevTables* d_tb, const Digest
                        uint32_t* long_list, uint32_t* long_count, uint32_t long_cap, uint32_t* d_err, cudaStream_t s);
 
 // ---- K9/K10 query ----------------------------------------------------------------
+// cnt32 (optional): the hit counts again as u32, the input of the hit-offset scan
 void launch_query(const double* e_mass, uint64_t n_entries, const double* lo, const double* hi, uint64_t nq,
-                  uint64_t* hit_begin, uint64_t* hit_count, cudaStream_t s);
+                  uint64_t* hit_begin, uint64_t* hit_count, uint32_t* cnt32, cudaStream_t s);
+
+// Unique-peptide tables of every rank of a sharded index (world = 1: this GPU's own).  A peptide is
+// named by its global id; rank r holds ids [uoff[r], uoff[r + 1]).  A rank whose tables are not mapped
+// here (nullptr) makes its peptides come back as DBI_REMOTE_BASE.
+constexpr int kMaxRanks = 16;
+struct UniqView {
+  const uint32_t* gpos[kMaxRanks];
+  const uint32_t* prot[kMaxRanks];
+  const uint16_t* len[kMaxRanks];
+  const uint64_t* plo[kMaxRanks];
+  const uint32_t* plist[kMaxRanks];
+  uint64_t uoff[kMaxRanks + 1];
+  int world;
+};
+// K10a: per hit of every query, in (query, rank-in-query) order: the entry it is, its peptide
+// length and its protein-list length.  hit_off = exclusive scan of the hit counts.
+void launch_hits_expand(const uint32_t* e_base, uint64_t ent_off, const UniqView& uv, const uint64_t* hit_begin,
+                        const uint64_t* hit_off, uint64_t nq, uint32_t* hit_entry, uint32_t* len32, uint32_t* np32,
+                        cudaStream_t s);
+// K10b: what parseAddPeptideInfo materialises per hit (DBIndexStoreSQLiteByteIndexMerge.java:386-481)
+void launch_hits_gather(const uint8_t* d_res, const uint32_t* pstart, const double* e_mass, const uint32_t* e_base,
+                        uint64_t ent_off, const uint32_t* e_pat, const UniqView& uv, const uint32_t* hit_entry,
+                        const uint64_t* seq_off, const uint64_t* plo_out, uint64_t n_hits, double* o_mass,
+                        uint32_t* o_prot, uint32_t* o_off, uint16_t* o_len, uint32_t* o_pat, uint8_t* o_flanks,
+                        uint8_t* o_seq, uint32_t* o_ids, cudaStream_t s);
 // per-entry protein-list length for entries [begin, begin+count) + per-tile sums.
 // e_base == nullptr means "entry i is unique peptide i" (no differential mods).
 // Base peptides are named by global ids; the handle holds [own_lo, own_lo + own_n) of them (all of

@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(ET_THREADS, 4)
     s.base[j] = gid_tab ? gid_tab[row] : row;
     s.idx[j] = row;
     s.seq[j] = (uint8_t)seq;
+    if (rel >= (int32_t)tile_n) continue;  // the group of the NEXT tile's first entry starts right after this tile
     ExpBlk b;
     b.start = rel; b.grp = (uint16_t)j; b.a0 = 0; b.b0 = 0; b.nb = 1; b.p = 0; b.k = (uint32_t)k;
     auto append = [&](const ExpBlk& x) {

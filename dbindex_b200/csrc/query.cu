@@ -36,7 +36,7 @@ __device__ __forceinline__ uint64_t upper_bound_d(const double* __restrict__ a, 
 __global__ void __launch_bounds__(Q_THREADS)
     query_kernel(const double* __restrict__ e_mass, uint64_t n, const double* __restrict__ lo,
                  const double* __restrict__ hi, uint64_t nq, uint64_t* __restrict__ hit_begin,
-                 uint64_t* __restrict__ hit_count) {
+                 uint64_t* __restrict__ hit_count, uint32_t* __restrict__ cnt32) {
   const uint64_t q = (uint64_t)blockIdx.x * Q_THREADS + threadIdx.x;
   if (q >= nq) return;
   const double l = lo[q], h = hi[q];
@@ -44,6 +44,98 @@ __global__ void __launch_bounds__(Q_THREADS)
   const uint64_t e = upper_bound_d(e_mass, n, h);  // mass > maxMass stops (Merge:415)
   hit_begin[q] = b;
   hit_count[q] = e > b ? e - b : 0;
+  if (cnt32) cnt32[q] = e > b ? (uint32_t)(e - b) : 0u;  // an index holds < 2^32 entries
+}
+
+// owner rank and row of a unique peptide named by its global id
+__device__ __forceinline__ int uniq_owner(const UniqView& uv, uint64_t gid, uint64_t* row) {
+  int r = 0;
+  while (r + 1 < uv.world && gid >= uv.uoff[r + 1]) ++r;
+  *row = gid - uv.uoff[r];
+  return r;
+}
+
+constexpr int HX_WARPS = Q_THREADS / 32;
+
+// K10a: one warp per query, lanes stride its hits (consecutive entries -> coalesced)
+__global__ void __launch_bounds__(Q_THREADS)
+    hits_expand_kernel(const uint32_t* __restrict__ e_base, uint64_t ent_off, UniqView uv,
+                       const uint64_t* __restrict__ hit_begin, const uint64_t* __restrict__ hit_off, uint64_t nq,
+                       uint32_t* __restrict__ hit_entry, uint32_t* __restrict__ len32, uint32_t* __restrict__ np32) {
+  const uint64_t q = (uint64_t)blockIdx.x * HX_WARPS + (threadIdx.x >> 5);
+  if (q >= nq) return;
+  const uint64_t b = hit_begin[q], h0 = hit_off[q];
+  const uint32_t n = (uint32_t)(hit_off[q + 1] - h0);
+  for (uint32_t i = lane_id(); i < n; i += 32) {
+    const uint64_t e = b + i;
+    const uint64_t gid = e_base ? (uint64_t)e_base[e] : ent_off + e;
+    uint64_t row;
+    const int r = uniq_owner(uv, gid, &row);
+    uint32_t len = 0, np = 0;
+    if (uv.len[r]) {
+      len = uv.len[r][row];
+      np = (uint32_t)(uv.plo[r][row + 1] - uv.plo[r][row]);
+    }
+    hit_entry[h0 + i] = (uint32_t)e;
+    len32[h0 + i] = len;
+    np32[h0 + i] = np;
+  }
+}
+
+// K10b: one thread per hit
+__global__ void __launch_bounds__(Q_THREADS)
+    hits_gather_kernel(const uint8_t* __restrict__ res, const uint32_t* __restrict__ pstart,
+                       const double* __restrict__ e_mass, const uint32_t* __restrict__ e_base, uint64_t ent_off,
+                       const uint32_t* __restrict__ e_pat, UniqView uv, const uint32_t* __restrict__ hit_entry,
+                       const uint64_t* __restrict__ seq_off, const uint64_t* __restrict__ plo_out, uint64_t n_hits,
+                       double* __restrict__ o_mass, uint32_t* __restrict__ o_prot, uint32_t* __restrict__ o_off,
+                       uint16_t* __restrict__ o_len, uint32_t* __restrict__ o_pat, uint8_t* __restrict__ o_flanks,
+                       uint8_t* __restrict__ o_seq, uint32_t* __restrict__ o_ids) {
+  const uint64_t h = (uint64_t)blockIdx.x * Q_THREADS + threadIdx.x;
+  if (h >= n_hits) return;
+  const uint64_t e = hit_entry[h];
+  const uint64_t gid = e_base ? (uint64_t)e_base[e] : ent_off + e;
+  uint64_t row;
+  const int r = uniq_owner(uv, gid, &row);
+  if (o_mass) o_mass[h] = e_mass[e];
+  if (o_pat) o_pat[h] = e_pat ? e_pat[e] : 0u;
+  if (!uv.len[r]) {  // the owner's tables are not mapped: the caller resolves the peptide through its owner
+    if (o_prot) o_prot[h] = DBI_REMOTE_BASE;
+    if (o_off) o_off[h] = (uint32_t)gid;
+    if (o_len) o_len[h] = 0;
+    if (o_flanks)
+      for (int k = 0; k < 6; ++k) o_flanks[6 * h + k] = '-';
+    return;
+  }
+  const uint32_t gp = uv.gpos[r][row], pr = uv.prot[r][row], len = uv.len[r][row];
+  if (o_prot) o_prot[h] = pr;
+  if (o_off) o_off[h] = gp - pstart[pr];  // sequenceOffset inside the first protein
+  if (o_len) o_len[h] = (uint16_t)len;
+  if (o_seq) {  // ProteinCache.getPeptideSequence: protSeq.substring(off, off + len)
+    uint8_t* d = o_seq + seq_off[h];
+    for (uint32_t k = 0; k < len; ++k) d[k] = ld_res(res, gp + k);
+  }
+  if (o_flanks) {
+    // Util.getResidues (Util.java:130-162): up to 3 residues on the left, '-' padded on the left; on
+    // the right min(3, protLen - end - 1) residues -- the reference's off-by-one drops the last
+    // residue of the protein from the right flank -- '-' padded on the right.
+    uint8_t* f = o_flanks + 6 * h;
+    uint8_t l2 = ld_res(res, gp - 1);
+    uint8_t l1 = l2 ? ld_res(res, gp - 2) : (uint8_t)0;
+    uint8_t l0 = l1 ? ld_res(res, gp - 3) : (uint8_t)0;
+    f[0] = l0 ? l0 : (uint8_t)'-';
+    f[1] = l1 ? l1 : (uint8_t)'-';
+    f[2] = l2 ? l2 : (uint8_t)'-';
+    const uint32_t endp = gp + len;  // first position after the peptide
+    uint32_t remaining = 0;          // residues after the peptide, up to 4
+    while (remaining < 4 && ld_res(res, endp + remaining) != 0) ++remaining;
+    const uint32_t rl = remaining > 0 ? min(3u, remaining - 1u) : 0u;
+    for (uint32_t k = 0; k < 3; ++k) f[3 + k] = k < rl ? ld_res(res, endp + k) : (uint8_t)'-';
+  }
+  if (o_ids) {  // every occurrence's protein id, insertion order (Merge:449-475)
+    const uint64_t src = uv.plo[r][row], n = uv.plo[r][row + 1] - src, dst = plo_out[h];
+    for (uint64_t k = 0; k < n; ++k) o_ids[dst + k] = uv.plist[r][src + k];
+  }
 }
 
 __global__ void __launch_bounds__(Q_THREADS)
@@ -151,10 +243,30 @@ __global__ void __launch_bounds__(Q_THREADS)
 }  // namespace
 
 void launch_query(const double* e_mass, uint64_t n_entries, const double* lo, const double* hi, uint64_t nq,
-                  uint64_t* hit_begin, uint64_t* hit_count, cudaStream_t s) {
+                  uint64_t* hit_begin, uint64_t* hit_count, uint32_t* cnt32, cudaStream_t s) {
   if (nq == 0) return;
   const unsigned grid = (unsigned)((nq + Q_THREADS - 1) / Q_THREADS);
-  DBI_LAUNCH(query_kernel, grid, Q_THREADS, 0, s, e_mass, n_entries, lo, hi, nq, hit_begin, hit_count);
+  DBI_LAUNCH(query_kernel, grid, Q_THREADS, 0, s, e_mass, n_entries, lo, hi, nq, hit_begin, hit_count, cnt32);
+}
+
+void launch_hits_expand(const uint32_t* e_base, uint64_t ent_off, const UniqView& uv, const uint64_t* hit_begin,
+                        const uint64_t* hit_off, uint64_t nq, uint32_t* hit_entry, uint32_t* len32, uint32_t* np32,
+                        cudaStream_t s) {
+  if (nq == 0) return;
+  const unsigned grid = (unsigned)((nq + HX_WARPS - 1) / HX_WARPS);
+  DBI_LAUNCH(hits_expand_kernel, grid, Q_THREADS, 0, s, e_base, ent_off, uv, hit_begin, hit_off, nq, hit_entry, len32,
+             np32);
+}
+
+void launch_hits_gather(const uint8_t* d_res, const uint32_t* pstart, const double* e_mass, const uint32_t* e_base,
+                        uint64_t ent_off, const uint32_t* e_pat, const UniqView& uv, const uint32_t* hit_entry,
+                        const uint64_t* seq_off, const uint64_t* plo_out, uint64_t n_hits, double* o_mass,
+                        uint32_t* o_prot, uint32_t* o_off, uint16_t* o_len, uint32_t* o_pat, uint8_t* o_flanks,
+                        uint8_t* o_seq, uint32_t* o_ids, cudaStream_t s) {
+  if (n_hits == 0) return;
+  const unsigned grid = (unsigned)((n_hits + Q_THREADS - 1) / Q_THREADS);
+  DBI_LAUNCH(hits_gather_kernel, grid, Q_THREADS, 0, s, d_res, pstart, e_mass, e_base, ent_off, e_pat, uv, hit_entry,
+             seq_off, plo_out, n_hits, o_mass, o_prot, o_off, o_len, o_pat, o_flanks, o_seq, o_ids);
 }
 
 void launch_fetch_sizes(const uint32_t* e_base, uint64_t base_off, uint64_t own_lo, uint64_t own_n,

@@ -258,26 +258,28 @@ class DBIndexer:
         nb = self.index_factor
         return int(lo) // bucket_range > nb - 1 or int(hi) // bucket_range > nb - 1
 
-    def _materialise(self, begin: np.ndarray, count: np.ndarray) -> List[List[IndexedSequence]]:
+    def _materialise(self, lo: np.ndarray, hi: np.ndarray, keep: Optional[np.ndarray] = None) -> List[List[IndexedSequence]]:
+        """getSequences for a batch of ranges in ONE device pass (dbi_query_hits): the objects
+        parseAddPeptideInfo builds (DBIndexStoreSQLiteByteIndexMerge.java:452-462) -- sequence, flanks,
+        mass and protein ids all come back from the GPU; only the Python objects are made here."""
+        try:
+            h = self.index.query_hits(lo, hi)
+        except DbiError as e:
+            raise DBIndexStoreException(str(e)) from e
+        ho, so, po = (h[k].astype(np.int64) for k in ("hit_off", "seq_off", "prot_list_off"))
+        seq, flanks = h["seq"].tobytes().decode("latin-1"), h["flanks"].tobytes().decode("latin-1")
         out = []
-        for b, c in zip(begin.tolist(), count.tolist()):
-            if c == 0:
+        for q in range(len(lo)):
+            if keep is not None and not keep[q]:
                 out.append([])
                 continue
-            f = self.index.fetch(b, c)
             lst = []
-            plo = f["prot_list_off"]
-            for i in range(c):
-                pid = int(f["first_prot"][i])
-                off = int(f["first_off"][i])
-                ln = int(f["len"][i])
-                prot_seq = self.getProteinSequence(pid)
-                pep = prot_seq[off:off + ln]  # ProteinCache.getPeptideSequence (ProteinCache.java:112-127)
-                left, right = get_residues(off, ln, prot_seq)
-                pat = int(f["modpat"][i])
+            for i in range(ho[q], ho[q + 1]):
+                pat = int(h["modpat"][i])
                 pos = tuple(((pat >> (8 * k)) & 0xFF) - 1 for k in range(4) if (pat >> (8 * k)) & 0xFF)
-                ids = f["prot_ids"][int(plo[i]):int(plo[i + 1])].tolist()
-                lst.append(IndexedSequence(float(f["mass"][i]), pep, ids, left, right, off, ln, pos))
+                lst.append(IndexedSequence(float(h["mass"][i]), seq[so[i]:so[i + 1]], h["prot_ids"][po[i]:po[i + 1]].tolist(),
+                                           flanks[6 * i:6 * i + 3], flanks[6 * i + 3:6 * i + 6], int(h["first_off"][i]),
+                                           int(h["len"][i]), pos))
             out.append(lst)
         return out
 
@@ -289,14 +291,8 @@ class DBIndexer:
         t = np.asarray(tolerances, dtype=np.float64)
         lo = np.maximum(m - t, 0.0)  # Mult:324-329
         hi = m + t
-        try:
-            begin, count = self.index.query(lo, hi)
-        except DbiError as e:
-            raise DBIndexStoreException(str(e)) from e
-        for i in range(len(m)):
-            if self._out_of_buckets(lo[i], hi[i]):
-                count[i] = 0
-        return self._materialise(begin, count)
+        keep = np.array([not self._out_of_buckets(lo[i], hi[i]) for i in range(len(m))], dtype=bool)
+        return self._materialise(lo, hi, keep)
 
     def getSequencesUsingDaltonTolerance(self, precursorMass: float, massToleranceInDa: float) -> List[IndexedSequence]:
         """DBIndexer.java:762-772 -> DBIndexStoreSQLiteMult.getSequences (Mult:315-350)."""
@@ -340,12 +336,8 @@ class DBIndexer:
             return []
         lo = np.array([m[0] for m in merged])
         hi = np.array([m[1] for m in merged])
-        try:
-            begin, count = self.index.query(lo, hi)
-        except DbiError as e:
-            raise DBIndexStoreException(str(e)) from e
         out: List[IndexedSequence] = []
-        for lst in self._materialise(begin, count):
+        for lst in self._materialise(lo, hi):
             out.extend(lst)
         return out
 

