@@ -91,7 +91,7 @@ void launch_split_entries(const uint64_t* skey, const uint64_t* spayload, uint64
 
 // Group path (class sequences <= 32, mods_grp.cu): one sort record per (peptide, class sequence)
 // group; payload = peptide << 32 | sequence << 27 | variant count.
-constexpr int kExpTile = 1024;  // entries per CTA of the expansion
+constexpr int kExpTile = 512;  // entries per CTA of the expansion
 // cmask[u * C + c] = 64-bit mask of the sites of shift class c in peptide u (all zero for peptides
 // longer than 64 residues, which are counted into *n_long).
 void launch_site_masks(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const uint32_t* u_gpos,

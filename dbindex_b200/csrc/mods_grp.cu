@@ -303,9 +303,9 @@ constexpr uint8_t kSlowGroup = 0xfe;   // k = 4, or the tile's list pool is full
 // shared pool and appends one record per block that overlaps the tile; phase 2 max-scans the block
 // heads so that every entry knows its block; phase 3 (thread per entry) is then
 //   rank in block -> (a, b) by one multiplication -> two byte loads -> pattern -> three coalesced stores.
-constexpr int ET_THREADS = 256;
+constexpr int ET_THREADS = 128;
 constexpr int ET_PER = kExpTile / ET_THREADS;
-constexpr int EP_POOL = 6144;  // bytes of site lists shared by the groups of a tile; pool[0] = 0 = "no site"
+constexpr int EP_POOL = 3072;  // bytes of site lists shared by the groups of a tile; pool[0] = 0 = "no site"
 
 struct ExpBlk {    // 16 bytes, read with one LDS.128
   int32_t start;   // tile-local entry of the block's first entry (may be negative)

@@ -180,10 +180,17 @@ def getDefaultDBIndexParams(fastaFilePath, inMemoryIndex: Optional[bool] = None,
         enzymeOffset=pr["default_enzyme_offset"], useMonoParent=mono)
 
 
-def getDefaultDBIndexParamsForCrosslinkerAnalysis(fastaFilePath, inMemoryIndex: Optional[bool] = None):
-    """DBIndexImpl.java:342-372,443-491: no H2O + proton and mandatory internal K.  The mandatory
-    internal residues (DBIndexer.java:334-344) are a "next" row of the scope table: not built yet."""
-    raise DBIndexerException("mandatoryInternalAAs (cross-linker parameter set) is not supported by the GPU index yet")
+def getDefaultDBIndexParamsForCrosslinkerAnalysis(fastaFilePath, inMemoryIndex: Optional[bool] = None,
+                                                  use_mono: Optional[bool] = None, **overrides) -> DBIndexSearchParams:
+    """DBIndexImpl.getDefaultDBIndexParamsForCrosslinkerAnalysis (DBIndexImpl.java:342-372,443-491): the
+    dbindex.properties defaults, but H2O + proton is NOT added to the peptide masses (:473) and every indexed
+    peptide needs one of `mandatory_internal_AAs` (= "K") as an internal residue (:477-478; semantics
+    DBIndexer.java:334-344 and DBIndexStoreSQLiteMult.java:245-263, applied by the digestion kernels)."""
+    kw = dict(add_h2o_proton=0, mandatory_internal=DBINDEX_PROPERTIES["mandatory_internal_AAs"])
+    kw.update(overrides)
+    sp = getDefaultDBIndexParams(fastaFilePath, inMemoryIndex, use_mono, **kw)
+    sp.mandatoryInternalAAs = kw["mandatory_internal"]
+    return sp
 
 
 def getDefaultDBIndexParamsForProteoformAnalysis(*args, **kwargs):

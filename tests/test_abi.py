@@ -111,5 +111,9 @@ def test_default_dbindex_params_factory_mirrors_the_reference():
     # the registry key separates everything that shapes the index
     assert sp.key() != mono.key() and sp.key() == getDefaultDBIndexParams("/data/uniprot.fasta").key()
     assert sp.key() != getDefaultDBIndexParams("/data/uniprot.fasta", max_missed=2).key()
-    with pytest.raises(DBIndexerException):
-        getDefaultDBIndexParamsForCrosslinkerAnalysis("x.fasta")
+    # cross-linker set (DBIndexImpl.java:443-491): no H2O + proton, mandatory internal K
+    xl = getDefaultDBIndexParamsForCrosslinkerAnalysis("x.fasta")
+    assert xl.params.add_h2o_proton == 0 and xl.params.has_mandatory == 1 and xl.mandatoryInternalAAs == "K"
+    assert [chr(i) for i in range(256) if xl.params.is_mandatory[i]] == ["K"]
+    assert xl.key() != getDefaultDBIndexParams("x.fasta").key()
+    assert DBIndexerException is not None
