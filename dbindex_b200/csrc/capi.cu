@@ -121,9 +121,16 @@ struct DevBuf {
     a = &arena;
     p = arena.get(b, &bytes);
   }
+  // a view into memory owned by somebody else (a multi-GPU window): release() only forgets it
+  void borrow(void* ptr, size_t b) {
+    release();
+    a = nullptr;
+    p = ptr;
+    bytes = b;
+  }
   void release() {
     if (p) {
-      a->put(p, bytes);
+      if (a) a->put(p, bytes);
       p = nullptr;
       bytes = 0;
     }
@@ -185,19 +192,31 @@ struct dbi_handle {
   // kept raw records (params.keep_emitted)
   DevBuf k_mass, k_gpos, k_prot, k_len;
 
-  // multi-GPU staged build (dbi_mg_*): this rank, and the slice of the replicated unique tables
-  // it owns; without mods the entries of a rank are that slice (entry i = unique ent_base_off + i)
+  // ---- sharded build (dbi_mg_*, capi_mg.inl) ----
+  // Three WINDOWS per rank are visible to the other ranks (mapped peer memory over NVLink):
+  //   0 proteome: the packed residues of ALL ranks + their protein starts (every rank packs its own
+  //     shard in place and pulls the others);  1 arena: what the exchanges deliver to this rank;
+  //   2 unique tables: first occurrence + protein lists of the peptides this rank owns.
+  struct MgWindow {
+    void* p = nullptr;                 // local allocation (exportable)
+    uint64_t cap = 0;
+    void* peer[kMaxRanks] = {};        // mapped base of every rank's window (own rank: p)
+    uint64_t peer_cap[kMaxRanks] = {};
+  };
   int mg_rank = 0, mg_world = 1;
+  MgWindow win[3];
+  uint64_t prot_off[kMaxRanks + 1] = {};  // global id of every rank's first protein
+  uint64_t pos_off[kMaxRanks + 1] = {};   // buffer position of every rank's first separator
+  bool mg_layout = false;                 // dbi_mg_set_shards done (d_res / d_pstart are views of window 0)
   uint64_t ent_base_off = 0;  // global id of this rank's first unique peptide (0 on a single GPU)
-  // sharded build with mods: (gpos, len) of EVERY rank's unique peptides, by global id -- all a
-  // rank needs to expand the groups it receives; the other unique tables stay with their owner
-  DevBuf ug_gpos, ug_len, ug_nlong;
-  uint64_t n_unique_global = 0;
+  uint64_t uoff[kMaxRanks + 1] = {};      // global id of every rank's first unique peptide
+  uint64_t uniq_cap[kMaxRanks] = {};      // layout capacity of every rank's window 2
   DevBuf mg_mass, mg_gpos, mg_prot, mg_len;  // local records between digest and exchange
   uint64_t mg_n = 0;
-  DevBuf mg_vkey, mg_vpay;                   // local variants between expansion and exchange
+  DevBuf mg_vkey, mg_vpay;                   // local groups / variants between listing and exchange
   uint64_t mg_v = 0;
-  DevBuf mg_dest, mg_idx[2], mg_counts, mg_thr;
+  uint64_t mg_recv[2] = {};                  // items delivered to this rank by exchange 0 / 1
+  uint64_t mg_thr[2][kMaxRanks] = {};        // key thresholds of the two exchanges (query routing)
 
   // pending result of dbi_query_hits (device side), read by dbi_query_hits_read
   struct HitResult {
@@ -381,12 +400,12 @@ void free_index(dbi_handle* h) {
   h->cmask_n = UINT64_MAX;
   h->k_mass.release(); h->k_gpos.release(); h->k_prot.release(); h->k_len.release();
   h->mg_mass.release(); h->mg_gpos.release(); h->mg_prot.release(); h->mg_len.release();
-  h->mg_vkey.release(); h->mg_vpay.release(); h->mg_dest.release(); h->mg_idx[0].release(); h->mg_idx[1].release();
-  h->mg_counts.release(); h->mg_thr.release();
+  h->mg_vkey.release(); h->mg_vpay.release();
   h->mg_n = h->mg_v = 0;
+  h->mg_recv[0] = h->mg_recv[1] = 0;
+  h->mg_layout = false;
   h->ent_base_off = 0;
-  h->ug_gpos.release(); h->ug_len.release(); h->ug_nlong.release();
-  h->n_unique_global = 0;
+  std::memset(h->uoff, 0, sizeof(h->uoff));
   h->n_emitted = h->n_unique = h->n_entries = 0;
   h->spans.clear();
   h->ev_used = 0;
@@ -492,7 +511,7 @@ void pack_residues(dbi_handle* h) {
   h->d_pstart.alloc(((uint64_t)n_prot + 1) * 4, h->arena);
   DBI_CUDA(cudaMemsetAsync((uint8_t*)h->d_res.p + res_end, 0, padded - res_end, h->stream));
   launch_pack(h->d_raw.as<uint8_t>(), h->d_off.as<uint64_t>(), n_prot, n_res, h->d_res.as<uint8_t>(),
-              h->d_pstart.as<uint32_t>(), h->d_err.as<uint32_t>(), h->stream);
+              h->d_pstart.as<uint32_t>(), 0u, h->d_err.as<uint32_t>(), h->stream);
   h->st.algo_bytes[DBI_STAGE_PACK] += 2 * n_res + (uint64_t)n_prot * 12;
 }
 
@@ -511,6 +530,22 @@ struct KeySpace {
   KeySpace(double lo, double hi) : base_bits(dbits(lo)), nbits(bit_length(dbits(hi) - dbits(lo))) {}
 };
 
+inline uint64_t al256(uint64_t x) { return (x + 255) & ~255ull; }
+
+// Window 2 of a sharded build: the unique tables of one rank, laid out by the CAPACITY of the window
+// (= the number of records exchange 0 delivered to that rank), which every rank knows.
+struct UniqLayout {
+  uint64_t gpos, prot, len, plo, plist, total;
+  explicit UniqLayout(uint64_t cap) {
+    gpos = 0;
+    prot = gpos + al256(4 * cap);
+    len = prot + al256(4 * cap);
+    plo = len + al256(2 * cap);
+    plist = plo + al256(8 * (cap + 1));
+    total = plist + al256(4 * cap);
+  }
+};
+
 // K7 + K8: sort N records by (mass, sequence hash, arrival order), merge equal peptides into
 // the handle's unique tables (u_*, plist).
 int sort_dedup(dbi_handle* h, const RecView& r, uint64_t N, const KeySpace& ks) {
@@ -522,7 +557,8 @@ int sort_dedup(dbi_handle* h, const RecView& r, uint64_t N, const KeySpace& ks) 
   h->n_unique = 0;
   h->st.n_unique = 0;
   if (N == 0) {
-    h->u_plo.alloc(8, h->arena);
+    if (h->mg_world > 1 && h->win[2].p) h->u_plo.borrow((uint8_t*)h->win[2].p + UniqLayout(h->uniq_cap[h->mg_rank]).plo, 8);
+    else h->u_plo.alloc(8, h->arena);
     DBI_CUDA(cudaMemsetAsync(h->u_plo.p, 0, 8, s));
     return DBI_OK;
   }
@@ -626,11 +662,25 @@ int sort_dedup(dbi_handle* h, const RecView& r, uint64_t N, const KeySpace& ks) 
     h->n_unique = n_unique;
     h->st.n_unique = n_unique;
     h->u_mass.alloc(n_unique * 8, h->arena);
-    h->u_gpos.alloc(n_unique * 4, h->arena);
-    h->u_prot.alloc(n_unique * 4, h->arena);
-    h->u_len.alloc(n_unique * 2, h->arena);
-    h->u_plo.alloc((n_unique + 1) * 8, h->arena);
-    h->plist.alloc(N * 4, h->arena);
+    if (h->mg_world > 1) {  // the other ranks read these through their mapping of window 2
+      const UniqLayout L(h->uniq_cap[h->mg_rank]);
+      uint8_t* base = (uint8_t*)h->win[2].p;
+      if (!base || h->win[2].cap < L.total || h->uniq_cap[h->mg_rank] < N) {
+        set_error("window 2 (unique tables) is smaller than the %llu records delivered", (unsigned long long)N);
+        return DBI_EINVAL;
+      }
+      h->u_gpos.borrow(base + L.gpos, n_unique * 4);
+      h->u_prot.borrow(base + L.prot, n_unique * 4);
+      h->u_len.borrow(base + L.len, n_unique * 2);
+      h->u_plo.borrow(base + L.plo, (n_unique + 1) * 8);
+      h->plist.borrow(base + L.plist, N * 4);
+    } else {
+      h->u_gpos.alloc(n_unique * 4, h->arena);
+      h->u_prot.alloc(n_unique * 4, h->arena);
+      h->u_len.alloc(n_unique * 2, h->arena);
+      h->u_plo.alloc((n_unique + 1) * 8, h->arena);
+      h->plist.alloc(N * 4, h->arena);
+    }
     launch_dedup_emit(mkey[sorted].as<uint64_t>(), idx[0].as<uint32_t>(), flags.as<uint8_t>(),
                       tile_offs.as<uint64_t>(), r.gpos, r.prot, r.len, N, base_bits, n_unique, h->u_mass.as<double>(),
                       h->u_gpos.as<uint32_t>(), h->u_prot.as<uint32_t>(), h->u_len.as<uint16_t>(),
@@ -801,7 +851,15 @@ int emit_groups(dbi_handle* h, uint32_t tile0, uint32_t ntiles, const KeySpace& 
 }
 
 // K7 on NG group records (clobbered), then K6x: expand the sorted groups into the entry arrays.
-int sort_expand_groups(dbi_handle* h, uint64_t* key_in, uint64_t* pay_in, uint64_t NG, const KeySpace& ks) {
+// side (sharded build): the groups arrived from any rank; their payload names an ARRIVAL ROW, and the
+// row's site masks / peptide global id travelled with the group (side tables in the arena).
+struct GroupSide {
+  const uint64_t* cmask = nullptr;   // [row * C + c]
+  const uint32_t* gid = nullptr;     // [row]
+  const UniqView* uv = nullptr;      // where the peptides' (gpos, len) live: only peptides longer than 64 residues need it
+};
+int sort_expand_groups(dbi_handle* h, uint64_t* key_in, uint64_t* pay_in, uint64_t NG, const KeySpace& ks,
+                       const GroupSide* side = nullptr) {
   cudaStream_t s = h->stream;
   if (NG >= (1ull << 32)) {
     set_error("more than 2^32 variant groups on one GPU (%llu)", (unsigned long long)NG);
@@ -813,27 +871,8 @@ int sort_expand_groups(dbi_handle* h, uint64_t* key_in, uint64_t* pay_in, uint64
     h->st.n_entries = 0;
     return DBI_OK;
   }
-  // sharded build: the groups received here belong to any rank's peptides.  Their site masks come
-  // from a table over ALL unique peptides when that is affordable (8 C bytes each, computed locally
-  // from the replicated residues: cheaper than re-deriving the masks per group up to ~8 ranks),
-  // otherwise the expansion kernel rebuilds them per group from (gpos, len).
-  const bool sharded = h->ug_gpos.p != nullptr;
-  const uint64_t mask_bytes = h->n_unique_global * (uint64_t)h->cfg.n_classes * 8;
-  static const bool no_table = std::getenv("DBI_MG_NO_MASK_TABLE") != nullptr;  // test hook
-  const bool global_masks = sharded;
-  (void)no_table;
-  DevBuf ug_cmask, scratch_nlong;
-  if (!sharded) {
-    ensure_site_masks(h);
-  } else if (global_masks) {
-    Stage sg(h, DBI_STAGE_MOD_COUNT);
-    ug_cmask.alloc(std::max<uint64_t>(mask_bytes, 8), h->arena);
-    scratch_nlong.alloc(16, h->arena);
-    DBI_CUDA(cudaMemsetAsync(scratch_nlong.p, 0, 16, s));
-    launch_site_masks(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->ug_gpos.as<uint32_t>(),
-                      h->ug_len.as<uint16_t>(), h->n_unique_global, ug_cmask.as<uint64_t>(),
-                      (unsigned long long*)scratch_nlong.p, s);
-  }
+  const bool sharded = side != nullptr;
+  if (!sharded) ensure_site_masks(h);
   DevBuf key2, pay2, vtmp;
   key2.alloc(NG * 8, h->arena);
   pay2.alloc(NG * 8, h->arena);
@@ -865,14 +904,16 @@ int sort_expand_groups(dbi_handle* h, uint64_t* key_in, uint64_t* pay_in, uint64
     launch_full_scan_u32_to_u64(cnt.as<uint32_t>(), NG, eoff.as<uint64_t>(), stmp.p, s);
     DBI_CUDA(cudaMemsetAsync(lcount.p, 0, 16, s));
     DBI_CUDA(cudaMemcpyAsync(&V, eoff.as<uint64_t>() + NG, 8, cudaMemcpyDeviceToHost, s));
-    DBI_CUDA(cudaMemcpyAsync(&n_long, sharded ? h->ug_nlong.p : h->d_nlong.p, 8, cudaMemcpyDeviceToHost, s));
+    if (!sharded) DBI_CUDA(cudaMemcpyAsync(&n_long, h->d_nlong.p, 8, cudaMemcpyDeviceToHost, s));
     DBI_CUDA(cudaStreamSynchronize(s));
+    if (sharded) n_long = NG;  // unknown here: any received group may belong to a long peptide
     if (V >= (1ull << 32)) {
       set_error("more than 2^32 index entries on one GPU (%llu)", (unsigned long long)V);
       return DBI_ERANGE;
     }
     // groups of long peptides that can land here: at most every modified class sequence of each
-    const uint64_t long_cap = std::min<uint64_t>(NG, n_long * (uint64_t)(h->cfg.n_seq - 1));
+    const uint64_t long_cap = std::min<uint64_t>(sharded ? std::min<uint64_t>(NG, 1u << 22) : NG,
+                                                 n_long * (uint64_t)(h->cfg.n_seq - 1));
     const uint64_t tiles = (V + kExpTile - 1) / kExpTile;
     h->e_mass.alloc(V * 8, h->arena);
     h->e_base.alloc(V * 4, h->arena);
@@ -886,11 +927,9 @@ int sort_expand_groups(dbi_handle* h, uint64_t* key_in, uint64_t* pay_in, uint64
       xa = h->get_event();
       cudaEventRecord(xa, s);
     }
-    launch_grp_expand(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg,
-                      sharded ? h->ug_gpos.as<uint32_t>() : h->u_gpos.as<uint32_t>(),
-                      sharded ? h->ug_len.as<uint16_t>() : h->u_len.as<uint16_t>(),
-                      sharded ? ug_cmask.as<uint64_t>() : h->u_cmask.as<uint64_t>(), nullptr, vk[r],
-                      vp[r], eoff.as<uint64_t>(),
+    launch_grp_expand(h->d_res.as<uint8_t>(), h->d_tables.as<DevTables>(), h->cfg, h->u_gpos.as<uint32_t>(),
+                      h->u_len.as<uint16_t>(), sharded ? side->cmask : h->u_cmask.as<uint64_t>(),
+                      sharded ? side->gid : nullptr, sharded ? side->uv : nullptr, vk[r], vp[r], eoff.as<uint64_t>(),
                       tfirst.as<uint32_t>(), NG, V, ks.base_bits, h->e_mass.as<double>(), h->e_base.as<uint32_t>(),
                       h->e_pat.as<uint32_t>(), llist.as<uint32_t>(), lcount.as<uint32_t>(), (uint32_t)long_cap,
                       h->d_err.as<uint32_t>(), s);
@@ -942,8 +981,42 @@ void finish_stats(dbi_handle* h) {
   resolve_spans(h);
   h->st.device_bytes = h->d_res.bytes + h->d_pstart.bytes + h->u_mass.bytes + h->u_gpos.bytes + h->u_prot.bytes +
                        h->u_len.bytes + h->u_plo.bytes + h->plist.bytes + h->e_mass.bytes + h->e_base.bytes +
-                       h->e_pat.bytes + h->ug_gpos.bytes + h->ug_len.bytes;
+                       h->e_pat.bytes;
 }
+
+// The unique-peptide tables a fetch resolves base peptides through: this GPU's own, and in a
+// sharded build the mapped tables of every connected rank.
+UniqView uniq_view(dbi_handle* h) {
+  UniqView uv;
+  std::memset(&uv, 0, sizeof(uv));
+  if (h->mg_world <= 1) {
+    uv.world = 1;
+    uv.gpos[0] = h->u_gpos.as<uint32_t>();
+    uv.prot[0] = h->u_prot.as<uint32_t>();
+    uv.len[0] = h->u_len.as<uint16_t>();
+    uv.plo[0] = h->u_plo.as<uint64_t>();
+    uv.plist[0] = h->plist.as<uint32_t>();
+    uv.uoff[0] = 0;
+    uv.uoff[1] = h->n_unique;
+    return uv;
+  }
+  uv.world = h->mg_world;
+  for (int r = 0; r < h->mg_world; ++r) {
+    uv.uoff[r] = h->uoff[r];
+    uint8_t* base = (uint8_t*)h->win[2].peer[r];
+    if (!base) continue;  // not connected: its peptides come back as DBI_REMOTE_BASE
+    const UniqLayout L(h->uniq_cap[r]);
+    uv.gpos[r] = (const uint32_t*)(base + L.gpos);
+    uv.prot[r] = (const uint32_t*)(base + L.prot);
+    uv.len[r] = (const uint16_t*)(base + L.len);
+    uv.plo[r] = (const uint64_t*)(base + L.plo);
+    uv.plist[r] = (const uint32_t*)(base + L.plist);
+  }
+  uv.uoff[h->mg_world] = h->uoff[h->mg_world];
+  return uv;
+}
+
+void mg_release(dbi_handle* h);  // capi_mg.inl
 
 }  // namespace
 
@@ -1290,6 +1363,7 @@ int dbi_fetch(dbi_handle* h, uint64_t begin, uint64_t count, double* mass, uint3
   }
   cudaStream_t s = h->stream;
   const uint64_t tiles = (count + kScanTile - 1) / kScanTile;
+  const UniqView uv = uniq_view(h);
   DevBuf sizes, tcnt, toff;
   sizes.alloc(count * 4, h->arena);
   tcnt.alloc(tiles * 4, h->arena);
@@ -1297,8 +1371,7 @@ int dbi_fetch(dbi_handle* h, uint64_t begin, uint64_t count, double* mass, uint3
   uint64_t total_ids = 0;
   {
     Stage sg(h, DBI_STAGE_FETCH);
-    launch_fetch_sizes(h->entry_base(), h->ent_base_off, h->ent_base_off, h->n_unique, h->u_plo.as<uint64_t>(), begin,
-                       count, sizes.as<uint32_t>(), tcnt.as<uint32_t>(), s);
+    launch_fetch_sizes(h->entry_base(), h->ent_base_off, uv, begin, count, sizes.as<uint32_t>(), tcnt.as<uint32_t>(), s);
     launch_scan_u32_to_u64(tcnt.as<uint32_t>(), tiles, toff.as<uint64_t>(), s);
     total_ids = read_u64(h, toff.as<uint64_t>() + tiles);
   }
@@ -1318,12 +1391,10 @@ int dbi_fetch(dbi_handle* h, uint64_t begin, uint64_t count, double* mass, uint3
   if (want_ids) o_ids.alloc(total_ids * 4, h->arena);
   {
     Stage sg(h, DBI_STAGE_FETCH);
-    launch_fetch_gather(h->entry_mass(), h->entry_base(), h->ent_base_off, h->ent_base_off, h->n_unique,
-                        h->ug_len.as<uint16_t>(), h->entry_pat(), h->u_gpos.as<uint32_t>(),
-                        h->u_prot.as<uint32_t>(), h->u_len.as<uint16_t>(), h->u_plo.as<uint64_t>(),
-                        h->plist.as<uint32_t>(), h->d_pstart.as<uint32_t>(), begin, count, sizes.as<uint32_t>(),
-                        toff.as<uint64_t>(), o_mass.as<double>(), o_prot.as<uint32_t>(), o_off.as<uint32_t>(),
-                        o_len.as<uint16_t>(), o_pat.as<uint32_t>(), o_lo.as<uint64_t>(), o_ids.as<uint32_t>(), s);
+    launch_fetch_gather(h->entry_mass(), h->entry_base(), h->ent_base_off, uv, h->entry_pat(),
+                        h->d_pstart.as<uint32_t>(), begin, count, sizes.as<uint32_t>(), toff.as<uint64_t>(),
+                        o_mass.as<double>(), o_prot.as<uint32_t>(), o_off.as<uint32_t>(), o_len.as<uint16_t>(),
+                        o_pat.as<uint32_t>(), o_lo.as<uint64_t>(), o_ids.as<uint32_t>(), s);
     h->st.algo_bytes[DBI_STAGE_FETCH] += count * (20 + 8 + 26) + total_ids * 8;
   }
   if (mass) DBI_CUDA(cudaMemcpyAsync(mass, o_mass.p, count * 8, cudaMemcpyDeviceToHost, s));
@@ -1338,23 +1409,6 @@ int dbi_fetch(dbi_handle* h, uint64_t begin, uint64_t count, double* mass, uint3
   return DBI_OK;
   DBI_API_END
 }
-
-namespace {
-// the unique-peptide tables a fetch resolves base peptides through: this GPU's own
-UniqView uniq_view(dbi_handle* h) {
-  UniqView uv;
-  std::memset(&uv, 0, sizeof(uv));
-  uv.world = 1;
-  uv.gpos[0] = h->u_gpos.as<uint32_t>();
-  uv.prot[0] = h->u_prot.as<uint32_t>();
-  uv.len[0] = h->u_len.as<uint16_t>();
-  uv.plo[0] = h->u_plo.as<uint64_t>();
-  uv.plist[0] = h->plist.as<uint32_t>();
-  uv.uoff[0] = h->ent_base_off;
-  uv.uoff[1] = h->ent_base_off + h->n_unique;
-  return uv;
-}
-}  // namespace
 
 int dbi_query_hits(dbi_handle* h, const double* lo, const double* hi, uint64_t nq, dbi_hit_counts* counts) {
   DBI_API_BEGIN(h)
@@ -1616,413 +1670,6 @@ int dbi_debug_emitted(dbi_handle* h, uint64_t capacity, double* mass, uint32_t* 
   DBI_API_END
 }
 
-// ---- multi-GPU staged build ------------------------------------------------------------------
-
-int dbi_mg_begin(dbi_handle* h, int rank, int world) {
-  DBI_API_BEGIN(h)
-  if (h->built) {
-    set_error("index already built");
-    return DBI_EALREADY;
-  }
-  if (world < 1 || world > 64 || rank < 0 || rank >= world) {
-    set_error("bad rank %d / world %d (1..64)", rank, world);
-    return DBI_EINVAL;
-  }
-  h->mg_rank = rank;
-  h->mg_world = world;
-  return DBI_OK;
-  DBI_API_END
-}
-
-int dbi_mg_digest(dbi_handle* h, uint64_t* n_records) {
-  DBI_API_BEGIN(h)
-  if (h->built) {
-    set_error("index already built");
-    return DBI_EALREADY;
-  }
-  cudaStream_t s = h->stream;
-  ensure_uploaded(h);
-  const uint32_t zero = 0;
-  DBI_CUDA(cudaMemcpyAsync(h->d_err.p, &zero, 4, cudaMemcpyHostToDevice, s));
-  pack_residues(h);
-  const uint32_t n_prot = (uint32_t)(h->h_off.size() - 1);
-  const uint64_t tiles_all = ((uint64_t)h->res_end + kDigestTile - 1) / kDigestTile;
-  // contiguous, ascending tile ranges: rank order == global emission order
-  const uint32_t t0 = (uint32_t)(tiles_all * h->mg_rank / h->mg_world);
-  const uint32_t t1 = (uint32_t)(tiles_all * (h->mg_rank + 1) / h->mg_world);
-  const uint32_t nt = t1 - t0;
-  DevBuf tile_counts, tile_offs, start_cnt;
-  tile_counts.alloc((uint64_t)nt * 4, h->arena);
-  tile_offs.alloc(((uint64_t)nt + 1) * 8, h->arena);
-  start_cnt.alloc(std::max<uint64_t>(1, nt) * kDigestTile, h->arena);
-  uint64_t N = 0;
-  {
-    Stage sg(h, DBI_STAGE_DIGEST_COUNT);
-    launch_digest_count(h->d_res.as<uint8_t>(), h->res_end, h->res_alloc, h->d_tables.as<DevTables>(), h->cfg, t0, nt,
-                        start_cnt.as<uint8_t>(), tile_counts.as<uint32_t>(), h->d_err.as<uint32_t>(), s);
-    launch_scan_u32_to_u64(tile_counts.as<uint32_t>(), nt, tile_offs.as<uint64_t>(), s);
-    N = read_u64(h, tile_offs.as<uint64_t>() + nt);
-    h->st.algo_bytes[DBI_STAGE_DIGEST_COUNT] += (uint64_t)nt * kDigestTile + (uint64_t)nt * 16;
-  }
-  if (int rc = check_err_bits(read_err(h))) {
-    free_index(h);
-    return rc;
-  }
-  if (N >= (1ull << 32)) {
-    set_error("more than 2^32 emitted records on one GPU");
-    return DBI_ERANGE;
-  }
-  h->mg_mass.alloc(N * 8, h->arena);
-  h->mg_gpos.alloc(N * 4, h->arena);
-  h->mg_prot.alloc(N * 4, h->arena);
-  h->mg_len.alloc(N * 2, h->arena);
-  {
-    Stage sg(h, DBI_STAGE_DIGEST_EMIT);
-    launch_digest_emit(h->d_res.as<uint8_t>(), h->res_end, h->res_alloc, h->d_tables.as<DevTables>(), h->cfg, t0, nt,
-                       start_cnt.as<uint8_t>(), tile_offs.as<uint64_t>(), h->d_pstart.as<uint32_t>(), n_prot,
-                       h->mg_mass.as<uint64_t>(),
-                       h->mg_gpos.as<uint32_t>(), h->mg_prot.as<uint32_t>(), h->mg_len.as<uint16_t>(),
-                       h->d_err.as<uint32_t>(), s);
-    h->st.algo_bytes[DBI_STAGE_DIGEST_EMIT] += (uint64_t)nt * kDigestTile + N * 18;
-  }
-  DBI_CUDA(cudaStreamSynchronize(s));
-  h->mg_n = N;
-  h->n_emitted = N;
-  h->st.n_emitted = N;
-  if (n_records) *n_records = N;
-  return DBI_OK;
-  DBI_API_END
-}
-
-namespace {
-// key array, count and key offset of an exchange stage
-struct MgStage {
-  const uint64_t* key;
-  uint64_t n;
-  uint64_t sub;
-};
-MgStage mg_stage(dbi_handle* h, int stage, const KeySpace& ks) {
-  if (stage == 0) return {h->mg_mass.as<uint64_t>(), h->mg_n, ks.base_bits};  // raw mass bits
-  return {h->mg_vkey.as<uint64_t>(), h->mg_v, 0};                              // already key - base
-}
-}  // namespace
-
-int dbi_mg_histogram(dbi_handle* h, int stage, uint64_t* d_hist, int* shift) {
-  DBI_API_BEGIN(h)
-  if (!d_hist || (stage != 0 && stage != 1)) {
-    set_error("bad argument");
-    return DBI_EINVAL;
-  }
-  const KeySpace ks(h->p.min_mass, h->p.max_mass);
-  const MgStage st = mg_stage(h, stage, ks);
-  const int sh = ks.nbits > 12 ? ks.nbits - 12 : 0;
-  const bool weighted = stage == 1 && h->cfg.n_seq > 0;  // group records: weigh by their variant count
-  launch_mg_hist(st.key, st.n, st.sub, sh, weighted ? h->mg_vpay.as<uint64_t>() : nullptr, kGrpCntMask,
-                 (unsigned long long*)d_hist, h->stream);
-  DBI_CUDA(cudaStreamSynchronize(h->stream));
-  if (shift) *shift = sh;
-  return DBI_OK;
-  DBI_API_END
-}
-
-int dbi_mg_partition(dbi_handle* h, int stage, const uint32_t* bin_splitters, uint64_t* send_counts) {
-  DBI_API_BEGIN(h)
-  if ((h->mg_world > 1 && !bin_splitters) || !send_counts || (stage != 0 && stage != 1)) {
-    set_error("bad argument");
-    return DBI_EINVAL;
-  }
-  cudaStream_t s = h->stream;
-  const KeySpace ks(h->p.min_mass, h->p.max_mass);
-  const MgStage st = mg_stage(h, stage, ks);
-  const int sh = ks.nbits > 12 ? ks.nbits - 12 : 0;
-  const int n_thr = h->mg_world - 1;
-  uint64_t thr[64];
-  for (int d = 0; d < n_thr; ++d) {
-    if (d > 0 && bin_splitters[d] < bin_splitters[d - 1]) {
-      set_error("bin_splitters must be ascending");
-      return DBI_EINVAL;
-    }
-    thr[d] = (uint64_t)bin_splitters[d] << sh;
-  }
-  const uint64_t n = st.n;
-  h->mg_dest.alloc(n * 4, h->arena);
-  h->mg_idx[0].alloc(n * 4, h->arena);
-  h->mg_idx[1].alloc(n * 4, h->arena);
-  h->mg_counts.alloc(64 * 8, h->arena);
-  h->mg_thr.alloc(64 * 8, h->arena);
-  DBI_CUDA(cudaMemsetAsync(h->mg_counts.p, 0, 64 * 8, s));
-  if (n_thr) DBI_CUDA(cudaMemcpyAsync(h->mg_thr.p, thr, n_thr * 8, cudaMemcpyHostToDevice, s));
-  {
-    Stage sg(h, DBI_STAGE_OTHER);
-    launch_mg_dest(st.key, n, st.sub, h->mg_thr.as<uint64_t>(), n_thr, h->mg_dest.as<uint32_t>(),
-                   h->mg_idx[0].as<uint32_t>(), (unsigned long long*)h->mg_counts.p, s);
-    // stable counting sort by destination = one radix pass over the rank id
-    DevBuf dest2, tmp;
-    dest2.alloc(n * 4, h->arena);
-    tmp.alloc(radix_sort_tmp_bytes(n), h->arena);
-    uint32_t* dk[2] = {h->mg_dest.as<uint32_t>(), dest2.as<uint32_t>()};
-    uint32_t* ix[2] = {h->mg_idx[0].as<uint32_t>(), h->mg_idx[1].as<uint32_t>()};
-    const int r = radix_sort_pairs<uint32_t, uint32_t>(dk, ix, n, 0, 6, tmp.p, s, nullptr);
-    if (r == 1) h->mg_idx[0].swap(h->mg_idx[1]);  // sorted permutation in mg_idx[0]
-  }
-  uint64_t counts[64];
-  DBI_CUDA(cudaMemcpyAsync(counts, h->mg_counts.p, 64 * 8, cudaMemcpyDeviceToHost, s));
-  DBI_CUDA(cudaStreamSynchronize(s));
-  for (int d = 0; d < h->mg_world; ++d) send_counts[d] = counts[d];
-  return DBI_OK;
-  DBI_API_END
-}
-
-int dbi_mg_pack_send(dbi_handle* h, int stage, void* d0, void* d1, void* d2, void* d3) {
-  DBI_API_BEGIN(h)
-  cudaStream_t s = h->stream;
-  const uint32_t* idx = h->mg_idx[0].as<uint32_t>();
-  Stage sg(h, DBI_STAGE_OTHER);
-  if (stage == 0) {
-    const uint64_t n = h->mg_n;
-    if (n && (!d0 || !d1 || !d2 || !d3)) {
-      set_error("null send buffer");
-      return DBI_EINVAL;
-    }
-    launch_gather_u64(h->mg_mass.as<uint64_t>(), idx, n, (uint64_t*)d0, s);
-    launch_gather_u32(h->mg_gpos.as<uint32_t>(), idx, n, (uint32_t*)d1, s);
-    launch_gather_u32(h->mg_prot.as<uint32_t>(), idx, n, (uint32_t*)d2, s);
-    launch_gather_u16(h->mg_len.as<uint16_t>(), idx, n, (uint16_t*)d3, s);
-    DBI_CUDA(cudaStreamSynchronize(s));
-    h->mg_mass.release(); h->mg_gpos.release(); h->mg_prot.release(); h->mg_len.release();
-  } else if (stage == 1) {
-    const uint64_t n = h->mg_v;
-    if (n && (!d0 || !d1)) {
-      set_error("null send buffer");
-      return DBI_EINVAL;
-    }
-    launch_gather_u64(h->mg_vkey.as<uint64_t>(), idx, n, (uint64_t*)d0, s);
-    launch_gather_u64(h->mg_vpay.as<uint64_t>(), idx, n, (uint64_t*)d1, s);
-    DBI_CUDA(cudaStreamSynchronize(s));
-    h->mg_vkey.release(); h->mg_vpay.release();
-  } else {
-    set_error("bad stage");
-    return DBI_EINVAL;
-  }
-  h->mg_dest.release(); h->mg_idx[0].release(); h->mg_idx[1].release();
-  return DBI_OK;
-  DBI_API_END
-}
-
-int dbi_mg_index_base(dbi_handle* h, const void* d_mass, const void* d_gpos, const void* d_prot, const void* d_len,
-                      uint64_t n) {
-  DBI_API_BEGIN(h)
-  if (n && (!d_mass || !d_gpos || !d_prot || !d_len)) {
-    set_error("null argument");
-    return DBI_EINVAL;
-  }
-  const KeySpace ks(h->p.min_mass, h->p.max_mass);
-  const RecView rv{(const uint64_t*)d_mass, (const uint32_t*)d_gpos, (const uint32_t*)d_prot, (const uint16_t*)d_len};
-  int rc = sort_dedup(h, rv, n, ks);
-  if (rc == DBI_OK) rc = check_err_bits(read_err(h));
-  if (rc == DBI_OK && n == 0) {  // empty slice: still needs (empty) tables
-    h->u_mass.alloc(8, h->arena); h->u_gpos.alloc(8, h->arena); h->u_prot.alloc(8, h->arena);
-    h->u_len.alloc(8, h->arena); h->plist.alloc(8, h->arena);
-  }
-  DBI_CUDA(cudaStreamSynchronize(h->stream));
-  return rc;
-  DBI_API_END
-}
-
-int dbi_mg_unique_counts(dbi_handle* h, uint64_t* n_unique, uint64_t* n_plist) {
-  DBI_API_BEGIN(h)
-  if (n_unique) *n_unique = h->n_unique;
-  if (n_plist) *n_plist = h->n_unique ? read_u64(h, h->u_plo.as<uint64_t>() + h->n_unique) : 0;
-  return DBI_OK;
-  DBI_API_END
-}
-
-int dbi_mg_export_unique(dbi_handle* h, void* d_gpos, void* d_len) {
-  DBI_API_BEGIN(h)
-  cudaStream_t s = h->stream;
-  const uint64_t u = h->n_unique;
-  if (u) {
-    if (!d_gpos || !d_len) {
-      set_error("null argument");
-      return DBI_EINVAL;
-    }
-    DBI_CUDA(cudaMemcpyAsync(d_gpos, h->u_gpos.p, u * 4, cudaMemcpyDeviceToDevice, s));
-    DBI_CUDA(cudaMemcpyAsync(d_len, h->u_len.p, u * 2, cudaMemcpyDeviceToDevice, s));
-    DBI_CUDA(cudaStreamSynchronize(s));
-  }
-  return DBI_OK;
-  DBI_API_END
-}
-
-int dbi_mg_import_unique(dbi_handle* h, const uint64_t* rank_unique, const void* d_gpos, const void* d_len) {
-  DBI_API_BEGIN(h)
-  if (!rank_unique) {
-    set_error("null argument");
-    return DBI_EINVAL;
-  }
-  cudaStream_t s = h->stream;
-  uint64_t U = 0, off = 0;
-  for (int r = 0; r < h->mg_world; ++r) {
-    if (r == h->mg_rank) off = U;
-    U += rank_unique[r];
-  }
-  if (U >= (1ull << 32)) {
-    set_error("more than 2^32 unique peptides in total");
-    return DBI_ERANGE;
-  }
-  if (rank_unique[h->mg_rank] != h->n_unique) {
-    set_error("rank_unique[%d] = %llu but this rank holds %llu unique peptides", h->mg_rank,
-              (unsigned long long)rank_unique[h->mg_rank], (unsigned long long)h->n_unique);
-    return DBI_EINVAL;
-  }
-  if (U && (!d_gpos || !d_len)) {
-    set_error("null argument");
-    return DBI_EINVAL;
-  }
-  h->ug_gpos.alloc(std::max<uint64_t>(U, 1) * 4, h->arena);
-  h->ug_len.alloc(std::max<uint64_t>(U, 1) * 2, h->arena);
-  h->ug_nlong.alloc(16, h->arena);
-  DBI_CUDA(cudaMemsetAsync(h->ug_nlong.p, 0, 16, s));
-  if (U) {
-    DBI_CUDA(cudaMemcpyAsync(h->ug_gpos.p, d_gpos, U * 4, cudaMemcpyDeviceToDevice, s));
-    DBI_CUDA(cudaMemcpyAsync(h->ug_len.p, d_len, U * 2, cudaMemcpyDeviceToDevice, s));
-    launch_count_long(h->ug_len.as<uint16_t>(), U, (unsigned long long*)h->ug_nlong.p, s);
-  }
-  DBI_CUDA(cudaStreamSynchronize(s));
-  h->n_unique_global = U;
-  h->ent_base_off = off;
-  h->n_entries = h->n_unique;  // until the groups are indexed
-  return DBI_OK;
-  DBI_API_END
-}
-
-int dbi_mg_finish(dbi_handle* h) {
-  DBI_API_BEGIN(h)
-  if (h->cfg.max_mods != 0) {
-    set_error("dbi_mg_finish is for builds without differential mods; use dbi_mg_index_variants");
-    return DBI_EINVAL;
-  }
-  h->e_mass.release(); h->e_base.release(); h->e_pat.release();
-  h->n_entries = h->n_unique;  // the entries of this rank are its own unique peptides
-  h->st.n_entries = h->n_entries;
-  h->built = true;
-  finish_stats(h);
-  return DBI_OK;
-  DBI_API_END
-}
-
-int dbi_mg_own_tiles(dbi_handle* h, uint32_t* tile_begin, uint32_t* n_tiles) {
-  DBI_API_BEGIN(h)
-  if (!tile_begin || !n_tiles) {
-    set_error("null argument");
-    return DBI_EINVAL;
-  }
-  *tile_begin = 0;
-  *n_tiles = (uint32_t)((h->n_unique + kModTile - 1) / kModTile);
-  return DBI_OK;
-  DBI_API_END
-}
-
-int dbi_mg_lookup_unique(dbi_handle* h, const uint32_t* gids, uint64_t n, uint32_t* first_prot, uint32_t* first_off,
-                         uint16_t* len, uint64_t* prot_list_off, uint32_t* prot_ids, uint64_t prot_ids_capacity,
-                         uint64_t* n_prot_ids) {
-  DBI_API_BEGIN(h)
-  if (!h->built) {
-    set_error("Indexer is not initialized");
-    return DBI_ENOTINIT;
-  }
-  if (n_prot_ids) *n_prot_ids = 0;
-  if (n == 0) {
-    if (prot_list_off) prot_list_off[0] = 0;
-    return DBI_OK;
-  }
-  if (!gids) {
-    set_error("null argument");
-    return DBI_EINVAL;
-  }
-  for (uint64_t i = 0; i < n; ++i)
-    if ((uint64_t)gids[i] - h->ent_base_off >= h->n_unique) {
-      set_error("unique peptide %u is not held by this rank ([%llu, +%llu))", gids[i],
-                (unsigned long long)h->ent_base_off, (unsigned long long)h->n_unique);
-      return DBI_EINVAL;
-    }
-  cudaStream_t s = h->stream;
-  const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
-  DevBuf d_g, sizes, tcnt, toff, o_prot, o_off, o_len, o_lo, o_ids;
-  d_g.alloc(n * 4, h->arena);
-  sizes.alloc(n * 4, h->arena);
-  tcnt.alloc(tiles * 4, h->arena);
-  toff.alloc((tiles + 1) * 8, h->arena);
-  DBI_CUDA(cudaMemcpyAsync(d_g.p, gids, n * 4, cudaMemcpyHostToDevice, s));
-  launch_fetch_sizes(d_g.as<uint32_t>(), 0, h->ent_base_off, h->n_unique, h->u_plo.as<uint64_t>(), 0, n,
-                     sizes.as<uint32_t>(), tcnt.as<uint32_t>(), s);
-  launch_scan_u32_to_u64(tcnt.as<uint32_t>(), tiles, toff.as<uint64_t>(), s);
-  const uint64_t total_ids = read_u64(h, toff.as<uint64_t>() + tiles);
-  if (n_prot_ids) *n_prot_ids = total_ids;
-  if (prot_ids && prot_ids_capacity < total_ids) {
-    set_error("prot_ids capacity %llu < %llu", (unsigned long long)prot_ids_capacity, (unsigned long long)total_ids);
-    return DBI_ERANGE;
-  }
-  if (first_prot) o_prot.alloc(n * 4, h->arena);
-  if (first_off) o_off.alloc(n * 4, h->arena);
-  if (len) o_len.alloc(n * 2, h->arena);
-  if (prot_list_off) o_lo.alloc((n + 1) * 8, h->arena);
-  if (prot_ids) o_ids.alloc(std::max<uint64_t>(total_ids, 1) * 4, h->arena);
-  launch_fetch_gather(nullptr, d_g.as<uint32_t>(), 0, h->ent_base_off, h->n_unique, h->ug_len.as<uint16_t>(), nullptr,
-                      h->u_gpos.as<uint32_t>(), h->u_prot.as<uint32_t>(), h->u_len.as<uint16_t>(),
-                      h->u_plo.as<uint64_t>(), h->plist.as<uint32_t>(), h->d_pstart.as<uint32_t>(), 0, n,
-                      sizes.as<uint32_t>(), toff.as<uint64_t>(), nullptr, o_prot.as<uint32_t>(), o_off.as<uint32_t>(),
-                      o_len.as<uint16_t>(), nullptr, o_lo.as<uint64_t>(), o_ids.as<uint32_t>(), s);
-  if (first_prot) DBI_CUDA(cudaMemcpyAsync(first_prot, o_prot.p, n * 4, cudaMemcpyDeviceToHost, s));
-  if (first_off) DBI_CUDA(cudaMemcpyAsync(first_off, o_off.p, n * 4, cudaMemcpyDeviceToHost, s));
-  if (len) DBI_CUDA(cudaMemcpyAsync(len, o_len.p, n * 2, cudaMemcpyDeviceToHost, s));
-  if (prot_list_off) DBI_CUDA(cudaMemcpyAsync(prot_list_off, o_lo.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
-  if (prot_ids && total_ids) DBI_CUDA(cudaMemcpyAsync(prot_ids, o_ids.p, total_ids * 4, cudaMemcpyDeviceToHost, s));
-  DBI_CUDA(cudaStreamSynchronize(s));
-  return DBI_OK;
-  DBI_API_END
-}
-
-int dbi_mg_expand(dbi_handle* h, uint32_t tile_begin, uint32_t n_tiles, uint64_t* n_variants) {
-  DBI_API_BEGIN(h)
-  const KeySpace ks(h->p.min_mass, h->p.max_mass);
-  const uint64_t all_tiles = (h->n_unique + kModTile - 1) / kModTile;
-  if ((uint64_t)tile_begin + n_tiles > all_tiles) {
-    set_error("tile range [%u, +%u) beyond %llu tiles", tile_begin, n_tiles, (unsigned long long)all_tiles);
-    return DBI_EINVAL;
-  }
-  uint64_t V = 0, NG = 0;
-  int rc;
-  if (h->cfg.n_seq > 0) {
-    rc = emit_groups(h, tile_begin, n_tiles, ks, h->mg_vkey, h->mg_vpay, &NG, &V);
-  } else {
-    rc = emit_variants(h, tile_begin, n_tiles, ks, h->mg_vkey, h->mg_vpay, &V);
-    NG = V;
-  }
-  DBI_CUDA(cudaStreamSynchronize(h->stream));
-  h->mg_v = NG;  // items that travel: group records, or variants on the per-variant path
-  if (n_variants) *n_variants = V;
-  return rc;
-  DBI_API_END
-}
-
-int dbi_mg_index_variants(dbi_handle* h, void* d_key, void* d_payload, uint64_t n) {
-  DBI_API_BEGIN(h)
-  if (n && (!d_key || !d_payload)) {
-    set_error("null argument");
-    return DBI_EINVAL;
-  }
-  const KeySpace ks(h->p.min_mass, h->p.max_mass);
-  int rc = h->cfg.n_seq > 0 ? sort_expand_groups(h, (uint64_t*)d_key, (uint64_t*)d_payload, n, ks)
-                            : sort_variants(h, (uint64_t*)d_key, (uint64_t*)d_payload, n, ks);
-  DBI_CUDA(cudaStreamSynchronize(h->stream));
-  if (rc != DBI_OK) return rc;
-  h->built = true;
-  finish_stats(h);
-  return DBI_OK;
-  DBI_API_END
-}
-
 int dbi_debug_radix_sort(dbi_handle* h, uint64_t* keys, uint64_t* vals, uint64_t n, int begin_bit, int end_bit) {
   DBI_API_BEGIN(h)
   if (n == 0) return DBI_OK;
@@ -2054,6 +1701,7 @@ void dbi_destroy(dbi_handle* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   free_index(h);
+  mg_release(h);
   h->d_raw.release();
   h->d_off.release();
   h->d_tables.release();
@@ -2084,3 +1732,5 @@ const char* dbi_last_error(void) { return t_err; }
 uint64_t dbi_kernel_launches(void) { return g_kernel_launches.load(); }
 
 }  // extern "C"
+
+#include "capi_mg.inl"

@@ -1,0 +1,750 @@
+// capi_mg.inl -- sharded (multi-GPU) build behind the C ABI; included at the end of capi.cu.
+//
+// The reference shards its index by mass: DBIndexStoreSQLiteMult keeps `indexFactor` SQLite files,
+// one per mass bucket (DBIndexStoreSQLiteMult.java:55-56,215-217) and a query walks the buckets its
+// range touches (:333-343).  Here a bucket is a GPU with one contiguous slice of the mass axis:
+//
+//   every rank adds ITS OWN shard of the FASTA (dbi_add_proteins), packs it into its place of the
+//   global residue buffer and pulls the other shards over NVLink (window 0); digests its share of the
+//   start positions; exchange 0 moves the records to the owners of their base-mass slices, exchange 1
+//   moves the variant groups (with their site masks) to the owners of their variant-mass slices.
+//   Both exchanges are ONE kernel each: a stable multisplit whose output pointers are the other
+//   GPUs' arenas (mapped peer memory), mg.cu.
+//
+// Small collectives (two 32 KB histograms, a world x world count matrix, barriers) are the caller's:
+// torch.distributed / NCCL between processes (dbindex_b200/multigpu.py), plain host code when one
+// process holds every handle (dbi_mg_build_local below, what a Java host calls).
+
+#include <unistd.h>
+
+#include <array>
+
+namespace {
+
+constexpr int kWinProt = 0, kWinArena = 1, kWinUniq = 2;
+
+// Exportable allocations and peer mappings outlive handles: a later handle of the same process gets
+// the same blocks back, so peers keep their mappings (and cudaIpcOpenMemHandle is paid once).
+struct WinBlock {
+  void* p;
+  uint64_t cap;
+};
+struct WinCaches {
+  std::mutex mu;
+  std::vector<WinBlock> free_[64][3];
+  std::map<std::array<uint8_t, 64>, void*> opened;  // IPC handle -> mapped base
+};
+WinCaches& win_caches() {
+  static WinCaches c;
+  return c;
+}
+
+void* win_get(int device, int window, uint64_t bytes, uint64_t* cap) {
+  WinCaches& c = win_caches();
+  {
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto& v = c.free_[device & 63][window];
+    int best = -1;
+    for (int i = 0; i < (int)v.size(); ++i)
+      if (v[i].cap >= bytes && (best < 0 || v[i].cap < v[best].cap)) best = i;
+    if (best >= 0) {
+      const WinBlock b = v[best];
+      v.erase(v.begin() + best);
+      *cap = b.cap;
+      return b.p;
+    }
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    DevCache::of(device).trim();
+    e = cudaMalloc(&p, bytes);
+  }
+  if (e != cudaSuccess) throw CudaError{e, "cudaMalloc (window)", __FILE__, __LINE__};
+  *cap = bytes;
+  return p;
+}
+
+void win_put(int device, int window, void* p, uint64_t cap) {
+  if (!p) return;
+  WinCaches& c = win_caches();
+  std::lock_guard<std::mutex> lk(c.mu);
+  c.free_[device & 63][window].push_back({p, cap});
+}
+
+void mg_release(dbi_handle* h) {
+  for (int w = 0; w < 3; ++w) {
+    win_put(h->device, w, h->win[w].p, h->win[w].cap);
+    h->win[w] = dbi_handle::MgWindow();
+  }
+}
+
+// arena layouts: what an exchange delivers to a rank that receives n items
+struct RecLayout {
+  uint64_t mass, gpos, prot, len, total;
+  explicit RecLayout(uint64_t n) {
+    mass = 0;
+    gpos = mass + al256(8 * n);
+    prot = gpos + al256(4 * n);
+    len = prot + al256(4 * n);
+    total = len + al256(2 * n);
+  }
+};
+struct GrpLayout {
+  uint64_t key, pay, gid, mask, total;
+  GrpLayout(uint64_t n, int C) {
+    key = 0;
+    pay = key + al256(8 * n);
+    gid = pay + al256(8 * n);
+    mask = gid + (C > 0 ? al256(4 * n) : 0);
+    total = mask + (C > 0 ? al256(8 * n * (uint64_t)C) : 0);
+  }
+};
+
+// classes travelling with a group record: the group path ships C masks, the per-variant path none
+int mg_side_classes(const dbi_handle* h) { return h->cfg.n_seq > 0 ? h->cfg.n_classes : 0; }
+
+int mg_shift(const KeySpace& ks) { return ks.nbits > 12 ? ks.nbits - 12 : 0; }
+
+}  // namespace
+
+extern "C" {
+
+int dbi_mg_begin(dbi_handle* h, int rank, int world) {
+  DBI_API_BEGIN(h)
+  if (h->built) {
+    set_error("index already built");
+    return DBI_EALREADY;
+  }
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) {
+    set_error("bad rank %d / world %d (1..%d)", rank, world, kMaxRanks);
+    return DBI_EINVAL;
+  }
+  h->mg_rank = rank;
+  h->mg_world = world;
+  return DBI_OK;
+  DBI_API_END
+}
+
+uint64_t dbi_mg_layout_bytes(int window, int stage, uint64_t n_items, int n_classes) {
+  if (window == kWinUniq) return UniqLayout(n_items).total;
+  if (window == kWinArena) return stage == 0 ? RecLayout(n_items).total : GrpLayout(n_items, n_classes).total;
+  return 0;
+}
+
+int dbi_mg_side_classes(dbi_handle* h) { return h ? mg_side_classes(h) : 0; }
+
+int dbi_mg_window_ensure(dbi_handle* h, int window, uint64_t bytes, dbi_mg_window* desc) {
+  DBI_API_BEGIN(h)
+  if (window < 0 || window > 2) {
+    set_error("bad window %d", window);
+    return DBI_EINVAL;
+  }
+  dbi_handle::MgWindow& w = h->win[window];
+  if (bytes > w.cap) {
+    if (window == kWinProt && h->mg_layout) {
+      set_error("window 0 cannot grow once the shards are laid out");
+      return DBI_EINVAL;
+    }
+    DBI_CUDA(cudaStreamSynchronize(h->stream));
+    win_put(h->device, window, w.p, w.cap);  // the old block stays allocated: peers may still map it
+    w.p = nullptr;
+    w.cap = 0;
+    w.p = win_get(h->device, window, bytes + bytes / 4 + 4096, &w.cap);
+  }
+  w.peer[h->mg_rank] = w.p;
+  w.peer_cap[h->mg_rank] = w.cap;
+  if (desc) {
+    std::memset(desc, 0, sizeof(*desc));
+    if (w.p) {
+      cudaIpcMemHandle_t ih;
+      DBI_CUDA(cudaIpcGetMemHandle(&ih, w.p));
+      static_assert(sizeof(ih) == 64, "cudaIpcMemHandle_t is 64 bytes");
+      std::memcpy(desc->ipc, &ih, 64);
+    }
+    desc->ptr = (uint64_t)(uintptr_t)w.p;
+    desc->bytes = w.cap;
+    desc->device = h->device;
+    desc->pid = (int32_t)getpid();
+  }
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_mg_window_import(dbi_handle* h, int window, int rank, const dbi_mg_window* desc) {
+  DBI_API_BEGIN(h)
+  if (window < 0 || window > 2 || rank < 0 || rank >= h->mg_world || !desc) {
+    set_error("bad argument");
+    return DBI_EINVAL;
+  }
+  dbi_handle::MgWindow& w = h->win[window];
+  if (rank == h->mg_rank) return DBI_OK;
+  void* base = nullptr;
+  if (desc->ptr == 0) {
+    base = nullptr;
+  } else if (desc->pid == (int32_t)getpid()) {
+    // same process: the pointer itself, after enabling peer access between the two devices
+    if (desc->device != h->device) {
+      int can = 0;
+      DBI_CUDA(cudaDeviceCanAccessPeer(&can, h->device, desc->device));
+      if (!can) {
+        set_error("device %d cannot access device %d (no P2P path)", h->device, desc->device);
+        return DBI_ECUDA;
+      }
+      const cudaError_t e = cudaDeviceEnablePeerAccess(desc->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) throw CudaError{e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__};
+      cudaGetLastError();
+    }
+    base = (void*)(uintptr_t)desc->ptr;
+  } else {
+    WinCaches& c = win_caches();
+    std::array<uint8_t, 64> key;
+    std::memcpy(key.data(), desc->ipc, 64);
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto it = c.opened.find(key);
+    if (it != c.opened.end()) {
+      base = it->second;
+    } else {
+      cudaIpcMemHandle_t ih;
+      std::memcpy(&ih, desc->ipc, 64);
+      DBI_CUDA(cudaIpcOpenMemHandle(&base, ih, cudaIpcMemLazyEnablePeerAccess));
+      c.opened.emplace(key, base);
+    }
+  }
+  w.peer[rank] = base;
+  w.peer_cap[rank] = desc->bytes;
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_mg_set_shards(dbi_handle* h, const uint64_t* shard_proteins, const uint64_t* shard_residues,
+                      uint64_t* window0_bytes) {
+  DBI_API_BEGIN(h)
+  if (h->built) {
+    set_error("index already built");
+    return DBI_EALREADY;
+  }
+  if (!shard_proteins || !shard_residues) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  const int W = h->mg_world, r = h->mg_rank;
+  const uint64_t my_prot = h->h_off.size() - 1;
+  if (shard_proteins[r] != my_prot || shard_residues[r] != h->n_res) {
+    set_error("shard %d is declared as %llu proteins / %llu residues but this rank holds %llu / %llu", r,
+              (unsigned long long)shard_proteins[r], (unsigned long long)shard_residues[r],
+              (unsigned long long)my_prot, (unsigned long long)h->n_res);
+    return DBI_EINVAL;
+  }
+  h->prot_off[0] = 0;
+  h->pos_off[0] = 0;
+  for (int s = 0; s < W; ++s) {
+    h->prot_off[s + 1] = h->prot_off[s] + shard_proteins[s];
+    h->pos_off[s + 1] = h->pos_off[s] + shard_residues[s] + shard_proteins[s];
+  }
+  const uint64_t P = h->prot_off[W], res_end = h->pos_off[W] + 1;
+  if (res_end + 4096 >= (1ull << 32) || P >= (1ull << 31)) {
+    set_error("more than 2^32 residues in the sharded proteome");
+    return DBI_ERANGE;
+  }
+  const uint64_t padded = (res_end + 64 + 15) & ~15ull;
+  const uint64_t pstart_at = al256(padded);
+  const uint64_t total = pstart_at + (P + 1) * 4;
+  if (window0_bytes) {  // sizing call: the caller ensures window 0 and calls again with NULL
+    *window0_bytes = total;
+    return DBI_OK;
+  }
+  dbi_handle::MgWindow& w = h->win[kWinProt];
+  if (w.cap < total) {
+    set_error("window 0 holds %llu bytes, the proteome needs %llu", (unsigned long long)w.cap, (unsigned long long)total);
+    return DBI_EINVAL;
+  }
+  cudaStream_t st = h->stream;
+  ensure_uploaded(h);
+  const uint32_t zero = 0;
+  DBI_CUDA(cudaMemcpyAsync(h->d_err.p, &zero, 4, cudaMemcpyHostToDevice, st));
+  h->res_end = (uint32_t)res_end;
+  h->res_alloc = padded;
+  h->d_res.borrow(w.p, padded);
+  h->d_pstart.borrow((uint8_t*)w.p + pstart_at, (P + 1) * 4);
+  if (r == W - 1) DBI_CUDA(cudaMemsetAsync((uint8_t*)w.p + res_end, 0, padded - res_end, st));
+  {
+    Stage sg(h, DBI_STAGE_PACK);
+    launch_pack(h->d_raw.as<uint8_t>(), h->d_off.as<uint64_t>(), (uint32_t)my_prot, h->n_res,
+                h->d_res.as<uint8_t>() + h->pos_off[r], h->d_pstart.as<uint32_t>() + h->prot_off[r],
+                (uint32_t)h->pos_off[r], h->d_err.as<uint32_t>(), st);
+    h->st.algo_bytes[DBI_STAGE_PACK] += 2 * h->n_res + my_prot * 12;
+  }
+  DBI_CUDA(cudaStreamSynchronize(st));
+  h->mg_layout = true;
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_mg_pull_proteome(dbi_handle* h) {
+  DBI_API_BEGIN(h)
+  if (!h->mg_layout) {
+    set_error("dbi_mg_set_shards first");
+    return DBI_ENOTINIT;
+  }
+  const int W = h->mg_world, r = h->mg_rank;
+  cudaStream_t st = h->stream;
+  const uint64_t pstart_at = (uint64_t)((uint8_t*)h->d_pstart.p - (uint8_t*)h->d_res.p);
+  Stage sg(h, DBI_STAGE_PACK);
+  for (int k = 1; k < W; ++k) {
+    const int s = (r + k) % W;  // start with the next rank: the pulls of the ranks spread over the links
+    const uint8_t* peer = (const uint8_t*)h->win[kWinProt].peer[s];
+    if (!peer) {
+      set_error("window 0 of rank %d is not mapped", s);
+      return DBI_EINVAL;
+    }
+    // shard s: its separator, residues and inner separators; the last shard also owns the final separator
+    const uint64_t b0 = h->pos_off[s], b1 = s == W - 1 ? (uint64_t)h->res_alloc : h->pos_off[s + 1];
+    const uint64_t p0 = h->prot_off[s], p1 = h->prot_off[s + 1] + (s == W - 1 ? 1 : 0);
+    if (b1 > b0)
+      DBI_CUDA(cudaMemcpyAsync(h->d_res.as<uint8_t>() + b0, peer + b0, b1 - b0, cudaMemcpyDefault, st));
+    if (p1 > p0)
+      DBI_CUDA(cudaMemcpyAsync((uint8_t*)h->d_pstart.p + p0 * 4, peer + pstart_at + p0 * 4, (p1 - p0) * 4,
+                               cudaMemcpyDefault, st));
+    h->st.algo_bytes[DBI_STAGE_PACK] += 2 * (b1 - b0) + 8 * (p1 - p0);
+  }
+  DBI_CUDA(cudaStreamSynchronize(st));
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_mg_digest(dbi_handle* h, uint64_t* n_records) {
+  DBI_API_BEGIN(h)
+  if (h->built) {
+    set_error("index already built");
+    return DBI_EALREADY;
+  }
+  if (!h->mg_layout) {
+    set_error("dbi_mg_set_shards first");
+    return DBI_ENOTINIT;
+  }
+  cudaStream_t s = h->stream;
+  const uint32_t n_prot = (uint32_t)h->prot_off[h->mg_world];
+  const uint64_t tiles_all = ((uint64_t)h->res_end + kDigestTile - 1) / kDigestTile;
+  // contiguous, ascending tile ranges: rank order == global emission order
+  const uint32_t t0 = (uint32_t)(tiles_all * h->mg_rank / h->mg_world);
+  const uint32_t t1 = (uint32_t)(tiles_all * (h->mg_rank + 1) / h->mg_world);
+  const uint32_t nt = t1 - t0;
+  DevBuf tile_counts, tile_offs, start_cnt;
+  tile_counts.alloc((uint64_t)nt * 4, h->arena);
+  tile_offs.alloc(((uint64_t)nt + 1) * 8, h->arena);
+  start_cnt.alloc(std::max<uint64_t>(1, nt) * kDigestTile, h->arena);
+  uint64_t N = 0;
+  {
+    Stage sg(h, DBI_STAGE_DIGEST_COUNT);
+    launch_digest_count(h->d_res.as<uint8_t>(), h->res_end, h->res_alloc, h->d_tables.as<DevTables>(), h->cfg, t0, nt,
+                        start_cnt.as<uint8_t>(), tile_counts.as<uint32_t>(), h->d_err.as<uint32_t>(), s);
+    launch_scan_u32_to_u64(tile_counts.as<uint32_t>(), nt, tile_offs.as<uint64_t>(), s);
+    N = read_u64(h, tile_offs.as<uint64_t>() + nt);
+    h->st.algo_bytes[DBI_STAGE_DIGEST_COUNT] += 2ull * nt * kDigestTile + (uint64_t)nt * 16;
+  }
+  if (int rc = check_err_bits(read_err(h))) {
+    free_index(h);
+    return rc;
+  }
+  if (N >= (1ull << 32)) {
+    set_error("more than 2^32 emitted records on one GPU");
+    return DBI_ERANGE;
+  }
+  h->mg_mass.alloc(N * 8, h->arena);
+  h->mg_gpos.alloc(N * 4, h->arena);
+  h->mg_prot.alloc(N * 4, h->arena);
+  h->mg_len.alloc(N * 2, h->arena);
+  {
+    Stage sg(h, DBI_STAGE_DIGEST_EMIT);
+    launch_digest_emit(h->d_res.as<uint8_t>(), h->res_end, h->res_alloc, h->d_tables.as<DevTables>(), h->cfg, t0, nt,
+                       start_cnt.as<uint8_t>(), tile_offs.as<uint64_t>(), h->d_pstart.as<uint32_t>(), n_prot,
+                       h->mg_mass.as<uint64_t>(), h->mg_gpos.as<uint32_t>(), h->mg_prot.as<uint32_t>(),
+                       h->mg_len.as<uint16_t>(), h->d_err.as<uint32_t>(), s);
+    h->st.algo_bytes[DBI_STAGE_DIGEST_EMIT] += 2ull * nt * kDigestTile + N * 18;
+  }
+  DBI_CUDA(cudaStreamSynchronize(s));
+  h->mg_n = N;
+  h->n_emitted = N;
+  h->st.n_emitted = N;
+  if (n_records) *n_records = N;
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_mg_hist(dbi_handle* h, int stage, void* d_hist, int* shift) {
+  DBI_API_BEGIN(h)
+  if (!d_hist || (stage != 0 && stage != 1)) {
+    set_error("bad argument");
+    return DBI_EINVAL;
+  }
+  const KeySpace ks(h->p.min_mass, h->p.max_mass);
+  const int sh = mg_shift(ks);
+  if (stage == 0) {
+    launch_mg_hist(h->mg_mass.as<uint64_t>(), h->mg_n, ks.base_bits, sh, nullptr, 0, (unsigned long long*)d_hist,
+                   h->stream);
+  } else {  // group records: weigh by their variant count
+    const bool weighted = h->cfg.n_seq > 0;
+    launch_mg_hist(h->mg_vkey.as<uint64_t>(), h->mg_v, 0, sh, weighted ? h->mg_vpay.as<uint64_t>() : nullptr,
+                   kGrpCntMask, (unsigned long long*)d_hist, h->stream);
+  }
+  if (shift) *shift = sh;
+  return DBI_OK;
+  DBI_API_END
+}
+
+// Pure host arithmetic: equal-weight bin splitters from the global weighted histogram (bins are never
+// split, so equal masses -- hence equal peptides -- meet on one rank), this rank's send counts from
+// its own plain histogram, every rank's receive total from the global plain histogram.
+int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_local, uint32_t* bin_splitters,
+                uint64_t* send_counts, uint64_t* recv_totals) {
+  if (world < 1 || world > kMaxRanks || !hist_global || !hist_local || !send_counts || !recv_totals ||
+      (world > 1 && !bin_splitters)) {
+    set_error("bad argument");
+    return DBI_EINVAL;
+  }
+  const int B = kMgBins;
+  unsigned __int128 total = 0;
+  for (int b = 0; b < B; ++b) total += hist_global[b];
+  uint32_t prev = 0;
+  unsigned __int128 cum = 0;
+  int b = 0;
+  for (int d = 1; d < world; ++d) {
+    const unsigned __int128 target = total * (unsigned)d / (unsigned)world;
+    // first bin boundary at which at least `target` of the weight lies below
+    while (b < B && cum + hist_global[b] < target) cum += hist_global[b++];
+    uint32_t cut = total ? (uint32_t)std::min(b + 1, B) : 0u;
+    if (cut < prev) cut = prev;
+    bin_splitters[d - 1] = cut;
+    prev = cut;
+  }
+  for (int d = 0; d < world; ++d) {
+    const uint32_t lo = d ? bin_splitters[d - 1] : 0u, hi = d < world - 1 ? bin_splitters[d] : (uint32_t)B;
+    uint64_t sc = 0, rt = 0;
+    for (uint32_t x = lo; x < hi; ++x) {
+      sc += hist_local[B + x];
+      rt += hist_global[B + x];
+    }
+    send_counts[d] = sc;
+    recv_totals[d] = rt;
+  }
+  return DBI_OK;
+}
+
+int dbi_mg_scatter(dbi_handle* h, int stage, const uint32_t* bin_splitters, const uint64_t* matrix) {
+  DBI_API_BEGIN(h)
+  const int W = h->mg_world, r = h->mg_rank;
+  if ((W > 1 && !bin_splitters) || !matrix || (stage != 0 && stage != 1)) {
+    set_error("bad argument");
+    return DBI_EINVAL;
+  }
+  cudaStream_t s = h->stream;
+  const KeySpace ks(h->p.min_mass, h->p.max_mass);
+  const int sh = mg_shift(ks);
+  const int C = mg_side_classes(h);
+  MgPlan pl;
+  std::memset(&pl, 0, sizeof(pl));
+  pl.world = W;
+  for (int d = 0; d + 1 < W; ++d) {
+    if (d > 0 && bin_splitters[d] < bin_splitters[d - 1]) {
+      set_error("bin_splitters must be ascending");
+      return DBI_EINVAL;
+    }
+    pl.thr[d] = (uint64_t)bin_splitters[d] << sh;
+    h->mg_thr[stage][d] = pl.thr[d];
+  }
+  uint64_t recv[kMaxRanks] = {}, sent = 0;
+  for (int d = 0; d < W; ++d) {
+    for (int src = 0; src < W; ++src) {
+      if (src < r) pl.row0[d] += matrix[src * W + d];
+      recv[d] += matrix[src * W + d];
+    }
+    sent += matrix[r * W + d];
+  }
+  const uint64_t n_local = stage == 0 ? h->mg_n : h->mg_v;
+  if (sent != n_local) {
+    set_error("count matrix row %d sums to %llu but this rank holds %llu items", r, (unsigned long long)sent,
+              (unsigned long long)n_local);
+    return DBI_EINVAL;
+  }
+  for (int d = 0; d < W; ++d) {
+    if (recv[d] >= (1ull << 32)) {
+      set_error("more than 2^32 items for rank %d", d);
+      return DBI_ERANGE;
+    }
+    const uint64_t need = stage == 0 ? RecLayout(recv[d]).total : GrpLayout(recv[d], C).total;
+    if (recv[d] && (!h->win[kWinArena].peer[d] || h->win[kWinArena].peer_cap[d] < need)) {
+      set_error("arena of rank %d is not mapped or too small (%llu < %llu bytes)", d,
+                (unsigned long long)h->win[kWinArena].peer_cap[d], (unsigned long long)need);
+      return DBI_EINVAL;
+    }
+  }
+  DevBuf tmp;
+  tmp.alloc(mg_scatter_tmp_bytes(n_local), h->arena);
+  Stage sg(h, DBI_STAGE_OTHER);
+  if (stage == 0) {
+    MgRecDst dst;
+    std::memset(&dst, 0, sizeof(dst));
+    for (int d = 0; d < W; ++d) {
+      uint8_t* base = (uint8_t*)h->win[kWinArena].peer[d];
+      const RecLayout L(recv[d]);
+      dst.mass[d] = (uint64_t*)(base + L.mass);
+      dst.gpos[d] = (uint32_t*)(base + L.gpos);
+      dst.prot[d] = (uint32_t*)(base + L.prot);
+      dst.len[d] = (uint16_t*)(base + L.len);
+      h->uniq_cap[d] = recv[d];  // window 2 of every rank is laid out by what exchange 0 delivers to it
+    }
+    launch_mg_scatter_records(h->mg_mass.as<uint64_t>(), h->mg_gpos.as<uint32_t>(), h->mg_prot.as<uint32_t>(),
+                              h->mg_len.as<uint16_t>(), n_local, ks.base_bits, pl, dst, tmp.p, s);
+    h->st.algo_bytes[DBI_STAGE_OTHER] += n_local * 2 * 18;
+    h->mg_mass.release(); h->mg_gpos.release(); h->mg_prot.release(); h->mg_len.release();
+  } else {
+    MgGrpDst dst;
+    std::memset(&dst, 0, sizeof(dst));
+    for (int d = 0; d < W; ++d) {
+      uint8_t* base = (uint8_t*)h->win[kWinArena].peer[d];
+      const GrpLayout L(recv[d], C);
+      dst.key[d] = (uint64_t*)(base + L.key);
+      dst.pay[d] = (uint64_t*)(base + L.pay);
+      dst.gid[d] = (uint32_t*)(base + L.gid);
+      dst.mask[d] = (uint64_t*)(base + L.mask);
+    }
+    if (C > 0) ensure_site_masks(h);
+    launch_mg_scatter_groups(h->mg_vkey.as<uint64_t>(), h->mg_vpay.as<uint64_t>(), h->u_cmask.as<uint64_t>(), C,
+                             h->uoff[r], n_local, pl, dst, tmp.p, s);
+    h->st.algo_bytes[DBI_STAGE_OTHER] += n_local * 2 * (20 + 8ull * C);
+    h->mg_vkey.release(); h->mg_vpay.release();
+  }
+  h->mg_recv[stage] = recv[r];
+  DBI_CUDA(cudaStreamSynchronize(s));  // the peers may read their arenas once every rank is past this point
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_mg_index_base(dbi_handle* h) {
+  DBI_API_BEGIN(h)
+  const uint64_t n = h->mg_recv[0];
+  const KeySpace ks(h->p.min_mass, h->p.max_mass);
+  const RecLayout L(n);
+  const uint8_t* base = (const uint8_t*)h->win[kWinArena].p;
+  const RecView rv{(const uint64_t*)(base + L.mass), (const uint32_t*)(base + L.gpos), (const uint32_t*)(base + L.prot),
+                   (const uint16_t*)(base + L.len)};
+  int rc = sort_dedup(h, rv, n, ks);
+  if (rc == DBI_OK) rc = check_err_bits(read_err(h));
+  if (rc == DBI_OK && n == 0) {  // empty slice: still needs (empty) tables
+    h->u_mass.alloc(8, h->arena);
+    if (!h->u_gpos.p) { h->u_gpos.alloc(8, h->arena); h->u_prot.alloc(8, h->arena); h->u_len.alloc(8, h->arena); h->plist.alloc(8, h->arena); }
+  }
+  DBI_CUDA(cudaStreamSynchronize(h->stream));
+  return rc;
+  DBI_API_END
+}
+
+int dbi_mg_unique_count(dbi_handle* h, uint64_t* n_unique) {
+  if (!h || !n_unique) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  *n_unique = h->n_unique;
+  return DBI_OK;
+}
+
+int dbi_mg_set_unique(dbi_handle* h, const uint64_t* rank_unique) {
+  DBI_API_BEGIN(h)
+  if (!rank_unique) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  if (rank_unique[h->mg_rank] != h->n_unique) {
+    set_error("rank_unique[%d] = %llu but this rank holds %llu unique peptides", h->mg_rank,
+              (unsigned long long)rank_unique[h->mg_rank], (unsigned long long)h->n_unique);
+    return DBI_EINVAL;
+  }
+  h->uoff[0] = 0;
+  for (int r = 0; r < h->mg_world; ++r) h->uoff[r + 1] = h->uoff[r] + rank_unique[r];
+  if (h->uoff[h->mg_world] >= (1ull << 32)) {
+    set_error("more than 2^32 unique peptides in total");
+    return DBI_ERANGE;
+  }
+  h->ent_base_off = h->uoff[h->mg_rank];
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_mg_groups(dbi_handle* h, uint64_t* n_items, uint64_t* n_variants) {
+  DBI_API_BEGIN(h)
+  const KeySpace ks(h->p.min_mass, h->p.max_mass);
+  const uint32_t utiles = (uint32_t)((h->n_unique + kModTile - 1) / kModTile);
+  uint64_t V = 0, NG = 0;
+  int rc;
+  const uint64_t keep = h->ent_base_off;
+  h->ent_base_off = 0;  // the records name LOCAL peptide rows; the exchange turns them into global ids
+  if (h->cfg.n_seq > 0) {
+    rc = emit_groups(h, 0, utiles, ks, h->mg_vkey, h->mg_vpay, &NG, &V);
+  } else {
+    rc = emit_variants(h, 0, utiles, ks, h->mg_vkey, h->mg_vpay, &V);
+    NG = V;
+  }
+  h->ent_base_off = keep;
+  DBI_CUDA(cudaStreamSynchronize(h->stream));
+  h->mg_v = NG;  // items that travel: group records, or variants on the per-variant path
+  if (n_items) *n_items = NG;
+  if (n_variants) *n_variants = V;
+  return rc;
+  DBI_API_END
+}
+
+int dbi_mg_index_variants(dbi_handle* h) {
+  DBI_API_BEGIN(h)
+  const uint64_t n = h->mg_recv[1];
+  const KeySpace ks(h->p.min_mass, h->p.max_mass);
+  const int C = mg_side_classes(h);
+  const GrpLayout L(n, C);
+  uint8_t* base = (uint8_t*)h->win[kWinArena].p;
+  int rc;
+  if (h->cfg.n_seq > 0) {
+    const UniqView uv = uniq_view(h);
+    GroupSide side;
+    side.cmask = (const uint64_t*)(base + L.mask);
+    side.gid = (const uint32_t*)(base + L.gid);
+    side.uv = &uv;
+    rc = sort_expand_groups(h, (uint64_t*)(base + L.key), (uint64_t*)(base + L.pay), n, ks, &side);
+  } else {
+    rc = sort_variants(h, (uint64_t*)(base + L.key), (uint64_t*)(base + L.pay), n, ks);
+  }
+  if (rc == DBI_OK) rc = check_err_bits(read_err(h));
+  DBI_CUDA(cudaStreamSynchronize(h->stream));
+  return rc;
+  DBI_API_END
+}
+
+int dbi_mg_finish(dbi_handle* h) {
+  DBI_API_BEGIN(h)
+  if (h->cfg.max_mods == 0) {
+    h->e_mass.release(); h->e_base.release(); h->e_pat.release();
+    h->n_entries = h->n_unique;  // the entries of this rank are its own unique peptides
+    h->st.n_entries = h->n_entries;
+  }
+  h->built = true;
+  finish_stats(h);
+  return DBI_OK;
+  DBI_API_END
+}
+
+int dbi_mg_split_masses(dbi_handle* h, double* split_mass) {
+  if (!h || (h->mg_world > 1 && !split_mass)) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  const KeySpace ks(h->p.min_mass, h->p.max_mass);
+  const int stage = h->cfg.max_mods > 0 ? 1 : 0;
+  for (int d = 0; d + 1 < h->mg_world; ++d) {
+    const uint64_t bits = h->mg_thr[stage][d] + ks.base_bits;
+    std::memcpy(&split_mass[d], &bits, 8);
+  }
+  return DBI_OK;
+}
+
+// The whole sharded build when ONE process holds a handle per GPU (what a Java host calls): the same
+// stages as above with the small collectives done by the host.  handles[r] becomes rank r; every
+// handle must have been given ITS shard of the FASTA (dbi_add_proteins) in rank order.
+int dbi_mg_build_local(dbi_handle** hs, int n) {
+  if (!hs || n < 1 || n > kMaxRanks) {
+    set_error("bad argument");
+    return DBI_EINVAL;
+  }
+  for (int r = 0; r < n; ++r)
+    if (!hs[r]) {
+      set_error("null handle");
+      return DBI_EINVAL;
+    }
+#define MG_ALL(expr)                         \
+  for (int r = 0; r < n; ++r) {              \
+    dbi_handle* h = hs[r];                   \
+    (void)h;                                 \
+    if (int rc_ = (expr)) return rc_;        \
+  }
+  try {
+    const int W = n;
+    std::vector<uint64_t> sp(W), sr(W);
+    for (int r = 0; r < W; ++r) {
+      sp[r] = hs[r]->h_off.size() - 1;
+      sr[r] = hs[r]->n_res;
+    }
+    MG_ALL(dbi_mg_begin(h, r, W));
+    auto connect = [&](int window) -> int {  // every rank maps every rank's window
+      std::vector<dbi_mg_window> d(W);
+      for (int r = 0; r < W; ++r)
+        if (int rc = dbi_mg_window_ensure(hs[r], window, 0, &d[r])) return rc;
+      for (int r = 0; r < W; ++r)
+        for (int q = 0; q < W; ++q)
+          if (int rc = dbi_mg_window_import(hs[r], window, q, &d[q])) return rc;
+      return DBI_OK;
+    };
+    {
+      uint64_t bytes = 0;
+      MG_ALL(dbi_mg_set_shards(h, sp.data(), sr.data(), &bytes));
+      MG_ALL(dbi_mg_window_ensure(h, kWinProt, bytes, nullptr));
+      MG_ALL(dbi_mg_set_shards(h, sp.data(), sr.data(), nullptr));
+      if (int rc = connect(kWinProt)) return rc;
+      MG_ALL(dbi_mg_pull_proteome(h));
+    }
+    MG_ALL(dbi_mg_digest(h, nullptr));
+    const bool mods = hs[0]->cfg.max_mods > 0;
+    const int C = mg_side_classes(hs[0]);
+    std::vector<uint64_t> matrix((size_t)W * W), recv(W);
+    std::vector<uint32_t> split(W);
+    auto exchange = [&](int stage) -> int {
+      const size_t HB = 2 * kMgBins;
+      std::vector<uint64_t> local((size_t)W * HB), global(HB, 0);
+      for (int r = 0; r < W; ++r) {
+        dbi_handle* h = hs[r];
+        DBI_CUDA(cudaSetDevice(h->device));
+        DevBuf d;
+        d.alloc(HB * 8, h->arena);
+        DBI_CUDA(cudaMemsetAsync(d.p, 0, HB * 8, h->stream));
+        int shift = 0;
+        if (int rc = dbi_mg_hist(h, stage, d.p, &shift)) return rc;
+        DBI_CUDA(cudaMemcpyAsync(&local[(size_t)r * HB], d.p, HB * 8, cudaMemcpyDeviceToHost, h->stream));
+        DBI_CUDA(cudaStreamSynchronize(h->stream));
+      }
+      for (int r = 0; r < W; ++r)
+        for (size_t i = 0; i < HB; ++i) global[i] += local[(size_t)r * HB + i];
+      for (int r = 0; r < W; ++r)
+        if (int rc = dbi_mg_plan(W, global.data(), &local[(size_t)r * HB], split.data(), &matrix[(size_t)r * W], recv.data()))
+          return rc;
+      for (int r = 0; r < W; ++r) {
+        const uint64_t need = dbi_mg_layout_bytes(kWinArena, stage, recv[r], C);
+        if (int rc = dbi_mg_window_ensure(hs[r], kWinArena, need, nullptr)) return rc;
+        if (stage == 0)
+          if (int rc = dbi_mg_window_ensure(hs[r], kWinUniq, dbi_mg_layout_bytes(kWinUniq, 0, recv[r], 0), nullptr)) return rc;
+      }
+      if (int rc = connect(kWinArena)) return rc;
+      if (stage == 0)
+        if (int rc = connect(kWinUniq)) return rc;
+      MG_ALL(dbi_mg_scatter(h, stage, split.data(), matrix.data()));
+      return DBI_OK;
+    };
+    if (int rc = exchange(0)) return rc;
+    MG_ALL(dbi_mg_index_base(h));
+    std::vector<uint64_t> ru(W);
+    for (int r = 0; r < W; ++r) ru[r] = hs[r]->n_unique;
+    MG_ALL(dbi_mg_set_unique(h, ru.data()));
+    if (mods) {
+      MG_ALL(dbi_mg_groups(h, nullptr, nullptr));
+      if (int rc = exchange(1)) return rc;
+      MG_ALL(dbi_mg_index_variants(h));
+    }
+    MG_ALL(dbi_mg_finish(h));
+    return DBI_OK;
+  } catch (const CudaError& e) {
+    return fail_cuda(e);
+  } catch (const std::bad_alloc&) {
+    set_error("host allocation failed");
+    return DBI_ENOMEM;
+  }
+#undef MG_ALL
+}
+
+}  // extern "C"

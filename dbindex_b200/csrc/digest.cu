@@ -334,12 +334,12 @@ constexpr int PK_BYTES = 16;  // raw bytes per thread
 
 __global__ void __launch_bounds__(PK_THREADS)
     pack_kernel(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ off, uint32_t n_prot, uint64_t n_res,
-                uint8_t* __restrict__ res, uint32_t* __restrict__ pstart, uint32_t* err) {
+                uint8_t* __restrict__ res, uint32_t* __restrict__ pstart, uint32_t pos_base, uint32_t* err) {
   const uint64_t tid = (uint64_t)blockIdx.x * PK_THREADS + threadIdx.x;
   // protein starts and separators
   if (tid <= n_prot) {
     const uint64_t ps = off[tid] + tid + 1;  // pstart[n_prot] = one past the last separator
-    pstart[tid] = (uint32_t)ps;
+    pstart[tid] = (uint32_t)ps + pos_base;
     res[ps - 1] = 0;  // separator before protein tid (tid == n_prot: the final one)
   }
   const uint64_t b0 = tid * PK_BYTES;
@@ -382,11 +382,11 @@ __global__ void __launch_bounds__(SC_THREADS)
 }  // namespace
 
 void launch_pack(const uint8_t* d_raw, const uint64_t* d_off, uint32_t n_prot, uint64_t n_res, uint8_t* d_res,
-                 uint32_t* d_pstart, uint32_t* d_err, cudaStream_t s) {
+                 uint32_t* d_pstart, uint32_t pos_base, uint32_t* d_err, cudaStream_t s) {
   uint64_t threads = (n_res + PK_BYTES - 1) / PK_BYTES;
   if (threads < (uint64_t)n_prot + 1) threads = (uint64_t)n_prot + 1;
   const unsigned grid = (unsigned)((threads + PK_THREADS - 1) / PK_THREADS);
-  DBI_LAUNCH(pack_kernel, grid, PK_THREADS, 0, s, d_raw, d_off, n_prot, n_res, d_res, d_pstart, d_err);
+  DBI_LAUNCH(pack_kernel, grid, PK_THREADS, 0, s, d_raw, d_off, n_prot, n_res, d_res, d_pstart, pos_base, d_err);
 }
 
 void launch_digest_count(const uint8_t* d_res, uint32_t res_end, uint64_t res_alloc, const DevTables* d_tb,

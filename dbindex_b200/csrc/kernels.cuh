@@ -36,8 +36,10 @@ constexpr int kModTile = 256;       // base peptides per CTA of the mod kernels 
 
 // K1: residues + offsets -> padded buffer res[] (0 separator before, between and
 // after proteins) and pstart[p] = position of protein p's first residue.
+// pos_base: buffer position d_res[0] stands for (a rank of a sharded build packs its shard of the FASTA
+// into its place of the global buffer; d_res / d_pstart then point at that place).
 void launch_pack(const uint8_t* d_raw, const uint64_t* d_off, uint32_t n_prot, uint64_t n_res, uint8_t* d_res,
-                 uint32_t* d_pstart, uint32_t* d_err, cudaStream_t s);
+                 uint32_t* d_pstart, uint32_t pos_base, uint32_t* d_err, cudaStream_t s);
 
 // K2: records cutSeq emits per START position (start_cnt[g - first position of tile0], saturating
 // at 255) and per tile.  Tiles [tile0, tile0 + ntiles) of kDigestTile start positions each (a
@@ -89,6 +91,28 @@ void launch_mod_emit(const uint8_t* d_res, const DevTables* d_tb, const DigestCf
 void launch_split_entries(const uint64_t* skey, const uint64_t* spayload, uint64_t n, uint64_t base_bits,
                           double* e_mass, uint32_t* e_base, uint32_t* e_pat, cudaStream_t s);
 
+// Unique-peptide tables of every rank of a sharded index (world = 1: this GPU's own).  A peptide is
+// named by its global id; rank r holds ids [uoff[r], uoff[r + 1]).  A rank whose tables are not mapped
+// here (nullptr) makes its peptides come back as DBI_REMOTE_BASE.
+constexpr int kMaxRanks = 16;
+struct UniqView {
+  const uint32_t* gpos[kMaxRanks];
+  const uint32_t* prot[kMaxRanks];
+  const uint16_t* len[kMaxRanks];
+  const uint64_t* plo[kMaxRanks];
+  const uint32_t* plist[kMaxRanks];
+  uint64_t uoff[kMaxRanks + 1];
+  int world;
+};
+#ifdef __CUDACC__
+// owner rank and row of a unique peptide named by its global id
+__device__ __forceinline__ int uniq_owner(const UniqView& uv, uint64_t gid, uint64_t* row) {
+  int r = 0;
+  while (r + 1 < uv.world && gid >= uv.uoff[r + 1]) ++r;
+  *row = gid - uv.uoff[r];
+  return r;
+}
+#endif
 // Group path (class sequences <= 32, mods_grp.cu): one sort record per (peptide, class sequence)
 // group; payload = peptide << 32 | sequence << 27 | variant count.
 constexpr int kExpTile = 512;  // entries per CTA of the expansion
@@ -115,31 +139,20 @@ void launch_grp_tile_first(const uint64_t* eoff, uint64_t n_groups, uint64_t n_e
 // entries of the sorted groups; groups of long peptides are listed in long_list and written by a
 // second kernel (launched when long_cap > 0).  The payload's peptide field is a ROW of cmask /
 // u_gpos / u_len; gid_tab (sharded build: rows are arrival slots of the group exchange) maps a row
-// to the peptide's global id, nullptr = the row is the id.
+// to the peptide's global id, nullptr = the row is the id; uv (with gid_tab) = the tables (of any rank)
+// holding (gpos, len) of a peptide, which only the rare peptides longer than 64 residues need.
 void launch_grp_expand(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const uint32_t* u_gpos,
-                       const uint16_t* u_len, const uint64_t* cmask, const uint32_t* gid_tab, const uint64_t* skey,
-                       const uint64_t* spay, const uint64_t* eoff, const uint32_t* tile_first, uint64_t n_groups,
-                       uint64_t n_entries, uint64_t base_bits, double* e_mass, uint32_t* e_base, uint32_t* e_pat,
-                       uint32_t* long_list, uint32_t* long_count, uint32_t long_cap, uint32_t* d_err, cudaStream_t s);
+                       const uint16_t* u_len, const uint64_t* cmask, const uint32_t* gid_tab, const UniqView* uv,
+                       const uint64_t* skey, const uint64_t* spay, const uint64_t* eoff, const uint32_t* tile_first,
+                       uint64_t n_groups, uint64_t n_entries, uint64_t base_bits, double* e_mass, uint32_t* e_base,
+                       uint32_t* e_pat, uint32_t* long_list, uint32_t* long_count, uint32_t long_cap, uint32_t* d_err,
+                       cudaStream_t s);
 
 // ---- K9/K10 query ----------------------------------------------------------------
 // cnt32 (optional): the hit counts again as u32, the input of the hit-offset scan
 void launch_query(const double* e_mass, uint64_t n_entries, const double* lo, const double* hi, uint64_t nq,
                   uint64_t* hit_begin, uint64_t* hit_count, uint32_t* cnt32, cudaStream_t s);
 
-// Unique-peptide tables of every rank of a sharded index (world = 1: this GPU's own).  A peptide is
-// named by its global id; rank r holds ids [uoff[r], uoff[r + 1]).  A rank whose tables are not mapped
-// here (nullptr) makes its peptides come back as DBI_REMOTE_BASE.
-constexpr int kMaxRanks = 16;
-struct UniqView {
-  const uint32_t* gpos[kMaxRanks];
-  const uint32_t* prot[kMaxRanks];
-  const uint16_t* len[kMaxRanks];
-  const uint64_t* plo[kMaxRanks];
-  const uint32_t* plist[kMaxRanks];
-  uint64_t uoff[kMaxRanks + 1];
-  int world;
-};
 // K10a: per hit of every query, in (query, rank-in-query) order: the entry it is, its peptide
 // length and its protein-list length.  hit_off = exclusive scan of the hit counts.
 void launch_hits_expand(const uint32_t* e_base, uint64_t ent_off, const UniqView& uv, const uint64_t* hit_begin,
@@ -152,20 +165,17 @@ void launch_hits_gather(const uint8_t* d_res, const uint32_t* pstart, const doub
                         uint32_t* o_prot, uint32_t* o_off, uint16_t* o_len, uint32_t* o_pat, uint8_t* o_flanks,
                         uint8_t* o_seq, uint32_t* o_ids, cudaStream_t s);
 // per-entry protein-list length for entries [begin, begin+count) + per-tile sums.
-// e_base == nullptr means "entry i is unique peptide i" (no differential mods).
-// Base peptides are named by global ids; the handle holds [own_lo, own_lo + own_n) of them (all of
-// them on a single GPU).  A base outside that range (sharded build) has list size 0 and comes back
-// as first_prot = DBI_REMOTE_BASE, first_off = global id, len = g_len[global id].
-void launch_fetch_sizes(const uint32_t* e_base, uint64_t base_off, uint64_t own_lo, uint64_t own_n,
-                        const uint64_t* u_plo, uint64_t begin, uint64_t count, uint32_t* sizes, uint32_t* tile_counts,
-                        cudaStream_t s);
+// e_base == nullptr means "entry i is unique peptide base_off + i" (no differential mods).
+// Base peptides are named by global ids and resolved through uv; a peptide whose owner's tables are
+// not mapped has list size 0 and comes back as first_prot = DBI_REMOTE_BASE, first_off = global id.
+void launch_fetch_sizes(const uint32_t* e_base, uint64_t base_off, const UniqView& uv, uint64_t begin, uint64_t count,
+                        uint32_t* sizes, uint32_t* tile_counts, cudaStream_t s);
 // what parseAddPeptideInfo materialises per hit; any output may be nullptr.
-void launch_fetch_gather(const double* e_mass, const uint32_t* e_base, uint64_t base_off, uint64_t own_lo,
-                         uint64_t own_n, const uint16_t* g_len, const uint32_t* e_pat,
-                         const uint32_t* u_gpos, const uint32_t* u_prot, const uint16_t* u_len, const uint64_t* u_plo, const uint32_t* plist,
-                         const uint32_t* pstart, uint64_t begin, uint64_t count, const uint32_t* sizes,
-                         const uint64_t* tile_offs, double* o_mass, uint32_t* o_prot, uint32_t* o_off,
-                         uint16_t* o_len, uint32_t* o_pat, uint64_t* o_list_off, uint32_t* o_ids, cudaStream_t s);
+void launch_fetch_gather(const double* e_mass, const uint32_t* e_base, uint64_t base_off, const UniqView& uv,
+                         const uint32_t* e_pat, const uint32_t* pstart, uint64_t begin, uint64_t count,
+                         const uint32_t* sizes, const uint64_t* tile_offs, double* o_mass, uint32_t* o_prot,
+                         uint32_t* o_off, uint16_t* o_len, uint32_t* o_pat, uint64_t* o_list_off, uint32_t* o_ids,
+                         cudaStream_t s);
 // distinct (int)(mass*factor) keys: flags + compaction
 void launch_key_flags(const double* e_mass, uint64_t n, double factor, uint8_t* flags, uint32_t* tile_counts,
                       cudaStream_t s);
@@ -174,16 +184,41 @@ void launch_key_emit(const double* e_mass, uint64_t n, double factor, const uint
 
 // ---- multi-GPU exchange helpers (mg.cu) -----------------------------------------------------
 constexpr int kMgBins = 4096;  // histogram bins over the top bits of the radix key
-// hist[min(kMgBins-1, (key[i] - sub) >> shift)] += 1   (hist is zeroed by the caller)
-// weight of item i = wpay ? (wpay[i] & wmask) : 1   (group records carry their variant count)
+// hist[0 .. kMgBins) += weight, hist[kMgBins .. 2 kMgBins) += 1 over min(kMgBins-1, (key[i] - sub) >> shift)
+// (hist is zeroed by the caller); weight of item i = wpay ? (wpay[i] & wmask) : 1 (group records
+// carry their variant count).
 void launch_mg_hist(const uint64_t* key, uint64_t n, uint64_t sub, int shift, const uint64_t* wpay, uint64_t wmask,
                     unsigned long long* hist, cudaStream_t s);
-// dest[i] = number of thresholds <= (key[i] - sub); idx[i] = i; counts[dest] += 1
-void launch_mg_dest(const uint64_t* key, uint64_t n, uint64_t sub, const uint64_t* thresholds, int n_thr,
-                    uint32_t* dest, uint32_t* idx, unsigned long long* counts, cudaStream_t s);
-void launch_gather_u64(const uint64_t* src, const uint32_t* idx, uint64_t n, uint64_t* dst, cudaStream_t s);
-void launch_gather_u32(const uint32_t* src, const uint32_t* idx, uint64_t n, uint32_t* dst, cudaStream_t s);
-void launch_gather_u16(const uint16_t* src, const uint32_t* idx, uint64_t n, uint16_t* dst, cudaStream_t s);
+// Where the items of one exchange go.  dest(item) = number of thresholds <= (key - sub); this rank's
+// items for destination d arrive at rows row0[d] .. of d's arrays (after the items of the lower ranks).
+struct MgPlan {
+  uint64_t thr[kMaxRanks];
+  uint64_t row0[kMaxRanks];
+  int world;
+};
+// destination arrays (mapped peer pointers; the own rank's are local)
+struct MgRecDst {
+  uint64_t* mass[kMaxRanks];
+  uint32_t* gpos[kMaxRanks];
+  uint32_t* prot[kMaxRanks];
+  uint16_t* len[kMaxRanks];
+};
+struct MgGrpDst {
+  uint64_t* key[kMaxRanks];
+  uint64_t* pay[kMaxRanks];
+  uint32_t* gid[kMaxRanks];   // global id of the group's peptide, by arrival row
+  uint64_t* mask[kMaxRanks];  // its C site masks, [row * C + c]
+};
+size_t mg_scatter_tmp_bytes(uint64_t n);
+// fused multisplit + peer-memory all-to-all (mg.cu); tmp = mg_scatter_tmp_bytes(n) bytes
+void launch_mg_scatter_records(const uint64_t* mass, const uint32_t* gpos, const uint32_t* prot, const uint16_t* len,
+                               uint64_t n, uint64_t sub, const MgPlan& pl, const MgRecDst& dst, void* tmp,
+                               cudaStream_t s);
+// The payloads name LOCAL peptide rows (id_off turns them into global ids).  C > 0: group records, the
+// payload's peptide field becomes the arrival row and (gid, masks) travel as side tables; C == 0:
+// per-variant records, only (key, payload + id_off) travel.
+void launch_mg_scatter_groups(const uint64_t* key, const uint64_t* pay, const uint64_t* cmask, int C, uint64_t id_off,
+                              uint64_t n, const MgPlan& pl, const MgGrpDst& dst, void* tmp, cudaStream_t s);
 // list length of every unique peptide: cnt[u] = plo[u+1] - plo[u]
 void launch_plo_to_counts(const uint64_t* plo, uint64_t n, uint32_t* cnt, cudaStream_t s);
 // full exclusive scan: offs[i] = sum(in[0..i)), offs[n] = total; tmp = (ntiles + 1) u64 + ntiles u32

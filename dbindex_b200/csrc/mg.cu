@@ -12,52 +12,230 @@ namespace {
 
 constexpr int MG_THREADS = 256;
 
+// ---- histograms of an exchange stage ------------------------------------------------------
+// hist[0 .. kMgBins)          += weight of the item  (stage 1: the variant count of the group; else 1)
+// hist[kMgBins .. 2 kMgBins)  += 1
+// over the bins min(kMgBins - 1, (key - sub) >> shift).  The weighted one chooses the splitters
+// (equal INDEX ENTRIES per rank), the plain one gives every rank the number of items it will send
+// and receive.  64-bit bins in shared memory: a group can stand for 2^27 variants.
 __global__ void __launch_bounds__(MG_THREADS)
     mg_hist_kernel(const uint64_t* __restrict__ key, uint64_t n, uint64_t sub, int shift,
                    const uint64_t* __restrict__ wpay, uint64_t wmask, unsigned long long* __restrict__ hist) {
-  __shared__ uint32_t sh[kMgBins];
-  for (int i = threadIdx.x; i < kMgBins; i += MG_THREADS) sh[i] = 0;
+  extern __shared__ __align__(16) unsigned long long sh_w[];  // [kMgBins] weighted, then u32 [kMgBins] plain
+  uint32_t* sh_c = reinterpret_cast<uint32_t*>(sh_w + kMgBins);
+  for (int i = threadIdx.x; i < kMgBins; i += MG_THREADS) {
+    sh_w[i] = 0;
+    sh_c[i] = 0;
+  }
   __syncthreads();
   const uint64_t stride = (uint64_t)gridDim.x * MG_THREADS;
   for (uint64_t i = (uint64_t)blockIdx.x * MG_THREADS + threadIdx.x; i < n; i += stride) {
     uint64_t b = (key[i] - sub) >> shift;
     if (b >= kMgBins) b = kMgBins - 1;
-    atomicAdd(&sh[b], wpay ? (uint32_t)(wpay[i] & wmask) : 1u);
+    atomicAdd(&sh_c[b], 1u);
+    atomicAdd(&sh_w[b], wpay ? (unsigned long long)(wpay[i] & wmask) : 1ull);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kMgBins; i += MG_THREADS)
-    if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+  for (int i = threadIdx.x; i < kMgBins; i += MG_THREADS) {
+    if (sh_w[i]) atomicAdd(&hist[i], sh_w[i]);
+    if (sh_c[i]) atomicAdd(&hist[kMgBins + i], (unsigned long long)sh_c[i]);
+  }
 }
 
-__global__ void __launch_bounds__(MG_THREADS)
-    mg_dest_kernel(const uint64_t* __restrict__ key, uint64_t n, uint64_t sub, const uint64_t* __restrict__ thr,
-                   int n_thr, uint32_t* __restrict__ dest, uint32_t* __restrict__ idx,
-                   unsigned long long* __restrict__ counts) {
-  __shared__ uint64_t s_thr[64];
-  __shared__ uint32_t s_cnt[64];
-  if (threadIdx.x < 64) {
-    s_thr[threadIdx.x] = (int)threadIdx.x < n_thr ? thr[threadIdx.x] : ~0ull;
-    s_cnt[threadIdx.x] = 0;
-  }
+// ---- fused multisplit + all-to-all over peer memory ------------------------------------------
+// One pass over the local items of an exchange stage: every item finds its destination rank
+// (thresholds on the radix key), gets its arrival row there -- stable: items keep their local
+// order per destination, and rank s's items follow rank s-1's, so the receive side is in global
+// emission order (SURVEY.md Q6 needs "first occurrence" to stay global) -- and is written STRAIGHT
+// into the destination GPU's arena through NVLink peer stores (mapped peer pointers), staged through
+// shared memory so that each destination receives contiguous, coalesced runs.  No pack buffer, no
+// NCCL all-to-all: the partition kernel is the transport.
+//
+// Cross-tile offsets come from a decoupled look-back over the tiles of THIS GPU only (tiles are
+// claimed in launch order); there is no waiting on another GPU inside the kernel.
+constexpr int SC_THREADS = 256;
+constexpr int SC_WARPS = SC_THREADS / 32;
+constexpr int SC_IPT = 8;
+constexpr int SC_TILE = SC_THREADS * SC_IPT;  // 2048 items per tile
+
+struct ScSmem {
+  uint64_t stage[SC_TILE];                 // one array at a time, in destination order
+  uint32_t wcnt[SC_WARPS][kMaxRanks];      // per-warp counts, then exclusive prefixes over the warps
+  uint32_t dstart[kMaxRanks + 1];          // first staging slot of each destination
+  uint64_t row0[kMaxRanks];                // arrival row of staging slot dstart[d]
+  uint8_t sdest[SC_TILE];                  // destination of each staging slot
+  uint32_t tile;
+};
+
+// look-back word: [63:62] flag, [61:0] count
+constexpr uint64_t SLB_AGG = 1ull << 62;
+constexpr uint64_t SLB_INC = 2ull << 62;
+constexpr uint64_t SLB_MASK = (1ull << 62) - 1;
+
+struct ScCtx {
+  uint32_t tile, tile_n;
+  uint64_t base;             // first local item of the tile
+  uint32_t slot[SC_IPT];     // staging slot of this thread's items
+  bool valid[SC_IPT];
+};
+
+// Ranks the tile's items by destination; leaves s.dstart / s.row0 / s.sdest and the slots in cx.
+__device__ __forceinline__ void sc_rank_tile(ScSmem& s, ScCtx& cx, const uint64_t* __restrict__ key, uint64_t n,
+                                             uint64_t sub, const MgPlan& pl, unsigned long long* lookback,
+                                             uint32_t* tile_counter) {
+  const int t = threadIdx.x, w = t >> 5;
+  const unsigned l = lane_id();
+  if (t == 0) s.tile = atomicAdd(tile_counter, 1u);
+  if (t < SC_WARPS * kMaxRanks) (&s.wcnt[0][0])[t] = 0;
   __syncthreads();
-  const uint64_t i = (uint64_t)blockIdx.x * MG_THREADS + threadIdx.x;
-  if (i < n) {
-    const uint64_t k = key[i] - sub;
+  cx.tile = s.tile;
+  cx.base = (uint64_t)cx.tile * SC_TILE;
+  cx.tile_n = (uint32_t)min((uint64_t)SC_TILE, n - cx.base);
+  uint32_t dest[SC_IPT], rank[SC_IPT];
+#pragma unroll
+  for (int i = 0; i < SC_IPT; ++i) {  // warp-striped: element e = w * 32 * IPT + i * 32 + lane
+    const uint32_t e = (uint32_t)w * 32 * SC_IPT + i * 32 + l;
+    cx.valid[i] = e < cx.tile_n;
     uint32_t d = 0;
-    for (int t = 0; t < n_thr; ++t) d += (s_thr[t] <= k) ? 1u : 0u;  // thresholds ascending
+    if (cx.valid[i]) {
+      const uint64_t k = key[cx.base + e] - sub;
+      for (int x = 0; x < pl.world - 1; ++x) d += (pl.thr[x] <= k) ? 1u : 0u;  // thresholds ascending
+    } else {
+      d = (uint32_t)pl.world;  // filler: after every real destination
+    }
     dest[i] = d;
-    idx[i] = (uint32_t)i;
-    atomicAdd(&s_cnt[d], 1u);
+    const unsigned m = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(m) - 1;
+    uint32_t old = 0;
+    if ((int)l == leader && d < (uint32_t)pl.world) {
+      old = s.wcnt[w][d];
+      s.wcnt[w][d] = old + (uint32_t)__popc(m);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[i] = old + (uint32_t)__popc(m & lanemask_lt());
+    __syncwarp();
   }
   __syncthreads();
-  if ((int)threadIdx.x <= n_thr && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+  // thread d < world owns destination d: prefix over the warps, tile count, look-back
+  if (t < pl.world) {
+    uint32_t sum = 0;
+    for (int ww = 0; ww < SC_WARPS; ++ww) {
+      const uint32_t c = s.wcnt[ww][t];
+      s.wcnt[ww][t] = sum;
+      sum += c;
+    }
+    s.dstart[t] = sum;  // count for now
+    volatile unsigned long long* lb = lookback;
+    uint64_t excl = 0;
+    if (cx.tile == 0) {
+      lb[(size_t)cx.tile * kMaxRanks + t] = SLB_INC | (uint64_t)sum;
+    } else {
+      lb[(size_t)cx.tile * kMaxRanks + t] = SLB_AGG | (uint64_t)sum;
+      int64_t j = (int64_t)cx.tile - 1;
+      while (true) {
+        const uint64_t st = lb[(size_t)j * kMaxRanks + t];
+        if ((st >> 62) == 0) continue;  // not published yet
+        excl += st & SLB_MASK;
+        if ((st >> 62) == 2) break;
+        --j;
+      }
+      lb[(size_t)cx.tile * kMaxRanks + t] = SLB_INC | (excl + sum);
+    }
+    s.row0[t] = pl.row0[t] + excl;
+  }
+  __syncthreads();
+  if (t == 0) {  // counts -> exclusive starts
+    uint32_t run = 0;
+    for (int d = 0; d < pl.world; ++d) {
+      const uint32_t c = s.dstart[d];
+      s.dstart[d] = run;
+      run += c;
+    }
+    s.dstart[pl.world] = run;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < SC_IPT; ++i) {
+    if (cx.valid[i]) {
+      cx.slot[i] = s.dstart[dest[i]] + s.wcnt[w][dest[i]] + rank[i];
+      s.sdest[cx.slot[i]] = (uint8_t)dest[i];
+    }
+  }
+  __syncthreads();
 }
 
-template <typename T>
-__global__ void __launch_bounds__(MG_THREADS)
-    gather_kernel(const T* __restrict__ src, const uint32_t* __restrict__ idx, uint64_t n, T* __restrict__ dst) {
-  const uint64_t i = (uint64_t)blockIdx.x * MG_THREADS + threadIdx.x;
-  if (i < n) dst[i] = src[idx[i]];
+// Moves one array: `load(e)` = value of local item e of the tile, `dst[d]` = the array at destination d.
+// Row r of destination d lands at dst[d][r * stride + offset] (interleaved side tables).
+template <typename T, typename L>
+__device__ __forceinline__ void sc_move(ScSmem& s, const ScCtx& cx, L&& load, T* const* dst, uint32_t stride = 1,
+                                        uint32_t offset = 0) {
+  const int t = threadIdx.x, w = t >> 5;
+  const unsigned l = lane_id();
+  T* st = reinterpret_cast<T*>(s.stage);
+#pragma unroll
+  for (int i = 0; i < SC_IPT; ++i)
+    if (cx.valid[i]) st[cx.slot[i]] = load((uint32_t)w * 32 * SC_IPT + i * 32 + l);
+  __syncthreads();
+  for (uint32_t j = t; j < cx.tile_n; j += SC_THREADS) {
+    const uint32_t d = s.sdest[j];
+    dst[d][(s.row0[d] + (j - s.dstart[d])) * stride + offset] = st[j];
+  }
+  __syncthreads();
+}
+
+// stage 0: digested records -> the owners of their mass slices
+__global__ void __launch_bounds__(SC_THREADS)
+    mg_scatter_records_kernel(const uint64_t* __restrict__ mass, const uint32_t* __restrict__ gpos,
+                              const uint32_t* __restrict__ prot, const uint16_t* __restrict__ len, uint64_t n,
+                              uint64_t sub, const __grid_constant__ MgPlan pl, const __grid_constant__ MgRecDst dst,
+                              unsigned long long* lookback, uint32_t* tile_counter) {
+  __shared__ ScSmem s;
+  ScCtx cx;
+  sc_rank_tile(s, cx, mass, n, sub, pl, lookback, tile_counter);
+  sc_move<uint64_t>(s, cx, [&](uint32_t e) { return mass[cx.base + e]; }, dst.mass);
+  sc_move<uint32_t>(s, cx, [&](uint32_t e) { return gpos[cx.base + e]; }, dst.gpos);
+  sc_move<uint32_t>(s, cx, [&](uint32_t e) { return prot[cx.base + e]; }, dst.prot);
+  sc_move<uint16_t>(s, cx, [&](uint32_t e) { return len[cx.base + e]; }, dst.len);
+  __threadfence_system();  // peer stores visible before the kernel is reported complete
+}
+
+// stage 1: variant groups -> the owners of their VARIANT mass slices.  A group travels with
+// everything its expansion needs: key, payload (the peptide field becomes the ARRIVAL ROW, which is
+// how the receiver finds the side tables), the peptide's global id and its C site masks.
+__global__ void __launch_bounds__(SC_THREADS)
+    mg_scatter_groups_kernel(const uint64_t* __restrict__ key, const uint64_t* __restrict__ pay,
+                             const uint64_t* __restrict__ cmask, int C, uint64_t id_off, uint64_t n,
+                             const __grid_constant__ MgPlan pl, const __grid_constant__ MgGrpDst dst,
+                             unsigned long long* lookback, uint32_t* tile_counter) {
+  __shared__ ScSmem s;
+  ScCtx cx;
+  sc_rank_tile(s, cx, key, n, 0, pl, lookback, tile_counter);
+  sc_move<uint64_t>(s, cx, [&](uint32_t e) { return key[cx.base + e]; }, dst.key);
+  if (C == 0) {  // per-variant records (more than 32 class sequences): payload = peptide id | pattern, nothing else
+    sc_move<uint64_t>(s, cx, [&](uint32_t e) { return pay[cx.base + e] + (id_off << 32); }, dst.pay);
+    __threadfence_system();
+    return;
+  }
+  {  // payload: peptide field := arrival row at the destination
+    const int t = threadIdx.x, w = t >> 5;
+    const unsigned l = lane_id();
+#pragma unroll
+    for (int i = 0; i < SC_IPT; ++i)
+      if (cx.valid[i]) s.stage[cx.slot[i]] = pay[cx.base + (uint32_t)w * 32 * SC_IPT + i * 32 + l];
+    __syncthreads();
+    for (uint32_t j = t; j < cx.tile_n; j += SC_THREADS) {
+      const uint32_t d = s.sdest[j];
+      const uint64_t row = s.row0[d] + (j - s.dstart[d]);
+      dst.pay[d][row] = (row << 32) | (s.stage[j] & 0xffffffffull);
+    }
+    __syncthreads();
+  }
+  sc_move<uint32_t>(s, cx, [&](uint32_t e) { return (uint32_t)((pay[cx.base + e] >> 32) + id_off); }, dst.gid);
+  for (int c = 0; c < C; ++c)
+    sc_move<uint64_t>(s, cx, [&](uint32_t e) {
+      return cmask[(pay[cx.base + e] >> 32) * (uint64_t)C + c];  // the payload names the LOCAL row of the (own) peptide
+    }, dst.mask, (uint32_t)C, (uint32_t)c);
+  __threadfence_system();
 }
 
 __global__ void __launch_bounds__(MG_THREADS)
@@ -105,28 +283,34 @@ void launch_mg_hist(const uint64_t* key, uint64_t n, uint64_t sub, int shift, co
                     unsigned long long* hist, cudaStream_t s) {
   if (n == 0) return;
   uint64_t g = (n + MG_THREADS * 8 - 1) / (MG_THREADS * 8);
-  if (g > (uint64_t)kNumSMsB200 * 8) g = (uint64_t)kNumSMsB200 * 8;
-  DBI_LAUNCH(mg_hist_kernel, (unsigned)g, MG_THREADS, 0, s, key, n, sub, shift, wpay, wmask, hist);
+  if (g > (uint64_t)kNumSMsB200 * 4) g = (uint64_t)kNumSMsB200 * 4;
+  const size_t smem = (size_t)kMgBins * 12;
+  DBI_CUDA(cudaFuncSetAttribute(mg_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DBI_LAUNCH(mg_hist_kernel, (unsigned)g, MG_THREADS, smem, s, key, n, sub, shift, wpay, wmask, hist);
 }
 
-void launch_mg_dest(const uint64_t* key, uint64_t n, uint64_t sub, const uint64_t* thresholds, int n_thr,
-                    uint32_t* dest, uint32_t* idx, unsigned long long* counts, cudaStream_t s) {
-  if (n == 0) return;
-  DBI_LAUNCH(mg_dest_kernel, (unsigned)((n + MG_THREADS - 1) / MG_THREADS), MG_THREADS, 0, s, key, n, sub, thresholds,
-             n_thr, dest, idx, counts);
+size_t mg_scatter_tmp_bytes(uint64_t n) {
+  const uint64_t tiles = (n + SC_TILE - 1) / SC_TILE;
+  return 256 + (size_t)tiles * kMaxRanks * 8;
 }
 
-void launch_gather_u64(const uint64_t* src, const uint32_t* idx, uint64_t n, uint64_t* dst, cudaStream_t s) {
+void launch_mg_scatter_records(const uint64_t* mass, const uint32_t* gpos, const uint32_t* prot, const uint16_t* len,
+                               uint64_t n, uint64_t sub, const MgPlan& pl, const MgRecDst& dst, void* tmp,
+                               cudaStream_t s) {
   if (n == 0) return;
-  DBI_LAUNCH(gather_kernel<uint64_t>, (unsigned)((n + MG_THREADS - 1) / MG_THREADS), MG_THREADS, 0, s, src, idx, n, dst);
+  const uint64_t tiles = (n + SC_TILE - 1) / SC_TILE;
+  DBI_CUDA(cudaMemsetAsync(tmp, 0, mg_scatter_tmp_bytes(n), s));
+  DBI_LAUNCH(mg_scatter_records_kernel, (unsigned)tiles, SC_THREADS, 0, s, mass, gpos, prot, len, n, sub, pl, dst,
+             (unsigned long long*)((uint8_t*)tmp + 256), (uint32_t*)tmp);
 }
-void launch_gather_u32(const uint32_t* src, const uint32_t* idx, uint64_t n, uint32_t* dst, cudaStream_t s) {
+
+void launch_mg_scatter_groups(const uint64_t* key, const uint64_t* pay, const uint64_t* cmask, int C, uint64_t id_off,
+                              uint64_t n, const MgPlan& pl, const MgGrpDst& dst, void* tmp, cudaStream_t s) {
   if (n == 0) return;
-  DBI_LAUNCH(gather_kernel<uint32_t>, (unsigned)((n + MG_THREADS - 1) / MG_THREADS), MG_THREADS, 0, s, src, idx, n, dst);
-}
-void launch_gather_u16(const uint16_t* src, const uint32_t* idx, uint64_t n, uint16_t* dst, cudaStream_t s) {
-  if (n == 0) return;
-  DBI_LAUNCH(gather_kernel<uint16_t>, (unsigned)((n + MG_THREADS - 1) / MG_THREADS), MG_THREADS, 0, s, src, idx, n, dst);
+  const uint64_t tiles = (n + SC_TILE - 1) / SC_TILE;
+  DBI_CUDA(cudaMemsetAsync(tmp, 0, mg_scatter_tmp_bytes(n), s));
+  DBI_LAUNCH(mg_scatter_groups_kernel, (unsigned)tiles, SC_THREADS, 0, s, key, pay, cmask, C, id_off, n, pl, dst,
+             (unsigned long long*)((uint8_t*)tmp + 256), (uint32_t*)tmp);
 }
 
 void launch_plo_to_counts(const uint64_t* plo, uint64_t n, uint32_t* cnt, cudaStream_t s) {

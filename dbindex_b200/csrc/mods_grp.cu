@@ -20,6 +20,8 @@
 // HBM-bound byte/integer work; no tensor cores.  Algorithmic bytes: K5m 14 + len per peptide read,
 // 8 C written; K5g/K6g 22 + 8 C per peptide, 16 per group written; K6x 24 per group + 8 C per
 // group (random 32-B sectors) read, 16 per entry written.
+#include <cstring>
+
 #include "mods_common.cuh"
 
 namespace dbi {
@@ -571,7 +573,8 @@ __global__ void __launch_bounds__(ET_THREADS, 4)
 __global__ void __launch_bounds__(MD_THREADS)
     grp_expand_long_kernel(const uint8_t* __restrict__ res, const DevTables* __restrict__ tb, DigestCfg cfg,
                            const uint32_t* __restrict__ u_gpos, const uint16_t* __restrict__ u_len,
-                           const uint32_t* __restrict__ gid_tab, const uint64_t* __restrict__ skey,
+                           const uint32_t* __restrict__ gid_tab, int use_uv, const __grid_constant__ UniqView uv,
+                           const uint64_t* __restrict__ skey,
                            const uint64_t* __restrict__ spay, const uint64_t* __restrict__ eoff,
                            const uint32_t* __restrict__ long_list,
                            const uint32_t* __restrict__ long_count, uint64_t base_bits, double* __restrict__ e_mass,
@@ -595,7 +598,17 @@ __global__ void __launch_bounds__(MD_THREADS)
     uint32_t bpk;
     const int bk = pack_seq(bseq, C, &bpk);
     bool bad = false;
-    const int n = warp_collect_sites(res, u_gpos[bb], u_len[bb], mt, ws, &bad);
+    uint32_t pgpos, plen;
+    if (use_uv) {  // sharded build: the peptide's (gpos, len) live with its owner (mapped peer table)
+      uint64_t prow;
+      const int pr = uniq_owner(uv, gid_tab[bb], &prow);
+      pgpos = uv.gpos[pr][prow];
+      plen = uv.len[pr][prow];
+    } else {
+      pgpos = u_gpos[bb];
+      plen = u_len[bb];
+    }
+    const int n = warp_collect_sites(res, pgpos, plen, mt, ws, &bad);
     // odometer over the first bk-1 sites, all lanes in lockstep.  State in registers only:
     // idxp byte L = site ordinal chosen at level L (0xff = none yet), pat = pattern of the prefix.
     uint32_t idxp = 0xffffffffu;
@@ -691,10 +704,11 @@ void launch_grp_tile_first(const uint64_t* eoff, uint64_t n_groups, uint64_t n_e
 
 // payload rows index cmask (and gid_tab, when the rows are arrival slots of a sharded build)
 void launch_grp_expand(const uint8_t* d_res, const DevTables* d_tb, const DigestCfg& cfg, const uint32_t* u_gpos,
-                       const uint16_t* u_len, const uint64_t* cmask, const uint32_t* gid_tab, const uint64_t* skey,
-                       const uint64_t* spay, const uint64_t* eoff, const uint32_t* tile_first, uint64_t n_groups,
-                       uint64_t n_entries, uint64_t base_bits, double* e_mass, uint32_t* e_base, uint32_t* e_pat,
-                       uint32_t* long_list, uint32_t* long_count, uint32_t long_cap, uint32_t* d_err, cudaStream_t s) {
+                       const uint16_t* u_len, const uint64_t* cmask, const uint32_t* gid_tab, const UniqView* uv,
+                       const uint64_t* skey, const uint64_t* spay, const uint64_t* eoff, const uint32_t* tile_first,
+                       uint64_t n_groups, uint64_t n_entries, uint64_t base_bits, double* e_mass, uint32_t* e_base,
+                       uint32_t* e_pat, uint32_t* long_list, uint32_t* long_count, uint32_t long_cap, uint32_t* d_err,
+                       cudaStream_t s) {
   if (n_groups == 0 || n_entries == 0) return;
   const uint64_t n_tiles = (n_entries + kExpTile - 1) / kExpTile;
   DBI_LAUNCH(grp_expand_tab_kernel, (unsigned)n_tiles, ET_THREADS, 0, s, cfg, cmask, gid_tab, skey, spay, eoff,
@@ -702,8 +716,11 @@ void launch_grp_expand(const uint8_t* d_res, const DevTables* d_tb, const Digest
   if (long_cap > 0) {
     unsigned grid = (long_cap + MD_WARPS - 1) / MD_WARPS;
     if (grid > (unsigned)kNumSMsB200 * 4) grid = (unsigned)kNumSMsB200 * 4;
-    DBI_LAUNCH(grp_expand_long_kernel, grid, MD_THREADS, 0, s, d_res, d_tb, cfg, u_gpos, u_len, gid_tab, skey, spay, eoff,
-               long_list, long_count, base_bits, e_mass, e_base, e_pat);
+    UniqView none;
+    std::memset(&none, 0, sizeof(none));
+    DBI_LAUNCH(grp_expand_long_kernel, grid, MD_THREADS, 0, s, d_res, d_tb, cfg, u_gpos, u_len, gid_tab,
+               (uv && gid_tab) ? 1 : 0, uv ? *uv : none, skey, spay, eoff, long_list, long_count, base_bits, e_mass,
+               e_base, e_pat);
   }
 }
 

@@ -47,19 +47,11 @@ __global__ void __launch_bounds__(Q_THREADS)
   if (cnt32) cnt32[q] = e > b ? (uint32_t)(e - b) : 0u;  // an index holds < 2^32 entries
 }
 
-// owner rank and row of a unique peptide named by its global id
-__device__ __forceinline__ int uniq_owner(const UniqView& uv, uint64_t gid, uint64_t* row) {
-  int r = 0;
-  while (r + 1 < uv.world && gid >= uv.uoff[r + 1]) ++r;
-  *row = gid - uv.uoff[r];
-  return r;
-}
-
 constexpr int HX_WARPS = Q_THREADS / 32;
 
 // K10a: one warp per query, lanes stride its hits (consecutive entries -> coalesced)
 __global__ void __launch_bounds__(Q_THREADS)
-    hits_expand_kernel(const uint32_t* __restrict__ e_base, uint64_t ent_off, UniqView uv,
+    hits_expand_kernel(const uint32_t* __restrict__ e_base, uint64_t ent_off, const __grid_constant__ UniqView uv,
                        const uint64_t* __restrict__ hit_begin, const uint64_t* __restrict__ hit_off, uint64_t nq,
                        uint32_t* __restrict__ hit_entry, uint32_t* __restrict__ len32, uint32_t* __restrict__ np32) {
   const uint64_t q = (uint64_t)blockIdx.x * HX_WARPS + (threadIdx.x >> 5);
@@ -86,7 +78,8 @@ __global__ void __launch_bounds__(Q_THREADS)
 __global__ void __launch_bounds__(Q_THREADS)
     hits_gather_kernel(const uint8_t* __restrict__ res, const uint32_t* __restrict__ pstart,
                        const double* __restrict__ e_mass, const uint32_t* __restrict__ e_base, uint64_t ent_off,
-                       const uint32_t* __restrict__ e_pat, UniqView uv, const uint32_t* __restrict__ hit_entry,
+                       const uint32_t* __restrict__ e_pat, const __grid_constant__ UniqView uv,
+                       const uint32_t* __restrict__ hit_entry,
                        const uint64_t* __restrict__ seq_off, const uint64_t* __restrict__ plo_out, uint64_t n_hits,
                        double* __restrict__ o_mass, uint32_t* __restrict__ o_prot, uint32_t* __restrict__ o_off,
                        uint16_t* __restrict__ o_len, uint32_t* __restrict__ o_pat, uint8_t* __restrict__ o_flanks,
@@ -138,19 +131,21 @@ __global__ void __launch_bounds__(Q_THREADS)
   }
 }
 
+// Entries name their base peptide by GLOBAL id; uv says which rank holds it (world = 1: this GPU).
 __global__ void __launch_bounds__(Q_THREADS)
-    fetch_sizes_kernel(const uint32_t* __restrict__ e_base, uint64_t base_off, uint64_t own_lo, uint64_t own_n,
-                       const uint64_t* __restrict__ u_plo, uint64_t begin, uint64_t count,
-                       uint32_t* __restrict__ sizes, uint32_t* __restrict__ tile_counts) {
+    fetch_sizes_kernel(const uint32_t* __restrict__ e_base, uint64_t base_off, const __grid_constant__ UniqView uv,
+                       uint64_t begin, uint64_t count, uint32_t* __restrict__ sizes,
+                       uint32_t* __restrict__ tile_counts) {
   __shared__ uint32_t scratch[Q_THREADS / 32 + 1];
   const uint64_t tile_base = (uint64_t)blockIdx.x * kScanTile;
   uint32_t sum = 0;
   for (int k = 0; k < Q_IPT; ++k) {
     const uint64_t i = tile_base + (uint64_t)k * Q_THREADS + threadIdx.x;
     if (i >= count) break;
-    // base peptides are named by GLOBAL ids; this handle holds [own_lo, own_lo + own_n) of them
-    const uint64_t b = (e_base ? (uint64_t)e_base[begin + i] : base_off + begin + i) - own_lo;
-    const uint32_t sz = b < own_n ? (uint32_t)(u_plo[b + 1] - u_plo[b]) : 0u;
+    const uint64_t gid = e_base ? (uint64_t)e_base[begin + i] : base_off + begin + i;
+    uint64_t row;
+    const int r = uniq_owner(uv, gid, &row);
+    const uint32_t sz = uv.plo[r] ? (uint32_t)(uv.plo[r][row + 1] - uv.plo[r][row]) : 0u;
     sizes[i] = sz;
     sum += sz;
   }
@@ -161,10 +156,7 @@ __global__ void __launch_bounds__(Q_THREADS)
 
 __global__ void __launch_bounds__(Q_THREADS)
     fetch_gather_kernel(const double* __restrict__ e_mass, const uint32_t* __restrict__ e_base, uint64_t base_off,
-                        uint64_t own_lo, uint64_t own_n, const uint16_t* __restrict__ g_len,
-                        const uint32_t* __restrict__ e_pat, const uint32_t* __restrict__ u_gpos,
-                        const uint32_t* __restrict__ u_prot, const uint16_t* __restrict__ u_len,
-                        const uint64_t* __restrict__ u_plo, const uint32_t* __restrict__ plist,
+                        const __grid_constant__ UniqView uv, const uint32_t* __restrict__ e_pat,
                         const uint32_t* __restrict__ pstart, uint64_t begin, uint64_t count,
                         const uint32_t* __restrict__ sizes, const uint64_t* __restrict__ tile_offs,
                         double* __restrict__ o_mass, uint32_t* __restrict__ o_prot, uint32_t* __restrict__ o_off,
@@ -184,19 +176,20 @@ __global__ void __launch_bounds__(Q_THREADS)
     if (valid) {
       const uint64_t e = begin + i;
       const uint64_t gid = e_base ? (uint64_t)e_base[e] : base_off + e;
-      const uint64_t b = gid - own_lo;
-      const bool own = b < own_n;  // else the base peptide lives on another GPU of a sharded build
-      const uint32_t pr = own ? u_prot[b] : 0xffffffffu;
+      uint64_t row;
+      const int r = uniq_owner(uv, gid, &row);
+      const bool own = uv.len[r] != nullptr;  // else the owner's tables are not mapped here
+      const uint32_t pr = own ? uv.prot[r][row] : 0xffffffffu;
       if (o_mass) o_mass[i] = e_mass[e];
       if (o_prot) o_prot[i] = pr;  // DBI_REMOTE_BASE
-      if (o_off) o_off[i] = own ? u_gpos[b] - pstart[pr] : (uint32_t)gid;  // sequenceOffset inside the first protein
-      if (o_len) o_len[i] = own ? u_len[b] : g_len[gid];
+      if (o_off) o_off[i] = own ? uv.gpos[r][row] - pstart[pr] : (uint32_t)gid;  // sequenceOffset inside the first protein
+      if (o_len) o_len[i] = own ? uv.len[r][row] : (uint16_t)0;
       if (o_pat) o_pat[i] = e_pat ? e_pat[e] : 0u;
       const uint64_t lo = running + ex;
       if (o_list_off) o_list_off[i] = lo;
       if (o_ids && own) {
-        const uint64_t src = u_plo[b];
-        for (uint32_t j = 0; j < sz; ++j) o_ids[lo + j] = plist[src + j];
+        const uint64_t src = uv.plo[r][row];
+        for (uint32_t j = 0; j < sz; ++j) o_ids[lo + j] = uv.plist[r][src + j];
       }
     }
     running += total;
@@ -269,25 +262,22 @@ void launch_hits_gather(const uint8_t* d_res, const uint32_t* pstart, const doub
              seq_off, plo_out, n_hits, o_mass, o_prot, o_off, o_len, o_pat, o_flanks, o_seq, o_ids);
 }
 
-void launch_fetch_sizes(const uint32_t* e_base, uint64_t base_off, uint64_t own_lo, uint64_t own_n,
-                        const uint64_t* u_plo, uint64_t begin, uint64_t count, uint32_t* sizes, uint32_t* tile_counts,
-                        cudaStream_t s) {
+void launch_fetch_sizes(const uint32_t* e_base, uint64_t base_off, const UniqView& uv, uint64_t begin, uint64_t count,
+                        uint32_t* sizes, uint32_t* tile_counts, cudaStream_t s) {
   if (count == 0) return;
   const unsigned tiles = (unsigned)((count + kScanTile - 1) / kScanTile);
-  DBI_LAUNCH(fetch_sizes_kernel, tiles, Q_THREADS, 0, s, e_base, base_off, own_lo, own_n, u_plo, begin, count, sizes,
-             tile_counts);
+  DBI_LAUNCH(fetch_sizes_kernel, tiles, Q_THREADS, 0, s, e_base, base_off, uv, begin, count, sizes, tile_counts);
 }
 
-void launch_fetch_gather(const double* e_mass, const uint32_t* e_base, uint64_t base_off, uint64_t own_lo,
-                         uint64_t own_n, const uint16_t* g_len, const uint32_t* e_pat,
-                         const uint32_t* u_gpos, const uint32_t* u_prot, const uint16_t* u_len, const uint64_t* u_plo, const uint32_t* plist,
-                         const uint32_t* pstart, uint64_t begin, uint64_t count, const uint32_t* sizes,
-                         const uint64_t* tile_offs, double* o_mass, uint32_t* o_prot, uint32_t* o_off,
-                         uint16_t* o_len, uint32_t* o_pat, uint64_t* o_list_off, uint32_t* o_ids, cudaStream_t s) {
+void launch_fetch_gather(const double* e_mass, const uint32_t* e_base, uint64_t base_off, const UniqView& uv,
+                         const uint32_t* e_pat, const uint32_t* pstart, uint64_t begin, uint64_t count,
+                         const uint32_t* sizes, const uint64_t* tile_offs, double* o_mass, uint32_t* o_prot,
+                         uint32_t* o_off, uint16_t* o_len, uint32_t* o_pat, uint64_t* o_list_off, uint32_t* o_ids,
+                         cudaStream_t s) {
   if (count == 0) return;
   const unsigned tiles = (unsigned)((count + kScanTile - 1) / kScanTile);
-  DBI_LAUNCH(fetch_gather_kernel, tiles, Q_THREADS, 0, s, e_mass, e_base, base_off, own_lo, own_n, g_len, e_pat, u_gpos, u_prot, u_len, u_plo, plist,
-             pstart, begin, count, sizes, tile_offs, o_mass, o_prot, o_off, o_len, o_pat, o_list_off, o_ids);
+  DBI_LAUNCH(fetch_gather_kernel, tiles, Q_THREADS, 0, s, e_mass, e_base, base_off, uv, e_pat, pstart, begin, count,
+             sizes, tile_offs, o_mass, o_prot, o_off, o_len, o_pat, o_list_off, o_ids);
 }
 
 void launch_key_flags(const double* e_mass, uint64_t n, double factor, uint8_t* flags, uint32_t* tile_counts,

@@ -1,45 +1,49 @@
-"""Multi-GPU index build and query routing: one process per GPU, torch.distributed
-for the plumbing (NCCL over NVLink on GPUs, gloo on CPU in the tests).
+"""Sharded (multi-GPU) index build and query routing: one process per GPU,
+torch.distributed for the SMALL collectives only (NCCL on GPUs, gloo on CPU in the tests).
 
 The reference shards its index by mass into `indexFactor` SQLite files
 (DBIndexStoreSQLiteMult.java:55-56,215-217) and answers a query from the buckets its range
 touches (:333-343).  Here a bucket is a GPU:
 
-  1. every rank holds the whole residue buffer (3 GB even at TrEMBL scale) and digests its own
-     range of start positions;
-  2. global key histogram (all-reduce) -> equal-count splitters -> all-to-all of the records, so
-     rank d receives one contiguous mass slice, rank-ordered = global emission order, which keeps
-     "first occurrence"  global;
-  3. local sort + merge: every rank owns the unique peptides (first occurrence, protein lists) of
-     its base-mass slice; a peptide is named by its global id = rank offset + local row;
-  4. differential mods: every rank lists the variant GROUPS of its own peptides (one record per
-     peptide and sequence of shift classes -- they share one mass); the groups go through a second
-     histogram -> splitters (weighted by variant count) -> all-to-all by VARIANT mass, and the
-     receiver sorts and expands them.  To expand a foreign peptide's group a rank only needs where
-     its residues are, so (gpos, len) of all unique peptides -- 6 bytes each -- are all-gathered;
-     nothing else is replicated.  A hit whose base peptide lives elsewhere is resolved by its owner
-     (`fetch_resolved`), the way a query is answered by the rank that owns its mass;
-  5. queries are routed on the host with the same splitters; a range that straddles a splitter is
+  1. every rank is given ITS OWN shard of the FASTA (proteins in rank order, so ids stay global),
+     packs it into its place of the global residue buffer (window 0) and pulls the other shards over
+     NVLink -- the FASTA crosses PCIe once, not once per GPU;
+  2. every rank digests its share of the start positions;
+  3. exchange 0: weighted key histogram -> all-reduce -> equal-count splitters -> ONE kernel that
+     partitions the records and writes them straight into the owners' arenas (mapped peer memory);
+     rank-ordered arrival keeps "first occurrence" global;
+  4. local sort + merge: every rank owns the unique peptides of its base-mass slice (window 2, mapped by
+     the others: a hit whose base peptide lives elsewhere is read through the mapping);
+  5. differential mods: every rank lists the variant GROUPS of its own peptides; exchange 1 moves them,
+     with their site masks, to the owners of their VARIANT mass slices, which sort and expand them;
+  6. queries are routed on the host with the splitter masses; a range that straddles a splitter is
      answered by both neighbours, exactly like Mult.getSequences walking two buckets.
 
-`ShardEngine` is the device side of one rank.  `GpuShardEngine` drives the C ABI (dbi_mg_*); the
-tests plug in a CPU engine so that the orchestration runs under gloo without a GPU.
+What crosses torch.distributed per exchange: one 64 KB all-reduce (the two histograms), one all-gather
+of ~350 bytes per rank (send counts, unique count, window descriptors) and one barrier.
+
+`ShardEngine` is the device side of one rank.  `GpuShardEngine` drives the C ABI (dbi_mg_*); the tests
+plug in a CPU engine so that the orchestration runs under gloo without a GPU.  A host that holds every
+handle in ONE process (the Java shim) calls dbi_mg_build_local instead of any of this.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Tuple
+from typing import Tuple
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
 MG_BINS = 4096
+WIN_PROTEOME, WIN_ARENA, WIN_UNIQUE = 0, 1, 2
+DESC_BYTES = 96  # sizeof(dbi_mg_window)
 
 
 # ---- pure host logic (unit-tested on CPU) -------------------------------------------------------
 def pick_splitters(hist: np.ndarray, world: int) -> np.ndarray:
     """Equal-count bin splitters: rank d receives the bins [s[d-1], s[d]).  Bins are never split, so
-    equal keys (equal masses) stay on one rank and the merge of equal peptides remains local."""
+    equal keys (equal masses) stay on one rank and the merge of equal peptides remains local.
+    (Same arithmetic as dbi_mg_plan in capi_mg.inl.)"""
     total = int(hist.sum())
     cum = np.cumsum(hist.astype(np.int64))
     out = np.empty(max(world - 1, 0), dtype=np.uint32)
@@ -49,6 +53,17 @@ def pick_splitters(hist: np.ndarray, world: int) -> np.ndarray:
         out[d - 1] = int(np.searchsorted(cum, target, side="left")) + 1 if total else 0
     np.minimum(out, len(hist), out=out)
     return np.maximum.accumulate(out) if len(out) else out
+
+
+def plan_exchange(world: int, hist_global: np.ndarray, hist_local: np.ndarray):
+    """(bin splitters, this rank's send counts, every rank's receive total) from the summed and the own
+    [weighted | plain] histograms."""
+    B = MG_BINS
+    split = pick_splitters(hist_global[:B], world)
+    edges = np.concatenate(([0], split, [B])).astype(np.int64)
+    send = np.array([hist_local[B + edges[d]:B + edges[d + 1]].sum() for d in range(world)], dtype=np.uint64)
+    recv = np.array([hist_global[B + edges[d]:B + edges[d + 1]].sum() for d in range(world)], dtype=np.uint64)
+    return split, send, recv
 
 
 def splitter_masses(bin_splitters: np.ndarray, shift: int, min_mass: float) -> np.ndarray:
@@ -65,117 +80,61 @@ def route_queries(lo: np.ndarray, hi: np.ndarray, split_mass: np.ndarray, rank: 
     return np.nonzero((hi >= left) & (lo < right))[0]
 
 
-# ---- collectives on raw bytes -------------------------------------------------------------------
+# ---- tiny collectives ---------------------------------------------------------------------------
 def _world() -> int:
     return dist.get_world_size() if dist.is_initialized() else 1
 
 
-def _all_to_all_rows(send: torch.Tensor, send_counts: Sequence[int], recv_counts: Sequence[int]) -> torch.Tensor:
-    """all-to-all-v of a 1-D typed tensor split by element counts (rank-ordered receive).  Moved as
-    raw bytes: NCCL has no 16-bit integer type and the payload is opaque anyway."""
-    out = torch.empty(int(sum(recv_counts)), dtype=send.dtype, device=send.device)
-    if _world() == 1:
-        out.copy_(send)
-        return out
-    w = send.element_size()
-    dist.all_to_all_single(out.view(torch.uint8), send.contiguous().view(torch.uint8),
-                           output_split_sizes=[int(c) * w for c in recv_counts],
-                           input_split_sizes=[int(c) * w for c in send_counts])
-    return out
-
-
-def _gather_concat(local: torch.Tensor, counts: Sequence[int]) -> torch.Tensor:
-    """Rank-order concatenation of every rank's 1-D tensor on every rank (variable sizes)."""
-    return _gather_tables([local], [counts])[0]
-
-
-def _gather_tables(tables: Sequence[torch.Tensor], counts: Sequence[Sequence[int]]) -> List[torch.Tensor]:
-    """Rank-order concatenation of several 1-D tensors at once: every rank packs its tables into one
-    byte buffer (padded to the largest rank), ONE all-gather moves them, and each table is cut out
-    of the gathered rows.  counts[i][r] = elements of table i on rank r."""
-    if _world() == 1:
-        return list(tables)
-    world = dist.get_world_size()
-    dev = tables[0].device
-    widths = [t.element_size() for t in tables]
-    # byte offset of table i inside rank r's row (16-byte aligned so that typed views stay aligned)
-    offs = []
-    row_bytes = 0
-    for r in range(world):
-        o, cur = [], 0
-        for i, w in enumerate(widths):
-            o.append(cur)
-            cur += (int(counts[i][r]) * w + 15) & ~15
-        offs.append(o)
-        row_bytes = max(row_bytes, cur)
-    row_bytes = max(row_bytes, 16)
-    rank = dist.get_rank()
-    row = torch.empty(row_bytes, dtype=torch.uint8, device=dev)
-    for i, t in enumerate(tables):
-        n = t.numel() * widths[i]
-        if n:
-            row[offs[rank][i]:offs[rank][i] + n].copy_(t.contiguous().view(torch.uint8))
-    rows = torch.empty(world * row_bytes, dtype=torch.uint8, device=dev)
-    dist.all_gather_into_tensor(rows, row)
-    rows = rows.view(world, row_bytes)
-    out = []
-    for i, t in enumerate(tables):
-        parts = [rows[r, offs[r][i]:offs[r][i] + int(counts[i][r]) * widths[i]] for r in range(world) if counts[i][r]]
-        cat = torch.cat(parts) if parts else torch.empty(0, dtype=torch.uint8, device=dev)
-        out.append(cat.view(t.dtype))
-    return out
-
-
-def _exchange_counts(send_counts: np.ndarray, device) -> np.ndarray:
+def _all_gather_bytes(row: np.ndarray, device) -> np.ndarray:
+    """Every rank's fixed-size byte row on every rank: [world, len(row)] (one small all-gather + D2H)."""
     world = _world()
-    s = torch.tensor(send_counts.astype(np.int64), device=device)
-    r = torch.empty(world, dtype=torch.int64, device=device)
     if world == 1:
-        r.copy_(s)
-    else:
-        dist.all_to_all_single(r, s)
-    return r.cpu().numpy()
+        return row[None, :].copy()
+    t = torch.from_numpy(np.ascontiguousarray(row, dtype=np.uint8)).to(device)
+    out = torch.empty(world * t.numel(), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(out, t)
+    return out.cpu().numpy().reshape(world, -1)
 
 
-def _all_gather_ints(vals: Sequence[int], device) -> np.ndarray:
-    world = _world()
-    t = torch.tensor(list(vals), dtype=torch.int64, device=device)
-    if world == 1:
-        return t.cpu().numpy()[None, :]
-    out = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(out, t)
-    return torch.stack(out).cpu().numpy()
+def _barrier(device):
+    """Stream-ordered barrier: work enqueued afterwards runs after every rank has reached this point."""
+    if _world() > 1:
+        dist.all_reduce(torch.zeros(1, dtype=torch.int32, device=device))
 
 
 class ShardEngine:
-    """Device side of one rank.  Arrays are 1-D torch tensors on `device` with signed dtypes of
-    the same width as the C types (int64 for u64/f64 bits, int32 for u32, int16 for u16)."""
+    """Device side of one rank (GpuShardEngine: libdbindex_gpu.so; tests: a CPU model)."""
 
     device = torch.device("cpu")
     has_mods = False
     min_mass = 0.0
 
     def begin(self, rank: int, world: int): ...
+    def shard_info(self) -> Tuple[int, int]: ...                 # (proteins, residues) of the own shard
+    def set_shards(self, shard_proteins, shard_residues) -> np.ndarray: ...   # lays window 0 out; its descriptor
+    def window(self, window: int, nbytes: int) -> np.ndarray: ...            # ensure + describe (uint8[96])
+    def import_window(self, window: int, rank: int, desc: np.ndarray): ...
+    def layout_bytes(self, window: int, stage: int, n_items: int) -> int: ...
+    def pull_proteome(self): ...
     def digest(self) -> int: ...
-    def histogram(self, stage: int) -> Tuple[torch.Tensor, int]: ...          # (int64[MG_BINS], shift)
-    def partition(self, stage: int, splitters: np.ndarray) -> np.ndarray: ...  # send counts [world]
-    def pack_send(self, stage: int) -> List[torch.Tensor]: ...
-    def index_base(self, mass, gpos, prot, length): ...
-    def export_unique(self) -> List[torch.Tensor]: ...   # gpos (int32), len (int16) of the own unique peptides
-    def import_unique(self, rank_unique, tables: List[torch.Tensor]): ...   # their rank-order concatenation
+    def hist(self, stage: int) -> Tuple[torch.Tensor, int]: ...   # (int64[2 * MG_BINS] on device, shift)
+    def scatter(self, stage: int, splitters: np.ndarray, matrix: np.ndarray): ...
+    def index_base(self): ...
+    def n_unique(self) -> int: ...
+    def set_unique(self, rank_unique: np.ndarray): ...
+    def groups(self) -> Tuple[int, int]: ...                      # (items that travel, variants)
+    def index_variants(self): ...
     def finish(self): ...
-    def own_tiles(self) -> Tuple[int, int]: ...                                # (tile_begin, n_tiles) of the own peptides
-    def expand(self, tile_begin: int, n_tiles: int) -> int: ...
-    def index_variants(self, key, payload): ...
 
 
 def build_sharded(engine: ShardEngine) -> dict:
-    """Run the staged multi-rank build on this rank.  Returns routing info:
-    {"split_mass": masses at which the entry slices are cut, "bytes_sent": ..., ...}."""
+    """Run the sharded build on this rank.  Returns routing info: {"split_mass": masses at which the entry
+    slices are cut, "unique_off": global id of every rank's first unique peptide, "a2a_bytes": ...}."""
     import time
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
     dev = engine.device
-    info = {"rank": rank, "world": world, "a2a_bytes": 0, "t": {}}
+    cuda = dev.type == "cuda"
+    info = {"rank": rank, "world": world, "a2a_bytes": 0, "a2a_ms": 0.0, "t": {}}
     t_last = [time.perf_counter()]
 
     def lap(name):  # host wall-clock per stage (every engine call ends synchronised)
@@ -183,247 +142,234 @@ def build_sharded(engine: ShardEngine) -> dict:
         info["t"][name] = info["t"].get(name, 0.0) + 1e3 * (now - t_last[0])
         t_last[0] = now
 
+    def connect(window: int, descs: np.ndarray):
+        for r in range(world):
+            if r != rank:
+                engine.import_window(window, r, descs[r])
+
     engine.begin(rank, world)
+    # ---- the proteome: own shard over PCIe (already added), the other shards over NVLink
+    np_, nr_ = engine.shard_info()
+    sizes = _all_gather_bytes(np.array([np_, nr_], dtype=np.uint64).view(np.uint8), dev).view(np.uint64).reshape(world, 2)
+    d0 = engine.set_shards(sizes[:, 0].copy(), sizes[:, 1].copy())
+    connect(WIN_PROTEOME, _all_gather_bytes(d0, dev))  # also the barrier: every shard is packed
+    engine.pull_proteome()
+    lap("proteome")
     engine.digest()
     lap("digest")
 
-    info["a2a_ms"] = 0.0
-    cuda = dev.type == "cuda"
-
-    def exchange(stage: int, widths: Sequence[int]):
-        hist, shift = engine.histogram(stage)
+    def exchange(stage: int, item_bytes: int):
+        hist, shift = engine.hist(stage)
+        local = hist.clone()
         if world > 1:
             dist.all_reduce(hist)
-        splitters = pick_splitters(hist.cpu().numpy(), world)
+        hg, hl = hist.cpu().numpy().view(np.uint64), local.cpu().numpy().view(np.uint64)
+        split, send, recv = plan_exchange(world, hg, hl)
         lap(f"hist{stage}")
-        send_counts = engine.partition(stage, splitters)
-        lap(f"partition{stage}")
-        recv_counts = _exchange_counts(send_counts, dev)
-        bufs = engine.pack_send(stage)
-        lap(f"pack{stage}")
+        d1 = engine.window(WIN_ARENA, engine.layout_bytes(WIN_ARENA, stage, int(recv[rank])))
+        d2 = engine.window(WIN_UNIQUE, engine.layout_bytes(WIN_UNIQUE, 0, int(recv[rank])) if stage == 0 else 0)
+        row = np.concatenate([send.view(np.uint8), np.array([engine.n_unique()], dtype=np.uint64).view(np.uint8), d1, d2])
+        rows = _all_gather_bytes(row, dev)  # every rank is past its previous use of the arenas
+        matrix = rows[:, :8 * world].copy().view(np.uint64).reshape(world, world)
+        ru = rows[:, 8 * world:8 * world + 8].copy().view(np.uint64).reshape(world)
+        o = 8 * world + 8
+        connect(WIN_ARENA, rows[:, o:o + DESC_BYTES])
+        connect(WIN_UNIQUE, rows[:, o + DESC_BYTES:o + 2 * DESC_BYTES])
+        if stage == 1:
+            engine.set_unique(ru)
+        lap(f"plan{stage}")
         if cuda:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        recv = [_all_to_all_rows(b, send_counts, recv_counts) for b in bufs]
+        engine.scatter(stage, split, matrix)
         if cuda:
             e1.record()
             e1.synchronize()
             info["a2a_ms"] += e0.elapsed_time(e1)
-        sent_off_rank = int(send_counts.sum() - send_counts[rank])
-        info["a2a_bytes"] += sent_off_rank * int(sum(widths))
-        lap(f"a2a{stage}")
-        return recv, splitters, shift
+        _barrier(dev)  # every rank's stores into this rank's arena are complete
+        info["a2a_bytes"] += int(send.sum() - send[rank]) * item_bytes
+        lap(f"scatter{stage}")
+        return split, shift
 
-    recv, base_split, shift = exchange(0, (8, 4, 4, 2))
-    engine.index_base(*recv)
-    del recv
+    base_split, shift = exchange(0, 18)
+    engine.index_base()
     lap("index_base")
     if not engine.has_mods:
-        n_u = engine.n_unique()
-        info["unique_off"] = np.concatenate(([0], np.cumsum(_all_gather_ints([n_u], dev)[:, 0])))
-        info["n_unique"] = int(info["unique_off"][-1])
+        ru = _all_gather_bytes(np.array([engine.n_unique()], dtype=np.uint64).view(np.uint8), dev).view(np.uint64).reshape(world)
+        engine.set_unique(ru)
         engine.finish()
+        _barrier(dev)
+        info["unique_off"] = np.concatenate(([0], np.cumsum(ru))).astype(np.int64)
+        info["n_unique"] = int(ru.sum())
         info["split_mass"] = splitter_masses(base_split, shift, engine.min_mass)
+        lap("finish")
         return info
-
-    tables = engine.export_unique()
-    rank_unique = _all_gather_ints([int(tables[0].numel())], dev)[:, 0]
-    gathered = _gather_tables(tables, [rank_unique] * len(tables))
-    lap("gather_gpos_len")
-    engine.import_unique(rank_unique, gathered)
-    del tables, gathered
-    lap("import_unique")
-    info["unique_off"] = np.concatenate(([0], np.cumsum(rank_unique)))
-    info["n_unique"] = int(rank_unique.sum())
     # every rank lists the groups of its own peptides: that work is small and nearly even; the
-    # expensive part (sort + expansion) is balanced by the variant-weighted splitters below
-    first_tile = 0
-    tb, tn = engine.own_tiles()
-    engine.expand(first_tile + tb, tn)
-    lap("expand")
-    recv, var_split, shift = exchange(1, (8, 8))
-    engine.index_variants(*recv)
+    # expensive part (sort + expansion) is balanced by the variant-weighted splitters
+    engine.groups()
+    lap("groups")
+    var_split, shift = exchange(1, engine.group_bytes())
+    engine.index_variants()
+    engine.finish()
+    _barrier(dev)  # nobody frees or rebuilds its windows while another rank may still read them
     lap("index_variants")
+    ru = engine.rank_unique
+    info["unique_off"] = np.concatenate(([0], np.cumsum(ru))).astype(np.int64)
+    info["n_unique"] = int(ru.sum())
     info["split_mass"] = splitter_masses(var_split, shift, engine.min_mass)
     return info
 
 
 # ---- the GPU engine ---------------------------------------------------------------------------
 class GpuShardEngine(ShardEngine):
-    """Drives libdbindex_gpu.so's dbi_mg_* entry points for one rank."""
+    """Drives libdbindex_gpu.so's dbi_mg_* entry points for one rank.  `index` is a
+    dbindex_b200.GpuIndex that was given THIS RANK'S shard of the proteins."""
 
     def __init__(self, index, device: torch.device):
         import ctypes as C
         self.C = C
-        self.g = index           # dbindex_b200.GpuIndex with the (replicated) proteins added
+        self.g = index
         self.lib = index.lib
         self.device = device
         p = index.params
         self.has_mods = p.n_mods > 0 and p.max_mods_per_peptide > 0
         self.min_mass = float(p.min_mass)
-        self._send = None
+        self.rank_unique = None
         vp, u64p = C.c_void_p, C.POINTER(C.c_uint64)
         sig = {
-            "dbi_mg_begin": [vp, C.c_int, C.c_int],
-            "dbi_mg_digest": [vp, u64p],
-            "dbi_mg_histogram": [vp, C.c_int, vp, C.POINTER(C.c_int)],
-            "dbi_mg_partition": [vp, C.c_int, vp, vp],
-            "dbi_mg_pack_send": [vp, C.c_int, vp, vp, vp, vp],
-            "dbi_mg_index_base": [vp, vp, vp, vp, vp, C.c_uint64],
-            "dbi_mg_unique_counts": [vp, u64p, u64p],
-            "dbi_mg_export_unique": [vp, vp, vp],
-            "dbi_mg_import_unique": [vp, vp, vp, vp],
-            "dbi_mg_finish": [vp],
-            "dbi_mg_own_tiles": [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)],
-            "dbi_mg_expand": [vp, C.c_uint32, C.c_uint32, u64p],
-            "dbi_mg_index_variants": [vp, vp, vp, C.c_uint64],
+            "dbi_mg_begin": (C.c_int, [vp, C.c_int, C.c_int]),
+            "dbi_mg_set_shards": (C.c_int, [vp, vp, vp, u64p]),
+            "dbi_mg_window_ensure": (C.c_int, [vp, C.c_int, C.c_uint64, vp]),
+            "dbi_mg_window_import": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+            "dbi_mg_layout_bytes": (C.c_uint64, [C.c_int, C.c_int, C.c_uint64, C.c_int]),
+            "dbi_mg_side_classes": (C.c_int, [vp]),
+            "dbi_mg_pull_proteome": (C.c_int, [vp]),
+            "dbi_mg_digest": (C.c_int, [vp, u64p]),
+            "dbi_mg_hist": (C.c_int, [vp, C.c_int, vp, C.POINTER(C.c_int)]),
+            "dbi_mg_scatter": (C.c_int, [vp, C.c_int, vp, vp]),
+            "dbi_mg_index_base": (C.c_int, [vp]),
+            "dbi_mg_unique_count": (C.c_int, [vp, u64p]),
+            "dbi_mg_set_unique": (C.c_int, [vp, vp]),
+            "dbi_mg_groups": (C.c_int, [vp, u64p, u64p]),
+            "dbi_mg_index_variants": (C.c_int, [vp]),
+            "dbi_mg_finish": (C.c_int, [vp]),
         }
-        for name, args in sig.items():
+        for name, (res, args) in sig.items():
             fn = getattr(self.lib, name)
-            fn.restype = C.c_int
+            fn.restype = res
             fn.argtypes = args
+        self.side_classes = self.lib.dbi_mg_side_classes(self.g._h)
 
     def _ck(self, rc):
         self.g._check(rc)
 
-    @staticmethod
-    def _p(t: Optional[torch.Tensor]):
-        return None if t is None or t.numel() == 0 else t.data_ptr()
-
-    def _empty(self, n, dtype):
-        return torch.empty(int(n), dtype=dtype, device=self.device)
-
     def begin(self, rank, world):
-        self.world = world
+        self.rank, self.world = rank, world
         self._ck(self.lib.dbi_mg_begin(self.g._h, rank, world))
+
+    def shard_info(self):
+        st = self.g.stats()
+        return st["n_proteins"], st["n_residues"]
+
+    def window(self, window, nbytes):
+        d = np.zeros(DESC_BYTES, dtype=np.uint8)
+        self._ck(self.lib.dbi_mg_window_ensure(self.g._h, window, int(nbytes), d.ctypes.data))
+        return d
+
+    def import_window(self, window, rank, desc):
+        d = np.ascontiguousarray(desc, dtype=np.uint8)
+        self._ck(self.lib.dbi_mg_window_import(self.g._h, window, rank, d.ctypes.data))
+
+    def layout_bytes(self, window, stage, n_items):
+        return int(self.lib.dbi_mg_layout_bytes(window, stage, int(n_items), self.side_classes))
+
+    def group_bytes(self):
+        return 20 + 8 * self.side_classes if self.side_classes else 16
+
+    def set_shards(self, shard_proteins, shard_residues):
+        sp = np.ascontiguousarray(shard_proteins, dtype=np.uint64)
+        sr = np.ascontiguousarray(shard_residues, dtype=np.uint64)
+        need = self.C.c_uint64()
+        self._ck(self.lib.dbi_mg_set_shards(self.g._h, sp.ctypes.data, sr.ctypes.data, self.C.byref(need)))
+        d = self.window(WIN_PROTEOME, need.value)
+        self._ck(self.lib.dbi_mg_set_shards(self.g._h, sp.ctypes.data, sr.ctypes.data, None))
+        return d
+
+    def pull_proteome(self):
+        self._ck(self.lib.dbi_mg_pull_proteome(self.g._h))
 
     def digest(self):
         n = self.C.c_uint64()
         self._ck(self.lib.dbi_mg_digest(self.g._h, self.C.byref(n)))
-        self.n_local = n.value
         return n.value
 
-    def histogram(self, stage):
-        hist = torch.zeros(MG_BINS, dtype=torch.int64, device=self.device)
+    def hist(self, stage):
+        hist = torch.zeros(2 * MG_BINS, dtype=torch.int64, device=self.device)
         shift = self.C.c_int()
         torch.cuda.current_stream().synchronize()
-        self._ck(self.lib.dbi_mg_histogram(self.g._h, stage, hist.data_ptr(), self.C.byref(shift)))
+        self._ck(self.lib.dbi_mg_hist(self.g._h, stage, hist.data_ptr(), self.C.byref(shift)))
         return hist, shift.value
 
-    def partition(self, stage, splitters):
+    def scatter(self, stage, splitters, matrix):
         sp = np.ascontiguousarray(splitters, dtype=np.uint32)
-        counts = np.zeros(self.world, dtype=np.uint64)
-        self._ck(self.lib.dbi_mg_partition(self.g._h, stage, sp.ctypes.data if len(sp) else None, counts.ctypes.data))
-        self._n_stage = int(counts.sum())
-        return counts
+        m = np.ascontiguousarray(matrix, dtype=np.uint64)
+        self._ck(self.lib.dbi_mg_scatter(self.g._h, stage, sp.ctypes.data if len(sp) else None, m.ctypes.data))
 
-    def pack_send(self, stage):
-        n = self._n_stage
-        if stage == 0:
-            bufs = [self._empty(n, torch.int64), self._empty(n, torch.int32), self._empty(n, torch.int32),
-                    self._empty(n, torch.int16)]
-        else:
-            bufs = [self._empty(n, torch.int64), self._empty(n, torch.int64), None, None]
+    def index_base(self):
         torch.cuda.current_stream().synchronize()
-        self._ck(self.lib.dbi_mg_pack_send(self.g._h, stage, *[self._p(b) for b in bufs]))
-        return [b for b in bufs if b is not None]
-
-    def index_base(self, mass, gpos, prot, length):
-        torch.cuda.current_stream().synchronize()
-        self._ck(self.lib.dbi_mg_index_base(self.g._h, self._p(mass), self._p(gpos), self._p(prot), self._p(length),
-                                            int(mass.numel())))
+        self._ck(self.lib.dbi_mg_index_base(self.g._h))
 
     def n_unique(self):
-        u, p = self.C.c_uint64(), self.C.c_uint64()
-        self._ck(self.lib.dbi_mg_unique_counts(self.g._h, self.C.byref(u), self.C.byref(p)))
+        u = self.C.c_uint64()
+        self._ck(self.lib.dbi_mg_unique_count(self.g._h, self.C.byref(u)))
         return u.value
 
-    def export_unique(self):
-        u = self.n_unique()
-        t = [self._empty(u, torch.int32), self._empty(u, torch.int16)]
-        torch.cuda.current_stream().synchronize()
-        self._ck(self.lib.dbi_mg_export_unique(self.g._h, *[self._p(x) for x in t]))
-        return t
-
-    def import_unique(self, rank_unique, tables):
+    def set_unique(self, rank_unique):
         ru = np.ascontiguousarray(rank_unique, dtype=np.uint64)
+        self.rank_unique = ru
+        self._ck(self.lib.dbi_mg_set_unique(self.g._h, ru.ctypes.data))
+
+    def groups(self):
+        n, v = self.C.c_uint64(), self.C.c_uint64()
+        self._ck(self.lib.dbi_mg_groups(self.g._h, self.C.byref(n), self.C.byref(v)))
+        return n.value, v.value
+
+    def index_variants(self):
         torch.cuda.current_stream().synchronize()
-        self._ck(self.lib.dbi_mg_import_unique(self.g._h, ru.ctypes.data, *[self._p(x) for x in tables]))
+        self._ck(self.lib.dbi_mg_index_variants(self.g._h))
 
     def finish(self):
         self._ck(self.lib.dbi_mg_finish(self.g._h))
 
-    def own_tiles(self):
-        t0, nt = self.C.c_uint32(), self.C.c_uint32()
-        self._ck(self.lib.dbi_mg_own_tiles(self.g._h, self.C.byref(t0), self.C.byref(nt)))
-        return t0.value, nt.value
 
-    def expand(self, tile_begin, n_tiles):
-        v = self.C.c_uint64()
-        self._ck(self.lib.dbi_mg_expand(self.g._h, tile_begin, n_tiles, self.C.byref(v)))
-        return v.value
-
-    def index_variants(self, key, payload):
-        torch.cuda.current_stream().synchronize()
-        self._ck(self.lib.dbi_mg_index_variants(self.g._h, self._p(key), self._p(payload), int(key.numel())))
+def shard_proteins(residues: np.ndarray, offsets: np.ndarray, rank: int, world: int):
+    """Rank's contiguous share of a proteome, balanced by residues: (residues, offsets, first protein id)."""
+    n = len(offsets) - 1
+    total = int(offsets[-1])
+    cuts = [int(np.searchsorted(offsets, total * r // world, side="left")) for r in range(world)] + [n]
+    cuts[0] = 0
+    cuts = np.minimum(np.maximum.accumulate(cuts), n)
+    p0, p1 = int(cuts[rank]), int(cuts[rank + 1])
+    off = offsets[p0:p1 + 1] - offsets[p0]
+    return residues[int(offsets[p0]):int(offsets[p1])], off.astype(np.uint64), p0
 
 
-# ---- hits whose base peptide lives on another rank ---------------------------------------------
-REMOTE_BASE = 0xFFFFFFFF
-
-
-def lookup_unique(g, gids: np.ndarray) -> dict:
-    """dbi_mg_lookup_unique on the rank that owns `gids`: first occurrence and protein list of each."""
+def build_local(indexes) -> None:
+    """dbi_mg_build_local: the whole sharded build when this process holds every handle (`indexes[r]` was
+    given shard r).  Same kernels as build_sharded; the small collectives are plain host code."""
     import ctypes as C
-    lib = g.lib
-    lib.dbi_mg_lookup_unique.restype = C.c_int
-    lib.dbi_mg_lookup_unique.argtypes = [C.c_void_p] * 2 + [C.c_uint64] + [C.c_void_p] * 5 + [C.c_uint64, C.c_void_p]
-    gids = np.ascontiguousarray(gids, dtype=np.uint32)
-    n = len(gids)
-    prot, off = np.empty(n, np.uint32), np.empty(n, np.uint32)
-    ln, plo = np.empty(n, np.uint16), np.empty(n + 1, np.uint64)
-    n_ids = C.c_uint64()
-    p = lambda a: a.ctypes.data if a.size else None  # noqa: E731
-    g._check(lib.dbi_mg_lookup_unique(g._h, p(gids), n, None, None, None, None, None, 0, C.byref(n_ids)))
-    ids = np.empty(n_ids.value, np.uint32)
-    g._check(lib.dbi_mg_lookup_unique(g._h, p(gids), n, p(prot), p(off), p(ln), plo.ctypes.data, p(ids), len(ids),
-                                      C.byref(n_ids)))
-    return {"first_prot": prot, "first_off": off, "len": ln, "prot_list_off": plo, "prot_ids": ids}
+    lib = indexes[0].lib
+    lib.dbi_mg_build_local.restype = C.c_int
+    lib.dbi_mg_build_local.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    arr = (C.c_void_p * len(indexes))(*[g._h for g in indexes])
+    indexes[0]._check(lib.dbi_mg_build_local(arr, len(indexes)))
 
 
-def fetch_resolved(g, info: dict, begin: int, count: int, lookup=None) -> dict:
-    """COLLECTIVE dbi_fetch of entries [begin, begin + count) of this rank's slice with every base
-    peptide resolved: hits whose base lives on another rank (first_prot == DBI_REMOTE_BASE, first_off
-    = global id) are answered by their owners.  A process that holds all the handles (the Java host)
-    calls the owner's handle directly instead of this exchange."""
-    f = g.fetch(begin, count)
-    if not dist.is_initialized() or dist.get_world_size() == 1:
-        return f
-    lookup = lookup or lookup_unique
-    world, rank = dist.get_world_size(), dist.get_rank()
-    uoff = np.asarray(info["unique_off"], dtype=np.int64)
-    remote = np.nonzero(f["first_prot"] == REMOTE_BASE)[0]
-    gids = f["first_off"][remote].astype(np.int64)
-    owner = np.searchsorted(uoff, gids, side="right") - 1
-    ask = [np.unique(gids[owner == r]).astype(np.uint32) for r in range(world)]
-    asked = [None] * world
-    dist.all_gather_object(asked, ask)           # asked[src][dst] = ids src wants from dst
-    answers = [lookup(g, asked[src][rank]) if len(asked[src][rank]) else None for src in range(world)]
-    got = [None] * world
-    dist.all_gather_object(got, answers)         # got[dst][src] = dst's answer to src
-    plo = f["prot_list_off"].astype(np.int64)
-    lists = [f["prot_ids"][plo[i]:plo[i + 1]] for i in range(len(plo) - 1)]
-    for r in range(world):
-        ans = got[r][rank]
-        if ans is None:
-            continue
-        pos = {int(gid): k for k, gid in enumerate(ask[r])}
-        alo = ans["prot_list_off"].astype(np.int64)
-        for i in remote[owner == r]:
-            k = pos[int(f["first_off"][i])]
-            f["first_prot"][i], f["first_off"][i] = ans["first_prot"][k], ans["first_off"][k]
-            lists[i] = ans["prot_ids"][alo[k]:alo[k + 1]]
-    sizes = np.array([len(x) for x in lists], dtype=np.int64)
-    f["prot_list_off"] = np.concatenate(([0], np.cumsum(sizes))).astype(np.uint64)
-    f["prot_ids"] = np.concatenate(lists).astype(np.uint32) if len(lists) and sizes.sum() else np.zeros(0, np.uint32)
-    return f
+def split_masses(index, world: int) -> np.ndarray:
+    import ctypes as C
+    lib = index.lib
+    lib.dbi_mg_split_masses.restype = C.c_int
+    lib.dbi_mg_split_masses.argtypes = [C.c_void_p, C.c_void_p]
+    out = np.zeros(max(world - 1, 0), dtype=np.float64)
+    index._check(lib.dbi_mg_split_masses(index._h, out.ctypes.data if world > 1 else None))
+    return out

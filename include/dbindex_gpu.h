@@ -35,7 +35,7 @@ extern "C" {
 #define DBI_EINVAL (-3)   /* bad argument / unsupported parameter      */
 #define DBI_ENOMEM (-4)   /* host or device allocation failed          */
 #define DBI_ECUDA (-5)    /* no device, or a CUDA call failed          */
-#define DBI_ENCCL (-6)    /* reserved for the multi-GPU exchange       */
+#define DBI_ENCCL (-6)    /* reserved (the exchanges need no NCCL)     */
 #define DBI_ERANGE (-7)   /* a hard limit was exceeded (see below)     */
 
 /* ---- hard limits ---------------------------------------------------------- */
@@ -309,75 +309,86 @@ int dbi_fasta_counts(const dbi_fasta* f, uint32_t* n_proteins, uint64_t* n_resid
 int dbi_fasta_read(const dbi_fasta* f, uint8_t* residues, uint64_t* offsets, char* deflines, uint64_t* defline_off);
 void dbi_fasta_close(dbi_fasta* f);
 
-/* ---- multi-GPU staged build -----------------------------------------
- * One process and one handle per GPU.  Every rank adds the SAME proteins (the residue
- * buffer is replicated, 4 GB even at TrEMBL scale), digests only its own range of start
- * positions, and the ranks exchange records so that rank d ends up with one contiguous
- * mass slice -- the GPU analogue of DBIndexStoreSQLiteMult's per-bucket SQLite files
- * (DBIndexStoreSQLiteMult.java:55-56,215-217).  The collectives themselves (all-reduce of
- * the histograms, all-to-all of the records and of the variant groups, all-gather of the
- * (gpos, len) of the unique peptides) are issued by
- * the host over NCCL on caller-owned device buffers; these entry points are the device work
- * between them.  dbindex_b200/multigpu.py is the reference orchestration.  All `d_` pointers
- * are device memory of the handle's GPU.
+/* ---- sharded (multi-GPU) build ------------------------------------------------
+ * The reference shards its index by mass into `indexFactor` SQLite files
+ * (DBIndexStoreSQLiteMult.java:55-56,215-217) and answers a query from the buckets its range touches
+ * (:333-343).  Here a bucket is a GPU holding one contiguous slice of the mass axis.  One handle per GPU
+ * = one rank; rank r is given ITS shard of the FASTA (dbi_add_proteins; the shards follow each other in
+ * rank order, so protein ids stay global and in file order).  The bulk data moves inside two kernels
+ * that write straight into the other GPUs' memory over NVLink (mapped peer memory); the caller only
+ * carries small host arrays between the ranks (two 32 KB histograms, a world x world count matrix,
+ * 96-byte window descriptors) with whatever transport it has -- torch.distributed / NCCL between
+ * processes (dbindex_b200/multigpu.py), nothing at all when one process holds every handle:
  *
- *   dbi_mg_begin -> dbi_mg_digest
- *   -> dbi_mg_histogram(0) .. all-reduce .. dbi_mg_partition(0) -> dbi_mg_pack_send(0) .. all-to-all ..
- *   -> dbi_mg_index_base
- *   no mods:  -> dbi_mg_finish
- *   mods:     -> dbi_mg_export_unique .. all-gather of (gpos, len) .. dbi_mg_import_unique
- *             -> dbi_mg_own_tiles -> dbi_mg_expand
- *             -> dbi_mg_histogram(1) .. dbi_mg_partition(1) -> dbi_mg_pack_send(1) .. all-to-all ..
- *             -> dbi_mg_index_variants
- */
+ *   dbi_mg_build_local(handles, n)        the whole sharded build, one process (what a Java host calls)
+ *
+ * or, one process per GPU, stage by stage:
+ *
+ *   dbi_mg_begin
+ *   dbi_mg_set_shards(sizing) -> dbi_mg_window_ensure(0) -> dbi_mg_set_shards -> [exchange window 0] ->
+ *   dbi_mg_pull_proteome                  every rank now holds the packed residues of all shards
+ *   dbi_mg_digest                         its share of the start positions
+ *   dbi_mg_hist(0) .. [all-reduce] .. dbi_mg_plan .. dbi_mg_window_ensure(1, 2) .. [all-gather counts +
+ *   windows] .. dbi_mg_window_import .. dbi_mg_scatter(0) .. [barrier]
+ *   dbi_mg_index_base                     sort + merge of this rank's base-mass slice
+ *   [all-gather n_unique] dbi_mg_set_unique
+ *   no mods:  dbi_mg_finish
+ *   mods:     dbi_mg_groups -> dbi_mg_hist(1) .. dbi_mg_plan .. dbi_mg_scatter(1) .. [barrier] ->
+ *             dbi_mg_index_variants -> dbi_mg_finish
+ *
+ * Afterwards dbi_query / dbi_query_hits / dbi_fetch answer for the rank's slice; base peptides owned by
+ * another rank are read through its mapped window 2.  Ranks are <= DBI_MG_MAX_RANKS (one NVSwitch box). */
 #define DBI_MG_BINS 4096
+#define DBI_MG_MAX_RANKS 16
+#define DBI_MG_WIN_PROTEOME 0 /* packed residues of all shards + protein starts        */
+#define DBI_MG_WIN_ARENA 1    /* what the exchanges deliver to this rank               */
+#define DBI_MG_WIN_UNIQUE 2   /* first occurrence + protein lists of the own peptides  */
+#define DBI_REMOTE_BASE 0xffffffffu /* first_prot of a hit whose owner's window 2 is not mapped */
+
+/* How another rank maps a window: a CUDA IPC handle between processes, the pointer itself inside one. */
+typedef struct dbi_mg_window {
+  uint8_t ipc[64];
+  uint64_t ptr;
+  uint64_t bytes;
+  int32_t device;
+  int32_t pid;
+  uint64_t reserved;
+} dbi_mg_window;
+
 int dbi_mg_begin(dbi_handle* h, int rank, int world);
-/* pack the replicated proteome, digest this rank's share of the start positions */
+/* shard_proteins / shard_residues [world]: what every rank added.  window0_bytes != NULL: sizing call;
+ * NULL: lay the global buffer out in window 0 and pack the own shard into its place. */
+int dbi_mg_set_shards(dbi_handle* h, const uint64_t* shard_proteins, const uint64_t* shard_residues,
+                      uint64_t* window0_bytes);
+/* make the window hold >= bytes (it only grows; bytes = 0 just describes it) and describe it */
+int dbi_mg_window_ensure(dbi_handle* h, int window, uint64_t bytes, dbi_mg_window* desc);
+int dbi_mg_window_import(dbi_handle* h, int window, int rank, const dbi_mg_window* desc);
+/* bytes of window 1 for n_items of exchange `stage`, or of window 2 for n_items records of exchange 0 */
+uint64_t dbi_mg_layout_bytes(int window, int stage, uint64_t n_items, int n_classes);
+int dbi_mg_side_classes(dbi_handle* h); /* n_classes argument of dbi_mg_layout_bytes for this handle */
+int dbi_mg_pull_proteome(dbi_handle* h);
 int dbi_mg_digest(dbi_handle* h, uint64_t* n_records);
-/* stage 0 = digested records, 1 = mod variants: d_hist[DBI_MG_BINS] (u64) += histogram of
- * (radix key >> *shift) */
-int dbi_mg_histogram(dbi_handle* h, int stage, uint64_t* d_hist, int* shift);
-/* bin_splitters[world-1] (host, ascending bin indices): items whose bin >= bin_splitters[d-1]
- * go to rank >= d.  send_counts[world] (host) receives how many items go to each rank. */
-int dbi_mg_partition(dbi_handle* h, int stage, const uint32_t* bin_splitters, uint64_t* send_counts);
-/* items grouped by destination rank (stable) into caller buffers.  stage 0: d0 = mass bits
- * u64[n], d1 = gpos u32[n], d2 = prot u32[n], d3 = len u16[n]; stage 1: d0 = key u64[n],
- * d1 = payload u64[n]. */
-int dbi_mg_pack_send(dbi_handle* h, int stage, void* d0, void* d1, void* d2, void* d3);
-/* sort + merge the n records received for this rank's mass slice (rank-ordered receive
- * buffers keep the global emission order, so "first occurrence" stays global) */
-int dbi_mg_index_base(dbi_handle* h, const void* d_mass, const void* d_gpos, const void* d_prot,
-                      const void* d_len, uint64_t n);
-int dbi_mg_unique_counts(dbi_handle* h, uint64_t* n_unique, uint64_t* n_plist);
-/* Differential mods only.  A rank expands the groups whose MASS falls into its slice, and their
- * peptides belong to any rank; all it needs of a foreign peptide is where its residues are.  So
- * every rank publishes (gpos u32[u], len u16[u]) of its unique peptides ... */
-int dbi_mg_export_unique(dbi_handle* h, void* d_gpos, void* d_len);
-/* ... and adopts the rank-order concatenation of them (device buffers, all-gathered by the host).
- * From here on a unique peptide is named by its GLOBAL id = sum(rank_unique[0..owner)) + local row;
- * masses, first occurrences and protein lists stay with the owner (dbi_mg_lookup_unique). */
-int dbi_mg_import_unique(dbi_handle* h, const uint64_t* rank_unique, const void* d_gpos, const void* d_len);
-/* no differential mods: the entries of this rank are its own unique peptides (no table exchange) */
+/* d_hist: u64[2 * DBI_MG_BINS] in device memory, zeroed by the caller: += weighted | plain histogram of
+ * the local items of exchange `stage` (0 = digested records, 1 = variant groups) over key >> *shift */
+int dbi_mg_hist(dbi_handle* h, int stage, void* d_hist, int* shift);
+/* host arithmetic on the summed (global) and the own (local) histograms: equal-weight bin splitters
+ * [world-1], this rank's send counts [world], every rank's receive total [world] */
+int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_local, uint32_t* bin_splitters,
+                uint64_t* send_counts, uint64_t* recv_totals);
+/* matrix[s * world + d] = items rank s sends to rank d.  Stable multisplit of the local items straight
+ * into the mapped arenas of their destinations; every rank's arena must have been ensured for its
+ * receive total and imported here.  A barrier across the ranks must follow before anybody consumes. */
+int dbi_mg_scatter(dbi_handle* h, int stage, const uint32_t* bin_splitters, const uint64_t* matrix);
+int dbi_mg_index_base(dbi_handle* h);
+int dbi_mg_unique_count(dbi_handle* h, uint64_t* n_unique);
+int dbi_mg_set_unique(dbi_handle* h, const uint64_t* rank_unique);
+int dbi_mg_groups(dbi_handle* h, uint64_t* n_items, uint64_t* n_variants);
+int dbi_mg_index_variants(dbi_handle* h);
 int dbi_mg_finish(dbi_handle* h);
-/* the mod tiles (256 unique peptides each) of this rank's own unique peptides */
-int dbi_mg_own_tiles(dbi_handle* h, uint32_t* tile_begin, uint32_t* n_tiles);
-/* dbi_fetch on a sharded index with mods returns first_prot = DBI_REMOTE_BASE and first_off =
- * global id for entries whose base peptide is held by another rank; that rank resolves them here:
- * first occurrence (protein, offset), length and the protein list of each listed global id
- * (same two-call sizing of prot_ids as dbi_fetch). */
-#define DBI_REMOTE_BASE 0xffffffffu
-int dbi_mg_lookup_unique(dbi_handle* h, const uint32_t* gids, uint64_t n, uint32_t* first_prot, uint32_t* first_off,
-                         uint16_t* len, uint64_t* prot_list_off, uint32_t* prot_ids, uint64_t prot_ids_capacity,
-                         uint64_t* n_prot_ids);
-/* list the variant groups of tiles [tile_begin, tile_begin + n_tiles) of this rank's unique
- * peptides.  What travels
- * in stage 1 is one {key, payload} record per (peptide, class sequence) group -- all its
- * variants share one mass -- or one per variant when there are more than 32 class sequences;
- * the stage-1 histogram weighs a group by its variant count. */
-int dbi_mg_expand(dbi_handle* h, uint32_t tile_begin, uint32_t n_tiles, uint64_t* n_variants);
-/* sort the n variants received for this rank's variant-mass slice into its entry arrays;
- * d_key / d_payload are clobbered */
-int dbi_mg_index_variants(dbi_handle* h, void* d_key, void* d_payload, uint64_t n);
+/* masses at which the entry slices are cut: a query [lo, hi] belongs to every rank d with
+ * split[d-1] <= hi and lo < split[d] (DBIndexStoreSQLiteMult.java:333-343 walks buckets the same way) */
+int dbi_mg_split_masses(dbi_handle* h, double* split_mass);
+int dbi_mg_build_local(dbi_handle** handles, int n);
 
 /* Test hook for K7: stable radix sort of n host (key, value) pairs on key bits
  * [begin_bit, end_bit), in place, on the handle's GPU. */

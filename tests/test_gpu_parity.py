@@ -378,14 +378,98 @@ def _visible_gpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("name", ["cfg1_tryptic", "cfg2_mods", "cfg3_semi", "cfg2_mods:no_mask_table",
-                                  "many_classes"])
+def _dup_proteome(n_prot, seed=4711):
+    """A proteome with duplicated proteins far apart (different shards): the merge must stay global."""
+    res, off = synth.synth_proteome(n_prot, seed, median_len=150 if n_prot <= 100 else 400, min_len=5)
+    seqs = [res[int(off[i]):int(off[i + 1])] for i in range(len(off) - 1)]
+    seqs = seqs + [seqs[0], seqs[1]] + seqs[20:23] + [np.frombuffer(b"G" * 70 + b"MSTYMWSTK" + b"G" * 12 + b"MR", np.uint8)]
+    res = np.concatenate(seqs)
+    off = np.zeros(len(seqs) + 1, np.uint64)
+    np.cumsum([len(x) for x in seqs], out=off[1:])
+    return res, off
+
+
+def check_sharded(handles, o, split_mass):
+    """The rank slices, in rank order, ARE the oracle's index: masses position by position, first
+    occurrences and protein lists global, slices cut at the splitter masses, routed queries and
+    materialised hits summing to the global answer."""
+    from dbindex_b200.multigpu import route_queries
+    exp = o.entries()
+    world = len(handles)
+    counts = [g.stats()["n_entries"] for g in handles]
+    assert sum(counts) == len(exp["mass"]), (counts, len(exp["mass"]))
+    a = 0
+    plo = exp["prot_list_off"].astype(np.int64)
+    for r, g in enumerate(handles):
+        n = counts[r]
+        got = g.fetch(0, n)
+        assert not np.any(got["first_prot"] == 0xFFFFFFFF), "a base peptide of another rank was not resolved"
+        sl = {k: exp[k][a:a + n] for k in ("mass", "first_prot", "first_off", "len", "modpat")}
+        sl["prot_list_off"] = (plo[a:a + n + 1] - plo[a]).astype(np.uint64)
+        sl["prot_ids"] = exp["prot_ids"][plo[a]:plo[a + n]]
+        assert_entries_equal(got, sl)
+        if n:
+            if r > 0:
+                assert got["mass"][0] >= split_mass[r - 1]
+            if r < world - 1:
+                assert got["mass"][-1] < split_mass[r]
+        a += n
+    _, _, lo, hi = synth.synth_queries(exp["mass"], 300, 3, da_fraction=0.4)
+    ob, oc, _ = o.query(lo, hi)
+    total = np.zeros(len(lo), np.int64)
+    exp_hits = hits_canonical(o.query_hits(lo, hi))
+    got_hits = [[] for _ in lo]
+    for r, g in enumerate(handles):
+        sel = route_queries(lo, hi, split_mass, r)
+        b, c = g.query(lo, hi)
+        part = np.zeros(len(lo), np.int64)
+        part[sel] = c[sel]
+        assert np.array_equal(c.astype(np.int64), part), "routing dropped hits"
+        total += part
+        if len(sel):
+            hc = hits_canonical(g.query_hits(lo[sel], hi[sel]))
+            for k, q in enumerate(sel):
+                got_hits[q].extend(hc[k])
+    assert np.array_equal(total, oc.astype(np.int64)), "routed hit counts differ from the global answer"
+    assert [sorted(x) for x in got_hits] == exp_hits, "materialised hits differ from the oracle's"
+
+
+@pytest.mark.parametrize("name,world", [("cfg1_tryptic", 2), ("cfg2_mods", 2), ("cfg2_mods", 3), ("cfg3_semi", 4),
+                                        ("many_classes", 2), ("three_classes_k2", 3), ("mandatory_K_no_h2o", 2)])
+def test_sharded_build_in_one_process_matches_oracle(name, world):
+    """SURVEY.md 8e / invariant 11 through dbi_mg_build_local: `world` ranks = `world` handles of THIS
+    process (all on cuda:0 here, so the 1-GPU test box exercises every kernel of the sharded path:
+    shard packing + peer pulls, the two multisplit-scatter exchanges into mapped windows, group
+    expansion from travelling site masks, hits resolved through the owners' windows)."""
+    from dbindex_b200.multigpu import build_local, shard_proteins, split_masses
+    p = dbi.default_params(**PARAM_SETS[name])
+    res, off = _dup_proteome(600)
+    handles = []
+    try:
+        for r in range(world):
+            g = dbi.GpuIndex(p)
+            sres, soff, _ = shard_proteins(res, off, r, world)
+            g.add_proteins(sres, soff)
+            handles.append(g)
+        build_local(handles)
+        o = Oracle(p, threads=NCPU)
+        o.add_proteins(res, off)
+        assert o.build() == 0
+        check_sharded(handles, o, split_masses(handles[0], world))
+        # idempotent: reset every rank and build again
+        for g in handles:
+            g.reset_index()
+        build_local(handles)
+        assert sum(g.stats()["n_entries"] for g in handles) == o.counts()["n_entries"]
+    finally:
+        for g in handles:
+            g.close()
+
+
+@pytest.mark.parametrize("name", ["cfg1_tryptic", "cfg2_mods", "cfg3_semi", "many_classes"])
 def test_multi_gpu_sharded_build_matches_oracle(name, tmp_path):
-    """SURVEY.md 8e / invariant 11: the N-GPU index (range-sharded digest, NCCL all-to-all by mass
-    slice, group exchange by variant mass, base peptides resolved by their owners) equals the
-    oracle's, slice by slice, and routed queries sum to the global answer.  Runs with every visible
-    GPU (needs >= 2).  ":no_mask_table" forces the expansion to rebuild site masks per group (the
-    path taken when a mask table over all unique peptides would not fit)."""
+    """The same through one process per GPU (torchrun, NCCL for the small collectives, CUDA IPC mappings
+    of the windows).  Runs with every visible GPU (needs >= 2)."""
     import subprocess
     import sys
     n = _visible_gpus()
@@ -394,12 +478,8 @@ def test_multi_gpu_sharded_build_matches_oracle(name, tmp_path):
     n = 2 if n < 4 else (4 if n < 8 else 8)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = tmp_path / "r.json"
-    env = dict(os.environ)
-    name, _, variant = name.partition(":")
-    if variant == "no_mask_table":
-        env["DBI_MG_NO_MASK_TABLE"] = "1"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
-           "127.0.0.1", "--master-port", str(29800 + len(name) + len(variant)), os.path.join(root, "tests", "dist_worker.py"),
+           "127.0.0.1", "--master-port", str(29800 + len(name)), os.path.join(root, "tests", "dist_worker.py"),
            name, str(out), "gpu", "1500"]
-    p = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=900, env=env)
+    p = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=900, env=dict(os.environ))
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
