@@ -1,14 +1,14 @@
 """A CPU ShardEngine backed by the oracle and numpy -- TEST INFRASTRUCTURE.  Lets the multi-rank
-orchestration of dbindex_b200/multigpu.py (splitters, all-to-all, the (gpos, len) all-gather, group
-exchange under global peptide ids, query routing) run under gloo without a GPU.  It shards by PROTEIN ranges (the GPU
-engine shards by start-position tiles; both concatenate to the global emission order)."""
+orchestration of dbindex_b200/multigpu.py (shard layout, histograms -> plan -> count matrix, the two
+exchanges, unique offsets, query routing) run under gloo without a GPU.  Windows do not exist here:
+`scatter` delivers with a gloo all-to-all and the descriptors are dummies."""
 from __future__ import annotations
 
 import numpy as np
 import torch
+import torch.distributed as dist
 
-import dbindex_b200 as dbi
-from dbindex_b200.multigpu import MG_BINS, ShardEngine
+from dbindex_b200.multigpu import DESC_BYTES, MG_BINS, ShardEngine, shard_proteins
 from oracle.oracle_py import Oracle
 
 from . import pyref
@@ -20,9 +20,10 @@ def _bits(a):
 
 class OracleShardEngine(ShardEngine):
     def __init__(self, params, residues, offsets):
+        """residues / offsets: the WHOLE proteome; begin() keeps only this rank's shard (like a rank that
+        parsed its own part of the FASTA) until pull_proteome() gathers the others."""
         self.params = params
-        self.residues = np.ascontiguousarray(residues, np.uint8)
-        self.offsets = np.ascontiguousarray(offsets, np.uint64)
+        self._all = (np.ascontiguousarray(residues, np.uint8), np.ascontiguousarray(offsets, np.uint64))
         self.has_mods = params.n_mods > 0 and params.max_mods_per_peptide > 0
         self.min_mass = float(params.min_mass)
         self.nomod = params.copy()
@@ -32,7 +33,8 @@ class OracleShardEngine(ShardEngine):
         span = int(np.float64(params.max_mass).view(np.uint64)) - self.base_bits
         self.nbits = span.bit_length()
         self.shift = max(0, self.nbits - 12)
-        self.pstart = (self.offsets[:-1] + np.arange(len(self.offsets) - 1, dtype=np.uint64) + 1).astype(np.int64)
+        self.rank_unique = None
+        self._nu = 0
 
     # ---- helpers
     def _gpos(self, prot, off):
@@ -48,65 +50,102 @@ class OracleShardEngine(ShardEngine):
     # ---- stages
     def begin(self, rank, world):
         self.rank, self.world = rank, world
+        self.shard_res, self.shard_off, self.p0 = shard_proteins(self._all[0], self._all[1], rank, world)
+        self._all = None  # from here on a rank only knows its own shard
+
+    def shard_info(self):
+        return len(self.shard_off) - 1, int(self.shard_off[-1])
+
+    def set_shards(self, shard_proteins_, shard_residues):
+        assert int(shard_proteins_[self.rank]) == len(self.shard_off) - 1
+        self.sp = np.asarray(shard_proteins_, dtype=np.int64)
+        return np.zeros(DESC_BYTES, np.uint8)
+
+    def window(self, window, nbytes):
+        return np.zeros(DESC_BYTES, np.uint8)
+
+    def import_window(self, window, rank, desc):
+        pass
+
+    def layout_bytes(self, window, stage, n_items):
+        return 0
+
+    def group_bytes(self):
+        return 16
+
+    def pull_proteome(self):
+        parts = [None] * self.world
+        dist.all_gather_object(parts, (self.shard_res, self.shard_off))
+        assert [len(o) - 1 for _, o in parts] == self.sp.tolist()
+        self.residues = np.concatenate([r for r, _ in parts])
+        lens = np.concatenate([np.diff(o.astype(np.int64)) for _, o in parts])
+        self.offsets = np.concatenate(([0], np.cumsum(lens))).astype(np.uint64)
+        self.pstart = (self.offsets[:-1] + np.arange(len(self.offsets) - 1, dtype=np.uint64) + 1).astype(np.int64)
 
     def digest(self):
-        P = len(self.offsets) - 1
-        p0, p1 = P * self.rank // self.world, P * (self.rank + 1) // self.world
         o = Oracle(self.nomod)
-        sub = self.offsets[p0:p1 + 1] - self.offsets[p0]
-        o.add_proteins(self.residues[int(self.offsets[p0]):int(self.offsets[p1])], sub)
+        o.add_proteins(self.shard_res, self.shard_off)
         assert o.build() == 0
         e = o.emitted()
-        prot = e["prot"] + np.uint32(p0)
+        prot = e["prot"] + np.uint32(self.p0)
         self.rec = [_bits(e["mass"]).copy(), self._gpos(prot, e["off"]), prot, e["len"].copy()]
         return len(prot)
 
     def _keys(self, stage):
         return (self.rec[0] - np.uint64(self.base_bits)) if stage == 0 else self.var[0]
 
-    def histogram(self, stage):
+    def hist(self, stage):
         bins = (self._keys(stage) >> np.uint64(self.shift)).astype(np.int64)
-        return torch.from_numpy(np.bincount(bins, minlength=MG_BINS).astype(np.int64)), self.shift
+        plain = np.bincount(bins, minlength=MG_BINS).astype(np.int64)
+        return torch.from_numpy(np.concatenate([plain, plain])), self.shift  # every item weighs 1 here
 
-    def partition(self, stage, splitters):
-        thr = splitters.astype(np.uint64) << np.uint64(self.shift)
+    def scatter(self, stage, splitters, matrix):
+        thr = np.asarray(splitters, dtype=np.uint64) << np.uint64(self.shift)
         dest = np.searchsorted(thr, self._keys(stage), side="right")
-        self.perm = np.argsort(dest, kind="stable")
-        return np.bincount(dest, minlength=self.world).astype(np.uint64)
-
-    def pack_send(self, stage):
+        perm = np.argsort(dest, kind="stable")
+        send = np.bincount(dest, minlength=self.world)
+        assert send.tolist() == matrix[self.rank].astype(np.int64).tolist(), "count matrix row differs from the partition"
+        recv = matrix[:, self.rank].astype(np.int64)
         src = self.rec if stage == 0 else self.var
-        dt = [np.int64, np.int32, np.int32, np.int16] if stage == 0 else [np.int64, np.int64]
-        return [torch.from_numpy(a[self.perm].view(d).copy()) for a, d in zip(src, dt)]
+        if stage == 1:  # peptides travel under their global id
+            src = [src[0], src[1] + (np.uint64(self.uoff) << np.uint64(32))]
+        out = []
+        for a in src:
+            raw = np.ascontiguousarray(a[perm]).view(np.uint8)
+            w = a.dtype.itemsize
+            got = torch.empty(int(recv.sum()) * w, dtype=torch.uint8)
+            if self.world == 1:
+                got.copy_(torch.from_numpy(raw.copy()))
+            else:
+                dist.all_to_all_single(got, torch.from_numpy(raw.copy()), output_split_sizes=[int(c) * w for c in recv],
+                                       input_split_sizes=[int(c) * w for c in send])
+            out.append(got.numpy().view(a.dtype))
+        self.arena = out
 
-    def index_base(self, mass, gpos, prot, length):
-        mass = mass.numpy().view(np.float64)
-        gpos, prot = gpos.numpy().view(np.uint32), prot.numpy().view(np.uint32)
-        length = length.numpy().view(np.uint16)
+    def index_base(self):
+        mass, gpos, prot, length = self.arena
         o = Oracle(self.nomod)
         o.add_proteins(self.residues, self.offsets)
-        assert o.build_from_records(mass, prot, self._prot_off(gpos, prot), length) == 0
+        assert o.build_from_records(mass.view(np.float64), prot, self._prot_off(gpos, prot), length) == 0
         e = o.entries()
         self.local = [_bits(e["mass"]).view(np.int64), self._gpos(e["first_prot"], e["first_off"]).view(np.int32),
                       e["first_prot"].view(np.int32), e["len"].view(np.int16),
                       np.diff(e["prot_list_off"].astype(np.int64)).astype(np.int32), e["prot_ids"].view(np.int32)]
+        self._nu = len(self.local[0])
 
     def n_unique(self):
-        return len(self.local[0])
+        return self._nu
 
-    def export_unique(self):
-        return [torch.from_numpy(np.ascontiguousarray(self.local[1])), torch.from_numpy(np.ascontiguousarray(self.local[3]))]
-
-    def import_unique(self, rank_unique, tables):
-        # all a rank learns about foreign peptides: where their residues are
-        self.g_gpos, self.g_len = tables[0].numpy().view(np.uint32), tables[1].numpy().view(np.uint16)
-        self.uoff = int(sum(rank_unique[:self.rank]))
-        assert int(rank_unique[self.rank]) == self.n_unique()
+    def set_unique(self, rank_unique):
+        self.rank_unique = np.asarray(rank_unique, dtype=np.uint64)
+        assert int(rank_unique[self.rank]) == self._nu
+        self.uoff = int(sum(int(x) for x in rank_unique[:self.rank]))
 
     def finish(self):
-        self.e_mass = self.local[0].view(np.float64)
-        self.e_base = None  # entry i = own unique peptide i
-        self.e_pat = np.zeros(self.n_unique(), np.uint32)
+        if not self.has_mods:
+            self.e_mass = self.local[0].view(np.float64)
+            self.e_base = None  # entry i = own unique peptide i
+            self.e_pat = np.zeros(self._nu, np.uint32)
 
     def _variants(self, u):
         pr = int(self.local[2].view(np.uint32)[u])
@@ -114,22 +153,18 @@ class OracleShardEngine(ShardEngine):
         return pyref.expand_set(self.params, self._seq(pr, off, self.local[3].view(np.uint16)[u]),
                                 float(self.local[0].view(np.float64)[u]))
 
-    def own_tiles(self):
-        return 0, (self.n_unique() + 255) // 256
-
-    def expand(self, tile_begin, n_tiles):
-        U = self.n_unique()
+    def groups(self):
         keys, pay = [], []
-        for u in range(tile_begin * 256, min(U, (tile_begin + n_tiles) * 256)):
+        for u in range(self._nu):
             for m, pos in self._variants(u):
                 pat = sum((q + 1) << (8 * k) for k, q in enumerate(pos))
                 keys.append(int(np.float64(m).view(np.uint64)) - self.base_bits)
-                pay.append(((self.uoff + u) << 32) | pat)  # peptides travel under their global id
+                pay.append((u << 32) | pat)  # LOCAL row; the exchange adds the rank's offset
         self.var = [np.array(keys, dtype=np.uint64), np.array(pay, dtype=np.uint64)]
-        return len(keys)
+        return len(keys), len(keys)
 
-    def index_variants(self, key, payload):
-        key, payload = key.numpy().view(np.uint64), payload.numpy().view(np.uint64)
+    def index_variants(self):
+        key, payload = self.arena
         order = np.argsort(key, kind="stable")
         self.e_mass = (key[order] + np.uint64(self.base_bits)).view(np.float64)
         self.e_base = (payload[order] >> np.uint64(32)).astype(np.uint32)
@@ -137,7 +172,6 @@ class OracleShardEngine(ShardEngine):
 
     # ---- what a query sees (COLLECTIVE: base peptides of other ranks are looked up in their tables)
     def entries(self):
-        import torch.distributed as dist
         tabs = [None] * self.world
         dist.all_gather_object(tabs, [np.asarray(a) for a in self.local])
         u_gpos = np.concatenate([t[1].view(np.uint32) for t in tabs])

@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 
 import dbindex_b200 as dbi  # noqa: E402
 from dbindex_b200 import synth  # noqa: E402
-from dbindex_b200.multigpu import build_sharded, fetch_resolved, route_queries  # noqa: E402
+from dbindex_b200.multigpu import build_sharded, route_queries, shard_proteins  # noqa: E402
 from oracle.oracle_py import Oracle  # noqa: E402
 from tests.cpu_engine import OracleShardEngine  # noqa: E402
 from tests.util import PARAM_SETS, bits  # noqa: E402
@@ -27,7 +27,8 @@ class GpuEntries:
 
     def entries(self):
         n = self.g.stats()["n_entries"]
-        f = fetch_resolved(self.g, self.info, 0, n)  # collective: remote base peptides are resolved by their owners
+        f = self.g.fetch(0, n)  # base peptides of other ranks are read through their mapped windows
+        assert not np.any(f["first_prot"] == 0xFFFFFFFF), "a base peptide of another rank was not resolved"
         plo = f["prot_list_off"].astype(np.int64)
         f["plist"] = [tuple(f["prot_ids"][plo[i]:plo[i + 1]].tolist()) for i in range(n)]
         return f
@@ -62,7 +63,8 @@ def main():
         from dbindex_b200.multigpu import GpuShardEngine
         params.device = local
         g = dbi.GpuIndex(params)
-        g.add_proteins(res, off)
+        sres, soff, _ = shard_proteins(res, off, rank, world)  # a rank only ever sees its own shard of the FASTA
+        g.add_proteins(sres, soff)
         info = build_sharded(GpuShardEngine(g, torch.device("cuda", local)))
         eng = GpuEntries(g, info)
     else:
@@ -112,6 +114,9 @@ def main():
     if rank == 0:
         with open(out_path, "w") as f:
             json.dump({"ok": True, "counts": counts, "a2a_bytes": info["a2a_bytes"], "engine": engine_kind}, f)
+    if engine_kind == "gpu":
+        dist.barrier()  # nobody unmaps / frees its windows while another rank may still read them
+        g.close()
         print("dist_worker OK", name, engine_kind, "world", world, "entries per rank", counts, flush=True)
     dist.destroy_process_group()
 
