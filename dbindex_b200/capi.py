@@ -157,6 +157,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "dbi_query_device": (C.c_int, [vp, vp, vp, C.c_uint64, vp, vp]),
         "dbi_fetch": (C.c_int, [vp, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp, vp, vp, C.c_uint64, u64p]),
         "dbi_query_hits": (C.c_int, [vp, vp, vp, C.c_uint64, C.POINTER(DbiHitCounts)]),
+        "dbi_query_hits_device": (C.c_int, [vp, vp, vp, C.c_uint64, C.POINTER(DbiHitCounts)]),
         "dbi_query_hits_read": (C.c_int, [vp, C.POINTER(DbiHitBuffers)]),
         "dbi_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(vp)]),
         "dbi_host_free": (C.c_int, [vp]),
@@ -195,7 +196,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
 ABI_SYMBOLS = [
     "dbi_default_params", "dbi_params_add_static_mod", "dbi_params_set_enzyme", "dbi_params_add_diff_mod",
     "dbi_create", "dbi_set_stream", "dbi_add_proteins", "dbi_upload", "dbi_reset_index", "dbi_build",
-    "dbi_stats_get", "dbi_query", "dbi_query_device", "dbi_fetch", "dbi_query_hits", "dbi_query_hits_read",
+    "dbi_stats_get", "dbi_query", "dbi_query_device", "dbi_fetch", "dbi_query_hits", "dbi_query_hits_device", "dbi_query_hits_read",
     "dbi_host_alloc", "dbi_host_free", "dbi_get_protein", "dbi_calculate_mass",
     "dbi_entry_keys", "dbi_debug_emitted", "dbi_build_from_records", "dbi_debug_radix_sort", "dbi_destroy",
     "dbi_abi_sizes", "dbi_release_cached_memory",
@@ -209,12 +210,12 @@ ABI_SYMBOLS = [
 ]
 
 
-def default_params(mono: bool = True, **overrides) -> DbiParams:
+def default_params(mono: bool = True, _lib=None, **overrides) -> DbiParams:
     """dbi_default_params + keyword overrides.
 
     Extra keywords: enzyme="KR", nocut="", static_mods={"C": 57.02146},
     diff_mods=[("M", 15.9949), ("STY", 79.96633)], mandatory_internal="K", peptide_filter=("K", 2)."""
-    lib = load_library()
+    lib = _lib if _lib is not None else load_library()  # _lib: any library exporting the dbi_params_* helpers
     p = DbiParams()
     lib.dbi_default_params(C.byref(p), 1 if mono else 0)
     enzyme = overrides.pop("enzyme", None)
@@ -378,6 +379,23 @@ class GpuIndex:
                                        _ptr(out["prot_list_off"]), _ptr(ids), n_ids.value, C.byref(n_ids)))
         out["prot_ids"] = ids
         return out
+
+    def query_hits_begin(self, lo: np.ndarray, hi: np.ndarray) -> DbiHitCounts:
+        """dbi_query_hits alone (host bounds): the hits stay in HBM until query_hits_read / the next call."""
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        cnt = DbiHitCounts()
+        self._check(self.lib.dbi_query_hits(self._h, _ptr(lo), _ptr(hi), len(lo), C.byref(cnt)))
+        return cnt
+
+    def query_hits_device(self, d_lo: int, d_hi: int, nq: int) -> DbiHitCounts:
+        """dbi_query_hits_device: bounds resident in HBM; the hits stay in HBM until query_hits_read / the next call."""
+        cnt = DbiHitCounts()
+        self._check(self.lib.dbi_query_hits_device(self._h, C.c_void_p(d_lo), C.c_void_p(d_hi), nq, C.byref(cnt)))
+        return cnt
+
+    def query_hits_read(self, bufs: "DbiHitBuffers"):
+        self._check(self.lib.dbi_query_hits_read(self._h, C.byref(bufs)))
 
     def query_hits(self, lo: np.ndarray, hi: np.ndarray, fields=None, alloc=None) -> dict:
         """dbi_query_hits + dbi_query_hits_read: every hit of every [lo[i], hi[i]] materialised (mass, first

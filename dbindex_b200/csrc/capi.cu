@@ -1410,16 +1410,11 @@ int dbi_fetch(dbi_handle* h, uint64_t begin, uint64_t count, double* mass, uint3
   DBI_API_END
 }
 
-int dbi_query_hits(dbi_handle* h, const double* lo, const double* hi, uint64_t nq, dbi_hit_counts* counts) {
-  DBI_API_BEGIN(h)
-  if (!h->built) {
-    set_error("Indexer is not initialized");
-    return DBI_ENOTINIT;
-  }
-  if (!counts || (nq && (!lo || !hi))) {
-    set_error("null argument");
-    return DBI_EINVAL;
-  }
+}  // extern "C"
+
+namespace {
+// dbi_query_hits with the bounds already on the device
+int query_hits_impl(dbi_handle* h, const double* d_lo, const double* d_hi, uint64_t nq, dbi_hit_counts* counts) {
   cudaStream_t s = h->stream;
   dbi_handle::HitResult& r = h->hits;
   r.drop();
@@ -1434,15 +1429,11 @@ int dbi_query_hits(dbi_handle* h, const double* lo, const double* hi, uint64_t n
     return DBI_OK;
   }
   DevBuf io, cnt32, stmp, hit_entry, len32, np32, stmp2;
-  io.alloc(nq * 32, h->arena);  // lo | hi | begin | count
-  double* d_lo = io.as<double>();
-  double* d_hi = d_lo + nq;
-  uint64_t* d_b = (uint64_t*)(d_hi + nq);
+  io.alloc(nq * 16, h->arena);  // begin | count
+  uint64_t* d_b = io.as<uint64_t>();
   uint64_t* d_c = d_b + nq;
   cnt32.alloc(nq * 4, h->arena);
   stmp.alloc(full_scan_tmp_bytes(nq), h->arena);
-  DBI_CUDA(cudaMemcpyAsync(d_lo, lo, nq * 8, cudaMemcpyHostToDevice, s));
-  DBI_CUDA(cudaMemcpyAsync(d_hi, hi, nq * 8, cudaMemcpyHostToDevice, s));
   uint64_t H = 0;
   {
     Stage sg(h, DBI_STAGE_QUERY);
@@ -1500,6 +1491,42 @@ int dbi_query_hits(dbi_handle* h, const double* lo, const double* hi, uint64_t n
   r.n = *counts;
   r.valid = true;
   return DBI_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int dbi_query_hits(dbi_handle* h, const double* lo, const double* hi, uint64_t nq, dbi_hit_counts* counts) {
+  DBI_API_BEGIN(h)
+  if (!h->built) {
+    set_error("Indexer is not initialized");
+    return DBI_ENOTINIT;
+  }
+  if (!counts || (nq && (!lo || !hi))) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  DevBuf io;  // lo | hi
+  io.alloc(std::max<uint64_t>(nq, 1) * 16, h->arena);
+  if (nq) {
+    DBI_CUDA(cudaMemcpyAsync(io.p, lo, nq * 8, cudaMemcpyHostToDevice, h->stream));
+    DBI_CUDA(cudaMemcpyAsync(io.as<double>() + nq, hi, nq * 8, cudaMemcpyHostToDevice, h->stream));
+  }
+  return query_hits_impl(h, io.as<double>(), io.as<double>() + nq, nq, counts);
+  DBI_API_END
+}
+
+int dbi_query_hits_device(dbi_handle* h, const double* d_lo, const double* d_hi, uint64_t nq, dbi_hit_counts* counts) {
+  DBI_API_BEGIN(h)
+  if (!h->built) {
+    set_error("Indexer is not initialized");
+    return DBI_ENOTINIT;
+  }
+  if (!counts || (nq && (!d_lo || !d_hi))) {
+    set_error("null argument");
+    return DBI_EINVAL;
+  }
+  return query_hits_impl(h, d_lo, d_hi, nq, counts);
   DBI_API_END
 }
 

@@ -390,6 +390,7 @@ int dbi_mg_hist(dbi_handle* h, int stage, void* d_hist, int* shift) {
                    kGrpCntMask, (unsigned long long*)d_hist, h->stream);
   }
   if (shift) *shift = sh;
+  DBI_CUDA(cudaStreamSynchronize(h->stream));  // the caller reduces d_hist on ITS stream next
   return DBI_OK;
   DBI_API_END
 }

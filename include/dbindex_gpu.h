@@ -261,6 +261,8 @@ typedef struct dbi_hit_buffers {
   uint32_t* prot_ids;      /* n_prot_ids  */
 } dbi_hit_buffers;
 int dbi_query_hits(dbi_handle* h, const double* lo, const double* hi, uint64_t nq, dbi_hit_counts* counts);
+/* same with the bounds already in device memory of the handle's GPU */
+int dbi_query_hits_device(dbi_handle* h, const double* d_lo, const double* d_hi, uint64_t nq, dbi_hit_counts* counts);
 int dbi_query_hits_read(dbi_handle* h, const dbi_hit_buffers* out);
 
 /* Page-locked host memory for the buffers above (cudaHostAlloc / cudaFreeHost); a JVM cannot pin

@@ -61,6 +61,24 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def default_params(mono: bool = True, **overrides):
+    """dbi_params for the oracle WITHOUT touching the product library: liboracle.so carries its own
+    copy of the host-only parameter helpers (csrc/params.cpp); only the struct definition (pure Python)
+    comes from dbindex_b200.capi.  bench.py --impl reference uses this."""
+    from dbindex_b200.capi import DbiParams, default_params as _dp
+    lib = load()
+    pp = C.POINTER(DbiParams)
+    lib.dbi_default_params.restype = None
+    lib.dbi_default_params.argtypes = [pp, C.c_int]
+    lib.dbi_params_add_static_mod.restype = None
+    lib.dbi_params_add_static_mod.argtypes = [pp, C.c_uint8, C.c_double]
+    lib.dbi_params_set_enzyme.restype = None
+    lib.dbi_params_set_enzyme.argtypes = [pp, C.c_char_p, C.c_char_p]
+    lib.dbi_params_add_diff_mod.restype = C.c_int
+    lib.dbi_params_add_diff_mod.argtypes = [pp, C.c_char_p, C.c_double]
+    return _dp(mono, _lib=lib, **overrides)
+
+
 class Oracle:
     """CPU restatement of the reference path (see dbindex_oracle.cpp)."""
 
