@@ -74,60 +74,118 @@ __global__ void __launch_bounds__(Q_THREADS)
   }
 }
 
-// K10b: one thread per hit
+// K10b: a CTA materialises HG_TILE consecutive hits.  Per-hit scalars are gathered by one thread per hit
+// (random reads of the owner tables, coalesced writes); the peptide residues and the flanks, whose
+// output regions are contiguous for consecutive hits, are written by the whole CTA in 16-byte chunks:
+// a thread finds the hit its chunk starts in (binary search over the tile's offsets in shared memory),
+// then walks the residues of that hit and its successors.
+constexpr int HG_TILE = Q_THREADS;
+
 __global__ void __launch_bounds__(Q_THREADS)
     hits_gather_kernel(const uint8_t* __restrict__ res, const uint32_t* __restrict__ pstart,
                        const double* __restrict__ e_mass, const uint32_t* __restrict__ e_base, uint64_t ent_off,
                        const uint32_t* __restrict__ e_pat, const __grid_constant__ UniqView uv,
-                       const uint32_t* __restrict__ hit_entry,
-                       const uint64_t* __restrict__ seq_off, const uint64_t* __restrict__ plo_out, uint64_t n_hits,
-                       double* __restrict__ o_mass, uint32_t* __restrict__ o_prot, uint32_t* __restrict__ o_off,
-                       uint16_t* __restrict__ o_len, uint32_t* __restrict__ o_pat, uint8_t* __restrict__ o_flanks,
-                       uint8_t* __restrict__ o_seq, uint32_t* __restrict__ o_ids) {
-  const uint64_t h = (uint64_t)blockIdx.x * Q_THREADS + threadIdx.x;
-  if (h >= n_hits) return;
-  const uint64_t e = hit_entry[h];
-  const uint64_t gid = e_base ? (uint64_t)e_base[e] : ent_off + e;
-  uint64_t row;
-  const int r = uniq_owner(uv, gid, &row);
-  if (o_mass) o_mass[h] = e_mass[e];
-  if (o_pat) o_pat[h] = e_pat ? e_pat[e] : 0u;
-  if (!uv.len[r]) {  // the owner's tables are not mapped: the caller resolves the peptide through its owner
-    if (o_prot) o_prot[h] = DBI_REMOTE_BASE;
-    if (o_off) o_off[h] = (uint32_t)gid;
-    if (o_len) o_len[h] = 0;
-    if (o_flanks)
-      for (int k = 0; k < 6; ++k) o_flanks[6 * h + k] = '-';
-    return;
+                       const uint32_t* __restrict__ hit_entry, const uint64_t* __restrict__ seq_off,
+                       const uint64_t* __restrict__ plo_out, uint64_t n_hits, double* __restrict__ o_mass,
+                       uint32_t* __restrict__ o_prot, uint32_t* __restrict__ o_off, uint16_t* __restrict__ o_len,
+                       uint32_t* __restrict__ o_pat, uint8_t* __restrict__ o_flanks, uint8_t* __restrict__ o_seq,
+                       uint32_t* __restrict__ o_ids) {
+  __shared__ uint32_t s_gpos[HG_TILE];
+  __shared__ uint32_t s_soff[HG_TILE + 1];  // seq offsets relative to the tile's first byte
+  __shared__ __align__(16) uint8_t s_fl[HG_TILE * 6 + 16];
+  const int t = threadIdx.x;
+  const uint64_t h0 = (uint64_t)blockIdx.x * HG_TILE;
+  const uint32_t tile_n = (uint32_t)min((uint64_t)HG_TILE, n_hits - h0);
+  const uint64_t h = h0 + t;
+  const uint64_t seq0 = seq_off[h0];
+  if (t == 0) s_soff[tile_n] = (uint32_t)(seq_off[h0 + tile_n] - seq0);
+  if ((uint32_t)t < tile_n) {
+    const uint64_t e = hit_entry[h];
+    const uint64_t gid = e_base ? (uint64_t)e_base[e] : ent_off + e;
+    uint64_t row;
+    const int r = uniq_owner(uv, gid, &row);
+    if (o_mass) o_mass[h] = e_mass[e];
+    if (o_pat) o_pat[h] = e_pat ? e_pat[e] : 0u;
+    s_soff[t] = (uint32_t)(seq_off[h] - seq0);
+    uint8_t* f = s_fl + 6 * t;
+    if (!uv.len[r]) {  // the owner's tables are not mapped: the caller resolves the peptide through its owner
+      if (o_prot) o_prot[h] = DBI_REMOTE_BASE;
+      if (o_off) o_off[h] = (uint32_t)gid;
+      if (o_len) o_len[h] = 0;
+      s_gpos[t] = 0;
+      for (int k = 0; k < 6; ++k) f[k] = '-';
+    } else {
+      const uint32_t gp = uv.gpos[r][row], pr = uv.prot[r][row], len = uv.len[r][row];
+      s_gpos[t] = gp;
+      if (o_prot) o_prot[h] = pr;
+      if (o_off) o_off[h] = gp - pstart[pr];  // sequenceOffset inside the first protein
+      if (o_len) o_len[h] = (uint16_t)len;
+      // Util.getResidues (Util.java:130-162): up to 3 residues on the left, '-' padded on the left; on
+      // the right min(3, protLen - end - 1) residues -- the reference's off-by-one drops the last
+      // residue of the protein from the right flank -- '-' padded on the right.
+      const uint8_t l2 = ld_res(res, gp - 1);
+      const uint8_t l1 = l2 ? ld_res(res, gp - 2) : (uint8_t)0;
+      const uint8_t l0 = l1 ? ld_res(res, gp - 3) : (uint8_t)0;
+      f[0] = l0 ? l0 : (uint8_t)'-';
+      f[1] = l1 ? l1 : (uint8_t)'-';
+      f[2] = l2 ? l2 : (uint8_t)'-';
+      const uint32_t endp = gp + len;  // first position after the peptide
+      uint8_t rr[4];
+      uint32_t remaining = 0;          // residues after the peptide, up to 4
+      while (remaining < 4 && (rr[remaining] = ld_res(res, endp + remaining)) != 0) ++remaining;
+      const uint32_t rl = remaining > 0 ? min(3u, remaining - 1u) : 0u;
+      for (uint32_t k = 0; k < 3; ++k) f[3 + k] = k < rl ? rr[k] : (uint8_t)'-';
+      if (o_ids) {  // every occurrence's protein id, insertion order (Merge:449-475)
+        const uint64_t src = uv.plo[r][row], n = uv.plo[r][row + 1] - src, dst = plo_out[h];
+        for (uint64_t k = 0; k < n; ++k) o_ids[dst + k] = uv.plist[r][src + k];
+      }
+    }
   }
-  const uint32_t gp = uv.gpos[r][row], pr = uv.prot[r][row], len = uv.len[r][row];
-  if (o_prot) o_prot[h] = pr;
-  if (o_off) o_off[h] = gp - pstart[pr];  // sequenceOffset inside the first protein
-  if (o_len) o_len[h] = (uint16_t)len;
-  if (o_seq) {  // ProteinCache.getPeptideSequence: protSeq.substring(off, off + len)
-    uint8_t* d = o_seq + seq_off[h];
-    for (uint32_t k = 0; k < len; ++k) d[k] = ld_res(res, gp + k);
+  __syncthreads();
+  if (o_flanks) {  // 6 bytes per hit, contiguous over the tile
+    uint8_t* dst = o_flanks + 6 * h0;
+    const uint32_t nb = 6 * tile_n;
+    for (uint32_t i = t; i < nb; i += Q_THREADS) dst[i] = s_fl[i];
   }
-  if (o_flanks) {
-    // Util.getResidues (Util.java:130-162): up to 3 residues on the left, '-' padded on the left; on
-    // the right min(3, protLen - end - 1) residues -- the reference's off-by-one drops the last
-    // residue of the protein from the right flank -- '-' padded on the right.
-    uint8_t* f = o_flanks + 6 * h;
-    uint8_t l2 = ld_res(res, gp - 1);
-    uint8_t l1 = l2 ? ld_res(res, gp - 2) : (uint8_t)0;
-    uint8_t l0 = l1 ? ld_res(res, gp - 3) : (uint8_t)0;
-    f[0] = l0 ? l0 : (uint8_t)'-';
-    f[1] = l1 ? l1 : (uint8_t)'-';
-    f[2] = l2 ? l2 : (uint8_t)'-';
-    const uint32_t endp = gp + len;  // first position after the peptide
-    uint32_t remaining = 0;          // residues after the peptide, up to 4
-    while (remaining < 4 && ld_res(res, endp + remaining) != 0) ++remaining;
-    const uint32_t rl = remaining > 0 ? min(3u, remaining - 1u) : 0u;
-    for (uint32_t k = 0; k < 3; ++k) f[3 + k] = k < rl ? ld_res(res, endp + k) : (uint8_t)'-';
+  if (!o_seq) return;
+  // ProteinCache.getPeptideSequence for the whole tile: bytes [seq0, seq0 + total) of o_seq
+  const uint32_t total = s_soff[tile_n];
+  uint8_t* out = o_seq + seq0;
+  const uint32_t head = min(total, (uint32_t)((16 - ((uintptr_t)out & 15)) & 15));  // bytes before the first aligned chunk
+  auto hit_of = [&](uint32_t p) {  // last hit with s_soff <= p
+    uint32_t lo = 0, hi = tile_n;
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (s_soff[mid] <= p) lo = mid; else hi = mid;
+    }
+    return lo;
+  };
+  if ((uint32_t)t < head) {
+    const uint32_t i = hit_of((uint32_t)t);
+    out[t] = ld_res(res, s_gpos[i] + ((uint32_t)t - s_soff[i]));
   }
-  if (o_ids) {  // every occurrence's protein id, insertion order (Merge:449-475)
-    const uint64_t src = uv.plo[r][row], n = uv.plo[r][row + 1] - src, dst = plo_out[h];
-    for (uint64_t k = 0; k < n; ++k) o_ids[dst + k] = uv.plist[r][src + k];
+  const uint32_t n_chunks = (total - head + 15) / 16;
+  for (uint32_t c = t; c < n_chunks; c += Q_THREADS) {
+    const uint32_t p0 = head + c * 16;
+    uint32_t i = hit_of(p0);
+    uint32_t nxt = s_soff[i + 1];
+    uint32_t src = s_gpos[i] + (p0 - s_soff[i]);
+    uint32_t w[4] = {0, 0, 0, 0};
+    const uint32_t nbytes = min(16u, total - p0);
+    for (uint32_t b = 0; b < nbytes; ++b) {
+      uint32_t p = p0 + b;
+      while (p >= nxt) {  // next hit (empty sequences are skipped)
+        ++i;
+        nxt = s_soff[i + 1];
+        src = s_gpos[i];
+      }
+      w[b >> 2] |= (uint32_t)ld_res(res, src++) << (8 * (b & 3));
+    }
+    if (nbytes == 16) {
+      *reinterpret_cast<uint4*>(out + p0) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+      for (uint32_t b = 0; b < nbytes; ++b) out[p0 + b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+    }
   }
 }
 
