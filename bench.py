@@ -623,7 +623,7 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
     g.add_proteins(sres, soff)
     g.upload()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    nq = args.queries * world
+    nq = args.queries  # ONE batch for the whole index: hits per query grow with the index, so per-GPU work stays fixed
     info = build_sharded(GpuShardEngine(g, dev))  # also warms NCCL and the window mappings up
     masses = sample_index_masses(g, g.stats()["n_entries"])
     # every rank contributes samples of its own slice so that the queries cover the whole range
@@ -749,6 +749,8 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
             "gpu_launches": int(launches_all),
             "clocks": clk,
             "host_stage_ms_rank0_last_step": {k: round(v, 3) for k, v in info["t"].items()},
+            "device_stage_ms_rank0_last_step": {k: round(v, 3) for k, v in st["stage_ms"].items() if v > 0},
+            "entries_rank0": int(n_entries),
         }
         print(json.dumps(line), flush=True)
     barrier()

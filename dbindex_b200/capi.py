@@ -153,6 +153,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "dbi_reset_index": (C.c_int, [vp]),
         "dbi_build": (C.c_int, [vp]),
         "dbi_stats_get": (C.c_int, [vp, C.POINTER(DbiStats)]),
+        "dbi_save": (C.c_int, [vp, C.c_char_p]),
+        "dbi_load": (C.c_int, [vp, C.c_char_p]),
         "dbi_query": (C.c_int, [vp, vp, vp, C.c_uint64, vp, vp]),
         "dbi_query_device": (C.c_int, [vp, vp, vp, C.c_uint64, vp, vp]),
         "dbi_fetch": (C.c_int, [vp, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp, vp, vp, C.c_uint64, u64p]),
@@ -196,7 +198,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
 ABI_SYMBOLS = [
     "dbi_default_params", "dbi_params_add_static_mod", "dbi_params_set_enzyme", "dbi_params_add_diff_mod",
     "dbi_create", "dbi_set_stream", "dbi_add_proteins", "dbi_upload", "dbi_reset_index", "dbi_build",
-    "dbi_stats_get", "dbi_query", "dbi_query_device", "dbi_fetch", "dbi_query_hits", "dbi_query_hits_device", "dbi_query_hits_read",
+    "dbi_stats_get", "dbi_save", "dbi_load", "dbi_query", "dbi_query_device", "dbi_fetch", "dbi_query_hits", "dbi_query_hits_device", "dbi_query_hits_read",
     "dbi_host_alloc", "dbi_host_free", "dbi_get_protein", "dbi_calculate_mass",
     "dbi_entry_keys", "dbi_debug_emitted", "dbi_build_from_records", "dbi_debug_radix_sort", "dbi_destroy",
     "dbi_abi_sizes", "dbi_release_cached_memory",
@@ -332,6 +334,12 @@ class GpuIndex:
         off = np.ascontiguousarray(off, dtype=np.uint32)
         length = np.ascontiguousarray(length, dtype=np.uint16)
         self._check(self.lib.dbi_build_from_records(self._h, _ptr(mass), _ptr(prot), _ptr(off), _ptr(length), len(mass)))
+
+    def save(self, path: str):
+        self._check(self.lib.dbi_save(self._h, os.fsencode(path)))
+
+    def load(self, path: str):
+        self._check(self.lib.dbi_load(self._h, os.fsencode(path)))
 
     def stats(self) -> dict:
         st = DbiStats()

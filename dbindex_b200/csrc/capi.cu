@@ -8,6 +8,8 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <stdexcept>
+#include <string>
 #include <vector>
 
 #include "kernels.cuh"
@@ -1761,3 +1763,4 @@ uint64_t dbi_kernel_launches(void) { return g_kernel_launches.load(); }
 }  // extern "C"
 
 #include "capi_mg.inl"
+#include "capi_persist.inl"

@@ -382,12 +382,13 @@ int dbi_mg_hist(dbi_handle* h, int stage, void* d_hist, int* shift) {
   const KeySpace ks(h->p.min_mass, h->p.max_mass);
   const int sh = mg_shift(ks);
   if (stage == 0) {
-    launch_mg_hist(h->mg_mass.as<uint64_t>(), h->mg_n, ks.base_bits, sh, nullptr, 0, (unsigned long long*)d_hist,
+    launch_mg_hist(h->mg_mass.as<uint64_t>(), h->mg_n, ks.base_bits, sh, nullptr, 0, 0u, (unsigned long long*)d_hist,
                    h->stream);
   } else {  // group records: weigh by their variant count
     const bool weighted = h->cfg.n_seq > 0;
+    // a group costs its entries (expansion) plus a constant (7 sort passes, staging): measured ~5 entries' worth
     launch_mg_hist(h->mg_vkey.as<uint64_t>(), h->mg_v, 0, sh, weighted ? h->mg_vpay.as<uint64_t>() : nullptr,
-                   kGrpCntMask, (unsigned long long*)d_hist, h->stream);
+                   kGrpCntMask, weighted ? 5u : 0u, (unsigned long long*)d_hist, h->stream);
   }
   if (shift) *shift = sh;
   DBI_CUDA(cudaStreamSynchronize(h->stream));  // the caller reduces d_hist on ITS stream next
@@ -598,6 +599,7 @@ int dbi_mg_groups(dbi_handle* h, uint64_t* n_items, uint64_t* n_variants) {
 
 int dbi_mg_index_variants(dbi_handle* h) {
   DBI_API_BEGIN(h)
+  TR("begin");
   const uint64_t n = h->mg_recv[1];
   const KeySpace ks(h->p.min_mass, h->p.max_mass);
   const int C = mg_side_classes(h);
@@ -616,6 +618,8 @@ int dbi_mg_index_variants(dbi_handle* h) {
   }
   if (rc == DBI_OK) rc = check_err_bits(read_err(h));
   DBI_CUDA(cudaStreamSynchronize(h->stream));
+  TR("final_sync");
+  g_trace.dump();
   return rc;
   DBI_API_END
 }

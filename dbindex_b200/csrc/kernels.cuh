@@ -185,10 +185,10 @@ void launch_key_emit(const double* e_mass, uint64_t n, double factor, const uint
 // ---- multi-GPU exchange helpers (mg.cu) -----------------------------------------------------
 constexpr int kMgBins = 4096;  // histogram bins over the top bits of the radix key
 // hist[0 .. kMgBins) += weight, hist[kMgBins .. 2 kMgBins) += 1 over min(kMgBins-1, (key[i] - sub) >> shift)
-// (hist is zeroed by the caller); weight of item i = wpay ? (wpay[i] & wmask) : 1 (group records
-// carry their variant count).
+// (hist is zeroed by the caller); weight of item i = wpay ? (wpay[i] & wmask) + wadd : 1 (group records
+// carry their variant count; wadd = the per-group cost in entries).
 void launch_mg_hist(const uint64_t* key, uint64_t n, uint64_t sub, int shift, const uint64_t* wpay, uint64_t wmask,
-                    unsigned long long* hist, cudaStream_t s);
+                    uint32_t wadd, unsigned long long* hist, cudaStream_t s);
 // Where the items of one exchange go.  dest(item) = number of thresholds <= (key - sub); this rank's
 // items for destination d arrive at rows row0[d] .. of d's arrays (after the items of the lower ranks).
 struct MgPlan {

@@ -20,7 +20,8 @@ constexpr int MG_THREADS = 256;
 // and receive.  64-bit bins in shared memory: a group can stand for 2^27 variants.
 __global__ void __launch_bounds__(MG_THREADS)
     mg_hist_kernel(const uint64_t* __restrict__ key, uint64_t n, uint64_t sub, int shift,
-                   const uint64_t* __restrict__ wpay, uint64_t wmask, unsigned long long* __restrict__ hist) {
+                   const uint64_t* __restrict__ wpay, uint64_t wmask, uint32_t wadd,
+                   unsigned long long* __restrict__ hist) {
   extern __shared__ __align__(16) unsigned long long sh_w[];  // [kMgBins] weighted, then u32 [kMgBins] plain
   uint32_t* sh_c = reinterpret_cast<uint32_t*>(sh_w + kMgBins);
   for (int i = threadIdx.x; i < kMgBins; i += MG_THREADS) {
@@ -33,7 +34,7 @@ __global__ void __launch_bounds__(MG_THREADS)
     uint64_t b = (key[i] - sub) >> shift;
     if (b >= kMgBins) b = kMgBins - 1;
     atomicAdd(&sh_c[b], 1u);
-    atomicAdd(&sh_w[b], wpay ? (unsigned long long)(wpay[i] & wmask) : 1ull);
+    atomicAdd(&sh_w[b], wpay ? (unsigned long long)(wpay[i] & wmask) + wadd : 1ull);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < kMgBins; i += MG_THREADS) {
@@ -280,13 +281,13 @@ __global__ void __launch_bounds__(MG_THREADS)
 }  // namespace
 
 void launch_mg_hist(const uint64_t* key, uint64_t n, uint64_t sub, int shift, const uint64_t* wpay, uint64_t wmask,
-                    unsigned long long* hist, cudaStream_t s) {
+                    uint32_t wadd, unsigned long long* hist, cudaStream_t s) {
   if (n == 0) return;
   uint64_t g = (n + MG_THREADS * 8 - 1) / (MG_THREADS * 8);
   if (g > (uint64_t)kNumSMsB200 * 4) g = (uint64_t)kNumSMsB200 * 4;
   const size_t smem = (size_t)kMgBins * 12;
   DBI_CUDA(cudaFuncSetAttribute(mg_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  DBI_LAUNCH(mg_hist_kernel, (unsigned)g, MG_THREADS, smem, s, key, n, sub, shift, wpay, wmask, hist);
+  DBI_LAUNCH(mg_hist_kernel, (unsigned)g, MG_THREADS, smem, s, key, n, sub, shift, wpay, wmask, wadd, hist);
 }
 
 size_t mg_scatter_tmp_bytes(uint64_t n) {

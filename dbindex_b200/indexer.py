@@ -140,6 +140,7 @@ class DBIndexSearchParams:
     useMonoParent: bool = False
     mandatoryInternalAAs: Optional[str] = None
     discardDecoyRegexp: Optional[str] = None
+    staticParams: str = ""         # SearchParams.getStaticParams(): text of the static mods, part of the index name
 
     def key(self) -> str:
         """What getByParam keys its registry on (DBIndexImpl.java:44-49: the full index file name, i.e.
@@ -198,12 +199,62 @@ def getDefaultDBIndexParamsForProteoformAnalysis(*args, **kwargs):
     raise DBIndexerException("proteoform analysis needs the UniProt annotation service; out of scope of the GPU index")
 
 
+def createFullIndexFileName(sparam: "DBIndexSearchParams") -> str:
+    """IndexUtil.createFullIndexFileName (util/IndexUtil.java:242-324): <database>_<md5 of the parameters that
+    shape the index>, the same fields in the same order and spelling.  Two things cannot be reproduced
+    byte for byte and are documented deviations: the reference appends `char[].toString()` of
+    mandatoryInternalAAs (a JVM identity hash, different on every run) -- the characters themselves are used
+    here -- and it knows no differential mods: they are appended only when present, so indexes without them
+    keep the reference's key."""
+    import hashlib
+    p = sparam.params
+
+    def jbool(b):
+        return "true" if b else "false"
+
+    def jdouble(x):  # Double.toString for the magnitudes that occur here
+        return repr(float(x))
+
+    enz = "".join(chr(i) for i in range(256) if p.is_enzyme[i])
+    nocut = "".join(chr(i) for i in range(256) if p.is_nocut[i])
+    u = "enzymeOffset:%d" % sparam.enzymeOffset
+    u += ", enzymeResidues:" + enz
+    u += ", enzymeNoCutResidues:" + nocut
+    u += ", maxCleavages:%d" % p.max_missed
+    u += ", minPrecursorMass:" + jdouble(p.min_mass)
+    u += ", maxPrecursorMass:" + jdouble(p.max_mass)
+    u += ", static:" + sparam.staticParams
+    u += ", semiCleave:" + jbool(p.semi)
+    if p.filter_aa > 0:
+        u += ", pepFilter:%s%d" % (chr(p.filter_aa), p.filter_max)  # PeptideFilterByMaxOccurrencies.toString
+    u += ", isH2OPlusProtonAdded:" + jbool(p.add_h2o_proton)
+    u += ", massGroupFactor:%d" % p.mass_group_factor
+    u += ", massType:" + jbool(sparam.useMonoParent)
+    if p.has_mandatory:
+        u += ", mandatoryInternalAAs:" + "".join(chr(i) for i in range(256) if p.is_mandatory[i])
+    u += ", proteoForms:false, maxVariationsPerPeptide:null, useUniprot:false, uniprotVersion:null"
+    u += ", usePhosphoSite:false, phosphoSiteSpecies:null, sufix:null"
+    u += ", discardDecoys:" + ("null" if sparam.discardDecoyRegexp is None else sparam.discardDecoyRegexp)
+    if p.n_mods > 0 and p.max_mods_per_peptide > 0:
+        u += ", diffMods:" + ",".join("%s%r" % (chr(p.mods[i].residue), p.mods[i].delta) for i in range(p.n_mods))
+        u += ", maxDiffMods:%d" % p.max_mods_per_peptide
+    return sparam.dataBaseName + "_" + hashlib.md5(u.encode("utf-8")).hexdigest()
+
+
+INDEX_FILE_SUFFIX = ".gpuidx"  # the reference's directory is <name>.idx (DBIndexer.java:63,429-431)
+
+
 class DBIndexer:
     """DBIndexer.java: the indexer / orchestrator, GPU store behind it."""
 
-    def __init__(self, params: DbiParams, index_factor: int = 8):
+    def __init__(self, params: DbiParams, index_factor: int = 8, index_path: Optional[str] = None):
+        """index_path: where the finished index lives on disk (None = in-memory index only).  run() skips
+        indexing when the file exists ("Found existing index, skipping indexing", DBIndexer.java:522-531)
+        and writes it after a fresh build."""
         self.sparam = params
         self.index_factor = index_factor  # dbindex.properties:6; only shapes the ">= MAX_MASS" query rule
+        self.index_path = index_path
+        self.loaded_from_disk = False
         self.inited = False
         self.index: Optional[GpuIndex] = None
         self.deflines: List[str] = []   # ProteinCache.defs
@@ -229,6 +280,19 @@ class DBIndexer:
     def run(self, fasta: Optional[str] = None, proteins: Optional[Tuple[Sequence[str], Sequence[str]]] = None):
         """DBIndexer.run(): stream the FASTA, cut every protein, close the store."""
         self._require()
+        if self.index_path is not None and os.path.exists(self.index_path):
+            # indexStore.indexExists() -> "Found existing index, skipping indexing" (DBIndexer.java:522-531)
+            try:
+                self.index.load(self.index_path)
+            except DbiError as e:
+                raise DBIndexerException(str(e)) from e
+            self.loaded_from_disk = True
+            # the deflines (ProteinCache.defs) are not part of the index file: re-read them when a FASTA is at hand
+            if fasta is not None:
+                self.deflines = [d.replace("\t", " ") for d in read_fasta(fasta)[0]]
+            elif proteins is not None:
+                self.deflines = [d.replace("\t", " ") for d in proteins[0]]
+            return
         if fasta is not None:
             deflines, residues, offsets = read_fasta(fasta)
             self.add_proteins(deflines, residues, offsets)
@@ -240,6 +304,8 @@ class DBIndexer:
             self.add_proteins(deflines, residues, offsets)
         try:
             self.index.build()  # cutSeq per protein + stopAddSeq (DBIndexer.java:616,666)
+            if self.index_path is not None:
+                self.index.save(self.index_path)
         except DbiError as e:
             raise DBIndexerException(str(e)) from e
 
@@ -386,7 +452,11 @@ class DBIndexImpl:
                 fasta = self.sparam.dataBaseName
             index_factor = self.sparam.indexFactor
             params = self.sparam.params
-        self.indexer = DBIndexer(params, index_factor)
+        index_path = None
+        if self.sparam is not None and not self.sparam.inMemoryIndex:
+            # an on-disk index, named like the reference's (DBIndexer.java:429 createFullIndexFileName)
+            index_path = createFullIndexFileName(self.sparam) + INDEX_FILE_SUFFIX
+        self.indexer = DBIndexer(params, index_factor, index_path=index_path)
         self.indexer.init()
         self.indexer.run(fasta=fasta, proteins=proteins)
         self._proteins_by_seq: dict = {}  # DBIndexImpl.java:33

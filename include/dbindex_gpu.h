@@ -201,6 +201,15 @@ int dbi_reset_index(dbi_handle* h);
  * merge equal peptides, expand differential mods, sort the variants. */
 int dbi_build(dbi_handle* h);
 
+/* Index persistence / resume.  The reference keeps its index on disk under
+ * <fasta>_<md5(params)> (util/IndexUtil.java:270-324) and skips indexing when it finds one
+ * (DBIndexer.java:522-531).  dbi_save writes the proteins and the finished index of a single-GPU
+ * handle to `path` (atomically: temp file + rename); dbi_load restores both into a FRESH handle created
+ * with the same search parameters (anything else is DBI_EINVAL) -- afterwards the handle answers queries
+ * exactly like the one that was saved.  The file name is the host's business. */
+int dbi_save(dbi_handle* h, const char* path);
+int dbi_load(dbi_handle* h, const char* path);
+
 /* getNumberSequences() and friends. */
 int dbi_stats_get(dbi_handle* h, dbi_stats* out);
 

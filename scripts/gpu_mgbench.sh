@@ -5,8 +5,8 @@ mkdir -p gpurun_out
 timeout -k 10 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps $K --warmup 3 > gpurun_out/bench_mg$N.json 2> gpurun_out/bench_mg$N.err; echo "bench rc=$?"; tail -5 gpurun_out/bench_mg$N.err
 python - <<PY
 import json
-d=json.load(open('gpurun_out/bench_mg$N.json'))
+d=json.loads([l for l in open('gpurun_out/bench_mg$N.json') if l.startswith('{')][-1])
 print({k:d[k] for k in ['value','ms_per_step','n_gpus']}); print('e2e', d['e2e']['value'], d['e2e']['ms_per_step']); print('a2a', d['all_to_all']); print('parity', d['parity']); print('queries', d['queries'])
-print('stages', d['host_stage_ms_rank0_last_step'])
+print('stages', d['host_stage_ms_rank0_last_step']); print('device', d['device_stage_ms_rank0_last_step'], d['entries_rank0'])
 r=d['roofline']; print(r['kernel'], round(r['frac'],3), round(r['avg_launch_ms'],4))
 PY

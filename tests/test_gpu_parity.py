@@ -266,6 +266,68 @@ def test_reference_api_mirror():
         d.getSequencesUsingDaltonTolerance(1000.0, 1.0)  # "Indexer is not initialized"
 
 
+@pytest.mark.parametrize("name", ["cfg1_tryptic", "cfg2_mods", "many_classes"])
+def test_save_load_roundtrip(name, tmp_path):
+    """dbi_save / dbi_load -- a fresh handle that loads the file answers exactly like the one
+    that built the index (entries, protein lists, queries, materialised hits, proteins), and other search
+    parameters are refused."""
+    p = dbi.default_params(**PARAM_SETS[name])
+    res, off = synth.synth_proteome(300, 99, median_len=200, min_len=5)
+    g, o = both(p, res, off, keep=False)
+    path = str(tmp_path / "index.gpuidx")
+    try:
+        g.save(path)
+        g2 = dbi.GpuIndex(p)
+        try:
+            g2.load(path)
+            st, st2 = g.stats(), g2.stats()
+            for k in ("n_proteins", "n_residues", "n_emitted", "n_unique", "n_entries"):
+                assert st[k] == st2[k], k
+            assert_entries_equal(g2.fetch(0, st2["n_entries"]), o.entries())
+            _, _, lo, hi = synth.synth_queries(o.entries()["mass"], 200, 4, da_fraction=0.3)
+            check_hits(g2, o, lo, hi)
+            assert g2.get_protein(7) == res[int(off[7]):int(off[8])].tobytes()
+            with pytest.raises(dbi.DbiError):
+                g2.load(path)  # not a fresh handle any more
+        finally:
+            g2.close()
+        q = dbi.default_params(**dict(PARAM_SETS[name], max_missed=1))
+        g3 = dbi.GpuIndex(q)
+        try:
+            with pytest.raises(dbi.DbiError) as ei:
+                g3.load(path)
+            assert "other search parameters" in str(ei.value)
+        finally:
+            g3.close()
+    finally:
+        g.close()
+
+
+def test_resume_from_disk_through_the_mirror(tmp_path):
+    """DBIndexImpl with inMemoryIndex = false: the first instance indexes and writes
+    <fasta>_<md5(params)>.gpuidx, the second finds it and skips indexing (DBIndexer.java:522-531)."""
+    from dbindex_b200.indexer import INDEX_FILE_SUFFIX, createFullIndexFileName, getDefaultDBIndexParams
+    res, off = synth.synth_proteome(80, 5, median_len=150, min_len=5)
+    fasta = str(tmp_path / "small.fasta")
+    synth.write_fasta(fasta, res, off)
+    sp = getDefaultDBIndexParams(fasta, inMemoryIndex=False, use_mono=True, max_missed=2)
+    name = createFullIndexFileName(sp)
+    assert name.startswith(fasta + "_") and len(name) == len(fasta) + 33
+    a = DBIndexImpl(sp)
+    try:
+        assert os.path.exists(name + INDEX_FILE_SUFFIX) and not a.indexer.loaded_from_disk
+        hits_a = [(s.mass, s.sequence, tuple(s.proteinIds)) for s in a.getSequences(1500.0, 2.0)]
+    finally:
+        a.close()
+    b = DBIndexImpl(sp)
+    try:
+        assert b.indexer.loaded_from_disk
+        assert [(s.mass, s.sequence, tuple(s.proteinIds)) for s in b.getSequences(1500.0, 2.0)] == hits_a
+        assert b.getIndexedProteinById(3).accession.startswith("sp|S0000003")
+    finally:
+        b.close()
+
+
 def test_lifecycle_errors_and_rebuild():
     p = dbi.default_params()
     res, off = synth.synth_proteome(50, 9)
