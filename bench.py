@@ -707,6 +707,9 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
         if i >= 1:
             e2e_ms.append(a.elapsed_time(b))
 
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, {"entries": int(n_entries), "hits": int(hits), "query_ms": round(sum(query_ms) / len(query_ms), 3),
+                                      **{k: round(v, 3) for k, v in st["stage_ms"].items() if v > 0}})
     t = torch.tensor([float(sum(step_ms)), float(sum(query_ms)), float(sum(e2e_ms)) / len(e2e_ms), a2a_ms],
                      device="cuda", dtype=torch.float64)
     u = torch.tensor([float(n_entries), float(n_launch), float(hits), float(a2a_bytes), float(sink.nbytes),
@@ -750,7 +753,7 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
             "clocks": clk,
             "host_stage_ms_rank0_last_step": {k: round(v, 3) for k, v in info["t"].items()},
             "device_stage_ms_rank0_last_step": {k: round(v, 3) for k, v in st["stage_ms"].items() if v > 0},
-            "entries_rank0": int(n_entries),
+            "per_rank_last_step": {k: [r.get(k, 0) for r in per_rank] for k in per_rank[0]},
         }
         print(json.dumps(line), flush=True)
     barrier()

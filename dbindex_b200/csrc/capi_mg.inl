@@ -386,9 +386,12 @@ int dbi_mg_hist(dbi_handle* h, int stage, void* d_hist, int* shift) {
                    h->stream);
   } else {  // group records: weigh by their variant count
     const bool weighted = h->cfg.n_seq > 0;
-    // a group costs its entries (expansion) plus a constant (7 sort passes, staging): measured ~5 entries' worth
+    // a group costs its entries (expansion, later the hits of the queries) plus a constant (7 sort passes,
+    // staging; ~120 ps per group against ~30 ps per entry).  Only a quarter of that constant is charged:
+    // the ranks of the light peptides (many small groups) send the least over NVLink in this exchange,
+    // which the weight does not see -- measured per-rank times, profiles/r02_scale_notes.md
     launch_mg_hist(h->mg_vkey.as<uint64_t>(), h->mg_v, 0, sh, weighted ? h->mg_vpay.as<uint64_t>() : nullptr,
-                   kGrpCntMask, weighted ? 5u : 0u, (unsigned long long*)d_hist, h->stream);
+                   kGrpCntMask, weighted ? 1u : 0u, (unsigned long long*)d_hist, h->stream);
   }
   if (shift) *shift = sh;
   DBI_CUDA(cudaStreamSynchronize(h->stream));  // the caller reduces d_hist on ITS stream next

@@ -13,32 +13,37 @@ namespace {
 constexpr int MG_THREADS = 256;
 
 // ---- histograms of an exchange stage ------------------------------------------------------
-// hist[0 .. kMgBins)          += weight of the item  (stage 1: the variant count of the group; else 1)
+// hist[0 .. kMgBins)          += weight of the item  (stage 1: variant count of the group + its fixed cost; else 1)
 // hist[kMgBins .. 2 kMgBins)  += 1
 // over the bins min(kMgBins - 1, (key - sub) >> shift).  The weighted one chooses the splitters
-// (equal INDEX ENTRIES per rank), the plain one gives every rank the number of items it will send
-// and receive.  64-bit bins in shared memory: a group can stand for 2^27 variants.
+// (equal WORK per rank), the plain one gives every rank the number of items it will send and receive.
+// 32-bit shared-memory bins (native atomics); a CTA sees at most 2^16 items and weights of 2^16 or more
+// (a group can stand for 2^27 variants) go straight to the 64-bit global bins, so nothing can wrap.
+constexpr uint32_t kMgMaxItemsPerCta = 1u << 16;
+
 __global__ void __launch_bounds__(MG_THREADS)
-    mg_hist_kernel(const uint64_t* __restrict__ key, uint64_t n, uint64_t sub, int shift,
+    mg_hist_kernel(const uint64_t* __restrict__ key, uint64_t n, uint64_t per_cta, uint64_t sub, int shift,
                    const uint64_t* __restrict__ wpay, uint64_t wmask, uint32_t wadd,
                    unsigned long long* __restrict__ hist) {
-  extern __shared__ __align__(16) unsigned long long sh_w[];  // [kMgBins] weighted, then u32 [kMgBins] plain
-  uint32_t* sh_c = reinterpret_cast<uint32_t*>(sh_w + kMgBins);
+  __shared__ uint32_t sh_w[kMgBins];
+  __shared__ uint32_t sh_c[kMgBins];
   for (int i = threadIdx.x; i < kMgBins; i += MG_THREADS) {
     sh_w[i] = 0;
     sh_c[i] = 0;
   }
   __syncthreads();
-  const uint64_t stride = (uint64_t)gridDim.x * MG_THREADS;
-  for (uint64_t i = (uint64_t)blockIdx.x * MG_THREADS + threadIdx.x; i < n; i += stride) {
+  const uint64_t i0 = (uint64_t)blockIdx.x * per_cta, i1 = min(n, i0 + per_cta);
+  for (uint64_t i = i0 + threadIdx.x; i < i1; i += MG_THREADS) {
     uint64_t b = (key[i] - sub) >> shift;
     if (b >= kMgBins) b = kMgBins - 1;
     atomicAdd(&sh_c[b], 1u);
-    atomicAdd(&sh_w[b], wpay ? (unsigned long long)(wpay[i] & wmask) + wadd : 1ull);
+    const uint64_t w = wpay ? (wpay[i] & wmask) + wadd : 1ull;
+    if (w < (1ull << 16)) atomicAdd(&sh_w[b], (uint32_t)w);
+    else atomicAdd(&hist[b], (unsigned long long)w);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < kMgBins; i += MG_THREADS) {
-    if (sh_w[i]) atomicAdd(&hist[i], sh_w[i]);
+    if (sh_w[i]) atomicAdd(&hist[i], (unsigned long long)sh_w[i]);
     if (sh_c[i]) atomicAdd(&hist[kMgBins + i], (unsigned long long)sh_c[i]);
   }
 }
@@ -283,11 +288,12 @@ __global__ void __launch_bounds__(MG_THREADS)
 void launch_mg_hist(const uint64_t* key, uint64_t n, uint64_t sub, int shift, const uint64_t* wpay, uint64_t wmask,
                     uint32_t wadd, unsigned long long* hist, cudaStream_t s) {
   if (n == 0) return;
-  uint64_t g = (n + MG_THREADS * 8 - 1) / (MG_THREADS * 8);
-  if (g > (uint64_t)kNumSMsB200 * 4) g = (uint64_t)kNumSMsB200 * 4;
-  const size_t smem = (size_t)kMgBins * 12;
-  DBI_CUDA(cudaFuncSetAttribute(mg_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  DBI_LAUNCH(mg_hist_kernel, (unsigned)g, MG_THREADS, smem, s, key, n, sub, shift, wpay, wmask, wadd, hist);
+  uint64_t g = (uint64_t)kNumSMsB200 * 4;
+  uint64_t per_cta = (n + g - 1) / g;
+  if (per_cta > kMgMaxItemsPerCta) per_cta = kMgMaxItemsPerCta;
+  per_cta = (per_cta + MG_THREADS - 1) / MG_THREADS * MG_THREADS;
+  g = (n + per_cta - 1) / per_cta;
+  DBI_LAUNCH(mg_hist_kernel, (unsigned)g, MG_THREADS, 0, s, key, n, per_cta, sub, shift, wpay, wmask, wadd, hist);
 }
 
 size_t mg_scatter_tmp_bytes(uint64_t n) {

@@ -160,16 +160,21 @@ def build_sharded(engine: ShardEngine) -> dict:
 
     def exchange(stage: int, item_bytes: int):
         hist, shift = engine.hist(stage)
+        lap(f"hist{stage}.kernel")
         local = hist.clone()
         if world > 1:
             dist.all_reduce(hist)
-        hg, hl = hist.cpu().numpy().view(np.uint64), local.cpu().numpy().view(np.uint64)
+        both = torch.stack([hist, local]).cpu().numpy().view(np.uint64)  # one D2H (the stage's first sync)
+        hg, hl = both[0], both[1]
+        lap(f"hist{stage}.reduce")
         split, send, recv = plan_exchange(world, hg, hl)
-        lap(f"hist{stage}")
+        lap(f"hist{stage}.plan")
         d1 = engine.window(WIN_ARENA, engine.layout_bytes(WIN_ARENA, stage, int(recv[rank])))
         d2 = engine.window(WIN_UNIQUE, engine.layout_bytes(WIN_UNIQUE, 0, int(recv[rank])) if stage == 0 else 0)
         row = np.concatenate([send.view(np.uint8), np.array([engine.n_unique()], dtype=np.uint64).view(np.uint8), d1, d2])
+        lap(f"plan{stage}.windows")
         rows = _all_gather_bytes(row, dev)  # every rank is past its previous use of the arenas
+        lap(f"plan{stage}.gather")
         matrix = rows[:, :8 * world].copy().view(np.uint64).reshape(world, world)
         ru = rows[:, 8 * world:8 * world + 8].copy().view(np.uint64).reshape(world)
         o = 8 * world + 8
@@ -186,6 +191,7 @@ def build_sharded(engine: ShardEngine) -> dict:
             e1.record()
             e1.synchronize()
             info["a2a_ms"] += e0.elapsed_time(e1)
+        lap(f"scatter{stage}.kernel")
         _barrier(dev)  # every rank's stores into this rank's arena are complete
         info["a2a_bytes"] += int(send.sum() - send[rank]) * item_bytes
         lap(f"scatter{stage}")

@@ -291,7 +291,7 @@ def test_save_load_roundtrip(name, tmp_path):
                 g2.load(path)  # not a fresh handle any more
         finally:
             g2.close()
-        q = dbi.default_params(**dict(PARAM_SETS[name], max_missed=1))
+        q = dbi.default_params(**dict(PARAM_SETS[name], min_mass=p.min_mass + 1.0))
         g3 = dbi.GpuIndex(q)
         try:
             with pytest.raises(dbi.DbiError) as ei:
