@@ -40,6 +40,7 @@ public class GpuDBIndexStore implements DBIndexStore {
 	private MemorySegment handle = MemorySegment.NULL;
 	private boolean inited = false, built = false;
 	private ProteinCache proteinCache;
+	private String indexFile; // null = in-memory index only
 	// proteins gathered by addProteinDef until stopAddSeq() (subsystem 1: packed residue buffer)
 	private final java.io.ByteArrayOutputStream residues = new java.io.ByteArrayOutputStream();
 	private final List<Long> offsets = new ArrayList<>(List.of(0L));
@@ -79,7 +80,34 @@ public class GpuDBIndexStore implements DBIndexStore {
 		set(p, "min_mass", sparam.getMinPrecursorMass());
 		set(p, "max_mass", sparam.getMaxPrecursorMass());
 		setInt(p, "mass_group_factor", sparam.getMassGroupFactor());
-		// differential mods: DiffModification table + max_num_differential_AA_per_mod when the host has them
+		// mandatoryInternalAAs (DBIndexer.java:248,334-344): null = no constraint, an empty array is legal
+		final char[] mandatory = sparam.getMandatoryInternalAAs();
+		if (mandatory != null) {
+			setInt(p, "has_mandatory", 1);
+			final long manOff = DbiNative.PARAMS.byteOffset(java.lang.foreign.MemoryLayout.PathElement.groupElement("is_mandatory"));
+			for (final char c : mandatory)
+				p.set(JAVA_BYTE, manOff + c, (byte) 1);
+		}
+		// PeptideFilterByMaxOccurrencies prints itself as <aa><max> (util/PeptideFilterByMaxOccurrencies.java:37-40)
+		if (sparam.getPeptideFilter() != null) {
+			final String pf = sparam.getPeptideFilter().toString();
+			setInt(p, "filter_aa", pf.charAt(0));
+			setInt(p, "filter_max", Integer.parseInt(pf.substring(1)));
+		}
+		// differential mods: the residue -> shift table SearchParamReader fills (io/SearchParamReader.java:631-667,
+		// model/DiffModification.java:11-54) and max_num_differential_AA_per_mod (:322)
+		final boolean[] isDiff = edu.scripps.yates.dbindex.model.DiffModification.getIsDiffMod();
+		final double[] diff = edu.scripps.yates.dbindex.model.DiffModification.getDiffMod();
+		int nMods = 0;
+		try (Arena a = Arena.ofConfined()) {
+			for (int c = 0; c < isDiff.length && c < 256; ++c)
+				if (isDiff[c] && diff[c] != 0) {
+					final MemorySegment res = a.allocateFrom(String.valueOf((char) c));
+					check((int) DbiNative.dbi_params_add_diff_mod.invoke(p, res, diff[c])); // DBI_ERANGE past 16 entries
+					++nMods;
+				}
+		}
+		setInt(p, "max_mods_per_peptide", nMods > 0 ? edu.scripps.yates.dbindex.SearchParams.getInstance().getMaxNumDiffMod() : 0);
 		return p;
 	}
 
@@ -99,6 +127,15 @@ public class GpuDBIndexStore implements DBIndexStore {
 			final MemorySegment out = arena.allocate(ADDRESS);
 			check((int) DbiNative.dbi_create.invoke(params(), out));
 			handle = out.get(ADDRESS, 0);
+			// on-disk index (in_memory_index = false): <fasta>_<md5(params)> like the reference (IndexUtil.java:270-324);
+			// if the file is there the index is loaded and DBIndexer.run() skips indexing (DBIndexer.java:522-531)
+			if (!sparam.isInMemoryIndex()) {
+				indexFile = sparam.getFullIndexFileName(null, null, false, null, false, null) + ".gpuidx";
+				if (new java.io.File(indexFile).exists()) {
+					check((int) DbiNative.dbi_load.invoke(handle, arena.allocateFrom(indexFile)));
+					built = true;
+				}
+			}
 		} catch (final DBIndexStoreException e) {
 			throw e;
 		} catch (final Throwable t) {
@@ -157,6 +194,8 @@ public class GpuDBIndexStore implements DBIndexStore {
 			check((int) DbiNative.dbi_add_proteins.invoke(handle, r, o, offsets.size() - 1));
 			check((int) DbiNative.dbi_build.invoke(handle));
 			built = true;
+			if (indexFile != null)
+				check((int) DbiNative.dbi_save.invoke(handle, a.allocateFrom(indexFile)));
 		} catch (final DBIndexStoreException e) {
 			throw e;
 		} catch (final Throwable t) {
@@ -191,7 +230,13 @@ public class GpuDBIndexStore implements DBIndexStore {
 		return query(lo, hi);
 	}
 
-	/** dbi_query + dbi_fetch, then the object assembly of parseAddPeptideInfo (Merge:452-477). */
+	/**
+	 * dbi_query_hits + dbi_query_hits_read: ONE device pass for all ranges of the call (bounds search, hit
+	 * materialisation incl. peptide residues and flanks, one D2H per array), then the object assembly of
+	 * parseAddPeptideInfo (Merge:452-477). The mod pattern (byte k = position + 1 of the k-th modified
+	 * residue) travels in IndexedSequence.setModSequence-style notation so that variants of one peptide
+	 * stay distinguishable.
+	 */
 	private List<IndexedSequence> query(double[] lo, double[] hi) throws DBIndexStoreException {
 		final List<IndexedSequence> ret = new ArrayList<>();
 		final int bucketRange = MAX_MASS / sparam.getIndexFactor();
@@ -201,36 +246,40 @@ public class GpuDBIndexStore implements DBIndexStore {
 		try (Arena a = Arena.ofConfined()) {
 			final int nq = lo.length;
 			final MemorySegment dlo = a.allocate(JAVA_DOUBLE, nq), dhi = a.allocate(JAVA_DOUBLE, nq);
-			final MemorySegment beg = a.allocate(JAVA_LONG, nq), cnt = a.allocate(JAVA_LONG, nq);
 			MemorySegment.copy(lo, 0, dlo, JAVA_DOUBLE, 0, nq);
 			MemorySegment.copy(hi, 0, dhi, JAVA_DOUBLE, 0, nq);
-			check((int) DbiNative.dbi_query.invoke(handle, dlo, dhi, (long) nq, beg, cnt));
-			for (int q = 0; q < nq; ++q) {
-				final long b = beg.getAtIndex(JAVA_LONG, q), c = cnt.getAtIndex(JAVA_LONG, q);
-				if (c == 0)
-					continue;
-				final MemorySegment mass = a.allocate(JAVA_DOUBLE, c), prot = a.allocate(JAVA_INT, c);
-				final MemorySegment off = a.allocate(JAVA_INT, c), len = a.allocate(JAVA_SHORT, c);
-				final MemorySegment plo = a.allocate(JAVA_LONG, c + 1), nIds = a.allocate(JAVA_LONG);
-				check((int) DbiNative.dbi_fetch.invoke(handle, b, c, MemorySegment.NULL, MemorySegment.NULL,
-						MemorySegment.NULL, MemorySegment.NULL, MemorySegment.NULL, MemorySegment.NULL,
-						MemorySegment.NULL, 0L, nIds)); // sizing call
-				final long n = nIds.get(JAVA_LONG, 0);
-				final MemorySegment ids = a.allocate(JAVA_INT, Math.max(1, n));
-				check((int) DbiNative.dbi_fetch.invoke(handle, b, c, mass, prot, off, len, MemorySegment.NULL, plo, ids,
-						n, nIds));
-				for (long i = 0; i < c; ++i) {
-					final int pid = prot.getAtIndex(JAVA_INT, i), o = off.getAtIndex(JAVA_INT, i);
-					final int l = len.getAtIndex(JAVA_SHORT, i) & 0xffff;
-					final String pep = proteinCache.getPeptideSequence(pid, o, l); // ProteinCache.java:112-127
-					final IndexedSequence s = new IndexedSequence(0, mass.getAtIndex(JAVA_DOUBLE, i), pep, "", "");
-					final List<Integer> pids = new ArrayList<>();
-					for (long k = plo.getAtIndex(JAVA_LONG, i); k < plo.getAtIndex(JAVA_LONG, i + 1); ++k)
-						pids.add(ids.getAtIndex(JAVA_INT, k));
-					s.setProteinIds(pids);
-					s.setResidues(Util.getResidues(null, o, l, proteinCache.getProteinSequence(pid))); // keeps Q8
-					ret.add(s);
-				}
+			final MemorySegment cnt = a.allocate(DbiNative.HIT_COUNTS);
+			check((int) DbiNative.dbi_query_hits.invoke(handle, dlo, dhi, (long) nq, cnt));
+			final long nHits = cnt.get(JAVA_LONG, 8), nSeq = cnt.get(JAVA_LONG, 16), nIds = cnt.get(JAVA_LONG, 24);
+			final MemorySegment mass = a.allocate(JAVA_DOUBLE, Math.max(1, nHits));
+			final MemorySegment prot = a.allocate(JAVA_INT, Math.max(1, nHits)), off = a.allocate(JAVA_INT, Math.max(1, nHits));
+			final MemorySegment len = a.allocate(JAVA_SHORT, Math.max(1, nHits)), pat = a.allocate(JAVA_INT, Math.max(1, nHits));
+			final MemorySegment flanks = a.allocate(Math.max(1, 6 * nHits));
+			final MemorySegment seqOff = a.allocate(JAVA_LONG, nHits + 1), seq = a.allocate(Math.max(1, nSeq));
+			final MemorySegment plo = a.allocate(JAVA_LONG, nHits + 1), ids = a.allocate(JAVA_INT, Math.max(1, nIds));
+			final MemorySegment bufs = a.allocate(DbiNative.HIT_BUFFERS);
+			final MemorySegment[] order = { MemorySegment.NULL /* hit_off: the union is returned as one list */, mass, prot,
+					off, len, pat, flanks, seqOff, seq, plo, ids };
+			for (int k = 0; k < order.length; ++k)
+				bufs.setAtIndex(ADDRESS, k, order[k]);
+			check((int) DbiNative.dbi_query_hits_read.invoke(handle, bufs));
+			final byte[] seqBytes = seq.asSlice(0, nSeq).toArray(JAVA_BYTE);
+			final byte[] flankBytes = flanks.asSlice(0, 6 * nHits).toArray(JAVA_BYTE);
+			for (long i = 0; i < nHits; ++i) {
+				final int s0 = (int) seqOff.getAtIndex(JAVA_LONG, i), s1 = (int) seqOff.getAtIndex(JAVA_LONG, i + 1);
+				final String pep = new String(seqBytes, s0, s1 - s0, java.nio.charset.StandardCharsets.ISO_8859_1);
+				final String resLeft = new String(flankBytes, (int) (6 * i), 3, java.nio.charset.StandardCharsets.ISO_8859_1);
+				final String resRight = new String(flankBytes, (int) (6 * i + 3), 3, java.nio.charset.StandardCharsets.ISO_8859_1);
+				final IndexedSequence s = new IndexedSequence(0, mass.getAtIndex(JAVA_DOUBLE, i), pep, resLeft, resRight);
+				final List<Integer> pids = new ArrayList<>();
+				for (long k = plo.getAtIndex(JAVA_LONG, i); k < plo.getAtIndex(JAVA_LONG, i + 1); ++k)
+					pids.add(ids.getAtIndex(JAVA_INT, k));
+				s.setProteinIds(pids);
+				s.setSequenceOffset(off.getAtIndex(JAVA_INT, i)); // SURVEY Q10: the offset is known, hand it over
+				final int mp = pat.getAtIndex(JAVA_INT, i);
+				if (mp != 0)
+					s.setModSequence(modNotation(pep, mp));
+				ret.add(s);
 			}
 		} catch (final DBIndexStoreException e) {
 			throw e;
@@ -238,6 +287,19 @@ public class GpuDBIndexStore implements DBIndexStore {
 			throw new DBIndexStoreException("Error getting peptides ", t);
 		}
 		return ret;
+	}
+
+	/** pattern byte k = position + 1 of the k-th modified residue -> "PEPT(+79.9663)IDE". */
+	private static String modNotation(String pep, int pattern) {
+		final double[] diff = edu.scripps.yates.dbindex.model.DiffModification.getDiffMod();
+		final StringBuilder sb = new StringBuilder();
+		for (int i = 0; i < pep.length(); ++i) {
+			sb.append(pep.charAt(i));
+			for (int k = 0; k < 4; ++k)
+				if (((pattern >>> (8 * k)) & 0xff) == i + 1)
+					sb.append("(").append(String.format(java.util.Locale.ROOT, "%+.4f", diff[pep.charAt(i)])).append(")");
+		}
+		return sb.toString();
 	}
 
 	@Override
