@@ -331,12 +331,16 @@ struct Stage {
       cudaEventRecord(a, h->stream);
     }
   }
-  ~Stage() {
+  ~Stage() {  // never throws: a failed event creation only loses this stage's timing
     h->st.stage_launches[id] += (uint32_t)(g_kernel_launches.load() - l0);
-    if (h->p.profile) {
-      cudaEvent_t b = h->get_event();
-      cudaEventRecord(b, h->stream);
-      h->spans.push_back({id, a, b});
+    if (h->p.profile && a) {
+      try {
+        cudaEvent_t b = h->get_event();
+        cudaEventRecord(b, h->stream);
+        h->spans.push_back({id, a, b});
+      } catch (...) {
+        cudaGetLastError();
+      }
     }
   }
 };
@@ -1129,7 +1133,8 @@ int dbi_add_proteins(dbi_handle* h, const uint8_t* residues, const uint64_t* off
     DBI_CUDA(cudaMemcpyAsync((uint8_t*)h->d_raw.p + base, residues + offsets[0], add, cudaMemcpyHostToDevice, s));
   h->h_off.reserve(h->h_off.size() + n);
   for (uint32_t i = 1; i <= n; ++i) h->h_off.push_back(base + (offsets[i] - offsets[0]));
-  if (h->h_raw_valid) h->h_raw.insert(h->h_raw.end(), residues + offsets[0], residues + offsets[n]);
+  // the host copy behind dbi_get_protein is rebuilt on demand: pointers handed out before this call end here
+  h->h_raw_valid = false;
   h->n_res = total_res;
   DBI_CUDA(cudaStreamSynchronize(s));
   h->st.n_proteins = total_prot;

@@ -21,6 +21,7 @@
 #include <cerrno>
 #include <cstring>
 #include <exception>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -79,10 +80,30 @@ void parallel_for(int n_threads, size_t n, F&& f) {
     f(0, n, 0);
     return;
   }
+  // A worker that throws (bad_alloc of a push_back) must not escape its thread, and a failed
+  // emplace_back must not unwind past joinable threads: both would be std::terminate instead of a
+  // DBI_* code.  The first failure is kept and rethrown on the calling thread after every join.
   std::vector<std::thread> th;
   const size_t T = std::min<size_t>((size_t)n_threads, n);
-  for (size_t t = 0; t < T; ++t) th.emplace_back([&, t] { f(n * t / T, n * (t + 1) / T, (int)t); });
+  std::exception_ptr first;
+  std::mutex mu;
+  auto guarded = [&](size_t t) {
+    try {
+      f(n * t / T, n * (t + 1) / T, (int)t);
+    } catch (...) {
+      std::lock_guard<std::mutex> lk(mu);
+      if (!first) first = std::current_exception();
+    }
+  };
+  try {
+    th.reserve(T);
+    for (size_t t = 0; t < T; ++t) th.emplace_back(guarded, t);
+  } catch (...) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!first) first = std::current_exception();
+  }
   for (auto& x : th) x.join();
+  if (first) std::rethrow_exception(first);
 }
 
 }  // namespace

@@ -221,7 +221,7 @@ void launch_mg_scatter_groups(const uint64_t* key, const uint64_t* pay, const ui
                               uint64_t n, const MgPlan& pl, const MgGrpDst& dst, void* tmp, cudaStream_t s);
 // list length of every unique peptide: cnt[u] = plo[u+1] - plo[u]
 void launch_plo_to_counts(const uint64_t* plo, uint64_t n, uint32_t* cnt, cudaStream_t s);
-// full exclusive scan: offs[i] = sum(in[0..i)), offs[n] = total; tmp = (ntiles + 1) u64 + ntiles u32
+// full exclusive scan: offs[i] = sum(in[0..i)), offs[n] = total; tmp = (ntiles + 1) u64 + ntiles u64 (64-bit tile sums)
 void launch_full_scan_u32_to_u64(const uint32_t* in, uint64_t n, uint64_t* offs, void* tmp, cudaStream_t s);
 size_t full_scan_tmp_bytes(uint64_t n);
 

@@ -253,31 +253,48 @@ __global__ void __launch_bounds__(MG_THREADS)
 constexpr int FS_IPT = kScanTile / MG_THREADS;
 
 __global__ void __launch_bounds__(MG_THREADS)
-    tile_sums_kernel(const uint32_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ tile_sums) {
-  __shared__ uint32_t scratch[MG_THREADS / 32 + 1];
+    tile_sums_kernel(const uint32_t* __restrict__ in, uint64_t n, unsigned long long* __restrict__ tile_sums) {
+  // 64-bit sums: the inputs are variant counts of up to 2^27 each (4096 of them wrap 32 bits)
+  __shared__ unsigned long long scratch[MG_THREADS / 32 + 1];
   const uint64_t tile_base = (uint64_t)blockIdx.x * kScanTile;
-  uint32_t sum = 0;
+  unsigned long long sum = 0;
   for (int k = 0; k < FS_IPT; ++k) {
     const uint64_t i = tile_base + (uint64_t)k * MG_THREADS + threadIdx.x;
     if (i < n) sum += in[i];
   }
-  uint32_t total;
-  block_exclusive_sum<uint32_t, MG_THREADS>(sum, scratch, &total);
+  unsigned long long total;
+  block_exclusive_sum<unsigned long long, MG_THREADS>(sum, scratch, &total);
   if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// exclusive scan of u64 tile sums in place; offs[n] = total (single CTA)
+__global__ void __launch_bounds__(1024)
+    scan_u64_kernel(const unsigned long long* __restrict__ in, uint64_t n, unsigned long long* __restrict__ offs) {
+  __shared__ unsigned long long scratch[1024 / 32 + 1];
+  unsigned long long carry = 0;
+  for (uint64_t base = 0; base < n; base += 1024) {
+    const uint64_t i = base + threadIdx.x;
+    const unsigned long long v = (i < n) ? in[i] : 0ull;
+    unsigned long long total;
+    const unsigned long long ex = block_exclusive_sum<unsigned long long, 1024>(v, scratch, &total);
+    if (i < n) offs[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) offs[n] = carry;
 }
 
 __global__ void __launch_bounds__(MG_THREADS)
     tile_scan_kernel(const uint32_t* __restrict__ in, uint64_t n, const uint64_t* __restrict__ tile_offs,
                      uint64_t ntiles, uint64_t* __restrict__ offs) {
-  __shared__ uint32_t scratch[MG_THREADS / 32 + 1];
+  __shared__ unsigned long long scratch[MG_THREADS / 32 + 1];
   const uint64_t tile_base = (uint64_t)blockIdx.x * kScanTile;
   uint64_t running = tile_offs[blockIdx.x];
   if (blockIdx.x == 0 && threadIdx.x == 0) offs[n] = tile_offs[ntiles];
   for (int k = 0; k < FS_IPT; ++k) {
     const uint64_t i = tile_base + (uint64_t)k * MG_THREADS + threadIdx.x;
-    const uint32_t v = (i < n) ? in[i] : 0u;
-    uint32_t total;
-    const uint32_t ex = block_exclusive_sum<uint32_t, MG_THREADS>(v, scratch, &total);
+    const unsigned long long v = (i < n) ? in[i] : 0ull;
+    unsigned long long total;
+    const unsigned long long ex = block_exclusive_sum<unsigned long long, MG_THREADS>(v, scratch, &total);
     if (i < n) offs[i] = running + ex;
     running += total;
   }
@@ -327,7 +344,7 @@ void launch_plo_to_counts(const uint64_t* plo, uint64_t n, uint32_t* cnt, cudaSt
 
 size_t full_scan_tmp_bytes(uint64_t n) {
   const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
-  return (tiles + 1) * 8 + tiles * 4 + 64;
+  return (tiles + 1) * 8 + tiles * 8 + 64;
 }
 
 void launch_full_scan_u32_to_u64(const uint32_t* in, uint64_t n, uint64_t* offs, void* tmp, cudaStream_t s) {
@@ -337,9 +354,9 @@ void launch_full_scan_u32_to_u64(const uint32_t* in, uint64_t n, uint64_t* offs,
   }
   const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
   uint64_t* tile_offs = (uint64_t*)tmp;
-  uint32_t* tile_sums = (uint32_t*)((uint8_t*)tmp + (tiles + 1) * 8);
+  unsigned long long* tile_sums = (unsigned long long*)((uint8_t*)tmp + (tiles + 1) * 8);
   DBI_LAUNCH(tile_sums_kernel, (unsigned)tiles, MG_THREADS, 0, s, in, n, tile_sums);
-  launch_scan_u32_to_u64(tile_sums, tiles, tile_offs, s);
+  DBI_LAUNCH(scan_u64_kernel, 1, 1024, 0, s, tile_sums, tiles, (unsigned long long*)tile_offs);
   DBI_LAUNCH(tile_scan_kernel, (unsigned)tiles, MG_THREADS, 0, s, in, n, tile_offs, tiles, offs);
 }
 

@@ -193,12 +193,16 @@ __global__ void __launch_bounds__(MD_THREADS)
     }
     ng_out[u] = (uint8_t)ng;
   }
-  uint32_t tot_g, tot_v;
+  uint32_t tot_g;
   block_exclusive_sum<uint32_t, MD_THREADS>(ng, scratch, &tot_g);
-  block_exclusive_sum<uint32_t, MD_THREADS>(nv, scratch, &tot_v);
+  // the variant total of a tile is informational (the entry count comes from the 64-bit scan of the sorted
+  // groups); summed in 64 bits and saturated so that a wrap can never look like a small number
+  __shared__ unsigned long long scratch64[MD_WARPS + 1];
+  unsigned long long tot_v;
+  block_exclusive_sum<unsigned long long, MD_THREADS>((unsigned long long)nv, scratch64, &tot_v);
   if (threadIdx.x == 0) {
     tile_groups[blockIdx.x] = tot_g;
-    tile_vars[blockIdx.x] = tot_v;
+    tile_vars[blockIdx.x] = tot_v > 0xffffffffull ? 0xffffffffu : (uint32_t)tot_v;
   }
 }
 

@@ -280,7 +280,8 @@ int dbi_host_alloc(uint64_t bytes, void** out);
 int dbi_host_free(void* p);
 
 /* ProteinCache.getProteinSequence(id) (ProteinCache.java; DBIndexImpl.java:511).
- * Returns a pointer into the handle's host copy, valid until dbi_destroy. */
+ * Returns a pointer into the handle's host copy, valid until the next dbi_add_proteins on this handle or
+ * dbi_destroy. */
 int dbi_get_protein(dbi_handle* h, uint32_t id, const uint8_t** residues, uint64_t* len);
 
 /* IndexUtil.calculateMass(seq) (util/IndexUtil.java:197-208): same summation

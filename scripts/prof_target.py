@@ -22,5 +22,5 @@ for _ in range(2):
 st = g.stats()
 m = g.fetch(st["n_entries"] // 2, 4096, with_ids=False)["mass"]
 _, _, lo, hi = synth.synth_queries(m, 10000, 1)
-b, c = g.query(lo, hi)
-print("entries", st["n_entries"], "hits", int(c.sum()), "launches", g.kernel_launches())
+h = g.query_hits(lo, hi)  # bounds + materialisation of every hit (what the bench step does after the build)
+print("entries", st["n_entries"], "hits", int(h["hit_off"][-1]), "launches", g.kernel_launches())
