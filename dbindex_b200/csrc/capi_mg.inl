@@ -386,12 +386,9 @@ int dbi_mg_hist(dbi_handle* h, int stage, void* d_hist, int* shift) {
                    h->stream);
   } else {  // group records: weigh by their variant count
     const bool weighted = h->cfg.n_seq > 0;
-    // a group costs its entries (expansion, later the hits of the queries) plus a constant (7 sort passes,
-    // staging; ~120 ps per group against ~30 ps per entry).  Only a quarter of that constant is charged:
-    // the ranks of the light peptides (many small groups) send the least over NVLink in this exchange,
-    // which the weight does not see -- measured per-rank times, profiles/r02_scale_notes.md
+    // weighted = index entries the groups stand for, plain = groups; dbi_mg_plan turns both into a cost
     launch_mg_hist(h->mg_vkey.as<uint64_t>(), h->mg_v, 0, sh, weighted ? h->mg_vpay.as<uint64_t>() : nullptr,
-                   kGrpCntMask, weighted ? 1u : 0u, (unsigned long long*)d_hist, h->stream);
+                   kGrpCntMask, 0u, (unsigned long long*)d_hist, h->stream);
   }
   if (shift) *shift = sh;
   DBI_CUDA(cudaStreamSynchronize(h->stream));  // the caller reduces d_hist on ITS stream next
@@ -399,27 +396,57 @@ int dbi_mg_hist(dbi_handle* h, int stage, void* d_hist, int* shift) {
   DBI_API_END
 }
 
-// Pure host arithmetic: equal-weight bin splitters from the global weighted histogram (bins are never
-// split, so equal masses -- hence equal peptides -- meet on one rank), this rank's send counts from
-// its own plain histogram, every rank's receive total from the global plain histogram.
-int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_local, uint32_t* bin_splitters,
-                uint64_t* send_counts, uint64_t* recv_totals) {
+// Pure host arithmetic: bin splitters of equal COST from the global histograms (bins are never split, so
+// equal masses -- hence equal peptides -- meet on one rank), this rank's send counts from its own plain
+// histogram, every rank's receive total from the global plain histogram.
+//
+// cost of a bin = cost[0] * items + cost[1] * weight + cost[2] * weight^2 * mass / (width * total weight)
+//   items  = records (exchange 0) or variant groups (exchange 1): sort passes, staging
+//   weight = index entries the items stand for: expansion writes
+//   last term = expected HITS of precursor queries that follow the indexed mass density at a relative (ppm)
+//   tolerance: queries landing in the bin ~ weight / total, hits per query ~ (weight / width) * mass.
+//   An index is built once and searched many times, so the slices are cut for the search load too.
+// cost == NULL: {0, 1, 0} (equal weight).  Every rank runs this on the same global histogram and gets the
+// same splitters.
+int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_local, int shift, double min_mass,
+                const double* cost, uint32_t* bin_splitters, uint64_t* send_counts, uint64_t* recv_totals) {
   if (world < 1 || world > kMaxRanks || !hist_global || !hist_local || !send_counts || !recv_totals ||
-      (world > 1 && !bin_splitters)) {
+      (world > 1 && !bin_splitters) || shift < 0 || shift > 52) {
     set_error("bad argument");
     return DBI_EINVAL;
   }
   const int B = kMgBins;
-  unsigned __int128 total = 0;
-  for (int b = 0; b < B; ++b) total += hist_global[b];
+  const double c_item = cost ? cost[0] : 0.0, c_w = cost ? cost[1] : 1.0, c_hit = cost ? cost[2] : 0.0;
+  double w_total = 0;
+  for (int b = 0; b < B; ++b) w_total += (double)hist_global[b];
+  const uint64_t base_bits = dbits(min_mass);
+  auto mass_at = [&](int b) {  // mass at the lower edge of bin b
+    const uint64_t bits = base_bits + ((uint64_t)b << shift);
+    double m;
+    std::memcpy(&m, &bits, 8);
+    return m;
+  };
+  std::vector<double> c(B);
+  double total = 0;
+  for (int b = 0; b < B; ++b) {
+    const double items = (double)hist_global[B + b], w = (double)hist_global[b];
+    double v = c_item * items + c_w * w;
+    if (c_hit > 0 && w > 0 && w_total > 0) {
+      const double m0 = mass_at(b), m1 = mass_at(b + 1);
+      const double width = m1 - m0;
+      if (width > 0) v += c_hit * w * w * (0.5 * (m0 + m1)) / (width * w_total);
+    }
+    c[b] = v;
+    total += v;
+  }
   uint32_t prev = 0;
-  unsigned __int128 cum = 0;
+  double cum = 0;
   int b = 0;
   for (int d = 1; d < world; ++d) {
-    const unsigned __int128 target = total * (unsigned)d / (unsigned)world;
-    // first bin boundary at which at least `target` of the weight lies below
-    while (b < B && cum + hist_global[b] < target) cum += hist_global[b++];
-    uint32_t cut = total ? (uint32_t)std::min(b + 1, B) : 0u;
+    const double target = total * (double)d / (double)world;
+    // first bin boundary at which at least `target` of the cost lies below
+    while (b < B && cum + c[b] < target) cum += c[b++];
+    uint32_t cut = total > 0 ? (uint32_t)std::min(b + 1, B) : 0u;
     if (cut < prev) cut = prev;
     bin_splitters[d - 1] = cut;
     prev = cut;
@@ -435,6 +462,25 @@ int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_loc
     recv_totals[d] = rt;
   }
   return DBI_OK;
+}
+
+// The cost model of an exchange for dbi_mg_plan: measured on B200 (profiles/r02_scale_notes.md), in ps.
+// DBI_MG_COST="item,weight,hit" overrides the variant exchange's.
+void dbi_mg_default_cost(int stage, int has_mods, double* cost) {
+  if (stage == 0) {
+    cost[0] = 1.0; cost[1] = 0.0; cost[2] = 0.0;  // records: equal counts
+    if (!has_mods) { cost[0] = 300.0; cost[1] = 0.0; cost[2] = 0.0; }
+    return;
+  }
+  cost[0] = 120.0;  // per group: 7 radix passes + expansion staging
+  cost[1] = 10.0;   // per entry: expansion write
+  cost[2] = 7.0;    // per expected hit of a 10 000-query batch at 10 ppm per build (70 ps per hit)
+  if (const char* e = std::getenv("DBI_MG_COST")) {
+    double a, b2, c2;
+    if (std::sscanf(e, "%lf,%lf,%lf", &a, &b2, &c2) == 3 && a >= 0 && b2 >= 0 && c2 >= 0 && a + b2 + c2 > 0) {
+      cost[0] = a; cost[1] = b2; cost[2] = c2;
+    }
+  }
 }
 
 int dbi_mg_scatter(dbi_handle* h, int stage, const uint32_t* bin_splitters, const uint64_t* matrix) {
@@ -706,21 +752,24 @@ int dbi_mg_build_local(dbi_handle** hs, int n) {
     auto exchange = [&](int stage) -> int {
       const size_t HB = 2 * kMgBins;
       std::vector<uint64_t> local((size_t)W * HB), global(HB, 0);
+      int shift_of = 0;
       for (int r = 0; r < W; ++r) {
         dbi_handle* h = hs[r];
         DBI_CUDA(cudaSetDevice(h->device));
         DevBuf d;
         d.alloc(HB * 8, h->arena);
         DBI_CUDA(cudaMemsetAsync(d.p, 0, HB * 8, h->stream));
-        int shift = 0;
-        if (int rc = dbi_mg_hist(h, stage, d.p, &shift)) return rc;
+        if (int rc = dbi_mg_hist(h, stage, d.p, &shift_of)) return rc;
         DBI_CUDA(cudaMemcpyAsync(&local[(size_t)r * HB], d.p, HB * 8, cudaMemcpyDeviceToHost, h->stream));
         DBI_CUDA(cudaStreamSynchronize(h->stream));
       }
       for (int r = 0; r < W; ++r)
         for (size_t i = 0; i < HB; ++i) global[i] += local[(size_t)r * HB + i];
+      double cost[3];
+      dbi_mg_default_cost(stage, mods ? 1 : 0, cost);
       for (int r = 0; r < W; ++r)
-        if (int rc = dbi_mg_plan(W, global.data(), &local[(size_t)r * HB], split.data(), &matrix[(size_t)r * W], recv.data()))
+        if (int rc = dbi_mg_plan(W, global.data(), &local[(size_t)r * HB], shift_of, hs[0]->p.min_mass, cost, split.data(),
+                                 &matrix[(size_t)r * W], recv.data()))
           return rc;
       for (int r = 0; r < W; ++r) {
         const uint64_t need = dbi_mg_layout_bytes(kWinArena, stage, recv[r], C);

@@ -55,15 +55,32 @@ def pick_splitters(hist: np.ndarray, world: int) -> np.ndarray:
     return np.maximum.accumulate(out) if len(out) else out
 
 
-def plan_exchange(world: int, hist_global: np.ndarray, hist_local: np.ndarray):
-    """(bin splitters, this rank's send counts, every rank's receive total) from the summed and the own
-    [weighted | plain] histograms."""
-    B = MG_BINS
-    split = pick_splitters(hist_global[:B], world)
-    edges = np.concatenate(([0], split, [B])).astype(np.int64)
-    send = np.array([hist_local[B + edges[d]:B + edges[d + 1]].sum() for d in range(world)], dtype=np.uint64)
-    recv = np.array([hist_global[B + edges[d]:B + edges[d + 1]].sum() for d in range(world)], dtype=np.uint64)
-    return split, send, recv
+def plan_exchange(world: int, hist_global: np.ndarray, hist_local: np.ndarray, shift: int, min_mass: float,
+                  stage: int = 0, has_mods: bool = False, cost=None):
+    """dbi_mg_plan (host arithmetic of libdbindex_gpu.so, no device needed): (bin splitters of equal cost,
+    this rank's send counts, every rank's receive total) from the summed and the own [weighted | plain]
+    histograms.  cost = None: the measured default model of the exchange (dbi_mg_default_cost)."""
+    import ctypes as C
+    from .capi import load_library
+    lib = load_library()
+    lib.dbi_mg_plan.restype = C.c_int
+    lib.dbi_mg_plan.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 4
+    lib.dbi_mg_default_cost.restype = None
+    lib.dbi_mg_default_cost.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    c = np.zeros(3, dtype=np.float64)
+    if cost is None:
+        lib.dbi_mg_default_cost(stage, 1 if has_mods else 0, c.ctypes.data)
+    else:
+        c[:] = cost
+    hg = np.ascontiguousarray(hist_global, dtype=np.uint64)
+    hl = np.ascontiguousarray(hist_local, dtype=np.uint64)
+    split = np.zeros(max(world - 1, 1), dtype=np.uint32)
+    send, recv = np.zeros(world, dtype=np.uint64), np.zeros(world, dtype=np.uint64)
+    rc = lib.dbi_mg_plan(world, hg.ctypes.data, hl.ctypes.data, int(shift), float(min_mass), c.ctypes.data,
+                         split.ctypes.data, send.ctypes.data, recv.ctypes.data)
+    if rc != 0:
+        raise RuntimeError((lib.dbi_last_error() or b"").decode(errors="replace"))
+    return split[:world - 1].copy(), send, recv
 
 
 def splitter_masses(bin_splitters: np.ndarray, shift: int, min_mass: float) -> np.ndarray:
@@ -167,7 +184,7 @@ def build_sharded(engine: ShardEngine) -> dict:
         both = torch.stack([hist, local]).cpu().numpy().view(np.uint64)  # one D2H (the stage's first sync)
         hg, hl = both[0], both[1]
         lap(f"hist{stage}.reduce")
-        split, send, recv = plan_exchange(world, hg, hl)
+        split, send, recv = plan_exchange(world, hg, hl, shift, engine.min_mass, stage, engine.has_mods)
         lap(f"hist{stage}.plan")
         d1 = engine.window(WIN_ARENA, engine.layout_bytes(WIN_ARENA, stage, int(recv[rank])))
         d2 = engine.window(WIN_UNIQUE, engine.layout_bytes(WIN_UNIQUE, 0, int(recv[rank])) if stage == 0 else 0)

@@ -383,10 +383,13 @@ int dbi_mg_digest(dbi_handle* h, uint64_t* n_records);
 /* d_hist: u64[2 * DBI_MG_BINS] in device memory, zeroed by the caller: += weighted | plain histogram of
  * the local items of exchange `stage` (0 = digested records, 1 = variant groups) over key >> *shift */
 int dbi_mg_hist(dbi_handle* h, int stage, void* d_hist, int* shift);
-/* host arithmetic on the summed (global) and the own (local) histograms: equal-weight bin splitters
- * [world-1], this rank's send counts [world], every rank's receive total [world] */
-int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_local, uint32_t* bin_splitters,
-                uint64_t* send_counts, uint64_t* recv_totals);
+/* host arithmetic on the summed (global) and the own (local) histograms: bin splitters [world-1] of equal
+ * COST, this rank's send counts [world], every rank's receive total [world].  cost[3] = {per item, per unit
+ * of weight (index entry), per expected query hit}; NULL = equal weight.  shift / min_mass as used by
+ * dbi_mg_hist (they give a bin its mass).  dbi_mg_default_cost fills the measured model of an exchange. */
+int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_local, int shift, double min_mass,
+                const double* cost, uint32_t* bin_splitters, uint64_t* send_counts, uint64_t* recv_totals);
+void dbi_mg_default_cost(int stage, int has_mods, double* cost);
 /* matrix[s * world + d] = items rank s sends to rank d.  Stable multisplit of the local items straight
  * into the mapped arenas of their destinations; every rank's arena must have been ensured for its
  * receive total and imported here.  A barrier across the ranks must follow before anybody consumes. */

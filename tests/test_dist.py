@@ -52,14 +52,10 @@ def test_two_rank_gloo_build_matches_oracle(name, tmp_path):
     assert r["ok"] and all(c > 0 for c in r["counts"]) and r["a2a_bytes"] > 0
 
 
-def test_dbi_mg_plan_equals_the_numpy_plan():
-    """dbi_mg_plan (C, what dbi_mg_build_local and a Java host use) == plan_exchange (numpy, what the
-    torch.distributed orchestration uses): splitters, send counts, receive totals."""
-    import ctypes as C
-    import dbindex_b200 as dbi
-    lib = dbi.load_library()
-    lib.dbi_mg_plan.restype = C.c_int
-    lib.dbi_mg_plan.argtypes = [C.c_int] + [C.c_void_p] * 5
+def test_dbi_mg_plan_cost_models():
+    """dbi_mg_plan: with the equal-weight model the splitters equal the numpy reference (pick_splitters);
+    send / receive counts partition the plain histograms; the query-aware model moves the cuts towards the
+    dense bins (fewer entries for the ranks that will see more hits) and stays monotone."""
     rng = np.random.default_rng(5)
     for world in (1, 2, 3, 8, 16):
         plain = [rng.integers(0, 50, size=MG_BINS).astype(np.uint64) for _ in range(world)]
@@ -69,14 +65,24 @@ def test_dbi_mg_plan_equals_the_numpy_plan():
         hg = np.concatenate([sum(weighted), sum(plain)]).astype(np.uint64)
         for r in range(world):
             hl = np.concatenate([weighted[r], plain[r]]).astype(np.uint64)
-            split, send, recv = plan_exchange(world, hg, hl)
-            c_split = np.zeros(max(world - 1, 1), np.uint32)
-            c_send, c_recv = np.zeros(world, np.uint64), np.zeros(world, np.uint64)
-            assert lib.dbi_mg_plan(world, hg.ctypes.data, hl.ctypes.data, c_split.ctypes.data, c_send.ctypes.data,
-                                   c_recv.ctypes.data) == 0
-            assert c_split[:world - 1].tolist() == split.tolist()
-            assert c_send.tolist() == send.tolist() and c_recv.tolist() == recv.tolist()
-            assert int(c_recv.sum()) == int(hg[MG_BINS:].sum())
+            split, send, recv = plan_exchange(world, hg, hl, 42, 600.0, cost=[0.0, 1.0, 0.0])
+            assert split.tolist() == pick_splitters(hg[:MG_BINS], world).tolist()
+            edges = np.concatenate(([0], split, [MG_BINS])).astype(int)
+            assert send.tolist() == [int(plain[r][edges[d]:edges[d + 1]].sum()) for d in range(world)]
+            assert recv.tolist() == [int(hg[MG_BINS:][edges[d]:edges[d + 1]].sum()) for d in range(world)]
+            assert int(recv.sum()) == int(hg[MG_BINS:].sum())
+        s2, _, _ = plan_exchange(world, hg, np.concatenate([weighted[0], plain[0]]), 42, 600.0, stage=1, has_mods=True)
+        assert np.all(np.diff(s2.astype(np.int64)) >= 0) and len(s2) == world - 1
+    # a density peak: the query-aware model gives the rank holding the peak a narrower slice
+    w = np.full(MG_BINS, 1000, dtype=np.uint64)
+    w[3000:3100] = 40000
+    hg = np.concatenate([w, np.full(MG_BINS, 100, dtype=np.uint64)])
+    flat, _, _ = plan_exchange(4, hg, hg, 42, 600.0, cost=[0.0, 1.0, 0.0])
+    aware, _, _ = plan_exchange(4, hg, hg, 42, 600.0, cost=[0.0, 1.0, 50.0])
+    width = lambda s: np.diff(np.concatenate(([0], s.astype(np.int64), [MG_BINS])))  # noqa: E731
+    k = int(np.searchsorted(flat, 3050))
+    k2 = int(np.searchsorted(aware, 3050))
+    assert width(aware)[k2] < width(flat)[k]
 
 
 def test_shard_proteins_covers_the_proteome_in_order():
