@@ -625,10 +625,16 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     nq = args.queries  # ONE batch for the whole index: hits per query grow with the index, so per-GPU work stays fixed
     info = build_sharded(GpuShardEngine(g, dev))  # also warms NCCL and the window mappings up
-    masses = sample_index_masses(g, g.stats()["n_entries"])
-    # every rank contributes samples of its own slice so that the queries cover the whole range
+    n_mine = g.stats()["n_entries"]
+    masses = sample_index_masses(g, n_mine)
+    # the query masses follow the indexed mass density, exactly like the N = 1 batch (which samples the index
+    # at evenly spaced ENTRY positions): every rank contributes samples of its slice in proportion to the
+    # entries it holds
+    counts = [None] * world
+    dist.all_gather_object(counts, int(n_mine))
+    k = max(1, int(round(16384 * n_mine / max(1, sum(counts)))))
     gathered = [None] * world
-    dist.all_gather_object(gathered, masses[:: max(1, len(masses) // 4096)].tolist())
+    dist.all_gather_object(gathered, masses[np.linspace(0, len(masses) - 1, k).astype(np.int64)].tolist() if len(masses) else [])
     allm = np.sort(np.concatenate([np.asarray(x) for x in gathered]))
     _, _, lo, hi = synth.synth_queries(allm, nq, 20240602)
 

@@ -214,6 +214,7 @@ struct dbi_handle {
   uint64_t uoff[kMaxRanks + 1] = {};      // global id of every rank's first unique peptide
   uint64_t uniq_cap[kMaxRanks] = {};      // layout capacity of every rank's window 2
   DevBuf mg_mass, mg_gpos, mg_prot, mg_len;  // local records between digest and exchange
+  DevBuf mg_nmod, mg_wtab;                   // their mod-site counts, and variants of a peptide with n sites
   uint64_t mg_n = 0;
   DevBuf mg_vkey, mg_vpay;                   // local groups / variants between listing and exchange
   uint64_t mg_v = 0;
@@ -406,6 +407,7 @@ void free_index(dbi_handle* h) {
   h->cmask_n = UINT64_MAX;
   h->k_mass.release(); h->k_gpos.release(); h->k_prot.release(); h->k_len.release();
   h->mg_mass.release(); h->mg_gpos.release(); h->mg_prot.release(); h->mg_len.release();
+  h->mg_nmod.release();
   h->mg_vkey.release(); h->mg_vpay.release();
   h->mg_n = h->mg_v = 0;
   h->mg_recv[0] = h->mg_recv[1] = 0;
@@ -1203,7 +1205,7 @@ int dbi_build(dbi_handle* h) {
     launch_digest_emit(h->d_res.as<uint8_t>(), h->res_end, h->res_alloc, h->d_tables.as<DevTables>(), h->cfg, 0,
                        (uint32_t)tiles, start_cnt.as<uint8_t>(), tile_offs.as<uint64_t>(), h->d_pstart.as<uint32_t>(),
                        n_prot, r_mass.as<uint64_t>(), r_gpos.as<uint32_t>(), r_prot.as<uint32_t>(),
-                       r_len.as<uint16_t>(), h->d_err.as<uint32_t>(), s);
+                       r_len.as<uint16_t>(), nullptr, h->d_err.as<uint32_t>(), s);
     h->st.algo_bytes[DBI_STAGE_DIGEST_EMIT] += 2ull * h->res_end + N * 18;
   }
   tile_counts.release();
@@ -1738,6 +1740,7 @@ void dbi_destroy(dbi_handle* h) {
   mg_release(h);
   h->d_raw.release();
   h->d_off.release();
+  h->mg_wtab.release();
   h->d_tables.release();
   h->d_err.release();
   cudaStreamSynchronize(h->stream);

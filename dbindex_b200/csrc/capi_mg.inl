@@ -356,12 +356,13 @@ int dbi_mg_digest(dbi_handle* h, uint64_t* n_records) {
   h->mg_gpos.alloc(N * 4, h->arena);
   h->mg_prot.alloc(N * 4, h->arena);
   h->mg_len.alloc(N * 2, h->arena);
+  if (h->cfg.max_mods > 0) h->mg_nmod.alloc(std::max<uint64_t>(N, 1), h->arena);
   {
     Stage sg(h, DBI_STAGE_DIGEST_EMIT);
     launch_digest_emit(h->d_res.as<uint8_t>(), h->res_end, h->res_alloc, h->d_tables.as<DevTables>(), h->cfg, t0, nt,
                        start_cnt.as<uint8_t>(), tile_offs.as<uint64_t>(), h->d_pstart.as<uint32_t>(), n_prot,
                        h->mg_mass.as<uint64_t>(), h->mg_gpos.as<uint32_t>(), h->mg_prot.as<uint32_t>(),
-                       h->mg_len.as<uint16_t>(), h->d_err.as<uint32_t>(), s);
+                       h->mg_len.as<uint16_t>(), h->mg_nmod.as<uint8_t>(), h->d_err.as<uint32_t>(), s);
     h->st.algo_bytes[DBI_STAGE_DIGEST_EMIT] += 2ull * nt * kDigestTile + N * 18;
   }
   DBI_CUDA(cudaStreamSynchronize(s));
@@ -382,13 +383,35 @@ int dbi_mg_hist(dbi_handle* h, int stage, void* d_hist, int* shift) {
   const KeySpace ks(h->p.min_mass, h->p.max_mass);
   const int sh = mg_shift(ks);
   if (stage == 0) {
-    launch_mg_hist(h->mg_mass.as<uint64_t>(), h->mg_n, ks.base_bits, sh, nullptr, 0, 0u, (unsigned long long*)d_hist,
-                   h->stream);
+    // weighted = variants the records will expand to (estimated from their mod-site counts: sum over k <= K
+    // of C(n, k)), plain = records: the cuts of exchange 0 are the cuts of the whole index, so they must
+    // anticipate the expansion
+    const uint32_t* wtab = nullptr;
+    if (h->cfg.max_mods > 0 && h->mg_nmod.p) {
+      if (!h->mg_wtab.p) {
+        uint32_t tab[256];
+        for (int n = 0; n < 256; ++n) {
+          uint64_t t = 0, c = 1;  // C(n, 0)
+          for (int k = 0; k <= h->cfg.max_mods; ++k) {
+            t += c;
+            c = c * (uint64_t)(n - k) / (uint64_t)(k + 1);
+            if (n - k <= 0) break;
+          }
+          tab[n] = (uint32_t)std::min<uint64_t>(t, 0xffffull);  // < 2^16: stays in the 32-bit shared bins
+        }
+        h->mg_wtab.alloc(sizeof(tab), h->arena);
+        DBI_CUDA(cudaMemcpyAsync(h->mg_wtab.p, tab, sizeof(tab), cudaMemcpyHostToDevice, h->stream));
+        DBI_CUDA(cudaStreamSynchronize(h->stream));
+      }
+      wtab = h->mg_wtab.as<uint32_t>();
+    }
+    launch_mg_hist(h->mg_mass.as<uint64_t>(), h->mg_n, ks.base_bits, sh, nullptr, 0, 0u, h->mg_nmod.as<uint8_t>(), wtab,
+                   (unsigned long long*)d_hist, h->stream);
   } else {  // group records: weigh by their variant count
     const bool weighted = h->cfg.n_seq > 0;
     // weighted = index entries the groups stand for, plain = groups; dbi_mg_plan turns both into a cost
     launch_mg_hist(h->mg_vkey.as<uint64_t>(), h->mg_v, 0, sh, weighted ? h->mg_vpay.as<uint64_t>() : nullptr,
-                   kGrpCntMask, 0u, (unsigned long long*)d_hist, h->stream);
+                   kGrpCntMask, 0u, nullptr, nullptr, (unsigned long long*)d_hist, h->stream);
   }
   if (shift) *shift = sh;
   DBI_CUDA(cudaStreamSynchronize(h->stream));  // the caller reduces d_hist on ITS stream next
@@ -467,20 +490,53 @@ int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_loc
 // The cost model of an exchange for dbi_mg_plan: measured on B200 (profiles/r02_scale_notes.md), in ps.
 // DBI_MG_COST="item,weight,hit" overrides the variant exchange's.
 void dbi_mg_default_cost(int stage, int has_mods, double* cost) {
-  if (stage == 0) {
-    cost[0] = 1.0; cost[1] = 0.0; cost[2] = 0.0;  // records: equal counts
-    if (!has_mods) { cost[0] = 300.0; cost[1] = 0.0; cost[2] = 0.0; }
+  if (stage == 0 && !has_mods) {
+    cost[0] = 1.0; cost[1] = 0.0; cost[2] = 0.0;  // records are the entries: equal counts
     return;
   }
-  cost[0] = 120.0;  // per group: 7 radix passes + expansion staging
-  cost[1] = 10.0;   // per entry: expansion write
-  cost[2] = 7.0;    // per expected hit of a 10 000-query batch at 10 ppm per build (70 ps per hit)
+  if (stage == 0) {
+    // The cuts of exchange 0 are the cuts of the whole index (the variant groups travel by the same cuts).
+    // per record: its own sort + merge (~300 ps) and the ~5 groups it will list (120 ps each: 7 radix passes,
+    // expansion staging); per estimated entry: expansion write; per expected hit (10 000 queries at 10 ppm per
+    // build, 70 ps each, x ~8 because the masses cluster inside a bin).
+    cost[0] = 900.0; cost[1] = 10.0; cost[2] = 60.0;
+  } else {
+    cost[0] = 120.0; cost[1] = 10.0; cost[2] = 60.0;  // exchange 1 alone (only used when it plans its own cuts)
+  }
   if (const char* e = std::getenv("DBI_MG_COST")) {
     double a, b2, c2;
     if (std::sscanf(e, "%lf,%lf,%lf", &a, &b2, &c2) == 3 && a >= 0 && b2 >= 0 && c2 >= 0 && a + b2 + c2 > 0) {
       cost[0] = a; cost[1] = b2; cost[2] = c2;
     }
   }
+}
+
+int dbi_mg_count(dbi_handle* h, int stage, const uint32_t* bin_splitters, uint64_t* send_counts) {
+  DBI_API_BEGIN(h)
+  const int W = h->mg_world;
+  if ((W > 1 && !bin_splitters) || !send_counts || (stage != 0 && stage != 1)) {
+    set_error("bad argument");
+    return DBI_EINVAL;
+  }
+  const KeySpace ks(h->p.min_mass, h->p.max_mass);
+  const int sh = mg_shift(ks);
+  MgPlan pl;
+  std::memset(&pl, 0, sizeof(pl));
+  pl.world = W;
+  for (int d = 0; d + 1 < W; ++d) pl.thr[d] = (uint64_t)bin_splitters[d] << sh;
+  DevBuf cnt;
+  cnt.alloc(kMaxRanks * 8, h->arena);
+  DBI_CUDA(cudaMemsetAsync(cnt.p, 0, kMaxRanks * 8, h->stream));
+  if (stage == 0)
+    launch_mg_count(h->mg_mass.as<uint64_t>(), h->mg_n, ks.base_bits, pl, (unsigned long long*)cnt.p, h->stream);
+  else
+    launch_mg_count(h->mg_vkey.as<uint64_t>(), h->mg_v, 0, pl, (unsigned long long*)cnt.p, h->stream);
+  uint64_t host[kMaxRanks];
+  DBI_CUDA(cudaMemcpyAsync(host, cnt.p, kMaxRanks * 8, cudaMemcpyDeviceToHost, h->stream));
+  DBI_CUDA(cudaStreamSynchronize(h->stream));
+  for (int d = 0; d < W; ++d) send_counts[d] = host[d];
+  return DBI_OK;
+  DBI_API_END
 }
 
 int dbi_mg_scatter(dbi_handle* h, int stage, const uint32_t* bin_splitters, const uint64_t* matrix) {
@@ -550,6 +606,7 @@ int dbi_mg_scatter(dbi_handle* h, int stage, const uint32_t* bin_splitters, cons
                               h->mg_len.as<uint16_t>(), n_local, ks.base_bits, pl, dst, tmp.p, s);
     h->st.algo_bytes[DBI_STAGE_OTHER] += n_local * 2 * 18;
     h->mg_mass.release(); h->mg_gpos.release(); h->mg_prot.release(); h->mg_len.release();
+    h->mg_nmod.release();
   } else {
     MgGrpDst dst;
     std::memset(&dst, 0, sizeof(dst));
@@ -749,28 +806,39 @@ int dbi_mg_build_local(dbi_handle** hs, int n) {
     const int C = mg_side_classes(hs[0]);
     std::vector<uint64_t> matrix((size_t)W * W), recv(W);
     std::vector<uint32_t> split(W);
+    // exchange 0 plans the cuts (histograms -> equal-cost splitters); exchange 1 reuses them, so the variant
+    // groups of a peptide mostly stay on the GPU that owns the peptide: only the counts are needed
     auto exchange = [&](int stage) -> int {
-      const size_t HB = 2 * kMgBins;
-      std::vector<uint64_t> local((size_t)W * HB), global(HB, 0);
-      int shift_of = 0;
-      for (int r = 0; r < W; ++r) {
-        dbi_handle* h = hs[r];
-        DBI_CUDA(cudaSetDevice(h->device));
-        DevBuf d;
-        d.alloc(HB * 8, h->arena);
-        DBI_CUDA(cudaMemsetAsync(d.p, 0, HB * 8, h->stream));
-        if (int rc = dbi_mg_hist(h, stage, d.p, &shift_of)) return rc;
-        DBI_CUDA(cudaMemcpyAsync(&local[(size_t)r * HB], d.p, HB * 8, cudaMemcpyDeviceToHost, h->stream));
-        DBI_CUDA(cudaStreamSynchronize(h->stream));
+      if (stage == 0) {
+        const size_t HB = 2 * kMgBins;
+        std::vector<uint64_t> local((size_t)W * HB), global(HB, 0);
+        int shift_of = 0;
+        for (int r = 0; r < W; ++r) {
+          dbi_handle* h = hs[r];
+          DBI_CUDA(cudaSetDevice(h->device));
+          DevBuf d;
+          d.alloc(HB * 8, h->arena);
+          DBI_CUDA(cudaMemsetAsync(d.p, 0, HB * 8, h->stream));
+          if (int rc = dbi_mg_hist(h, stage, d.p, &shift_of)) return rc;
+          DBI_CUDA(cudaMemcpyAsync(&local[(size_t)r * HB], d.p, HB * 8, cudaMemcpyDeviceToHost, h->stream));
+          DBI_CUDA(cudaStreamSynchronize(h->stream));
+        }
+        for (int r = 0; r < W; ++r)
+          for (size_t i = 0; i < HB; ++i) global[i] += local[(size_t)r * HB + i];
+        double cost[3];
+        dbi_mg_default_cost(stage, mods ? 1 : 0, cost);
+        for (int r = 0; r < W; ++r)
+          if (int rc = dbi_mg_plan(W, global.data(), &local[(size_t)r * HB], shift_of, hs[0]->p.min_mass, cost, split.data(),
+                                   &matrix[(size_t)r * W], recv.data()))
+            return rc;
+      } else {
+        for (int r = 0; r < W; ++r)
+          if (int rc = dbi_mg_count(hs[r], stage, split.data(), &matrix[(size_t)r * W])) return rc;
+        for (int d = 0; d < W; ++d) {
+          recv[d] = 0;
+          for (int r = 0; r < W; ++r) recv[d] += matrix[(size_t)r * W + d];
+        }
       }
-      for (int r = 0; r < W; ++r)
-        for (size_t i = 0; i < HB; ++i) global[i] += local[(size_t)r * HB + i];
-      double cost[3];
-      dbi_mg_default_cost(stage, mods ? 1 : 0, cost);
-      for (int r = 0; r < W; ++r)
-        if (int rc = dbi_mg_plan(W, global.data(), &local[(size_t)r * HB], shift_of, hs[0]->p.min_mass, cost, split.data(),
-                                 &matrix[(size_t)r * W], recv.data()))
-          return rc;
       for (int r = 0; r < W; ++r) {
         const uint64_t need = dbi_mg_layout_bytes(kWinArena, stage, recv[r], C);
         if (int rc = dbi_mg_window_ensure(hs[r], kWinArena, need, nullptr)) return rc;

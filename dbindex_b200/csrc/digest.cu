@@ -40,6 +40,7 @@ constexpr uint8_t I_COK = 4;    // C side of checkCleavage holds when the window
 constexpr uint8_t I_NOK = 8;    // N side of checkCleavage holds when the window STARTS here
 constexpr uint8_t I_MAND = 16;  // one of mandatoryInternalAAs
 constexpr uint8_t I_FILT = 32;  // the residue PeptideFilterByMaxOccurrencies counts
+constexpr uint8_t I_MOD = 64;   // a differential-mod site (sharded build: the cost estimate of a record)
 
 // ---- mbarrier + bulk copy (PTX; SASS: SYNCS.*, UBLKCP) --------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -76,7 +77,7 @@ __device__ __forceinline__ uint8_t raw_bits(uint8_t c, const DevTables* __restri
   if (c == 0) return I_SEP;
   const uint8_t f = __ldg(&tb->flags[c]);
   return (uint8_t)(((f & kFlagEnzyme) ? I_ENZ : 0) | ((f & kFlagNocut) ? 0x80 : 0) | ((f & kFlagMandatory) ? I_MAND : 0) |
-                   ((f & kFlagFilterAA) ? I_FILT : 0));
+                   ((f & kFlagFilterAA) ? I_FILT : 0) | ((f & kFlagDiffMod) ? I_MOD : 0));
 }
 // Enzyme.checkCleavage, one side each (contract of SURVEY.md 8c): the window may start at a
 // residue if it is the protein's first or follows an enzyme residue and is not a no-cut residue;
@@ -84,7 +85,7 @@ __device__ __forceinline__ uint8_t raw_bits(uint8_t c, const DevTables* __restri
 // no-cut residue.  (0x80 = raw no-cut bit, dropped from the stored byte.)
 __device__ __forceinline__ uint8_t compose_bits(uint8_t prev, uint8_t cur, uint8_t next) {
   if (cur & I_SEP) return I_SEP;
-  uint8_t o = cur & (I_ENZ | I_MAND | I_FILT);
+  uint8_t o = cur & (I_ENZ | I_MAND | I_FILT | I_MOD);
   if ((prev & I_SEP) || ((prev & I_ENZ) && !(cur & 0x80))) o |= I_NOK;
   if ((next & I_SEP) || ((cur & I_ENZ) && !(next & 0x80))) o |= I_COK;
   return o;
@@ -145,11 +146,13 @@ __device__ __forceinline__ uint32_t walk_start(const TileCtx& cx, uint32_t g, co
   int mc = -1;                  // intMisCleavageCount, :280
   int n_mand = 0;               // mandatory residues strictly before the current one
   int n_filt = 0;
+  uint32_t n_mod = 0;           // differential-mod sites of the window so far
   uint32_t len = 0, count = 0;
   uint32_t pos = g;
   while (mass <= cfg.max_mass && !(inf & I_SEP)) {  // :284  (end < length  <=>  not a separator)
     ++len;                                          // pepSize++, :285
     mass = __dadd_rn(mass, m);                      // precMass = precMass + aaMass, :308
+    n_mod += (inf >> 6) & 1;                        // I_MOD = 64
     if (FILTERS && (inf & I_FILT) && ++n_filt > cfg.filt_max && cfg.filt_max >= 0) break;  // peptideFilter.isValid, :310-313
     mc += (inf >> 1) & 1;                           // isEnzyme(cur) -> intMisCleavageCount++, :314-316 (I_ENZ = 2)
     if (cok_any || (inf & I_COK)) {                 // cleavageStatus, :318-320
@@ -166,7 +169,7 @@ __device__ __forceinline__ uint32_t walk_start(const TileCtx& cx, uint32_t g, co
             atomicOr(err, kErrPepTooLong);
             break;
           }
-          emit(mass, len);
+          emit(mass, len, n_mod);
           ++count;
         }
       }
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(DG_THREADS)
   uint32_t cnt = 0;
   for (uint32_t i = t; i < total; i += DG_THREADS) {
     const uint32_t l = s.list[i];
-    const uint32_t c = walk_start<FILTERS>(cx, w0 + 1 + l, cfg, err, [](double, uint32_t) {});
+    const uint32_t c = walk_start<FILTERS>(cx, w0 + 1 + l, cfg, err, [](double, uint32_t, uint32_t) {});
     s.cnt8[l] = (uint8_t)(c < 255u ? c : 255u);
     cnt += c;
   }
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(DG_THREADS)
                        const uint8_t* __restrict__ start_cnt, const uint64_t* __restrict__ tile_offs,
                        const uint32_t* __restrict__ pstart, uint32_t n_prot, uint64_t* __restrict__ o_mass,
                        uint32_t* __restrict__ o_gpos, uint32_t* __restrict__ o_prot, uint16_t* __restrict__ o_len,
-                       uint32_t* err) {
+                       uint8_t* __restrict__ o_nmod, uint32_t* err) {
   __shared__ TileSmem s;
   __shared__ uint32_t s_off[kDigestTile];   // first record of each emitting start (tile-local)
   __shared__ uint16_t s_zero[kDigestTile];  // separators between the tile's first start and this one
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(DG_THREADS)
 #pragma unroll
     for (int k = 0; k < DG_SPT; ++k) {
       c[k] = ((k < 4 ? packed.x : packed.y) >> (8 * (k & 3))) & 0xffu;
-      if (c[k] == 255u) c[k] = walk_start<FILTERS>(cx, w0 + 1 + t * DG_SPT + k, cfg, err, [](double, uint32_t) {});
+      if (c[k] == 255u) c[k] = walk_start<FILTERS>(cx, w0 + 1 + t * DG_SPT + k, cfg, err, [](double, uint32_t, uint32_t) {});
       n_emit += c[k] ? 1u : 0u;
       sum += c[k];
       if (s.info[1 + t * DG_SPT + k] & I_SEP) {
@@ -318,11 +321,12 @@ __global__ void __launch_bounds__(DG_THREADS)
     // protein of this start = separators at positions <= g, minus one
     const uint32_t prot = zbase + s_zero[i] - 1u;
     uint64_t o = tile_off + s_off[i];
-    walk_start<FILTERS>(cx, g, cfg, err, [&](double m, uint32_t len) {
+    walk_start<FILTERS>(cx, g, cfg, err, [&](double m, uint32_t len, uint32_t n_mod) {
       o_mass[o] = (uint64_t)__double_as_longlong(m);
       o_gpos[o] = g;
       o_prot[o] = prot;
       o_len[o] = (uint16_t)len;
+      if (o_nmod) o_nmod[o] = (uint8_t)(n_mod < 255u ? n_mod : 255u);
       ++o;
     });
   }
@@ -408,14 +412,15 @@ void launch_scan_u32_to_u64(const uint32_t* d_in, uint64_t n, uint64_t* d_offs, 
 void launch_digest_emit(const uint8_t* d_res, uint32_t res_end, uint64_t res_alloc, const DevTables* d_tb,
                         const DigestCfg& cfg, uint32_t tile0, uint32_t ntiles, const uint8_t* d_start_cnt,
                         const uint64_t* d_tile_offs, const uint32_t* d_pstart, uint32_t n_prot, uint64_t* o_mass,
-                        uint32_t* o_gpos, uint32_t* o_prot, uint16_t* o_len, uint32_t* d_err, cudaStream_t s) {
+                        uint32_t* o_gpos, uint32_t* o_prot, uint16_t* o_len, uint8_t* o_nmod, uint32_t* d_err,
+                        cudaStream_t s) {
   if (ntiles == 0) return;
   if (cfg.mand_on || cfg.filt_max >= 0)
     DBI_LAUNCH(digest_emit_kernel<true>, ntiles, DG_THREADS, 0, s, d_res, res_end, res_alloc, d_tb, cfg, tile0,
-               d_start_cnt, d_tile_offs, d_pstart, n_prot, o_mass, o_gpos, o_prot, o_len, d_err);
+               d_start_cnt, d_tile_offs, d_pstart, n_prot, o_mass, o_gpos, o_prot, o_len, o_nmod, d_err);
   else
     DBI_LAUNCH(digest_emit_kernel<false>, ntiles, DG_THREADS, 0, s, d_res, res_end, res_alloc, d_tb, cfg, tile0,
-               d_start_cnt, d_tile_offs, d_pstart, n_prot, o_mass, o_gpos, o_prot, o_len, d_err);
+               d_start_cnt, d_tile_offs, d_pstart, n_prot, o_mass, o_gpos, o_prot, o_len, o_nmod, d_err);
 }
 
 }  // namespace dbi

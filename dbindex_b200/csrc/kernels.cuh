@@ -54,10 +54,13 @@ void launch_scan_u32_to_u64(const uint32_t* d_in, uint64_t n, uint64_t* d_offs, 
 
 // K4: emit (mass bits, gpos, prot, len) in (protein, start, end) order.
 // (one walk per emitting start: the per-start counts of K2 replace the counting walk)
+// o_nmod (optional): differential-mod sites of every record, saturating at 255 -- the sharded build
+// estimates a record's downstream cost from it
 void launch_digest_emit(const uint8_t* d_res, uint32_t res_end, uint64_t res_alloc, const DevTables* d_tb,
                         const DigestCfg& cfg, uint32_t tile0, uint32_t ntiles, const uint8_t* d_start_cnt,
                         const uint64_t* d_tile_offs, const uint32_t* d_pstart, uint32_t n_prot, uint64_t* o_mass,
-                        uint32_t* o_gpos, uint32_t* o_prot, uint16_t* o_len, uint32_t* d_err, cudaStream_t s);
+                        uint32_t* o_gpos, uint32_t* o_prot, uint16_t* o_len, uint8_t* o_nmod, uint32_t* d_err,
+                        cudaStream_t s);
 
 // ---- sort helpers / K8 dedup -------------------------------------------------
 // hash[i] = seeded hash of the residues of record i (u32, or u64 when wide); idx[i] = i.
@@ -184,11 +187,6 @@ void launch_key_emit(const double* e_mass, uint64_t n, double factor, const uint
 
 // ---- multi-GPU exchange helpers (mg.cu) -----------------------------------------------------
 constexpr int kMgBins = 4096;  // histogram bins over the top bits of the radix key
-// hist[0 .. kMgBins) += weight, hist[kMgBins .. 2 kMgBins) += 1 over min(kMgBins-1, (key[i] - sub) >> shift)
-// (hist is zeroed by the caller); weight of item i = wpay ? (wpay[i] & wmask) + wadd : 1 (group records
-// carry their variant count; wadd = the per-group cost in entries).
-void launch_mg_hist(const uint64_t* key, uint64_t n, uint64_t sub, int shift, const uint64_t* wpay, uint64_t wmask,
-                    uint32_t wadd, unsigned long long* hist, cudaStream_t s);
 // Where the items of one exchange go.  dest(item) = number of thresholds <= (key - sub); this rank's
 // items for destination d arrive at rows row0[d] .. of d's arrays (after the items of the lower ranks).
 struct MgPlan {
@@ -196,6 +194,14 @@ struct MgPlan {
   uint64_t row0[kMaxRanks];
   int world;
 };
+// hist[0 .. kMgBins) += weight, hist[kMgBins .. 2 kMgBins) += 1 over min(kMgBins-1, (key[i] - sub) >> shift)
+// (hist is zeroed by the caller); weight of item i = wpay ? (wpay[i] & wmask) + wadd  (group records carry
+// their variant count)  :  wtab ? wtab[wcode[i]]  (records: variants of a peptide with wcode[i] mod sites)  :  1.
+void launch_mg_hist(const uint64_t* key, uint64_t n, uint64_t sub, int shift, const uint64_t* wpay, uint64_t wmask,
+                    uint32_t wadd, const uint8_t* wcode, const uint32_t* wtab, unsigned long long* hist, cudaStream_t s);
+// counts[d] += items whose destination is d (dest = number of thresholds <= key - sub); counts zeroed by the caller
+void launch_mg_count(const uint64_t* key, uint64_t n, uint64_t sub, const MgPlan& pl, unsigned long long* counts,
+                     cudaStream_t s);
 // destination arrays (mapped peer pointers; the own rank's are local)
 struct MgRecDst {
   uint64_t* mass[kMaxRanks];

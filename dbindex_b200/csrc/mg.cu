@@ -24,6 +24,7 @@ constexpr uint32_t kMgMaxItemsPerCta = 1u << 16;
 __global__ void __launch_bounds__(MG_THREADS)
     mg_hist_kernel(const uint64_t* __restrict__ key, uint64_t n, uint64_t per_cta, uint64_t sub, int shift,
                    const uint64_t* __restrict__ wpay, uint64_t wmask, uint32_t wadd,
+                   const uint8_t* __restrict__ wcode, const uint32_t* __restrict__ wtab,
                    unsigned long long* __restrict__ hist) {
   __shared__ uint32_t sh_w[kMgBins];
   __shared__ uint32_t sh_c[kMgBins];
@@ -37,7 +38,7 @@ __global__ void __launch_bounds__(MG_THREADS)
     uint64_t b = (key[i] - sub) >> shift;
     if (b >= kMgBins) b = kMgBins - 1;
     atomicAdd(&sh_c[b], 1u);
-    const uint64_t w = wpay ? (wpay[i] & wmask) + wadd : 1ull;
+    const uint64_t w = wpay ? (wpay[i] & wmask) + wadd : (wtab ? (uint64_t)__ldg(wtab + wcode[i]) : 1ull);
     if (w < (1ull << 16)) atomicAdd(&sh_w[b], (uint32_t)w);
     else atomicAdd(&hist[b], (unsigned long long)w);
   }
@@ -46,6 +47,32 @@ __global__ void __launch_bounds__(MG_THREADS)
     if (sh_w[i]) atomicAdd(&hist[i], (unsigned long long)sh_w[i]);
     if (sh_c[i]) atomicAdd(&hist[kMgBins + i], (unsigned long long)sh_c[i]);
   }
+}
+
+// items per destination for given thresholds (the variant exchange reuses the cuts of the record exchange,
+// so it needs no histogram: only how many groups cross each cut)
+__global__ void __launch_bounds__(MG_THREADS)
+    mg_count_kernel(const uint64_t* __restrict__ key, uint64_t n, uint64_t sub, const __grid_constant__ MgPlan pl,
+                    unsigned long long* __restrict__ counts) {
+  __shared__ uint32_t sh[kMaxRanks];
+  if (threadIdx.x < kMaxRanks) sh[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t mine[kMaxRanks];
+#pragma unroll
+  for (int d = 0; d < kMaxRanks; ++d) mine[d] = 0;
+  const uint64_t stride = (uint64_t)gridDim.x * MG_THREADS;
+  for (uint64_t i = (uint64_t)blockIdx.x * MG_THREADS + threadIdx.x; i < n; i += stride) {
+    const uint64_t k = key[i] - sub;
+    uint32_t d = 0;
+    for (int x = 0; x < pl.world - 1; ++x) d += (pl.thr[x] <= k) ? 1u : 0u;
+#pragma unroll
+    for (int x = 0; x < kMaxRanks; ++x) mine[x] += (d == (uint32_t)x) ? 1u : 0u;
+  }
+#pragma unroll
+  for (int d = 0; d < kMaxRanks; ++d)
+    if (mine[d]) atomicAdd(&sh[d], mine[d]);
+  __syncthreads();
+  if (threadIdx.x < kMaxRanks && sh[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
 }
 
 // ---- fused multisplit + all-to-all over peer memory ------------------------------------------
@@ -303,14 +330,23 @@ __global__ void __launch_bounds__(MG_THREADS)
 }  // namespace
 
 void launch_mg_hist(const uint64_t* key, uint64_t n, uint64_t sub, int shift, const uint64_t* wpay, uint64_t wmask,
-                    uint32_t wadd, unsigned long long* hist, cudaStream_t s) {
+                    uint32_t wadd, const uint8_t* wcode, const uint32_t* wtab, unsigned long long* hist, cudaStream_t s) {
   if (n == 0) return;
   uint64_t g = (uint64_t)kNumSMsB200 * 4;
   uint64_t per_cta = (n + g - 1) / g;
   if (per_cta > kMgMaxItemsPerCta) per_cta = kMgMaxItemsPerCta;
   per_cta = (per_cta + MG_THREADS - 1) / MG_THREADS * MG_THREADS;
   g = (n + per_cta - 1) / per_cta;
-  DBI_LAUNCH(mg_hist_kernel, (unsigned)g, MG_THREADS, 0, s, key, n, per_cta, sub, shift, wpay, wmask, wadd, hist);
+  DBI_LAUNCH(mg_hist_kernel, (unsigned)g, MG_THREADS, 0, s, key, n, per_cta, sub, shift, wpay, wmask, wadd, wcode, wtab,
+             hist);
+}
+
+void launch_mg_count(const uint64_t* key, uint64_t n, uint64_t sub, const MgPlan& pl, unsigned long long* counts,
+                     cudaStream_t s) {
+  if (n == 0) return;
+  uint64_t g = (n + MG_THREADS * 16 - 1) / (MG_THREADS * 16);
+  if (g > (uint64_t)kNumSMsB200 * 8) g = (uint64_t)kNumSMsB200 * 8;
+  DBI_LAUNCH(mg_count_kernel, (unsigned)g, MG_THREADS, 0, s, key, n, sub, pl, counts);
 }
 
 size_t mg_scatter_tmp_bytes(uint64_t n) {

@@ -9,18 +9,21 @@ touches (:333-343).  Here a bucket is a GPU:
      packs it into its place of the global residue buffer (window 0) and pulls the other shards over
      NVLink -- the FASTA crosses PCIe once, not once per GPU;
   2. every rank digests its share of the start positions;
-  3. exchange 0: weighted key histogram -> all-reduce -> equal-count splitters -> ONE kernel that
-     partitions the records and writes them straight into the owners' arenas (mapped peer memory);
-     rank-ordered arrival keeps "first occurrence" global (SURVEY.md Q6);
+  3. exchange 0: key histograms (records, and the variants they will expand to) -> all-reduce -> cuts of
+     equal estimated COST (sorting, expansion, expected query hits) -> ONE kernel that partitions the
+     records and writes them straight into the owners' arenas (mapped peer memory); rank-ordered arrival
+     keeps "first occurrence" global (SURVEY.md Q6);
   4. local sort + merge: every rank owns the unique peptides of its base-mass slice (window 2, mapped by
      the others: a hit whose base peptide lives elsewhere is read through the mapping);
-  5. differential mods: every rank lists the variant GROUPS of its own peptides; exchange 1 moves them,
-     with their site masks, to the owners of their VARIANT mass slices, which sort and expand them;
+  5. differential mods: every rank lists the variant GROUPS of its own peptides; exchange 1 moves the ones
+     whose variant mass crosses a cut (the SAME cuts: most groups stay where their peptide is), with their
+     site masks, to the owners of those slices, which sort and expand what they hold;
   6. queries are routed on the host with the splitter masses; a range that straddles a splitter is
      answered by both neighbours, exactly like Mult.getSequences walking two buckets.
 
-What crosses torch.distributed per exchange: one 64 KB all-reduce (the two histograms), one all-gather
-of ~350 bytes per rank (send counts, unique count, window descriptors) and one barrier.
+What crosses torch.distributed: exchange 0 -- one 64 KB all-reduce (the two histograms), one all-gather of
+~350 bytes per rank (send counts, unique count, window descriptors) and one barrier; exchange 1 -- the
+all-gather and the barrier only (it reuses the cuts of exchange 0).
 
 `ShardEngine` is the device side of one rank.  `GpuShardEngine` drives the C ABI (dbi_mg_*); the tests
 plug in a CPU engine so that the orchestration runs under gloo without a GPU.  A host that holds every
@@ -135,6 +138,7 @@ class ShardEngine:
     def pull_proteome(self): ...
     def digest(self) -> int: ...
     def hist(self, stage: int) -> Tuple[torch.Tensor, int]: ...   # (int64[2 * MG_BINS] on device, shift)
+    def count(self, stage: int, splitters: np.ndarray) -> np.ndarray: ...   # items per destination under the cuts
     def scatter(self, stage: int, splitters: np.ndarray, matrix: np.ndarray): ...
     def index_base(self): ...
     def n_unique(self) -> int: ...
@@ -175,19 +179,31 @@ def build_sharded(engine: ShardEngine) -> dict:
     engine.digest()
     lap("digest")
 
+    state = {"split": None, "shift": 0}
+
     def exchange(stage: int, item_bytes: int):
-        hist, shift = engine.hist(stage)
-        lap(f"hist{stage}.kernel")
-        local = hist.clone()
-        if world > 1:
-            dist.all_reduce(hist)
-        both = torch.stack([hist, local]).cpu().numpy().view(np.uint64)  # one D2H (the stage's first sync)
-        hg, hl = both[0], both[1]
-        lap(f"hist{stage}.reduce")
-        split, send, recv = plan_exchange(world, hg, hl, shift, engine.min_mass, stage, engine.has_mods)
-        lap(f"hist{stage}.plan")
-        d1 = engine.window(WIN_ARENA, engine.layout_bytes(WIN_ARENA, stage, int(recv[rank])))
-        d2 = engine.window(WIN_UNIQUE, engine.layout_bytes(WIN_UNIQUE, 0, int(recv[rank])) if stage == 0 else 0)
+        """Exchange 0 plans the cuts of the index (histograms -> all-reduce -> equal-cost splitters); exchange 1
+        reuses them -- a variant lies at most a few shifts above its peptide, so most groups stay on the GPU
+        that owns the peptide -- and only needs the counts of the groups that cross a cut."""
+        if stage == 0:
+            hist, shift = engine.hist(stage)
+            lap(f"hist{stage}.kernel")
+            local = hist.clone()
+            if world > 1:
+                dist.all_reduce(hist)
+            both = torch.stack([hist, local]).cpu().numpy().view(np.uint64)  # one D2H (the stage's first sync)
+            lap(f"hist{stage}.reduce")
+            split, send, recv = plan_exchange(world, both[0], both[1], shift, engine.min_mass, stage, engine.has_mods)
+            state["split"], state["shift"] = split, shift
+            recv_mine = int(recv[rank])
+            lap(f"hist{stage}.plan")
+        else:
+            split = state["split"]
+            send = engine.count(stage, split)
+            recv_mine = None  # known once every rank's counts are
+            lap(f"count{stage}")
+        d1 = engine.window(WIN_ARENA, engine.layout_bytes(WIN_ARENA, stage, recv_mine) if recv_mine is not None else 0)
+        d2 = engine.window(WIN_UNIQUE, engine.layout_bytes(WIN_UNIQUE, 0, recv_mine) if stage == 0 else 0)
         row = np.concatenate([send.view(np.uint8), np.array([engine.n_unique()], dtype=np.uint64).view(np.uint8), d1, d2])
         lap(f"plan{stage}.windows")
         rows = _all_gather_bytes(row, dev)  # every rank is past its previous use of the arenas
@@ -195,7 +211,16 @@ def build_sharded(engine: ShardEngine) -> dict:
         matrix = rows[:, :8 * world].copy().view(np.uint64).reshape(world, world)
         ru = rows[:, 8 * world:8 * world + 8].copy().view(np.uint64).reshape(world)
         o = 8 * world + 8
-        connect(WIN_ARENA, rows[:, o:o + DESC_BYTES])
+        arena_desc = rows[:, o:o + DESC_BYTES]
+        if stage == 1:
+            # the arenas were sized before the receive totals were known: every rank sees the same matrix and
+            # the same capacities, so all agree on whether somebody has to grow (rare after the first build)
+            need = [engine.layout_bytes(WIN_ARENA, stage, int(matrix[:, d].sum())) for d in range(world)]
+            caps = [int(arena_desc[d, 72:80].copy().view(np.uint64)[0]) for d in range(world)]  # dbi_mg_window.bytes
+            if any(n > c for n, c in zip(need, caps)):
+                d1 = engine.window(WIN_ARENA, need[rank])
+                arena_desc = _all_gather_bytes(d1, dev)
+        connect(WIN_ARENA, arena_desc)
         connect(WIN_UNIQUE, rows[:, o + DESC_BYTES:o + 2 * DESC_BYTES])
         if stage == 1:
             engine.set_unique(ru)
@@ -212,7 +237,7 @@ def build_sharded(engine: ShardEngine) -> dict:
         _barrier(dev)  # every rank's stores into this rank's arena are complete
         info["a2a_bytes"] += int(send.sum() - send[rank]) * item_bytes
         lap(f"scatter{stage}")
-        return split, shift
+        return split, state["shift"]
 
     base_split, shift = exchange(0, 18)
     engine.index_base()
@@ -269,6 +294,7 @@ class GpuShardEngine(ShardEngine):
             "dbi_mg_pull_proteome": (C.c_int, [vp]),
             "dbi_mg_digest": (C.c_int, [vp, u64p]),
             "dbi_mg_hist": (C.c_int, [vp, C.c_int, vp, C.POINTER(C.c_int)]),
+            "dbi_mg_count": (C.c_int, [vp, C.c_int, vp, vp]),
             "dbi_mg_scatter": (C.c_int, [vp, C.c_int, vp, vp]),
             "dbi_mg_index_base": (C.c_int, [vp]),
             "dbi_mg_unique_count": (C.c_int, [vp, u64p]),
@@ -332,6 +358,12 @@ class GpuShardEngine(ShardEngine):
         torch.cuda.current_stream().synchronize()
         self._ck(self.lib.dbi_mg_hist(self.g._h, stage, hist.data_ptr(), self.C.byref(shift)))
         return hist, shift.value
+
+    def count(self, stage, splitters):
+        sp = np.ascontiguousarray(splitters, dtype=np.uint32)
+        out = np.zeros(self.world, dtype=np.uint64)
+        self._ck(self.lib.dbi_mg_count(self.g._h, stage, sp.ctypes.data if len(sp) else None, out.ctypes.data))
+        return out
 
     def scatter(self, stage, splitters, matrix):
         sp = np.ascontiguousarray(splitters, dtype=np.uint32)

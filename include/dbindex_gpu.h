@@ -342,11 +342,12 @@ void dbi_fasta_close(dbi_fasta* f);
  *   dbi_mg_digest                         its share of the start positions
  *   dbi_mg_hist(0) .. [all-reduce] .. dbi_mg_plan .. dbi_mg_window_ensure(1, 2) .. [all-gather counts +
  *   windows] .. dbi_mg_window_import .. dbi_mg_scatter(0) .. [barrier]
- *   dbi_mg_index_base                     sort + merge of this rank's base-mass slice
+ *   dbi_mg_index_base                     sort + merge of this rank's mass slice
  *   [all-gather n_unique] dbi_mg_set_unique
  *   no mods:  dbi_mg_finish
- *   mods:     dbi_mg_groups -> dbi_mg_hist(1) .. dbi_mg_plan .. dbi_mg_scatter(1) .. [barrier] ->
- *             dbi_mg_index_variants -> dbi_mg_finish
+ *   mods:     dbi_mg_groups -> dbi_mg_count(1) [the SAME cuts: a variant lives at most 4 shifts above its
+ *             peptide, so most groups stay where their peptide is] .. [all-gather counts] ..
+ *             dbi_mg_window_ensure(1) .. dbi_mg_scatter(1) .. [barrier] -> dbi_mg_index_variants -> dbi_mg_finish
  *
  * Afterwards dbi_query / dbi_query_hits / dbi_fetch answer for the rank's slice; base peptides owned by
  * another rank are read through its mapped window 2.  Ranks are <= DBI_MG_MAX_RANKS (one NVSwitch box). */
@@ -390,6 +391,8 @@ int dbi_mg_hist(dbi_handle* h, int stage, void* d_hist, int* shift);
 int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_local, int shift, double min_mass,
                 const double* cost, uint32_t* bin_splitters, uint64_t* send_counts, uint64_t* recv_totals);
 void dbi_mg_default_cost(int stage, int has_mods, double* cost);
+/* items of exchange `stage` this rank would send to every rank under the given cuts [world] */
+int dbi_mg_count(dbi_handle* h, int stage, const uint32_t* bin_splitters, uint64_t* send_counts);
 /* matrix[s * world + d] = items rank s sends to rank d.  Stable multisplit of the local items straight
  * into the mapped arenas of their destinations; every rank's arena must have been ensured for its
  * receive total and imported here.  A barrier across the ranks must follow before anybody consumes. */

@@ -99,6 +99,11 @@ class OracleShardEngine(ShardEngine):
         plain = np.bincount(bins, minlength=MG_BINS).astype(np.int64)
         return torch.from_numpy(np.concatenate([plain, plain])), self.shift  # every item weighs 1 here
 
+    def count(self, stage, splitters):
+        thr = np.asarray(splitters, dtype=np.uint64) << np.uint64(self.shift)
+        dest = np.searchsorted(thr, self._keys(stage), side="right")
+        return np.bincount(dest, minlength=self.world).astype(np.uint64)
+
     def scatter(self, stage, splitters, matrix):
         thr = np.asarray(splitters, dtype=np.uint64) << np.uint64(self.shift)
         dest = np.searchsorted(thr, self._keys(stage), side="right")
