@@ -491,7 +491,7 @@ int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_loc
 // DBI_MG_COST="item,weight,hit" overrides the variant exchange's.
 void dbi_mg_default_cost(int stage, int has_mods, double* cost) {
   if (stage == 0 && !has_mods) {
-    cost[0] = 1.0; cost[1] = 0.0; cost[2] = 0.0;  // records are the entries: equal counts
+    cost[0] = 1.0; cost[1] = 0.0; cost[2] = 0.0;  // records are the entries (or exchange 1 plans its own cuts): equal counts
     return;
   }
   if (stage == 0) {
@@ -499,11 +499,11 @@ void dbi_mg_default_cost(int stage, int has_mods, double* cost) {
     // per record: its own sort + merge (~300 ps) and the ~5 groups it will list (120 ps each: 7 radix passes,
     // expansion staging); per estimated entry: expansion write; per expected hit (10 000 queries at 10 ppm per
     // build, 70 ps each, x ~8 because the masses cluster inside a bin).
-    cost[0] = 900.0; cost[1] = 10.0; cost[2] = 60.0;
+    cost[0] = 900.0; cost[1] = 10.0; cost[2] = 25.0;
   } else {
-    cost[0] = 120.0; cost[1] = 10.0; cost[2] = 60.0;  // exchange 1 alone (only used when it plans its own cuts)
+    cost[0] = 120.0; cost[1] = 10.0; cost[2] = 7.0;  // exchange 1 alone (only used when it plans its own cuts)
   }
-  if (const char* e = std::getenv("DBI_MG_COST")) {
+  if (const char* e = std::getenv(stage == 0 ? "DBI_MG_COST0" : "DBI_MG_COST")) {
     double a, b2, c2;
     if (std::sscanf(e, "%lf,%lf,%lf", &a, &b2, &c2) == 3 && a >= 0 && b2 >= 0 && c2 >= 0 && a + b2 + c2 > 0) {
       cost[0] = a; cost[1] = b2; cost[2] = c2;

@@ -31,6 +31,7 @@ handle in ONE process (the Java shim) calls dbi_mg_build_local instead of any of
 """
 from __future__ import annotations
 
+import os
 from typing import Tuple
 
 import numpy as np
@@ -180,12 +181,15 @@ def build_sharded(engine: ShardEngine) -> dict:
     lap("digest")
 
     state = {"split": None, "shift": 0}
+    # DBI_MG_UNIFIED=0: the variant exchange plans its own cuts (equal cost of the variant work alone; almost
+    # every group then leaves its rank).  Default: one set of cuts for the whole index.
+    unified = os.environ.get("DBI_MG_UNIFIED", "1") != "0"
 
     def exchange(stage: int, item_bytes: int):
         """Exchange 0 plans the cuts of the index (histograms -> all-reduce -> equal-cost splitters); exchange 1
         reuses them -- a variant lies at most a few shifts above its peptide, so most groups stay on the GPU
         that owns the peptide -- and only needs the counts of the groups that cross a cut."""
-        if stage == 0:
+        if stage == 0 or not unified:
             hist, shift = engine.hist(stage)
             lap(f"hist{stage}.kernel")
             local = hist.clone()
@@ -193,7 +197,8 @@ def build_sharded(engine: ShardEngine) -> dict:
                 dist.all_reduce(hist)
             both = torch.stack([hist, local]).cpu().numpy().view(np.uint64)  # one D2H (the stage's first sync)
             lap(f"hist{stage}.reduce")
-            split, send, recv = plan_exchange(world, both[0], both[1], shift, engine.min_mass, stage, engine.has_mods)
+            split, send, recv = plan_exchange(world, both[0], both[1], shift, engine.min_mass, stage,
+                                              engine.has_mods and unified)
             state["split"], state["shift"] = split, shift
             recv_mine = int(recv[rank])
             lap(f"hist{stage}.plan")
@@ -212,7 +217,7 @@ def build_sharded(engine: ShardEngine) -> dict:
         ru = rows[:, 8 * world:8 * world + 8].copy().view(np.uint64).reshape(world)
         o = 8 * world + 8
         arena_desc = rows[:, o:o + DESC_BYTES]
-        if stage == 1:
+        if stage == 1 and recv_mine is None:
             # the arenas were sized before the receive totals were known: every rank sees the same matrix and
             # the same capacities, so all agree on whether somebody has to grow (rare after the first build)
             need = [engine.layout_bytes(WIN_ARENA, stage, int(matrix[:, d].sum())) for d in range(world)]
