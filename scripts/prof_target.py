@@ -11,12 +11,13 @@ from dbindex_b200 import synth  # noqa: E402
 from bench import CFG2  # noqa: E402
 
 n_prot = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+n_builds = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 res, off = synth.config_proteome(2, n_prot)
 p = dbi.default_params(**CFG2)
 g = dbi.GpuIndex(p)
 g.add_proteins(res, off)
 g.upload()
-for _ in range(2):
+for _ in range(n_builds):
     g.reset_index()
     g.build()
 st = g.stats()
