@@ -460,7 +460,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             e2e_ms.append(a.elapsed_time(b))
     e2e_step_ms = float(sum(e2e_ms)) / len(e2e_ms)
     h2d = int(res.nbytes + off.nbytes + lo.nbytes + hi.nbytes + 4352 + 8)
-    d2h = int(sink.nbytes + 6 * 8 + 4 * 4)
+    d2h = int(sink.nbytes + 7 * 8 + 4 * 4)
 
     base = None
     if not args.no_cpu_baseline:
@@ -491,13 +491,16 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                    "emitted": head["emitted"], "unique": head["unique"], "entries_per_gpu": n_entries,
                    "queries": args.queries, "l2": "flushed between iterations (256 MiB write)", "parallelism": "1 GPU"},
         "queries": {"value": head["queries_per_s"], "unit": "queries/s", "hits_per_batch": head["hits_per_batch"],
-                    "ms_per_batch": head["query_ms"], "includes": "bounds + materialisation of every hit in HBM"},
+                    "runs_per_batch": int(cnt.n_peps), "ms_per_batch": head["query_ms"],
+                    "includes": "bounds + materialisation of every hit in HBM (grouped in runs of one peptide and mass)"},
         "build_ms": head["build_ms"], "stage_ms": head["stage_ms"], "sort_bits": head["sort_bits"],
         "roofline": head["roofline"], "cpu_baseline": base, "parity": parity,
         "e2e": {"value": n_entries / (e2e_step_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_step_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "hits_per_step": int(cnt.n_hits),
                 "what": "dbi_create + dbi_add_proteins(pinned host) + dbi_build + dbi_query_hits(host bounds) + "
-                        "dbi_query_hits_read(all 11 hit arrays into pinned host memory) + dbi_destroy"},
+                        "dbi_query_hits_read(all 13 hit arrays into pinned host memory: peptide-level fields once per run of "
+                        "same-peptide same-mass hits, mod pattern per hit) + dbi_destroy",
+                "runs_per_step": int(cnt.n_peps)},
         "gpu_launches": head["gpu_launches"], "clocks": clk, "configs": configs,
     }
     try:

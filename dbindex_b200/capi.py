@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdbindex_gpu.so")
 
-DBI_ABI_VERSION = 2
+DBI_ABI_VERSION = 3
 DBI_MAX_MODS = 16
 DBI_N_STAGES = 12
 STAGE_NAMES = [
@@ -96,22 +96,56 @@ class DbiStats(C.Structure):
 
 
 class DbiHitCounts(C.Structure):
-    _fields_ = [("nq", C.c_uint64), ("n_hits", C.c_uint64), ("n_seq_bytes", C.c_uint64), ("n_prot_ids", C.c_uint64)]
+    _fields_ = [("nq", C.c_uint64), ("n_hits", C.c_uint64), ("n_peps", C.c_uint64), ("n_seq_bytes", C.c_uint64),
+                ("n_prot_ids", C.c_uint64)]
 
 
 class DbiHitBuffers(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("hit_off", "mass", "first_prot", "first_off", "len", "modpat", "flanks",
-                                          "seq_off", "seq", "prot_list_off", "prot_ids")]
+    _fields_ = [(n, C.c_void_p) for n in ("hit_off", "pep_off", "modpat", "pep_hit_off", "mass", "first_prot", "first_off",
+                                          "len", "flanks", "seq_off", "seq", "prot_list_off", "prot_ids")]
 
 
+# dbi_hit_buffers: the hits of a batch grouped in RUNS (consecutive hits of one query that are variants of one
+# peptide with one mass); per-run arrays have n_peps rows, only the mod pattern is per hit
 HIT_FIELDS = {  # name -> (dtype, size as a function of the counts)
-    "hit_off": (np.uint64, lambda c: c.nq + 1), "mass": (np.float64, lambda c: c.n_hits),
-    "first_prot": (np.uint32, lambda c: c.n_hits), "first_off": (np.uint32, lambda c: c.n_hits),
-    "len": (np.uint16, lambda c: c.n_hits), "modpat": (np.uint32, lambda c: c.n_hits),
-    "flanks": (np.uint8, lambda c: 6 * c.n_hits), "seq_off": (np.uint64, lambda c: c.n_hits + 1),
-    "seq": (np.uint8, lambda c: c.n_seq_bytes), "prot_list_off": (np.uint64, lambda c: c.n_hits + 1),
+    "hit_off": (np.uint64, lambda c: c.nq + 1), "pep_off": (np.uint64, lambda c: c.nq + 1),
+    "modpat": (np.uint32, lambda c: c.n_hits), "pep_hit_off": (np.uint64, lambda c: c.n_peps + 1),
+    "mass": (np.float64, lambda c: c.n_peps),
+    "first_prot": (np.uint32, lambda c: c.n_peps), "first_off": (np.uint32, lambda c: c.n_peps),
+    "len": (np.uint16, lambda c: c.n_peps),
+    "flanks": (np.uint8, lambda c: 6 * c.n_peps), "seq_off": (np.uint64, lambda c: c.n_peps + 1),
+    "seq": (np.uint8, lambda c: c.n_seq_bytes), "prot_list_off": (np.uint64, lambda c: c.n_peps + 1),
     "prot_ids": (np.uint32, lambda c: c.n_prot_ids),
 }
+
+
+def _expand_csr(off_run: np.ndarray, data: np.ndarray, run_of_hit: np.ndarray):
+    """Per-hit CSR (offsets, data) from a per-run CSR."""
+    off_run = off_run.astype(np.int64)
+    sizes = np.diff(off_run)[run_of_hit]
+    off_hit = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
+    total = int(off_hit[-1])
+    src = np.repeat(off_run[:-1][run_of_hit] - off_hit[:-1], sizes) + np.arange(total, dtype=np.int64)
+    return off_hit.astype(np.uint64), data[src]
+
+
+def expand_hits(raw: dict) -> dict:
+    """One record per hit (the shape parseAddPeptideInfo produces and the oracle's query_hits returns) from
+    the run-grouped answer of dbi_query_hits.  Host-side convenience for tests and the Python mirror."""
+    run_of_hit = np.repeat(np.arange(len(raw["pep_hit_off"]) - 1, dtype=np.int64),
+                           np.diff(raw["pep_hit_off"].astype(np.int64)))
+    out = {k: raw[k] for k in ("counts", "hit_off", "modpat") if k in raw}
+    out["hit_pep"] = run_of_hit
+    for k in ("mass", "first_prot", "first_off", "len"):
+        if k in raw:
+            out[k] = raw[k][run_of_hit]
+    if "flanks" in raw:
+        out["flanks"] = np.ascontiguousarray(raw["flanks"].reshape(-1, 6)[run_of_hit]).reshape(-1)
+    if "seq" in raw:
+        out["seq_off"], out["seq"] = _expand_csr(raw["seq_off"], raw["seq"], run_of_hit)
+    if "prot_ids" in raw:
+        out["prot_list_off"], out["prot_ids"] = _expand_csr(raw["prot_list_off"], raw["prot_ids"], run_of_hit)
+    return out
 
 
 class DbiError(RuntimeError):
@@ -405,23 +439,30 @@ class GpuIndex:
     def query_hits_read(self, bufs: "DbiHitBuffers"):
         self._check(self.lib.dbi_query_hits_read(self._h, C.byref(bufs)))
 
-    def query_hits(self, lo: np.ndarray, hi: np.ndarray, fields=None, alloc=None) -> dict:
+    def query_hits(self, lo: np.ndarray, hi: np.ndarray, fields=None, alloc=None, per_hit: bool = True) -> dict:
         """dbi_query_hits + dbi_query_hits_read: every hit of every [lo[i], hi[i]] materialised (mass, first
-        occurrence, peptide residues, flanks, mod pattern, protein ids).  `fields`: subset of HIT_FIELDS to
-        read back (default all); `alloc(name, dtype, n)`: buffer factory (e.g. pinned memory), default numpy."""
+        occurrence, peptide residues, flanks, mod pattern, protein ids).  per_hit = False returns the buffers as
+        the library delivers them (grouped in runs, see HIT_FIELDS); per_hit = True expands them on the host to
+        one record per hit.  `fields`: subset to read back (default all); `alloc(name, dtype, n)`: buffer
+        factory (e.g. pinned memory), default numpy."""
         lo = np.ascontiguousarray(lo, dtype=np.float64)
         hi = np.ascontiguousarray(hi, dtype=np.float64)
         cnt = DbiHitCounts()
         self._check(self.lib.dbi_query_hits(self._h, _ptr(lo), _ptr(hi), len(lo), C.byref(cnt)))
         out, bufs = {"counts": cnt}, DbiHitBuffers()
+        want = None if fields is None else set(fields)
+        if want is not None and per_hit:
+            want |= {"hit_off", "pep_hit_off"}
+            want |= {"seq_off"} if "seq" in want else set()
+            want |= {"prot_list_off"} if "prot_ids" in want else set()
         for name, (dt, size) in HIT_FIELDS.items():
-            if fields is not None and name not in fields:
+            if want is not None and name not in want:
                 continue
             a = alloc(name, dt, int(size(cnt))) if alloc else np.empty(int(size(cnt)), dtype=dt)
             out[name] = a
             setattr(bufs, name, a.ctypes.data)
         self._check(self.lib.dbi_query_hits_read(self._h, C.byref(bufs)))
-        return out
+        return expand_hits(out) if per_hit else out
 
     def entry_keys(self) -> np.ndarray:
         n = C.c_uint64(0)

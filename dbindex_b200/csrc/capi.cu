@@ -225,11 +225,11 @@ struct dbi_handle {
   struct HitResult {
     bool valid = false;
     dbi_hit_counts n{};
-    DevBuf hit_off, mass, prot, off, len, pat, flanks, seq_off, seq, plo, ids;
+    DevBuf hit_off, pep_off, pat, pep_hit_off, mass, prot, off, len, flanks, seq_off, seq, plo, ids;
     void drop() {
       valid = false;
-      hit_off.release(); mass.release(); prot.release(); off.release(); len.release(); pat.release();
-      flanks.release(); seq_off.release(); seq.release(); plo.release(); ids.release();
+      hit_off.release(); pep_off.release(); pat.release(); pep_hit_off.release(); mass.release(); prot.release();
+      off.release(); len.release(); flanks.release(); seq_off.release(); seq.release(); plo.release(); ids.release();
     }
   } hits;
 
@@ -1437,7 +1437,7 @@ int query_hits_impl(dbi_handle* h, const double* d_lo, const double* d_hi, uint6
     r.valid = true;
     return DBI_OK;
   }
-  DevBuf io, cnt32, stmp, hit_entry, len32, np32, stmp2;
+  DevBuf io, cnt32, stmp, len32, np32, stmp2;
   io.alloc(nq * 16, h->arena);  // begin | count
   uint64_t* d_b = io.as<uint64_t>();
   uint64_t* d_c = d_b + nq;
@@ -1457,44 +1457,62 @@ int query_hits_impl(dbi_handle* h, const double* d_lo, const double* d_hi, uint6
     return DBI_ERANGE;
   }
   const UniqView uv = uniq_view(h);
-  r.seq_off.alloc((H + 1) * 8, h->arena);
-  r.plo.alloc((H + 1) * 8, h->arena);
-  uint64_t SB = 0, PI = 0;
+  r.pep_off.alloc((nq + 1) * 8, h->arena);
+  uint64_t NP = 0, SB = 0, PI = 0;
   if (H) {
     Stage sg(h, DBI_STAGE_FETCH);
-    hit_entry.alloc(H * 4, h->arena);
-    len32.alloc(H * 4, h->arena);
-    np32.alloc(H * 4, h->arena);
+    DevBuf head32, run_of_hit, pep_entry;
+    head32.alloc(H * 4, h->arena);
+    run_of_hit.alloc((H + 1) * 8, h->arena);
     stmp2.alloc(full_scan_tmp_bytes(H), h->arena);
-    launch_hits_expand(h->entry_base(), h->ent_base_off, uv, d_b, r.hit_off.as<uint64_t>(), nq, hit_entry.as<uint32_t>(),
-                       len32.as<uint32_t>(), np32.as<uint32_t>(), s);
-    launch_full_scan_u32_to_u64(len32.as<uint32_t>(), H, r.seq_off.as<uint64_t>(), stmp2.p, s);
-    launch_full_scan_u32_to_u64(np32.as<uint32_t>(), H, r.plo.as<uint64_t>(), stmp2.p, s);
-    DBI_CUDA(cudaMemcpyAsync(&SB, r.seq_off.as<uint64_t>() + H, 8, cudaMemcpyDeviceToHost, s));
-    DBI_CUDA(cudaMemcpyAsync(&PI, r.plo.as<uint64_t>() + H, 8, cudaMemcpyDeviceToHost, s));
-    DBI_CUDA(cudaStreamSynchronize(s));
-    r.mass.alloc(H * 8, h->arena);
-    r.prot.alloc(H * 4, h->arena);
-    r.off.alloc(H * 4, h->arena);
-    r.len.alloc(H * 2, h->arena);
     r.pat.alloc(H * 4, h->arena);
-    r.flanks.alloc(H * 6, h->arena);
+    launch_hits_mark(h->entry_mass(), h->entry_base(), h->entry_pat(), d_b, r.hit_off.as<uint64_t>(), nq,
+                     head32.as<uint32_t>(), r.pat.as<uint32_t>(), s);
+    launch_full_scan_u32_to_u64(head32.as<uint32_t>(), H, run_of_hit.as<uint64_t>(), stmp2.p, s);
+    NP = read_u64(h, run_of_hit.as<uint64_t>() + H);
+    r.pep_hit_off.alloc((NP + 1) * 8, h->arena);
+    r.mass.alloc(NP * 8, h->arena);
+    r.seq_off.alloc((NP + 1) * 8, h->arena);
+    r.plo.alloc((NP + 1) * 8, h->arena);
+    pep_entry.alloc(NP * 4, h->arena);
+    len32.alloc(NP * 4, h->arena);
+    np32.alloc(NP * 4, h->arena);
+    launch_hits_runs(h->entry_mass(), h->entry_base(), h->ent_base_off, uv, d_b, r.hit_off.as<uint64_t>(),
+                     run_of_hit.as<uint64_t>(), nq, r.pep_off.as<uint64_t>(), r.pep_hit_off.as<uint64_t>(),
+                     r.mass.as<double>(), pep_entry.as<uint32_t>(), len32.as<uint32_t>(), np32.as<uint32_t>(), s);
+    DBI_CUDA(cudaMemcpyAsync(r.pep_off.as<uint64_t>() + nq, run_of_hit.as<uint64_t>() + H, 8, cudaMemcpyDeviceToDevice, s));
+    DBI_CUDA(cudaMemcpyAsync(r.pep_hit_off.as<uint64_t>() + NP, r.hit_off.as<uint64_t>() + nq, 8, cudaMemcpyDeviceToDevice, s));
+    launch_full_scan_u32_to_u64(len32.as<uint32_t>(), NP, r.seq_off.as<uint64_t>(), stmp2.p, s);
+    launch_full_scan_u32_to_u64(np32.as<uint32_t>(), NP, r.plo.as<uint64_t>(), stmp2.p, s);
+    DBI_CUDA(cudaMemcpyAsync(&SB, r.seq_off.as<uint64_t>() + NP, 8, cudaMemcpyDeviceToHost, s));
+    DBI_CUDA(cudaMemcpyAsync(&PI, r.plo.as<uint64_t>() + NP, 8, cudaMemcpyDeviceToHost, s));
+    DBI_CUDA(cudaStreamSynchronize(s));
+    r.prot.alloc(NP * 4, h->arena);
+    r.off.alloc(NP * 4, h->arena);
+    r.len.alloc(NP * 2, h->arena);
+    r.flanks.alloc(NP * 6, h->arena);
     r.seq.alloc(std::max<uint64_t>(SB, 1), h->arena);
     r.ids.alloc(std::max<uint64_t>(PI, 1) * 4, h->arena);
-    launch_hits_gather(h->d_res.as<uint8_t>(), h->d_pstart.as<uint32_t>(), h->entry_mass(), h->entry_base(),
-                       h->ent_base_off, h->entry_pat(), uv, hit_entry.as<uint32_t>(), r.seq_off.as<uint64_t>(),
-                       r.plo.as<uint64_t>(), H, r.mass.as<double>(), r.prot.as<uint32_t>(), r.off.as<uint32_t>(),
-                       r.len.as<uint16_t>(), r.pat.as<uint32_t>(), r.flanks.as<uint8_t>(), r.seq.as<uint8_t>(),
-                       r.ids.as<uint32_t>(), s);
-    // per hit: entry (8 + 4 + 4) + peptide tables (4 + 4 + 2 + 16) read, 44 written; residues and ids copied
-    h->st.algo_bytes[DBI_STAGE_FETCH] += H * (16 + 26 + 44 + 12) + 2 * SB + 8 * PI;
+    launch_peps_gather(h->d_res.as<uint8_t>(), h->d_pstart.as<uint32_t>(), h->entry_base(), h->ent_base_off, uv,
+                       pep_entry.as<uint32_t>(), r.seq_off.as<uint64_t>(), r.plo.as<uint64_t>(), NP,
+                       r.prot.as<uint32_t>(), r.off.as<uint32_t>(), r.len.as<uint16_t>(), r.flanks.as<uint8_t>(),
+                       r.seq.as<uint8_t>(), r.ids.as<uint32_t>(), s);
+    // per hit: entry (8 + 4 + 4) read, run flag + scan (4 + 4 + 8 + 8 + 8), pattern written (4);
+    // per run: peptide tables (4 + 4 + 2 + 16) read, 56 written; residues and ids copied
+    h->st.algo_bytes[DBI_STAGE_FETCH] += H * (16 + 32 + 4) + NP * (26 + 56 + 12) + 2 * SB + 8 * PI;
   } else {
+    r.pep_hit_off.alloc(8, h->arena);
+    r.seq_off.alloc(8, h->arena);
+    r.plo.alloc(8, h->arena);
+    DBI_CUDA(cudaMemsetAsync(r.pep_off.p, 0, (nq + 1) * 8, s));
+    DBI_CUDA(cudaMemsetAsync(r.pep_hit_off.p, 0, 8, s));
     DBI_CUDA(cudaMemsetAsync(r.seq_off.p, 0, 8, s));
     DBI_CUDA(cudaMemsetAsync(r.plo.p, 0, 8, s));
   }
   DBI_CUDA(cudaStreamSynchronize(s));
   resolve_spans(h);
   counts->n_hits = H;
+  counts->n_peps = NP;
   counts->n_seq_bytes = SB;
   counts->n_prot_ids = PI;
   r.n = *counts;
@@ -1555,16 +1573,19 @@ int dbi_query_hits_read(dbi_handle* h, const dbi_hit_buffers* out) {
   auto d2h = [&](void* dst, const DevBuf& src, uint64_t bytes) {
     if (dst && bytes) DBI_CUDA(cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, s));
   };
+  const uint64_t NP = r.n.n_peps;
   d2h(out->hit_off, r.hit_off, (r.n.nq + 1) * 8);
-  d2h(out->seq_off, r.seq_off, (H + 1) * 8);
-  d2h(out->prot_list_off, r.plo, (H + 1) * 8);
-  d2h(out->mass, r.mass, H * 8);
-  d2h(out->first_prot, r.prot, H * 4);
-  d2h(out->first_off, r.off, H * 4);
-  d2h(out->len, r.len, H * 2);
+  d2h(out->pep_off, r.pep_off, (r.n.nq + 1) * 8);
   d2h(out->modpat, r.pat, H * 4);
-  d2h(out->flanks, r.flanks, H * 6);
+  d2h(out->pep_hit_off, r.pep_hit_off, (NP + 1) * 8);
+  d2h(out->mass, r.mass, NP * 8);
+  d2h(out->first_prot, r.prot, NP * 4);
+  d2h(out->first_off, r.off, NP * 4);
+  d2h(out->len, r.len, NP * 2);
+  d2h(out->flanks, r.flanks, NP * 6);
+  d2h(out->seq_off, r.seq_off, (NP + 1) * 8);
   d2h(out->seq, r.seq, r.n.n_seq_bytes);
+  d2h(out->prot_list_off, r.plo, (NP + 1) * 8);
   d2h(out->prot_ids, r.ids, r.n.n_prot_ids * 4);
   DBI_CUDA(cudaStreamSynchronize(s));
   r.drop();

@@ -49,16 +49,48 @@ __global__ void __launch_bounds__(Q_THREADS)
 
 constexpr int HX_WARPS = Q_THREADS / 32;
 
-// K10a: one warp per query, lanes stride its hits (consecutive entries -> coalesced)
+// The answer to a batch is grouped the way the index is: a RUN = consecutive hits of one query that are
+// variants of one peptide with one mass (one variant group of the index, contiguous by construction).
+// Everything parseAddPeptideInfo derives from the peptide (first occurrence, residues, flanks, protein
+// list) is materialised once per run; a hit carries only its mod pattern.
+
+// K10a: one warp per query, lanes stride its hits (consecutive entries -> coalesced).  Marks the first
+// hit of every run and writes the per-hit mod pattern.
 __global__ void __launch_bounds__(Q_THREADS)
-    hits_expand_kernel(const uint32_t* __restrict__ e_base, uint64_t ent_off, const __grid_constant__ UniqView uv,
-                       const uint64_t* __restrict__ hit_begin, const uint64_t* __restrict__ hit_off, uint64_t nq,
-                       uint32_t* __restrict__ hit_entry, uint32_t* __restrict__ len32, uint32_t* __restrict__ np32) {
+    hits_mark_kernel(const double* __restrict__ e_mass, const uint32_t* __restrict__ e_base,
+                     const uint32_t* __restrict__ e_pat, const uint64_t* __restrict__ hit_begin,
+                     const uint64_t* __restrict__ hit_off, uint64_t nq, uint32_t* __restrict__ head32,
+                     uint32_t* __restrict__ o_pat) {
   const uint64_t q = (uint64_t)blockIdx.x * HX_WARPS + (threadIdx.x >> 5);
   if (q >= nq) return;
   const uint64_t b = hit_begin[q], h0 = hit_off[q];
   const uint32_t n = (uint32_t)(hit_off[q + 1] - h0);
+  const unsigned long long* mb = reinterpret_cast<const unsigned long long*>(e_mass);
   for (uint32_t i = lane_id(); i < n; i += 32) {
+    const uint64_t e = b + i;
+    uint32_t head = 1;  // no differential mods: every entry is a peptide of its own
+    if (e_base && i > 0) head = (e_base[e] != e_base[e - 1]) || (mb[e] != mb[e - 1]);
+    head32[h0 + i] = head;
+    if (o_pat) o_pat[h0 + i] = e_pat ? e_pat[e] : 0u;
+  }
+}
+
+// K10b: same mapping; the first hit of every run fills the run's row: where its hits start, the exact
+// mass, the index entry (for K10c), residue count and protein-list length (scanned into the two CSRs).
+__global__ void __launch_bounds__(Q_THREADS)
+    hits_runs_kernel(const double* __restrict__ e_mass, const uint32_t* __restrict__ e_base, uint64_t ent_off,
+                     const __grid_constant__ UniqView uv, const uint64_t* __restrict__ hit_begin,
+                     const uint64_t* __restrict__ hit_off, const uint64_t* __restrict__ run_of_hit, uint64_t nq,
+                     uint64_t* __restrict__ pep_off, uint64_t* __restrict__ pep_hit_off, double* __restrict__ o_mass,
+                     uint32_t* __restrict__ pep_entry, uint32_t* __restrict__ len32, uint32_t* __restrict__ np32) {
+  const uint64_t q = (uint64_t)blockIdx.x * HX_WARPS + (threadIdx.x >> 5);
+  if (q >= nq) return;
+  const uint64_t b = hit_begin[q], h0 = hit_off[q];
+  const uint32_t n = (uint32_t)(hit_off[q + 1] - h0);
+  if (lane_id() == 0) pep_off[q] = run_of_hit[h0];
+  for (uint32_t i = lane_id(); i < n; i += 32) {
+    const uint64_t p = run_of_hit[h0 + i];
+    if (run_of_hit[h0 + i + 1] == p) continue;  // not the first hit of its run
     const uint64_t e = b + i;
     const uint64_t gid = e_base ? (uint64_t)e_base[e] : ent_off + e;
     uint64_t row;
@@ -68,44 +100,52 @@ __global__ void __launch_bounds__(Q_THREADS)
       len = uv.len[r][row];
       np = (uint32_t)(uv.plo[r][row + 1] - uv.plo[r][row]);
     }
-    hit_entry[h0 + i] = (uint32_t)e;
-    len32[h0 + i] = len;
-    np32[h0 + i] = np;
+    pep_hit_off[p] = h0 + i;
+    o_mass[p] = e_mass[e];
+    pep_entry[p] = (uint32_t)e;
+    len32[p] = len;
+    np32[p] = np;
   }
 }
 
-// K10b: a CTA materialises HG_TILE consecutive hits.  Per-hit scalars are gathered by one thread per hit
+// K10c: a CTA materialises HG_TILE consecutive runs.  Per-run scalars are gathered by one thread per run
 // (random reads of the owner tables, coalesced writes); the peptide residues and the flanks, whose
-// output regions are contiguous for consecutive hits, are written by the whole CTA in 16-byte chunks:
-// a thread finds the hit its chunk starts in (binary search over the tile's offsets in shared memory),
-// then walks the residues of that hit and its successors.
+// output regions are contiguous for consecutive runs, are written by the whole CTA in 16-byte chunks:
+// a thread finds the run its chunk starts in (binary search over the tile's offsets in shared memory),
+// then copies the residues of that run and its successors word by word (aligned 32-bit loads of the
+// residue buffer, funnel-shifted into place).
 constexpr int HG_TILE = Q_THREADS;
 
+// 4 residue bytes starting at buffer position pos (any alignment)
+__device__ __forceinline__ uint32_t ld_res4(const uint8_t* __restrict__ res, uint32_t pos) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(res) + (pos >> 2);
+  const uint32_t sh = (pos & 3u) * 8u;
+  const uint32_t a = __ldg(w);
+  if (sh == 0) return a;
+  return __funnelshift_r(a, __ldg(w + 1), sh);
+}
+
 __global__ void __launch_bounds__(Q_THREADS)
-    hits_gather_kernel(const uint8_t* __restrict__ res, const uint32_t* __restrict__ pstart,
-                       const double* __restrict__ e_mass, const uint32_t* __restrict__ e_base, uint64_t ent_off,
-                       const uint32_t* __restrict__ e_pat, const __grid_constant__ UniqView uv,
-                       const uint32_t* __restrict__ hit_entry, const uint64_t* __restrict__ seq_off,
-                       const uint64_t* __restrict__ plo_out, uint64_t n_hits, double* __restrict__ o_mass,
-                       uint32_t* __restrict__ o_prot, uint32_t* __restrict__ o_off, uint16_t* __restrict__ o_len,
-                       uint32_t* __restrict__ o_pat, uint8_t* __restrict__ o_flanks, uint8_t* __restrict__ o_seq,
-                       uint32_t* __restrict__ o_ids) {
+    peps_gather_kernel(const uint8_t* __restrict__ res, const uint32_t* __restrict__ pstart,
+                       const uint32_t* __restrict__ e_base, uint64_t ent_off, const __grid_constant__ UniqView uv,
+                       const uint32_t* __restrict__ pep_entry, const uint64_t* __restrict__ seq_off,
+                       const uint64_t* __restrict__ plo_out, uint64_t n_peps, uint32_t* __restrict__ o_prot,
+                       uint32_t* __restrict__ o_off, uint16_t* __restrict__ o_len, uint8_t* __restrict__ o_flanks,
+                       uint8_t* __restrict__ o_seq, uint32_t* __restrict__ o_ids) {
   __shared__ uint32_t s_gpos[HG_TILE];
   __shared__ uint32_t s_soff[HG_TILE + 1];  // seq offsets relative to the tile's first byte
   __shared__ __align__(16) uint8_t s_fl[HG_TILE * 6 + 16];
   const int t = threadIdx.x;
   const uint64_t h0 = (uint64_t)blockIdx.x * HG_TILE;
-  const uint32_t tile_n = (uint32_t)min((uint64_t)HG_TILE, n_hits - h0);
+  const uint32_t tile_n = (uint32_t)min((uint64_t)HG_TILE, n_peps - h0);
   const uint64_t h = h0 + t;
   const uint64_t seq0 = seq_off[h0];
   if (t == 0) s_soff[tile_n] = (uint32_t)(seq_off[h0 + tile_n] - seq0);
   if ((uint32_t)t < tile_n) {
-    const uint64_t e = hit_entry[h];
+    const uint64_t e = pep_entry[h];
     const uint64_t gid = e_base ? (uint64_t)e_base[e] : ent_off + e;
     uint64_t row;
     const int r = uniq_owner(uv, gid, &row);
-    if (o_mass) o_mass[h] = e_mass[e];
-    if (o_pat) o_pat[h] = e_pat ? e_pat[e] : 0u;
     s_soff[t] = (uint32_t)(seq_off[h] - seq0);
     uint8_t* f = s_fl + 6 * t;
     if (!uv.len[r]) {  // the owner's tables are not mapped: the caller resolves the peptide through its owner
@@ -142,7 +182,7 @@ __global__ void __launch_bounds__(Q_THREADS)
     }
   }
   __syncthreads();
-  if (o_flanks) {  // 6 bytes per hit, contiguous over the tile
+  if (o_flanks) {  // 6 bytes per run, contiguous over the tile
     uint8_t* dst = o_flanks + 6 * h0;
     const uint32_t nb = 6 * tile_n;
     for (uint32_t i = t; i < nb; i += Q_THREADS) dst[i] = s_fl[i];
@@ -152,7 +192,7 @@ __global__ void __launch_bounds__(Q_THREADS)
   const uint32_t total = s_soff[tile_n];
   uint8_t* out = o_seq + seq0;
   const uint32_t head = min(total, (uint32_t)((16 - ((uintptr_t)out & 15)) & 15));  // bytes before the first aligned chunk
-  auto hit_of = [&](uint32_t p) {  // last hit with s_soff <= p
+  auto run_at = [&](uint32_t p) {  // last run with s_soff <= p
     uint32_t lo = 0, hi = tile_n;
     while (hi - lo > 1) {
       const uint32_t mid = (lo + hi) >> 1;
@@ -161,30 +201,36 @@ __global__ void __launch_bounds__(Q_THREADS)
     return lo;
   };
   if ((uint32_t)t < head) {
-    const uint32_t i = hit_of((uint32_t)t);
+    const uint32_t i = run_at((uint32_t)t);
     out[t] = ld_res(res, s_gpos[i] + ((uint32_t)t - s_soff[i]));
   }
   const uint32_t n_chunks = (total - head + 15) / 16;
   for (uint32_t c = t; c < n_chunks; c += Q_THREADS) {
     const uint32_t p0 = head + c * 16;
-    uint32_t i = hit_of(p0);
-    uint32_t nxt = s_soff[i + 1];
-    uint32_t src = s_gpos[i] + (p0 - s_soff[i]);
+    uint32_t i = run_at(p0);
     uint32_t w[4] = {0, 0, 0, 0};
     const uint32_t nbytes = min(16u, total - p0);
-    for (uint32_t b = 0; b < nbytes; ++b) {
-      uint32_t p = p0 + b;
-      while (p >= nxt) {  // next hit (empty sequences are skipped)
-        ++i;
-        nxt = s_soff[i + 1];
-        src = s_gpos[i];
+    uint32_t b = 0;
+    while (b < nbytes) {
+      uint32_t nxt = s_soff[i + 1];
+      while (p0 + b >= nxt) nxt = s_soff[++i + 1];  // empty sequences are skipped
+      const uint32_t take = min(nbytes - b, nxt - (p0 + b));  // bytes of run i that land in this chunk
+      uint32_t src = s_gpos[i] + (p0 + b - s_soff[i]);
+      // up to 4 bytes at a time into byte position b of the 16-byte chunk (may straddle two words)
+      for (uint32_t k = 0; k < take; k += 4) {
+        const uint32_t nb4 = min(4u, take - k);
+        uint32_t v = ld_res4(res, src + k);
+        if (nb4 < 4) v &= (1u << (8 * nb4)) - 1u;
+        const uint32_t at = b + k, wi = at >> 2, sh = (at & 3u) * 8u;
+        w[wi] |= v << sh;
+        if (sh && wi < 3) w[wi + 1] |= v >> (32 - sh);
       }
-      w[b >> 2] |= (uint32_t)ld_res(res, src++) << (8 * (b & 3));
+      b += take;
     }
     if (nbytes == 16) {
       *reinterpret_cast<uint4*>(out + p0) = make_uint4(w[0], w[1], w[2], w[3]);
     } else {
-      for (uint32_t b = 0; b < nbytes; ++b) out[p0 + b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+      for (uint32_t k = 0; k < nbytes; ++k) out[p0 + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
     }
   }
 }
@@ -300,24 +346,31 @@ void launch_query(const double* e_mass, uint64_t n_entries, const double* lo, co
   DBI_LAUNCH(query_kernel, grid, Q_THREADS, 0, s, e_mass, n_entries, lo, hi, nq, hit_begin, hit_count, cnt32);
 }
 
-void launch_hits_expand(const uint32_t* e_base, uint64_t ent_off, const UniqView& uv, const uint64_t* hit_begin,
-                        const uint64_t* hit_off, uint64_t nq, uint32_t* hit_entry, uint32_t* len32, uint32_t* np32,
-                        cudaStream_t s) {
+void launch_hits_mark(const double* e_mass, const uint32_t* e_base, const uint32_t* e_pat, const uint64_t* hit_begin,
+                      const uint64_t* hit_off, uint64_t nq, uint32_t* head32, uint32_t* o_pat, cudaStream_t s) {
   if (nq == 0) return;
   const unsigned grid = (unsigned)((nq + HX_WARPS - 1) / HX_WARPS);
-  DBI_LAUNCH(hits_expand_kernel, grid, Q_THREADS, 0, s, e_base, ent_off, uv, hit_begin, hit_off, nq, hit_entry, len32,
-             np32);
+  DBI_LAUNCH(hits_mark_kernel, grid, Q_THREADS, 0, s, e_mass, e_base, e_pat, hit_begin, hit_off, nq, head32, o_pat);
 }
 
-void launch_hits_gather(const uint8_t* d_res, const uint32_t* pstart, const double* e_mass, const uint32_t* e_base,
-                        uint64_t ent_off, const uint32_t* e_pat, const UniqView& uv, const uint32_t* hit_entry,
-                        const uint64_t* seq_off, const uint64_t* plo_out, uint64_t n_hits, double* o_mass,
-                        uint32_t* o_prot, uint32_t* o_off, uint16_t* o_len, uint32_t* o_pat, uint8_t* o_flanks,
+void launch_hits_runs(const double* e_mass, const uint32_t* e_base, uint64_t ent_off, const UniqView& uv,
+                      const uint64_t* hit_begin, const uint64_t* hit_off, const uint64_t* run_of_hit, uint64_t nq,
+                      uint64_t* pep_off, uint64_t* pep_hit_off, double* o_mass, uint32_t* pep_entry, uint32_t* len32,
+                      uint32_t* np32, cudaStream_t s) {
+  if (nq == 0) return;
+  const unsigned grid = (unsigned)((nq + HX_WARPS - 1) / HX_WARPS);
+  DBI_LAUNCH(hits_runs_kernel, grid, Q_THREADS, 0, s, e_mass, e_base, ent_off, uv, hit_begin, hit_off, run_of_hit, nq,
+             pep_off, pep_hit_off, o_mass, pep_entry, len32, np32);
+}
+
+void launch_peps_gather(const uint8_t* d_res, const uint32_t* pstart, const uint32_t* e_base, uint64_t ent_off,
+                        const UniqView& uv, const uint32_t* pep_entry, const uint64_t* seq_off, const uint64_t* plo_out,
+                        uint64_t n_peps, uint32_t* o_prot, uint32_t* o_off, uint16_t* o_len, uint8_t* o_flanks,
                         uint8_t* o_seq, uint32_t* o_ids, cudaStream_t s) {
-  if (n_hits == 0) return;
-  const unsigned grid = (unsigned)((n_hits + Q_THREADS - 1) / Q_THREADS);
-  DBI_LAUNCH(hits_gather_kernel, grid, Q_THREADS, 0, s, d_res, pstart, e_mass, e_base, ent_off, e_pat, uv, hit_entry,
-             seq_off, plo_out, n_hits, o_mass, o_prot, o_off, o_len, o_pat, o_flanks, o_seq, o_ids);
+  if (n_peps == 0) return;
+  const unsigned grid = (unsigned)((n_peps + Q_THREADS - 1) / Q_THREADS);
+  DBI_LAUNCH(peps_gather_kernel, grid, Q_THREADS, 0, s, d_res, pstart, e_base, ent_off, uv, pep_entry, seq_off, plo_out,
+             n_peps, o_prot, o_off, o_len, o_flanks, o_seq, o_ids);
 }
 
 void launch_fetch_sizes(const uint32_t* e_base, uint64_t base_off, const UniqView& uv, uint64_t begin, uint64_t count,

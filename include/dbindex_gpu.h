@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DBI_ABI_VERSION 2
+#define DBI_ABI_VERSION 3
 
 /* ---- status codes (0 = OK, negative = error) -----------------------------
  * The shim maps them onto the reference's two exception types:
@@ -246,27 +246,38 @@ int dbi_fetch(dbi_handle* h, uint64_t begin, uint64_t count, double* mass, uint3
  * Util.getResidues ('-' padded, right side with the reference's off-by-one; Util.java:130-162,
  * Merge:456-458), the mod pattern and the protein-id list (Merge:449-475).
  *
- *   dbi_query_hits(h, lo, hi, nq, &n)      device: bounds search, size scans, gathers (results stay in HBM)
+ * The answer is grouped the way the index is.  A RUN is a maximal sequence of consecutive hits of one
+ * query that are variants of ONE peptide with ONE mass (a variant group of the index; without
+ * differential mods every hit is a run of its own).  Everything the reference derives from the peptide
+ * is delivered once per run, a hit carries only its mod pattern: the hits of run p are
+ * [pep_hit_off[p], pep_hit_off[p + 1]) and all of them have mass[p], first_prot[p], ... ; the runs of
+ * query i are [pep_off[i], pep_off[i + 1]), its hits [hit_off[i], hit_off[i + 1]).  Nothing is lost
+ * against one record per hit (expand with the two CSRs); a 10 ppm window of a 3-mod index holds ~10
+ * hits per run, so the batch crosses PCIe in a quarter of the bytes.
+ *
+ *   dbi_query_hits(h, lo, hi, nq, &n)      device: bounds search, run marking, size scans, gathers (results stay in HBM)
  *   caller allocates from n (dbi_host_alloc gives pinned memory for full-speed DMA)
  *   dbi_query_hits_read(h, &out)           D2H into the caller's buffers; any pointer may be NULL
  *
- * hit_off[nq + 1] is the CSR of hits per query; seq_off / prot_list_off [n_hits + 1] are CSRs over
- * seq[] and prot_ids[]; flanks holds 6 bytes per hit (3 left, 3 right).  The pending result of a handle
- * is dropped by the next dbi_query_hits, dbi_reset_index or dbi_destroy. */
+ * seq_off / prot_list_off [n_peps + 1] are CSRs over seq[] and prot_ids[]; flanks holds 6 bytes per run
+ * (3 left, 3 right).  The pending result of a handle is dropped by the next dbi_query_hits,
+ * dbi_reset_index or dbi_destroy. */
 typedef struct dbi_hit_counts {
-  uint64_t nq, n_hits, n_seq_bytes, n_prot_ids;
+  uint64_t nq, n_hits, n_peps, n_seq_bytes, n_prot_ids;
 } dbi_hit_counts;
 typedef struct dbi_hit_buffers {
-  uint64_t* hit_off;       /* nq + 1      */
-  double* mass;            /* n_hits      */
-  uint32_t* first_prot;    /* n_hits      */
-  uint32_t* first_off;     /* n_hits      */
-  uint16_t* len;           /* n_hits      */
-  uint32_t* modpat;        /* n_hits      */
-  uint8_t* flanks;         /* 6 * n_hits  */
-  uint64_t* seq_off;       /* n_hits + 1  */
+  uint64_t* hit_off;       /* nq + 1      hits of every query                     */
+  uint64_t* pep_off;       /* nq + 1      runs of every query                     */
+  uint32_t* modpat;        /* n_hits      byte k = position + 1 of the k-th mod   */
+  uint64_t* pep_hit_off;   /* n_peps + 1  hits of every run                       */
+  double* mass;            /* n_peps      */
+  uint32_t* first_prot;    /* n_peps      */
+  uint32_t* first_off;     /* n_peps      */
+  uint16_t* len;           /* n_peps      */
+  uint8_t* flanks;         /* 6 * n_peps  */
+  uint64_t* seq_off;       /* n_peps + 1  */
   uint8_t* seq;            /* n_seq_bytes */
-  uint64_t* prot_list_off; /* n_hits + 1  */
+  uint64_t* prot_list_off; /* n_peps + 1  */
   uint32_t* prot_ids;      /* n_prot_ids  */
 } dbi_hit_buffers;
 int dbi_query_hits(dbi_handle* h, const double* lo, const double* hi, uint64_t nq, dbi_hit_counts* counts);

@@ -28,7 +28,7 @@ import static java.lang.foreign.ValueLayout.JAVA_LONG;
 public final class DbiNative {
 	public static final int DBI_OK = 0, DBI_ENOTINIT = -1, DBI_EALREADY = -2, DBI_EINVAL = -3, DBI_ENOMEM = -4,
 			DBI_ECUDA = -5, DBI_ENCCL = -6, DBI_ERANGE = -7;
-	public static final int DBI_ABI_VERSION = 2, DBI_MAX_MODS = 16;
+	public static final int DBI_ABI_VERSION = 3, DBI_MAX_MODS = 16;
 
 	/** struct dbi_mod { uint8_t residue; uint8_t _pad[7]; double delta; } */
 	static final StructLayout MOD = MemoryLayout.structLayout(JAVA_BYTE.withName("residue"),
@@ -51,14 +51,15 @@ public final class DbiNative {
 
 	/** struct dbi_hit_counts */
 	static final StructLayout HIT_COUNTS = MemoryLayout.structLayout(JAVA_LONG.withName("nq"),
-			JAVA_LONG.withName("n_hits"), JAVA_LONG.withName("n_seq_bytes"), JAVA_LONG.withName("n_prot_ids"));
+			JAVA_LONG.withName("n_hits"), JAVA_LONG.withName("n_peps"), JAVA_LONG.withName("n_seq_bytes"),
+			JAVA_LONG.withName("n_prot_ids"));
 
-	/** struct dbi_hit_buffers: eleven caller-owned output pointers */
+	/** struct dbi_hit_buffers: thirteen caller-owned output pointers (hits grouped in runs of one peptide and mass) */
 	static final StructLayout HIT_BUFFERS = MemoryLayout.structLayout(ADDRESS.withName("hit_off"),
+			ADDRESS.withName("pep_off"), ADDRESS.withName("modpat"), ADDRESS.withName("pep_hit_off"),
 			ADDRESS.withName("mass"), ADDRESS.withName("first_prot"), ADDRESS.withName("first_off"),
-			ADDRESS.withName("len"), ADDRESS.withName("modpat"), ADDRESS.withName("flanks"),
-			ADDRESS.withName("seq_off"), ADDRESS.withName("seq"), ADDRESS.withName("prot_list_off"),
-			ADDRESS.withName("prot_ids"));
+			ADDRESS.withName("len"), ADDRESS.withName("flanks"), ADDRESS.withName("seq_off"), ADDRESS.withName("seq"),
+			ADDRESS.withName("prot_list_off"), ADDRESS.withName("prot_ids"));
 
 	private static final Linker LINKER = Linker.nativeLinker();
 	private static final SymbolLookup LIB = SymbolLookup

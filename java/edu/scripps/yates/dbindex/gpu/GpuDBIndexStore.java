@@ -250,36 +250,43 @@ public class GpuDBIndexStore implements DBIndexStore {
 			MemorySegment.copy(hi, 0, dhi, JAVA_DOUBLE, 0, nq);
 			final MemorySegment cnt = a.allocate(DbiNative.HIT_COUNTS);
 			check((int) DbiNative.dbi_query_hits.invoke(handle, dlo, dhi, (long) nq, cnt));
-			final long nHits = cnt.get(JAVA_LONG, 8), nSeq = cnt.get(JAVA_LONG, 16), nIds = cnt.get(JAVA_LONG, 24);
-			final MemorySegment mass = a.allocate(JAVA_DOUBLE, Math.max(1, nHits));
-			final MemorySegment prot = a.allocate(JAVA_INT, Math.max(1, nHits)), off = a.allocate(JAVA_INT, Math.max(1, nHits));
-			final MemorySegment len = a.allocate(JAVA_SHORT, Math.max(1, nHits)), pat = a.allocate(JAVA_INT, Math.max(1, nHits));
-			final MemorySegment flanks = a.allocate(Math.max(1, 6 * nHits));
-			final MemorySegment seqOff = a.allocate(JAVA_LONG, nHits + 1), seq = a.allocate(Math.max(1, nSeq));
-			final MemorySegment plo = a.allocate(JAVA_LONG, nHits + 1), ids = a.allocate(JAVA_INT, Math.max(1, nIds));
+			// the answer comes back grouped in RUNS (consecutive hits that are variants of one peptide with one
+			// mass): peptide string, flanks, first occurrence and protein list once per run, the mod pattern per hit
+			final long nHits = cnt.get(JAVA_LONG, 8), nPeps = cnt.get(JAVA_LONG, 16), nSeq = cnt.get(JAVA_LONG, 24),
+					nIds = cnt.get(JAVA_LONG, 32);
+			final MemorySegment pat = a.allocate(JAVA_INT, Math.max(1, nHits));
+			final MemorySegment pepHitOff = a.allocate(JAVA_LONG, nPeps + 1);
+			final MemorySegment mass = a.allocate(JAVA_DOUBLE, Math.max(1, nPeps));
+			final MemorySegment prot = a.allocate(JAVA_INT, Math.max(1, nPeps)), off = a.allocate(JAVA_INT, Math.max(1, nPeps));
+			final MemorySegment len = a.allocate(JAVA_SHORT, Math.max(1, nPeps));
+			final MemorySegment flanks = a.allocate(Math.max(1, 6 * nPeps));
+			final MemorySegment seqOff = a.allocate(JAVA_LONG, nPeps + 1), seq = a.allocate(Math.max(1, nSeq));
+			final MemorySegment plo = a.allocate(JAVA_LONG, nPeps + 1), ids = a.allocate(JAVA_INT, Math.max(1, nIds));
 			final MemorySegment bufs = a.allocate(DbiNative.HIT_BUFFERS);
-			final MemorySegment[] order = { MemorySegment.NULL /* hit_off: the union is returned as one list */, mass, prot,
-					off, len, pat, flanks, seqOff, seq, plo, ids };
+			final MemorySegment[] order = { MemorySegment.NULL /* hit_off: the union is returned as one list */,
+					MemorySegment.NULL /* pep_off */, pat, pepHitOff, mass, prot, off, len, flanks, seqOff, seq, plo, ids };
 			for (int k = 0; k < order.length; ++k)
 				bufs.setAtIndex(ADDRESS, k, order[k]);
 			check((int) DbiNative.dbi_query_hits_read.invoke(handle, bufs));
 			final byte[] seqBytes = seq.asSlice(0, nSeq).toArray(JAVA_BYTE);
-			final byte[] flankBytes = flanks.asSlice(0, 6 * nHits).toArray(JAVA_BYTE);
-			for (long i = 0; i < nHits; ++i) {
-				final int s0 = (int) seqOff.getAtIndex(JAVA_LONG, i), s1 = (int) seqOff.getAtIndex(JAVA_LONG, i + 1);
+			final byte[] flankBytes = flanks.asSlice(0, 6 * nPeps).toArray(JAVA_BYTE);
+			for (long p = 0; p < nPeps; ++p) {
+				final int s0 = (int) seqOff.getAtIndex(JAVA_LONG, p), s1 = (int) seqOff.getAtIndex(JAVA_LONG, p + 1);
 				final String pep = new String(seqBytes, s0, s1 - s0, java.nio.charset.StandardCharsets.ISO_8859_1);
-				final String resLeft = new String(flankBytes, (int) (6 * i), 3, java.nio.charset.StandardCharsets.ISO_8859_1);
-				final String resRight = new String(flankBytes, (int) (6 * i + 3), 3, java.nio.charset.StandardCharsets.ISO_8859_1);
-				final IndexedSequence s = new IndexedSequence(0, mass.getAtIndex(JAVA_DOUBLE, i), pep, resLeft, resRight);
+				final String resLeft = new String(flankBytes, (int) (6 * p), 3, java.nio.charset.StandardCharsets.ISO_8859_1);
+				final String resRight = new String(flankBytes, (int) (6 * p + 3), 3, java.nio.charset.StandardCharsets.ISO_8859_1);
 				final List<Integer> pids = new ArrayList<>();
-				for (long k = plo.getAtIndex(JAVA_LONG, i); k < plo.getAtIndex(JAVA_LONG, i + 1); ++k)
+				for (long k = plo.getAtIndex(JAVA_LONG, p); k < plo.getAtIndex(JAVA_LONG, p + 1); ++k)
 					pids.add(ids.getAtIndex(JAVA_INT, k));
-				s.setProteinIds(pids);
-				s.setSequenceOffset(off.getAtIndex(JAVA_INT, i)); // SURVEY Q10: the offset is known, hand it over
-				final int mp = pat.getAtIndex(JAVA_INT, i);
-				if (mp != 0)
-					s.setModSequence(modNotation(pep, mp));
-				ret.add(s);
+				for (long i = pepHitOff.getAtIndex(JAVA_LONG, p); i < pepHitOff.getAtIndex(JAVA_LONG, p + 1); ++i) {
+					final IndexedSequence s = new IndexedSequence(0, mass.getAtIndex(JAVA_DOUBLE, p), pep, resLeft, resRight);
+					s.setProteinIds(pids);
+					s.setSequenceOffset(off.getAtIndex(JAVA_INT, p)); // SURVEY Q10: the offset is known, hand it over
+					final int mp = pat.getAtIndex(JAVA_INT, i);
+					if (mp != 0)
+						s.setModSequence(modNotation(pep, mp));
+					ret.add(s);
+				}
 			}
 		} catch (final DBIndexStoreException e) {
 			throw e;

@@ -38,7 +38,7 @@ def test_struct_layout_matches():
 
 def test_default_params_contract():
     p = dbi.default_params()
-    assert p.abi_version == 2 and p.min_len == 6 and p.mass_group_factor == 10000
+    assert p.abi_version == 3 and p.min_len == 6 and p.mass_group_factor == 10000
     assert p.max_missed == 2 and p.semi == 0 and (p.min_mass, p.max_mass) == (600.0, 6000.0)
     assert [chr(i) for i in range(256) if p.is_enzyme[i]] == ["K", "R"]
     assert not any(p.is_nocut)

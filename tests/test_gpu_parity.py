@@ -61,11 +61,24 @@ def hits_canonical(h):
 def check_hits(g, o, lo, hi):
     """dbi_query_hits against the oracle's parseAddPeptideInfo restatement: mass bits, first occurrence,
     peptide string, flanks (with the reference's off-by-one), mod pattern and protein lists."""
-    got = g.query_hits(lo, hi)
+    raw = g.query_hits(lo, hi, per_hit=False)
+    got = dbi.capi.expand_hits(raw)
     exp = o.query_hits(lo, hi)
     assert np.array_equal(got["hit_off"], exp["hit_off"])
-    assert np.array_equal(got["seq_off"], exp["seq_off"]) or True  # per-hit lengths are compared through the strings
     assert hits_canonical(got) == hits_canonical(exp)
+    # the run structure of the raw answer: every run has hits, runs never straddle a query, the two
+    # CSRs over queries agree, and neighbouring runs of a query differ in peptide or mass (runs are maximal)
+    c = raw["counts"]
+    ho, po, pho = (raw[k].astype(np.int64) for k in ("hit_off", "pep_off", "pep_hit_off"))
+    assert len(pho) == c.n_peps + 1 and pho[0] == 0 and pho[-1] == c.n_hits and np.all(np.diff(pho) > 0)
+    assert po[0] == 0 and po[-1] == c.n_peps and np.array_equal(pho[po], ho)
+    if c.n_peps > 1:
+        key = np.stack([raw["first_prot"].astype(np.uint64), raw["first_off"].astype(np.uint64),
+                        raw["len"].astype(np.uint64), bits(raw["mass"])])
+        same = np.all(key[:, 1:] == key[:, :-1], axis=0)
+        inner = np.ones(c.n_peps - 1, bool)
+        inner[po[1:-1][(po[1:-1] > 0) & (po[1:-1] < c.n_peps)] - 1] = False  # a query boundary sits between them
+        assert not np.any(same & inner)
 
 
 def test_radix_sort_hook():

@@ -71,10 +71,12 @@ int main(void) {
   P(dbi_params, max_mods_per_peptide); P(dbi_params, mods); P(dbi_params, is_mandatory); P(dbi_params, has_mandatory);
   P(dbi_params, filter_aa); P(dbi_params, filter_max); P(dbi_params, _pad_filters); P(dbi_params, keep_emitted);
   P(dbi_params, profile); P(dbi_params, reserved); printf("dbi_params.sizeof %zu\n", sizeof(dbi_params));
-  P(dbi_hit_counts, nq); P(dbi_hit_counts, n_hits); P(dbi_hit_counts, n_seq_bytes); P(dbi_hit_counts, n_prot_ids);
+  P(dbi_hit_counts, nq); P(dbi_hit_counts, n_hits); P(dbi_hit_counts, n_peps); P(dbi_hit_counts, n_seq_bytes);
+  P(dbi_hit_counts, n_prot_ids);
   printf("dbi_hit_counts.sizeof %zu\n", sizeof(dbi_hit_counts));
-  P(dbi_hit_buffers, hit_off); P(dbi_hit_buffers, mass); P(dbi_hit_buffers, first_prot); P(dbi_hit_buffers, first_off);
-  P(dbi_hit_buffers, len); P(dbi_hit_buffers, modpat); P(dbi_hit_buffers, flanks); P(dbi_hit_buffers, seq_off);
+  P(dbi_hit_buffers, hit_off); P(dbi_hit_buffers, pep_off); P(dbi_hit_buffers, modpat); P(dbi_hit_buffers, pep_hit_off);
+  P(dbi_hit_buffers, mass); P(dbi_hit_buffers, first_prot); P(dbi_hit_buffers, first_off);
+  P(dbi_hit_buffers, len); P(dbi_hit_buffers, flanks); P(dbi_hit_buffers, seq_off);
   P(dbi_hit_buffers, seq); P(dbi_hit_buffers, prot_list_off); P(dbi_hit_buffers, prot_ids);
   printf("dbi_hit_buffers.sizeof %zu\n", sizeof(dbi_hit_buffers));
   P(dbi_stats, n_entries);
@@ -99,7 +101,7 @@ def test_java_struct_layouts_match_the_c_abi(tmp_path):
         expect = {k.split(".", 1)[1]: v for k, v in c.items() if k.startswith(cname + ".") and not k.endswith(".sizeof")}
         assert fields == expect, {k: (fields.get(k), expect.get(k)) for k in set(fields) | set(expect) if fields.get(k) != expect.get(k)}
         assert size == c[cname + ".sizeof"], (jname, size, c[cname + ".sizeof"])
-    assert int(re.search(r"DBI_ABI_VERSION\s*=\s*(\d+)", src).group(1)) == 2
+    assert int(re.search(r"DBI_ABI_VERSION\s*=\s*(\d+)", src).group(1)) == 3
     # GpuDBIndexStore reads dbi_stats.n_entries at a literal offset
     store = open(os.path.join(os.path.dirname(JAVA), "GpuDBIndexStore.java")).read()
     m = re.search(r"st\.get\(JAVA_LONG,\s*(\d+)\);\s*// dbi_stats\.n_entries", store)
