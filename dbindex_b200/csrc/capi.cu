@@ -1432,24 +1432,32 @@ int query_hits_impl(dbi_handle* h, const double* d_lo, const double* d_hi, uint6
   r.n = *counts;
   r.hit_off.alloc((nq + 1) * 8, h->arena);
   if (nq == 0) {
-    DBI_CUDA(cudaMemsetAsync(r.hit_off.p, 0, 8, s));
+    r.pep_off.alloc(8, h->arena); r.pep_hit_off.alloc(8, h->arena); r.seq_off.alloc(8, h->arena); r.plo.alloc(8, h->arena);
+    for (DevBuf* z : {&r.hit_off, &r.pep_off, &r.pep_hit_off, &r.seq_off, &r.plo}) DBI_CUDA(cudaMemsetAsync(z->p, 0, 8, s));
     DBI_CUDA(cudaStreamSynchronize(s));
     r.valid = true;
     return DBI_OK;
   }
-  DevBuf io, cnt32, stmp, len32, np32, stmp2;
+  DevBuf io, cnt32, stmp, len32, np32, stmp2, nseg32, seg_off;
   io.alloc(nq * 16, h->arena);  // begin | count
   uint64_t* d_b = io.as<uint64_t>();
   uint64_t* d_c = d_b + nq;
   cnt32.alloc(nq * 4, h->arena);
   stmp.alloc(full_scan_tmp_bytes(nq), h->arena);
-  uint64_t H = 0;
+  uint64_t H = 0, NS = 0;
   {
     Stage sg(h, DBI_STAGE_QUERY);
     launch_query(h->entry_mass(), h->n_entries, d_lo, d_hi, nq, d_b, d_c, cnt32.as<uint32_t>(), s);
     launch_full_scan_u32_to_u64(cnt32.as<uint32_t>(), nq, r.hit_off.as<uint64_t>(), stmp.p, s);
     h->st.algo_bytes[DBI_STAGE_QUERY] += nq * (32 + 2ull * 32 * (uint64_t)bit_length(h->n_entries));
-    H = read_u64(h, r.hit_off.as<uint64_t>() + nq);
+    // the hits of a query are materialised in segments of 256 (one warp each)
+    nseg32.alloc(nq * 4, h->arena);
+    seg_off.alloc((nq + 1) * 8, h->arena);
+    launch_hits_seg_count(d_c, nq, nseg32.as<uint32_t>(), s);
+    launch_full_scan_u32_to_u64(nseg32.as<uint32_t>(), nq, seg_off.as<uint64_t>(), stmp.p, s);
+    DBI_CUDA(cudaMemcpyAsync(&H, r.hit_off.as<uint64_t>() + nq, 8, cudaMemcpyDeviceToHost, s));
+    DBI_CUDA(cudaMemcpyAsync(&NS, seg_off.as<uint64_t>() + nq, 8, cudaMemcpyDeviceToHost, s));
+    DBI_CUDA(cudaStreamSynchronize(s));
   }
   if (H >= (1ull << 32)) {
     set_error("%llu hits in one batch: split the batch (< 2^32 hits per call)", (unsigned long long)H);
@@ -1461,15 +1469,18 @@ int query_hits_impl(dbi_handle* h, const double* d_lo, const double* d_hi, uint6
   uint64_t NP = 0, SB = 0, PI = 0;
   if (H) {
     Stage sg(h, DBI_STAGE_FETCH);
-    DevBuf head32, run_of_hit, pep_entry;
-    head32.alloc(H * 4, h->arena);
-    run_of_hit.alloc((H + 1) * 8, h->arena);
-    stmp2.alloc(full_scan_tmp_bytes(H), h->arena);
+    DevBuf seg_q, nruns32, seg_run_off, pep_entry, stmp3;
+    seg_q.alloc(NS * 4, h->arena);
+    nruns32.alloc(NS * 4, h->arena);
+    seg_run_off.alloc((NS + 1) * 8, h->arena);
+    stmp3.alloc(full_scan_tmp_bytes(NS), h->arena);
     r.pat.alloc(H * 4, h->arena);
-    launch_hits_mark(h->entry_mass(), h->entry_base(), h->entry_pat(), d_b, r.hit_off.as<uint64_t>(), nq,
-                     head32.as<uint32_t>(), r.pat.as<uint32_t>(), s);
-    launch_full_scan_u32_to_u64(head32.as<uint32_t>(), H, run_of_hit.as<uint64_t>(), stmp2.p, s);
-    NP = read_u64(h, run_of_hit.as<uint64_t>() + H);
+    launch_hits_seg_fill(seg_off.as<uint64_t>(), nq, seg_q.as<uint32_t>(), s);
+    launch_hits_count_runs(h->entry_mass(), h->entry_base(), seg_q.as<uint32_t>(), seg_off.as<uint64_t>(), d_b,
+                           r.hit_off.as<uint64_t>(), NS, nruns32.as<uint32_t>(), s);
+    launch_full_scan_u32_to_u64(nruns32.as<uint32_t>(), NS, seg_run_off.as<uint64_t>(), stmp3.p, s);
+    launch_hits_pep_off(seg_off.as<uint64_t>(), seg_run_off.as<uint64_t>(), nq, r.pep_off.as<uint64_t>(), s);
+    NP = read_u64(h, seg_run_off.as<uint64_t>() + NS);
     r.pep_hit_off.alloc((NP + 1) * 8, h->arena);
     r.mass.alloc(NP * 8, h->arena);
     r.seq_off.alloc((NP + 1) * 8, h->arena);
@@ -1477,10 +1488,11 @@ int query_hits_impl(dbi_handle* h, const double* d_lo, const double* d_hi, uint6
     pep_entry.alloc(NP * 4, h->arena);
     len32.alloc(NP * 4, h->arena);
     np32.alloc(NP * 4, h->arena);
-    launch_hits_runs(h->entry_mass(), h->entry_base(), h->ent_base_off, uv, d_b, r.hit_off.as<uint64_t>(),
-                     run_of_hit.as<uint64_t>(), nq, r.pep_off.as<uint64_t>(), r.pep_hit_off.as<uint64_t>(),
-                     r.mass.as<double>(), pep_entry.as<uint32_t>(), len32.as<uint32_t>(), np32.as<uint32_t>(), s);
-    DBI_CUDA(cudaMemcpyAsync(r.pep_off.as<uint64_t>() + nq, run_of_hit.as<uint64_t>() + H, 8, cudaMemcpyDeviceToDevice, s));
+    stmp2.alloc(full_scan_tmp_bytes(NP), h->arena);
+    launch_hits_runs(h->entry_mass(), h->entry_base(), h->ent_base_off, h->entry_pat(), uv, seg_q.as<uint32_t>(),
+                     seg_off.as<uint64_t>(), d_b, r.hit_off.as<uint64_t>(), seg_run_off.as<uint64_t>(), NS,
+                     r.pat.as<uint32_t>(), r.pep_hit_off.as<uint64_t>(), r.mass.as<double>(), pep_entry.as<uint32_t>(),
+                     len32.as<uint32_t>(), np32.as<uint32_t>(), s);
     DBI_CUDA(cudaMemcpyAsync(r.pep_hit_off.as<uint64_t>() + NP, r.hit_off.as<uint64_t>() + nq, 8, cudaMemcpyDeviceToDevice, s));
     launch_full_scan_u32_to_u64(len32.as<uint32_t>(), NP, r.seq_off.as<uint64_t>(), stmp2.p, s);
     launch_full_scan_u32_to_u64(np32.as<uint32_t>(), NP, r.plo.as<uint64_t>(), stmp2.p, s);
@@ -1497,9 +1509,9 @@ int query_hits_impl(dbi_handle* h, const double* d_lo, const double* d_hi, uint6
                        pep_entry.as<uint32_t>(), r.seq_off.as<uint64_t>(), r.plo.as<uint64_t>(), NP,
                        r.prot.as<uint32_t>(), r.off.as<uint32_t>(), r.len.as<uint16_t>(), r.flanks.as<uint8_t>(),
                        r.seq.as<uint8_t>(), r.ids.as<uint32_t>(), s);
-    // per hit: entry (8 + 4 + 4) read, run flag + scan (4 + 4 + 8 + 8 + 8), pattern written (4);
-    // per run: peptide tables (4 + 4 + 2 + 16) read, 56 written; residues and ids copied
-    h->st.algo_bytes[DBI_STAGE_FETCH] += H * (16 + 32 + 4) + NP * (26 + 56 + 12) + 2 * SB + 8 * PI;
+    // per hit: entry read twice (12 + 16), pattern written (4); per run: peptide tables (4 + 4 + 2 + 16)
+    // read, 56 written; residues and ids copied
+    h->st.algo_bytes[DBI_STAGE_FETCH] += H * (28 + 4) + NP * (26 + 56 + 12) + 2 * SB + 8 * PI;
   } else {
     r.pep_hit_off.alloc(8, h->arena);
     r.seq_off.alloc(8, h->arena);

@@ -157,15 +157,23 @@ void launch_query(const double* e_mass, uint64_t n_entries, const double* lo, co
                   uint64_t* hit_begin, uint64_t* hit_count, uint32_t* cnt32, cudaStream_t s);
 
 // K10a-c: the hits of a query batch grouped in RUNS (consecutive hits of one query that are variants of
-// one peptide with one mass).  hit_off = exclusive scan of the hit counts; head32[h] = 1 on the first hit
-// of a run; run_of_hit = exclusive scan of head32 (H + 1 values); what parseAddPeptideInfo materialises
+// one peptide with one mass).  hit_off = exclusive scan of the hit counts; pep_off = runs before every
+// query; what parseAddPeptideInfo materialises
 // (DBIndexStoreSQLiteByteIndexMerge.java:386-481) is written once per run, the mod pattern per hit.
-void launch_hits_mark(const double* e_mass, const uint32_t* e_base, const uint32_t* e_pat, const uint64_t* hit_begin,
-                      const uint64_t* hit_off, uint64_t nq, uint32_t* head32, uint32_t* o_pat, cudaStream_t s);
-void launch_hits_runs(const double* e_mass, const uint32_t* e_base, uint64_t ent_off, const UniqView& uv,
-                      const uint64_t* hit_begin, const uint64_t* hit_off, const uint64_t* run_of_hit, uint64_t nq,
-                      uint64_t* pep_off, uint64_t* pep_hit_off, double* o_mass, uint32_t* pep_entry, uint32_t* len32,
-                      uint32_t* np32, cudaStream_t s);
+// (a query's hits are cut into segments of 256, one warp each: seg_off = scan of the segment counts,
+// seg_q[s] = query of segment s, seg_run_off = scan of the runs that start in every segment)
+void launch_hits_seg_count(const uint64_t* hit_count, uint64_t nq, uint32_t* nseg32, cudaStream_t s);
+void launch_hits_seg_fill(const uint64_t* seg_off, uint64_t nq, uint32_t* seg_q, cudaStream_t s);
+void launch_hits_count_runs(const double* e_mass, const uint32_t* e_base, const uint32_t* seg_q, const uint64_t* seg_off,
+                            const uint64_t* hit_begin, const uint64_t* hit_off, uint64_t nseg, uint32_t* nruns32,
+                            cudaStream_t s);
+void launch_hits_pep_off(const uint64_t* seg_off, const uint64_t* seg_run_off, uint64_t nq, uint64_t* pep_off,
+                         cudaStream_t s);
+void launch_hits_runs(const double* e_mass, const uint32_t* e_base, uint64_t ent_off, const uint32_t* e_pat,
+                      const UniqView& uv, const uint32_t* seg_q, const uint64_t* seg_off, const uint64_t* hit_begin,
+                      const uint64_t* hit_off, const uint64_t* seg_run_off, uint64_t nseg, uint32_t* o_pat,
+                      uint64_t* pep_hit_off, double* o_mass, uint32_t* pep_entry, uint32_t* len32, uint32_t* np32,
+                      cudaStream_t s);
 void launch_peps_gather(const uint8_t* d_res, const uint32_t* pstart, const uint32_t* e_base, uint64_t ent_off,
                         const UniqView& uv, const uint32_t* pep_entry, const uint64_t* seq_off, const uint64_t* plo_out,
                         uint64_t n_peps, uint32_t* o_prot, uint32_t* o_off, uint16_t* o_len, uint8_t* o_flanks,

@@ -48,63 +48,125 @@ __global__ void __launch_bounds__(Q_THREADS)
 }
 
 constexpr int HX_WARPS = Q_THREADS / 32;
+constexpr uint32_t HX_SEG = 256;  // hits per warp
 
 // The answer to a batch is grouped the way the index is: a RUN = consecutive hits of one query that are
 // variants of one peptide with one mass (one variant group of the index, contiguous by construction).
 // Everything parseAddPeptideInfo derives from the peptide (first occurrence, residues, flanks, protein
 // list) is materialised once per run; a hit carries only its mod pattern.
 
-// K10a: one warp per query, lanes stride its hits (consecutive entries -> coalesced).  Marks the first
-// hit of every run and writes the per-hit mod pattern.
-__global__ void __launch_bounds__(Q_THREADS)
-    hits_mark_kernel(const double* __restrict__ e_mass, const uint32_t* __restrict__ e_base,
-                     const uint32_t* __restrict__ e_pat, const uint64_t* __restrict__ hit_begin,
-                     const uint64_t* __restrict__ hit_off, uint64_t nq, uint32_t* __restrict__ head32,
-                     uint32_t* __restrict__ o_pat) {
-  const uint64_t q = (uint64_t)blockIdx.x * HX_WARPS + (threadIdx.x >> 5);
-  if (q >= nq) return;
-  const uint64_t b = hit_begin[q], h0 = hit_off[q];
-  const uint32_t n = (uint32_t)(hit_off[q + 1] - h0);
-  const unsigned long long* mb = reinterpret_cast<const unsigned long long*>(e_mass);
-  for (uint32_t i = lane_id(); i < n; i += 32) {
-    const uint64_t e = b + i;
-    uint32_t head = 1;  // no differential mods: every entry is a peptide of its own
-    if (e_base && i > 0) head = (e_base[e] != e_base[e - 1]) || (mb[e] != mb[e - 1]);
-    head32[h0 + i] = head;
-    if (o_pat) o_pat[h0 + i] = e_pat ? e_pat[e] : 0u;
-  }
+// first hit of a run?  (hit i of a query that starts at entry b; no differential mods: every entry is a
+// peptide of its own)
+__device__ __forceinline__ bool run_head(const unsigned long long* __restrict__ mass_bits,
+                                         const uint32_t* __restrict__ e_base, uint64_t e, uint32_t i) {
+  if (!e_base || i == 0) return true;
+  return e_base[e] != e_base[e - 1] || mass_bits[e] != mass_bits[e - 1];
 }
 
-// K10b: same mapping; the first hit of every run fills the run's row: where its hits start, the exact
-// mass, the index entry (for K10c), residue count and protein-list length (scanned into the two CSRs).
+// The hits of a query are processed in SEGMENTS of HX_SEG consecutive hits, one warp each, so that a
+// +-3 Da window with 10^5 hits and a 10 ppm window with 50 spread over the machine alike.
+// seg_off = exclusive scan of ceil(count / HX_SEG) over the queries.
 __global__ void __launch_bounds__(Q_THREADS)
-    hits_runs_kernel(const double* __restrict__ e_mass, const uint32_t* __restrict__ e_base, uint64_t ent_off,
-                     const __grid_constant__ UniqView uv, const uint64_t* __restrict__ hit_begin,
-                     const uint64_t* __restrict__ hit_off, const uint64_t* __restrict__ run_of_hit, uint64_t nq,
-                     uint64_t* __restrict__ pep_off, uint64_t* __restrict__ pep_hit_off, double* __restrict__ o_mass,
-                     uint32_t* __restrict__ pep_entry, uint32_t* __restrict__ len32, uint32_t* __restrict__ np32) {
+    hits_seg_count_kernel(const uint64_t* __restrict__ hit_count, uint64_t nq, uint32_t* __restrict__ nseg32) {
+  const uint64_t q = (uint64_t)blockIdx.x * Q_THREADS + threadIdx.x;
+  if (q < nq) nseg32[q] = (uint32_t)((hit_count[q] + HX_SEG - 1) / HX_SEG);
+}
+
+__global__ void __launch_bounds__(Q_THREADS)
+    hits_seg_fill_kernel(const uint64_t* __restrict__ seg_off, uint64_t nq, uint32_t* __restrict__ seg_q) {
   const uint64_t q = (uint64_t)blockIdx.x * HX_WARPS + (threadIdx.x >> 5);
   if (q >= nq) return;
-  const uint64_t b = hit_begin[q], h0 = hit_off[q];
-  const uint32_t n = (uint32_t)(hit_off[q + 1] - h0);
-  if (lane_id() == 0) pep_off[q] = run_of_hit[h0];
-  for (uint32_t i = lane_id(); i < n; i += 32) {
-    const uint64_t p = run_of_hit[h0 + i];
-    if (run_of_hit[h0 + i + 1] == p) continue;  // not the first hit of its run
-    const uint64_t e = b + i;
-    const uint64_t gid = e_base ? (uint64_t)e_base[e] : ent_off + e;
-    uint64_t row;
-    const int r = uniq_owner(uv, gid, &row);
-    uint32_t len = 0, np = 0;
-    if (uv.len[r]) {
-      len = uv.len[r][row];
-      np = (uint32_t)(uv.plo[r][row + 1] - uv.plo[r][row]);
+  const uint64_t s0 = seg_off[q], s1 = seg_off[q + 1];
+  for (uint64_t s = s0 + lane_id(); s < s1; s += 32) seg_q[s] = (uint32_t)q;
+}
+
+struct HitSeg {
+  uint64_t b;    // index entry of the segment's first hit
+  uint64_t h0;   // its position in the batch's hit list
+  uint32_t i0;   // its rank inside its query
+  uint32_t n;    // hits in the segment
+};
+__device__ __forceinline__ HitSeg hit_segment(uint64_t s, const uint32_t* __restrict__ seg_q,
+                                              const uint64_t* __restrict__ seg_off,
+                                              const uint64_t* __restrict__ hit_begin,
+                                              const uint64_t* __restrict__ hit_off) {
+  const uint32_t q = seg_q[s];
+  const uint64_t k = s - seg_off[q];
+  const uint64_t hq = hit_off[q], nq_hits = hit_off[q + 1] - hq;
+  HitSeg g;
+  g.i0 = (uint32_t)(k * HX_SEG);
+  g.n = (uint32_t)min((uint64_t)HX_SEG, nq_hits - g.i0);
+  g.b = hit_begin[q] + g.i0;
+  g.h0 = hq + g.i0;
+  return g;
+}
+
+// K10a: one warp per segment, lanes stride its hits (consecutive entries -> coalesced): runs that START
+// in the segment.
+__global__ void __launch_bounds__(Q_THREADS)
+    hits_count_runs_kernel(const double* __restrict__ e_mass, const uint32_t* __restrict__ e_base,
+                           const uint32_t* __restrict__ seg_q, const uint64_t* __restrict__ seg_off,
+                           const uint64_t* __restrict__ hit_begin, const uint64_t* __restrict__ hit_off, uint64_t nseg,
+                           uint32_t* __restrict__ nruns32) {
+  const uint64_t sg = (uint64_t)blockIdx.x * HX_WARPS + (threadIdx.x >> 5);
+  if (sg >= nseg) return;
+  const HitSeg g = hit_segment(sg, seg_q, seg_off, hit_begin, hit_off);
+  const unsigned long long* mb = reinterpret_cast<const unsigned long long*>(e_mass);
+  uint32_t cnt = 0;
+  for (uint32_t i = lane_id(); i < g.n; i += 32) cnt += run_head(mb, e_base, g.b + i, g.i0 + i) ? 1u : 0u;
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (lane_id() == 0) nruns32[sg] = cnt;
+}
+
+// runs of every query: pep_off[q] = runs that start before the first segment of q (nq + 1 values)
+__global__ void __launch_bounds__(Q_THREADS)
+    hits_pep_off_kernel(const uint64_t* __restrict__ seg_off, const uint64_t* __restrict__ seg_run_off, uint64_t nq,
+                        uint64_t* __restrict__ pep_off) {
+  const uint64_t q = (uint64_t)blockIdx.x * Q_THREADS + threadIdx.x;
+  if (q <= nq) pep_off[q] = seg_run_off[seg_off[q]];
+}
+
+// K10b: same mapping.  seg_run_off = exclusive scan of the run counts; a warp numbers the runs of its
+// segment on the fly (ballot prefix), writes the mod pattern of every hit, and the first hit of every run
+// fills the run's row: where its hits start, the exact mass, the index entry (for K10c), residue count
+// and protein-list length (scanned into the two CSRs afterwards).
+__global__ void __launch_bounds__(Q_THREADS)
+    hits_runs_kernel(const double* __restrict__ e_mass, const uint32_t* __restrict__ e_base, uint64_t ent_off,
+                     const uint32_t* __restrict__ e_pat, const __grid_constant__ UniqView uv,
+                     const uint32_t* __restrict__ seg_q, const uint64_t* __restrict__ seg_off,
+                     const uint64_t* __restrict__ hit_begin, const uint64_t* __restrict__ hit_off,
+                     const uint64_t* __restrict__ seg_run_off, uint64_t nseg, uint32_t* __restrict__ o_pat,
+                     uint64_t* __restrict__ pep_hit_off, double* __restrict__ o_mass, uint32_t* __restrict__ pep_entry,
+                     uint32_t* __restrict__ len32, uint32_t* __restrict__ np32) {
+  const uint64_t sg = (uint64_t)blockIdx.x * HX_WARPS + (threadIdx.x >> 5);
+  if (sg >= nseg) return;
+  const HitSeg g = hit_segment(sg, seg_q, seg_off, hit_begin, hit_off);
+  const unsigned long long* mb = reinterpret_cast<const unsigned long long*>(e_mass);
+  uint64_t done = seg_run_off[sg];  // runs that start before the current 32 hits
+  for (uint32_t j = 0; j < g.n; j += 32) {  // warp-uniform trip count
+    const uint32_t i = j + lane_id();
+    const bool valid = i < g.n;
+    const uint64_t e = g.b + i;
+    const bool head = valid && run_head(mb, e_base, e, g.i0 + i);
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    if (valid && o_pat) o_pat[g.h0 + i] = e_pat ? e_pat[e] : 0u;
+    if (head) {
+      const uint64_t p = done + (uint32_t)__popc(heads & lanemask_lt());
+      const uint64_t gid = e_base ? (uint64_t)e_base[e] : ent_off + e;
+      uint64_t row;
+      const int r = uniq_owner(uv, gid, &row);
+      uint32_t len = 0, np = 0;
+      if (uv.len[r]) {
+        len = uv.len[r][row];
+        np = (uint32_t)(uv.plo[r][row + 1] - uv.plo[r][row]);
+      }
+      pep_hit_off[p] = g.h0 + i;
+      o_mass[p] = e_mass[e];
+      pep_entry[p] = (uint32_t)e;
+      len32[p] = len;
+      np32[p] = np;
     }
-    pep_hit_off[p] = h0 + i;
-    o_mass[p] = e_mass[e];
-    pep_entry[p] = (uint32_t)e;
-    len32[p] = len;
-    np32[p] = np;
+    done += (uint32_t)__popc(heads);
   }
 }
 
@@ -346,21 +408,40 @@ void launch_query(const double* e_mass, uint64_t n_entries, const double* lo, co
   DBI_LAUNCH(query_kernel, grid, Q_THREADS, 0, s, e_mass, n_entries, lo, hi, nq, hit_begin, hit_count, cnt32);
 }
 
-void launch_hits_mark(const double* e_mass, const uint32_t* e_base, const uint32_t* e_pat, const uint64_t* hit_begin,
-                      const uint64_t* hit_off, uint64_t nq, uint32_t* head32, uint32_t* o_pat, cudaStream_t s) {
+void launch_hits_seg_count(const uint64_t* hit_count, uint64_t nq, uint32_t* nseg32, cudaStream_t s) {
   if (nq == 0) return;
-  const unsigned grid = (unsigned)((nq + HX_WARPS - 1) / HX_WARPS);
-  DBI_LAUNCH(hits_mark_kernel, grid, Q_THREADS, 0, s, e_mass, e_base, e_pat, hit_begin, hit_off, nq, head32, o_pat);
+  DBI_LAUNCH(hits_seg_count_kernel, (unsigned)((nq + Q_THREADS - 1) / Q_THREADS), Q_THREADS, 0, s, hit_count, nq, nseg32);
 }
 
-void launch_hits_runs(const double* e_mass, const uint32_t* e_base, uint64_t ent_off, const UniqView& uv,
-                      const uint64_t* hit_begin, const uint64_t* hit_off, const uint64_t* run_of_hit, uint64_t nq,
-                      uint64_t* pep_off, uint64_t* pep_hit_off, double* o_mass, uint32_t* pep_entry, uint32_t* len32,
-                      uint32_t* np32, cudaStream_t s) {
+void launch_hits_seg_fill(const uint64_t* seg_off, uint64_t nq, uint32_t* seg_q, cudaStream_t s) {
   if (nq == 0) return;
-  const unsigned grid = (unsigned)((nq + HX_WARPS - 1) / HX_WARPS);
-  DBI_LAUNCH(hits_runs_kernel, grid, Q_THREADS, 0, s, e_mass, e_base, ent_off, uv, hit_begin, hit_off, run_of_hit, nq,
-             pep_off, pep_hit_off, o_mass, pep_entry, len32, np32);
+  DBI_LAUNCH(hits_seg_fill_kernel, (unsigned)((nq + HX_WARPS - 1) / HX_WARPS), Q_THREADS, 0, s, seg_off, nq, seg_q);
+}
+
+void launch_hits_count_runs(const double* e_mass, const uint32_t* e_base, const uint32_t* seg_q, const uint64_t* seg_off,
+                            const uint64_t* hit_begin, const uint64_t* hit_off, uint64_t nseg, uint32_t* nruns32,
+                            cudaStream_t s) {
+  if (nseg == 0) return;
+  const unsigned grid = (unsigned)((nseg + HX_WARPS - 1) / HX_WARPS);
+  DBI_LAUNCH(hits_count_runs_kernel, grid, Q_THREADS, 0, s, e_mass, e_base, seg_q, seg_off, hit_begin, hit_off, nseg,
+             nruns32);
+}
+
+void launch_hits_pep_off(const uint64_t* seg_off, const uint64_t* seg_run_off, uint64_t nq, uint64_t* pep_off,
+                         cudaStream_t s) {
+  DBI_LAUNCH(hits_pep_off_kernel, (unsigned)((nq + 1 + Q_THREADS - 1) / Q_THREADS), Q_THREADS, 0, s, seg_off, seg_run_off,
+             nq, pep_off);
+}
+
+void launch_hits_runs(const double* e_mass, const uint32_t* e_base, uint64_t ent_off, const uint32_t* e_pat,
+                      const UniqView& uv, const uint32_t* seg_q, const uint64_t* seg_off, const uint64_t* hit_begin,
+                      const uint64_t* hit_off, const uint64_t* seg_run_off, uint64_t nseg, uint32_t* o_pat,
+                      uint64_t* pep_hit_off, double* o_mass, uint32_t* pep_entry, uint32_t* len32, uint32_t* np32,
+                      cudaStream_t s) {
+  if (nseg == 0) return;
+  const unsigned grid = (unsigned)((nseg + HX_WARPS - 1) / HX_WARPS);
+  DBI_LAUNCH(hits_runs_kernel, grid, Q_THREADS, 0, s, e_mass, e_base, ent_off, e_pat, uv, seg_q, seg_off, hit_begin,
+             hit_off, seg_run_off, nseg, o_pat, pep_hit_off, o_mass, pep_entry, len32, np32);
 }
 
 void launch_peps_gather(const uint8_t* d_res, const uint32_t* pstart, const uint32_t* e_base, uint64_t ent_off,

@@ -143,6 +143,32 @@ def test_parity_param_sets(name):
         g.close()
 
 
+@pytest.mark.parametrize("name", ["cfg1_tryptic", "cfg2_mods"])
+def test_query_hits_batch_shapes(name):
+    """dbi_query_hits on the shapes a batch can take: the empty batch, only misses, windows of thousands of
+    hits (several 256-hit segments, runs that straddle a segment boundary) next to windows of none, a
+    window over the whole index, duplicated and degenerate ranges."""
+    p = dbi.default_params(**PARAM_SETS[name])
+    res, off = synth.synth_proteome(150, 4242, median_len=300, min_len=5)
+    seqs = [res[int(off[i]):int(off[i + 1])].tobytes().decode() for i in range(len(off) - 1)]
+    seqs += [seqs[0], seqs[1], "MSTYMSTYMSTYMSTYK", "MSTYMSTYMSTYMSTYK"]
+    g, o = both(p, *pack(seqs))
+    try:
+        m = o.entries()["mass"]
+        empty = g.query_hits(np.zeros(0), np.zeros(0), per_hit=False)
+        assert empty["counts"].n_hits == 0 and empty["counts"].n_peps == 0 and empty["hit_off"].tolist() == [0]
+        assert empty["pep_off"].tolist() == [0] and empty["pep_hit_off"].tolist() == [0]
+        lo = np.array([10.0, 7000.0, 599.0])
+        hi = np.array([20.0, 7999.0, 599.5])
+        check_hits(g, o, lo, hi)  # misses only
+        mid = float(np.median(m))
+        lo = np.array([0.0, mid - 3.0, 5.0, mid, m[0], m[-1], mid + 1.0, mid - 50.0, mid - 3.0, 6500.0])
+        hi = np.array([8000.0, mid + 3.0, 6.0, mid, m[0], m[-1], mid - 1.0, mid + 50.0, mid + 3.0, 6400.0])
+        check_hits(g, o, lo, hi)
+    finally:
+        g.close()
+
+
 def test_wide_sequence_hash_path(monkeypatch):
     """Large builds sort a sequence hash of more than 32 bits (the number of equal-mass string pairs
     grows with N^2); force that path on a small input with duplicates and isomers."""
