@@ -699,17 +699,24 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
+        t0 = time.perf_counter()
         p2 = params.copy()
         p2.profile = 0
         g2 = dbi.GpuIndex(p2)
         g2.set_stream(stream.cuda_stream)
         g2.add_proteins(h_res.numpy(), h_off.numpy().view(np.uint64))
+        t1 = time.perf_counter()
         inf2 = build_sharded(GpuShardEngine(g2, dev))
+        t2 = time.perf_counter()
         sel = route_queries(lo, hi, inf2["split_mass"], rank)
         c2 = g2.query_hits_begin(lo[sel], hi[sel])
+        t3 = time.perf_counter()
         g2.query_hits_read(sink.bufs)
         b.record(stream)
         torch.cuda.synchronize()
+        t4 = time.perf_counter()
+        e2e_host = {"create+add": 1e3 * (t1 - t0), "build": 1e3 * (t2 - t1), "route+query": 1e3 * (t3 - t2),
+                    "read": 1e3 * (t4 - t3), **{"build." + k: v for k, v in inf2["t"].items()}}
         assert c2.n_hits == hits
         barrier()  # nobody releases its windows while another rank may still read them
         g2.close()
@@ -761,6 +768,7 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
             "gpu_launches": int(launches_all),
             "clocks": clk,
             "host_stage_ms_rank0_last_step": {k: round(v, 3) for k, v in info["t"].items()},
+            "e2e_host_ms_rank0_last_step": {k: round(v, 3) for k, v in e2e_host.items()},
             "device_stage_ms_rank0_last_step": {k: round(v, 3) for k, v in st["stage_ms"].items() if v > 0},
             "per_rank_last_step": {k: [r.get(k, 0) for r in per_rank] for k in per_rank[0]},
         }

@@ -383,35 +383,42 @@ int dbi_mg_hist(dbi_handle* h, int stage, void* d_hist, int* shift) {
   const KeySpace ks(h->p.min_mass, h->p.max_mass);
   const int sh = mg_shift(ks);
   if (stage == 0) {
-    // weighted = variants the records will expand to (estimated from their mod-site counts: sum over k <= K
-    // of C(n, k)), plain = records: the cuts of exchange 0 are the cuts of the whole index, so they must
-    // anticipate the expansion
+    // weighted = index entries the records will expand to, estimated from their mod-site counts n: sum over
+    // k <= K of C(n, k); groups = variant groups they will list: sum over k <= min(n, K) of min(C^k, C(n, k));
+    // plain = records.  The cuts of exchange 0 are the cuts of the whole index, so they must anticipate the
+    // expansion.
     const uint32_t* wtab = nullptr;
+    const uint32_t* gtab = nullptr;
     if (h->cfg.max_mods > 0 && h->mg_nmod.p) {
       if (!h->mg_wtab.p) {
-        uint32_t tab[256];
+        uint32_t tab[512];
+        const int K = h->cfg.max_mods, C = std::max(1, h->cfg.n_classes);
         for (int n = 0; n < 256; ++n) {
-          uint64_t t = 0, c = 1;  // C(n, 0)
-          for (int k = 0; k <= h->cfg.max_mods; ++k) {
+          uint64_t t = 0, g = 0, c = 1, ck = 1;  // C(n, 0), C^0
+          for (int k = 0; k <= K; ++k) {
             t += c;
+            g += std::min<uint64_t>(c, ck);
             c = c * (uint64_t)(n - k) / (uint64_t)(k + 1);
+            ck = std::min<uint64_t>(ck * (uint64_t)C, 1u << 20);
             if (n - k <= 0) break;
           }
           tab[n] = (uint32_t)std::min<uint64_t>(t, 0xffffull);  // < 2^16: stays in the 32-bit shared bins
+          tab[256 + n] = (uint32_t)std::min<uint64_t>(g, h->cfg.n_seq > 0 ? (uint64_t)h->cfg.n_seq : 0xffull);
         }
         h->mg_wtab.alloc(sizeof(tab), h->arena);
         DBI_CUDA(cudaMemcpyAsync(h->mg_wtab.p, tab, sizeof(tab), cudaMemcpyHostToDevice, h->stream));
         DBI_CUDA(cudaStreamSynchronize(h->stream));
       }
       wtab = h->mg_wtab.as<uint32_t>();
+      gtab = wtab + 256;
     }
     launch_mg_hist(h->mg_mass.as<uint64_t>(), h->mg_n, ks.base_bits, sh, nullptr, 0, 0u, h->mg_nmod.as<uint8_t>(), wtab,
-                   (unsigned long long*)d_hist, h->stream);
+                   gtab, (unsigned long long*)d_hist, h->stream);
   } else {  // group records: weigh by their variant count
     const bool weighted = h->cfg.n_seq > 0;
     // weighted = index entries the groups stand for, plain = groups; dbi_mg_plan turns both into a cost
     launch_mg_hist(h->mg_vkey.as<uint64_t>(), h->mg_v, 0, sh, weighted ? h->mg_vpay.as<uint64_t>() : nullptr,
-                   kGrpCntMask, 0u, nullptr, nullptr, (unsigned long long*)d_hist, h->stream);
+                   kGrpCntMask, 0u, nullptr, nullptr, nullptr, (unsigned long long*)d_hist, h->stream);
   }
   if (shift) *shift = sh;
   DBI_CUDA(cudaStreamSynchronize(h->stream));  // the caller reduces d_hist on ITS stream next
@@ -419,18 +426,22 @@ int dbi_mg_hist(dbi_handle* h, int stage, void* d_hist, int* shift) {
   DBI_API_END
 }
 
-// Pure host arithmetic: bin splitters of equal COST from the global histograms (bins are never split, so
-// equal masses -- hence equal peptides -- meet on one rank), this rank's send counts from its own plain
-// histogram, every rank's receive total from the global plain histogram.
+// Pure host arithmetic: bin splitters from the global histograms [weighted | plain | groups] (bins are never
+// split, so equal masses -- hence equal peptides -- meet on one rank), this rank's send counts from its own
+// plain histogram, every rank's receive total from the global plain histogram.
 //
-// cost of a bin = cost[0] * items + cost[1] * weight + cost[2] * weight^2 * mass / (width * total weight)
-//   items  = records (exchange 0) or variant groups (exchange 1): sort passes, staging
-//   weight = index entries the items stand for: expansion writes
-//   last term = expected HITS of precursor queries that follow the indexed mass density at a relative (ppm)
-//   tolerance: queries landing in the bin ~ weight / total, hits per query ~ (weight / width) * mass.
-//   An index is built once and searched many times, so the slices are cut for the search load too.
-// cost == NULL: {0, 1, 0} (equal weight).  Every rank runs this on the same global histogram and gets the
-// same splitters.
+// A sharded build runs in PHASES separated by exchanges, and a step lasts as long as the slowest rank of
+// every phase.  Per bin:
+//   base phase    B = cost[0] * items                      (sort + merge of the records / of the items)
+//   variant phase V = cost[1] * groups + cost[2] * weight  (group sort; expansion writes per index entry)
+//   search phase  Q = cost[3] * weight^2 * mass / (width * total weight)
+//     = expected HITS of precursor queries that follow the indexed mass density at a relative (ppm) tolerance:
+//     queries landing in the bin ~ weight / total, hits per query ~ (weight / width) * mass.  An index is built
+//     once and searched many times, so the slices are cut for the search load too.
+// The cuts start where the SUM B + V + Q is equal per rank; when more than one phase has a cost they are then
+// moved, one at a time, to wherever  max_r B + max_r V + max_r Q  gets smallest (coordinate descent on the
+// prefix sums: a few thousand operations).  cost == NULL: {0, 0, 1, 0} (equal weight).  Every rank runs this on
+// the same global histogram and gets the same splitters.
 int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_local, int shift, double min_mass,
                 const double* cost, uint32_t* bin_splitters, uint64_t* send_counts, uint64_t* recv_totals) {
   if (world < 1 || world > kMaxRanks || !hist_global || !hist_local || !send_counts || !recv_totals ||
@@ -439,7 +450,8 @@ int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_loc
     return DBI_EINVAL;
   }
   const int B = kMgBins;
-  const double c_item = cost ? cost[0] : 0.0, c_w = cost ? cost[1] : 1.0, c_hit = cost ? cost[2] : 0.0;
+  const double c_item = cost ? cost[0] : 0.0, c_grp = cost ? cost[1] : 0.0, c_w = cost ? cost[2] : 1.0,
+               c_hit = cost ? cost[3] : 0.0;
   double w_total = 0;
   for (int b = 0; b < B; ++b) w_total += (double)hist_global[b];
   const uint64_t base_bits = dbits(min_mass);
@@ -449,35 +461,79 @@ int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_loc
     std::memcpy(&m, &bits, 8);
     return m;
   };
-  std::vector<double> c(B);
-  double total = 0;
+  // prefix sums of the three phase costs: P[ph][b] = cost of bins [0, b)
+  std::vector<double> P[3];
+  for (auto& v : P) v.assign(B + 1, 0.0);
   for (int b = 0; b < B; ++b) {
-    const double items = (double)hist_global[B + b], w = (double)hist_global[b];
-    double v = c_item * items + c_w * w;
+    const double items = (double)hist_global[B + b], w = (double)hist_global[b], g = (double)hist_global[2 * B + b];
+    double q = 0;
     if (c_hit > 0 && w > 0 && w_total > 0) {
       const double m0 = mass_at(b), m1 = mass_at(b + 1);
       const double width = m1 - m0;
-      if (width > 0) v += c_hit * w * w * (0.5 * (m0 + m1)) / (width * w_total);
+      if (width > 0) q = c_hit * w * w * (0.5 * (m0 + m1)) / (width * w_total);
     }
-    c[b] = v;
-    total += v;
+    P[0][b + 1] = P[0][b] + c_item * items;
+    P[1][b + 1] = P[1][b] + c_grp * g + c_w * w;
+    P[2][b + 1] = P[2][b] + q;
   }
-  uint32_t prev = 0;
-  double cum = 0;
-  int b = 0;
-  for (int d = 1; d < world; ++d) {
-    const double target = total * (double)d / (double)world;
-    // first bin boundary at which at least `target` of the cost lies below
-    while (b < B && cum + c[b] < target) cum += c[b++];
-    uint32_t cut = total > 0 ? (uint32_t)std::min(b + 1, B) : 0u;
-    if (cut < prev) cut = prev;
-    bin_splitters[d - 1] = cut;
-    prev = cut;
+  const double total = P[0][B] + P[1][B] + P[2][B];
+  std::vector<int> cut(world + 1, 0);  // slice d = bins [cut[d], cut[d + 1])
+  cut[world] = B;
+  {
+    int b = 0;
+    for (int d = 1; d < world; ++d) {
+      const double target = total * (double)d / (double)world;
+      // first bin boundary at which at least `target` of the cost lies below
+      while (b < B && (P[0][b + 1] + P[1][b + 1] + P[2][b + 1]) < target) ++b;
+      int c = total > 0 ? std::min(b + 1, B) : 0;
+      if (c < cut[d - 1]) c = cut[d - 1];
+      cut[d] = c;
+    }
   }
+  const int phases = (P[0][B] > 0) + (P[1][B] > 0) + (P[2][B] > 0);
+  if (world > 1 && phases > 1) {
+    auto objective = [&]() {
+      double o = 0;
+      for (int ph = 0; ph < 3; ++ph) {
+        double mx = 0;
+        for (int d = 0; d < world; ++d) mx = std::max(mx, P[ph][cut[d + 1]] - P[ph][cut[d]]);
+        o += mx;
+      }
+      return o;
+    };
+    double best = objective();
+    for (int sweep = 0; sweep < 6; ++sweep) {
+      bool moved = false;
+      for (int d = 1; d < world; ++d) {
+        const int lo = cut[d - 1], hi = cut[d + 1];
+        int keep = cut[d];
+        // coarse grid over the whole gap, then two refinements around the best candidate
+        int span = hi - lo, centre = keep;
+        for (int level = 0; level < 3 && span > 0; ++level) {
+          const int steps = 32;
+          const int a = level == 0 ? lo : std::max(lo, centre - span), z = level == 0 ? hi : std::min(hi, centre + span);
+          for (int i = 0; i <= steps; ++i) {
+            const int c = a + (int)((int64_t)(z - a) * i / steps);
+            cut[d] = c;
+            const double o = objective();
+            if (o < best * (1.0 - 1e-12)) {
+              best = o;
+              keep = c;
+              moved = true;
+            }
+          }
+          centre = keep;
+          span = std::max(1, (z - a) / steps);
+        }
+        cut[d] = keep;
+      }
+      if (!moved) break;
+    }
+  }
+  for (int d = 1; d < world; ++d) bin_splitters[d - 1] = (uint32_t)cut[d];
   for (int d = 0; d < world; ++d) {
-    const uint32_t lo = d ? bin_splitters[d - 1] : 0u, hi = d < world - 1 ? bin_splitters[d] : (uint32_t)B;
     uint64_t sc = 0, rt = 0;
-    for (uint32_t x = lo; x < hi; ++x) {
+    for (int x = cut[d]; x < cut[d + 1]; ++x) {
       sc += hist_local[B + x];
       rt += hist_global[B + x];
     }
@@ -487,26 +543,29 @@ int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_loc
   return DBI_OK;
 }
 
-// The cost model of an exchange for dbi_mg_plan: measured on B200 (profiles/r02_scale_notes.md), in ps.
-// DBI_MG_COST="item,weight,hit" overrides the variant exchange's.
+// The cost model of an exchange for dbi_mg_plan {per item, per estimated group, per unit of weight (index
+// entry), per expected hit}: measured on B200 (profiles/r02_*), in ps.  DBI_MG_COST0 / DBI_MG_COST =
+// "item,group,weight,hit" override exchange 0's / exchange 1's.
 void dbi_mg_default_cost(int stage, int has_mods, double* cost) {
   if (stage == 0 && !has_mods) {
-    cost[0] = 1.0; cost[1] = 0.0; cost[2] = 0.0;  // records are the entries (or exchange 1 plans its own cuts): equal counts
+    cost[0] = 1.0; cost[1] = 0.0; cost[2] = 0.0; cost[3] = 0.0;  // records are the entries: equal counts
     return;
   }
   if (stage == 0) {
     // The cuts of exchange 0 are the cuts of the whole index (the variant groups travel by the same cuts).
-    // per record: its own sort + merge (~300 ps) and the ~5 groups it will list (120 ps each: 7 radix passes,
-    // expansion staging); per estimated entry: expansion write; per expected hit (10 000 queries at 10 ppm per
-    // build, 70 ps each, x ~8 because the masses cluster inside a bin).
-    cost[0] = 900.0; cost[1] = 10.0; cost[2] = 25.0;
+    // per record: hash + 11 radix passes + merge + group count (sort_base 0.63 + dedup 0.14 + mod_count 0.29 ms
+    // per 2.7 M); per group: listing + 7 radix passes + the scatter (mod_emit 0.22 + sort_var 1.04 + 0.4 ms per
+    // 13 M); per entry: the expansion write (1.21 ms per 69 M); per expected hit: 13 ps x 10 000 queries x 2e-5
+    // (+-10 ppm) x ~8 (masses cluster inside a bin).
+    cost[0] = 400.0; cost[1] = 125.0; cost[2] = 17.5; cost[3] = 20.0;
   } else {
-    cost[0] = 120.0; cost[1] = 10.0; cost[2] = 7.0;  // exchange 1 alone (only used when it plans its own cuts)
+    cost[0] = 125.0; cost[1] = 0.0; cost[2] = 17.5; cost[3] = 20.0;  // exchange 1 alone (only when it plans its own cuts)
   }
   if (const char* e = std::getenv(stage == 0 ? "DBI_MG_COST0" : "DBI_MG_COST")) {
-    double a, b2, c2;
-    if (std::sscanf(e, "%lf,%lf,%lf", &a, &b2, &c2) == 3 && a >= 0 && b2 >= 0 && c2 >= 0 && a + b2 + c2 > 0) {
-      cost[0] = a; cost[1] = b2; cost[2] = c2;
+    double a, g2, b2, c2;
+    if (std::sscanf(e, "%lf,%lf,%lf,%lf", &a, &g2, &b2, &c2) == 4 && a >= 0 && g2 >= 0 && b2 >= 0 && c2 >= 0 &&
+        a + g2 + b2 + c2 > 0) {
+      cost[0] = a; cost[1] = g2; cost[2] = b2; cost[3] = c2;
     }
   }
 }
@@ -810,7 +869,7 @@ int dbi_mg_build_local(dbi_handle** hs, int n) {
     // groups of a peptide mostly stay on the GPU that owns the peptide: only the counts are needed
     auto exchange = [&](int stage) -> int {
       if (stage == 0) {
-        const size_t HB = 2 * kMgBins;
+        const size_t HB = 3 * kMgBins;
         std::vector<uint64_t> local((size_t)W * HB), global(HB, 0);
         int shift_of = 0;
         for (int r = 0; r < W; ++r) {
@@ -825,7 +884,7 @@ int dbi_mg_build_local(dbi_handle** hs, int n) {
         }
         for (int r = 0; r < W; ++r)
           for (size_t i = 0; i < HB; ++i) global[i] += local[(size_t)r * HB + i];
-        double cost[3];
+        double cost[4];
         dbi_mg_default_cost(stage, mods ? 1 : 0, cost);
         for (int r = 0; r < W; ++r)
           if (int rc = dbi_mg_plan(W, global.data(), &local[(size_t)r * HB], shift_of, hs[0]->p.min_mass, cost, split.data(),

@@ -205,11 +205,13 @@ struct MgPlan {
   uint64_t row0[kMaxRanks];
   int world;
 };
-// hist[0 .. kMgBins) += weight, hist[kMgBins .. 2 kMgBins) += 1 over min(kMgBins-1, (key[i] - sub) >> shift)
-// (hist is zeroed by the caller); weight of item i = wpay ? (wpay[i] & wmask) + wadd  (group records carry
-// their variant count)  :  wtab ? wtab[wcode[i]]  (records: variants of a peptide with wcode[i] mod sites)  :  1.
+// hist[0 .. kMgBins) += weight, hist[kMgBins .. 2 kMgBins) += 1, hist[2 kMgBins .. 3 kMgBins) += group estimate
+// over min(kMgBins-1, (key[i] - sub) >> shift) (hist is zeroed by the caller); weight of item i =
+// wpay ? (wpay[i] & wmask) + wadd  (group records carry their variant count)  :  wtab ? wtab[wcode[i]]
+// (records: variants of a peptide with wcode[i] mod sites)  :  1;  group estimate = gtab ? gtab[wcode[i]] : 0.
 void launch_mg_hist(const uint64_t* key, uint64_t n, uint64_t sub, int shift, const uint64_t* wpay, uint64_t wmask,
-                    uint32_t wadd, const uint8_t* wcode, const uint32_t* wtab, unsigned long long* hist, cudaStream_t s);
+                    uint32_t wadd, const uint8_t* wcode, const uint32_t* wtab, const uint32_t* gtab,
+                    unsigned long long* hist, cudaStream_t s);
 // counts[d] += items whose destination is d (dest = number of thresholds <= key - sub); counts zeroed by the caller
 void launch_mg_count(const uint64_t* key, uint64_t n, uint64_t sub, const MgPlan& pl, unsigned long long* counts,
                      cudaStream_t s);

@@ -13,10 +13,12 @@ namespace {
 constexpr int MG_THREADS = 256;
 
 // ---- histograms of an exchange stage ------------------------------------------------------
-// hist[0 .. kMgBins)          += weight of the item  (stage 1: variant count of the group + its fixed cost; else 1)
-// hist[kMgBins .. 2 kMgBins)  += 1
-// over the bins min(kMgBins - 1, (key - sub) >> shift).  The weighted one chooses the splitters
-// (equal WORK per rank), the plain one gives every rank the number of items it will send and receive.
+// hist[0 .. kMgBins)            += weight of the item  (stage 1: variant count of the group; stage 0: the
+//                                  index entries a record will expand to, estimated from its mod sites; else 1)
+// hist[kMgBins .. 2 kMgBins)    += 1
+// hist[2 kMgBins .. 3 kMgBins)  += variant GROUPS a record will list (stage 0 with mods, estimated; else 0)
+// over the bins min(kMgBins - 1, (key - sub) >> shift).  The plain one gives every rank the number of
+// items it will send and receive; all three feed the cost model that places the cuts (dbi_mg_plan).
 // 32-bit shared-memory bins (native atomics); a CTA sees at most 2^16 items and weights of 2^16 or more
 // (a group can stand for 2^27 variants) go straight to the 64-bit global bins, so nothing can wrap.
 constexpr uint32_t kMgMaxItemsPerCta = 1u << 16;
@@ -25,12 +27,14 @@ __global__ void __launch_bounds__(MG_THREADS)
     mg_hist_kernel(const uint64_t* __restrict__ key, uint64_t n, uint64_t per_cta, uint64_t sub, int shift,
                    const uint64_t* __restrict__ wpay, uint64_t wmask, uint32_t wadd,
                    const uint8_t* __restrict__ wcode, const uint32_t* __restrict__ wtab,
-                   unsigned long long* __restrict__ hist) {
+                   const uint32_t* __restrict__ gtab, unsigned long long* __restrict__ hist) {
   __shared__ uint32_t sh_w[kMgBins];
   __shared__ uint32_t sh_c[kMgBins];
+  __shared__ uint32_t sh_g[kMgBins];  // 3 x 16 KB: exactly the 48 KB of static shared memory
   for (int i = threadIdx.x; i < kMgBins; i += MG_THREADS) {
     sh_w[i] = 0;
     sh_c[i] = 0;
+    sh_g[i] = 0;
   }
   __syncthreads();
   const uint64_t i0 = (uint64_t)blockIdx.x * per_cta, i1 = min(n, i0 + per_cta);
@@ -38,14 +42,17 @@ __global__ void __launch_bounds__(MG_THREADS)
     uint64_t b = (key[i] - sub) >> shift;
     if (b >= kMgBins) b = kMgBins - 1;
     atomicAdd(&sh_c[b], 1u);
-    const uint64_t w = wpay ? (wpay[i] & wmask) + wadd : (wtab ? (uint64_t)__ldg(wtab + wcode[i]) : 1ull);
+    const uint32_t code = wcode ? wcode[i] : 0u;
+    const uint64_t w = wpay ? (wpay[i] & wmask) + wadd : (wtab ? (uint64_t)__ldg(wtab + code) : 1ull);
     if (w < (1ull << 16)) atomicAdd(&sh_w[b], (uint32_t)w);
     else atomicAdd(&hist[b], (unsigned long long)w);
+    if (gtab) atomicAdd(&sh_g[b], __ldg(gtab + code));  // < 2^8 per record
   }
   __syncthreads();
   for (int i = threadIdx.x; i < kMgBins; i += MG_THREADS) {
     if (sh_w[i]) atomicAdd(&hist[i], (unsigned long long)sh_w[i]);
     if (sh_c[i]) atomicAdd(&hist[kMgBins + i], (unsigned long long)sh_c[i]);
+    if (sh_g[i]) atomicAdd(&hist[2 * kMgBins + i], (unsigned long long)sh_g[i]);
   }
 }
 
@@ -330,7 +337,8 @@ __global__ void __launch_bounds__(MG_THREADS)
 }  // namespace
 
 void launch_mg_hist(const uint64_t* key, uint64_t n, uint64_t sub, int shift, const uint64_t* wpay, uint64_t wmask,
-                    uint32_t wadd, const uint8_t* wcode, const uint32_t* wtab, unsigned long long* hist, cudaStream_t s) {
+                    uint32_t wadd, const uint8_t* wcode, const uint32_t* wtab, const uint32_t* gtab,
+                    unsigned long long* hist, cudaStream_t s) {
   if (n == 0) return;
   uint64_t g = (uint64_t)kNumSMsB200 * 4;
   uint64_t per_cta = (n + g - 1) / g;
@@ -338,7 +346,7 @@ void launch_mg_hist(const uint64_t* key, uint64_t n, uint64_t sub, int shift, co
   per_cta = (per_cta + MG_THREADS - 1) / MG_THREADS * MG_THREADS;
   g = (n + per_cta - 1) / per_cta;
   DBI_LAUNCH(mg_hist_kernel, (unsigned)g, MG_THREADS, 0, s, key, n, per_cta, sub, shift, wpay, wmask, wadd, wcode, wtab,
-             hist);
+             gtab, hist);
 }
 
 void launch_mg_count(const uint64_t* key, uint64_t n, uint64_t sub, const MgPlan& pl, unsigned long long* counts,

@@ -21,7 +21,7 @@ touches (:333-343).  Here a bucket is a GPU:
   6. queries are routed on the host with the splitter masses; a range that straddles a splitter is
      answered by both neighbours, exactly like Mult.getSequences walking two buckets.
 
-What crosses torch.distributed: exchange 0 -- one 64 KB all-reduce (the two histograms), one all-gather of
+What crosses torch.distributed: exchange 0 -- one 96 KB all-reduce (the three histograms), one all-gather of
 ~350 bytes per rank (send counts, unique count, window descriptors) and one barrier; exchange 1 -- the
 all-gather and the barrier only (it reuses the cuts of exchange 0).
 
@@ -62,8 +62,9 @@ def pick_splitters(hist: np.ndarray, world: int) -> np.ndarray:
 def plan_exchange(world: int, hist_global: np.ndarray, hist_local: np.ndarray, shift: int, min_mass: float,
                   stage: int = 0, has_mods: bool = False, cost=None):
     """dbi_mg_plan (host arithmetic of libdbindex_gpu.so, no device needed): (bin splitters of equal cost,
-    this rank's send counts, every rank's receive total) from the summed and the own [weighted | plain]
-    histograms.  cost = None: the measured default model of the exchange (dbi_mg_default_cost)."""
+    this rank's send counts, every rank's receive total) from the summed and the own [weighted | plain | groups]
+    histograms.  cost = (per item, per estimated group, per unit of weight, per expected hit); None: the
+    measured default model of the exchange (dbi_mg_default_cost)."""
     import ctypes as C
     from .capi import load_library
     lib = load_library()
@@ -71,13 +72,17 @@ def plan_exchange(world: int, hist_global: np.ndarray, hist_local: np.ndarray, s
     lib.dbi_mg_plan.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 4
     lib.dbi_mg_default_cost.restype = None
     lib.dbi_mg_default_cost.argtypes = [C.c_int, C.c_int, C.c_void_p]
-    c = np.zeros(3, dtype=np.float64)
+    c = np.zeros(4, dtype=np.float64)
     if cost is None:
         lib.dbi_mg_default_cost(stage, 1 if has_mods else 0, c.ctypes.data)
     else:
         c[:] = cost
     hg = np.ascontiguousarray(hist_global, dtype=np.uint64)
     hl = np.ascontiguousarray(hist_local, dtype=np.uint64)
+    if len(hg) == 2 * MG_BINS:  # no group estimates
+        hg = np.concatenate([hg, np.zeros(MG_BINS, np.uint64)])
+        hl = np.concatenate([hl, np.zeros(MG_BINS, np.uint64)])
+    assert len(hg) == 3 * MG_BINS and len(hl) == 3 * MG_BINS
     split = np.zeros(max(world - 1, 1), dtype=np.uint32)
     send, recv = np.zeros(world, dtype=np.uint64), np.zeros(world, dtype=np.uint64)
     rc = lib.dbi_mg_plan(world, hg.ctypes.data, hl.ctypes.data, int(shift), float(min_mass), c.ctypes.data,
@@ -138,7 +143,7 @@ class ShardEngine:
     def layout_bytes(self, window: int, stage: int, n_items: int) -> int: ...
     def pull_proteome(self): ...
     def digest(self) -> int: ...
-    def hist(self, stage: int) -> Tuple[torch.Tensor, int]: ...   # (int64[2 * MG_BINS] on device, shift)
+    def hist(self, stage: int) -> Tuple[torch.Tensor, int]: ...   # (int64[3 * MG_BINS] on device, shift)
     def count(self, stage: int, splitters: np.ndarray) -> np.ndarray: ...   # items per destination under the cuts
     def scatter(self, stage: int, splitters: np.ndarray, matrix: np.ndarray): ...
     def index_base(self): ...
@@ -358,7 +363,7 @@ class GpuShardEngine(ShardEngine):
         return n.value
 
     def hist(self, stage):
-        hist = torch.zeros(2 * MG_BINS, dtype=torch.int64, device=self.device)
+        hist = torch.zeros(3 * MG_BINS, dtype=torch.int64, device=self.device)
         shift = self.C.c_int()
         torch.cuda.current_stream().synchronize()
         self._ck(self.lib.dbi_mg_hist(self.g._h, stage, hist.data_ptr(), self.C.byref(shift)))

@@ -392,13 +392,17 @@ uint64_t dbi_mg_layout_bytes(int window, int stage, uint64_t n_items, int n_clas
 int dbi_mg_side_classes(dbi_handle* h); /* n_classes argument of dbi_mg_layout_bytes for this handle */
 int dbi_mg_pull_proteome(dbi_handle* h);
 int dbi_mg_digest(dbi_handle* h, uint64_t* n_records);
-/* d_hist: u64[2 * DBI_MG_BINS] in device memory, zeroed by the caller: += weighted | plain histogram of
- * the local items of exchange `stage` (0 = digested records, 1 = variant groups) over key >> *shift */
+/* d_hist: u64[3 * DBI_MG_BINS] in device memory, zeroed by the caller: += weighted | plain | groups histogram
+ * of the local items of exchange `stage` (0 = digested records: weight = index entries a record will expand
+ * to, groups = variant groups it will list, both estimated from its mod sites; 1 = variant groups: weight =
+ * their entries, no third part) over key >> *shift */
 int dbi_mg_hist(dbi_handle* h, int stage, void* d_hist, int* shift);
-/* host arithmetic on the summed (global) and the own (local) histograms: bin splitters [world-1] of equal
- * COST, this rank's send counts [world], every rank's receive total [world].  cost[3] = {per item, per unit
- * of weight (index entry), per expected query hit}; NULL = equal weight.  shift / min_mass as used by
- * dbi_mg_hist (they give a bin its mass).  dbi_mg_default_cost fills the measured model of an exchange. */
+/* host arithmetic on the summed (global) and the own (local) histograms: bin splitters [world-1], this rank's
+ * send counts [world], every rank's receive total [world].  cost[4] = {per item, per estimated group, per unit
+ * of weight (index entry), per expected query hit}; NULL = equal weight.  The cuts minimise the sum over the
+ * phases of a build (base: items; variants: groups + weight; search: hits) of the slowest rank's cost.
+ * shift / min_mass as used by dbi_mg_hist (they give a bin its mass).  dbi_mg_default_cost fills the measured
+ * model of an exchange (cost[4]). */
 int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_local, int shift, double min_mass,
                 const double* cost, uint32_t* bin_splitters, uint64_t* send_counts, uint64_t* recv_totals);
 void dbi_mg_default_cost(int stage, int has_mods, double* cost);

@@ -97,7 +97,7 @@ class OracleShardEngine(ShardEngine):
     def hist(self, stage):
         bins = (self._keys(stage) >> np.uint64(self.shift)).astype(np.int64)
         plain = np.bincount(bins, minlength=MG_BINS).astype(np.int64)
-        return torch.from_numpy(np.concatenate([plain, plain])), self.shift  # every item weighs 1 here
+        return torch.from_numpy(np.concatenate([plain, plain, np.zeros_like(plain)])), self.shift  # every item weighs 1 here, no group estimates
 
     def count(self, stage, splitters):
         thr = np.asarray(splitters, dtype=np.uint64) << np.uint64(self.shift)

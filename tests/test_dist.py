@@ -52,37 +52,74 @@ def test_two_rank_gloo_build_matches_oracle(name, tmp_path):
     assert r["ok"] and all(c > 0 for c in r["counts"]) and r["a2a_bytes"] > 0
 
 
+def _phase_objective(hg, split, cost, shift=42, min_mass=600.0):
+    """max over ranks of every phase's cost, summed over the phases (what dbi_mg_plan minimises)."""
+    w, items, grp = (hg[i * MG_BINS:(i + 1) * MG_BINS].astype(np.float64) for i in range(3))
+    base = np.float64(min_mass).view(np.uint64)
+    edges_m = ((np.arange(MG_BINS + 1, dtype=np.uint64) << np.uint64(shift)) + base).view(np.float64)
+    width = np.diff(edges_m)
+    q = np.where(w > 0, cost[3] * w * w * 0.5 * (edges_m[:-1] + edges_m[1:]) / (width * max(w.sum(), 1.0)), 0.0)
+    phases = [cost[0] * items, cost[1] * grp + cost[2] * w, q]
+    e = np.concatenate(([0], split, [MG_BINS])).astype(int)
+    return sum(max(ph[e[d]:e[d + 1]].sum() for d in range(len(e) - 1)) for ph in phases)
+
+
 def test_dbi_mg_plan_cost_models():
     """dbi_mg_plan: with the equal-weight model the splitters equal the numpy reference (pick_splitters);
     send / receive counts partition the plain histograms; the query-aware model moves the cuts towards the
-    dense bins (fewer entries for the ranks that will see more hits) and stays monotone."""
+    dense bins (fewer entries for the ranks that will see more hits) and stays monotone; with several phases
+    the cuts minimise the sum of the per-phase maxima at least as well as equal-sum cuts do."""
     rng = np.random.default_rng(5)
     for world in (1, 2, 3, 8, 16):
         plain = [rng.integers(0, 50, size=MG_BINS).astype(np.uint64) for _ in range(world)]
         for p in plain:
             p[:100] = 0
         weighted = [p * rng.integers(1, 2000, size=MG_BINS).astype(np.uint64) for p in plain]
-        hg = np.concatenate([sum(weighted), sum(plain)]).astype(np.uint64)
+        groups = [p * rng.integers(1, 15, size=MG_BINS).astype(np.uint64) for p in plain]
+        hg = np.concatenate([sum(weighted), sum(plain), sum(groups)]).astype(np.uint64)
         for r in range(world):
-            hl = np.concatenate([weighted[r], plain[r]]).astype(np.uint64)
-            split, send, recv = plan_exchange(world, hg, hl, 42, 600.0, cost=[0.0, 1.0, 0.0])
+            hl = np.concatenate([weighted[r], plain[r], groups[r]]).astype(np.uint64)
+            split, send, recv = plan_exchange(world, hg, hl, 42, 600.0, cost=[0.0, 0.0, 1.0, 0.0])
             assert split.tolist() == pick_splitters(hg[:MG_BINS], world).tolist()
             edges = np.concatenate(([0], split, [MG_BINS])).astype(int)
             assert send.tolist() == [int(plain[r][edges[d]:edges[d + 1]].sum()) for d in range(world)]
-            assert recv.tolist() == [int(hg[MG_BINS:][edges[d]:edges[d + 1]].sum()) for d in range(world)]
-            assert int(recv.sum()) == int(hg[MG_BINS:].sum())
-        s2, _, _ = plan_exchange(world, hg, np.concatenate([weighted[0], plain[0]]), 42, 600.0, stage=1, has_mods=True)
-        assert np.all(np.diff(s2.astype(np.int64)) >= 0) and len(s2) == world - 1
+            assert recv.tolist() == [int(hg[MG_BINS:2 * MG_BINS][edges[d]:edges[d + 1]].sum()) for d in range(world)]
+            assert int(recv.sum()) == int(hg[MG_BINS:2 * MG_BINS].sum())
+            # the two-histogram form (no group estimates) is accepted and means the same
+            s2h, _, _ = plan_exchange(world, hg[:2 * MG_BINS], hl[:2 * MG_BINS], 42, 600.0, cost=[0.0, 0.0, 1.0, 0.0])
+            assert s2h.tolist() == split.tolist()
+        for stage in (0, 1):
+            s2, send, recv = plan_exchange(world, hg, np.concatenate([weighted[0], plain[0], groups[0]]), 42, 600.0,
+                                           stage=stage, has_mods=True)
+            assert np.all(np.diff(s2.astype(np.int64)) >= 0) and len(s2) == world - 1
+            assert int(send.sum()) == int(plain[0].sum()) and int(recv.sum()) == int(hg[MG_BINS:2 * MG_BINS].sum())
     # a density peak: the query-aware model gives the rank holding the peak a narrower slice
     w = np.full(MG_BINS, 1000, dtype=np.uint64)
     w[3000:3100] = 40000
-    hg = np.concatenate([w, np.full(MG_BINS, 100, dtype=np.uint64)])
-    flat, _, _ = plan_exchange(4, hg, hg, 42, 600.0, cost=[0.0, 1.0, 0.0])
-    aware, _, _ = plan_exchange(4, hg, hg, 42, 600.0, cost=[0.0, 1.0, 50.0])
+    hg = np.concatenate([w, np.full(MG_BINS, 100, dtype=np.uint64), np.zeros(MG_BINS, np.uint64)])
+    flat, _, _ = plan_exchange(4, hg, hg, 42, 600.0, cost=[0.0, 0.0, 1.0, 0.0])
+    aware, _, _ = plan_exchange(4, hg, hg, 42, 600.0, cost=[0.0, 0.0, 1.0, 50.0])
     width = lambda s: np.diff(np.concatenate(([0], s.astype(np.int64), [MG_BINS])))  # noqa: E731
     k = int(np.searchsorted(flat, 3050))
     k2 = int(np.searchsorted(aware, 3050))
     assert width(aware)[k2] < width(flat)[k]
+    # records crowd the light end, entries the heavy end (what differential mods do): cuts of equal SUM leave
+    # the first rank with the slowest base phase and the last with the slowest variant phase; the planner must
+    # do at least as well on the sum of the phase maxima, and better here
+    x = np.arange(MG_BINS, dtype=np.float64) / MG_BINS
+    items = (2000 * np.exp(-3 * x)).astype(np.uint64)
+    wgt = (items * (1 + 400 * x ** 3)).astype(np.uint64)
+    grp = (items * (1 + 12 * x)).astype(np.uint64)
+    hg = np.concatenate([wgt, items, grp])
+    cost = [400.0, 125.0, 17.5, 0.0]
+    total = cost[0] * items + cost[1] * grp + cost[2] * wgt
+    cum = np.cumsum(total)
+    for world in (2, 4, 8):
+        equal_sum = np.array([int(np.searchsorted(cum, cum[-1] * d / world)) + 1 for d in range(1, world)])
+        got, _, _ = plan_exchange(world, hg, hg, 42, 600.0, cost=cost)
+        assert np.all(np.diff(got.astype(np.int64)) >= 0)
+        assert _phase_objective(hg, got, cost) <= _phase_objective(hg, equal_sum, cost) * (1 + 1e-9)
+    assert _phase_objective(hg, got, cost) < 0.97 * _phase_objective(hg, equal_sum, cost)
 
 
 def test_shard_proteins_covers_the_proteome_in_order():
