@@ -550,6 +550,7 @@ def sharded_parity(torch, dist, dbi, g, info, res, off, params, rank, world, n_s
     with the oracle alone, the entries of the same sampled proteins, and each of them must be held by
     EXACTLY ONE rank -- zero-tolerance query, same peptide string, same mod pattern, the protein in the
     list; plus local sortedness and slices cut at the splitter masses."""
+    from dbindex_b200.multigpu import owned_mask
     from oracle.oracle_py import Oracle
     srng = np.random.default_rng(5)
     P = len(off) - 1
@@ -589,15 +590,12 @@ def sharded_parity(torch, dist, dbi, g, info, res, off, params, rank, world, n_s
     for s in sorted(set([0, max(0, n - chunk)] + [int(x) for x in rng.integers(0, max(1, n - chunk), size=4)])):
         mm = g.fetch(s, min(chunk, n - s), with_ids=False)["mass"]
         bad += 0 if np.all(np.diff(mm) >= 0) else 1
-        if len(mm) and s == 0 and rank > 0:
-            bad += 0 if mm[0] >= sm[rank - 1] else 1
-        if len(mm) and s + len(mm) == n and rank < world - 1:
-            bad += 0 if mm[-1] < sm[rank] else 1
+        bad += 0 if np.all(owned_mask(mm, sm, rank, world)) else 1  # every entry lies in a slice this rank holds
     t2 = torch.tensor([bad], device="cuda", dtype=torch.int64)
     dist.all_reduce(t2)
     return {"checked": int(len(m)) + 6 * world, "failed": failed + int(t2.item()),
             "what": f"{len(m)} oracle-derived entries of {n_sample} sampled proteins each held by exactly one rank (string, mod "
-                    "pattern, protein list); every slice sorted and cut at the splitter masses"}
+                    "pattern, protein list); every rank's entries sorted and inside the slices it holds"}
 
 
 def run_sharded(args, rank: int, local_rank: int, world: int):
@@ -663,7 +661,7 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
         e0.record(stream)
         info = build_sharded(GpuShardEngine(g, dev))
         e1.record(stream)
-        sel = route_queries(lo, hi, info["split_mass"], rank)
+        sel = route_queries(lo, hi, info["split_mass"], rank, world)
         d_lo = torch.from_numpy(lo[sel]).cuda()
         d_hi = torch.from_numpy(hi[sel]).cuda()
         stream.synchronize()
@@ -691,7 +689,7 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
     # ---- e2e: fresh handle, host buffers, copies and routing inside the timed region ----
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
     h_res, h_off = pin(sres), pin(soff.view(np.int64))
-    sel0 = route_queries(lo, hi, info["split_mass"], rank)
+    sel0 = route_queries(lo, hi, info["split_mass"], rank, world)
     sink = PinnedHits(g.query_hits_begin(lo[sel0], hi[sel0]))
     e2e_ms = []
     for i in range(1 + max(1, min(args.steps, 3))):
@@ -708,7 +706,7 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
         t1 = time.perf_counter()
         inf2 = build_sharded(GpuShardEngine(g2, dev))
         t2 = time.perf_counter()
-        sel = route_queries(lo, hi, inf2["split_mass"], rank)
+        sel = route_queries(lo, hi, inf2["split_mass"], rank, world)
         c2 = g2.query_hits_begin(lo[sel], hi[sel])
         t3 = time.perf_counter()
         g2.query_hits_read(sink.bufs)
@@ -724,7 +722,9 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
             e2e_ms.append(a.elapsed_time(b))
 
     per_rank = [None] * world
-    dist.all_gather_object(per_rank, {"entries": int(n_entries), "hits": int(hits), "query_ms": round(sum(query_ms) / len(query_ms), 3),
+    dist.all_gather_object(per_rank, {"entries": int(n_entries), "records": int(info.get("recv0", 0)),
+                                      "groups": int(info.get("recv1", 0)), "unique": int(st["n_unique"]),
+                                      "hits": int(hits), "query_ms": round(sum(query_ms) / len(query_ms), 3),
                                       **{k: round(v, 3) for k, v in st["stage_ms"].items() if v > 0}})
     t = torch.tensor([float(sum(step_ms)), float(sum(query_ms)), float(sum(e2e_ms)) / len(e2e_ms), a2a_ms],
                      device="cuda", dtype=torch.float64)
@@ -747,9 +747,10 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
                        "proteins_total": args.proteins * world, "residues_total": int(res.nbytes),
                        "entries_total": int(entries_all), "unique_total": info["n_unique"],
                        "queries": nq, "l2": "flushed between iterations (256 MiB write)",
-                       "parallelism": f"{world} GPUs: FASTA sharded by protein, residues replicated over NVLink, "
-                                      "range-sharded digest, fused multisplit + peer-memory scatter by mass slice "
-                                      "(records, then variant groups with their site masks), routed queries"},
+                       "parallelism": f"{world} GPUs: FASTA sharded by protein (each rank digests its shard while the "
+                                      "others arrive over NVLink), fused multisplit + peer-memory scatter by mass slice "
+                                      f"(records, then variant groups with their site masks; {info.get('n_slices', world)} "
+                                      "folded slices, one light + one heavy per rank), routed queries"},
             "queries": {"value": nq * K / (q_ms / 1e3), "unit": "queries/s", "hits_per_batch": int(hits_all),
                         "ms_per_batch": q_ms / K,
                         "includes": "host routing + H2D of the routed bounds + materialisation of every hit in HBM"},
@@ -771,6 +772,8 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
             "e2e_host_ms_rank0_last_step": {k: round(v, 3) for k, v in e2e_host.items()},
             "device_stage_ms_rank0_last_step": {k: round(v, 3) for k, v in st["stage_ms"].items() if v > 0},
             "per_rank_last_step": {k: [r.get(k, 0) for r in per_rank] for k in per_rank[0]},
+            "split_mass": [float(x) for x in info["split_mass"]],
+            "step_ms_rank0": [round(float(x), 3) for x in step_ms],
         }
         print(json.dumps(line), flush=True)
     barrier()

@@ -210,6 +210,9 @@ struct dbi_handle {
   uint64_t prot_off[kMaxRanks + 1] = {};  // global id of every rank's first protein
   uint64_t pos_off[kMaxRanks + 1] = {};   // buffer position of every rank's first separator
   bool mg_layout = false;                 // dbi_mg_set_shards done (d_res / d_pstart are views of window 0)
+  cudaStream_t side_stream = nullptr;     // carries the peer pulls of the proteome next to the digest
+  cudaEvent_t pull_done = nullptr;
+  bool pull_pending = false;
   uint64_t ent_base_off = 0;  // global id of this rank's first unique peptide (0 on a single GPU)
   uint64_t uoff[kMaxRanks + 1] = {};      // global id of every rank's first unique peptide
   uint64_t uniq_cap[kMaxRanks] = {};      // layout capacity of every rank's window 2
@@ -219,7 +222,8 @@ struct dbi_handle {
   DevBuf mg_vkey, mg_vpay;                   // local groups / variants between listing and exchange
   uint64_t mg_v = 0;
   uint64_t mg_recv[2] = {};                  // items delivered to this rank by exchange 0 / 1
-  uint64_t mg_thr[2][kMaxRanks] = {};        // key thresholds of the two exchanges (query routing)
+  uint64_t mg_thr[2][kMaxSlices] = {};       // key thresholds of the two exchanges (query routing)
+  int mg_nthr[2] = {};                       // how many: slices - 1
 
   // pending result of dbi_query_hits (device side), read by dbi_query_hits_read
   struct HitResult {
@@ -396,6 +400,10 @@ uint64_t read_u64(dbi_handle* h, const uint64_t* d) {
 }
 
 void free_index(dbi_handle* h) {
+  if (h->pull_pending) {  // peer copies into d_res still in flight
+    cudaStreamSynchronize(h->side_stream);
+    h->pull_pending = false;
+  }
   h->built = false;
   h->hits.drop();
   h->d_res.release();
@@ -1182,9 +1190,10 @@ int dbi_build(dbi_handle* h) {
   tile_offs.alloc((tiles + 1) * 8, h->arena);
   start_cnt.alloc(tiles * kDigestTile, h->arena);
   uint64_t N = 0;
+  const DigestRange whole{0u, h->res_end, 0u, n_prot};
   {
     Stage sg(h, DBI_STAGE_DIGEST_COUNT);
-    launch_digest_count(h->d_res.as<uint8_t>(), h->res_end, h->res_alloc, h->d_tables.as<DevTables>(), h->cfg, 0,
+    launch_digest_count(h->d_res.as<uint8_t>(), whole, h->res_alloc, h->d_tables.as<DevTables>(), h->cfg, 0,
                         (uint32_t)tiles, start_cnt.as<uint8_t>(), tile_counts.as<uint32_t>(), h->d_err.as<uint32_t>(), s);
     launch_scan_u32_to_u64(tile_counts.as<uint32_t>(), tiles, tile_offs.as<uint64_t>(), s);
     N = read_u64(h, tile_offs.as<uint64_t>() + tiles);
@@ -1202,9 +1211,9 @@ int dbi_build(dbi_handle* h) {
   r_len.alloc(N * 2, h->arena);
   {
     Stage sg(h, DBI_STAGE_DIGEST_EMIT);
-    launch_digest_emit(h->d_res.as<uint8_t>(), h->res_end, h->res_alloc, h->d_tables.as<DevTables>(), h->cfg, 0,
+    launch_digest_emit(h->d_res.as<uint8_t>(), whole, h->res_alloc, h->d_tables.as<DevTables>(), h->cfg, 0,
                        (uint32_t)tiles, start_cnt.as<uint8_t>(), tile_offs.as<uint64_t>(), h->d_pstart.as<uint32_t>(),
-                       n_prot, r_mass.as<uint64_t>(), r_gpos.as<uint32_t>(), r_prot.as<uint32_t>(),
+                       r_mass.as<uint64_t>(), r_gpos.as<uint32_t>(), r_prot.as<uint32_t>(),
                        r_len.as<uint16_t>(), nullptr, h->d_err.as<uint32_t>(), s);
     h->st.algo_bytes[DBI_STAGE_DIGEST_EMIT] += 2ull * h->res_end + N * 18;
   }
@@ -1779,6 +1788,11 @@ void dbi_destroy(dbi_handle* h) {
   cudaStreamSynchronize(h->stream);
   h->arena.flush();
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  if (h->side_stream) {
+    cudaStreamSynchronize(h->side_stream);
+    cudaStreamDestroy(h->side_stream);
+    cudaEventDestroy(h->pull_done);
+  }
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }

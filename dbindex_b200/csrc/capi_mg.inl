@@ -107,6 +107,32 @@ int mg_side_classes(const dbi_handle* h) { return h->cfg.n_seq > 0 ? h->cfg.n_cl
 
 int mg_shift(const KeySpace& ks) { return ks.nbits > 12 ? ks.nbits - 12 : 0; }
 
+// fills the thresholds of a plan from bin splitters; false (error set) if they are malformed
+bool mg_fill_plan(MgPlan& pl, int W, int n_slices, const uint32_t* bin_splitters, int sh) {
+  std::memset(&pl, 0, sizeof(pl));
+  if ((n_slices != W && n_slices != 2 * W) || (n_slices > 1 && !bin_splitters)) {
+    set_error("n_slices must be world or 2 * world (%d for world %d)", n_slices, W);
+    return false;
+  }
+  pl.world = W;
+  pl.n_thr = n_slices - 1;
+  for (int d = 0; d + 1 < n_slices; ++d) {
+    if (d > 0 && bin_splitters[d] < bin_splitters[d - 1]) {
+      set_error("bin_splitters must be ascending");
+      return false;
+    }
+    pl.thr[d] = (uint64_t)bin_splitters[d] << sh;
+  }
+  return true;
+}
+
+// the main stream waits for the shards pulled on the side stream
+void mg_join_pull(dbi_handle* h) {
+  if (!h->pull_pending) return;
+  DBI_CUDA(cudaStreamWaitEvent(h->stream, h->pull_done, 0));
+  h->pull_pending = false;
+}
+
 }  // namespace
 
 extern "C" {
@@ -289,9 +315,15 @@ int dbi_mg_pull_proteome(dbi_handle* h) {
     return DBI_ENOTINIT;
   }
   const int W = h->mg_world, r = h->mg_rank;
-  cudaStream_t st = h->stream;
+  // The copies run on the handle's side stream, concurrently with the digest of the own shard (which reads
+  // nothing else); whatever reads foreign residues afterwards waits for pull_done (mg_join_pull).
+  if (!h->side_stream) {
+    DBI_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    DBI_CUDA(cudaEventCreateWithFlags(&h->pull_done, cudaEventDisableTiming));
+  }
+  cudaStream_t st = h->side_stream;
+  // the own shard is packed (main stream, synchronised by dbi_mg_set_shards); the last rank also zeroed the tail
   const uint64_t pstart_at = (uint64_t)((uint8_t*)h->d_pstart.p - (uint8_t*)h->d_res.p);
-  Stage sg(h, DBI_STAGE_PACK);
   for (int k = 1; k < W; ++k) {
     const int s = (r + k) % W;  // start with the next rank: the pulls of the ranks spread over the links
     const uint8_t* peer = (const uint8_t*)h->win[kWinProt].peer[s];
@@ -309,7 +341,8 @@ int dbi_mg_pull_proteome(dbi_handle* h) {
                                cudaMemcpyDefault, st));
     h->st.algo_bytes[DBI_STAGE_PACK] += 2 * (b1 - b0) + 8 * (p1 - p0);
   }
-  DBI_CUDA(cudaStreamSynchronize(st));
+  DBI_CUDA(cudaEventRecord(h->pull_done, st));
+  h->pull_pending = true;
   return DBI_OK;
   DBI_API_END
 }
@@ -325,12 +358,15 @@ int dbi_mg_digest(dbi_handle* h, uint64_t* n_records) {
     return DBI_ENOTINIT;
   }
   cudaStream_t s = h->stream;
-  const uint32_t n_prot = (uint32_t)h->prot_off[h->mg_world];
-  const uint64_t tiles_all = ((uint64_t)h->res_end + kDigestTile - 1) / kDigestTile;
-  // contiguous, ascending tile ranges: rank order == global emission order
-  const uint32_t t0 = (uint32_t)(tiles_all * h->mg_rank / h->mg_world);
-  const uint32_t t1 = (uint32_t)(tiles_all * (h->mg_rank + 1) / h->mg_world);
-  const uint32_t nt = t1 - t0;
+  // Every rank digests the start positions of ITS OWN shard: contiguous, ascending ranges, so rank order ==
+  // global emission order, and nothing outside the shard is read for the result -- the other shards may
+  // still be arriving (dbi_mg_pull_proteome runs on the side stream).
+  const int W = h->mg_world, r = h->mg_rank;
+  const uint64_t lo_pos = h->pos_off[r], hi_pos = r == W - 1 ? (uint64_t)h->res_end : h->pos_off[r + 1];
+  const DigestRange rg{(uint32_t)lo_pos, (uint32_t)hi_pos, (uint32_t)h->prot_off[r], (uint32_t)h->prot_off[r + 1]};
+  const uint32_t t0 = (uint32_t)(lo_pos / kDigestTile);
+  const uint32_t t1 = (uint32_t)((hi_pos + kDigestTile - 1) / kDigestTile);
+  const uint32_t nt = hi_pos > lo_pos ? t1 - t0 : 0u;
   DevBuf tile_counts, tile_offs, start_cnt;
   tile_counts.alloc((uint64_t)nt * 4, h->arena);
   tile_offs.alloc(((uint64_t)nt + 1) * 8, h->arena);
@@ -338,7 +374,7 @@ int dbi_mg_digest(dbi_handle* h, uint64_t* n_records) {
   uint64_t N = 0;
   {
     Stage sg(h, DBI_STAGE_DIGEST_COUNT);
-    launch_digest_count(h->d_res.as<uint8_t>(), h->res_end, h->res_alloc, h->d_tables.as<DevTables>(), h->cfg, t0, nt,
+    launch_digest_count(h->d_res.as<uint8_t>(), rg, h->res_alloc, h->d_tables.as<DevTables>(), h->cfg, t0, nt,
                         start_cnt.as<uint8_t>(), tile_counts.as<uint32_t>(), h->d_err.as<uint32_t>(), s);
     launch_scan_u32_to_u64(tile_counts.as<uint32_t>(), nt, tile_offs.as<uint64_t>(), s);
     N = read_u64(h, tile_offs.as<uint64_t>() + nt);
@@ -359,8 +395,8 @@ int dbi_mg_digest(dbi_handle* h, uint64_t* n_records) {
   if (h->cfg.max_mods > 0) h->mg_nmod.alloc(std::max<uint64_t>(N, 1), h->arena);
   {
     Stage sg(h, DBI_STAGE_DIGEST_EMIT);
-    launch_digest_emit(h->d_res.as<uint8_t>(), h->res_end, h->res_alloc, h->d_tables.as<DevTables>(), h->cfg, t0, nt,
-                       start_cnt.as<uint8_t>(), tile_offs.as<uint64_t>(), h->d_pstart.as<uint32_t>(), n_prot,
+    launch_digest_emit(h->d_res.as<uint8_t>(), rg, h->res_alloc, h->d_tables.as<DevTables>(), h->cfg, t0, nt,
+                       start_cnt.as<uint8_t>(), tile_offs.as<uint64_t>(), h->d_pstart.as<uint32_t>(),
                        h->mg_mass.as<uint64_t>(), h->mg_gpos.as<uint32_t>(), h->mg_prot.as<uint32_t>(),
                        h->mg_len.as<uint16_t>(), h->mg_nmod.as<uint8_t>(), h->d_err.as<uint32_t>(), s);
     h->st.algo_bytes[DBI_STAGE_DIGEST_EMIT] += 2ull * nt * kDigestTile + N * 18;
@@ -426,30 +462,36 @@ int dbi_mg_hist(dbi_handle* h, int stage, void* d_hist, int* shift) {
   DBI_API_END
 }
 
-// Pure host arithmetic: bin splitters from the global histograms [weighted | plain | groups] (bins are never
-// split, so equal masses -- hence equal peptides -- meet on one rank), this rank's send counts from its own
-// plain histogram, every rank's receive total from the global plain histogram.
+// Pure host arithmetic: the cuts of the mass axis from the global histograms [weighted | plain | groups]
+// (bins are never split, so equal masses -- hence equal peptides -- meet on one rank), this rank's send
+// counts from its own plain histogram, every rank's receive total from the global plain histogram.
 //
-// A sharded build runs in PHASES separated by exchanges, and a step lasts as long as the slowest rank of
-// every phase.  Per bin:
+// n_slices = world: slice s lives on rank s.  n_slices = 2 * world: FOLDED slices, slice s lives on rank
+// s < world ? s : 2 * world - 1 - s -- every rank holds one light and one heavy slice.  With differential
+// mods the light end of the axis is crowded with records (base phase) and the heavy end with variants
+// (variant and search phases); contiguous slices can balance the sum of the phases but not each of them,
+// and a sharded build lasts as long as the slowest rank of EVERY phase (the exchanges are barriers).
+//
+// Per bin:
 //   base phase    B = cost[0] * items                      (sort + merge of the records / of the items)
 //   variant phase V = cost[1] * groups + cost[2] * weight  (group sort; expansion writes per index entry)
 //   search phase  Q = cost[3] * weight^2 * mass / (width * total weight)
 //     = expected HITS of precursor queries that follow the indexed mass density at a relative (ppm) tolerance:
 //     queries landing in the bin ~ weight / total, hits per query ~ (weight / width) * mass.  An index is built
 //     once and searched many times, so the slices are cut for the search load too.
-// The cuts start where the SUM B + V + Q is equal per rank; when more than one phase has a cost they are then
+// The cuts start where the SUM B + V + Q is equal per slice; when more than one phase has a cost they are then
 // moved, one at a time, to wherever  max_r B + max_r V + max_r Q  gets smallest (coordinate descent on the
 // prefix sums: a few thousand operations).  cost == NULL: {0, 0, 1, 0} (equal weight).  Every rank runs this on
 // the same global histogram and gets the same splitters.
 int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_local, int shift, double min_mass,
-                const double* cost, uint32_t* bin_splitters, uint64_t* send_counts, uint64_t* recv_totals) {
+                const double* cost, int n_slices, uint32_t* bin_splitters, uint64_t* send_counts,
+                uint64_t* recv_totals) {
   if (world < 1 || world > kMaxRanks || !hist_global || !hist_local || !send_counts || !recv_totals ||
-      (world > 1 && !bin_splitters) || shift < 0 || shift > 52) {
+      (n_slices != world && n_slices != 2 * world) || (n_slices > 1 && !bin_splitters) || shift < 0 || shift > 52) {
     set_error("bad argument");
     return DBI_EINVAL;
   }
-  const int B = kMgBins;
+  const int B = kMgBins, S = n_slices, W = world;
   const double c_item = cost ? cost[0] : 0.0, c_grp = cost ? cost[1] : 0.0, c_w = cost ? cost[2] : 1.0,
                c_hit = cost ? cost[3] : 0.0;
   double w_total = 0;
@@ -477,12 +519,12 @@ int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_loc
     P[2][b + 1] = P[2][b] + q;
   }
   const double total = P[0][B] + P[1][B] + P[2][B];
-  std::vector<int> cut(world + 1, 0);  // slice d = bins [cut[d], cut[d + 1])
-  cut[world] = B;
+  std::vector<int> cut(S + 1, 0);  // slice s = bins [cut[s], cut[s + 1])
+  cut[S] = B;
   {
     int b = 0;
-    for (int d = 1; d < world; ++d) {
-      const double target = total * (double)d / (double)world;
+    for (int d = 1; d < S; ++d) {
+      const double target = total * (double)d / (double)S;
       // first bin boundary at which at least `target` of the cost lies below
       while (b < B && (P[0][b + 1] + P[1][b + 1] + P[2][b + 1]) < target) ++b;
       int c = total > 0 ? std::min(b + 1, B) : 0;
@@ -490,55 +532,77 @@ int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_loc
       cut[d] = c;
     }
   }
+  auto owner = [&](int sl) { return (int)mg_slice_owner((uint32_t)sl, (uint32_t)S, (uint32_t)W); };
   const int phases = (P[0][B] > 0) + (P[1][B] > 0) + (P[2][B] > 0);
-  if (world > 1 && phases > 1) {
+  const char* no_refine = std::getenv("DBI_MG_REFINE");  // "0": keep the equal-sum cuts (diagnostic)
+  if (S > 1 && phases > 1 && !(no_refine && no_refine[0] == '0')) {
+    double load[3][kMaxRanks];  // per phase and rank, under the current cuts
+    auto slice_cost = [&](int ph, int sl) { return P[ph][cut[sl + 1]] - P[ph][cut[sl]]; };
+    auto reload = [&]() {
+      for (int ph = 0; ph < 3; ++ph) {
+        for (int r = 0; r < W; ++r) load[ph][r] = 0;
+        for (int sl = 0; sl < S; ++sl) load[ph][owner(sl)] += slice_cost(ph, sl);
+      }
+    };
     auto objective = [&]() {
       double o = 0;
       for (int ph = 0; ph < 3; ++ph) {
         double mx = 0;
-        for (int d = 0; d < world; ++d) mx = std::max(mx, P[ph][cut[d + 1]] - P[ph][cut[d]]);
+        for (int r = 0; r < W; ++r) mx = std::max(mx, load[ph][r]);
         o += mx;
       }
       return o;
     };
+    // moving cut d shifts cost between slices d - 1 and d only
+    auto move_cut = [&](int d, int c) {
+      const int ra = owner(d - 1), rb = owner(d);
+      for (int ph = 0; ph < 3; ++ph) {
+        const double delta = P[ph][c] - P[ph][cut[d]];
+        load[ph][ra] += delta;
+        load[ph][rb] -= delta;
+      }
+      cut[d] = c;
+    };
+    reload();
     double best = objective();
-    for (int sweep = 0; sweep < 6; ++sweep) {
+    for (int sweep = 0; sweep < 5; ++sweep) {
       bool moved = false;
-      for (int d = 1; d < world; ++d) {
+      for (int d = 1; d < S; ++d) {
         const int lo = cut[d - 1], hi = cut[d + 1];
         int keep = cut[d];
         // coarse grid over the whole gap, then two refinements around the best candidate
         int span = hi - lo, centre = keep;
         for (int level = 0; level < 3 && span > 0; ++level) {
-          const int steps = 32;
+          const int steps = 16;
           const int a = level == 0 ? lo : std::max(lo, centre - span), z = level == 0 ? hi : std::min(hi, centre + span);
           for (int i = 0; i <= steps; ++i) {
-            const int c = a + (int)((int64_t)(z - a) * i / steps);
-            cut[d] = c;
+            move_cut(d, a + (int)((int64_t)(z - a) * i / steps));
             const double o = objective();
             if (o < best * (1.0 - 1e-12)) {
               best = o;
-              keep = c;
+              keep = cut[d];
               moved = true;
             }
           }
           centre = keep;
           span = std::max(1, (z - a) / steps);
         }
-        cut[d] = keep;
+        move_cut(d, keep);
       }
+      reload();  // drop the rounding drift of the incremental updates
       if (!moved) break;
     }
   }
-  for (int d = 1; d < world; ++d) bin_splitters[d - 1] = (uint32_t)cut[d];
-  for (int d = 0; d < world; ++d) {
+  for (int d = 1; d < S; ++d) bin_splitters[d - 1] = (uint32_t)cut[d];
+  for (int d = 0; d < W; ++d) send_counts[d] = recv_totals[d] = 0;
+  for (int sl = 0; sl < S; ++sl) {
     uint64_t sc = 0, rt = 0;
-    for (int x = cut[d]; x < cut[d + 1]; ++x) {
+    for (int x = cut[sl]; x < cut[sl + 1]; ++x) {
       sc += hist_local[B + x];
       rt += hist_global[B + x];
     }
-    send_counts[d] = sc;
-    recv_totals[d] = rt;
+    send_counts[owner(sl)] += sc;
+    recv_totals[owner(sl)] += rt;
   }
   return DBI_OK;
 }
@@ -570,19 +634,17 @@ void dbi_mg_default_cost(int stage, int has_mods, double* cost) {
   }
 }
 
-int dbi_mg_count(dbi_handle* h, int stage, const uint32_t* bin_splitters, uint64_t* send_counts) {
+int dbi_mg_count(dbi_handle* h, int stage, const uint32_t* bin_splitters, int n_slices, uint64_t* send_counts) {
   DBI_API_BEGIN(h)
   const int W = h->mg_world;
-  if ((W > 1 && !bin_splitters) || !send_counts || (stage != 0 && stage != 1)) {
+  if (!send_counts || (stage != 0 && stage != 1)) {
     set_error("bad argument");
     return DBI_EINVAL;
   }
   const KeySpace ks(h->p.min_mass, h->p.max_mass);
   const int sh = mg_shift(ks);
   MgPlan pl;
-  std::memset(&pl, 0, sizeof(pl));
-  pl.world = W;
-  for (int d = 0; d + 1 < W; ++d) pl.thr[d] = (uint64_t)bin_splitters[d] << sh;
+  if (!mg_fill_plan(pl, W, n_slices, bin_splitters, sh)) return DBI_EINVAL;
   DevBuf cnt;
   cnt.alloc(kMaxRanks * 8, h->arena);
   DBI_CUDA(cudaMemsetAsync(cnt.p, 0, kMaxRanks * 8, h->stream));
@@ -598,10 +660,10 @@ int dbi_mg_count(dbi_handle* h, int stage, const uint32_t* bin_splitters, uint64
   DBI_API_END
 }
 
-int dbi_mg_scatter(dbi_handle* h, int stage, const uint32_t* bin_splitters, const uint64_t* matrix) {
+int dbi_mg_scatter(dbi_handle* h, int stage, const uint32_t* bin_splitters, int n_slices, const uint64_t* matrix) {
   DBI_API_BEGIN(h)
   const int W = h->mg_world, r = h->mg_rank;
-  if ((W > 1 && !bin_splitters) || !matrix || (stage != 0 && stage != 1)) {
+  if (!matrix || (stage != 0 && stage != 1)) {
     set_error("bad argument");
     return DBI_EINVAL;
   }
@@ -610,16 +672,9 @@ int dbi_mg_scatter(dbi_handle* h, int stage, const uint32_t* bin_splitters, cons
   const int sh = mg_shift(ks);
   const int C = mg_side_classes(h);
   MgPlan pl;
-  std::memset(&pl, 0, sizeof(pl));
-  pl.world = W;
-  for (int d = 0; d + 1 < W; ++d) {
-    if (d > 0 && bin_splitters[d] < bin_splitters[d - 1]) {
-      set_error("bin_splitters must be ascending");
-      return DBI_EINVAL;
-    }
-    pl.thr[d] = (uint64_t)bin_splitters[d] << sh;
-    h->mg_thr[stage][d] = pl.thr[d];
-  }
+  if (!mg_fill_plan(pl, W, n_slices, bin_splitters, sh)) return DBI_EINVAL;
+  h->mg_nthr[stage] = pl.n_thr;
+  for (int d = 0; d < pl.n_thr; ++d) h->mg_thr[stage][d] = pl.thr[d];
   uint64_t recv[kMaxRanks] = {}, sent = 0;
   for (int d = 0; d < W; ++d) {
     for (int src = 0; src < W; ++src) {
@@ -691,6 +746,7 @@ int dbi_mg_scatter(dbi_handle* h, int stage, const uint32_t* bin_splitters, cons
 
 int dbi_mg_index_base(dbi_handle* h) {
   DBI_API_BEGIN(h)
+  mg_join_pull(h);  // the records delivered here name residues of every shard
   const uint64_t n = h->mg_recv[0];
   const KeySpace ks(h->p.min_mass, h->p.max_mass);
   const RecLayout L(n);
@@ -802,6 +858,12 @@ int dbi_mg_finish(dbi_handle* h) {
   DBI_API_END
 }
 
+int dbi_mg_slices(dbi_handle* h) {
+  if (!h) return 0;
+  const int stage = h->cfg.max_mods > 0 ? 1 : 0;
+  return h->mg_world > 1 ? h->mg_nthr[stage] + 1 : 1;
+}
+
 int dbi_mg_split_masses(dbi_handle* h, double* split_mass) {
   if (!h || (h->mg_world > 1 && !split_mass)) {
     set_error("null argument");
@@ -809,10 +871,11 @@ int dbi_mg_split_masses(dbi_handle* h, double* split_mass) {
   }
   const KeySpace ks(h->p.min_mass, h->p.max_mass);
   const int stage = h->cfg.max_mods > 0 ? 1 : 0;
-  for (int d = 0; d + 1 < h->mg_world; ++d) {
-    const uint64_t bits = h->mg_thr[stage][d] + ks.base_bits;
-    std::memcpy(&split_mass[d], &bits, 8);
-  }
+  if (h->mg_world > 1)
+    for (int d = 0; d < h->mg_nthr[stage]; ++d) {
+      const uint64_t bits = h->mg_thr[stage][d] + ks.base_bits;
+      std::memcpy(&split_mass[d], &bits, 8);
+    }
   return DBI_OK;
 }
 
@@ -864,7 +927,9 @@ int dbi_mg_build_local(dbi_handle** hs, int n) {
     const bool mods = hs[0]->cfg.max_mods > 0;
     const int C = mg_side_classes(hs[0]);
     std::vector<uint64_t> matrix((size_t)W * W), recv(W);
-    std::vector<uint32_t> split(W);
+    // folded slices when differential mods make the phases of a build pull the cuts apart
+    const int S = (mods && W > 1) ? 2 * W : W;
+    std::vector<uint32_t> split((size_t)S);
     // exchange 0 plans the cuts (histograms -> equal-cost splitters); exchange 1 reuses them, so the variant
     // groups of a peptide mostly stay on the GPU that owns the peptide: only the counts are needed
     auto exchange = [&](int stage) -> int {
@@ -887,12 +952,12 @@ int dbi_mg_build_local(dbi_handle** hs, int n) {
         double cost[4];
         dbi_mg_default_cost(stage, mods ? 1 : 0, cost);
         for (int r = 0; r < W; ++r)
-          if (int rc = dbi_mg_plan(W, global.data(), &local[(size_t)r * HB], shift_of, hs[0]->p.min_mass, cost, split.data(),
-                                   &matrix[(size_t)r * W], recv.data()))
+          if (int rc = dbi_mg_plan(W, global.data(), &local[(size_t)r * HB], shift_of, hs[0]->p.min_mass, cost, S,
+                                   split.data(), &matrix[(size_t)r * W], recv.data()))
             return rc;
       } else {
         for (int r = 0; r < W; ++r)
-          if (int rc = dbi_mg_count(hs[r], stage, split.data(), &matrix[(size_t)r * W])) return rc;
+          if (int rc = dbi_mg_count(hs[r], stage, split.data(), S, &matrix[(size_t)r * W])) return rc;
         for (int d = 0; d < W; ++d) {
           recv[d] = 0;
           for (int r = 0; r < W; ++r) recv[d] += matrix[(size_t)r * W + d];
@@ -907,7 +972,7 @@ int dbi_mg_build_local(dbi_handle** hs, int n) {
       if (int rc = connect(kWinArena)) return rc;
       if (stage == 0)
         if (int rc = connect(kWinUniq)) return rc;
-      MG_ALL(dbi_mg_scatter(h, stage, split.data(), matrix.data()));
+      MG_ALL(dbi_mg_scatter(h, stage, split.data(), S, matrix.data()));
       return DBI_OK;
     };
     if (int rc = exchange(0)) return rc;

@@ -215,7 +215,7 @@ __device__ __forceinline__ void stage_tile(TileSmem& s, const uint8_t* __restric
 // back to HBM for K4.
 template <bool FILTERS>
 __global__ void __launch_bounds__(DG_THREADS)
-    digest_count_kernel(const uint8_t* __restrict__ res, uint32_t res_end, uint64_t res_alloc,
+    digest_count_kernel(const uint8_t* __restrict__ res, DigestRange rg, uint64_t res_alloc,
                         const DevTables* __restrict__ tb, DigestCfg cfg, uint32_t tile0,
                         uint8_t* __restrict__ start_cnt, uint32_t* __restrict__ tile_counts, uint32_t* err) {
   __shared__ TileSmem s;
@@ -228,7 +228,8 @@ __global__ void __launch_bounds__(DG_THREADS)
   for (int k = 0; k < DG_SPT; ++k) {
     const uint32_t l = t * DG_SPT + k;
     const uint8_t inf = s.info[l + 1];
-    if (w0 + 1 + l < res_end && !(inf & I_SEP) && (cfg.semi || (inf & I_NOK))) {
+    const uint32_t g = w0 + 1 + l;
+    if (g >= rg.start_lo && g < rg.start_hi && !(inf & I_SEP) && (cfg.semi || (inf & I_NOK))) {
       live |= 1u << k;
       ++n_live;
     }
@@ -257,10 +258,10 @@ __global__ void __launch_bounds__(DG_THREADS)
 // ---- K4 -----------------------------------------------------------------------------
 template <bool FILTERS>
 __global__ void __launch_bounds__(DG_THREADS)
-    digest_emit_kernel(const uint8_t* __restrict__ res, uint32_t res_end, uint64_t res_alloc,
+    digest_emit_kernel(const uint8_t* __restrict__ res, DigestRange rg, uint64_t res_alloc,
                        const DevTables* __restrict__ tb, DigestCfg cfg, uint32_t tile0,
                        const uint8_t* __restrict__ start_cnt, const uint64_t* __restrict__ tile_offs,
-                       const uint32_t* __restrict__ pstart, uint32_t n_prot, uint64_t* __restrict__ o_mass,
+                       const uint32_t* __restrict__ pstart, uint64_t* __restrict__ o_mass,
                        uint32_t* __restrict__ o_gpos, uint32_t* __restrict__ o_prot, uint16_t* __restrict__ o_len,
                        uint8_t* __restrict__ o_nmod, uint32_t* err) {
   __shared__ TileSmem s;
@@ -273,9 +274,12 @@ __global__ void __launch_bounds__(DG_THREADS)
   const uint32_t w0 = (tile0 + blockIdx.x) * (uint32_t)kDigestTile;
   stage_tile(s, res, res_alloc, tb, w0, start_cnt + (size_t)blockIdx.x * kDigestTile);
   if (t == 0) {
-    // separators at positions <= w0 = proteins p with pstart[p] - 1 <= w0 (pstart has n_prot + 1 entries,
-    // the last one names the final separator): upper_bound(pstart, w0 + 1)
-    uint32_t lo = 0, hi = n_prot + 1;
+    // separators at positions <= w0.  Those below the range (rg.start_lo: the other shards of a sharded
+    // build, whose bytes may not have arrived yet) are known by count: rg.prot_lo, one per earlier protein.
+    // Inside the range: proteins p of [prot_lo, prot_hi] with pstart[p] - 1 <= w0 (pstart[prot_hi] names
+    // the separator that ends the range): upper_bound(pstart, w0 + 1)
+    uint32_t lo = rg.prot_lo, hi = rg.prot_hi + 1;
+    if (w0 < rg.start_lo) hi = lo;
     while (lo < hi) {
       const uint32_t mid = (lo + hi) >> 1;
       if (__ldg(pstart + mid) <= w0 + 1) lo = mid + 1; else hi = mid;
@@ -295,7 +299,7 @@ __global__ void __launch_bounds__(DG_THREADS)
       if (c[k] == 255u) c[k] = walk_start<FILTERS>(cx, w0 + 1 + t * DG_SPT + k, cfg, err, [](double, uint32_t, uint32_t) {});
       n_emit += c[k] ? 1u : 0u;
       sum += c[k];
-      if (s.info[1 + t * DG_SPT + k] & I_SEP) {
+      if ((s.info[1 + t * DG_SPT + k] & I_SEP) && w0 + 1 + t * DG_SPT + k >= rg.start_lo) {
         sepmask |= 1u << k;
         ++zeros;
       }
@@ -393,15 +397,15 @@ void launch_pack(const uint8_t* d_raw, const uint64_t* d_off, uint32_t n_prot, u
   DBI_LAUNCH(pack_kernel, grid, PK_THREADS, 0, s, d_raw, d_off, n_prot, n_res, d_res, d_pstart, pos_base, d_err);
 }
 
-void launch_digest_count(const uint8_t* d_res, uint32_t res_end, uint64_t res_alloc, const DevTables* d_tb,
+void launch_digest_count(const uint8_t* d_res, const DigestRange& rg, uint64_t res_alloc, const DevTables* d_tb,
                          const DigestCfg& cfg, uint32_t tile0, uint32_t ntiles, uint8_t* d_start_cnt,
                          uint32_t* d_tile_counts, uint32_t* d_err, cudaStream_t s) {
   if (ntiles == 0) return;
   if (cfg.mand_on || cfg.filt_max >= 0)
-    DBI_LAUNCH(digest_count_kernel<true>, ntiles, DG_THREADS, 0, s, d_res, res_end, res_alloc, d_tb, cfg, tile0,
+    DBI_LAUNCH(digest_count_kernel<true>, ntiles, DG_THREADS, 0, s, d_res, rg, res_alloc, d_tb, cfg, tile0,
                d_start_cnt, d_tile_counts, d_err);
   else
-    DBI_LAUNCH(digest_count_kernel<false>, ntiles, DG_THREADS, 0, s, d_res, res_end, res_alloc, d_tb, cfg, tile0,
+    DBI_LAUNCH(digest_count_kernel<false>, ntiles, DG_THREADS, 0, s, d_res, rg, res_alloc, d_tb, cfg, tile0,
                d_start_cnt, d_tile_counts, d_err);
 }
 
@@ -409,18 +413,18 @@ void launch_scan_u32_to_u64(const uint32_t* d_in, uint64_t n, uint64_t* d_offs, 
   DBI_LAUNCH(scan_u32_to_u64_kernel, 1, SC_THREADS, 0, s, d_in, n, d_offs);
 }
 
-void launch_digest_emit(const uint8_t* d_res, uint32_t res_end, uint64_t res_alloc, const DevTables* d_tb,
+void launch_digest_emit(const uint8_t* d_res, const DigestRange& rg, uint64_t res_alloc, const DevTables* d_tb,
                         const DigestCfg& cfg, uint32_t tile0, uint32_t ntiles, const uint8_t* d_start_cnt,
-                        const uint64_t* d_tile_offs, const uint32_t* d_pstart, uint32_t n_prot, uint64_t* o_mass,
+                        const uint64_t* d_tile_offs, const uint32_t* d_pstart, uint64_t* o_mass,
                         uint32_t* o_gpos, uint32_t* o_prot, uint16_t* o_len, uint8_t* o_nmod, uint32_t* d_err,
                         cudaStream_t s) {
   if (ntiles == 0) return;
   if (cfg.mand_on || cfg.filt_max >= 0)
-    DBI_LAUNCH(digest_emit_kernel<true>, ntiles, DG_THREADS, 0, s, d_res, res_end, res_alloc, d_tb, cfg, tile0,
-               d_start_cnt, d_tile_offs, d_pstart, n_prot, o_mass, o_gpos, o_prot, o_len, o_nmod, d_err);
+    DBI_LAUNCH(digest_emit_kernel<true>, ntiles, DG_THREADS, 0, s, d_res, rg, res_alloc, d_tb, cfg, tile0,
+               d_start_cnt, d_tile_offs, d_pstart, o_mass, o_gpos, o_prot, o_len, o_nmod, d_err);
   else
-    DBI_LAUNCH(digest_emit_kernel<false>, ntiles, DG_THREADS, 0, s, d_res, res_end, res_alloc, d_tb, cfg, tile0,
-               d_start_cnt, d_tile_offs, d_pstart, n_prot, o_mass, o_gpos, o_prot, o_len, o_nmod, d_err);
+    DBI_LAUNCH(digest_emit_kernel<false>, ntiles, DG_THREADS, 0, s, d_res, rg, res_alloc, d_tb, cfg, tile0,
+               d_start_cnt, d_tile_offs, d_pstart, o_mass, o_gpos, o_prot, o_len, o_nmod, d_err);
 }
 
 }  // namespace dbi

@@ -45,7 +45,13 @@ void launch_pack(const uint8_t* d_raw, const uint64_t* d_off, uint32_t n_prot, u
 // at 255) and per tile.  Tiles [tile0, tile0 + ntiles) of kDigestTile start positions each (a
 // multi-GPU rank digests only its own tile range of the replicated buffer).  res_alloc = bytes
 // readable at d_res (a multiple of 16: the tiles are staged with 16-byte bulk copies).
-void launch_digest_count(const uint8_t* d_res, uint32_t res_end, uint64_t res_alloc, const DevTables* d_tb,
+// The start positions a digest launch covers: [start_lo, start_hi) of the residue buffer, holding the
+// proteins [prot_lo, prot_hi) (a whole buffer: 0, res_end, 0, n_prot; a sharded build: the rank's own
+// shard, so that nothing outside it is read for the result -- the other shards may still be in flight).
+struct DigestRange {
+  uint32_t start_lo, start_hi, prot_lo, prot_hi;
+};
+void launch_digest_count(const uint8_t* d_res, const DigestRange& rg, uint64_t res_alloc, const DevTables* d_tb,
                          const DigestCfg& cfg, uint32_t tile0, uint32_t ntiles, uint8_t* d_start_cnt,
                          uint32_t* d_tile_counts, uint32_t* d_err, cudaStream_t s);
 
@@ -56,9 +62,9 @@ void launch_scan_u32_to_u64(const uint32_t* d_in, uint64_t n, uint64_t* d_offs, 
 // (one walk per emitting start: the per-start counts of K2 replace the counting walk)
 // o_nmod (optional): differential-mod sites of every record, saturating at 255 -- the sharded build
 // estimates a record's downstream cost from it
-void launch_digest_emit(const uint8_t* d_res, uint32_t res_end, uint64_t res_alloc, const DevTables* d_tb,
+void launch_digest_emit(const uint8_t* d_res, const DigestRange& rg, uint64_t res_alloc, const DevTables* d_tb,
                         const DigestCfg& cfg, uint32_t tile0, uint32_t ntiles, const uint8_t* d_start_cnt,
-                        const uint64_t* d_tile_offs, const uint32_t* d_pstart, uint32_t n_prot, uint64_t* o_mass,
+                        const uint64_t* d_tile_offs, const uint32_t* d_pstart, uint64_t* o_mass,
                         uint32_t* o_gpos, uint32_t* o_prot, uint16_t* o_len, uint8_t* o_nmod, uint32_t* d_err,
                         cudaStream_t s);
 
@@ -198,13 +204,21 @@ void launch_key_emit(const double* e_mass, uint64_t n, double factor, const uint
 
 // ---- multi-GPU exchange helpers (mg.cu) -----------------------------------------------------
 constexpr int kMgBins = 4096;  // histogram bins over the top bits of the radix key
-// Where the items of one exchange go.  dest(item) = number of thresholds <= (key - sub); this rank's
-// items for destination d arrive at rows row0[d] .. of d's arrays (after the items of the lower ranks).
+// Where the items of one exchange go.  The mass axis is cut into n_thr + 1 SLICES (slice of an item =
+// number of thresholds <= key - sub); there are `world` slices, slice s living on rank s, or 2 * world
+// FOLDED slices: slice s lives on rank s < world ? s : 2 * world - 1 - s, so that every rank holds one light
+// slice (many records, few variants) and one heavy slice (few records, many variants).  This rank's items
+// for destination d arrive at rows row0[d] .. of d's arrays (after the items of the lower ranks).
+constexpr int kMaxSlices = 2 * kMaxRanks;
 struct MgPlan {
-  uint64_t thr[kMaxRanks];
+  uint64_t thr[kMaxSlices];
   uint64_t row0[kMaxRanks];
   int world;
+  int n_thr;
 };
+__host__ __device__ inline uint32_t mg_slice_owner(uint32_t slice, uint32_t n_slices, uint32_t world) {
+  return slice < world ? slice : n_slices - 1u - slice;
+}
 // hist[0 .. kMgBins) += weight, hist[kMgBins .. 2 kMgBins) += 1, hist[2 kMgBins .. 3 kMgBins) += group estimate
 // over min(kMgBins-1, (key[i] - sub) >> shift) (hist is zeroed by the caller); weight of item i =
 // wpay ? (wpay[i] & wmask) + wadd  (group records carry their variant count)  :  wtab ? wtab[wcode[i]]

@@ -23,6 +23,13 @@ constexpr int MG_THREADS = 256;
 // (a group can stand for 2^27 variants) go straight to the 64-bit global bins, so nothing can wrap.
 constexpr uint32_t kMgMaxItemsPerCta = 1u << 16;
 
+// destination rank of a key: its slice (thresholds ascending), folded onto the ranks
+__device__ __forceinline__ uint32_t mg_dest(const MgPlan& pl, uint64_t k) {
+  uint32_t sl = 0;
+  for (int x = 0; x < pl.n_thr; ++x) sl += (pl.thr[x] <= k) ? 1u : 0u;
+  return mg_slice_owner(sl, (uint32_t)pl.n_thr + 1u, (uint32_t)pl.world);
+}
+
 __global__ void __launch_bounds__(MG_THREADS)
     mg_hist_kernel(const uint64_t* __restrict__ key, uint64_t n, uint64_t per_cta, uint64_t sub, int shift,
                    const uint64_t* __restrict__ wpay, uint64_t wmask, uint32_t wadd,
@@ -69,9 +76,7 @@ __global__ void __launch_bounds__(MG_THREADS)
   for (int d = 0; d < kMaxRanks; ++d) mine[d] = 0;
   const uint64_t stride = (uint64_t)gridDim.x * MG_THREADS;
   for (uint64_t i = (uint64_t)blockIdx.x * MG_THREADS + threadIdx.x; i < n; i += stride) {
-    const uint64_t k = key[i] - sub;
-    uint32_t d = 0;
-    for (int x = 0; x < pl.world - 1; ++x) d += (pl.thr[x] <= k) ? 1u : 0u;
+    const uint32_t d = mg_dest(pl, key[i] - sub);
 #pragma unroll
     for (int x = 0; x < kMaxRanks; ++x) mine[x] += (d == (uint32_t)x) ? 1u : 0u;
   }
@@ -138,8 +143,7 @@ __device__ __forceinline__ void sc_rank_tile(ScSmem& s, ScCtx& cx, const uint64_
     cx.valid[i] = e < cx.tile_n;
     uint32_t d = 0;
     if (cx.valid[i]) {
-      const uint64_t k = key[cx.base + e] - sub;
-      for (int x = 0; x < pl.world - 1; ++x) d += (pl.thr[x] <= k) ? 1u : 0u;  // thresholds ascending
+      d = mg_dest(pl, key[cx.base + e] - sub);
     } else {
       d = (uint32_t)pl.world;  // filler: after every real destination
     }

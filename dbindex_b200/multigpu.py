@@ -19,7 +19,10 @@ touches (:333-343).  Here a bucket is a GPU:
      whose variant mass crosses a cut (the SAME cuts: most groups stay where their peptide is), with their
      site masks, to the owners of those slices, which sort and expand what they hold;
   6. queries are routed on the host with the splitter masses; a range that straddles a splitter is
-     answered by both neighbours, exactly like Mult.getSequences walking two buckets.
+     answered by the owners of both slices, exactly like Mult.getSequences walking two buckets.
+With differential mods the axis is cut into 2 x world FOLDED slices (slice s on rank s < world ? s :
+2 world - 1 - s): the light end is crowded with records, the heavy end with variants, and every rank gets one
+slice of each so that the base phase, the variant phase and the search load are all even (dbi_mg_plan).
 
 What crosses torch.distributed: exchange 0 -- one 96 KB all-reduce (the three histograms), one all-gather of
 ~350 bytes per rank (send counts, unique count, window descriptors) and one barrier; exchange 1 -- the
@@ -59,19 +62,27 @@ def pick_splitters(hist: np.ndarray, world: int) -> np.ndarray:
     return np.maximum.accumulate(out) if len(out) else out
 
 
+def slice_owner(s, n_slices: int, world: int):
+    """Rank that holds slice s: slice s itself, or, with 2 * world FOLDED slices, 2 * world - 1 - s for the upper
+    half -- every rank holds one light and one heavy slice (mg_slice_owner in kernels.cuh)."""
+    s = np.asarray(s)
+    return np.where(s < world, s, n_slices - 1 - s)
+
+
 def plan_exchange(world: int, hist_global: np.ndarray, hist_local: np.ndarray, shift: int, min_mass: float,
-                  stage: int = 0, has_mods: bool = False, cost=None):
-    """dbi_mg_plan (host arithmetic of libdbindex_gpu.so, no device needed): (bin splitters of equal cost,
+                  stage: int = 0, has_mods: bool = False, cost=None, n_slices: int = 0):
+    """dbi_mg_plan (host arithmetic of libdbindex_gpu.so, no device needed): (bin splitters [n_slices - 1],
     this rank's send counts, every rank's receive total) from the summed and the own [weighted | plain | groups]
     histograms.  cost = (per item, per estimated group, per unit of weight, per expected hit); None: the
-    measured default model of the exchange (dbi_mg_default_cost)."""
+    measured default model of the exchange (dbi_mg_default_cost).  n_slices: world (default) or 2 * world."""
     import ctypes as C
     from .capi import load_library
     lib = load_library()
     lib.dbi_mg_plan.restype = C.c_int
-    lib.dbi_mg_plan.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 4
+    lib.dbi_mg_plan.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int] + [C.c_void_p] * 3
     lib.dbi_mg_default_cost.restype = None
     lib.dbi_mg_default_cost.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    n_slices = n_slices or world
     c = np.zeros(4, dtype=np.float64)
     if cost is None:
         lib.dbi_mg_default_cost(stage, 1 if has_mods else 0, c.ctypes.data)
@@ -83,13 +94,13 @@ def plan_exchange(world: int, hist_global: np.ndarray, hist_local: np.ndarray, s
         hg = np.concatenate([hg, np.zeros(MG_BINS, np.uint64)])
         hl = np.concatenate([hl, np.zeros(MG_BINS, np.uint64)])
     assert len(hg) == 3 * MG_BINS and len(hl) == 3 * MG_BINS
-    split = np.zeros(max(world - 1, 1), dtype=np.uint32)
+    split = np.zeros(max(n_slices - 1, 1), dtype=np.uint32)
     send, recv = np.zeros(world, dtype=np.uint64), np.zeros(world, dtype=np.uint64)
-    rc = lib.dbi_mg_plan(world, hg.ctypes.data, hl.ctypes.data, int(shift), float(min_mass), c.ctypes.data,
+    rc = lib.dbi_mg_plan(world, hg.ctypes.data, hl.ctypes.data, int(shift), float(min_mass), c.ctypes.data, int(n_slices),
                          split.ctypes.data, send.ctypes.data, recv.ctypes.data)
     if rc != 0:
         raise RuntimeError((lib.dbi_last_error() or b"").decode(errors="replace"))
-    return split[:world - 1].copy(), send, recv
+    return split[:n_slices - 1].copy(), send, recv
 
 
 def splitter_masses(bin_splitters: np.ndarray, shift: int, min_mass: float) -> np.ndarray:
@@ -99,11 +110,22 @@ def splitter_masses(bin_splitters: np.ndarray, shift: int, min_mass: float) -> n
     return keys.view(np.float64)
 
 
-def route_queries(lo: np.ndarray, hi: np.ndarray, split_mass: np.ndarray, rank: int) -> np.ndarray:
-    """Indices of the queries whose [lo, hi] intersects rank's slice [split[rank-1], split[rank])."""
-    left = split_mass[rank - 1] if rank > 0 else -np.inf
-    right = split_mass[rank] if rank < len(split_mass) else np.inf
-    return np.nonzero((hi >= left) & (lo < right))[0]
+def route_queries(lo: np.ndarray, hi: np.ndarray, split_mass: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """Indices of the queries whose [lo, hi] intersects a slice [split[s-1], split[s]) that `rank` holds.
+    len(split_mass) + 1 slices: world of them (slice s on rank s) or 2 * world folded ones (slice_owner)."""
+    n_slices = len(split_mass) + 1
+    edges = np.concatenate(([-np.inf], np.asarray(split_mass, dtype=np.float64), [np.inf]))
+    mine = np.zeros(len(lo), dtype=bool)
+    for s in range(n_slices):
+        if int(slice_owner(s, n_slices, world)) == rank:
+            mine |= (hi >= edges[s]) & (lo < edges[s + 1])
+    return np.nonzero(mine)[0]
+
+
+def owned_mask(masses: np.ndarray, split_mass: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """True where an entry of this mass belongs to `rank`: its slice is the number of cuts <= mass."""
+    sl = np.searchsorted(np.asarray(split_mass, dtype=np.float64), np.asarray(masses, dtype=np.float64), side="right")
+    return slice_owner(sl, len(split_mass) + 1, world) == rank
 
 
 # ---- tiny collectives ---------------------------------------------------------------------------
@@ -144,8 +166,8 @@ class ShardEngine:
     def pull_proteome(self): ...
     def digest(self) -> int: ...
     def hist(self, stage: int) -> Tuple[torch.Tensor, int]: ...   # (int64[3 * MG_BINS] on device, shift)
-    def count(self, stage: int, splitters: np.ndarray) -> np.ndarray: ...   # items per destination under the cuts
-    def scatter(self, stage: int, splitters: np.ndarray, matrix: np.ndarray): ...
+    def count(self, stage: int, splitters: np.ndarray, n_slices: int) -> np.ndarray: ...   # items per destination under the cuts
+    def scatter(self, stage: int, splitters: np.ndarray, n_slices: int, matrix: np.ndarray): ...
     def index_base(self): ...
     def n_unique(self) -> int: ...
     def set_unique(self, rank_unique: np.ndarray): ...
@@ -186,6 +208,10 @@ def build_sharded(engine: ShardEngine) -> dict:
     lap("digest")
 
     state = {"split": None, "shift": 0}
+    # folded slices (one light + one heavy per rank) when differential mods make the phases of a build pull
+    # the cuts apart; DBI_MG_FOLD=0 keeps one contiguous slice per rank
+    n_slices = 2 * world if (engine.has_mods and world > 1 and os.environ.get("DBI_MG_FOLD", "1") != "0") else world
+    info["n_slices"] = n_slices
     # DBI_MG_UNIFIED=0: the variant exchange plans its own cuts (equal cost of the variant work alone; almost
     # every group then leaves its rank).  Default: one set of cuts for the whole index.
     unified = os.environ.get("DBI_MG_UNIFIED", "1") != "0"
@@ -203,13 +229,13 @@ def build_sharded(engine: ShardEngine) -> dict:
             both = torch.stack([hist, local]).cpu().numpy().view(np.uint64)  # one D2H (the stage's first sync)
             lap(f"hist{stage}.reduce")
             split, send, recv = plan_exchange(world, both[0], both[1], shift, engine.min_mass, stage,
-                                              engine.has_mods and unified)
+                                              engine.has_mods and unified, n_slices=n_slices)
             state["split"], state["shift"] = split, shift
             recv_mine = int(recv[rank])
             lap(f"hist{stage}.plan")
         else:
             split = state["split"]
-            send = engine.count(stage, split)
+            send = engine.count(stage, split, n_slices)
             recv_mine = None  # known once every rank's counts are
             lap(f"count{stage}")
         d1 = engine.window(WIN_ARENA, engine.layout_bytes(WIN_ARENA, stage, recv_mine) if recv_mine is not None else 0)
@@ -219,6 +245,7 @@ def build_sharded(engine: ShardEngine) -> dict:
         rows = _all_gather_bytes(row, dev)  # every rank is past its previous use of the arenas
         lap(f"plan{stage}.gather")
         matrix = rows[:, :8 * world].copy().view(np.uint64).reshape(world, world)
+        info[f"recv{stage}"] = int(matrix[:, rank].sum())  # items this rank holds after the exchange
         ru = rows[:, 8 * world:8 * world + 8].copy().view(np.uint64).reshape(world)
         o = 8 * world + 8
         arena_desc = rows[:, o:o + DESC_BYTES]
@@ -238,7 +265,7 @@ def build_sharded(engine: ShardEngine) -> dict:
         if cuda:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        engine.scatter(stage, split, matrix)
+        engine.scatter(stage, split, n_slices, matrix)
         if cuda:
             e1.record()
             e1.synchronize()
@@ -304,8 +331,8 @@ class GpuShardEngine(ShardEngine):
             "dbi_mg_pull_proteome": (C.c_int, [vp]),
             "dbi_mg_digest": (C.c_int, [vp, u64p]),
             "dbi_mg_hist": (C.c_int, [vp, C.c_int, vp, C.POINTER(C.c_int)]),
-            "dbi_mg_count": (C.c_int, [vp, C.c_int, vp, vp]),
-            "dbi_mg_scatter": (C.c_int, [vp, C.c_int, vp, vp]),
+            "dbi_mg_count": (C.c_int, [vp, C.c_int, vp, C.c_int, vp]),
+            "dbi_mg_scatter": (C.c_int, [vp, C.c_int, vp, C.c_int, vp]),
             "dbi_mg_index_base": (C.c_int, [vp]),
             "dbi_mg_unique_count": (C.c_int, [vp, u64p]),
             "dbi_mg_set_unique": (C.c_int, [vp, vp]),
@@ -369,16 +396,16 @@ class GpuShardEngine(ShardEngine):
         self._ck(self.lib.dbi_mg_hist(self.g._h, stage, hist.data_ptr(), self.C.byref(shift)))
         return hist, shift.value
 
-    def count(self, stage, splitters):
+    def count(self, stage, splitters, n_slices):
         sp = np.ascontiguousarray(splitters, dtype=np.uint32)
         out = np.zeros(self.world, dtype=np.uint64)
-        self._ck(self.lib.dbi_mg_count(self.g._h, stage, sp.ctypes.data if len(sp) else None, out.ctypes.data))
+        self._ck(self.lib.dbi_mg_count(self.g._h, stage, sp.ctypes.data if len(sp) else None, int(n_slices), out.ctypes.data))
         return out
 
-    def scatter(self, stage, splitters, matrix):
+    def scatter(self, stage, splitters, n_slices, matrix):
         sp = np.ascontiguousarray(splitters, dtype=np.uint32)
         m = np.ascontiguousarray(matrix, dtype=np.uint64)
-        self._ck(self.lib.dbi_mg_scatter(self.g._h, stage, sp.ctypes.data if len(sp) else None, m.ctypes.data))
+        self._ck(self.lib.dbi_mg_scatter(self.g._h, stage, sp.ctypes.data if len(sp) else None, int(n_slices), m.ctypes.data))
 
     def index_base(self):
         torch.cuda.current_stream().synchronize()
@@ -431,10 +458,14 @@ def build_local(indexes) -> None:
 
 
 def split_masses(index, world: int) -> np.ndarray:
+    """Masses at which the slices of a built sharded index are cut (dbi_mg_slices - 1 values)."""
     import ctypes as C
     lib = index.lib
     lib.dbi_mg_split_masses.restype = C.c_int
     lib.dbi_mg_split_masses.argtypes = [C.c_void_p, C.c_void_p]
-    out = np.zeros(max(world - 1, 0), dtype=np.float64)
-    index._check(lib.dbi_mg_split_masses(index._h, out.ctypes.data if world > 1 else None))
+    lib.dbi_mg_slices.restype = C.c_int
+    lib.dbi_mg_slices.argtypes = [C.c_void_p]
+    n = int(lib.dbi_mg_slices(index._h))
+    out = np.zeros(max(n - 1, 0), dtype=np.float64)
+    index._check(lib.dbi_mg_split_masses(index._h, out.ctypes.data if n > 1 else None))
     return out

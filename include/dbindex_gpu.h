@@ -397,30 +397,35 @@ int dbi_mg_digest(dbi_handle* h, uint64_t* n_records);
  * to, groups = variant groups it will list, both estimated from its mod sites; 1 = variant groups: weight =
  * their entries, no third part) over key >> *shift */
 int dbi_mg_hist(dbi_handle* h, int stage, void* d_hist, int* shift);
-/* host arithmetic on the summed (global) and the own (local) histograms: bin splitters [world-1], this rank's
- * send counts [world], every rank's receive total [world].  cost[4] = {per item, per estimated group, per unit
- * of weight (index entry), per expected query hit}; NULL = equal weight.  The cuts minimise the sum over the
- * phases of a build (base: items; variants: groups + weight; search: hits) of the slowest rank's cost.
- * shift / min_mass as used by dbi_mg_hist (they give a bin its mass).  dbi_mg_default_cost fills the measured
- * model of an exchange (cost[4]). */
+/* host arithmetic on the summed (global) and the own (local) histograms: the cuts of the mass axis
+ * [n_slices - 1], this rank's send counts [world], every rank's receive total [world].  n_slices = world: slice s
+ * lives on rank s; n_slices = 2 * world: FOLDED slices, slice s lives on rank s < world ? s : 2 * world - 1 - s
+ * (one light and one heavy slice per rank: what balances every phase of a build with differential mods).
+ * cost[4] = {per item, per estimated group, per unit of weight (index entry), per expected query hit}; NULL =
+ * equal weight.  The cuts minimise the sum over the phases of a build (base: items; variants: groups + weight;
+ * search: hits) of the slowest rank's cost.  shift / min_mass as used by dbi_mg_hist (they give a bin its
+ * mass).  dbi_mg_default_cost fills the measured model of an exchange (cost[4]). */
 int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_local, int shift, double min_mass,
-                const double* cost, uint32_t* bin_splitters, uint64_t* send_counts, uint64_t* recv_totals);
+                const double* cost, int n_slices, uint32_t* bin_splitters, uint64_t* send_counts,
+                uint64_t* recv_totals);
 void dbi_mg_default_cost(int stage, int has_mods, double* cost);
 /* items of exchange `stage` this rank would send to every rank under the given cuts [world] */
-int dbi_mg_count(dbi_handle* h, int stage, const uint32_t* bin_splitters, uint64_t* send_counts);
+int dbi_mg_count(dbi_handle* h, int stage, const uint32_t* bin_splitters, int n_slices, uint64_t* send_counts);
 /* matrix[s * world + d] = items rank s sends to rank d.  Stable multisplit of the local items straight
  * into the mapped arenas of their destinations; every rank's arena must have been ensured for its
  * receive total and imported here.  A barrier across the ranks must follow before anybody consumes. */
-int dbi_mg_scatter(dbi_handle* h, int stage, const uint32_t* bin_splitters, const uint64_t* matrix);
+int dbi_mg_scatter(dbi_handle* h, int stage, const uint32_t* bin_splitters, int n_slices, const uint64_t* matrix);
 int dbi_mg_index_base(dbi_handle* h);
 int dbi_mg_unique_count(dbi_handle* h, uint64_t* n_unique);
 int dbi_mg_set_unique(dbi_handle* h, const uint64_t* rank_unique);
 int dbi_mg_groups(dbi_handle* h, uint64_t* n_items, uint64_t* n_variants);
 int dbi_mg_index_variants(dbi_handle* h);
 int dbi_mg_finish(dbi_handle* h);
-/* masses at which the entry slices are cut: a query [lo, hi] belongs to every rank d with
- * split[d-1] <= hi and lo < split[d] (DBIndexStoreSQLiteMult.java:333-343 walks buckets the same way) */
-int dbi_mg_split_masses(dbi_handle* h, double* split_mass);
+/* masses at which the entry slices are cut: a query [lo, hi] belongs to the owner of every slice s with
+ * split[s-1] <= hi and lo < split[s] (DBIndexStoreSQLiteMult.java:333-343 walks buckets the same way);
+ * owner(s) = s < world ? s : slices - 1 - s */
+int dbi_mg_slices(dbi_handle* h); /* slices of the built sharded index (world or 2 * world) */
+int dbi_mg_split_masses(dbi_handle* h, double* split_mass); /* [dbi_mg_slices - 1] */
 int dbi_mg_build_local(dbi_handle** handles, int n);
 
 /* Test hook for K7: stable radix sort of n host (key, value) pairs on key bits

@@ -82,10 +82,8 @@ def main():
                                   (total - free) / 1e9))
     sm = info["split_mass"]
     if n:
-        if rank > 0:
-            assert first >= sm[rank - 1]
-        if rank < world - 1:
-            assert last < sm[rank]
+        from dbindex_b200.multigpu import owned_mask
+        assert bool(np.all(owned_mask(np.array([first, last]), sm, rank, world)))
     # ---- membership of oracle-derived entries (same sample on every rank; the owner must hold each)
     srng = np.random.default_rng(5)
     P = len(off) - 1
@@ -128,7 +126,7 @@ def main():
     dist.all_gather_object(gathered, samp[::8].tolist())
     allm = np.sort(np.concatenate([np.asarray(x) for x in gathered]))
     _, _, lo, hi = synth.synth_queries(allm, nq, 20240605, da_fraction=0.5)
-    sel = route_queries(lo, hi, sm, rank)
+    sel = route_queries(lo, hi, sm, rank, world)
     d_lo, d_hi = torch.from_numpy(lo[sel]).cuda(), torch.from_numpy(hi[sel]).cuda()
     d_b = torch.empty(len(sel), dtype=torch.int64, device="cuda")
     d_c = torch.empty(len(sel), dtype=torch.int64, device="cuda")

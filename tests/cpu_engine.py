@@ -8,7 +8,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from dbindex_b200.multigpu import DESC_BYTES, MG_BINS, ShardEngine, shard_proteins
+from dbindex_b200.multigpu import DESC_BYTES, MG_BINS, ShardEngine, shard_proteins, slice_owner
 from oracle.oracle_py import Oracle
 
 from . import pyref
@@ -99,14 +99,16 @@ class OracleShardEngine(ShardEngine):
         plain = np.bincount(bins, minlength=MG_BINS).astype(np.int64)
         return torch.from_numpy(np.concatenate([plain, plain, np.zeros_like(plain)])), self.shift  # every item weighs 1 here, no group estimates
 
-    def count(self, stage, splitters):
+    def _dest(self, stage, splitters, n_slices):
         thr = np.asarray(splitters, dtype=np.uint64) << np.uint64(self.shift)
-        dest = np.searchsorted(thr, self._keys(stage), side="right")
+        return slice_owner(np.searchsorted(thr, self._keys(stage), side="right"), n_slices, self.world)
+
+    def count(self, stage, splitters, n_slices):
+        dest = self._dest(stage, splitters, n_slices)
         return np.bincount(dest, minlength=self.world).astype(np.uint64)
 
-    def scatter(self, stage, splitters, matrix):
-        thr = np.asarray(splitters, dtype=np.uint64) << np.uint64(self.shift)
-        dest = np.searchsorted(thr, self._keys(stage), side="right")
+    def scatter(self, stage, splitters, n_slices, matrix):
+        dest = self._dest(stage, splitters, n_slices)
         perm = np.argsort(dest, kind="stable")
         send = np.bincount(dest, minlength=self.world)
         assert send.tolist() == matrix[self.rank].astype(np.int64).tolist(), "count matrix row differs from the partition"

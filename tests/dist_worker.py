@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 
 import dbindex_b200 as dbi  # noqa: E402
 from dbindex_b200 import synth  # noqa: E402
-from dbindex_b200.multigpu import build_sharded, route_queries, shard_proteins  # noqa: E402
+from dbindex_b200.multigpu import build_sharded, owned_mask, route_queries, shard_proteins  # noqa: E402
 from oracle.oracle_py import Oracle  # noqa: E402
 from tests.cpu_engine import OracleShardEngine  # noqa: E402
 from tests.util import PARAM_SETS, bits  # noqa: E402
@@ -81,27 +81,22 @@ def main():
     counts = [None] * world
     dist.all_gather_object(counts, n_mine)
     assert sum(counts) == len(exp["mass"]), (counts, len(exp["mass"]))
-    a = sum(counts[:rank])
-    sl = slice(a, a + n_mine)
+    # what this rank must hold: the oracle's entries whose mass falls into one of its slices, in mass order
+    sm = info["split_mass"]
+    sl = np.nonzero(owned_mask(exp["mass"], sm, rank, world))[0]
+    assert len(sl) == n_mine, (len(sl), n_mine)
     assert np.array_equal(bits(mine["mass"]), bits(exp["mass"][sl])), "slice masses differ from the global index"
     plo = exp["prot_list_off"].astype(np.int64)
     exp_t = sorted(zip(bits(exp["mass"][sl]).tolist(), exp["first_prot"][sl].tolist(), exp["first_off"][sl].tolist(),
                        exp["len"][sl].tolist(), exp["modpat"][sl].tolist(),
-                       [tuple(exp["prot_ids"][plo[i]:plo[i + 1]].tolist()) for i in range(a, a + n_mine)]))
+                       [tuple(exp["prot_ids"][plo[i]:plo[i + 1]].tolist()) for i in sl]))
     got_t = sorted(zip(bits(mine["mass"]).tolist(), mine["first_prot"].tolist(), mine["first_off"].tolist(),
                        mine["len"].tolist(), mine["modpat"].tolist(), mine["plist"]))
     assert got_t == exp_t, "slice entries differ (first occurrence / protein lists must be global)"
-    # slices are cut at the splitter masses
-    sm = info["split_mass"]
-    if n_mine:
-        if rank > 0:
-            assert mine["mass"][0] >= sm[rank - 1]
-        if rank < world - 1:
-            assert mine["mass"][-1] < sm[rank]
     # routed queries: each rank answers the queries touching its slice; the sum is the global answer
     _, _, lo, hi = synth.synth_queries(exp["mass"], 400, 3, da_fraction=0.5)
     ob, oc, _ = o.query(lo, hi)
-    sel = route_queries(lo, hi, sm, rank)
+    sel = route_queries(lo, hi, sm, rank, world)
     part = np.zeros(len(lo), np.int64)
     b, c = eng.query(lo[sel], hi[sel])
     part[sel] = c

@@ -34,9 +34,37 @@ def test_route_queries_straddling():
     assert sm[0] < sm[1]
     lo = np.array([600.0, sm[0] - 1, sm[0], sm[1] + 5, 0.0])
     hi = np.array([700.0, sm[0] + 1, sm[0], 9000.0, 1e9])
-    assert route_queries(lo, hi, sm, 0).tolist() == [0, 1, 4]
-    assert route_queries(lo, hi, sm, 1).tolist() == [1, 2, 4]
-    assert route_queries(lo, hi, sm, 2).tolist() == [3, 4]
+    assert route_queries(lo, hi, sm, 0, 3).tolist() == [0, 1, 4]
+    assert route_queries(lo, hi, sm, 1, 3).tolist() == [1, 2, 4]
+    assert route_queries(lo, hi, sm, 2, 3).tolist() == [3, 4]
+
+
+def test_folded_slices_route_and_own():
+    """2 * world folded slices: slice s lives on rank s < world ? s : 2 * world - 1 - s."""
+    from dbindex_b200.multigpu import owned_mask, slice_owner
+    assert slice_owner(np.arange(4), 4, 2).tolist() == [0, 1, 1, 0]
+    assert slice_owner(np.arange(6), 6, 3).tolist() == [0, 1, 2, 2, 1, 0]
+    assert slice_owner(np.arange(3), 3, 3).tolist() == [0, 1, 2]
+    sm = np.array([1000.0, 2000.0, 3000.0])  # 4 slices on 2 ranks: rank 0 holds [.., 1000) and [3000, ..)
+    m = np.array([600.0, 999.9, 1000.0, 2500.0, 3000.0, 5000.0])
+    assert owned_mask(m, sm, 0, 2).tolist() == [True, True, False, False, True, True]
+    assert owned_mask(m, sm, 1, 2).tolist() == [False, False, True, True, False, False]
+    lo = np.array([600.0, 990.0, 1500.0, 2990.0, 3500.0, 0.0])
+    hi = np.array([700.0, 1010.0, 1600.0, 3010.0, 3600.0, 9000.0])
+    assert route_queries(lo, hi, sm, 0, 2).tolist() == [0, 1, 3, 4, 5]
+    assert route_queries(lo, hi, sm, 1, 2).tolist() == [1, 2, 3, 5]
+    # the planner with folded slices: send / receive counts follow the owners
+    rng = np.random.default_rng(7)
+    for world in (2, 3, 8):
+        plain = rng.integers(0, 50, size=MG_BINS).astype(np.uint64)
+        hg = np.concatenate([plain * np.uint64(7), plain, plain * np.uint64(3)])
+        split, send, recv = plan_exchange(world, hg, hg, 42, 600.0, cost=[400.0, 125.0, 17.5, 20.0], n_slices=2 * world)
+        assert len(split) == 2 * world - 1 and np.all(np.diff(split.astype(np.int64)) >= 0)
+        edges = np.concatenate(([0], split, [MG_BINS])).astype(int)
+        want = np.zeros(world, np.int64)
+        for s_ in range(2 * world):
+            want[int(slice_owner(s_, 2 * world, world))] += int(plain[edges[s_]:edges[s_ + 1]].sum())
+        assert send.tolist() == want.tolist() and recv.tolist() == want.tolist()
 
 
 @pytest.mark.parametrize("name", ["cfg1_tryptic", "cfg2_mods", "semi_nocut_mods"])

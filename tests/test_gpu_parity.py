@@ -494,34 +494,32 @@ def check_sharded(handles, o, split_mass):
     """The rank slices, in rank order, ARE the oracle's index: masses position by position, first
     occurrences and protein lists global, slices cut at the splitter masses, routed queries and
     materialised hits summing to the global answer."""
-    from dbindex_b200.multigpu import route_queries
+    from dbindex_b200.multigpu import owned_mask, route_queries
     exp = o.entries()
     world = len(handles)
     counts = [g.stats()["n_entries"] for g in handles]
     assert sum(counts) == len(exp["mass"]), (counts, len(exp["mass"]))
-    a = 0
     plo = exp["prot_list_off"].astype(np.int64)
     for r, g in enumerate(handles):
         n = counts[r]
         got = g.fetch(0, n)
         assert not np.any(got["first_prot"] == 0xFFFFFFFF), "a base peptide of another rank was not resolved"
-        sl = {k: exp[k][a:a + n] for k in ("mass", "first_prot", "first_off", "len", "modpat")}
-        sl["prot_list_off"] = (plo[a:a + n + 1] - plo[a]).astype(np.uint64)
-        sl["prot_ids"] = exp["prot_ids"][plo[a]:plo[a + n]]
+        # the oracle's entries whose mass falls into one of this rank's slices, in mass order
+        idx = np.nonzero(owned_mask(exp["mass"], split_mass, r, world))[0]
+        assert len(idx) == n, (r, len(idx), n)
+        sl = {k: exp[k][idx] for k in ("mass", "first_prot", "first_off", "len", "modpat")}
+        sizes = (plo[idx + 1] - plo[idx]) if n else np.zeros(0, np.int64)
+        sl["prot_list_off"] = np.concatenate(([0], np.cumsum(sizes))).astype(np.uint64)
+        sl["prot_ids"] = (np.concatenate([exp["prot_ids"][plo[i]:plo[i + 1]] for i in idx]) if n
+                          else np.zeros(0, np.uint32))
         assert_entries_equal(got, sl)
-        if n:
-            if r > 0:
-                assert got["mass"][0] >= split_mass[r - 1]
-            if r < world - 1:
-                assert got["mass"][-1] < split_mass[r]
-        a += n
     _, _, lo, hi = synth.synth_queries(exp["mass"], 300, 3, da_fraction=0.4)
     ob, oc, _ = o.query(lo, hi)
     total = np.zeros(len(lo), np.int64)
     exp_hits = hits_canonical(o.query_hits(lo, hi))
     got_hits = [[] for _ in lo]
     for r, g in enumerate(handles):
-        sel = route_queries(lo, hi, split_mass, r)
+        sel = route_queries(lo, hi, split_mass, r, world)
         b, c = g.query(lo, hi)
         part = np.zeros(len(lo), np.int64)
         part[sel] = c[sel]
