@@ -1,9 +1,11 @@
 """cfg4 / cfg5 on N GPUs (torchrun): ONE index over --proteins synthetic proteins (TrEMBL-like
-config 4 seed), trypsin + 3 variable mods, mass-range sharded with the NCCL all-to-all, then a
-routed query sweep.  Size-independent checks: every rank's slice is sorted, slices are ordered
-across ranks and cut at the splitter masses, entry counts add up over ranks, and the entries the
-oracle derives from sampled proteins alone are found (zero-tolerance query on the owning rank,
-same peptide string + mod pattern, protein in the list).  Rank 0 prints one JSON line.
+config 4 seed), trypsin + 3 variable mods.  The FASTA is sharded by protein (every rank adds only its
+shard), the records and variant groups travel inside the two fused multisplit / peer-memory scatter
+kernels into folded mass slices, then a routed query sweep (cfg5: half 10 ppm, half +-3 Da).
+Size-independent checks (bench.sharded_parity): every rank's entries are sorted and lie inside the
+slices it holds, entry counts add up over the ranks, and the entries the oracle derives from sampled
+proteins alone are held by exactly one rank (zero-tolerance query, same peptide string + mod pattern,
+protein in the list).  Rank 0 prints one JSON line.
 
   python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/mg_scale_check.py --proteins P
 """
@@ -20,10 +22,9 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import dbindex_b200 as dbi  # noqa: E402
-from bench import CFG2  # noqa: E402
+from bench import CFG2, sharded_parity  # noqa: E402
 from dbindex_b200 import synth  # noqa: E402
-from dbindex_b200.multigpu import GpuShardEngine, build_sharded, fetch_resolved, route_queries  # noqa: E402
-from oracle.oracle_py import Oracle  # noqa: E402  (checker only)
+from dbindex_b200.multigpu import GpuShardEngine, build_sharded, route_queries, shard_proteins  # noqa: E402
 
 
 def main():
@@ -38,8 +39,9 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     t0 = time.perf_counter()
-    res, off = synth.config_proteome(4, args.proteins)  # identical on every rank
+    res, off = synth.config_proteome(4, args.proteins)  # generated on every rank; each keeps only its shard
     t_synth = time.perf_counter() - t0
+    sres, soff, _ = shard_proteins(res, off, rank, world)
     params = dbi.default_params(**CFG2)
     params.device = local
     params.profile = 1
@@ -47,7 +49,7 @@ def main():
     torch.cuda.set_stream(stream)
     g = dbi.GpuIndex(params)
     g.set_stream(stream.cuda_stream)
-    g.add_proteins(res, off)
+    g.add_proteins(sres, soff)
     g.upload()
     ms, a2a_ms, a2a_bytes, info = [], [], [], None
     for i in range(1 + args.builds):
@@ -66,77 +68,32 @@ def main():
     st = g.stats()
     n = st["n_entries"]
     free, total = torch.cuda.mem_get_info()
-    # ---- slice checks
-    rng = np.random.default_rng(11 + rank)
-    chunk = 1 << 20
-    first = last = None
-    for s in sorted(set([0, max(0, n - chunk)] + [int(x) for x in rng.integers(0, max(1, n - chunk), size=8)])):
-        m = g.fetch(s, min(chunk, n - s), with_ids=False)["mass"]
-        assert np.all(np.diff(m) >= 0), "slice not sorted"
-        if s == 0:
-            first = float(m[0])
-        if s + len(m) == n:
-            last = float(m[-1])
     ends = [None] * world
-    dist.all_gather_object(ends, (n, first, last, float(min(ms)), float(max(a2a_ms)), int(a2a_bytes[-1]),
-                                  (total - free) / 1e9))
-    sm = info["split_mass"]
-    if n:
-        from dbindex_b200.multigpu import owned_mask
-        assert bool(np.all(owned_mask(np.array([first, last]), sm, rank, world)))
-    # ---- membership of oracle-derived entries (same sample on every rank; the owner must hold each)
-    srng = np.random.default_rng(5)
-    P = len(off) - 1
-    found = np.zeros(0, np.int64)
-    checked = 0
-    for pid in np.sort(srng.choice(P, size=min(args.sample, P), replace=False)):
-        r0, r1 = int(off[pid]), int(off[pid + 1])
-        o = Oracle(params, threads=1)
-        o.add_proteins(res[r0:r1], np.array([0, r1 - r0], dtype=np.uint64))
-        assert o.build() == 0
-        e = o.entries()
-        if not len(e["mass"]):
-            continue
-        sel = srng.choice(len(e["mass"]), size=min(24, len(e["mass"])), replace=False)
-        lo = e["mass"][sel].copy()
-        bq, cq = g.query(lo, lo)
-        ok = np.zeros(len(sel), np.int64)
-        for k2, (b0, c0) in enumerate(zip(bq, cq)):
-            i2 = sel[k2]
-            want = res[r0 + int(e["first_off"][i2]):r0 + int(e["first_off"][i2]) + int(e["len"][i2])].tobytes()
-            # COLLECTIVE: every rank fetches its (possibly empty) hit range; base peptides held by other
-            # ranks are resolved by their owners
-            hit = fetch_resolved(g, info, int(b0), int(min(c0, 1 << 16)))
-            plo = hit["prot_list_off"].astype(np.int64)
-            for h in np.nonzero((hit["len"] == len(want)) & (hit["modpat"] == e["modpat"][i2]))[0]:
-                fp, fo = int(hit["first_prot"][h]), int(hit["first_off"][h])
-                if res[int(off[fp]) + fo:int(off[fp]) + fo + len(want)].tobytes() == want and \
-                        pid in hit["prot_ids"][plo[h]:plo[h + 1]]:
-                    ok[k2] = 1
-                    break
-        found = np.concatenate([found, ok])
-        checked += len(sel)
-    tot = torch.from_numpy(found).cuda()
-    dist.all_reduce(tot)
-    assert bool((tot == 1).all()), "an oracle entry is missing (or held twice) across the ranks"
+    dist.all_gather_object(ends, (n, float(min(ms)), float(max(a2a_ms)), int(a2a_bytes[-1]), (total - free) / 1e9))
+    # ---- order, slices, membership of oracle-derived entries (the check every bench line carries)
+    parity = sharded_parity(torch, dist, dbi, g, info, res, off, params, rank, world, n_sample=args.sample)
+    assert parity["failed"] == 0, parity
     # ---- cfg5: routed query sweep, half 10 ppm / half +-3 Da
     nq = args.queries
-    samp = np.concatenate([g.fetch(int(s), 2048, with_ids=False)["mass"] for s in rng.integers(0, max(1, n - 2048), size=32)])
+    rng = np.random.default_rng(11 + rank)
+    samp = (np.concatenate([g.fetch(int(s), 2048, with_ids=False)["mass"] for s in rng.integers(0, max(1, n - 2048), size=32)])
+            if n > 2048 else g.fetch(0, n, with_ids=False)["mass"])
     gathered = [None] * world
     dist.all_gather_object(gathered, samp[::8].tolist())
     allm = np.sort(np.concatenate([np.asarray(x) for x in gathered]))
     _, _, lo, hi = synth.synth_queries(allm, nq, 20240605, da_fraction=0.5)
-    sel = route_queries(lo, hi, sm, rank, world)
+    sel = route_queries(lo, hi, info["split_mass"], rank, world)
     d_lo, d_hi = torch.from_numpy(lo[sel]).cuda(), torch.from_numpy(hi[sel]).cuda()
-    d_b = torch.empty(len(sel), dtype=torch.int64, device="cuda")
-    d_c = torch.empty(len(sel), dtype=torch.int64, device="cuda")
+    d_b = torch.empty(max(1, len(sel)), dtype=torch.int64, device="cuda")
+    d_c = torch.zeros(max(1, len(sel)), dtype=torch.int64, device="cuda")
     q_ms = []
     for i in range(3):
         dist.barrier()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
-        g.query_device(d_lo.data_ptr(), d_hi.data_ptr(), len(sel), d_b.data_ptr(), d_c.data_ptr())
+        if len(sel):
+            g.query_device(d_lo.data_ptr(), d_hi.data_ptr(), len(sel), d_b.data_ptr(), d_c.data_ptr())
         b.record(stream)
         torch.cuda.synchronize()
         if i:
@@ -147,26 +104,24 @@ def main():
     dist.all_reduce(qt)
     if rank == 0:
         n_all = sum(e[0] for e in ends)
-        t_max = max(e[3] for e in ends)
-        for r in range(world - 1):
-            if ends[r][0] and ends[r + 1][0]:
-                assert ends[r][2] <= ends[r + 1][1], "slices overlap across ranks"
-        bytes_all = sum(e[5] for e in ends)
-        a2a_t = max(e[4] for e in ends)
+        t_max = max(e[1] for e in ends)
+        bytes_all = sum(e[3] for e in ends)
+        a2a_t = max(e[2] for e in ends)
         print(json.dumps({
             "workload": "cfg4-style: trypsin, 2 missed cleavages, 600-6000 Da, static C, variable M / STY <= 3; "
                         "cfg5 sweep: half 10 ppm, half +-3 Da, routed to the owning GPU",
             "n_gpus": world, "proteins": args.proteins, "residues": int(len(res)), "entries_total": int(n_all),
             "entries_per_rank": [e[0] for e in ends], "build_ms_max_rank": t_max,
-            "entries_per_s": n_all / (t_max / 1e3),
+            "entries_per_s": n_all / (t_max / 1e3), "n_slices": info.get("n_slices", world),
             "all_to_all": {"bytes_all_ranks": bytes_all, "ms_max_rank": a2a_t,
-                           "bus_gbs_per_gpu": bytes_all / world / 1e9 / (a2a_t / 1e3)},
-            "gpu_mem_used_gb": [round(e[6], 1) for e in ends],
+                           "bus_gbs_per_gpu": bytes_all / world / 1e9 / max(a2a_t / 1e3, 1e-12)},
+            "gpu_mem_used_gb": [round(e[4], 1) for e in ends],
             "host_stage_ms_rank0": {k: round(v, 2) for k, v in info["t"].items()},
-            "oracle_entries_checked": int(checked), "synth_s": t_synth,
+            "parity": parity, "synth_s": t_synth,
             "queries": {"n": nq, "routed": int(qt[2].item()), "ms_max_rank": float(qmax[0].item()),
                         "queries_per_s": nq / (float(qmax[0].item()) / 1e3), "hits": int(qt[1].item())},
         }), flush=True)
+    dist.barrier()  # nobody releases its windows while another rank may still read them
     g.close()
     dist.destroy_process_group()
 
