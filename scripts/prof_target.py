@@ -1,5 +1,5 @@
 """Small profiling target: two builds of the bench workload (cfg2, full size) + one query batch.
-The first build is the warm-up; run under ncu as described in scripts/gpu_profile.sh."""
+The first build is the warm-up; run under ncu as scripts/gpu_round.sh / scripts/gpu_prof.sh / scripts/gpu_list.sh do."""
 import os
 import sys
 
