@@ -609,7 +609,7 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
     import torch.distributed as dist
     import dbindex_b200 as dbi
     from dbindex_b200 import synth
-    from dbindex_b200.multigpu import GpuShardEngine, build_sharded, route_queries, shard_proteins
+    from dbindex_b200.multigpu import GpuShardEngine, build_sharded, route_queries, shard_proteins, shard_sizes
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -617,6 +617,7 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
     lib = dbi.load_library()
     res, off = synth.config_proteome(2, args.proteins * world)  # generated on every rank; each keeps only its shard
     sres, soff, _ = shard_proteins(res, off, rank, world)
+    sizes = shard_sizes(off, world)  # the host that cut the FASTA knows every shard's size: one collective less
     params = dbi.default_params(**CFG2)
     params.device = local_rank
     params.profile = 1
@@ -628,7 +629,7 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
     g.upload()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     nq = args.queries  # ONE batch for the whole index: hits per query grow with the index, so per-GPU work stays fixed
-    info = build_sharded(GpuShardEngine(g, dev))  # also warms NCCL and the window mappings up
+    info = build_sharded(GpuShardEngine(g, dev), sizes)  # also warms NCCL and the window mappings up
     n_mine = g.stats()["n_entries"]
     masses = sample_index_masses(g, n_mine)
     # the query masses follow the indexed mass density, exactly like the N = 1 batch (which samples the index
@@ -662,7 +663,7 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
         barrier()
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record(stream)
-        info = build_sharded(GpuShardEngine(g, dev))
+        info = build_sharded(GpuShardEngine(g, dev), sizes)
         e1.record(stream)
         sel = route_queries(lo, hi, info["split_mass"], rank, world)
         d_lo = torch.from_numpy(lo[sel]).cuda()
@@ -708,7 +709,7 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
         g2.set_stream(stream.cuda_stream)
         g2.add_proteins(h_res.numpy(), h_off.numpy().view(np.uint64))
         t1 = time.perf_counter()
-        inf2 = build_sharded(GpuShardEngine(g2, dev))
+        inf2 = build_sharded(GpuShardEngine(g2, dev), sizes)
         t2 = time.perf_counter()
         sel = route_queries(lo, hi, inf2["split_mass"], rank, world)
         c2 = g2.query_hits_begin(lo[sel], hi[sel])

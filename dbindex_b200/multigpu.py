@@ -24,9 +24,11 @@ With differential mods the axis is cut into 2 x world FOLDED slices (slice s on 
 2 world - 1 - s): the light end is crowded with records, the heavy end with variants, and every rank gets one
 slice of each so that the base phase, the variant phase and the search load are all even (dbi_mg_plan).
 
-What crosses torch.distributed: exchange 0 -- one 96 KB all-reduce (the three histograms), one all-gather of
-~350 bytes per rank (send counts, unique count, window descriptors) and one barrier; exchange 1 -- the
-all-gather and the barrier only (it reuses the cuts of exchange 0).
+What crosses torch.distributed: the window-0 descriptors (one all-gather; a second one for the shard sizes
+unless the caller passes them); exchange 0 -- ONE all-gather of every rank's three local histograms + window
+descriptors (96 KB per rank: every rank derives the global histogram, the cuts and the whole count matrix from
+it) and one barrier; exchange 1 -- one all-gather of ~350 bytes per rank (send counts, unique count, window
+descriptors) and the barrier (it reuses the cuts of exchange 0); a last barrier before anybody may rebuild.
 
 `ShardEngine` is the device side of one rank.  `GpuShardEngine` drives the C ABI (dbi_mg_*); the tests
 plug in a CPU engine so that the orchestration runs under gloo without a GPU.  A host that holds every
@@ -133,14 +135,15 @@ def _world() -> int:
     return dist.get_world_size() if dist.is_initialized() else 1
 
 
-def _all_gather_bytes(row: np.ndarray, device) -> np.ndarray:
-    """Every rank's fixed-size byte row on every rank: [world, len(row)] (one small all-gather + D2H)."""
+def _all_gather_bytes(row, device) -> np.ndarray:
+    """Every rank's fixed-size byte row (numpy, or a uint8 tensor already on `device`) on every rank:
+    [world, len(row)] (one small all-gather + D2H)."""
     world = _world()
+    t = row if isinstance(row, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(row, dtype=np.uint8)).to(device)
     if world == 1:
-        return row[None, :].copy()
-    t = torch.from_numpy(np.ascontiguousarray(row, dtype=np.uint8)).to(device)
+        return t.cpu().numpy()[None, :].copy()
     out = torch.empty(world * t.numel(), dtype=torch.uint8, device=device)
-    dist.all_gather_into_tensor(out, t)
+    dist.all_gather_into_tensor(out, t.contiguous())
     return out.cpu().numpy().reshape(world, -1)
 
 
@@ -176,8 +179,9 @@ class ShardEngine:
     def finish(self): ...
 
 
-def build_sharded(engine: ShardEngine) -> dict:
-    """Run the sharded build on this rank.  Returns routing info: {"split_mass": masses at which the entry
+def build_sharded(engine: ShardEngine, shard_sizes=None) -> dict:
+    """Run the sharded build on this rank.  shard_sizes: (proteins, residues) of EVERY rank's shard, [world, 2], when
+    the caller knows them (it cut the FASTA): saves the first all-gather.  Returns routing info: {"split_mass": masses at which the entry
     slices are cut, "unique_off": global id of every rank's first unique peptide, "a2a_bytes": ...}."""
     import time
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
@@ -199,7 +203,11 @@ def build_sharded(engine: ShardEngine) -> dict:
     engine.begin(rank, world)
     # ---- the proteome: own shard over PCIe (already added), the other shards over NVLink
     np_, nr_ = engine.shard_info()
-    sizes = _all_gather_bytes(np.array([np_, nr_], dtype=np.uint64).view(np.uint8), dev).view(np.uint64).reshape(world, 2)
+    if shard_sizes is None:
+        sizes = _all_gather_bytes(np.array([np_, nr_], dtype=np.uint64).view(np.uint8), dev).view(np.uint64).reshape(world, 2)
+    else:
+        sizes = np.ascontiguousarray(shard_sizes, dtype=np.uint64).reshape(world, 2)
+        assert (int(sizes[rank, 0]), int(sizes[rank, 1])) == (np_, nr_), "shard_sizes disagree with the shard this rank added"
     d0 = engine.set_shards(sizes[:, 0].copy(), sizes[:, 1].copy())
     connect(WIN_PROTEOME, _all_gather_bytes(d0, dev))  # also the barrier: every shard is packed
     engine.pull_proteome()
@@ -220,36 +228,54 @@ def build_sharded(engine: ShardEngine) -> dict:
         """Exchange 0 plans the cuts of the index (histograms -> all-reduce -> equal-cost splitters); exchange 1
         reuses them -- a variant lies at most a few shifts above its peptide, so most groups stay on the GPU
         that owns the peptide -- and only needs the counts of the groups that cross a cut."""
+        nu = np.array([engine.n_unique()], dtype=np.uint64).view(np.uint8)
         if stage == 0 or not unified:
+            # ONE all-gather carries every rank's local histograms and the windows it has: every rank then sums
+            # the global histogram, places the same cuts, and knows the whole count matrix and whether anybody's
+            # window has to grow (rare after the first build) -- no second collective in the steady state
             hist, shift = engine.hist(stage)
             lap(f"hist{stage}.kernel")
-            local = hist.clone()
-            if world > 1:
-                dist.all_reduce(hist)
-            both = torch.stack([hist, local]).cpu().numpy().view(np.uint64)  # one D2H (the stage's first sync)
-            lap(f"hist{stage}.reduce")
-            split, send, recv = plan_exchange(world, both[0], both[1], shift, engine.min_mass, stage,
-                                              engine.has_mods and unified, n_slices=n_slices)
+            d1 = engine.window(WIN_ARENA, 0)
+            d2 = engine.window(WIN_UNIQUE, 0)
+            tail = torch.from_numpy(np.concatenate([nu, d1, d2])).to(dev)
+            rows = _all_gather_bytes(torch.cat([hist.view(torch.uint8), tail]), dev)
+            hb = 3 * MG_BINS * 8
+            hists = rows[:, :hb].copy().view(np.uint64).reshape(world, 3 * MG_BINS)
+            lap(f"hist{stage}.gather")
+            split, send, recv = plan_exchange(world, hists.sum(axis=0, dtype=np.uint64), hists[rank], shift, engine.min_mass,
+                                              stage, engine.has_mods and unified, n_slices=n_slices)
             state["split"], state["shift"] = split, shift
-            recv_mine = int(recv[rank])
+            edges = np.concatenate(([0], split.astype(np.int64), [MG_BINS]))
+            owners = slice_owner(np.arange(n_slices), n_slices, world)
+            matrix = np.zeros((world, world), dtype=np.uint64)
+            for src in range(world):
+                cs = np.concatenate(([0], np.cumsum(hists[src, MG_BINS:2 * MG_BINS].astype(np.int64))))
+                np.add.at(matrix[src], owners, (cs[edges[1:]] - cs[edges[:-1]]).astype(np.uint64))
+            assert np.array_equal(matrix[rank], send) and np.array_equal(matrix.sum(axis=0), recv)
+            ru = rows[:, hb:hb + 8].copy().view(np.uint64).reshape(world)
+            descs = rows[:, hb + 8:]
             lap(f"hist{stage}.plan")
+            need_a = [engine.layout_bytes(WIN_ARENA, stage, int(recv[d])) for d in range(world)]
+            need_u = [engine.layout_bytes(WIN_UNIQUE, 0, int(recv[d])) if stage == 0 else 0 for d in range(world)]
+            cap = lambda d, w: int(descs[d, w * DESC_BYTES + 72:w * DESC_BYTES + 80].copy().view(np.uint64)[0])  # noqa: E731  dbi_mg_window.bytes
+            if any(need_a[d] > cap(d, 0) or need_u[d] > cap(d, 1) for d in range(world)):
+                d1 = engine.window(WIN_ARENA, need_a[rank])
+                d2 = engine.window(WIN_UNIQUE, need_u[rank])
+                descs = _all_gather_bytes(np.concatenate([d1, d2]), dev)
+                lap(f"plan{stage}.grow")
+            arena_desc, uniq_desc = descs[:, :DESC_BYTES], descs[:, DESC_BYTES:2 * DESC_BYTES]
         else:
             split = state["split"]
             send = engine.count(stage, split, n_slices)
-            recv_mine = None  # known once every rank's counts are
             lap(f"count{stage}")
-        d1 = engine.window(WIN_ARENA, engine.layout_bytes(WIN_ARENA, stage, recv_mine) if recv_mine is not None else 0)
-        d2 = engine.window(WIN_UNIQUE, engine.layout_bytes(WIN_UNIQUE, 0, recv_mine) if stage == 0 else 0)
-        row = np.concatenate([send.view(np.uint8), np.array([engine.n_unique()], dtype=np.uint64).view(np.uint8), d1, d2])
-        lap(f"plan{stage}.windows")
-        rows = _all_gather_bytes(row, dev)  # every rank is past its previous use of the arenas
-        lap(f"plan{stage}.gather")
-        matrix = rows[:, :8 * world].copy().view(np.uint64).reshape(world, world)
-        info[f"recv{stage}"] = int(matrix[:, rank].sum())  # items this rank holds after the exchange
-        ru = rows[:, 8 * world:8 * world + 8].copy().view(np.uint64).reshape(world)
-        o = 8 * world + 8
-        arena_desc = rows[:, o:o + DESC_BYTES]
-        if stage == 1 and recv_mine is None:
+            d1 = engine.window(WIN_ARENA, 0)
+            d2 = engine.window(WIN_UNIQUE, 0)
+            rows = _all_gather_bytes(np.concatenate([send.view(np.uint8), nu, d1, d2]), dev)  # every rank is past its previous use of the arenas
+            lap(f"plan{stage}.gather")
+            matrix = rows[:, :8 * world].copy().view(np.uint64).reshape(world, world)
+            ru = rows[:, 8 * world:8 * world + 8].copy().view(np.uint64).reshape(world)
+            o = 8 * world + 8
+            arena_desc, uniq_desc = rows[:, o:o + DESC_BYTES], rows[:, o + DESC_BYTES:o + 2 * DESC_BYTES]
             # the arenas were sized before the receive totals were known: every rank sees the same matrix and
             # the same capacities, so all agree on whether somebody has to grow (rare after the first build)
             need = [engine.layout_bytes(WIN_ARENA, stage, int(matrix[:, d].sum())) for d in range(world)]
@@ -257,8 +283,10 @@ def build_sharded(engine: ShardEngine) -> dict:
             if any(n > c for n, c in zip(need, caps)):
                 d1 = engine.window(WIN_ARENA, need[rank])
                 arena_desc = _all_gather_bytes(d1, dev)
+                lap(f"plan{stage}.grow")
+        info[f"recv{stage}"] = int(matrix[:, rank].sum())  # items this rank holds after the exchange
         connect(WIN_ARENA, arena_desc)
-        connect(WIN_UNIQUE, rows[:, o + DESC_BYTES:o + 2 * DESC_BYTES])
+        connect(WIN_UNIQUE, uniq_desc)
         if stage == 1:
             engine.set_unique(ru)
         lap(f"plan{stage}")
@@ -444,6 +472,19 @@ def shard_proteins(residues: np.ndarray, offsets: np.ndarray, rank: int, world: 
     p0, p1 = int(cuts[rank]), int(cuts[rank + 1])
     off = offsets[p0:p1 + 1] - offsets[p0]
     return residues[int(offsets[p0]):int(offsets[p1])], off.astype(np.uint64), p0
+
+
+def shard_sizes(offsets: np.ndarray, world: int) -> np.ndarray:
+    """(proteins, residues) of every rank's shard under shard_proteins: [world, 2] for build_sharded(shard_sizes=)."""
+    n = len(offsets) - 1
+    total = int(offsets[-1])
+    cuts = [int(np.searchsorted(offsets, total * r // world, side="left")) for r in range(world)] + [n]
+    cuts[0] = 0
+    cuts = np.minimum(np.maximum.accumulate(cuts), n)
+    out = np.zeros((world, 2), dtype=np.uint64)
+    for r in range(world):
+        out[r] = (cuts[r + 1] - cuts[r], int(offsets[cuts[r + 1]]) - int(offsets[cuts[r]]))
+    return out
 
 
 def build_local(indexes) -> None:

@@ -24,7 +24,7 @@ import torch.distributed as dist  # noqa: E402
 import dbindex_b200 as dbi  # noqa: E402
 from bench import CFG2, sharded_parity  # noqa: E402
 from dbindex_b200 import synth  # noqa: E402
-from dbindex_b200.multigpu import GpuShardEngine, build_sharded, route_queries, shard_proteins  # noqa: E402
+from dbindex_b200.multigpu import GpuShardEngine, build_sharded, route_queries, shard_proteins, shard_sizes  # noqa: E402
 
 
 def main():
@@ -58,7 +58,7 @@ def main():
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
-        info = build_sharded(GpuShardEngine(g, dev))
+        info = build_sharded(GpuShardEngine(g, dev), shard_sizes(off, world))
         b.record(stream)
         torch.cuda.synchronize()
         if i:

@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 
 import dbindex_b200 as dbi  # noqa: E402
 from dbindex_b200 import synth  # noqa: E402
-from dbindex_b200.multigpu import build_sharded, owned_mask, route_queries, shard_proteins  # noqa: E402
+from dbindex_b200.multigpu import build_sharded, owned_mask, route_queries, shard_proteins, shard_sizes  # noqa: E402
 from oracle.oracle_py import Oracle  # noqa: E402
 from tests.cpu_engine import OracleShardEngine  # noqa: E402
 from tests.util import PARAM_SETS, bits  # noqa: E402
@@ -65,11 +65,12 @@ def main():
         g = dbi.GpuIndex(params)
         sres, soff, _ = shard_proteins(res, off, rank, world)  # a rank only ever sees its own shard of the FASTA
         g.add_proteins(sres, soff)
-        info = build_sharded(GpuShardEngine(g, torch.device("cuda", local)))
+        info = build_sharded(GpuShardEngine(g, torch.device("cuda", local)), shard_sizes(off, world))
         eng = GpuEntries(g, info)
     else:
         eng = OracleShardEngine(params, res, off)
-        info = build_sharded(eng)
+        # both forms: the shard sizes gathered by the build itself, or handed over by the caller that cut the FASTA
+        info = build_sharded(eng, shard_sizes(off, world) if name == "cfg2_mods" else None)
     mine = eng.entries()
 
     # the single-process answer
