@@ -66,6 +66,22 @@ void* win_get(int device, int window, uint64_t bytes, uint64_t* cap) {
   return p;
 }
 
+// the largest cached block of a window, if any (no allocation): a fresh handle adopts what an earlier
+// handle of this process left, so its peers keep their mappings and nothing has to grow again
+void* win_adopt(int device, int window, uint64_t* cap) {
+  WinCaches& c = win_caches();
+  std::lock_guard<std::mutex> lk(c.mu);
+  auto& v = c.free_[device & 63][window];
+  int best = -1;
+  for (int i = 0; i < (int)v.size(); ++i)
+    if (best < 0 || v[i].cap > v[best].cap) best = i;
+  if (best < 0) return nullptr;
+  const WinBlock b = v[best];
+  v.erase(v.begin() + best);
+  *cap = b.cap;
+  return b.p;
+}
+
 void win_put(int device, int window, void* p, uint64_t cap) {
   if (!p) return;
   WinCaches& c = win_caches();
@@ -168,6 +184,7 @@ int dbi_mg_window_ensure(dbi_handle* h, int window, uint64_t bytes, dbi_mg_windo
     return DBI_EINVAL;
   }
   dbi_handle::MgWindow& w = h->win[window];
+  if (!w.p) w.p = win_adopt(h->device, window, &w.cap);
   if (bytes > w.cap) {
     if (window == kWinProt && h->mg_layout) {
       set_error("window 0 cannot grow once the shards are laid out");
@@ -603,6 +620,39 @@ int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_loc
     }
     send_counts[owner(sl)] += sc;
     recv_totals[owner(sl)] += rt;
+  }
+  return DBI_OK;
+}
+
+// dbi_mg_plan for a rank that holds EVERY rank's local histograms (one all-gather instead of an all-reduce plus
+// a second exchange of the send counts): hist_all[world][3 * DBI_MG_BINS].  Sums the global histogram, places
+// the cuts, and fills the whole count matrix: matrix[src * world + dst] = items rank src sends to rank dst.
+int dbi_mg_plan_matrix(int world, const uint64_t* hist_all, int shift, double min_mass, const double* cost,
+                       int n_slices, uint32_t* bin_splitters, uint64_t* matrix) {
+  if (world < 1 || world > kMaxRanks || !hist_all || !matrix) {
+    set_error("bad argument");
+    return DBI_EINVAL;
+  }
+  const size_t HB = 3 * (size_t)kMgBins;
+  std::vector<uint64_t> global(HB, 0);
+  for (int r = 0; r < world; ++r)
+    for (size_t i = 0; i < HB; ++i) global[i] += hist_all[(size_t)r * HB + i];
+  uint64_t send[kMaxRanks], recv[kMaxRanks];
+  uint32_t split_local[kMaxSlices];
+  uint32_t* split = bin_splitters ? bin_splitters : split_local;
+  if (int rc = dbi_mg_plan(world, global.data(), hist_all, shift, min_mass, cost, n_slices, split, send, recv)) return rc;
+  for (int src = 0; src < world; ++src) {
+    uint64_t* row = matrix + (size_t)src * world;
+    for (int d = 0; d < world; ++d) row[d] = 0;
+    const uint64_t* plain = hist_all + (size_t)src * HB + kMgBins;
+    int lo = 0;
+    for (int sl = 0; sl < n_slices; ++sl) {
+      const int hi = sl + 1 < n_slices ? (int)split[sl] : kMgBins;
+      uint64_t c = 0;
+      for (int x = lo; x < hi; ++x) c += plain[x];
+      row[mg_slice_owner((uint32_t)sl, (uint32_t)n_slices, (uint32_t)world)] += c;
+      lo = hi;
+    }
   }
   return DBI_OK;
 }

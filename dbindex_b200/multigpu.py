@@ -105,6 +105,33 @@ def plan_exchange(world: int, hist_global: np.ndarray, hist_local: np.ndarray, s
     return split[:n_slices - 1].copy(), send, recv
 
 
+def plan_matrix(world: int, hist_all: np.ndarray, shift: int, min_mass: float, stage: int = 0, has_mods: bool = False,
+                cost=None, n_slices: int = 0):
+    """dbi_mg_plan_matrix: from EVERY rank's local [weighted | plain | groups] histograms ([world, 3 * MG_BINS]) the
+    bin splitters [n_slices - 1] and the whole count matrix [world, world] (row = sender)."""
+    import ctypes as C
+    from .capi import load_library
+    lib = load_library()
+    lib.dbi_mg_plan_matrix.restype = C.c_int
+    lib.dbi_mg_plan_matrix.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.dbi_mg_default_cost.restype = None
+    lib.dbi_mg_default_cost.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    n_slices = n_slices or world
+    c = np.zeros(4, dtype=np.float64)
+    if cost is None:
+        lib.dbi_mg_default_cost(stage, 1 if has_mods else 0, c.ctypes.data)
+    else:
+        c[:] = cost
+    ha = np.ascontiguousarray(hist_all, dtype=np.uint64).reshape(world, 3 * MG_BINS)
+    split = np.zeros(max(n_slices - 1, 1), dtype=np.uint32)
+    matrix = np.zeros((world, world), dtype=np.uint64)
+    rc = lib.dbi_mg_plan_matrix(world, ha.ctypes.data, int(shift), float(min_mass), c.ctypes.data, int(n_slices),
+                                split.ctypes.data, matrix.ctypes.data)
+    if rc != 0:
+        raise RuntimeError((lib.dbi_last_error() or b"").decode(errors="replace"))
+    return split[:n_slices - 1].copy(), matrix
+
+
 def splitter_masses(bin_splitters: np.ndarray, shift: int, min_mass: float) -> np.ndarray:
     """The mass at which each splitter sits: radix key = bits(mass) - bits(min_mass)."""
     base = np.float64(min_mass).view(np.uint64)
@@ -225,9 +252,9 @@ def build_sharded(engine: ShardEngine, shard_sizes=None) -> dict:
     unified = os.environ.get("DBI_MG_UNIFIED", "1") != "0"
 
     def exchange(stage: int, item_bytes: int):
-        """Exchange 0 plans the cuts of the index (histograms -> all-reduce -> equal-cost splitters); exchange 1
-        reuses them -- a variant lies at most a few shifts above its peptide, so most groups stay on the GPU
-        that owns the peptide -- and only needs the counts of the groups that cross a cut."""
+        """Exchange 0 plans the cuts of the index (local histograms -> one all-gather -> dbi_mg_plan_matrix on every
+        rank); exchange 1 reuses them -- a variant lies at most a few shifts above its peptide, so most groups stay
+        on the GPU that owns the peptide -- and only needs the counts of the groups that cross a cut."""
         nu = np.array([engine.n_unique()], dtype=np.uint64).view(np.uint8)
         if stage == 0 or not unified:
             # ONE all-gather carries every rank's local histograms and the windows it has: every rank then sums
@@ -242,16 +269,10 @@ def build_sharded(engine: ShardEngine, shard_sizes=None) -> dict:
             hb = 3 * MG_BINS * 8
             hists = rows[:, :hb].copy().view(np.uint64).reshape(world, 3 * MG_BINS)
             lap(f"hist{stage}.gather")
-            split, send, recv = plan_exchange(world, hists.sum(axis=0, dtype=np.uint64), hists[rank], shift, engine.min_mass,
-                                              stage, engine.has_mods and unified, n_slices=n_slices)
+            split, matrix = plan_matrix(world, hists, shift, engine.min_mass, stage, engine.has_mods and unified,
+                                        n_slices=n_slices)
             state["split"], state["shift"] = split, shift
-            edges = np.concatenate(([0], split.astype(np.int64), [MG_BINS]))
-            owners = slice_owner(np.arange(n_slices), n_slices, world)
-            matrix = np.zeros((world, world), dtype=np.uint64)
-            for src in range(world):
-                cs = np.concatenate(([0], np.cumsum(hists[src, MG_BINS:2 * MG_BINS].astype(np.int64))))
-                np.add.at(matrix[src], owners, (cs[edges[1:]] - cs[edges[:-1]]).astype(np.uint64))
-            assert np.array_equal(matrix[rank], send) and np.array_equal(matrix.sum(axis=0), recv)
+            send, recv = matrix[rank], matrix.sum(axis=0, dtype=np.uint64)
             ru = rows[:, hb:hb + 8].copy().view(np.uint64).reshape(world)
             descs = rows[:, hb + 8:]
             lap(f"hist{stage}.plan")

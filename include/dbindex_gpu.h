@@ -408,6 +408,11 @@ int dbi_mg_hist(dbi_handle* h, int stage, void* d_hist, int* shift);
 int dbi_mg_plan(int world, const uint64_t* hist_global, const uint64_t* hist_local, int shift, double min_mass,
                 const double* cost, int n_slices, uint32_t* bin_splitters, uint64_t* send_counts,
                 uint64_t* recv_totals);
+/* the same for a rank that holds every rank's local histograms, hist_all[world][3 * DBI_MG_BINS] (one all-gather
+ * instead of an all-reduce plus an exchange of the send counts): cuts + the whole count matrix,
+ * matrix[src * world + dst] = items rank src sends to rank dst */
+int dbi_mg_plan_matrix(int world, const uint64_t* hist_all, int shift, double min_mass, const double* cost,
+                       int n_slices, uint32_t* bin_splitters, uint64_t* matrix);
 void dbi_mg_default_cost(int stage, int has_mods, double* cost);
 /* items of exchange `stage` this rank would send to every rank under the given cuts [world] */
 int dbi_mg_count(dbi_handle* h, int stage, const uint32_t* bin_splitters, int n_slices, uint64_t* send_counts);

@@ -161,3 +161,19 @@ def test_shard_proteins_covers_the_proteome_in_order():
             first += len(soff) - 1
             got.append(sres)
         assert first == len(off) - 1 and np.array_equal(np.concatenate(got), res)
+
+
+def test_plan_matrix_equals_per_rank_plans():
+    """dbi_mg_plan_matrix (every rank's local histograms -> cuts + whole count matrix) agrees with dbi_mg_plan run
+    on the summed histogram with each rank's own one."""
+    from dbindex_b200.multigpu import plan_matrix
+    rng = np.random.default_rng(11)
+    for world, fold in ((1, 1), (2, 2), (3, 1), (8, 2), (16, 2)):
+        hists = np.stack([np.concatenate([p * np.uint64(9), p, p * np.uint64(4)]) for p in
+                          (rng.integers(0, 40, size=MG_BINS).astype(np.uint64) for _ in range(world))])
+        split, matrix = plan_matrix(world, hists, 42, 600.0, stage=0, has_mods=True, n_slices=fold * world)
+        hg = hists.sum(axis=0, dtype=np.uint64)
+        for r in range(world):
+            s2, send, recv = plan_exchange(world, hg, hists[r], 42, 600.0, stage=0, has_mods=True, n_slices=fold * world)
+            assert s2.tolist() == split.tolist()
+            assert send.tolist() == matrix[r].tolist() and recv.tolist() == matrix.sum(axis=0).tolist()
