@@ -792,6 +792,8 @@ def run_sharded(args, rank: int, local_rank: int, world: int):
 
 
 def main():
+    import gc
+    gc.disable()  # no collector pauses inside timed regions (the steps allocate no cycles worth collecting)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

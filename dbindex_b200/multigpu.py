@@ -162,15 +162,17 @@ def _world() -> int:
     return dist.get_world_size() if dist.is_initialized() else 1
 
 
-_pinned = {}  # nbytes -> page-locked staging buffer (a pageable D2H of the 768 KB histogram gather costs ~0.15 ms)
+_pinned = [None]  # ONE page-locked staging buffer for every small gather (a pageable D2H of the 768 KB histogram
+#                   gather costs ~0.15 ms; allocating pinned memory costs milliseconds, so it happens once)
 
 
 def _to_host(t: torch.Tensor) -> np.ndarray:
     if t.device.type != "cuda":
         return t.numpy()
-    buf = _pinned.get(t.numel())
-    if buf is None:
-        buf = _pinned[t.numel()] = torch.empty(t.numel(), dtype=torch.uint8).pin_memory()
+    n = t.numel()
+    if _pinned[0] is None or _pinned[0].numel() < n:
+        _pinned[0] = torch.empty(max(2 * n, 4 << 20), dtype=torch.uint8).pin_memory()
+    buf = _pinned[0][:n]
     buf.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return buf.numpy()
