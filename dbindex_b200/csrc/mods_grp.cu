@@ -338,6 +338,15 @@ struct ExpSmem {
 
 __device__ __forceinline__ uint64_t below(int i) { return ~(~0ull << i); }  // bits strictly below position i
 
+// appends (position + 1) of every set bit of c, ascending, to the byte pool; the two 32-bit halves are walked
+// separately (most peptides have fewer than 33 residues: half the instructions of a 64-bit walk)
+__device__ __forceinline__ uint32_t fill_sites(uint64_t c, uint8_t* pool, uint32_t x) {
+  uint32_t lo = (uint32_t)c, hi = (uint32_t)(c >> 32);
+  for (; lo; lo &= lo - 1) pool[x++] = (uint8_t)__ffs((int)lo);
+  for (; hi; hi &= hi - 1) pool[x++] = (uint8_t)(32 + __ffs((int)hi));
+  return x;
+}
+
 // pairs i2 < i3 above position i (third and fourth class)
 __device__ __forceinline__ uint32_t pairs_above(int i, uint64_t c2, uint64_t c3) {
   uint32_t w = 0;
@@ -473,18 +482,16 @@ __global__ void __launch_bounds__(ET_THREADS, 4)
       append(b);
       continue;
     }
-    uint32_t x = at;
-    for (uint64_t m = c0; m; m &= m - 1) s.pool[x++] = (uint8_t)__ffsll((long long)m);  // position + 1
+    uint32_t x = fill_sites(c0, s.pool, at);
     const uint32_t l0 = at;
     uint32_t l1 = l0, l2 = l0;
     if (n1) {
       l1 = x;
-      for (uint64_t m = c1; m; m &= m - 1) s.pool[x++] = (uint8_t)__ffsll((long long)m);
+      x = fill_sites(c1, s.pool, x);
     }
     if (k > 2) {
       l2 = q2 == q0 ? l0 : (q2 == q1 ? l1 : x);
-      if (n2)
-        for (uint64_t m = c2; m; m &= m - 1) s.pool[x++] = (uint8_t)__ffsll((long long)m);
+      if (n2) x = fill_sites(c2, s.pool, x);
     }
     if (k == 1) {
       b.b0 = (uint16_t)l0;
