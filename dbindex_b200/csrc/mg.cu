@@ -3,8 +3,9 @@
 // The reference already shards its index by mass: DBIndexStoreSQLiteMult splits the mass axis
 // into `indexFactor` equal-width buckets, one SQLite file each (DBIndexStoreSQLiteMult.java:55-56,
 // 215-217) and answers a query from the buckets its range touches (:333-343).  Here a bucket is
-// a GPU, the bucket edges are equal-COUNT splitters taken from a key histogram (the mass density
-// is far from uniform), and records travel to their bucket with an NCCL all-to-all.
+// a GPU slice of the mass axis, the slice edges are taken from key histograms (the mass density is
+// far from uniform; dbi_mg_plan balances every phase of the build), and records travel to their
+// bucket inside the partition kernel itself: peer stores over NVLink into the owners' arenas.
 #include "kernels.cuh"
 
 namespace dbi {

@@ -8,8 +8,8 @@ touches (:333-343).  Here a bucket is a GPU:
   1. every rank is given ITS OWN shard of the FASTA (proteins in rank order, so ids stay global),
      packs it into its place of the global residue buffer (window 0) and pulls the other shards over
      NVLink -- the FASTA crosses PCIe once, not once per GPU;
-  2. every rank digests its share of the start positions;
-  3. exchange 0: key histograms (records, and the variants they will expand to) -> all-reduce -> cuts of
+  2. every rank digests the start positions of its own shard while the other shards arrive (side stream);
+  3. exchange 0: key histograms (records, and the groups / variants they will expand to) -> one all-gather -> cuts of
      equal estimated COST (sorting, expansion, expected query hits) -> ONE kernel that partitions the
      records and writes them straight into the owners' arenas (mapped peer memory); rank-ordered arrival
      keeps "first occurrence" global (SURVEY.md Q6);

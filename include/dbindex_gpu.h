@@ -335,11 +335,12 @@ void dbi_fasta_close(dbi_fasta* f);
 /* ---- sharded (multi-GPU) build ------------------------------------------------
  * The reference shards its index by mass into `indexFactor` SQLite files
  * (DBIndexStoreSQLiteMult.java:55-56,215-217) and answers a query from the buckets its range touches
- * (:333-343).  Here a bucket is a GPU holding one contiguous slice of the mass axis.  One handle per GPU
+ * (:333-343).  Here a bucket is a GPU holding one slice of the mass axis (with differential mods: two
+ * FOLDED slices, a light and a heavy one, see dbi_mg_plan).  One handle per GPU
  * = one rank; rank r is given ITS shard of the FASTA (dbi_add_proteins; the shards follow each other in
  * rank order, so protein ids stay global and in file order).  The bulk data moves inside two kernels
  * that write straight into the other GPUs' memory over NVLink (mapped peer memory); the caller only
- * carries small host arrays between the ranks (two 32 KB histograms, a world x world count matrix,
+ * carries small host arrays between the ranks (three 32 KB histograms, a world x world count matrix,
  * 96-byte window descriptors) with whatever transport it has -- torch.distributed / NCCL between
  * processes (dbindex_b200/multigpu.py), nothing at all when one process holds every handle:
  *
@@ -349,10 +350,11 @@ void dbi_fasta_close(dbi_fasta* f);
  *
  *   dbi_mg_begin
  *   dbi_mg_set_shards(sizing) -> dbi_mg_window_ensure(0) -> dbi_mg_set_shards -> [exchange window 0] ->
- *   dbi_mg_pull_proteome                  every rank now holds the packed residues of all shards
- *   dbi_mg_digest                         its share of the start positions
- *   dbi_mg_hist(0) .. [all-reduce] .. dbi_mg_plan .. dbi_mg_window_ensure(1, 2) .. [all-gather counts +
- *   windows] .. dbi_mg_window_import .. dbi_mg_scatter(0) .. [barrier]
+ *   dbi_mg_pull_proteome                  the other shards arrive on a side stream (joined by dbi_mg_index_base)
+ *   dbi_mg_digest                         the start positions of the OWN shard (reads nothing else)
+ *   dbi_mg_hist(0) .. [all-gather local histograms + window descriptors] .. dbi_mg_plan_matrix (or all-reduce
+ *   .. dbi_mg_plan .. all-gather counts) .. dbi_mg_window_ensure(1, 2) [re-gather the descriptors only if a
+ *   window grew] .. dbi_mg_window_import .. dbi_mg_scatter(0) .. [barrier]
  *   dbi_mg_index_base                     sort + merge of this rank's mass slice
  *   [all-gather n_unique] dbi_mg_set_unique
  *   no mods:  dbi_mg_finish
