@@ -267,6 +267,17 @@ class DBIndexer:
         self.index = GpuIndex(self.sparam)
         self.inited = True
 
+    def export_reference_index(self, database_id: str) -> dict:
+        """Write the built index as the reference's own on-disk index -- directory `<database_id>.idx/` with one
+        SQLite file per mass bucket, merged rows (dbindex_b200/sqlite_export.py; DBIndexStoreSQLiteMult.java:101-142,
+        DBIndexStoreSQLiteByteIndexMerge.java:696-716) -- so that an unmodified reference finds an existing index
+        there.  Differential-mod variants have no counterpart in that format and are left out."""
+        from .sqlite_export import export_sqlite
+        self._require()
+        n = self.index.stats()["n_entries"]
+        return export_sqlite(lambda b, c: self.index.fetch(b, c), n, database_id, index_factor=self.index_factor,
+                             mass_group_factor=self.sparam.mass_group_factor)
+
     def _require(self):
         if not self.inited or self.index is None:
             raise DBIndexStoreException("Indexer is not initialized")  # DBIndexStoreSQLiteMult.java:153
