@@ -242,6 +242,32 @@ def test_store_level_kat_mult_main_gpu():
         assert sorted(pep[int(b[0]):int(b[0] + c[0])]) == sorted(["AB", "ABC", "GHI", "HIJ", "ABCD", "IJKLM"])
 
 
+def test_export_reference_sqlite_index(tmp_path):
+    """the GPU-built index written as the reference's own bucket directory; its rows, read back
+    through the row walk of parseAddPeptideInfo, are the oracle's unmodified entries (cfg2: variants are skipped)."""
+    from dbindex_b200.sqlite_export import read_rows
+    p = dbi.default_params(**PARAM_SETS["cfg2_mods"])
+    res, off = synth.synth_proteome(80, 31, median_len=250, min_len=5)
+    seqs = [res[int(off[i]):int(off[i + 1])].tobytes().decode() for i in range(len(off) - 1)]
+    seqs += [seqs[2], seqs[2]]
+    ix = DBIndexer(p)
+    ix.init()
+    ix.run(proteins=(synth.deflines(len(seqs)), seqs))
+    try:
+        info = ix.export_reference_index(str(tmp_path / "proteome.fasta_0123"))
+        o = Oracle(p); o.add_proteins(*pack(seqs)); assert o.build() == 0
+        e = o.entries()
+        plo = e["prot_list_off"].astype(np.int64)
+        want = sorted((int(bits(e["mass"][i:i + 1])[0]), int(e["first_off"][i]), int(e["len"][i]),
+                       tuple(int(x) for x in e["prot_ids"][plo[i]:plo[i + 1]]))
+                      for i in range(len(e["mass"])) if e["modpat"][i] == 0)
+        got = sorted((int(bits(np.array([m]))[0]), o_, l_, ids) for _, peps in read_rows(info["dir"]) for m, o_, l_, ids in peps)
+        assert info["peptides"] == len(want) == o.counts()["n_unique"]
+        assert got == want
+    finally:
+        ix.close()
+
+
 def test_reference_api_mirror():
     """The DBIndexImpl / DBIndexer surface (DBIndexImpl.java:180-237,501-513; DBIndexer.java:762-947)."""
     p = dbi.default_params()
