@@ -344,3 +344,40 @@ def test_oracle_matches_a_sqlite_restatement_of_the_reference_store():
         got = canon(store.get_sequences(float(qm[k]), float(tol[k])))
         exp = canon(mine[int(b[k]):int(b[k] + c[k])])
         assert got == exp, (k, qm[k], tol[k], len(got), len(exp))
+
+
+@pytest.mark.parametrize("name", ["cfg1_tryptic", "cfg2_mods", "semi_nocut_mods"])
+def test_oracle_query_hits_match_entries_and_python_flanks(name):
+    """orc_query_hits (the checker of dbi_query_hits) against an independent formulation: the hits of [lo, hi] are
+    the entries with lo <= mass <= hi (both ends inclusive), each with the peptide cut from its first
+    protein (ProteinCache.getPeptideSequence), the flanks of the Python restatement of Util.getResidues
+    (dbindex_b200/indexer.get_residues, Util.java:130-162 incl. the right-side off-by-one), its mod pattern and
+    its protein list."""
+    from dbindex_b200.indexer import get_residues
+    p = dbi.default_params(**PARAM_SETS[name])
+    res, off = synth.synth_proteome(25, 2024, median_len=160, min_len=5)
+    seqs = [res[int(off[i]):int(off[i + 1])].tobytes().decode() for i in range(len(off) - 1)]
+    seqs += [seqs[1], "MSTYMSTYK", "K", ""]
+    o = run_oracle(p, seqs)
+    e = o.entries()
+    n = len(e["mass"])
+    plo = e["prot_list_off"].astype(np.int64)
+    rng = np.random.default_rng(12)
+    qm = np.concatenate([e["mass"][rng.integers(0, n, 25)], rng.uniform(600, 6000, 10), [e["mass"][0], e["mass"][-1]]])
+    tol = np.concatenate([qm[:10] * 1e-5, np.zeros(15), np.full(10, 3.0), [0.0, 0.0]])
+    lo, hi = np.maximum(qm - tol, 0.0), qm + tol
+    h = o.query_hits(lo, hi)
+    ho, so, po = (h[k].astype(np.int64) for k in ("hit_off", "seq_off", "prot_list_off"))
+    fl = h["flanks"].reshape(-1, 6)
+    assert ho[0] == 0 and ho[-1] == len(h["mass"])
+    for q in range(len(qm)):
+        want = []
+        for i in np.nonzero((e["mass"] >= lo[q]) & (e["mass"] <= hi[q]))[0]:
+            prot, o_, l_ = int(e["first_prot"][i]), int(e["first_off"][i]), int(e["len"][i])
+            left, right = get_residues(o_, l_, seqs[prot])
+            want.append((int(bits(e["mass"][i:i + 1])[0]), prot, o_, l_, int(e["modpat"][i]), seqs[prot][o_:o_ + l_],
+                         left + right, tuple(int(x) for x in e["prot_ids"][plo[i]:plo[i + 1]])))
+        got = [(int(bits(h["mass"][i:i + 1])[0]), int(h["first_prot"][i]), int(h["first_off"][i]), int(h["len"][i]),
+                int(h["modpat"][i]), h["seq"][so[i]:so[i + 1]].tobytes().decode(), fl[i].tobytes().decode(),
+                tuple(int(x) for x in h["prot_ids"][po[i]:po[i + 1]])) for i in range(ho[q], ho[q + 1])]
+        assert sorted(got) == sorted(want), (q, qm[q], tol[q])
