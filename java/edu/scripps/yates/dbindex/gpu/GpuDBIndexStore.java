@@ -37,7 +37,12 @@ public class GpuDBIndexStore implements DBIndexStore {
 	private static final int MAX_MASS = 8000; // Constants.MAX_PRECURSOR_MASS, DBIndexStoreSQLiteMult buckets
 	private final DBIndexSearchParams sparam;
 	private final Arena arena = Arena.ofShared();
-	private MemorySegment handle = MemorySegment.NULL;
+	private MemorySegment handle = MemorySegment.NULL; // handles[0]
+	// -Ddbindex.gpu.devices=N: ONE index sharded over N GPUs of this box (the reference's mass buckets,
+	// DBIndexStoreSQLiteMult.java:55-56,215-217, as GPUs): handle r lives on device r and is given shard r of the proteins
+	private final int nDevices = Math.max(1, Integer.getInteger("dbindex.gpu.devices", 1));
+	private MemorySegment[] handles = new MemorySegment[0];
+	private double[] splitMass = new double[0]; // masses at which the slices of the sharded index are cut
 	private boolean inited = false, built = false;
 	private ProteinCache proteinCache;
 	private String indexFile; // null = in-memory index only
@@ -124,12 +129,18 @@ public class GpuDBIndexStore implements DBIndexStore {
 		if (inited)
 			throw new DBIndexStoreException("Already intialized"); // DBIndexStoreSQLiteMult.java:97-99
 		try {
-			final MemorySegment out = arena.allocate(ADDRESS);
-			check((int) DbiNative.dbi_create.invoke(params(), out));
-			handle = out.get(ADDRESS, 0);
+			handles = new MemorySegment[nDevices];
+			for (int d = 0; d < nDevices; ++d) {
+				final MemorySegment out = arena.allocate(ADDRESS);
+				final MemorySegment p = params();
+				setInt(p, "device", d);
+				check((int) DbiNative.dbi_create.invoke(p, out));
+				handles[d] = out.get(ADDRESS, 0);
+			}
+			handle = handles[0];
 			// on-disk index (in_memory_index = false): <fasta>_<md5(params)> like the reference (IndexUtil.java:270-324);
 			// if the file is there the index is loaded and DBIndexer.run() skips indexing (DBIndexer.java:522-531)
-			if (!sparam.isInMemoryIndex()) {
+			if (!sparam.isInMemoryIndex() && nDevices == 1) { // a sharded index is rebuilt (dbi_save holds one GPU's index)
 				indexFile = sparam.getFullIndexFileName(null, null, false, null, false, null) + ".gpuidx";
 				if (new java.io.File(indexFile).exists()) {
 					check((int) DbiNative.dbi_load.invoke(handle, arena.allocateFrom(indexFile)));
@@ -191,8 +202,38 @@ public class GpuDBIndexStore implements DBIndexStore {
 			final MemorySegment o = a.allocate(JAVA_LONG, offsets.size());
 			for (int i = 0; i < offsets.size(); ++i)
 				o.setAtIndex(JAVA_LONG, i, offsets.get(i));
-			check((int) DbiNative.dbi_add_proteins.invoke(handle, r, o, offsets.size() - 1));
-			check((int) DbiNative.dbi_build.invoke(handle));
+			if (nDevices == 1) {
+				check((int) DbiNative.dbi_add_proteins.invoke(handle, r, o, offsets.size() - 1));
+				check((int) DbiNative.dbi_build.invoke(handle));
+			} else {
+				// contiguous shards of about equal residue count, in protein order (ids stay global and in file order);
+				// dbi_add_proteins takes offsets[first .. last] of the shared buffer as they are
+				final int nProt = offsets.size() - 1;
+				final long total = offsets.get(nProt);
+				int first = 0;
+				for (int d = 0; d < nDevices; ++d) {
+					int last = nProt;
+					if (d < nDevices - 1) {
+						last = first;
+						while (last < nProt && offsets.get(last) < total * (d + 1) / nDevices)
+							++last;
+					}
+					check((int) DbiNative.dbi_add_proteins.invoke(handles[d], r, o.asSlice(8L * first), last - first));
+					first = last;
+				}
+				// the whole exchange in one call: shard packing, NVLink pulls, own-shard digest, the two multisplit /
+				// peer-memory scatter kernels into folded mass slices, per-GPU sort + merge + expansion
+				final MemorySegment hs = a.allocate(ADDRESS, nDevices);
+				for (int d = 0; d < nDevices; ++d)
+					hs.setAtIndex(ADDRESS, d, handles[d]);
+				check((int) DbiNative.dbi_mg_build_local.invoke(hs, nDevices));
+				final int slices = (int) DbiNative.dbi_mg_slices.invoke(handle);
+				final MemorySegment sm = a.allocate(JAVA_DOUBLE, Math.max(1, slices - 1));
+				check((int) DbiNative.dbi_mg_split_masses.invoke(handle, sm));
+				splitMass = new double[slices - 1];
+				for (int i = 0; i < slices - 1; ++i)
+					splitMass[i] = sm.getAtIndex(JAVA_DOUBLE, i);
+			}
 			built = true;
 			if (indexFile != null)
 				check((int) DbiNative.dbi_save.invoke(handle, a.allocateFrom(indexFile)));
@@ -243,6 +284,38 @@ public class GpuDBIndexStore implements DBIndexStore {
 		for (int i = 0; i < lo.length; ++i) // "Cannot query, unsupported precursor mass" -> empty (Mult:333-338)
 			if ((int) lo[i] / bucketRange > sparam.getIndexFactor() - 1 || (int) hi[i] / bucketRange > sparam.getIndexFactor() - 1)
 				return ret;
+		if (nDevices > 1) {
+			// Mult.getSequences walks the buckets a range touches (:333-343); here: the GPUs owning the slices it
+			// touches.  Slice s = [splitMass[s-1], splitMass[s]) lives on GPU s < N ? s : slices - 1 - s.
+			final int slices = splitMass.length + 1;
+			for (int d = 0; d < nDevices; ++d) {
+				final List<Double> l = new ArrayList<>(), h = new ArrayList<>();
+				for (int i = 0; i < lo.length; ++i) {
+					boolean mine = false;
+					for (int sl = 0; sl < slices && !mine; ++sl) {
+						final int owner = sl < nDevices ? sl : slices - 1 - sl;
+						final double left = sl == 0 ? Double.NEGATIVE_INFINITY : splitMass[sl - 1];
+						final double right = sl == slices - 1 ? Double.POSITIVE_INFINITY : splitMass[sl];
+						mine = owner == d && hi[i] >= left && lo[i] < right;
+					}
+					if (mine) {
+						l.add(lo[i]);
+						h.add(hi[i]);
+					}
+				}
+				if (!l.isEmpty())
+					queryOn(handles[d], l.stream().mapToDouble(Double::doubleValue).toArray(),
+							h.stream().mapToDouble(Double::doubleValue).toArray(), ret);
+			}
+			return ret;
+		}
+		queryOn(handle, lo, hi, ret);
+		return ret;
+	}
+
+	/** one dbi_query_hits + dbi_query_hits_read on one GPU; the hits are appended to ret */
+	private void queryOn(MemorySegment handle, double[] lo, double[] hi, List<IndexedSequence> ret)
+			throws DBIndexStoreException {
 		try (Arena a = Arena.ofConfined()) {
 			final int nq = lo.length;
 			final MemorySegment dlo = a.allocate(JAVA_DOUBLE, nq), dhi = a.allocate(JAVA_DOUBLE, nq);
@@ -293,7 +366,6 @@ public class GpuDBIndexStore implements DBIndexStore {
 		} catch (final Throwable t) {
 			throw new DBIndexStoreException("Error getting peptides ", t);
 		}
-		return ret;
 	}
 
 	/** pattern byte k = position + 1 of the k-th modified residue -> "PEPT(+79.9663)IDE". */
@@ -336,9 +408,13 @@ public class GpuDBIndexStore implements DBIndexStore {
 	public long getNumberSequences() throws DBIndexStoreException {
 		requireInit();
 		try (Arena a = Arena.ofConfined()) {
-			final MemorySegment st = a.allocate(512);
-			check((int) DbiNative.dbi_stats_get.invoke(handle, st));
-			return st.get(JAVA_LONG, 32); // dbi_stats.n_entries
+			long total = 0;
+			for (final MemorySegment h : handles) {
+				final MemorySegment st = a.allocate(512);
+				check((int) DbiNative.dbi_stats_get.invoke(h, st));
+				total += st.get(JAVA_LONG, 32); // dbi_stats.n_entries
+			}
+			return total;
 		} catch (final DBIndexStoreException e) {
 			throw e;
 		} catch (final Throwable t) {
@@ -359,14 +435,16 @@ public class GpuDBIndexStore implements DBIndexStore {
 	public List<Integer> getEntryKeys() throws DBIndexStoreException {
 		requireInit();
 		try (Arena a = Arena.ofConfined()) {
-			final MemorySegment n = a.allocate(JAVA_LONG);
-			check((int) DbiNative.dbi_entry_keys.invoke(handle, MemorySegment.NULL, 0L, n));
-			final long k = n.get(JAVA_LONG, 0);
-			final MemorySegment keys = a.allocate(JAVA_INT, Math.max(1, k));
-			check((int) DbiNative.dbi_entry_keys.invoke(handle, keys, k, n));
-			final List<Integer> ret = new ArrayList<>((int) k);
-			for (long i = 0; i < k; ++i)
-				ret.add(keys.getAtIndex(JAVA_INT, i));
+			final List<Integer> ret = new ArrayList<>();
+			for (final MemorySegment h : handles) { // Mult.getEntryKeys concatenates its buckets the same way (:196-201)
+				final MemorySegment n = a.allocate(JAVA_LONG);
+				check((int) DbiNative.dbi_entry_keys.invoke(h, MemorySegment.NULL, 0L, n));
+				final long k = n.get(JAVA_LONG, 0);
+				final MemorySegment keys = a.allocate(JAVA_INT, Math.max(1, k));
+				check((int) DbiNative.dbi_entry_keys.invoke(h, keys, k, n));
+				for (long i = 0; i < k; ++i)
+					ret.add(keys.getAtIndex(JAVA_INT, i));
+			}
 			return ret;
 		} catch (final DBIndexStoreException e) {
 			throw e;
@@ -381,11 +459,13 @@ public class GpuDBIndexStore implements DBIndexStore {
 	}
 
 	public void close() {
-		try {
-			if (!handle.equals(MemorySegment.NULL))
-				DbiNative.dbi_destroy.invoke(handle);
-		} catch (final Throwable ignored) {
-		}
+		for (final MemorySegment h : handles)
+			try {
+				if (h != null && !h.equals(MemorySegment.NULL))
+					DbiNative.dbi_destroy.invoke(h);
+			} catch (final Throwable ignored) {
+			}
+		handles = new MemorySegment[0];
 		handle = MemorySegment.NULL;
 		arena.close();
 	}
