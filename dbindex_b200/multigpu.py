@@ -247,7 +247,7 @@ def build_sharded(engine: ShardEngine, shard_sizes=None) -> dict:
     # ---- the proteome: own shard over PCIe (already added), the other shards over NVLink
     np_, nr_ = engine.shard_info()
     if shard_sizes is None:
-        sizes = _all_gather_bytes(np.array([np_, nr_], dtype=np.uint64).view(np.uint8), dev).view(np.uint64).reshape(world, 2)
+        sizes = _all_gather_bytes(np.array([np_, nr_], dtype=np.uint64).view(np.uint8), dev).copy().view(np.uint64).reshape(world, 2)
     else:
         sizes = np.ascontiguousarray(shard_sizes, dtype=np.uint64).reshape(world, 2)
         assert (int(sizes[rank, 0]), int(sizes[rank, 1])) == (np_, nr_), "shard_sizes disagree with the shard this rank added"
@@ -345,7 +345,7 @@ def build_sharded(engine: ShardEngine, shard_sizes=None) -> dict:
     engine.index_base()
     lap("index_base")
     if not engine.has_mods:
-        ru = _all_gather_bytes(np.array([engine.n_unique()], dtype=np.uint64).view(np.uint8), dev).view(np.uint64).reshape(world)
+        ru = _all_gather_bytes(np.array([engine.n_unique()], dtype=np.uint64).view(np.uint8), dev).copy().view(np.uint64).reshape(world)
         engine.set_unique(ru)
         engine.finish()
         _barrier(dev)
