@@ -177,3 +177,32 @@ def test_plan_matrix_equals_per_rank_plans():
             s2, send, recv = plan_exchange(world, hg, hists[r], 42, 600.0, stage=0, has_mods=True, n_slices=fold * world)
             assert s2.tolist() == split.tolist()
             assert send.tolist() == matrix[r].tolist() and recv.tolist() == matrix.sum(axis=0).tolist()
+
+
+def test_planner_degenerate_histograms():
+    """dbi_mg_plan / dbi_mg_plan_matrix on inputs a build can produce at the edges: nothing at all, everything in
+    one bin, items only in the last bin, more ranks than occupied bins -- cuts stay ascending and inside the bin
+    range, counts are conserved, nothing divides by zero."""
+    from dbindex_b200.multigpu import plan_matrix
+    B = MG_BINS
+    cases = {
+        "empty": np.zeros(3 * B, np.uint64),
+        "one_bin": np.concatenate([np.eye(1, B, 1234, dtype=np.uint64)[0] * np.uint64(10 ** 6)] * 3),
+        "last_bin": np.concatenate([np.eye(1, B, B - 1, dtype=np.uint64)[0] * np.uint64(7)] * 3),
+        "three_bins": np.concatenate([(np.eye(1, B, 5, dtype=np.uint64)[0] + np.eye(1, B, 2000, dtype=np.uint64)[0] +
+                                       np.eye(1, B, 4000, dtype=np.uint64)[0]) * np.uint64(100)] * 3),
+    }
+    for name, hg in cases.items():
+        for world in (1, 2, 8, 16):
+            for fold in (1, 2):
+                if world == 1 and fold == 2:
+                    continue
+                for cost in ([0.0, 0.0, 1.0, 0.0], [400.0, 125.0, 17.5, 20.0], [1.0, 0.0, 0.0, 0.0]):
+                    split, send, recv = plan_exchange(world, hg, hg, 42, 600.0, cost=cost, n_slices=fold * world)
+                    assert len(split) == fold * world - 1 and np.all(np.diff(split.astype(np.int64)) >= 0), (name, world, fold)
+                    assert np.all(split <= B)
+                    assert int(send.sum()) == int(hg[B:2 * B].sum()) == int(recv.sum()), (name, world, fold)
+                    s2, matrix = plan_matrix(world, np.stack([hg] + [np.zeros_like(hg)] * (world - 1)), 42, 600.0, cost=cost,
+                                             n_slices=fold * world)
+                    assert s2.tolist() == split.tolist() and matrix[0].tolist() == send.tolist()
+                    assert int(matrix[1:].sum()) == 0
